@@ -1,0 +1,842 @@
+/*
+ * lk_oracle.c — TEST INFRASTRUCTURE ONLY.  CPU restatement (plain C, scalar, V=1 layout) of the
+ * reference's reversible-model likelihood kernel, IQ-TREE 2.4.0 tree/phylokernelnew.h.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+ * load this library.  The product path (iqtree2_b200/csrc, libb200lk.so) never links or calls it.
+ *
+ * Pinning status: the reference ships NO golden vectors / known-answer tests for this path
+ * (SURVEY §4, §8c).  This restatement is pinned (a) against an independent brute-force Felsenstein
+ * pruning with P(t)=expm(Qrt) (tests/test_oracle.py, "Route C") and (b) against the REAL reference
+ * kernel templates compiled from /root/reference into oracle/_ref (oracle/build_ref.sh, "Route A")
+ * when that build is available; see DESIGN.md §Oracle for which of the two held at commit time.
+ *
+ * Each function cites the reference file:line it follows.  All paths are relative to /root/reference.
+ * Summation orders follow the reference helper templates (phylokernelnew.h:82-842) lane-for-lane, so
+ * oracle-vs-reference noise is at the last-ulp level; the product is only required to agree to 1e-11
+ * relative per pattern (BASELINE.json north_star) and bit-exactly on scale_num.
+ *
+ * Buffer layouts are the reference's with SIMD width V=1 (SURVEY §8a "Layout crib"):
+ *   partial_lh / theta : [p*B + c*n + i]           B = n*ncat_mix
+ *   scale_num NORM_LH  : [p]   (uint16)            SAFE_LH: [p*C + c]
+ *   echildren          : [c*n*n + x*n + i]         partial_lh_leaves: [state*B + c*n + x]
+ *   tip_partial_lh     : [state*nmix*n + m*n + i]
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* tree/phylotree.h:74-80 */
+#define SCALING_THRESHOLD 8.636168555094444625386e-78
+#define SCALING_THRESHOLD_EXP 256
+#define LOG_SCALING_THRESHOLD (-177.4456782233459932741)
+
+typedef struct {
+    int32_t nstates, ncat, nmix, fused_mix_rate, safe_numeric;
+    int32_t seq_type;      /* 0 generic, 1 DNA, 2 protein */
+    int32_t state_unknown; /* aln->STATE_UNKNOWN */
+    int32_t ntaxa;
+    int64_t nptn;
+    int32_t nslots;
+    int32_t device; /* unused here; keeps the struct identical to b200lk_config */
+} orc_config;
+
+typedef struct { int32_t kind; int32_t id; double length; } orc_child; /* kind 0 = tip (id = taxon), 1 = slot */
+typedef struct { int32_t dst_slot; int32_t pad_; orc_child left, right; } orc_op;
+
+typedef struct {
+    orc_config cfg;
+    int C, B, denom;
+    uint8_t *tips;    /* [ntaxa][nptn] */
+    double *ptn_freq, *ptn_invar;
+    double *eval, *evec, *inv_evec, *mix_weight, *cat_rate, *cat_prop;
+    double *tip_partial_lh; /* [(SU+1)][nmix][n] */
+    double *partial;        /* [nslots][nptn*B] */
+    uint16_t *scale;        /* [nslots][nptn*S] */
+    double *theta, *buffer_scale_all, *pattern_lh, *pattern_lh_cat, *pattern_scaling;
+    int theta_computed;
+    /* end points of the branch the theta buffer was built for are irrelevant after the build */
+    char err[256];
+} orc_engine;
+
+static size_t S_of(const orc_engine *e) { return e->cfg.safe_numeric ? (size_t)e->C : 1; }
+
+/* ---------------------------------------------------------------------------------------------
+ * helper dot products — phylokernelnew.h:82-842 (scalar lanes of the VectorClass templates)
+ * ------------------------------------------------------------------------------------------- */
+
+/* dotProductVec, JAMES_VERSION branch — phylokernelnew.h:89-126 */
+static inline double dot_vec(const double *A, const double *B, size_t N) {
+    if (N == 4) return (A[0] * B[0] + A[1] * B[1]) + (A[2] * B[2] + A[3] * B[3]);
+    size_t cruft = N & 3;
+    if (N == cruft) {
+        double X = 0;
+        for (size_t i = 0; i < cruft; i++) X = fma(A[i], B[i], X);
+        return X;
+    }
+    double X = A[0] * B[0], v1 = A[1] * B[1], v2 = A[2] * B[2], v3 = A[3] * B[3];
+    size_t stop = N - cruft, k = 4;
+    for (; k < stop; k += 4) {
+        X = fma(A[k], B[k], X);
+        v1 = fma(A[k + 1], B[k + 1], v1);
+        v2 = fma(A[k + 2], B[k + 2], v2);
+        v3 = fma(A[k + 3], B[k + 3], v3);
+    }
+    if (cruft > 0) {
+        X = fma(A[k], B[k], X);
+        if (cruft > 1) {
+            v1 = fma(A[k + 1], B[k + 1], v1);
+            if (cruft > 2) v2 = fma(A[k + 2], B[k + 2], v2);
+        }
+    }
+    return (X + v1) + (v2 + v3);
+}
+
+/* dotProductDualVec — phylokernelnew.h:214-314 : (A.B)*(C.D) */
+static inline double dot_dual(const double *A, const double *B, const double *C, const double *D, size_t N) {
+    switch (N) {
+    case 1: return (A[0] * B[0]) * (C[0] * D[0]);
+    case 2: return fma(A[1], B[1], A[0] * B[0]) * fma(C[1], D[1], C[0] * D[0]);
+    case 3: return fma(A[2], B[2], fma(A[1], B[1], A[0] * B[0])) * fma(C[2], D[2], fma(C[1], D[1], C[0] * D[0]));
+    case 4: return (fma(A[1], B[1], A[0] * B[0]) + fma(A[3], B[3], A[2] * B[2])) *
+                   (fma(C[1], D[1], C[0] * D[0]) + fma(C[3], D[3], C[2] * D[2]));
+    default: break;
+    }
+    size_t i, j;
+    switch (N % 4) {
+    case 0: {
+        double AB[4], CD[4];
+        for (j = 0; j < 4; j++) { AB[j] = A[j] * B[j]; CD[j] = C[j] * D[j]; }
+        for (i = 4; i < N; i += 4)
+            for (j = 0; j < 4; j++) { AB[j] = fma(A[i + j], B[i + j], AB[j]); CD[j] = fma(C[i + j], D[i + j], CD[j]); }
+        return ((AB[0] + AB[1]) + (AB[2] + AB[3])) * ((CD[0] + CD[1]) + CD[2] + CD[3]);
+    }
+    case 1: {
+        size_t Nm1 = N - 1;
+        double AB[4], CD[4];
+        for (j = 0; j < 4; j++) { AB[j] = A[j] * B[j]; CD[j] = C[j] * D[j]; }
+        for (i = 4; i < Nm1; i += 4)
+            for (j = 0; j < 4; j++) { AB[j] = fma(A[i + j], B[i + j], AB[j]); CD[j] = fma(C[i + j], D[i + j], CD[j]); }
+        return fma(A[Nm1], B[Nm1], (AB[0] + AB[1]) + (AB[2] + AB[3])) * fma(C[Nm1], D[Nm1], (CD[0] + CD[1]) + CD[2] + CD[3]);
+    }
+    case 2: {
+        double AB[2], CD[2];
+        for (j = 0; j < 2; j++) { AB[j] = A[j] * B[j]; CD[j] = C[j] * D[j]; }
+        for (i = 2; i < N; i += 2)
+            for (j = 0; j < 2; j++) { AB[j] = fma(A[i + j], B[i + j], AB[j]); CD[j] = fma(C[i + j], D[i + j], CD[j]); }
+        return (AB[0] + AB[1]) * (CD[0] + CD[1]);
+    }
+    default: {
+        double AB[2], CD[2];
+        for (j = 0; j < 2; j++) { AB[j] = A[j] * B[j]; CD[j] = C[j] * D[j]; }
+        for (i = 2; i < N - 1; i += 2)
+            for (j = 0; j < 2; j++) { AB[j] = fma(A[i + j], B[i + j], AB[j]); CD[j] = fma(C[i + j], D[i + j], CD[j]); }
+        AB[0] = fma(A[N - 1], B[N - 1], AB[0] + AB[1]);
+        CD[0] = fma(C[N - 1], D[N - 1], CD[0] + CD[1]);
+        return AB[0] * CD[0];
+    }
+    }
+}
+
+/* one row of productVecMat — phylokernelnew.h:326-567: X[i] = sum_x A[x]*M[i*N+x] */
+static inline double pvm_row(const double *A, const double *M, size_t N) {
+    size_t x, j;
+    if (N == 4) return fma(A[1], M[1], A[0] * M[0]) + fma(A[3], M[3], A[2] * M[2]);
+    switch (N) {
+    case 1: return A[0] * M[0];
+    case 2: return fma(A[1], M[1], A[0] * M[0]);
+    case 3: return fma(A[2], M[2], fma(A[1], M[1], A[0] * M[0]));
+    default: break;
+    }
+    switch (N % 4) {
+    case 0: {
+        double V[4];
+        for (j = 0; j < 4; j++) V[j] = A[j] * M[j];
+        for (x = 4; x < N; x += 4)
+            for (j = 0; j < 4; j++) V[j] = fma(A[x + j], M[x + j], V[j]);
+        return (V[0] + V[1]) + (V[2] + V[3]);
+    }
+    case 1: {
+        size_t Nm1 = N - 1;
+        double V[4];
+        for (j = 0; j < 4; j++) V[j] = A[j] * M[j];
+        for (x = 4; x < Nm1; x += 4)
+            for (j = 0; j < 4; j++) V[j] = fma(A[x + j], M[x + j], V[j]);
+        return fma(A[Nm1], M[Nm1], (V[0] + V[1]) + (V[2] + V[3]));
+    }
+    case 2: {
+        double V[2];
+        for (j = 0; j < 2; j++) V[j] = A[j] * M[j];
+        for (x = 2; x < N; x += 2)
+            for (j = 0; j < 2; j++) V[j] = fma(A[x + j], M[x + j], V[j]);
+        return V[0] + V[1];
+    }
+    default: {
+        double V[2];
+        for (j = 0; j < 2; j++) V[j] = A[j] * M[j];
+        for (x = 2; x < N - 1; x += 2)
+            for (j = 0; j < 2; j++) V[j] = fma(A[x + j], M[x + j], V[j]);
+        return fma(A[N - 1], M[N - 1], V[0] + V[1]);
+    }
+    }
+}
+
+/* productVecMat with Xmax — phylokernelnew.h:450-567 */
+static inline void prod_vec_mat(const double *A, const double *M, double *X, double *Xmax, size_t N) {
+    for (size_t i = 0; i < N; i++) {
+        X[i] = pvm_row(A, M + i * N, N);
+        if (Xmax) { double a = fabs(X[i]); if (a > *Xmax) *Xmax = a; }
+    }
+}
+
+/* dotProduct3Vec — phylokernelnew.h:737-793 : sum A*B*C */
+static inline double dot3(const double *A, const double *B, const double *C, size_t N) {
+    size_t i, j;
+    switch (N % 4) {
+    case 0: {
+        double V[4];
+        for (j = 0; j < 4; j++) V[j] = A[j] * B[j] * C[j];
+        for (i = 4; i < N; i += 4)
+            for (j = 0; j < 4; j++) V[j] = fma(A[i + j] * B[i + j], C[i + j], V[j]);
+        return (V[0] + V[1]) + (V[2] + V[3]);
+    }
+    case 1: {
+        double V[4];
+        size_t Nm1 = N - 1;
+        for (j = 0; j < 4; j++) V[j] = A[j] * B[j] * C[j];
+        for (i = 4; i < Nm1; i += 4)
+            for (j = 0; j < 4; j++) V[j] = fma(A[i + j] * B[i + j], C[i + j], V[j]);
+        return fma(A[Nm1] * B[Nm1], C[Nm1], (V[0] + V[1]) + (V[2] + V[3]));
+    }
+    case 2: {
+        double V[2];
+        for (j = 0; j < 2; j++) V[j] = A[j] * B[j] * C[j];
+        for (i = 2; i < N; i += 2)
+            for (j = 0; j < 2; j++) V[j] = fma(A[i + j] * B[i + j], C[i + j], V[j]);
+        return V[0] + V[1];
+    }
+    default: {
+        double V[2];
+        for (j = 0; j < 2; j++) V[j] = A[j] * B[j] * C[j];
+        for (i = 2; i < N - 1; i += 2)
+            for (j = 0; j < 2; j++) V[j] = fma(A[i + j] * B[i + j], C[i + j], V[j]);
+        return fma(A[N - 1] * B[N - 1], C[N - 1], V[0] + V[1]);
+    }
+    }
+}
+
+/* dotProductTriple<ADD=false> — phylokernelnew.h:666-725.  NOTE: for odd nstates the reference loop
+ * `for (i = 2; i < N-1; i += 2)` with an EVEN total N (= block) visits index N-1 inside the loop and again in
+ * the trailing mul_add, double-counting the last element; this restatement sums every element exactly once
+ * (the intended mathematics) and DESIGN.md lists the discrepancy. For even nstates and for odd N it is
+ * lane-for-lane identical to the reference. */
+static inline void dot_triple(const double *A, const double *B, const double *C, const double *D, size_t N,
+                              double *X, double *Y, double *Z) {
+    double AD[2], BD[2], CD[2];
+    size_t i, j;
+    for (j = 0; j < 2; j++) { AD[j] = A[j] * D[j]; BD[j] = B[j] * D[j]; CD[j] = C[j] * D[j]; }
+    size_t stop = N - (N & 1);
+    for (i = 2; i < stop; i += 2)
+        for (j = 0; j < 2; j++) {
+            AD[j] = fma(A[i + j], D[i + j], AD[j]);
+            BD[j] = fma(B[i + j], D[i + j], BD[j]);
+            CD[j] = fma(C[i + j], D[i + j], CD[j]);
+        }
+    if ((N & 1) == 0) {
+        *X = AD[0] + AD[1]; *Y = BD[0] + BD[1]; *Z = CD[0] + CD[1];
+    } else {
+        *X = fma(A[N - 1], D[N - 1], AD[0] + AD[1]);
+        *Y = fma(B[N - 1], D[N - 1], BD[0] + BD[1]);
+        *Z = fma(C[N - 1], D[N - 1], CD[0] + CD[1]);
+    }
+}
+
+/* sumVec<append=true> — phylokernelnew.h:43-69 */
+static inline double sum_vec_append(const double *A, double X, size_t N) {
+    size_t cruft = N & 3;
+    if (cruft < N) {
+        double V[4] = {0, 0, 0, 0};
+        size_t k = 0;
+        for (; k < N - cruft; k += 4) { V[0] += A[k]; V[1] += A[k + 1]; V[2] += A[k + 2]; V[3] += A[k + 3]; }
+        V[0] += V[2]; V[1] += V[3]; V[0] += V[1];
+        X += V[0];
+        if (cruft == 0) return X;
+        A += k;
+    }
+    for (size_t k = 0; k < cruft; k++) X += A[k];
+    return X;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * engine life-cycle
+ * ------------------------------------------------------------------------------------------- */
+orc_engine *orc_create(const orc_config *cfg) {
+    orc_engine *e = (orc_engine *)calloc(1, sizeof(orc_engine));
+    e->cfg = *cfg;
+    int n = cfg->nstates;
+    e->C = cfg->fused_mix_rate ? cfg->ncat : cfg->ncat * cfg->nmix; /* phylokernelnew.h:1322-1323 */
+    e->denom = cfg->fused_mix_rate ? 1 : cfg->ncat;                 /* :1325 */
+    e->B = n * e->C;
+    size_t P = (size_t)cfg->nptn;
+    e->tips = (uint8_t *)calloc((size_t)cfg->ntaxa * P + 1, 1);
+    e->ptn_freq = (double *)calloc(P + 1, sizeof(double));
+    e->ptn_invar = (double *)calloc(P + 1, sizeof(double));
+    e->eval = (double *)calloc((size_t)cfg->nmix * n, sizeof(double));
+    e->evec = (double *)calloc((size_t)cfg->nmix * n * n, sizeof(double));
+    e->inv_evec = (double *)calloc((size_t)cfg->nmix * n * n, sizeof(double));
+    e->mix_weight = (double *)calloc(cfg->nmix, sizeof(double));
+    e->cat_rate = (double *)calloc(cfg->ncat, sizeof(double));
+    e->cat_prop = (double *)calloc(cfg->ncat, sizeof(double));
+    e->tip_partial_lh = (double *)calloc((size_t)(cfg->state_unknown + 1) * cfg->nmix * n, sizeof(double));
+    e->partial = (double *)calloc((size_t)cfg->nslots * P * e->B + 1, sizeof(double));
+    e->scale = (uint16_t *)calloc((size_t)cfg->nslots * P * S_of(e) + 1, sizeof(uint16_t));
+    e->theta = (double *)calloc(P * e->B + 1, sizeof(double));
+    e->buffer_scale_all = (double *)calloc(P + 1, sizeof(double));
+    e->pattern_lh = (double *)calloc(P + 1, sizeof(double));
+    e->pattern_scaling = (double *)calloc(P + 1, sizeof(double));
+    e->pattern_lh_cat = (double *)calloc(P * e->C + 1, sizeof(double));
+    if (!e->partial || !e->scale || !e->theta) { free(e); return NULL; }
+    return e;
+}
+
+void orc_destroy(orc_engine *e) {
+    if (!e) return;
+    free(e->tips); free(e->ptn_freq); free(e->ptn_invar); free(e->eval); free(e->evec); free(e->inv_evec);
+    free(e->mix_weight); free(e->cat_rate); free(e->cat_prop); free(e->tip_partial_lh); free(e->partial);
+    free(e->scale); free(e->theta); free(e->buffer_scale_all); free(e->pattern_lh); free(e->pattern_scaling);
+    free(e->pattern_lh_cat); free(e);
+}
+
+const char *orc_last_error(orc_engine *e) { return e->err; }
+
+int orc_set_tip_states(orc_engine *e, const uint8_t *states) {
+    memcpy(e->tips, states, (size_t)e->cfg.ntaxa * e->cfg.nptn);
+    return 0;
+}
+int orc_set_pattern_freq(orc_engine *e, const double *f) { memcpy(e->ptn_freq, f, sizeof(double) * e->cfg.nptn); return 0; }
+int orc_set_pattern_invar(orc_engine *e, const double *f) { memcpy(e->ptn_invar, f, sizeof(double) * e->cfg.nptn); return 0; }
+int orc_set_rates(orc_engine *e, const double *rate, const double *prop) {
+    memcpy(e->cat_rate, rate, sizeof(double) * e->cfg.ncat);
+    memcpy(e->cat_prop, prop, sizeof(double) * e->cfg.ncat);
+    return 0;
+}
+
+/* 0/1 tip likelihood of state — model/modelsubst.cpp:197-207, modeldna.cpp:462-475, modelprotein.cpp:1149-1166 */
+static void tip_indicator(const orc_engine *e, int state, double *lk) {
+    int n = e->cfg.nstates;
+    if (state < n) {
+        memset(lk, 0, sizeof(double) * n);
+        lk[state] = 1.0;
+    } else if (e->cfg.seq_type == 1 && state < 18) {
+        memset(lk, 0, sizeof(double) * n);
+        int cstate = state - n + 1;
+        for (int i = 0; i < n; i++) if (cstate & (1 << i)) lk[i] = 1.0;
+    } else if (e->cfg.seq_type == 2 && state < n + 3) {
+        static const int ambi_aa[] = {2, 3, 5, 6, 9, 10};
+        memset(lk, 0, sizeof(double) * n);
+        int cstate = state - n;
+        lk[ambi_aa[cstate * 2]] = 1.0;
+        lk[ambi_aa[cstate * 2 + 1]] = 1.0;
+    } else {
+        for (int i = 0; i < n; i++) lk[i] = 1.0;
+    }
+}
+
+/* computeTipPartialLikelihood — tree/phylotreesse.cpp:367-375 + ModelSubst::multiplyWithInvEigenvector
+ * (model/modelsubst.cpp:182-195) */
+int orc_set_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec, const double *mix_weight) {
+    int n = e->cfg.nstates, nmix = e->cfg.nmix;
+    memcpy(e->eval, eval, sizeof(double) * nmix * n);
+    memcpy(e->evec, evec, sizeof(double) * nmix * n * n);
+    memcpy(e->inv_evec, inv_evec, sizeof(double) * nmix * n * n);
+    memcpy(e->mix_weight, mix_weight, sizeof(double) * nmix);
+    double *saved = (double *)malloc(sizeof(double) * n);
+    for (int state = 0; state <= e->cfg.state_unknown; state++) {
+        double *lk = e->tip_partial_lh + (size_t)state * nmix * n;
+        tip_indicator(e, state, saved);
+        for (int m = 0; m < nmix; m++) {
+            const double *iv = e->inv_evec + (size_t)m * n * n;
+            for (int i = 0; i < n; i++) {
+                double acc = 0.0;
+                for (int j = 0; j < n; j++) acc += iv[i * n + j] * saved[j];
+                lk[m * n + i] = acc;
+            }
+        }
+    }
+    free(saved);
+    e->theta_computed = 0;
+    return 0;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * computePartialInfo — phylokernelnew.h:900-1110 (reversible branch)
+ * ------------------------------------------------------------------------------------------- */
+static void partial_info_child(const orc_engine *e, const orc_child *ch, double *echild, double *leaf /* or NULL */) {
+    int n = e->cfg.nstates, C = e->C, B = e->B, nmix = e->cfg.nmix, ncat = e->cfg.ncat;
+    int tip_block = n * nmix;
+    double *expchild = (double *)malloc(sizeof(double) * n);
+    for (int c = 0; c < C; c++) {
+        int m = c / e->denom, r = c % ncat;
+        double len_child = e->cat_rate[r] * ch->length; /* :1017 */
+        const double *eval_ptr = e->eval + (size_t)m * n;
+        const double *evec_ptr = e->evec + (size_t)m * n * n;
+        for (int i = 0; i < n; i++) expchild[i] = exp(eval_ptr[i] * len_child); /* :1022 / :1073 */
+        for (int x = 0; x < n; x++)
+            for (int i = 0; i < n; i++)
+                echild[(size_t)c * n * n + x * n + i] = evec_ptr[x * n + i] * expchild[i]; /* :1027 / :1077 */
+    }
+    free(expchild);
+    if (!leaf) return;
+    int su = e->cfg.state_unknown;
+    for (int state = 0; state <= su; state++) {
+        for (int c = 0; c < C; c++) {
+            int m = c / e->denom;
+            const double *tip = e->tip_partial_lh + (size_t)state * tip_block + m * n;
+            for (int x = 0; x < n; x++) {
+                const double *ep = echild + (size_t)c * n * n + x * n;
+                double v;
+                if (n % 4 == 0) {
+                    /* vectorised (Vec4d) branch :1036-1051: lane accumulators then horizontal_add */
+                    double a0 = ep[0] * tip[0], a1 = ep[1] * tip[1], a2 = ep[2] * tip[2], a3 = ep[3] * tip[3];
+                    for (int i = 4; i < n; i += 4) {
+                        a0 = fma(ep[i], tip[i], a0); a1 = fma(ep[i + 1], tip[i + 1], a1);
+                        a2 = fma(ep[i + 2], tip[i + 2], a2); a3 = fma(ep[i + 3], tip[i + 3], a3);
+                    }
+                    v = (a0 + a1) + (a2 + a3);
+                } else {
+                    /* non-vectorised branch :1085-1099 */
+                    v = ep[0] * tip[0];
+                    for (int i = 1; i < n; i++) v += ep[i] * tip[i];
+                }
+                leaf[(size_t)state * B + c * n + x] = v;
+            }
+        }
+    }
+    for (int x = 0; x < B; x++) leaf[(size_t)su * B + x] = 1.0; /* :1052-1055 */
+}
+
+static inline int tip_state(const orc_engine *e, int taxon, size_t p) { return e->tips[(size_t)taxon * e->cfg.nptn + p]; }
+
+/* ---------------------------------------------------------------------------------------------
+ * computePartialLikelihood(Generic)SIMD — phylokernelnew.h:1289-2039 (binary nodes, normal models)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    orc_op op;            /* after the leaf swap: a single leaf child is `left` (:1395-1405) */
+    double *echildren;    /* owns eleft+eright */
+    double *leaves;       /* owns leaf tables */
+    double *eleft, *eright, *leafL, *leafR;
+} orc_opinfo;
+
+/* per-op precompute = computePartialInfo for one TraversalInfo (:1243-1260) */
+static void opinfo_init(const orc_engine *e, const orc_op *op_in, orc_opinfo *oi) {
+    int n = e->cfg.nstates, B = e->B;
+    oi->op = *op_in;
+    size_t info_sz = (size_t)B * n;
+    oi->echildren = (double *)malloc(sizeof(double) * 2 * info_sz);
+    size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * B;
+    oi->leaves = (double *)malloc(sizeof(double) * 2 * leaf_sz);
+    /* echildren in neighbour order; partial_lh_leaves only for leaf children, in neighbour order (:1012-1058) */
+    double *leaf_ptr = oi->leaves;
+    oi->leafL = oi->leafR = NULL;
+    if (oi->op.left.kind == 0) { oi->leafL = leaf_ptr; leaf_ptr += leaf_sz; }
+    if (oi->op.right.kind == 0) { oi->leafR = leaf_ptr; leaf_ptr += leaf_sz; }
+    partial_info_child(e, &oi->op.left, oi->echildren, oi->leafL);
+    partial_info_child(e, &oi->op.right, oi->echildren + info_sz, oi->leafR);
+    oi->eleft = oi->echildren;
+    oi->eright = oi->echildren + info_sz;
+    if (oi->op.left.kind != 0 && oi->op.right.kind == 0) {
+        orc_child t = oi->op.left; oi->op.left = oi->op.right; oi->op.right = t;
+        double *et = oi->eleft; oi->eleft = oi->eright; oi->eright = et;
+        oi->leafL = oi->leafR; oi->leafR = NULL;
+    }
+}
+static void opinfo_free(orc_opinfo *oi) { free(oi->echildren); free(oi->leaves); }
+
+#define ORC_MAX_STATES 256
+
+/* one TraversalInfo over the pattern range [lo, hi) — the body of computePartialLikelihood(info, lo, hi, packet) */
+static void compute_partial_range(orc_engine *e, const orc_opinfo *oi, size_t lo, size_t hi) {
+    int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric;
+    size_t P = (size_t)e->cfg.nptn, S = S_of(e);
+    const orc_op *op = &oi->op;
+    double *dad_lh = e->partial + (size_t)op->dst_slot * P * B;
+    uint16_t *dad_sc = e->scale + (size_t)op->dst_slot * P * S;
+    double tmpv[ORC_MAX_STATES];
+
+    if (op->left.kind == 0 && op->right.kind == 0) {
+        /* TIP-TIP :1632-1746 — scale_num zeroed, never rescaled */
+        memset(dad_sc + lo * S, 0, sizeof(uint16_t) * (hi - lo) * S);
+        for (size_t p = lo; p < hi; p++) {
+            const double *vl = oi->leafL + (size_t)tip_state(e, op->left.id, p) * B;
+            const double *vr = oi->leafR + (size_t)tip_state(e, op->right.id, p) * B;
+            double *out = dad_lh + p * B;
+            for (int c = 0; c < C; c++) {
+                const double *inv = e->inv_evec + (size_t)(c / e->denom) * n * n;
+                for (int x = 0; x < n; x++) tmpv[x] = vl[c * n + x] * vr[c * n + x];
+                prod_vec_mat(tmpv, inv, out + c * n, NULL, n);
+            }
+        }
+    } else if (op->left.kind == 0) {
+        /* TIP-INNER :1748-1905 */
+        const double *right_lh = e->partial + (size_t)op->right.id * P * B;
+        const uint16_t *right_sc = e->scale + (size_t)op->right.id * P * S;
+        memcpy(dad_sc + lo * S, right_sc + lo * S, sizeof(uint16_t) * (hi - lo) * S);
+        for (size_t p = lo; p < hi; p++) {
+            const double *vl = oi->leafL + (size_t)tip_state(e, op->left.id, p) * B;
+            const double *pr = right_lh + p * B;
+            double *out = dad_lh + p * B;
+            double lh_max = 0.0;
+            for (int c = 0; c < C; c++) {
+                if (safe) lh_max = 0.0;
+                const double *inv = e->inv_evec + (size_t)(c / e->denom) * n * n;
+                const double *er = oi->eright + (size_t)c * n * n;
+                for (int x = 0; x < n; x++) {
+                    double vright = dot_vec(er + x * n, pr + c * n, n);
+                    tmpv[x] = vl[c * n + x] * vright;
+                }
+                prod_vec_mat(tmpv, inv, out + c * n, &lh_max, n);
+                if (safe && lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                    for (int i = 0; i < n; i++) out[c * n + i] = ldexp(out[c * n + i], SCALING_THRESHOLD_EXP);
+                    dad_sc[p * C + c] += 1;
+                }
+            }
+            if (!safe && lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                for (int i = 0; i < B; i++) out[i] = ldexp(out[i], SCALING_THRESHOLD_EXP);
+                dad_sc[p] += 1;
+            }
+        }
+    } else {
+        /* INNER-INNER :1907-2032 */
+        const double *left_lh = e->partial + (size_t)op->left.id * P * B;
+        const double *right_lh = e->partial + (size_t)op->right.id * P * B;
+        const uint16_t *left_sc = e->scale + (size_t)op->left.id * P * S;
+        const uint16_t *right_sc = e->scale + (size_t)op->right.id * P * S;
+        for (size_t p = lo; p < hi; p++) {
+            const double *pl = left_lh + p * B, *pr = right_lh + p * B;
+            double *out = dad_lh + p * B;
+            double lh_max = 0.0;
+            if (!safe) dad_sc[p] = (uint16_t)(left_sc[p] + right_sc[p]);
+            for (int c = 0; c < C; c++) {
+                if (safe) { lh_max = 0.0; dad_sc[p * C + c] = (uint16_t)(left_sc[p * C + c] + right_sc[p * C + c]); }
+                const double *inv = e->inv_evec + (size_t)(c / e->denom) * n * n;
+                const double *el = oi->eleft + (size_t)c * n * n, *er = oi->eright + (size_t)c * n * n;
+                for (int x = 0; x < n; x++) tmpv[x] = dot_dual(el + x * n, pl + c * n, er + x * n, pr + c * n, n);
+                prod_vec_mat(tmpv, inv, out + c * n, &lh_max, n);
+                if (safe && lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                    for (int i = 0; i < n; i++) out[c * n + i] = ldexp(out[c * n + i], SCALING_THRESHOLD_EXP);
+                    dad_sc[p * C + c] += 1;
+                }
+            }
+            if (!safe && lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                for (int i = 0; i < B; i++) out[i] = ldexp(out[i], SCALING_THRESHOLD_EXP);
+                dad_sc[p] += 1;
+            }
+        }
+    }
+}
+
+/* The reference walks the WHOLE traversal list per pattern packet (phylokernelnew.h:1270-1277, 2087-2089,
+ * 2821-2824): packets are independent pattern ranges, so children written by a packet are still cache-hot
+ * when the same packet computes their parent.  Same structure here (packet = ORC_PACKET patterns). */
+#define ORC_PACKET 512
+int orc_update_partials(orc_engine *e, const orc_op *ops, int nops) {
+    if (nops <= 0) return 0;
+    if (e->cfg.nstates > ORC_MAX_STATES) { snprintf(e->err, sizeof e->err, "nstates > %d", ORC_MAX_STATES); return -1; }
+    orc_opinfo *info = (orc_opinfo *)malloc(sizeof(orc_opinfo) * nops);
+#pragma omp parallel for schedule(static) if (nops >= 3)
+    for (int k = 0; k < nops; k++) opinfo_init(e, &ops[k], &info[k]);
+    size_t P = (size_t)e->cfg.nptn;
+    long npacket = (long)((P + ORC_PACKET - 1) / ORC_PACKET);
+#pragma omp parallel for schedule(dynamic, 1)
+    for (long pk = 0; pk < npacket; pk++) {
+        size_t lo = (size_t)pk * ORC_PACKET, hi = lo + ORC_PACKET;
+        if (hi > P) hi = P;
+        for (int k = 0; k < nops; k++) compute_partial_range(e, &info[k], lo, hi);
+    }
+    for (int k = 0; k < nops; k++) opinfo_free(&info[k]);
+    free(info);
+    return 0;
+}
+
+/* val[c][i] = exp(eval_i * rate_c * len) * prop_c * weight_m — phylokernelnew.h:2714-2745 ;
+ * with derivatives :2322-2358 */
+static void compute_vals(const orc_engine *e, double len_branch, double *val0, double *val1, double *val2) {
+    int n = e->cfg.nstates, C = e->C, ncat = e->cfg.ncat;
+    for (int c = 0; c < C; c++) {
+        int m = c / e->denom, r = c % ncat;
+        double prop = e->cat_prop[r] * e->mix_weight[m];
+        const double *eval_ptr = e->eval + (size_t)m * n;
+        if (val1) {
+            double myrate = e->cat_rate[r];
+            for (int i = 0; i < n; i++) {
+                double cof = eval_ptr[i] * myrate;
+                double val = exp(cof * len_branch) * prop;
+                double v1 = cof * val;
+                val0[c * n + i] = val; val1[c * n + i] = v1; val2[c * n + i] = cof * v1;
+            }
+        } else {
+            double len = e->cat_rate[r] * len_branch;
+            for (int i = 0; i < n; i++) val0[c * n + i] = exp(eval_ptr[i] * len) * prop;
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * computeLikelihoodBranch(Generic)SIMD — phylokernelnew.h:2641-3223 (no +ASC, no robust-phylo)
+ *   node end must be a slot; dad end is a tip (dad_kind 0) or a slot (dad_kind 1).
+ * ------------------------------------------------------------------------------------------- */
+int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
+                    double length, int save_log_value, double *logl_out) {
+    orc_update_partials(e, ops, nops);
+    int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric, nmix = e->cfg.nmix;
+    size_t P = (size_t)e->cfg.nptn, S = S_of(e);
+    double *val = (double *)malloc(sizeof(double) * B);
+    compute_vals(e, length, val, NULL, NULL);
+    /* naming follows the reference after its leaf swap: dad_branch->partial_lh is the slot side */
+    const double *dad_lh = e->partial + (size_t)node_slot * P * B;
+    const uint16_t *dad_sc = e->scale + (size_t)node_slot * P * S;
+    double tree_lh = 0.0;
+    if (dad_kind == 0) {
+        /* TIP-INNER :2753-2965 : partial_lh_node[state][c][i] = val[c][i]*tip_partial_lh[state][m][i] */
+        int su = e->cfg.state_unknown;
+        double *plnode = (double *)malloc(sizeof(double) * (su + 1) * B);
+        for (int state = 0; state <= su; state++)
+            for (int c = 0; c < C; c++) {
+                int m = c / e->denom;
+                for (int i = 0; i < n; i++)
+                    plnode[(size_t)state * B + c * n + i] = val[c * n + i] * e->tip_partial_lh[(size_t)state * nmix * n + m * n + i];
+            }
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+        for (size_t p = 0; p < P; p++) {
+            const double *lh_node = plnode + (size_t)tip_state(e, dad_id, p) * B;
+            const double *pd = dad_lh + p * B;
+            double *lh_cat = e->pattern_lh_cat + p * C;
+            double lh_ptn = 0.0;
+            for (int c = 0; c < C; c++) {
+                lh_cat[c] = dot_vec(lh_node + c * n, pd + c * n, n);
+                if (!safe) lh_ptn += lh_cat[c];
+            }
+            double min_scale_d;
+            if (safe) {
+                const uint16_t *sd = dad_sc + p * C;
+                uint16_t min_scale = sd[0];
+                for (int c = 1; c < C; c++) if (sd[c] < min_scale) min_scale = sd[c];
+                min_scale_d = min_scale;
+                for (int c = 0; c < C; c++) {
+                    if (sd[c] == min_scale + 1) lh_cat[c] *= SCALING_THRESHOLD;
+                    else if (sd[c] > min_scale + 1) lh_cat[c] = 0.0;
+                }
+                lh_ptn = sum_vec_append(lh_cat, lh_ptn, C);
+            } else min_scale_d = dad_sc[p];
+            min_scale_d *= LOG_SCALING_THRESHOLD;
+            lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+            double lg = log(lh_ptn) + min_scale_d;
+            if (save_log_value) e->pattern_lh[p] = lg;
+            else { e->pattern_lh[p] = lh_ptn; e->pattern_scaling[p] = min_scale_d; }
+            tree_lh += lg * e->ptn_freq[p];
+        }
+        free(plnode);
+    } else {
+        /* INNER-INNER :2966-3104 */
+        const double *node_lh = e->partial + (size_t)dad_id * P * B;
+        const uint16_t *node_sc = e->scale + (size_t)dad_id * P * S;
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+        for (size_t p = 0; p < P; p++) {
+            const double *pd = dad_lh + p * B, *pn = node_lh + p * B;
+            double *lh_cat = e->pattern_lh_cat + p * C;
+            double lh_ptn = 0.0;
+            for (int c = 0; c < C; c++) {
+                lh_cat[c] = dot3(val + c * n, pn + c * n, pd + c * n, n);
+                if (!safe) lh_ptn += lh_cat[c];
+            }
+            double min_scale_d;
+            if (safe) {
+                const uint16_t *sd = dad_sc + p * C, *sn = node_sc + p * C;
+                uint16_t min_scale = (uint16_t)(sd[0] + sn[0]);
+                for (int c = 1; c < C; c++) { uint16_t s = (uint16_t)(sd[c] + sn[c]); if (s < min_scale) min_scale = s; }
+                min_scale_d = min_scale;
+                for (int c = 0; c < C; c++) {
+                    uint16_t s = (uint16_t)(sd[c] + sn[c]);
+                    if (s == min_scale + 1) lh_cat[c] *= SCALING_THRESHOLD;
+                    else if (s > min_scale + 1) lh_cat[c] = 0.0;
+                }
+                lh_ptn = sum_vec_append(lh_cat, lh_ptn, C);
+            } else min_scale_d = (double)(dad_sc[p] + node_sc[p]);
+            min_scale_d *= LOG_SCALING_THRESHOLD;
+            lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+            double lg = log(lh_ptn) + min_scale_d;
+            if (save_log_value) e->pattern_lh[p] = lg;
+            else { e->pattern_lh[p] = lh_ptn; e->pattern_scaling[p] = min_scale_d; }
+            tree_lh += lg * e->ptn_freq[p];
+        }
+    }
+    free(val);
+    int status = 0;
+    if (!isfinite(tree_lh)) {
+        /* NaN repair :3115-3132 */
+        status = 1;
+        tree_lh = 0.0;
+        for (size_t p = 0; p < P; p++) {
+            double ptn_lh = e->pattern_lh[p];
+            if (!isfinite(ptn_lh)) {
+                if (save_log_value) e->pattern_lh[p] = LOG_SCALING_THRESHOLD * 4;
+                else { e->pattern_lh[p] = 1.0; e->pattern_scaling[p] = LOG_SCALING_THRESHOLD * 4; }
+                ptn_lh = LOG_SCALING_THRESHOLD * 4;
+            }
+            tree_lh += ptn_lh * e->ptn_freq[p];
+        }
+    }
+    *logl_out = tree_lh;
+    return status;
+}
+
+/* computeLikelihoodBuffer(Generic)SIMD — phylokernelnew.h:2048-2231 */
+static void build_theta(orc_engine *e, int node_slot, int dad_kind, int dad_id) {
+    int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric, nmix = e->cfg.nmix;
+    size_t P = (size_t)e->cfg.nptn, S = S_of(e);
+    const double *dad_lh = e->partial + (size_t)node_slot * P * B;
+    const uint16_t *dad_sc = e->scale + (size_t)node_slot * P * S;
+    if (dad_kind == 0) {
+        int tip_block = n * nmix;
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < P; p++) {
+            const double *tip = e->tip_partial_lh + (size_t)tip_state(e, dad_id, p) * tip_block;
+            const double *pd = dad_lh + p * B;
+            double *theta = e->theta + p * B;
+            for (int c = 0; c < C; c++) {
+                const double *lh_tip = tip + (c / e->denom) * n;
+                for (int i = 0; i < n; i++) theta[c * n + i] = lh_tip[i] * pd[c * n + i];
+            }
+            if (safe) {
+                const uint16_t *sd = dad_sc + p * C;
+                uint16_t min_scale = sd[0];
+                for (int c = 1; c < C; c++) if (sd[c] < min_scale) min_scale = sd[c];
+                e->buffer_scale_all[p] = min_scale;
+                for (int c = 0; c < C; c++) {
+                    if (sd[c] == min_scale + 1) for (int x = 0; x < n; x++) theta[c * n + x] *= SCALING_THRESHOLD;
+                    else if (sd[c] > min_scale + 1) for (int x = 0; x < n; x++) theta[c * n + x] = 0.0;
+                }
+            } else e->buffer_scale_all[p] = dad_sc[p];
+            e->buffer_scale_all[p] *= LOG_SCALING_THRESHOLD;
+        }
+    } else {
+        const double *node_lh = e->partial + (size_t)dad_id * P * B;
+        const uint16_t *node_sc = e->scale + (size_t)dad_id * P * S;
+#pragma omp parallel for schedule(static)
+        for (size_t p = 0; p < P; p++) {
+            const double *pd = dad_lh + p * B, *pn = node_lh + p * B;
+            double *theta = e->theta + p * B;
+            for (int i = 0; i < B; i++) theta[i] = pn[i] * pd[i];
+            if (safe) {
+                const uint16_t *sd = dad_sc + p * C, *sn = node_sc + p * C;
+                uint16_t min_scale = (uint16_t)(sd[0] + sn[0]);
+                for (int c = 1; c < C; c++) { uint16_t s = (uint16_t)(sd[c] + sn[c]); if (s < min_scale) min_scale = s; }
+                e->buffer_scale_all[p] = min_scale;
+                for (int c = 0; c < C; c++) {
+                    uint16_t s = (uint16_t)(sd[c] + sn[c]);
+                    if (s == min_scale + 1) for (int x = 0; x < n; x++) theta[c * n + x] *= SCALING_THRESHOLD;
+                    else if (s > min_scale + 1) for (int x = 0; x < n; x++) theta[c * n + x] = 0.0;
+                }
+            } else e->buffer_scale_all[p] = (double)(dad_sc[p] + node_sc[p]);
+            e->buffer_scale_all[p] *= LOG_SCALING_THRESHOLD;
+        }
+    }
+    e->theta_computed = 1;
+}
+
+int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
+
+/* computeLikelihoodDerv(Generic)SIMD — phylokernelnew.h:2233-2633 (joint branch length, no +ASC) */
+int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
+                    double length, double *df_out, double *ddf_out) {
+    orc_update_partials(e, ops, nops);
+    if (!e->theta_computed) build_theta(e, node_slot, dad_kind, dad_id);
+    int B = e->B;
+    size_t P = (size_t)e->cfg.nptn;
+    double *val0 = (double *)malloc(sizeof(double) * 3 * B), *val1 = val0 + B, *val2 = val1 + B;
+    compute_vals(e, length, val0, val1, val2);
+    double all_df = 0.0, all_ddf = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : all_df, all_ddf)
+    for (size_t p = 0; p < P; p++) {
+        double lh_ptn, df_ptn, ddf_ptn;
+        dot_triple(val0, val1, val2, e->theta + p * B, B, &lh_ptn, &df_ptn, &ddf_ptn);
+        lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+        lh_ptn = 1.0 / lh_ptn;
+        double df_frac = df_ptn * lh_ptn, ddf_frac = ddf_ptn * lh_ptn;
+        double freq = e->ptn_freq[p];
+        double tmp1 = df_frac * freq, tmp2 = ddf_frac * freq;
+        all_df += tmp1;
+        all_ddf += fma(-tmp1, df_frac, tmp2); /* nmul_add(tmp1, df_frac, tmp2) :2505 */
+    }
+    free(val0);
+    *df_out = all_df;
+    *ddf_out = all_ddf;
+    if (!isfinite(all_df)) { *df_out = *ddf_out = 0.0; return 1; } /* :2629-2632 */
+    return 0;
+}
+
+/* computeLikelihoodFromBuffer(Generic)SIMD — phylokernelnew.h:3232-3428 */
+int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
+    if (!e->theta_computed) { snprintf(e->err, sizeof e->err, "theta not computed"); return -1; }
+    int B = e->B;
+    size_t P = (size_t)e->cfg.nptn;
+    double *val0 = (double *)malloc(sizeof(double) * B);
+    compute_vals(e, length, val0, NULL, NULL);
+    double tree_lh = 0.0;
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+    for (size_t p = 0; p < P; p++) {
+        double lh_ptn = dot_vec(val0, e->theta + p * B, B); /* dotProductVec over the whole block :3329 */
+        lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+        lh_ptn = log(fabs(lh_ptn)) + e->buffer_scale_all[p];
+        e->pattern_lh[p] = lh_ptn;
+        tree_lh += lh_ptn * e->ptn_freq[p];
+    }
+    free(val0);
+    int status = 0;
+    if (!isfinite(tree_lh)) {
+        status = 1;
+        tree_lh = 0.0;
+        for (size_t p = 0; p < P; p++) {
+            if (!isfinite(e->pattern_lh[p])) e->pattern_lh[p] = LOG_SCALING_THRESHOLD * 4;
+            tree_lh += e->pattern_lh[p] * e->ptn_freq[p];
+        }
+    }
+    *logl_out = tree_lh;
+    return status;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * read-backs (reference layouts)
+ * ------------------------------------------------------------------------------------------- */
+int orc_get_pattern_lh(orc_engine *e, double *out) { memcpy(out, e->pattern_lh, sizeof(double) * e->cfg.nptn); return 0; }
+int orc_get_pattern_scaling(orc_engine *e, double *out) { memcpy(out, e->pattern_scaling, sizeof(double) * e->cfg.nptn); return 0; }
+int orc_get_pattern_lh_cat(orc_engine *e, double *out) { memcpy(out, e->pattern_lh_cat, sizeof(double) * e->cfg.nptn * e->C); return 0; }
+int orc_get_theta(orc_engine *e, double *out) { memcpy(out, e->theta, sizeof(double) * e->cfg.nptn * e->B); return 0; }
+int orc_get_buffer_scale_all(orc_engine *e, double *out) { memcpy(out, e->buffer_scale_all, sizeof(double) * e->cfg.nptn); return 0; }
+int orc_get_scale_num(orc_engine *e, int slot, uint16_t *out) {
+    size_t sz = (size_t)e->cfg.nptn * S_of(e);
+    memcpy(out, e->scale + (size_t)slot * sz, sizeof(uint16_t) * sz);
+    return 0;
+}
+/* partial_lh of one slot in the V=1 reference layout [p*B + c*n + i] */
+int orc_get_partial(orc_engine *e, int slot, double *out) {
+    size_t sz = (size_t)e->cfg.nptn * e->B;
+    memcpy(out, e->partial + (size_t)slot * sz, sizeof(double) * sz);
+    return 0;
+}
+int orc_get_tip_partial_lh(orc_engine *e, double *out) {
+    memcpy(out, e->tip_partial_lh, sizeof(double) * (e->cfg.state_unknown + 1) * e->cfg.nmix * e->cfg.nstates);
+    return 0;
+}
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

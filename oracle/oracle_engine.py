@@ -1,0 +1,171 @@
+"""ctypes wrapper around oracle/_build/liblkoracle.so — TEST INFRASTRUCTURE (see lk_oracle.c header).
+
+Exposes the same method names as iqtree2_b200.engine.LikelihoodEngine so parity tests drive both with the
+same code.  Never imported by the product package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "_build", "liblkoracle.so")
+
+
+class _Config(C.Structure):
+    _fields_ = [("nstates", C.c_int32), ("ncat", C.c_int32), ("nmix", C.c_int32), ("fused_mix_rate", C.c_int32),
+                ("safe_numeric", C.c_int32), ("seq_type", C.c_int32), ("state_unknown", C.c_int32),
+                ("ntaxa", C.c_int32), ("nptn", C.c_int64), ("nslots", C.c_int32), ("device", C.c_int32)]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "lk_oracle.c")
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.orc_create.restype = C.c_void_p
+        _lib.orc_last_error.restype = C.c_char_p
+    return _lib
+
+
+SEQ_TYPES = {"GENERIC": 0, "DNA": 1, "AA": 2}
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class OracleEngine:
+    """CPU oracle with the engine interface (set_* / update_partials / branch_logl / branch_derv / ...)."""
+
+    def __init__(self, model, ntaxa, nptn, nslots=None, safe_numeric=False):
+        self.model = model
+        self.n, self.ncat, self.nmix = model.nstates, model.ncat, model.nmix
+        self.Cmix = model.ncat_mix
+        self.B = self.n * self.Cmix
+        self.ntaxa, self.nptn = int(ntaxa), int(nptn)
+        self.nslots = int(nslots if nslots is not None else max(ntaxa - 2, 1) + 2)
+        self.safe = bool(safe_numeric)
+        cfg = _Config(self.n, self.ncat, self.nmix, int(model.fused_mix_rate), int(self.safe), SEQ_TYPES[model.seq_type],
+                      model.state_unknown, self.ntaxa, self.nptn, self.nslots, 0)
+        self._h = C.c_void_p(lib().orc_create(C.byref(cfg)))
+        if not self._h:
+            raise MemoryError("orc_create failed")
+        self.set_model(model)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    # ---- inputs -------------------------------------------------------------------------------
+    def set_model(self, model):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        ev, U, Ui, w = f(model.eval), f(model.evec), f(model.inv_evec), f(model.mix_weight)
+        lib().orc_set_model(self._h, _dp(ev), _dp(U), _dp(Ui), _dp(w))
+        r, p = f(model.cat_rate), f(model.cat_prop)
+        lib().orc_set_rates(self._h, _dp(r), _dp(p))
+
+    def set_tip_states(self, states):
+        s = np.ascontiguousarray(states, dtype=np.uint8)
+        assert s.shape == (self.ntaxa, self.nptn)
+        lib().orc_set_tip_states(self._h, _dp(s))
+
+    def set_pattern_freq(self, freq):
+        f = np.ascontiguousarray(freq, dtype=np.float64)
+        assert f.shape == (self.nptn,)
+        lib().orc_set_pattern_freq(self._h, _dp(f))
+
+    def set_pattern_invar(self, invar):
+        f = np.ascontiguousarray(invar, dtype=np.float64)
+        assert f.shape == (self.nptn,)
+        lib().orc_set_pattern_invar(self._h, _dp(f))
+
+    # ---- compute ------------------------------------------------------------------------------
+    def update_partials(self, ops):
+        ops = np.ascontiguousarray(ops)
+        rc = lib().orc_update_partials(self._h, _dp(ops), C.c_int(len(ops)))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+
+    def branch_logl(self, ops, end_a, end_b, length, save_log_value=True):
+        ops = np.ascontiguousarray(ops)
+        out = C.c_double()
+        assert end_a[0] == 1
+        rc = lib().orc_branch_logl(self._h, _dp(ops), C.c_int(len(ops)), C.c_int(end_a[1]), C.c_int(end_b[0]),
+                                   C.c_int(end_b[1]), C.c_double(length), C.c_int(int(save_log_value)), C.byref(out))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        self.last_status = rc
+        return out.value
+
+    def theta_reset(self):
+        lib().orc_theta_reset(self._h)
+
+    def branch_derv(self, ops, end_a, end_b, length):
+        ops = np.ascontiguousarray(ops)
+        df, ddf = C.c_double(), C.c_double()
+        rc = lib().orc_branch_derv(self._h, _dp(ops), C.c_int(len(ops)), C.c_int(end_a[1]), C.c_int(end_b[0]),
+                                   C.c_int(end_b[1]), C.c_double(length), C.byref(df), C.byref(ddf))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        self.last_status = rc
+        return df.value, ddf.value
+
+    def logl_from_buffer(self, length):
+        out = C.c_double()
+        rc = lib().orc_logl_from_buffer(self._h, C.c_double(length), C.byref(out))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        self.last_status = rc
+        return out.value
+
+    # ---- read-backs ---------------------------------------------------------------------------
+    def _get(self, fn, n, dtype=np.float64, *args):
+        out = np.empty(n, dtype=dtype)
+        getattr(lib(), fn)(self._h, *args, _dp(out))
+        return out
+
+    def get_pattern_lh(self):
+        return self._get("orc_get_pattern_lh", self.nptn)
+
+    def get_pattern_scaling(self):
+        return self._get("orc_get_pattern_scaling", self.nptn)
+
+    def get_pattern_lh_cat(self):
+        return self._get("orc_get_pattern_lh_cat", self.nptn * self.Cmix).reshape(self.nptn, self.Cmix)
+
+    def get_theta(self):
+        return self._get("orc_get_theta", self.nptn * self.B).reshape(self.nptn, self.Cmix, self.n)
+
+    def get_buffer_scale_all(self):
+        return self._get("orc_get_buffer_scale_all", self.nptn)
+
+    def get_scale_num(self, slot):
+        S = self.Cmix if self.safe else 1
+        return self._get("orc_get_scale_num", self.nptn * S, np.uint16, C.c_int(slot)).reshape(self.nptn, S)
+
+    def get_partial(self, slot):
+        """[nptn][ncat_mix][nstates] (the reference's V=1 layout)."""
+        return self._get("orc_get_partial", self.nptn * self.B, np.float64, C.c_int(slot)).reshape(self.nptn, self.Cmix, self.n)
+
+    def get_tip_partial_lh(self):
+        return self._get("orc_get_tip_partial_lh", (self.model.state_unknown + 1) * self.nmix * self.n)
+
+    @staticmethod
+    def num_threads():
+        return int(lib().orc_num_threads())
