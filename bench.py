@@ -1,0 +1,341 @@
+#!/usr/bin/env python3
+"""bench.py — full-tree logL+derivative evaluations/s (BASELINE.json metric) through the C ABI.
+
+One STEP = one EVAL of SURVEY §8(d):  invalidate every CLV (clearAllPartialLH) -> computeLikelihoodBranch at a
+fixed branch (full post-order traversal + root reduction) -> computeLikelihoodDerv at that branch (theta build +
+one (df, ddf) pass).  Default workload = BASELINE.json configs[1]: synthetic DNA 1000 taxa x 1,000,000 patterns,
+GTR+G4 (NORM_LH), which fits one B200 (127.7 GB of CLVs).
+
+  python bench.py --gpus N --steps K --warmup W               # this framework (CUDA engine; no CPU fallback)
+  python bench.py --impl reference --gpus N --steps K ...     # the reference's CPU algorithm on the host cores
+
+N > 1 (torchrun): the pattern axis is sharded across ranks (each GPU owns a contiguous pattern slice of every CLV,
+SURVEY §8e); the only exchange is an all-reduce of the (logL, df, ddf) scalars.  Total work is fixed => "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from iqtree2_b200 import models, plan, treesim  # noqa: E402
+
+WORKLOADS = {
+    # name: (ntaxa, npatterns, model factory, description)   -- BASELINE.json configs[1..3]
+    "dna_1000x1M_gtr_g4": (1000, 1_000_000, lambda: models.make_gtr_gamma(), "synthetic DNA 1000 taxa x 1M patterns, GTR+G4"),
+    "aa_200x100k_lg_g4": (200, 100_000, lambda: models.make_lg_gamma(), "synthetic protein 200 taxa x 100k patterns, LG+G4"),
+    "aa_100x50k_lg_c60_g4": (100, 50_000, lambda: models.make_lg_c60_gamma(), "synthetic protein 100 taxa x 50k patterns, LG+C60+G4"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.device_index = device_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def algorithmic_bytes(ops, nptn, B, S, ntaxa, n_root_slots=2):
+    """per pattern 2(T-2)(8B+2S) [each internal CLV+scale written once, read once] + T [tip codes]
+    + 16 [freq, invar] + 8 [_pattern_lh] + 2*8B + 16 [theta write + read, freq, invar].
+    Returns (bytes per eval, bytes of the partial-likelihood kernels only), computed from the actual op list."""
+    clv = 8 * B + 2 * S
+    partial = 0
+    for op in ops:
+        partial += clv  # write dst
+        for side in ("left", "right"):
+            partial += clv if op[side]["kind"] == plan.KIND_SLOT else 1
+    # the CLVs at the evaluation branch are read once by the root stage: one slot when the other end is a leaf
+    root_reads = clv * n_root_slots
+    per_ptn_eval = partial + root_reads + 16 + 8 + 2 * 8 * B + 16
+    return per_ptn_eval * nptn, partial * nptn
+
+
+def make_inputs(ntaxa, nptn, model, seed_tree=1, seed_seq=2, block=262_144):
+    tree = treesim.yule_tree(ntaxa, seed=seed_tree)
+    nb = min(nptn, block)
+    base = treesim.evolve_patterns_fast(tree, model.nstates, nb, seed=seed_seq)
+    reps = (nptn + nb - 1) // nb
+    tips = np.tile(base, (1, reps))[:, :nptn] if reps > 1 else base
+    tips = np.ascontiguousarray(tips)
+    freq = np.ones(nptn)
+    data = (f"synthetic: Yule-Harding tree (seed {seed_tree}), Exp(0.1) branch lengths; {nb} tree-evolved columns (seed {seed_seq})"
+            + (f" tiled x{reps} to {nptn} patterns" if reps > 1 else "") + "; every column counted as its own pattern (freq 1)")
+    return tree, tips, freq, data
+
+
+def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, warmup):
+    """The reference's CPU algorithm (oracle port, OpenMP over pattern packets) on a bounded pattern sample."""
+    from oracle.oracle_engine import OracleEngine
+    sample_ptn = int(min(sample_ptn, tips.shape[1]))
+    o = OracleEngine(model, tree.ntaxa, sample_ptn, safe_numeric=False)
+    o.set_tip_states(np.ascontiguousarray(tips[:, :sample_ptn]))
+    o.set_pattern_freq(freq[:sample_ptn])
+    o.set_pattern_invar(np.zeros(sample_ptn))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        o.theta_reset()
+        ll = o.branch_logl(ops, a, b, L)
+        df, ddf = o.branch_derv(ops[:0], a, b, L)
+        times.append(time.perf_counter() - t0)
+    t = times[warmup:]
+    return {"sec_per_sample_eval": float(np.mean(t)), "best_sec": float(np.min(t)), "sample_ptn": sample_ptn,
+            "cores": OracleEngine.num_threads(), "logl": ll, "df": df, "ddf": ddf}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS))
+    ap.add_argument("--taxa", type=int, default=0, help="override taxa (debug)")
+    ap.add_argument("--patterns", type=int, default=0, help="override patterns (debug)")
+    ap.add_argument("--schedule", type=int, default=0, help="0 auto, 1 levelled, 2 walker")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    ntaxa, nptn, mk, desc = WORKLOADS[args.workload]
+    if args.taxa:
+        ntaxa = args.taxa
+    if args.patterns:
+        nptn = args.patterns
+    model = mk()
+    B, S = model.nstates * model.ncat_mix, 1
+    workload_name = args.workload if not (args.taxa or args.patterns) else f"{args.workload}[override {ntaxa}x{nptn}]"
+
+    # ---------------------------------------------------------------------------------------------------------
+    # reference arm: the reference's own CPU algorithm on the host cores (rank 0 only)
+    # ---------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        tree, tips, freq, data = make_inputs(ntaxa, min(nptn, 65536), model)
+        ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+        # bounded sample: about 1.5 s of CPU work per step
+        sample = args.cpu_sample or max(256, int(4.0e9 / (len(ops) * B * model.nstates * 6)))
+        sample = min(sample, tips.shape[1])
+        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, args.steps, max(1, args.warmup))
+        evals = (sample / nptn) / r["sec_per_sample_eval"]
+        line = {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / evals,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
+                "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "NORM_LH"},
+                "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": "port",
+                                 "sample": f"{sample} of {nptn} patterns per step, all {len(ops)} partial updates + root + derivative; "
+                                           f"throughput scaled by {sample}/{nptn}"},
+                "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------------------------------------------------------------------------------------------------
+    # this framework
+    # ---------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from iqtree2_b200.engine import LikelihoodEngine
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the likelihood engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # pattern shard of this rank: contiguous, multiple of the 128-pattern tile except for the last rank
+    per = (nptn + world - 1) // world
+    per = (per + 127) // 128 * 128
+    lo, hi = min(rank * per, nptn), min((rank + 1) * per, nptn)
+    my_nptn = hi - lo
+    tree, tips, freq, data = make_inputs(ntaxa, nptn, model)
+    tips = np.ascontiguousarray(tips[:, lo:hi])
+    freq = freq[lo:hi]
+    br = plan.pendant_branch_of(tree, 0)
+    ops, a, b, L = plan.plan_branch(tree, br)
+
+    eng = LikelihoodEngine(model, ntaxa, my_nptn, device=local_rank, schedule=args.schedule)
+    stream = torch.cuda.current_stream()
+    eng.set_stream(stream.cuda_stream)
+    eng.set_tip_states(tips)
+    eng.set_pattern_freq(freq)
+    eng.set_pattern_invar(np.zeros(my_nptn))
+    eng.set_profiling(True)
+
+    scal = torch.zeros(3, dtype=torch.float64, device="cuda")
+    pinned_model = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in
+                    (model.eval, model.evec, model.inv_evec, model.mix_weight, model.cat_rate, model.cat_prop)]
+    h2d = int(ops.nbytes) + int(sum(t.numel() * 8 for t in pinned_model))
+    d2h = 3 * 8
+
+    def one_eval(upload_model):
+        """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
+        if upload_model:
+            eng.set_model(model)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
+        eng.theta_reset()
+        ll = eng.branch_logl(ops, a, b, L)
+        t1 = eng.last_timing()
+        df, ddf = eng.branch_derv(ops[:0], a, b, L)
+        t2 = eng.last_timing()
+        if world > 1:
+            scal.copy_(torch.tensor([ll, df, ddf], dtype=torch.float64))
+            dist.all_reduce(scal)
+            ll, df, ddf = scal.tolist()
+        return (ll, df, ddf), t1, t2
+
+    for _ in range(args.warmup):
+        res, _, _ = one_eval(True)
+
+    def timed(upload_model):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        dev_ms = partial_ms = 0.0
+        launches0 = eng.launch_count
+        for _ in range(args.steps):
+            r, t1, t2 = one_eval(upload_model)
+            dev_ms += t1["total_ms"] + t2["total_ms"]
+            partial_ms += t1["partials_kernel_ms"]
+        ev1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        out = {"event_ms": ev0.elapsed_time(ev1), "wall_s": wall, "device_ms": dev_ms, "partials_kernel_ms": partial_ms,
+               "launches": eng.launch_count - launches0, "result": r, "clocks": clocks}
+        if world > 1:
+            t = torch.tensor([out["event_ms"], out["device_ms"], out["partials_kernel_ms"], wall * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["event_ms"], out["device_ms"], out["partials_kernel_ms"], w = t.tolist()
+            out["wall_s"] = w / 1e3
+        return out
+
+    e2e_run = timed(True)     # host buffers in every step, H2D/D2H inside the timed region
+    res_run = timed(False)    # inputs resident; device-time of the kernels only
+
+    K = args.steps
+    value = K / (res_run["device_ms"] * 1e-3)
+    e2e_value = K / (e2e_run["event_ms"] * 1e-3)
+    bytes_eval, bytes_partials = algorithmic_bytes(ops, nptn, B, S, ntaxa, n_root_slots=1 + (b[0] == plan.KIND_SLOT))
+    my_bytes_partials = bytes_partials * (my_nptn / nptn)
+    peak, peak_src = load_peaks()
+    ker_s = res_run["partials_kernel_ms"] * 1e-3 / K
+    achieved = my_bytes_partials / ker_s / 1e9
+    n_ii, n_ti, n_tt = plan.count_node_cases(ops)
+
+    line = {
+        "metric": "full_tree_logl_deriv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
+        "warmup": args.warmup, "ms_per_step": res_run["device_ms"] / K, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": data,
+        "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "patterns_per_gpu": my_nptn, "model": desc,
+                   "kernel": "NORM_LH", "nstates": model.nstates, "ncat_mix": model.ncat_mix, "partial_updates_per_eval": len(ops),
+                   "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
+                   "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}[args.schedule],
+                   "clv_bytes_resident": eng.device_bytes, "l2": "inputs (CLVs) far larger than L2; no flush needed",
+                   "parallelism": f"pattern-sharded x{world}" if world > 1 else "single GPU",
+                   "algorithmic_GB_per_eval": bytes_eval / 1e9},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_run["event_ms"] / K, "wall_ms_per_step": e2e_run["wall_s"] * 1e3 / K,
+                "what": "set_model+set_rates (eigensystem, rates), op list with branch lengths from host memory, "
+                        "branch_logl + branch_derv through the C ABI, (logL, df, ddf) read back each step"},
+        "gpu_launches": int(res_run["launches"]),
+        "clocks": res_run["clocks"],
+        "roofline": {"bound": "hbm", "kernel": "k_partials_n4c4 (pattern-tile walker)" if model.nstates == 4 and model.ncat_mix == 4 else "k_partials_generic",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": my_bytes_partials,
+                     "launch_ms": ker_s * 1e3, "partial_lh_GBps": achieved},
+        "result": {"logl": res_run["result"][0], "df": res_run["result"][1], "ddf": res_run["result"][2]},
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = args.cpu_sample or max(256, int(2.0e10 / (len(ops) * B * model.nstates * 6)))
+        sample = min(sample, my_nptn)
+        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 3, 1)
+        cpu_evals = (sample / nptn) / r["sec_per_sample_eval"]
+        line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": "port",
+                                "sample": f"first {sample} of {nptn} patterns, all {len(ops)} partial updates + root + derivative, "
+                                          f"3 timed evals after 1 warm-up; throughput scaled by {sample}/{nptn}",
+                                "sec_per_sample_eval": r["sec_per_sample_eval"]}
+    if rank == 0:
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

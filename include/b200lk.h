@@ -1,0 +1,159 @@
+/*
+ * b200lk.h — C ABI of the B200-native phylogenetic likelihood engine (libb200lk.so).
+ *
+ * Drop-in boundary for IQ-TREE 2's PhyloTree likelihood path.  Every entry point names the reference
+ * interface it replaces (paths relative to the IQ-TREE 2.4.0 source tree).  The five pointers-to-member
+ * that PhyloTree::setLikelihoodKernel assigns (tree/phylotreesse.cpp:91-199; declared at
+ * tree/phylotree.h:900-901, 947-948, 1000-1001, 1342-1343) would be pointed at thin members that marshal
+ * into these calls — see INTEGRATION.md for the shim.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are HOST pointers unless a name says `_dev`;
+ *   - every call returns 0 on success, >0 for a numerical condition the reference reports with a warning
+ *     (B200LK_WARN_*), <0 for an error (message via b200lk_last_error); nothing throws, nothing exits;
+ *   - one engine = one PhyloTree's buffers on one GPU for one pattern range. Distinct engines may be used
+ *     concurrently from different host threads (PhyloSuperTree calls partition trees in an omp parallel for,
+ *     tree/phylosupertreeplen.cpp:380-409); calls on the same engine must be serialised by the caller;
+ *   - there is NO CPU fallback: without a CUDA device b200lk_create fails.
+ *
+ * Host-visible layouts are the reference's with SIMD width V=1 (SURVEY §8a "Layout crib"):
+ *   partial_lh[p*B + c*n + i], B = n*ncat_mix, c = m*ncat + r;   scale_num NORM_LH [p], SAFE_LH [p*C + c];
+ *   the device keeps a warp-interleaved layout internally and converts on read-back.
+ */
+#ifndef B200LK_H_
+#define B200LK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LK_ABI_VERSION 1
+
+/* status codes (>0: numerical warnings the reference prints and repairs; <0: errors) */
+#define B200LK_OK 0
+#define B200LK_WARN_UNDERFLOW 1      /* non-finite tree logL repaired per pattern (phylokernelnew.h:3107-3132, 3374-3383) */
+#define B200LK_WARN_DERV_UNDERFLOW 2 /* non-finite df: df = ddf = 0 returned (phylokernelnew.h:2629-2632) */
+#define B200LK_ERR_INVALID (-1)
+#define B200LK_ERR_CUDA (-2)
+#define B200LK_ERR_NOMEM (-3)
+#define B200LK_ERR_STATE (-4)        /* e.g. logl_from_buffer without a theta buffer (ASSERT at phylokernelnew.h:3240) */
+
+#define B200LK_SEQ_GENERIC 0 /* states >= nstates are all "unknown" (model/modelsubst.cpp:197-207) */
+#define B200LK_SEQ_DNA 1     /* states 4..17 are IUPAC ambiguity bitmasks state-3 (model/modeldna.cpp:462-475) */
+#define B200LK_SEQ_PROTEIN 2 /* states 20,21,22 = B,Z,J (model/modelprotein.cpp:1149-1166) */
+
+/* What PhyloTree::initializeAllPartialLh sizes its buffers from (tree/phylotree.cpp:893-939, 1060-1188). */
+typedef struct b200lk_config {
+    int32_t nstates;        /* aln->num_states */
+    int32_t ncat;           /* site_rate->getNRate() */
+    int32_t nmix;           /* model->getNMixtures() */
+    int32_t fused_mix_rate; /* model_factory->fused_mix_rate */
+    int32_t safe_numeric;   /* 0 = NORM_LH, 1 = SAFE_LH (tree/phylotreesse.cpp:95-96) */
+    int32_t seq_type;       /* B200LK_SEQ_* */
+    int32_t state_unknown;  /* aln->STATE_UNKNOWN (alignment/alignment.cpp:738-745) */
+    int32_t ntaxa;          /* aln->getNSeq() */
+    int64_t nptn;           /* patterns owned by this engine (aln->size(), or this GPU's slice of it) */
+    int32_t nslots;         /* CLV slots: (ntaxa-2) for LM_PER_NODE + 2 NNI spares (tree/phylotree.cpp:1071-1104) */
+    int32_t device;         /* CUDA device ordinal */
+} b200lk_config;
+
+/* One child of a TraversalInfo entry: a leaf (kind 0, id = alignment row) or an internal CLV (kind 1, id = slot). */
+typedef struct b200lk_child {
+    int32_t kind;
+    int32_t id;
+    double length; /* child->length */
+} b200lk_child;
+
+/* One pending partial update = one TraversalInfo (tree/phylotree.h:320-331): write dad_branch->partial_lh
+ * (slot dst_slot) from the two children in neighbour order. echildren / partial_lh_leaves are built on device. */
+typedef struct b200lk_op {
+    int32_t dst_slot;
+    int32_t reserved;
+    b200lk_child left, right;
+} b200lk_op;
+
+typedef struct b200lk_engine b200lk_engine;
+
+/* ---- life-cycle: initializeAllPartialLh / deleteAllPartialLh (tree/phylotree.cpp:893, 754) ------------------ */
+int b200lk_abi_version(void);
+int b200lk_create(const b200lk_config *cfg, b200lk_engine **out);
+void b200lk_destroy(b200lk_engine *e);
+const char *b200lk_last_error(const b200lk_engine *e); /* e may be NULL: error of the last failed create */
+/* bytes of device memory the engine holds (PhyloTree::getMemoryRequired, tree/phylotree.cpp:967) */
+int64_t b200lk_device_bytes(const b200lk_engine *e);
+/* run on a caller-owned stream (cudaStream_t as void*); NULL restores the engine's own stream */
+int b200lk_set_stream(b200lk_engine *e, void *cuda_stream);
+/* schedule for multi-op traversals: 0 = auto, 1 = one levelled launch per tree depth, 2 = pattern-tile walker */
+int b200lk_set_schedule(b200lk_engine *e, int schedule);
+
+/* ---- inputs ------------------------------------------------------------------------------------------------- */
+/* tip states, sequence-major [ntaxa][nptn] (AlignmentSummary::sequenceMatrix rows, tree/phylotree.cpp:3251-3256;
+ * value = Pattern entry aln->at(ptn)[taxon], 0..state_unknown) */
+int b200lk_set_tip_states(b200lk_engine *e, const uint8_t *states);
+/* ptn_freq / ptn_invar as computePtnFreq / computePtnInvar fill them (tree/phylotreesse.cpp:537-612) */
+int b200lk_set_pattern_freq(b200lk_engine *e, const double *ptn_freq);
+int b200lk_set_pattern_invar(b200lk_engine *e, const double *ptn_invar);
+/* model->getEigenvalues/getEigenvectors/getInverseEigenvectors/getMixtureWeight (model/modelmixture.cpp:1536-1575);
+ * recomputes tip_partial_lh on device = computeTipPartialLikelihood (tree/phylotreesse.cpp:243-375) */
+int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec,
+                     const double *mix_weight);
+/* site_rate->getRate(c) / getProp(c) */
+int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop);
+
+/* ---- the five kernel entry points --------------------------------------------------------------------------- */
+/* computePartialLikelihood over a traversal_info list in post-order
+ * (computeTraversalInfo<VC>(node, dad, compute_partial_lh=true), tree/phylokernelnew.h:1150-1281, 1289-2039) */
+int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops);
+
+/* computeLikelihoodBranch(dad_branch, dad, save_log_value) (tree/phylokernelnew.h:2641-3223): flush `ops`, then the
+ * branch between CLV slot `node_slot` and the other end (dad_kind 0: leaf `dad_id`; 1: slot `dad_id`).
+ * Fills _pattern_lh (+ _pattern_scaling when !save_log_value) and _pattern_lh_cat; returns this engine's
+ * sum_p ptn_freq[p]*_pattern_lh[p]. */
+int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                       int32_t dad_id, double length, int32_t save_log_value, double *logl);
+
+/* computeLikelihoodDerv(dad_branch, dad, &df, &ddf) (tree/phylokernelnew.h:2233-2633): flush `ops`, build
+ * theta_all/buffer_scale_all if !theta_computed (computeLikelihoodBuffer, :2048-2231), then one (df, ddf) pass. */
+int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                       int32_t dad_id, double length, double *df, double *ddf);
+/* theta_computed = false (PhyloTree::optimizeOneBranch, tree/phylotree.cpp:2608) */
+int b200lk_theta_reset(b200lk_engine *e);
+
+/* computeLikelihoodFromBuffer() (tree/phylokernelnew.h:3232-3428) at current_it->length = length */
+int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *logl);
+
+/* Fused Newton-Raphson on the theta buffer = Optimization::minimizeNewton (utils/optimization.cpp:422-499) driving
+ * computeFuncDerv (tree/phylotree.cpp:2529-2536) without a host round trip per step. Flushes `ops` and builds theta
+ * first when needed. Returns the optimised length in *length_out. */
+int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                         int32_t dad_id, double min_len, double guess, double max_len, double tolerance,
+                         int32_t max_steps, double *length_out, int32_t *steps_out);
+
+/* ---- read-backs (computePatternLikelihood & friends, tree/phylotree.cpp:1458-1603; parity dumps) -------------- */
+int b200lk_get_pattern_lh(b200lk_engine *e, double *out /* [nptn] */);
+int b200lk_get_pattern_scaling(b200lk_engine *e, double *out /* [nptn] */);
+int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out /* [nptn][ncat_mix], after transformPatternLhCat */);
+int b200lk_get_theta(b200lk_engine *e, double *out /* [nptn][B] */);
+int b200lk_get_buffer_scale_all(b200lk_engine *e, double *out /* [nptn] */);
+int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out /* [nptn] or [nptn][ncat_mix] */);
+int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out /* [nptn][B] */);
+int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out /* [(state_unknown+1)][nmix][n] */);
+/* device pointer of _pattern_lh (length >= nptn doubles) for on-device consumers (UFBoot RELL) */
+void *b200lk_pattern_lh_dev(b200lk_engine *e);
+
+/* ---- measurement --------------------------------------------------------------------------------------------- */
+/* When enabled, every call brackets its kernel groups with CUDA events on the engine stream. */
+int b200lk_set_profiling(b200lk_engine *e, int32_t on);
+/* milliseconds of the last call: [0] op staging + partial_info + partial-likelihood kernels, [1] root/logl kernels,
+ * [2] theta/derv kernels, [3] whole call on the stream, [4] the partial-likelihood kernel launch(es) alone;
+ * launches[0..2] = kernel launches in groups [0..2] */
+int b200lk_last_timing(b200lk_engine *e, float ms[5], int32_t launches[3]);
+/* total kernel launches issued by this engine since creation */
+int64_t b200lk_launch_count(const b200lk_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LK_H_ */

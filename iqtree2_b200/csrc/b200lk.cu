@@ -1,0 +1,703 @@
+// b200lk.cu — engine (device buffers, op staging, launches) and the C ABI declared in include/b200lk.h.
+//
+// One engine = the likelihood buffers of one PhyloTree on one GPU for one pattern range
+// (central_partial_lh / central_scale_num / theta_all / buffer_scale_all / _pattern_lh / _pattern_lh_cat /
+// ptn_freq / ptn_invar / tip_partial_lh, tree/phylotree.cpp:893-1188), resident in HBM across calls.
+// No CPU fallback: every compute entry point launches CUDA kernels or fails.
+#include "b200lk.h"
+#include "b200lk_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace b200lk;
+
+struct b200lk_engine {
+    b200lk_config cfg{};
+    int C = 0, B = 0, denom = 1, S = 1;
+    long long P = 0, Ppad = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    Dev d{};
+    // owned device buffers
+    uint8_t *d_tips = nullptr;
+    double *d_freq = nullptr, *d_invar = nullptr;
+    double *d_model = nullptr;   // eval | evec | inv_evec | mix_weight | cat_rate | cat_prop | tip_lh | val(3B)
+    double *d_partial = nullptr;
+    uint16_t *d_scale = nullptr;
+    double *d_theta = nullptr, *d_buffer_scale = nullptr, *d_pattern_lh = nullptr, *d_pattern_scaling = nullptr,
+           *d_pattern_lh_cat = nullptr;
+    double *d_opinfo = nullptr;
+    size_t opinfo_cap = 0;   // doubles
+    DevOp *d_ops = nullptr;
+    ChildJob *d_jobs = nullptr;
+    size_t ops_cap = 0;
+    void *h_stage = nullptr;   // pinned staging: ops + jobs
+    size_t h_stage_cap = 0;
+    double *d_red = nullptr;   // per-block partial sums
+    double *d_result = nullptr;
+    double *h_result = nullptr;   // pinned, 8 doubles
+    unsigned long long *d_counter = nullptr;
+    double *d_scratch = nullptr;   // read-back conversion buffer
+    size_t scratch_cap = 0;
+    std::vector<double> h_freq;
+    int64_t device_bytes = 0;
+    bool theta_computed = false;
+    int schedule = 0;
+    int num_sms = 148;
+    int info_smem_optin = 0;
+    // profiling
+    bool profiling = false;
+    bool partials_timed = false;
+    cudaEvent_t ev[6]{};
+    float last_ms[5] = {0, 0, 0, 0, 0};
+    int last_launch[3] = {0, 0, 0};
+    int64_t launches = 0;
+    std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t err__ = (call);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            e->err = std::string(#call) + ": " + cudaGetErrorString(err__);                           \
+            return B200LK_ERR_CUDA;                                                                   \
+        }                                                                                             \
+    } while (0)
+
+static int fail(b200lk_engine *e, int code, const std::string &msg) {
+    e->err = msg;
+    return code;
+}
+
+template <typename T>
+static int dev_alloc(b200lk_engine *e, T **ptr, size_t count) {
+    cudaError_t err = cudaMalloc((void **)ptr, std::max<size_t>(count, 1) * sizeof(T));
+    if (err != cudaSuccess) {
+        e->err = std::string("cudaMalloc(") + std::to_string(count * sizeof(T)) + " bytes): " + cudaGetErrorString(err);
+        return err == cudaErrorMemoryAllocation ? B200LK_ERR_NOMEM : B200LK_ERR_CUDA;
+    }
+    e->device_bytes += (int64_t)(count * sizeof(T));
+    return 0;
+}
+
+extern "C" int b200lk_abi_version(void) { return B200LK_ABI_VERSION; }
+
+extern "C" const char *b200lk_last_error(const b200lk_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+extern "C" int64_t b200lk_device_bytes(const b200lk_engine *e) { return e->device_bytes; }
+extern "C" int64_t b200lk_launch_count(const b200lk_engine *e) { return e->launches; }
+
+extern "C" void b200lk_destroy(b200lk_engine *e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
+    cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
+    cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
+    cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_result); cudaFree(e->d_counter); cudaFree(e->d_scratch);
+    if (e->h_stage) cudaFreeHost(e->h_stage);
+    if (e->h_result) cudaFreeHost(e->h_result);
+    for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
+    *out = nullptr;
+    if (!cfg || cfg->nstates < 1 || cfg->ncat < 1 || cfg->nmix < 1 || cfg->ntaxa < 2 || cfg->nptn < 1 || cfg->nslots < 1 ||
+        cfg->state_unknown < cfg->nstates || cfg->state_unknown > 255) {
+        g_create_err = "b200lk_create: invalid configuration";
+        return B200LK_ERR_INVALID;
+    }
+    if (cfg->nstates > 64) {
+        g_create_err = "b200lk_create: nstates > 64 not supported by this build";
+        return B200LK_ERR_INVALID;
+    }
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_err = std::string("b200lk_create: no usable CUDA device (") + (ce != cudaSuccess ? cudaGetErrorString(ce) : "count=0 or bad ordinal") +
+                       "); this engine has no CPU fallback";
+        return B200LK_ERR_CUDA;
+    }
+    b200lk_engine *e = new b200lk_engine();
+    e->cfg = *cfg;
+    auto bail = [&](int rc) { g_create_err = e->err; b200lk_destroy(e); return rc; };
+    if (cudaSetDevice(cfg->device) != cudaSuccess) { e->err = "cudaSetDevice failed"; return bail(B200LK_ERR_CUDA); }
+    cudaDeviceProp prop{};
+    cudaGetDeviceProperties(&prop, cfg->device);
+    e->num_sms = prop.multiProcessorCount;
+    const int n = cfg->nstates;
+    e->C = cfg->fused_mix_rate ? cfg->ncat : cfg->ncat * cfg->nmix;   // phylokernelnew.h:1322-1323
+    e->denom = cfg->fused_mix_rate ? 1 : cfg->ncat;                    // :1325
+    e->B = n * e->C;
+    e->S = cfg->safe_numeric ? e->C : 1;
+    e->P = cfg->nptn;
+    e->Ppad = (cfg->nptn + kTile - 1) / kTile * kTile;
+    int rc;
+#define TRY(x) if ((rc = (x)) != 0) return bail(rc)
+    if (cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking) != cudaSuccess) { e->err = "cudaStreamCreate failed"; return bail(B200LK_ERR_CUDA); }
+    e->stream = e->own_stream;
+    for (auto &ev : e->ev) cudaEventCreate(&ev);
+    const long long Ppad = e->Ppad;
+    TRY(dev_alloc(e, &e->d_tips, (size_t)cfg->ntaxa * Ppad));
+    TRY(dev_alloc(e, &e->d_freq, Ppad));
+    TRY(dev_alloc(e, &e->d_invar, Ppad));
+    const size_t n_eval = (size_t)cfg->nmix * n, n_mat = (size_t)cfg->nmix * n * n;
+    const size_t n_tip = (size_t)(cfg->state_unknown + 1) * cfg->nmix * n;
+    const size_t model_doubles = n_eval + 2 * n_mat + cfg->nmix + 2 * cfg->ncat + n_tip + 3 * (size_t)e->B;
+    TRY(dev_alloc(e, &e->d_model, model_doubles));
+    TRY(dev_alloc(e, &e->d_partial, (size_t)cfg->nslots * Ppad * e->B));
+    TRY(dev_alloc(e, &e->d_scale, (size_t)cfg->nslots * Ppad * e->S));
+    TRY(dev_alloc(e, &e->d_theta, (size_t)Ppad * e->B));
+    TRY(dev_alloc(e, &e->d_buffer_scale, Ppad));
+    TRY(dev_alloc(e, &e->d_pattern_lh, Ppad));
+    TRY(dev_alloc(e, &e->d_pattern_scaling, Ppad));
+    TRY(dev_alloc(e, &e->d_pattern_lh_cat, (size_t)Ppad * e->C));
+    TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 3));
+    TRY(dev_alloc(e, &e->d_result, 8));
+    TRY(dev_alloc(e, &e->d_counter, 8));
+#undef TRY
+    if (cudaMallocHost((void **)&e->h_result, 8 * sizeof(double)) != cudaSuccess) { e->err = "cudaMallocHost failed"; return bail(B200LK_ERR_CUDA); }
+    cudaMemsetAsync(e->d_tips, cfg->state_unknown, (size_t)cfg->ntaxa * Ppad, e->stream);
+    cudaMemsetAsync(e->d_freq, 0, sizeof(double) * Ppad, e->stream);
+    cudaMemsetAsync(e->d_invar, 0, sizeof(double) * Ppad, e->stream);
+    cudaMemsetAsync(e->d_scale, 0, sizeof(uint16_t) * (size_t)cfg->nslots * Ppad * e->S, e->stream);
+    cudaMemsetAsync(e->d_model, 0, sizeof(double) * model_doubles, e->stream);
+    e->h_freq.assign(cfg->nptn, 0.0);
+
+    Dev &d = e->d;
+    d.n = n; d.C = e->C; d.ncat = cfg->ncat; d.nmix = cfg->nmix; d.denom = e->denom; d.B = e->B; d.S = e->S;
+    d.su = cfg->state_unknown; d.P = e->P; d.Ppad = Ppad;
+    d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
+    d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
+    double *m = e->d_model;
+    d.eval = m; m += n_eval;
+    d.evec = m; m += n_mat;
+    d.inv_evec = m; m += n_mat;
+    d.mix_weight = m; m += cfg->nmix;
+    d.cat_rate = m; m += cfg->ncat;
+    d.cat_prop = m; m += cfg->ncat;
+    d.tip_lh = m; m += n_tip;
+    d.val = m;
+    d.opinfo = nullptr;
+    d.theta = e->d_theta; d.buffer_scale = e->d_buffer_scale; d.pattern_lh = e->d_pattern_lh;
+    d.pattern_scaling = e->d_pattern_scaling; d.pattern_lh_cat = e->d_pattern_lh_cat;
+
+    // k_partial_info keeps exp(eval*r*t) for the whole block in shared memory
+    size_t info_smem = sizeof(double) * e->B;
+    if (info_smem > 48 * 1024) {
+        if (info_smem > 200 * 1024) { e->err = "ncat_mix*nstates too large for k_partial_info"; return bail(B200LK_ERR_INVALID); }
+        cudaFuncSetAttribute(k_partial_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem);
+    }
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { e->err = "initialisation failed"; return bail(B200LK_ERR_CUDA); }
+    *out = e;
+    return 0;
+}
+
+extern "C" int b200lk_set_stream(b200lk_engine *e, void *cuda_stream) {
+    cudaStreamSynchronize(e->stream);
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return 0;
+}
+
+extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
+    if (schedule < 0 || schedule > 2) return fail(e, B200LK_ERR_INVALID, "schedule must be 0, 1 or 2");
+    e->schedule = schedule;
+    return 0;
+}
+
+extern "C" int b200lk_set_profiling(b200lk_engine *e, int32_t on) { e->profiling = on != 0; return 0; }
+
+extern "C" int b200lk_last_timing(b200lk_engine *e, float ms[5], int32_t launches[3]) {
+    for (int i = 0; i < 5; i++) ms[i] = e->last_ms[i];
+    for (int i = 0; i < 3; i++) launches[i] = e->last_launch[i];
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200lk_set_tip_states(b200lk_engine *e, const uint8_t *states) {
+    cudaSetDevice(e->cfg.device);
+    const size_t total = (size_t)e->cfg.ntaxa * e->P;
+    for (size_t k = 0; k < total; k++)
+        if (states[k] > e->cfg.state_unknown) return fail(e, B200LK_ERR_INVALID, "tip state > STATE_UNKNOWN");
+    CK(cudaMemcpy2DAsync(e->d_tips, e->Ppad, states, e->P, e->P, e->cfg.ntaxa, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int b200lk_set_pattern_freq(b200lk_engine *e, const double *f) {
+    cudaSetDevice(e->cfg.device);
+    e->h_freq.assign(f, f + e->P);
+    CK(cudaMemcpyAsync(e->d_freq, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int b200lk_set_pattern_invar(b200lk_engine *e, const double *f) {
+    cudaSetDevice(e->cfg.device);
+    CK(cudaMemcpyAsync(e->d_invar, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->theta_computed = false;
+    return 0;
+}
+
+extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec,
+                                const double *mix_weight) {
+    cudaSetDevice(e->cfg.device);
+    const int n = e->cfg.nstates, nmix = e->cfg.nmix;
+    CK(cudaMemcpyAsync((void *)e->d.eval, eval, sizeof(double) * nmix * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync((void *)e->d.evec, evec, sizeof(double) * nmix * n * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync((void *)e->d.inv_evec, inv_evec, sizeof(double) * nmix * n * n, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync((void *)e->d.mix_weight, mix_weight, sizeof(double) * nmix, cudaMemcpyHostToDevice, e->stream));
+    const int total = (e->cfg.state_unknown + 1) * nmix * n;
+    k_tip_partial_lh<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d, (double *)e->d.tip_lh, e->cfg.seq_type);
+    e->launches++;
+    CK(cudaGetLastError());
+    // pageable host sources: make sure the copies have consumed them before returning
+    CK(cudaStreamSynchronize(e->stream));
+    e->theta_computed = false;
+    return 0;
+}
+
+extern "C" int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop) {
+    cudaSetDevice(e->cfg.device);
+    CK(cudaMemcpyAsync((void *)e->d.cat_rate, cat_rate, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync((void *)e->d.cat_prop, cat_prop, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->theta_computed = false;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// op staging + partial-likelihood launches
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
+    const size_t e_sz = (size_t)e->B * e->cfg.nstates;
+    const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
+    const size_t need_info = nops * 2 * (e_sz + leaf_sz);
+    if (need_info > e->opinfo_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
+        e->d_opinfo = nullptr; e->opinfo_cap = 0;
+        size_t cap = std::max(need_info, (size_t)4 * 2 * (e_sz + leaf_sz));
+        int rc = dev_alloc(e, &e->d_opinfo, cap);
+        if (rc) return rc;
+        e->opinfo_cap = cap;
+        e->d.opinfo = e->d_opinfo;
+    }
+    if (nops > e->ops_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        cudaFree(e->d_ops); cudaFree(e->d_jobs);
+        if (e->h_stage) cudaFreeHost(e->h_stage);
+        e->d_ops = nullptr; e->d_jobs = nullptr; e->h_stage = nullptr;
+        size_t cap = std::max<size_t>(nops, 16);
+        int rc = dev_alloc(e, &e->d_ops, cap);
+        if (rc) return rc;
+        rc = dev_alloc(e, &e->d_jobs, cap * 2);
+        if (rc) return rc;
+        e->h_stage_cap = cap * (sizeof(DevOp) + 2 * sizeof(ChildJob));
+        CK(cudaMallocHost(&e->h_stage, e->h_stage_cap));
+        e->ops_cap = cap;
+    }
+    return 0;
+}
+
+template <bool SAFE>
+static void launch_partials(b200lk_engine *e, int op_begin, int op_end, int walk, int grid) {
+    const int n = e->cfg.nstates, C = e->C;
+    cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream);
+    if (n == 4 && C == 4 && e->cfg.nmix == 1 && e->cfg.state_unknown < kMaxLeafRows4)
+        k_partials_n4c4<SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
+    else if (n == 4)
+        k_partials_generic<4, SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
+    else if (n == 20)
+        k_partials_generic<20, SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
+    else if (n == 2)
+        k_partials_generic<2, SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
+    else
+        k_partials_generic<0, SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
+    e->launches++;
+    e->last_launch[0]++;
+}
+
+// Enqueue (no sync) everything computePartialLikelihood needs for the op list.
+static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    if (nops <= 0) return 0;
+    int rc = ensure_op_capacity(e, nops);
+    if (rc) return rc;
+    const size_t e_sz = (size_t)e->B * e->cfg.nstates;
+    const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
+    DevOp *hops = (DevOp *)e->h_stage;
+    ChildJob *hjobs = (ChildJob *)((char *)e->h_stage + e->ops_cap * sizeof(DevOp));
+    // the pinned staging buffer may still be in flight from the previous call on this stream
+    CK(cudaStreamSynchronize(e->stream));
+    std::vector<int> level_of_slot(e->cfg.nslots, -1);
+    std::vector<int> level(nops, 0);
+    int max_level = 0;
+    bool ordered_levels = true;
+    for (int k = 0; k < nops; k++) {
+        const b200lk_op &op = ops[k];
+        if (op.dst_slot < 0 || op.dst_slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "op: dst_slot out of range");
+        b200lk_child ch[2] = {op.left, op.right};
+        for (auto &c : ch) {
+            if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
+            else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
+            else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+        }
+        const size_t base = (size_t)k * 2 * (e_sz + leaf_sz);
+        int64_t eoff[2] = {(int64_t)base, (int64_t)(base + e_sz)};
+        int64_t loff[2] = {(int64_t)(base + 2 * e_sz), (int64_t)(base + 2 * e_sz + leaf_sz)};
+        for (int s = 0; s < 2; s++) {
+            hjobs[2 * k + s].length = ch[s].length;
+            hjobs[2 * k + s].e_off = eoff[s];
+            hjobs[2 * k + s].leaf_off = ch[s].kind == 0 ? loff[s] : -1;
+        }
+        int a = 0, b = 1;   // swap so that a single leaf child is `left` (phylokernelnew.h:1395-1405)
+        if (ch[0].kind != 0 && ch[1].kind == 0) { a = 1; b = 0; }
+        DevOp &d = hops[k];
+        d.dst = op.dst_slot;
+        d.ncase = (ch[a].kind == 0 && ch[b].kind == 0) ? 0 : (ch[a].kind == 0 ? 1 : 2);
+        d.lid = ch[a].id; d.rid = ch[b].id;
+        d.eL = eoff[a]; d.eR = eoff[b];
+        d.leafL = ch[a].kind == 0 ? loff[a] : -1;
+        d.leafR = ch[b].kind == 0 ? loff[b] : -1;
+        int lv = 0;
+        for (auto &c : ch) if (c.kind == 1 && level_of_slot[c.id] >= 0) lv = std::max(lv, level_of_slot[c.id] + 1);
+        level[k] = lv;
+        level_of_slot[op.dst_slot] = lv;
+        max_level = std::max(max_level, lv);
+        if (k > 0 && level[k] < level[k - 1]) ordered_levels = false;
+    }
+    int schedule = e->schedule;
+    if (schedule == 0) schedule = 2;
+    // the levelled schedule needs the ops grouped by depth: stable-sort a copy of the staged ops by level
+    std::vector<int> level_start;
+    if (schedule == 1) {
+        if (!ordered_levels) {
+            std::vector<int> idx(nops);
+            for (int k = 0; k < nops; k++) idx[k] = k;
+            std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return level[x] < level[y]; });
+            std::vector<DevOp> tmp(hops, hops + nops);
+            std::vector<int> lv2(nops);
+            for (int k = 0; k < nops; k++) { hops[k] = tmp[idx[k]]; lv2[k] = level[idx[k]]; }
+            level = lv2;
+        }
+        for (int k = 0; k < nops; k++) if (k == 0 || level[k] != level[k - 1]) level_start.push_back(k);
+        level_start.push_back(nops);
+    }
+    CK(cudaMemcpyAsync(e->d_ops, hops, sizeof(DevOp) * nops, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(e->d_jobs, hjobs, sizeof(ChildJob) * 2 * nops, cudaMemcpyHostToDevice, e->stream));
+    k_partial_info<<<2 * nops, 256, sizeof(double) * e->B, e->stream>>>(e->d, e->d_jobs);
+    e->launches++;
+    e->last_launch[0]++;
+    const long long ntiles = e->Ppad / kTile;
+    const int resident = e->num_sms * 4;
+    if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+    if (schedule == 2) {
+        int grid = (int)std::min<long long>(ntiles, resident);
+        if (e->cfg.safe_numeric) launch_partials<true>(e, 0, nops, 1, grid);
+        else launch_partials<false>(e, 0, nops, 1, grid);
+    } else {
+        for (size_t l = 0; l + 1 < level_start.size(); l++) {
+            long long items = ntiles * (level_start[l + 1] - level_start[l]);
+            int grid = (int)std::min<long long>(items, resident);
+            if (e->cfg.safe_numeric) launch_partials<true>(e, level_start[l], level_start[l + 1], 0, grid);
+            else launch_partials<false>(e, level_start[l], level_start[l + 1], 0, grid);
+        }
+    }
+    if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+    e->partials_timed = e->profiling;
+    CK(cudaGetLastError());
+    e->theta_computed = false;   // any partial update invalidates the theta buffer
+    return 0;
+}
+
+static void prof_begin(b200lk_engine *e) {
+    e->last_launch[0] = e->last_launch[1] = e->last_launch[2] = 0;
+    e->partials_timed = false;
+    if (e->profiling) cudaEventRecord(e->ev[0], e->stream);
+}
+static void prof_mark(b200lk_engine *e, int i) {
+    if (e->profiling) cudaEventRecord(e->ev[i], e->stream);
+}
+static void prof_end(b200lk_engine *e, int last) {
+    if (!e->profiling) return;
+    cudaEventSynchronize(e->ev[last]);
+    for (int i = 0; i < 3; i++) e->last_ms[i] = 0.f;
+    for (int i = 1; i <= last; i++) cudaEventElapsedTime(&e->last_ms[i - 1], e->ev[i - 1], e->ev[i]);
+    cudaEventElapsedTime(&e->last_ms[3], e->ev[0], e->ev[last]);
+    e->last_ms[4] = 0.f;
+    if (e->partials_timed) cudaEventElapsedTime(&e->last_ms[4], e->ev[4], e->ev[5]);
+}
+
+extern "C" int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    cudaSetDevice(e->cfg.device);
+    prof_begin(e);
+    int rc = enqueue_partials(e, ops, nops);
+    if (rc) return rc;
+    prof_mark(e, 1);
+    CK(cudaStreamSynchronize(e->stream));
+    prof_end(e, 1);
+    return 0;
+}
+
+static int check_branch(b200lk_engine *e, int node_slot, int dad_kind, int dad_id) {
+    if (node_slot < 0 || node_slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "node_slot out of range");
+    if (dad_kind == 0) { if (dad_id < 0 || dad_id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "dad taxon out of range"); }
+    else if (dad_kind == 1) { if (dad_id < 0 || dad_id >= e->cfg.nslots || dad_id == node_slot) return fail(e, B200LK_ERR_INVALID, "dad slot invalid"); }
+    else return fail(e, B200LK_ERR_INVALID, "dad_kind must be 0 or 1");
+    return 0;
+}
+
+// NaN repair of the reference (phylokernelnew.h:3115-3132, 3374-3383): rare, done on the host copy.
+static int repair_pattern_lh(b200lk_engine *e, bool save_log, double *logl) {
+    std::vector<double> lh(e->P), sc;
+    CK(cudaMemcpy(lh.data(), e->d_pattern_lh, sizeof(double) * e->P, cudaMemcpyDeviceToHost));
+    if (!save_log) {
+        sc.resize(e->P);
+        CK(cudaMemcpy(sc.data(), e->d_pattern_scaling, sizeof(double) * e->P, cudaMemcpyDeviceToHost));
+    }
+    double tree_lh = 0.0;
+    for (long long p = 0; p < e->P; p++) {
+        double ptn_lh = save_log ? lh[p] : std::log(lh[p]) + sc[p];
+        if (!std::isfinite(ptn_lh)) {
+            if (save_log) lh[p] = kLogScalingThreshold * 4;
+            else { lh[p] = 1.0; sc[p] = kLogScalingThreshold * 4; }
+            ptn_lh = kLogScalingThreshold * 4;
+        }
+        tree_lh += ptn_lh * e->h_freq[p];
+    }
+    CK(cudaMemcpy(e->d_pattern_lh, lh.data(), sizeof(double) * e->P, cudaMemcpyHostToDevice));
+    if (!save_log) CK(cudaMemcpy(e->d_pattern_scaling, sc.data(), sizeof(double) * e->P, cudaMemcpyHostToDevice));
+    *logl = tree_lh;
+    return B200LK_WARN_UNDERFLOW;
+}
+
+extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                  int32_t dad_id, double length, int32_t save_log_value, double *logl) {
+    cudaSetDevice(e->cfg.device);
+    int rc = check_branch(e, node_slot, dad_kind, dad_id);
+    if (rc) return rc;
+    prof_begin(e);
+    rc = enqueue_partials(e, ops, nops);
+    if (rc) return rc;
+    prof_mark(e, 1);
+    const int nblocks = (int)(e->Ppad / kTile);
+    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0);
+    if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red);
+    else k_root<false><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red);
+    k_final_reduce<1><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
+    e->launches += 3;
+    e->last_launch[1] += 3;
+    prof_mark(e, 2);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    prof_end(e, 2);
+    *logl = e->h_result[0];
+    if (!std::isfinite(*logl)) return repair_pattern_lh(e, save_log_value != 0, logl);
+    return 0;
+}
+
+static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_id) {
+    const int nblocks = (int)(e->Ppad / kTile);
+    if (e->cfg.safe_numeric) k_theta<true><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id);
+    else k_theta<false><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id);
+    e->launches++;
+    e->last_launch[2]++;
+    e->theta_computed = true;
+    return 0;
+}
+
+static void enqueue_derv(b200lk_engine *e, double length) {
+    const int nblocks = (int)(e->Ppad / kTile);
+    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 1);
+    if (e->B == 16) k_derv<16><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    else if (e->B == 80) k_derv<80><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    else k_derv<0><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    k_final_reduce<2><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
+    e->launches += 3;
+    e->last_launch[2] += 3;
+}
+
+extern "C" int b200lk_theta_reset(b200lk_engine *e) { e->theta_computed = false; return 0; }
+
+extern "C" int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                  int32_t dad_id, double length, double *df, double *ddf) {
+    cudaSetDevice(e->cfg.device);
+    int rc = check_branch(e, node_slot, dad_kind, dad_id);
+    if (rc) return rc;
+    prof_begin(e);
+    if (nops > 0) e->theta_computed = false;
+    rc = enqueue_partials(e, ops, nops);
+    if (rc) return rc;
+    prof_mark(e, 1);
+    prof_mark(e, 2);
+    if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
+    enqueue_derv(e, length);
+    prof_mark(e, 3);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_result, e->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    prof_end(e, 3);
+    *df = e->h_result[0];
+    *ddf = e->h_result[1];
+    if (!std::isfinite(*df)) {   // phylokernelnew.h:2629-2632 (the NORM_LH outError at :2577 is the caller's policy)
+        *df = *ddf = 0.0;
+        return B200LK_WARN_DERV_UNDERFLOW;
+    }
+    return 0;
+}
+
+extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *logl) {
+    cudaSetDevice(e->cfg.device);
+    if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
+    prof_begin(e);
+    prof_mark(e, 1);
+    const int nblocks = (int)(e->Ppad / kTile);
+    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0);
+    if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    else if (e->B == 80) k_from_buffer<80><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    else k_from_buffer<0><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
+    k_final_reduce<1><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
+    e->launches += 3;
+    e->last_launch[1] += 3;
+    prof_mark(e, 2);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    prof_end(e, 2);
+    *logl = e->h_result[0];
+    if (!std::isfinite(*logl)) return repair_pattern_lh(e, true, logl);
+    return 0;
+}
+
+// Optimization::minimizeNewton (utils/optimization.cpp:422-499) with f = -df, f' = -ddf (computeFuncDerv,
+// tree/phylotree.cpp:2529-2536), evaluated on the resident theta buffer.
+extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                    int32_t dad_id, double x1, double xguess, double x2, double xacc, int32_t maxNRStep,
+                                    double *length_out, int32_t *steps_out) {
+    cudaSetDevice(e->cfg.device);
+    int rc = check_branch(e, node_slot, dad_kind, dad_id);
+    if (rc) return rc;
+    if (nops > 0) e->theta_computed = false;
+    rc = enqueue_partials(e, ops, nops);
+    if (rc) return rc;
+    if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
+    int nsteps = 0;
+    auto func_derv = [&](double x, double &f, double &df) -> int {
+        enqueue_derv(e, x);
+        cudaError_t ce = cudaMemcpyAsync(e->h_result, e->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
+        f = -e->h_result[0];
+        df = -e->h_result[1];
+        nsteps++;
+        return 0;
+    };
+    double df, dx, dxold, f, temp, xh, xl, rts, rts_old;
+    rts = xguess;
+    if (rts < x1) rts = x1;
+    if (rts > x2) rts = x2;
+    auto done = [&](double x) { *length_out = x; if (steps_out) *steps_out = nsteps; return 0; };
+    if ((rc = func_derv(rts, f, df))) return rc;
+    if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; if (steps_out) *steps_out = nsteps; return B200LK_WARN_DERV_UNDERFLOW; }
+    if (df >= 0.0 && std::fabs(f) < xacc) return done(rts);
+    if (f < 0.0) { xl = rts; xh = x2; } else { xh = rts; xl = x1; }
+    dx = dxold = std::fabs(xh - xl);
+    for (int j = 1; j <= maxNRStep; j++) {
+        rts_old = rts;
+        if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)) {
+            dxold = dx;
+            dx = 0.5 * (xh - xl);
+            rts = xl + dx;
+            if (xl == rts) return done(rts);
+        } else {
+            dxold = dx;
+            dx = f / df;
+            temp = rts;
+            rts -= dx;
+            if (temp == rts) return done(rts);
+        }
+        if (std::fabs(dx) < xacc || (j == maxNRStep)) return done(rts_old);
+        if ((rc = func_derv(rts, f, df))) return rc;
+        if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; if (steps_out) *steps_out = nsteps; return B200LK_WARN_DERV_UNDERFLOW; }
+        if (df > 0.0 && std::fabs(f) < xacc) return done(rts);
+        if (f < 0.0) xl = rts;
+        else if (f > 0.0) xh = rts;
+    }
+    (void)dxold;
+    return done(rts);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// read-backs
+// ---------------------------------------------------------------------------------------------------------------
+static int ensure_scratch(b200lk_engine *e, size_t bytes) {
+    if (bytes <= e->scratch_cap) return 0;
+    if (e->d_scratch) { cudaFree(e->d_scratch); e->device_bytes -= (int64_t)e->scratch_cap; }
+    e->d_scratch = nullptr; e->scratch_cap = 0;
+    int rc = dev_alloc(e, (char **)&e->d_scratch, bytes);
+    if (rc) return rc;
+    e->scratch_cap = bytes;
+    return 0;
+}
+
+static int read_interleaved_f64(b200lk_engine *e, const double *src, int W, double *out) {
+    cudaSetDevice(e->cfg.device);
+    const size_t total = (size_t)e->P * W;
+    int rc = ensure_scratch(e, total * sizeof(double));
+    if (rc) return rc;
+    k_deinterleave_f64<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(src, e->d_scratch, e->P, W);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+static int read_plain(b200lk_engine *e, const void *src, size_t bytes, void *out) {
+    cudaSetDevice(e->cfg.device);
+    CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+extern "C" int b200lk_get_pattern_lh(b200lk_engine *e, double *out) { return read_plain(e, e->d_pattern_lh, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_pattern_scaling(b200lk_engine *e, double *out) { return read_plain(e, e->d_pattern_scaling, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_buffer_scale_all(b200lk_engine *e, double *out) { return read_plain(e, e->d_buffer_scale, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_pattern_lh_cat, e->C, out); }
+extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_theta, e->B, out); }
+extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
+    if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
+    return read_interleaved_f64(e, e->d_partial + (size_t)slot * e->d.slot_stride, e->B, out);
+}
+extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out) {
+    if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
+    const uint16_t *src = e->d_scale + (size_t)slot * e->d.scale_stride;
+    if (!e->cfg.safe_numeric) return read_plain(e, src, sizeof(uint16_t) * e->P, out);
+    cudaSetDevice(e->cfg.device);
+    const size_t total = (size_t)e->P * e->C;
+    int rc = ensure_scratch(e, total * sizeof(uint16_t));
+    if (rc) return rc;
+    k_deinterleave_u16<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(src, (uint16_t *)e->d_scratch, e->P, e->C);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+extern "C" int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out) {
+    return read_plain(e, e->d.tip_lh, sizeof(double) * (e->cfg.state_unknown + 1) * e->cfg.nmix * e->cfg.nstates, out);
+}
+extern "C" void *b200lk_pattern_lh_dev(b200lk_engine *e) { return e->d_pattern_lh; }

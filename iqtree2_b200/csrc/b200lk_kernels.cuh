@@ -1,0 +1,650 @@
+// b200lk_kernels.cuh — hand-written sm_100a kernels of the B200 likelihood engine.
+//
+// Device data layout: every per-pattern vector is WARP-INTERLEAVED, i.e. the reference's
+// SIMD layout (tree/phylokernelnew.h:1914-1916) with V = 32:
+//     partial(slot, p, k) = partial[slot*Ppad*B + (p/32)*B*32 + k*32 + p%32]      k = c*n + i
+// so that a warp working on 32 consecutive patterns reads/writes 256 contiguous bytes per element index k,
+// transition matrices are warp-uniform operands, and per-pattern reductions (scaling max, lh, df, ddf) never
+// leave the thread.  Patterns are padded to a multiple of kTile with all-unknown states and zero frequency.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200lk {
+
+constexpr int kWarp = 32;
+constexpr int kTile = 128;                                   // patterns per CTA tile == threads per CTA
+constexpr double kScalingThreshold = 8.636168555094444625386e-78;   // tree/phylotree.h:77  (2^-256)
+constexpr double kLogScalingThreshold = -177.4456782233459932741;   // tree/phylotree.h:80
+constexpr double kTwo256 = 0x1p256;                          // ldexp(x, SCALING_THRESHOLD_EXP)
+
+// one TraversalInfo after host-side normalisation (a single leaf child is always `left`,
+// tree/phylokernelnew.h:1395-1405)
+struct DevOp {
+    int32_t dst;     // destination CLV slot
+    int32_t ncase;   // 0 tip-tip, 1 tip-inner, 2 inner-inner
+    int32_t lid;     // taxon row (tip) or slot
+    int32_t rid;
+    int64_t eL, eR;        // offsets (in doubles) of echild[c][x][i] blocks inside opinfo
+    int64_t leafL, leafR;  // offsets of partial_lh_leaves[state][c][x] tables, -1 if the child is internal
+};
+
+struct ChildJob {
+    double length;
+    int64_t e_off;
+    int64_t leaf_off;  // -1: internal child, no table
+};
+
+struct Dev {
+    int n, C, ncat, nmix, denom, B, S, su;
+    long long P, Ppad;
+    long long slot_stride;   // Ppad * B   doubles per CLV slot
+    long long scale_stride;  // Ppad * S   uint16 per slot
+    double *partial;
+    uint16_t *scale;
+    const uint8_t *tips;     // [ntaxa][Ppad]
+    const double *freq, *invar;
+    const double *eval, *evec, *inv_evec, *tip_lh, *cat_rate, *cat_prop, *mix_weight;
+    double *opinfo;
+    double *theta, *buffer_scale, *pattern_lh, *pattern_scaling, *pattern_lh_cat;
+    double *val;             // val0 | val1 | val2, B doubles each
+};
+
+__device__ __forceinline__ long long pbase(long long p, int width) {
+    return (p >> 5) * (long long)width * kWarp + (p & 31);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// computePartialInfo (tree/phylokernelnew.h:900-1110): echild = evec * exp(eval * rate_c * len) and, for leaf
+// children, the per-state lookup table.  One CTA per (op, child).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_partial_info(Dev D, const ChildJob *jobs) {
+    extern __shared__ double s_exp[];  // [C][n]
+    const ChildJob job = jobs[blockIdx.x];
+    const int n = D.n, C = D.C, B = D.B, nn = D.n * D.n;
+    for (int k = threadIdx.x; k < B; k += blockDim.x) {
+        int c = k / n, i = k - c * n;
+        int m = c / D.denom, r = c % D.ncat;
+        double len_child = D.cat_rate[r] * job.length;           // :1017
+        s_exp[k] = exp(D.eval[m * n + i] * len_child);           // :1022
+    }
+    __syncthreads();
+    double *E = D.opinfo + job.e_off;
+    for (int k = threadIdx.x; k < C * nn; k += blockDim.x) {
+        int c = k / nn, rem = k - c * nn;
+        int i = rem % n;
+        int m = c / D.denom;
+        E[k] = D.evec[m * nn + rem] * s_exp[c * n + i];          // :1027
+    }
+    if (job.leaf_off < 0) return;
+    __syncthreads();
+    double *leaf = D.opinfo + job.leaf_off;
+    const int tip_block = n * D.nmix;
+    const int total = (D.su + 1) * B;
+    for (int k = threadIdx.x; k < total; k += blockDim.x) {
+        int state = k / B, cx = k - state * B;
+        if (state == D.su) { leaf[k] = 1.0; continue; }          // :1052-1055
+        int c = cx / n;
+        int m = c / D.denom;
+        const double *ep = E + (long long)cx * n;
+        const double *tip = D.tip_lh + state * tip_block + m * n;
+        double v;
+        if ((n & 3) == 0) {   // Vec4d lane accumulators + horizontal_add (:1036-1051)
+            double a0 = ep[0] * tip[0], a1 = ep[1] * tip[1], a2 = ep[2] * tip[2], a3 = ep[3] * tip[3];
+            for (int i = 4; i < n; i += 4) {
+                a0 = fma(ep[i], tip[i], a0); a1 = fma(ep[i + 1], tip[i + 1], a1);
+                a2 = fma(ep[i + 2], tip[i + 2], a2); a3 = fma(ep[i + 3], tip[i + 3], a3);
+            }
+            v = (a0 + a1) + (a2 + a3);
+        } else {              // scalar branch (:1085-1099)
+            v = ep[0] * tip[0];
+            for (int i = 1; i < n; i++) v += ep[i] * tip[i];
+        }
+        leaf[k] = v;
+    }
+}
+
+// tip_partial_lh[state][m][i] = sum_j inv_evec_m[i][j] * ind_state[j]  (tree/phylotreesse.cpp:367-375,
+// model/modelsubst.cpp:182-207, modeldna.cpp:462-475, modelprotein.cpp:1149-1166)
+__global__ void k_tip_partial_lh(Dev D, double *tip_lh, int seq_type) {
+    const int n = D.n;
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    int total = (D.su + 1) * D.nmix * n;
+    if (idx >= total) return;
+    int state = idx / (D.nmix * n);
+    int rem = idx - state * D.nmix * n;
+    int m = rem / n, i = rem - m * n;
+    const double *iv = D.inv_evec + (long long)m * n * n + i * n;
+    double acc = 0.0;
+    for (int j = 0; j < n; j++) {
+        double ind;
+        if (state < n) ind = (j == state) ? 1.0 : 0.0;
+        else if (seq_type == 1 && state < 18) ind = ((state - n + 1) >> j) & 1 ? 1.0 : 0.0;
+        else if (seq_type == 2 && state < n + 3) {
+            const int a0 = (state - n == 0) ? 2 : (state - n == 1) ? 5 : 9;
+            ind = (j == a0 || j == a0 + 1) ? 1.0 : 0.0;
+        } else ind = 1.0;
+        acc += iv[j] * ind;
+    }
+    tip_lh[idx] = acc;
+}
+
+// val0/val1/val2 (tree/phylokernelnew.h:2322-2358, 2714-2745)
+__global__ void k_vals(Dev D, double length, int with_derv) {
+    const int n = D.n;
+    for (int k = threadIdx.x; k < D.B; k += blockDim.x) {
+        int c = k / n, i = k - c * n;
+        int m = c / D.denom, r = c % D.ncat;
+        double prop = D.cat_prop[r] * D.mix_weight[m];
+        if (with_derv) {
+            double cof = D.eval[m * n + i] * D.cat_rate[r];
+            double val = exp(cof * length) * prop;
+            double v1 = cof * val;
+            D.val[k] = val;
+            D.val[D.B + k] = v1;
+            D.val[2 * D.B + k] = cof * v1;
+        } else {
+            double len = D.cat_rate[r] * length;
+            D.val[k] = exp(D.eval[m * n + i] * len) * prop;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// work distribution shared by the partial-likelihood kernels.
+//   walk = 1 : "pattern-tile walker" — a work item is one tile of kTile patterns; the CTA walks the whole
+//              post-order op list for it (each thread keeps its pattern, so a child CLV written at op k is re-read
+//              by the same thread at its parent and is still L2-resident); this is the packet loop of the
+//              reference (tree/phylokernelnew.h:1270-1277) with the packet shrunk to a tile.
+//   walk = 0 : "levelled" — ops[op_begin, op_end) are mutually independent (one tree depth); a work item is
+//              (tile, op).
+// ------------------------------------------------------------------------------------------------------------
+struct WorkItem { long long tile; int o0, o1; };
+
+__device__ __forceinline__ bool next_item(unsigned long long *counter, long long *s_item, long long ntiles, int op_begin,
+                                          int op_end, int walk, WorkItem &w) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_item = (long long)atomicAdd(counter, 1ULL);
+    __syncthreads();
+    long long item = *s_item;
+    int nops = op_end - op_begin;
+    long long nitems = walk ? ntiles : ntiles * nops;
+    if (item >= nitems) return false;
+    if (walk) { w.tile = item; w.o0 = op_begin; w.o1 = op_end; }
+    else { w.tile = item / nops; w.o0 = op_begin + (int)(item - w.tile * nops); w.o1 = w.o0 + 1; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Generic partial-likelihood kernel (any nstates, any ncat_mix, NORM_LH or SAFE_LH): thread per pattern, matrices
+// read as warp-uniform loads from the per-op info block.  computePartialLikelihood{,Generic}SIMD, binary nodes
+// (tree/phylokernelnew.h:1632-2032).
+// ------------------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ double dot4acc(const double *__restrict__ m, const double *v, int n) {
+    // 4 lane accumulators as the reference's N%4==0 paths; tail handled sequentially
+    const int nn = NT ? NT : n;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int i = 0;
+#pragma unroll
+    for (; i + 3 < nn; i += 4) {
+        a0 = fma(__ldg(m + i), v[i], a0);
+        a1 = fma(__ldg(m + i + 1), v[i + 1], a1);
+        a2 = fma(__ldg(m + i + 2), v[i + 2], a2);
+        a3 = fma(__ldg(m + i + 3), v[i + 3], a3);
+    }
+    double s = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (; i < nn; i++) s = fma(__ldg(m + i), v[i], s);
+    return s;
+}
+
+template <int NT, bool SAFE>
+__device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op, long long p) {
+    constexpr int NMAX = NT ? NT : 64;
+    const int n = NT ? NT : D.n;
+    const int C = D.C, B = D.B;
+    const long long pb = pbase(p, B);
+    const long long sb = SAFE ? pbase(p, C) : p;
+    double *out = D.partial + (long long)op.dst * D.slot_stride + pb;
+    uint16_t *osc = D.scale + (long long)op.dst * D.scale_stride + sb;
+    const double *Lp = (op.ncase == 2) ? D.partial + (long long)op.lid * D.slot_stride + pb : nullptr;
+    const double *Rp = (op.ncase >= 1) ? D.partial + (long long)op.rid * D.slot_stride + pb : nullptr;
+    const uint16_t *lsc = (op.ncase == 2) ? D.scale + (long long)op.lid * D.scale_stride + sb : nullptr;
+    const uint16_t *rsc = (op.ncase >= 1) ? D.scale + (long long)op.rid * D.scale_stride + sb : nullptr;
+    const double *leafL = nullptr, *leafR = nullptr;
+    if (op.ncase <= 1) leafL = D.opinfo + op.leafL + (long long)D.tips[(long long)op.lid * D.Ppad + p] * B;
+    if (op.ncase == 0) leafR = D.opinfo + op.leafR + (long long)D.tips[(long long)op.rid * D.Ppad + p] * B;
+    const double *eL = D.opinfo + op.eL, *eR = D.opinfo + op.eR;
+    const bool check = (op.ncase != 0) && (D.invar[p] == 0.0);   // tip-tip never rescales (:1640)
+    double lh_max = 0.0;
+    unsigned norm_scale = 0;
+    if (!SAFE) norm_scale = (lsc ? lsc[0] : 0u) + (rsc ? rsc[0] : 0u);
+
+    double lv[NMAX], rv[NMAX], tmp[NMAX];
+    for (int c = 0; c < C; c++) {
+        const int m = c / D.denom;
+        const double *inv = D.inv_evec + (long long)m * n * n;
+        if (Lp) {
+#pragma unroll
+            for (int i = 0; i < n; i++) lv[i] = Lp[(long long)(c * n + i) * kWarp];
+        }
+        if (Rp) {
+#pragma unroll
+            for (int i = 0; i < n; i++) rv[i] = Rp[(long long)(c * n + i) * kWarp];
+        }
+#pragma unroll
+        for (int x = 0; x < n; x++) {
+            double a = Lp ? dot4acc<NT>(eL + (long long)(c * n + x) * n, lv, n) : leafL[c * n + x];
+            double b = Rp ? dot4acc<NT>(eR + (long long)(c * n + x) * n, rv, n) : leafR[c * n + x];
+            tmp[x] = a * b;
+        }
+        double cmax = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double v = dot4acc<NT>(inv + i * n, tmp, n);
+            lv[i] = v;   // reuse as output staging
+            cmax = fmax(cmax, fabs(v));
+        }
+        if (SAFE) {
+            unsigned sc = (lsc ? lsc[c * kWarp] : 0u) + (rsc ? rsc[c * kWarp] : 0u);
+            if (check && cmax < kScalingThreshold) {
+#pragma unroll
+                for (int i = 0; i < n; i++) lv[i] *= kTwo256;
+                sc += 1;
+            }
+            osc[c * kWarp] = (uint16_t)sc;
+        } else {
+            lh_max = fmax(lh_max, cmax);
+        }
+#pragma unroll
+        for (int i = 0; i < n; i++) out[(long long)(c * n + i) * kWarp] = lv[i];
+    }
+    if (!SAFE) {
+        if (check && lh_max < kScalingThreshold) {
+            for (int k = 0; k < B; k++) out[(long long)k * kWarp] *= kTwo256;   // rare path: re-scale own output
+            norm_scale += 1;
+        }
+        osc[0] = (uint16_t)norm_scale;
+    }
+}
+
+template <int NT, bool SAFE>
+__global__ void __launch_bounds__(kTile) k_partials_generic(Dev D, const DevOp *ops, int op_begin, int op_end, int walk,
+                                                            unsigned long long *counter) {
+    __shared__ long long s_item;
+    const long long ntiles = D.Ppad / kTile;
+    WorkItem w;
+    while (next_item(counter, &s_item, ntiles, op_begin, op_end, walk, w)) {
+        const long long p = w.tile * kTile + threadIdx.x;
+        for (int o = w.o0; o < w.o1; o++) process_op_generic<NT, SAFE>(D, ops[o], p);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 4-state x 4-category kernel (GTR+G4 and every DNA model with 4 rate categories): bandwidth-bound.
+// Per op the CTA stages echild(left,right) [4][4][4] and the leaf lookup tables in shared memory; each thread owns
+// one pattern: 32 coalesced 8-byte loads (2 children x 16), 192 FP64 FMA-class ops against warp-uniform shared
+// operands (LDS.128 broadcasts), 16 coalesced stores + one uint16 scale count.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kMaxLeafRows4 = 19;   // DNA: states 0..18 (alignment/alignment.cpp:738)
+
+__device__ __forceinline__ double dotq(const double2 *m, double v0, double v1, double v2, double v3) {
+    // productVecMat / dotProductDualVec N==4 form: fma(a1,b1,a0*b0) + fma(a3,b3,a2*b2)  (:235, :335)
+    double2 m01 = m[0], m23 = m[1];
+    return fma(m01.y, v1, m01.x * v0) + fma(m23.y, v3, m23.x * v2);
+}
+
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile, 4) k_partials_n4c4(Dev D, const DevOp *ops, int op_begin, int op_end, int walk,
+                                                           unsigned long long *counter) {
+    __shared__ __align__(16) double s_e[2][64];                       // echild left | right : [c][x][i]
+    __shared__ __align__(16) double s_leaf[2][kMaxLeafRows4 * 16];    // [state][c][x]
+    __shared__ __align__(16) double s_inv[16];                        // inv_evec[i][x]
+    __shared__ long long s_item;
+    const int tid = threadIdx.x;
+    if (tid < 16) s_inv[tid] = D.inv_evec[tid];
+    const long long ntiles = D.Ppad / kTile;
+    const int nleaf = (D.su + 1) * 16;
+    WorkItem w;
+    while (next_item(counter, &s_item, ntiles, op_begin, op_end, walk, w)) {
+        const long long p = w.tile * kTile + tid;
+        const long long pb = pbase(p, 16);
+        const long long sb = SAFE ? pbase(p, 4) : p;
+        const double invar = D.invar[p];
+        for (int o = w.o0; o < w.o1; o++) {
+            const DevOp op = ops[o];
+            __syncthreads();   // previous op's readers of s_e/s_leaf are done
+            if (tid < 64) s_e[0][tid] = D.opinfo[op.eL + tid];
+            else s_e[1][tid - 64] = D.opinfo[op.eR + tid - 64];
+            if (op.ncase <= 1)
+                for (int k = tid; k < nleaf; k += kTile) s_leaf[0][k] = D.opinfo[op.leafL + k];
+            if (op.ncase == 0)
+                for (int k = tid; k < nleaf; k += kTile) s_leaf[1][k] = D.opinfo[op.leafR + k];
+            __syncthreads();
+
+            double L[16], R[16], out[16];
+            unsigned sc[SAFE ? 4 : 1];
+            if (op.ncase == 2) {
+                const double *Lp = D.partial + (long long)op.lid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 16; k++) L[k] = Lp[k * kWarp];
+            }
+            if (op.ncase >= 1) {
+                const double *Rp = D.partial + (long long)op.rid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 16; k++) R[k] = Rp[k * kWarp];
+            }
+            // scale_num of the children (:1640, :1753-1756, :1926-1931, :1949)
+#pragma unroll
+            for (int c = 0; c < (SAFE ? 4 : 1); c++) {
+                unsigned s = 0;
+                if (op.ncase == 2) s += D.scale[(long long)op.lid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+                if (op.ncase >= 1) s += D.scale[(long long)op.rid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+                sc[c] = s;
+            }
+            const double *tl = nullptr, *tr = nullptr;
+            if (op.ncase <= 1) tl = &s_leaf[0][(int)D.tips[(long long)op.lid * D.Ppad + p] * 16];
+            if (op.ncase == 0) tr = &s_leaf[1][(int)D.tips[(long long)op.rid * D.Ppad + p] * 16];
+
+            const double2 *eLq = reinterpret_cast<const double2 *>(s_e[0]);
+            const double2 *eRq = reinterpret_cast<const double2 *>(s_e[1]);
+            const double2 *invq = reinterpret_cast<const double2 *>(s_inv);
+            double lh_max = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double tmp[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    double a, b;
+                    if (op.ncase == 2) a = dotq(eLq + (c * 4 + x) * 2, L[c * 4], L[c * 4 + 1], L[c * 4 + 2], L[c * 4 + 3]);
+                    else a = tl[c * 4 + x];
+                    if (op.ncase >= 1) b = dotq(eRq + (c * 4 + x) * 2, R[c * 4], R[c * 4 + 1], R[c * 4 + 2], R[c * 4 + 3]);
+                    else b = tr[c * 4 + x];
+                    tmp[x] = a * b;
+                }
+                double cmax = 0.0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    double v = dotq(invq + i * 2, tmp[0], tmp[1], tmp[2], tmp[3]);
+                    out[c * 4 + i] = v;
+                    cmax = fmax(cmax, fabs(v));
+                }
+                if (SAFE) {
+                    if (op.ncase != 0 && cmax < kScalingThreshold && invar == 0.0) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) out[c * 4 + i] *= kTwo256;
+                        sc[c] += 1;
+                    }
+                } else lh_max = fmax(lh_max, cmax);
+            }
+            if (!SAFE && op.ncase != 0 && lh_max < kScalingThreshold && invar == 0.0) {
+#pragma unroll
+                for (int k = 0; k < 16; k++) out[k] *= kTwo256;
+                sc[0] += 1;
+            }
+            double *Op = D.partial + (long long)op.dst * D.slot_stride + pb;
+#pragma unroll
+            for (int k = 0; k < 16; k++) Op[k * kWarp] = out[k];
+#pragma unroll
+            for (int c = 0; c < (SAFE ? 4 : 1); c++)
+                D.scale[(long long)op.dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)sc[c];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// block reduction of up to 3 doubles per thread into red[blockIdx.x*3 + j]; a 1-CTA kernel sums the per-block
+// values in index order, so results are bit-reproducible for a given pattern count.
+// ------------------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red) {
+    __shared__ double s_red[NV][32];
+#pragma unroll
+    for (int j = 0; j < NV; j++)
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v[j] += __shfl_down_sync(0xffffffffu, v[j], off);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (lane == 0)
+#pragma unroll
+        for (int j = 0; j < NV; j++) s_red[j][wid] = v[j];
+    __syncthreads();
+    if (wid == 0) {
+        const int nw = blockDim.x >> 5;
+#pragma unroll
+        for (int j = 0; j < NV; j++) {
+            double x = lane < nw ? s_red[j][lane] : 0.0;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if (lane == 0) red[(long long)blockIdx.x * NV + j] = x;
+        }
+    }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(256) k_final_reduce(const double *red, int nblocks, double *result) {
+    __shared__ double s[NV][256];
+    double acc[NV];
+#pragma unroll
+    for (int j = 0; j < NV; j++) acc[j] = 0.0;
+    // fixed assignment: thread t sums blocks t, t+256, ... in order
+    for (int b = threadIdx.x; b < nblocks; b += 256)
+#pragma unroll
+        for (int j = 0; j < NV; j++) acc[j] += red[(long long)b * NV + j];
+#pragma unroll
+    for (int j = 0; j < NV; j++) s[j][threadIdx.x] = acc[j];
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off)
+#pragma unroll
+            for (int j = 0; j < NV; j++) s[j][threadIdx.x] += s[j][threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+#pragma unroll
+        for (int j = 0; j < NV; j++) result[j] = s[j][0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// computeLikelihoodBranch{,Generic}SIMD root stage (tree/phylokernelnew.h:2753-3104): per-pattern likelihood across
+// the evaluation branch, _pattern_lh / _pattern_lh_cat, and the frequency-weighted sum.
+// ------------------------------------------------------------------------------------------------------------
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red) {
+    const int n = D.n, C = D.C, B = D.B;
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long pb = pbase(p, B), cb = pbase(p, C);
+    const long long sb = SAFE ? cb : p;
+    const double *dad = D.partial + (long long)node_slot * D.slot_stride + pb;       // dad_branch->partial_lh
+    const uint16_t *dsc = D.scale + (long long)node_slot * D.scale_stride + sb;
+    const double *node = nullptr, *tip = nullptr;
+    const uint16_t *nsc = nullptr;
+    if (dad_kind == 1) {
+        node = D.partial + (long long)dad_id * D.slot_stride + pb;
+        nsc = D.scale + (long long)dad_id * D.scale_stride + sb;
+    } else {
+        tip = D.tip_lh + (long long)D.tips[(long long)dad_id * D.Ppad + p] * (n * D.nmix);
+    }
+    double *lh_cat = D.pattern_lh_cat + cb;
+    double lh_ptn = 0.0;
+    unsigned min_scale = 0xffffffffu;
+    for (int c = 0; c < C; c++) {
+        const double *val = D.val + c * n;
+        const double *tp = tip ? tip + (c / D.denom) * n : nullptr;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int i = 0;
+        for (; i + 3 < n; i += 4) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                double f = __ldg(val + i + j) * (node ? node[(long long)(c * n + i + j) * kWarp] : __ldg(tp + i + j));
+                double d = dad[(long long)(c * n + i + j) * kWarp];
+                if (j == 0) a0 = fma(f, d, a0); else if (j == 1) a1 = fma(f, d, a1);
+                else if (j == 2) a2 = fma(f, d, a2); else a3 = fma(f, d, a3);
+            }
+        }
+        double s = (a0 + a1) + (a2 + a3);
+        for (; i < n; i++) {
+            double f = __ldg(val + i) * (node ? node[(long long)(c * n + i) * kWarp] : __ldg(tp + i));
+            s = fma(f, dad[(long long)(c * n + i) * kWarp], s);
+        }
+        if (SAFE) {
+            unsigned sc = dsc[c * kWarp] + (nsc ? nsc[c * kWarp] : 0u);
+            min_scale = min(min_scale, sc);
+            lh_cat[c * kWarp] = s;       // rescaled in the second pass
+        } else {
+            lh_cat[c * kWarp] = s;
+            lh_ptn += s;
+        }
+    }
+    double vc_min_scale;
+    if (SAFE) {
+        // align categories to the minimum scale count (:2891-2915, :3028-3053), then sumVec
+        double v0 = 0, v1 = 0, v2 = 0, v3 = 0, tail = 0;
+        const int c4 = C & ~3;
+        for (int c = 0; c < C; c++) {
+            unsigned sc = dsc[c * kWarp] + (nsc ? nsc[c * kWarp] : 0u);
+            double x = lh_cat[c * kWarp];
+            if (sc == min_scale + 1) x *= kScalingThreshold;
+            else if (sc > min_scale + 1) x = 0.0;
+            lh_cat[c * kWarp] = x;
+            if (c < c4) { if ((c & 3) == 0) v0 += x; else if ((c & 3) == 1) v1 += x; else if ((c & 3) == 2) v2 += x; else v3 += x; }
+            else tail += x;
+        }
+        v0 += v2; v1 += v3; v0 += v1;
+        lh_ptn = (c4 ? v0 : 0.0) + tail;
+        vc_min_scale = (double)min_scale;
+    } else {
+        vc_min_scale = (double)(dsc[0] + (nsc ? nsc[0] : 0u));
+    }
+    vc_min_scale *= kLogScalingThreshold;
+    lh_ptn = fabs(lh_ptn) + D.invar[p];
+    double lg = log(lh_ptn) + vc_min_scale;
+    double acc[1] = {0.0};
+    if (p < D.P) {
+        if (save_log) D.pattern_lh[p] = lg;
+        else { D.pattern_lh[p] = lh_ptn; D.pattern_scaling[p] = vc_min_scale; }
+        acc[0] = lg * D.freq[p];
+    }
+    block_reduce_store<1>(acc, red);
+}
+
+// computeLikelihoodBuffer{,Generic}SIMD (tree/phylokernelnew.h:2091-2230): theta_all and buffer_scale_all
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_kind, int dad_id) {
+    const int n = D.n, C = D.C, B = D.B;
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long pb = pbase(p, B);
+    const long long sb = SAFE ? pbase(p, C) : p;
+    const double *dad = D.partial + (long long)node_slot * D.slot_stride + pb;
+    const uint16_t *dsc = D.scale + (long long)node_slot * D.scale_stride + sb;
+    const double *node = nullptr, *tip = nullptr;
+    const uint16_t *nsc = nullptr;
+    if (dad_kind == 1) {
+        node = D.partial + (long long)dad_id * D.slot_stride + pb;
+        nsc = D.scale + (long long)dad_id * D.scale_stride + sb;
+    } else {
+        tip = D.tip_lh + (long long)D.tips[(long long)dad_id * D.Ppad + p] * (n * D.nmix);
+    }
+    double *theta = D.theta + pb;
+    unsigned min_scale = 0xffffffffu;
+    if (SAFE)
+        for (int c = 0; c < C; c++) min_scale = min(min_scale, dsc[c * kWarp] + (nsc ? nsc[c * kWarp] : 0u));
+    for (int c = 0; c < C; c++) {
+        double f = 1.0;
+        bool zero = false;
+        if (SAFE) {
+            unsigned sc = dsc[c * kWarp] + (nsc ? nsc[c * kWarp] : 0u);
+            if (sc == min_scale + 1) f = kScalingThreshold;
+            else if (sc > min_scale + 1) zero = true;
+        }
+        const double *tp = tip ? tip + (c / D.denom) * n : nullptr;
+        for (int i = 0; i < n; i++) {
+            const long long k = (long long)(c * n + i) * kWarp;
+            double t = (node ? node[k] : __ldg(tp + i)) * dad[k];
+            if (SAFE) t = zero ? 0.0 : (f != 1.0 ? t * f : t);
+            theta[k] = t;
+        }
+    }
+    double bs = SAFE ? (double)min_scale : (double)(dsc[0] + (nsc ? nsc[0] : 0u));
+    D.buffer_scale[p] = bs * kLogScalingThreshold;
+}
+
+// computeLikelihoodDerv{,Generic}SIMD pattern loop (tree/phylokernelnew.h:2463-2505): (lh, df, ddf) = val{0,1,2}.theta
+template <int BT>
+__global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red) {
+    const int B = BT ? BT : D.B;
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const double *theta = D.theta + pbase(p, B);
+    const double *v0 = D.val, *v1 = D.val + B, *v2 = D.val + 2 * B;
+    // dotProductTriple: two lane accumulators (even / odd k)
+    double ad[2] = {0, 0}, bd[2] = {0, 0}, cd[2] = {0, 0};
+    int k = 0;
+#pragma unroll 8
+    for (; k + 1 < B; k += 2) {
+        double t0 = theta[(long long)k * kWarp], t1 = theta[(long long)(k + 1) * kWarp];
+        ad[0] = fma(__ldg(v0 + k), t0, ad[0]); ad[1] = fma(__ldg(v0 + k + 1), t1, ad[1]);
+        bd[0] = fma(__ldg(v1 + k), t0, bd[0]); bd[1] = fma(__ldg(v1 + k + 1), t1, bd[1]);
+        cd[0] = fma(__ldg(v2 + k), t0, cd[0]); cd[1] = fma(__ldg(v2 + k + 1), t1, cd[1]);
+    }
+    double lh = ad[0] + ad[1], df = bd[0] + bd[1], ddf = cd[0] + cd[1];
+    if (k < B) {
+        double t = theta[(long long)k * kWarp];
+        lh = fma(__ldg(v0 + k), t, lh); df = fma(__ldg(v1 + k), t, df); ddf = fma(__ldg(v2 + k), t, ddf);
+    }
+    lh = fabs(lh) + D.invar[p];
+    double acc[2] = {0.0, 0.0};
+    if (p < D.P) {
+        double inv = 1.0 / lh;
+        double df_frac = df * inv, ddf_frac = ddf * inv;
+        double freq = D.freq[p];
+        double tmp1 = df_frac * freq, tmp2 = ddf_frac * freq;
+        acc[0] = tmp1;
+        acc[1] = fma(-tmp1, df_frac, tmp2);   // nmul_add(tmp1, df_frac, tmp2) :2505
+    }
+    block_reduce_store<2>(acc, red);
+}
+
+// computeLikelihoodFromBuffer{,Generic}SIMD pattern loop (tree/phylokernelnew.h:3313-3368)
+template <int BT>
+__global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red) {
+    const int B = BT ? BT : D.B;
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const double *theta = D.theta + pbase(p, B);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    int k = 0;
+#pragma unroll 4
+    for (; k + 3 < B; k += 4) {
+        a0 = fma(__ldg(D.val + k), theta[(long long)k * kWarp], a0);
+        a1 = fma(__ldg(D.val + k + 1), theta[(long long)(k + 1) * kWarp], a1);
+        a2 = fma(__ldg(D.val + k + 2), theta[(long long)(k + 2) * kWarp], a2);
+        a3 = fma(__ldg(D.val + k + 3), theta[(long long)(k + 3) * kWarp], a3);
+    }
+    double lh = (a0 + a1) + (a2 + a3);
+    for (; k < B; k++) lh = fma(__ldg(D.val + k), theta[(long long)k * kWarp], lh);
+    lh = fabs(lh) + D.invar[p];
+    double acc[1] = {0.0};
+    if (p < D.P) {
+        double lg = log(fabs(lh)) + D.buffer_scale[p];
+        D.pattern_lh[p] = lg;
+        acc[0] = lg * D.freq[p];
+    }
+    block_reduce_store<1>(acc, red);
+}
+
+// layout converters for read-backs: device warp-interleaved -> reference V=1 layout [p*W + k]
+__global__ void k_deinterleave_f64(const double *src, double *dst, long long P, int W) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * W) return;
+    long long p = idx / W;
+    int k = (int)(idx - p * W);
+    dst[idx] = src[pbase(p, W) + (long long)k * kWarp];
+}
+__global__ void k_deinterleave_u16(const uint16_t *src, uint16_t *dst, long long P, int W) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P * W) return;
+    long long p = idx / W;
+    int k = (int)(idx - p * W);
+    dst[idx] = src[pbase(p, W) + (long long)k * kWarp];
+}
+
+}  // namespace b200lk

@@ -1,0 +1,77 @@
+"""Shared seeded test cases: (tree, model, tip patterns, frequencies, invariant-site terms)."""
+from __future__ import annotations
+
+import numpy as np
+
+from iqtree2_b200 import models, treesim
+
+
+def ptn_invar_for(model, pat):
+    """computePtnInvar (tree/phylotreesse.cpp:549-612) for unambiguous constant patterns and all-gap patterns."""
+    nptn = pat.shape[1]
+    inv = np.zeros(nptn)
+    if model.pinvar == 0:
+        return inv
+    freq = model.state_freq.reshape(model.nmix, model.nstates)[0]
+    for p in range(nptn):
+        col = pat[:, p]
+        real = col[col < model.nstates]
+        other = col[col >= model.nstates]
+        if not (other == model.state_unknown).all():
+            continue
+        if real.size == 0:
+            inv[p] = model.pinvar
+        elif (real == real[0]).all():
+            inv[p] = model.pinvar * freq[real[0]]
+    return inv
+
+
+def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, tree_kind="yule", mean_len=0.1):
+    if kind == "dna":
+        model = models.make_gtr_gamma()
+    elif kind == "dna_inv":
+        model = models.make_gtr_gamma(pinvar=0.2)
+    elif kind == "dna_g1":
+        model = models.make_gtr_gamma(ncat=1)
+    elif kind == "dna_g8":
+        model = models.make_gtr_gamma(ncat=8, alpha=0.3)
+    elif kind == "aa":
+        model = models.make_lg_gamma()
+    elif kind == "aa_c4":  # small LG+C60-style mixture: 4 classes x 4 rates
+        model = models.make_lg_c60_gamma(nclasses=4)
+    elif kind == "bin":
+        model = models.make_random_reversible(2, ncat=4, seed=seed)
+    elif kind == "n5mix":
+        model = models.make_random_reversible(5, ncat=3, nmix=2, seed=seed)
+    elif kind == "codon":
+        model = models.make_random_reversible(61, ncat=1, seed=seed)
+    elif kind == "n7":
+        model = models.make_random_reversible(7, ncat=2, seed=seed)
+    else:
+        raise ValueError(kind)
+    if tree_kind == "yule":
+        tree = treesim.yule_tree(ntaxa, seed=seed, mean_len=mean_len)
+    else:
+        tree = treesim.caterpillar_tree(ntaxa, seed=seed, mean_len=mean_len)
+    aln = treesim.simulate_alignment(tree, model, nsites, seed=seed + 1)
+    pat, freq = treesim.compress_patterns(aln)
+    rng = np.random.default_rng(seed + 2)
+    pat = pat.copy()
+    if gaps > 0:
+        pat[rng.random(pat.shape) < gaps] = model.state_unknown
+    if ambig > 0 and model.seq_type == "DNA":
+        m = rng.random(pat.shape) < ambig
+        pat[m] = rng.integers(4, 18, size=int(m.sum()))
+    if ambig > 0 and model.seq_type == "AA":
+        m = rng.random(pat.shape) < ambig
+        pat[m] = rng.integers(20, 23, size=int(m.sum()))
+    inv = ptn_invar_for(model, pat)
+    return tree, model, pat, freq, inv
+
+
+def load_engine(cls, tree, model, pat, freq, inv, safe=False, **kw):
+    e = cls(model, tree.ntaxa, pat.shape[1], safe_numeric=safe, **kw)
+    e.set_tip_states(pat)
+    e.set_pattern_freq(freq)
+    e.set_pattern_invar(inv)
+    return e
