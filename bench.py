@@ -303,7 +303,7 @@ def main():
         "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "patterns_per_gpu": my_nptn, "model": desc,
                    "kernel": "NORM_LH", "nstates": model.nstates, "ncat_mix": model.ncat_mix, "partial_updates_per_eval": len(ops),
                    "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
-                   "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}[args.schedule],
+                   "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}.get(args.schedule, f"variant{args.schedule}"),
                    "clv_bytes_resident": eng.device_bytes, "l2": "inputs (CLVs) far larger than L2; no flush needed",
                    "parallelism": f"pattern-sharded x{world}" if world > 1 else "single GPU",
                    "algorithmic_GB_per_eval": bytes_eval / 1e9},

@@ -45,6 +45,7 @@ struct b200lk_engine {
     double *d_scratch = nullptr;   // read-back conversion buffer
     size_t scratch_cap = 0;
     std::vector<double> h_freq;
+    std::vector<double> h_evec, h_inv_evec;   // host copies: constant-bank operands of the 4-state walker
     int64_t device_bytes = 0;
     bool theta_computed = false;
     int schedule = 0;
@@ -259,6 +260,8 @@ extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const doub
     CK(cudaMemcpyAsync((void *)e->d.evec, evec, sizeof(double) * nmix * n * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync((void *)e->d.inv_evec, inv_evec, sizeof(double) * nmix * n * n, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync((void *)e->d.mix_weight, mix_weight, sizeof(double) * nmix, cudaMemcpyHostToDevice, e->stream));
+    e->h_evec.assign(evec, evec + (size_t)nmix * n * n);
+    e->h_inv_evec.assign(inv_evec, inv_evec + (size_t)nmix * n * n);
     const int total = (e->cfg.state_unknown + 1) * nmix * n;
     k_tip_partial_lh<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d, (double *)e->d.tip_lh, e->cfg.seq_type);
     e->launches++;
@@ -330,11 +333,75 @@ static void launch_partials(b200lk_engine *e, int op_begin, int op_end, int walk
     e->last_launch[0]++;
 }
 
+
+static int validate_op(b200lk_engine *e, const b200lk_op &op) {
+    if (op.dst_slot < 0 || op.dst_slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "op: dst_slot out of range");
+    const b200lk_child ch[2] = {op.left, op.right};
+    for (auto &c : ch) {
+        if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
+        else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
+        else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+    }
+    return 0;
+}
+
+// the specialised 4-state x 4-category walker (k_walk_n4c4) serves the walker schedule of every single-class DNA model
+static bool use_walk4(const b200lk_engine *e) {
+    return e->schedule != 1 && e->cfg.nstates == 4 && e->C == 4 && e->cfg.nmix == 1 && e->cfg.ncat == 4 &&
+           e->cfg.state_unknown < kMaxLeafRows4 && e->h_evec.size() == 16;
+}
+
+static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    WalkJob4 *hj = (WalkJob4 *)e->h_stage;
+    CK(cudaStreamSynchronize(e->stream));   // the pinned staging buffer may still be in flight
+    int prev_dst = -1;
+    for (int k = 0; k < nops; k++) {
+        const b200lk_op &op = ops[k];
+        int rc = validate_op(e, op);
+        if (rc) return rc;
+        const b200lk_child *A = &op.left, *B = &op.right;
+        WalkJob4 &j = hj[k];
+        if (A->kind == 0 && B->kind == 0) { j.ncase = 0; j.loadA = 0; }
+        else if (A->kind == 1 && B->kind == 1) {
+            j.ncase = 2;
+            if (B->id == prev_dst) std::swap(A, B);   // chain: the CLV produced by the previous op stays in registers
+            j.loadA = A->id != prev_dst;
+        } else {
+            j.ncase = 1;
+            if (A->kind == 0) std::swap(A, B);        // A = the internal child
+            j.loadA = A->id != prev_dst;
+        }
+        j.lenA = A->length; j.lenB = B->length;
+        j.aid = A->id; j.bid = B->id;
+        j.dst = op.dst_slot; j.pad = 0;
+        prev_dst = op.dst_slot;
+    }
+    WalkJob4 *dj = (WalkJob4 *)e->d_jobs;
+    CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob4) * nops, cudaMemcpyHostToDevice, e->stream));
+    k_walk_info_n4c4<<<nops, 64, 0, e->stream>>>(e->d, dj, e->d_opinfo);
+    Model4 M;
+    for (int k = 0; k < 16; k++) { M.evec[k] = e->h_evec[k]; M.inv[k] = e->h_inv_evec[k]; }
+    const long long ntiles = e->Ppad / kTile;
+    const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * 4);   // 4 resident CTAs per SM (128 regs/thread)
+    CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+    if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+    if (e->cfg.safe_numeric) k_walk_n4c4<true><<<grid, kTile, 0, e->stream>>>(e->d, M, e->d_opinfo, nops, e->d_counter);
+    else k_walk_n4c4<false><<<grid, kTile, 0, e->stream>>>(e->d, M, e->d_opinfo, nops, e->d_counter);
+    if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+    e->partials_timed = e->profiling;
+    e->launches += 2;
+    e->last_launch[0] += 2;
+    CK(cudaGetLastError());
+    e->theta_computed = false;
+    return 0;
+}
+
 // Enqueue (no sync) everything computePartialLikelihood needs for the op list.
 static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     if (nops <= 0) return 0;
     int rc = ensure_op_capacity(e, nops);
     if (rc) return rc;
+    if (use_walk4(e)) return enqueue_walk4(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
     DevOp *hops = (DevOp *)e->h_stage;

@@ -394,6 +394,256 @@ __global__ void __launch_bounds__(kTile, 4) k_partials_n4c4(Dev D, const DevOp *
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 4-state x 4-category WALKER, v2 (the hot kernel of BASELINE config 2).
+//
+// What changed against k_partials_n4c4 (profiles/r1_v1_*: latency-bound, 604 instr per warp-op, 96 LDS.128 per
+// thread-op, 4-way bank conflicts on the leaf tables, two CTA barriers and three dependent L2 round trips per op):
+//   * register chaining — in post-order the parent of an internal child is the NEXT op, so the CLV a thread has
+//     just produced is consumed from registers (`cur`) instead of being re-loaded: at most ONE child CLV is loaded
+//     per op (the sibling subtree's), none for tip-inner nodes;
+//   * factorised operator — echild[c][x][i] = evec[x][i]*exp(eval_i r_c t) (tree/phylokernelnew.h:1016-1031) is
+//     applied as evec . (exp (.) L): the per-op data shrinks from 2x64 to 2x16 doubles and evec / inv_evec become
+//     kernel-parameter (constant-bank) operands of the FP64 FMAs — no shared-memory traffic for them;
+//   * tip children — unambiguous states index a [c][x][state] table (conflict-free, 4 states contiguous), the gap
+//     state is the constant 1, IUPAC codes fall back to the direct sum;
+//   * one CTA barrier per op; the next op's 1.3 KB staging block is fetched into registers while the current op
+//     computes, and stored to the other shared buffer afterwards;
+//   * the underflow test max|v| < 2^-256 is an integer compare on the exponent fields (ALU pipe, not FP64).
+// ------------------------------------------------------------------------------------------------------------
+struct Model4 {
+    double evec[16];   // evec[x*4 + i]
+    double inv[16];    // inv_evec[i*4 + x]
+};
+
+struct WalkJob4 {      // host -> k_walk_info_n4c4
+    double lenA, lenB;
+    int32_t dst, ncase, aid, bid, loadA, pad;
+};
+
+// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[64] | tabB[64]
+constexpr int kStage4 = 4 + 16 + 16 + 64 + 64;   // 164 doubles = 1312 bytes (16-byte multiple)
+struct StageHdr4 { int32_t dst, ncase, aid, bid, loadA, pad0, pad1, pad2; };
+
+// child A is the CLV that lives in registers (`cur`: chained from the previous op, or loaded when loadA), child B the
+// other one: an internal CLV loaded from memory (ncase 2) or a tip (ncase <= 1); ncase 0: both are tips.
+__global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jobs, double *stage) {
+    __shared__ double s_exp[2][16];
+    const WalkJob4 job = jobs[blockIdx.x];
+    double *st = stage + (size_t)blockIdx.x * kStage4;
+    const int t = threadIdx.x;
+    if (t < 32) {
+        const int ch = t >> 4, k = t & 15, c = k >> 2, i = k & 3;
+        const double len_child = D.cat_rate[c] * (ch ? job.lenB : job.lenA);   // :1017
+        const double v = exp(D.eval[i] * len_child);                           // :1022
+        s_exp[ch][k] = v;
+        st[4 + ch * 16 + k] = v;
+    }
+    if (t == 0) {
+        StageHdr4 h{job.dst, job.ncase, job.aid, job.bid, job.loadA, 0, 0, 0};
+        *reinterpret_cast<StageHdr4 *>(st) = h;
+    }
+    __syncthreads();
+    // partial_lh_leaves for the 4 unambiguous states, stored [c][x][state] (:1036-1051, Vec4d lanes + horizontal_add)
+    const int c = t >> 4, x = (t >> 2) & 3, s = t & 3;
+    for (int ch = 0; ch < 2; ch++) {
+        const bool is_tip = ch == 0 ? (job.ncase == 0) : (job.ncase <= 1);
+        double v = 0.0;
+        if (is_tip) {
+            const double *tip = D.tip_lh + s * 4;
+            double p0 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 0], s_exp[ch][c * 4 + 0]), tip[0]);
+            double p1 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 1], s_exp[ch][c * 4 + 1]), tip[1]);
+            double p2 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 2], s_exp[ch][c * 4 + 2]), tip[2]);
+            double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
+            v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
+        }
+        st[36 + ch * 64 + t] = v;
+    }
+}
+
+__device__ __forceinline__ unsigned abs_hi(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
+constexpr unsigned kThresholdHi = (1023u - 256u) << 20;   // high word of 2^-256: |v| < 2^-256  <=>  abs_hi(v) < this
+
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_constant__ Model4 M, const double *stage, int nops,
+                                                       unsigned long long *counter) {
+    // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
+    // L1 prefetch of op o+1's operands) and block o+2 is in flight in registers.
+    __shared__ __align__(16) double s_stage[3][kStage4];
+    __shared__ double s_tip[kMaxLeafRows4 * 4];
+    __shared__ long long s_item;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < (D.su + 1) * 4; k += kTile) s_tip[k] = D.tip_lh[k];
+    const long long ntiles = D.Ppad / kTile;
+    constexpr int kStageVec = kStage4 / 2;   // double2 elements per staging block
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const long long tile = s_item;
+        if (tile >= ntiles) break;
+        const long long p = tile * kTile + tid;
+        const long long pb = pbase(p, 16);
+        const long long sb = SAFE ? pbase(p, 4) : p;
+        const bool may_scale = D.invar[p] == 0.0;
+        if (tid < kStageVec) {
+            reinterpret_cast<double2 *>(s_stage[0])[tid] = reinterpret_cast<const double2 *>(stage)[tid];
+            if (nops > 1) reinterpret_cast<double2 *>(s_stage[1])[tid] = reinterpret_cast<const double2 *>(stage + kStage4)[tid];
+        }
+        double cur[16];
+        unsigned cursc[SAFE ? 4 : 1];
+#pragma unroll
+        for (int k = 0; k < 16; k++) cur[k] = 0.0;
+#pragma unroll
+        for (int c = 0; c < (SAFE ? 4 : 1); c++) cursc[c] = 0;
+        int sA_next = 0, sB_next = 0;
+        {   // tip states of op 0
+            const int4 h = *reinterpret_cast<const int4 *>(stage);   // global: the shared copy is not visible yet
+            if (h.y <= 1) sB_next = D.tips[(long long)h.w * D.Ppad + p];
+            if (h.y == 0) sA_next = D.tips[(long long)h.z * D.Ppad + p];
+        }
+
+        int buf = 0;
+        for (int o = 0; o < nops; o++) {
+            __syncthreads();
+            const double *st = s_stage[buf];
+            const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
+            const int4 h0 = *reinterpret_cast<const int4 *>(st);
+            const int h_loadA = *reinterpret_cast<const int *>(st + 2);
+            const int dst = h0.x, ncase = h0.y, aid = h0.z, bid = h0.w;
+            const bool do_pre = (tid < kStageVec) && (o + 2 < nops);
+            double2 pre;
+            if (do_pre) pre = __ldg(reinterpret_cast<const double2 *>(stage + (size_t)(o + 2) * kStage4) + tid);
+            const int sA = sA_next, sB = sB_next;
+
+            double X[16];
+            unsigned scB[SAFE ? 4 : 1];
+            if (ncase == 2) {
+                const double *Bp = D.partial + (long long)bid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 16; k++) X[k] = Bp[k * kWarp];
+#pragma unroll
+                for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = D.scale[(long long)bid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+            } else {
+#pragma unroll
+                for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = 0;
+            }
+            if (ncase == 0) {
+#pragma unroll
+                for (int c = 0; c < (SAFE ? 4 : 1); c++) cursc[c] = 0;
+            } else if (h_loadA) {
+                const double *Ap = D.partial + (long long)aid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 16; k++) cur[k] = Ap[k * kWarp];
+#pragma unroll
+                for (int c = 0; c < (SAFE ? 4 : 1); c++) cursc[c] = D.scale[(long long)aid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+            }
+            if (o + 1 < nops) {
+                // steer the next op: its tip states go to registers, its CLV operands towards L1
+                const double *sn = s_stage[buf1];
+                const int4 hn = *reinterpret_cast<const int4 *>(sn);
+                const int n_loadA = *reinterpret_cast<const int *>(sn + 2);
+                if (hn.y <= 1) sB_next = D.tips[(long long)hn.w * D.Ppad + p];
+                if (hn.y == 0) sA_next = D.tips[(long long)hn.z * D.Ppad + p];
+                if (hn.y == 2) {
+                    const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) prefetch_l1(Bn + k * kWarp);
+                }
+                if (hn.y >= 1 && n_loadA) {
+                    const double *An = D.partial + (long long)hn.z * D.slot_stride + pb;
+#pragma unroll
+                    for (int k = 0; k < 16; k++) prefetch_l1(An + k * kWarp);
+                }
+            }
+            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
+            unsigned mhi = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                double fa[4], fb[4];
+                if (ncase >= 1) {
+                    const double2 e01 = *reinterpret_cast<const double2 *>(expA + c * 4), e23 = *reinterpret_cast<const double2 *>(expA + c * 4 + 2);
+                    const double a0 = e01.x * cur[c * 4], a1 = e01.y * cur[c * 4 + 1], a2 = e23.x * cur[c * 4 + 2], a3 = e23.y * cur[c * 4 + 3];
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+                        fa[x] = fma(M.evec[x * 4 + 3], a3, fma(M.evec[x * 4 + 2], a2, fma(M.evec[x * 4 + 1], a1, M.evec[x * 4] * a0)));
+                } else if (sA < 4) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fa[x] = tabA[c * 16 + x * 4 + sA];
+                } else if (sA == D.su) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fa[x] = 1.0;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expA[c * 4 + 0]), s_tip[sA * 4 + 0]);
+                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expA[c * 4 + 1]), s_tip[sA * 4 + 1]);
+                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expA[c * 4 + 2]), s_tip[sA * 4 + 2]);
+                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expA[c * 4 + 3]), s_tip[sA * 4 + 3]);
+                        fa[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
+                    }
+                }
+                if (ncase == 2) {
+                    const double2 e01 = *reinterpret_cast<const double2 *>(expB + c * 4), e23 = *reinterpret_cast<const double2 *>(expB + c * 4 + 2);
+                    const double b0 = e01.x * X[c * 4], b1 = e01.y * X[c * 4 + 1], b2 = e23.x * X[c * 4 + 2], b3 = e23.y * X[c * 4 + 3];
+#pragma unroll
+                    for (int x = 0; x < 4; x++)
+                        fb[x] = fma(M.evec[x * 4 + 3], b3, fma(M.evec[x * 4 + 2], b2, fma(M.evec[x * 4 + 1], b1, M.evec[x * 4] * b0)));
+                } else if (sB < 4) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fb[x] = tabB[c * 16 + x * 4 + sB];
+                } else if (sB == D.su) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fb[x] = 1.0;
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) {
+                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expB[c * 4 + 0]), s_tip[sB * 4 + 0]);
+                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expB[c * 4 + 1]), s_tip[sB * 4 + 1]);
+                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expB[c * 4 + 2]), s_tip[sB * 4 + 2]);
+                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expB[c * 4 + 3]), s_tip[sB * 4 + 3]);
+                        fb[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
+                    }
+                }
+                const double t0 = fa[0] * fb[0], t1 = fa[1] * fb[1], t2 = fa[2] * fb[2], t3 = fa[3] * fb[3];
+                unsigned chi = 0;
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const double v = fma(M.inv[i * 4 + 3], t3, fma(M.inv[i * 4 + 2], t2, fma(M.inv[i * 4 + 1], t1, M.inv[i * 4] * t0)));
+                    cur[c * 4 + i] = v;
+                    chi = max(chi, abs_hi(v));
+                }
+                if (SAFE) {
+                    cursc[c] += scB[c];
+                    if (ncase != 0 && may_scale && chi < kThresholdHi) {
+#pragma unroll
+                        for (int i = 0; i < 4; i++) cur[c * 4 + i] *= kTwo256;
+                        cursc[c] += 1;
+                    }
+                } else mhi = max(mhi, chi);
+            }
+            if (!SAFE) {
+                cursc[0] += scB[0];
+                if (ncase != 0 && may_scale && mhi < kThresholdHi) {
+#pragma unroll
+                    for (int k = 0; k < 16; k++) cur[k] *= kTwo256;
+                    cursc[0] += 1;
+                }
+            }
+            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
+#pragma unroll
+            for (int k = 0; k < 16; k++) Op[k * kWarp] = cur[k];
+#pragma unroll
+            for (int c = 0; c < (SAFE ? 4 : 1); c++)
+                D.scale[(long long)dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
+            if (do_pre) reinterpret_cast<double2 *>(s_stage[buf2])[tid] = pre;
+            buf = buf1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // block reduction of up to 3 doubles per thread into red[blockIdx.x*3 + j]; a 1-CTA kernel sums the per-block
 // values in index order, so results are bit-reproducible for a given pattern count.
 // ------------------------------------------------------------------------------------------------------------
