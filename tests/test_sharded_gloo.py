@@ -1,0 +1,73 @@
+"""CPU, world_size 2, gloo: the pattern-sharding host logic (slice bounds, scalar all-reduce, pattern_lh gather).
+The local engine here is the oracle (test infrastructure); on the GPU box bench.py runs the same class over the
+CUDA engine with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cases import load_engine, make_case
+from iqtree2_b200 import plan
+from iqtree2_b200.sharded import ShardedLikelihood, shard_bounds
+
+
+def test_shard_bounds_cover_everything():
+    for nptn in (1, 127, 128, 129, 1000, 1_000_000):
+        for world in (1, 2, 3, 8):
+            covered = 0
+            for r in range(world):
+                lo, hi = shard_bounds(nptn, world, r)
+                assert lo == covered or lo == hi == nptn
+                assert r == world - 1 or (hi - lo) % 128 == 0 or hi == nptn
+                covered = hi
+            assert covered == nptn
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(here))
+    from oracle.oracle_engine import OracleEngine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tree, model, pat, freq, inv = make_case("dna_inv", ntaxa=11, nsites=900, seed=6)
+    sh = ShardedLikelihood(OracleEngine, model, tree.ntaxa, pat, freq, inv)
+    ops, a, b, L = plan.plan_branch(tree, 3)
+    ll = sh.branch_logl(ops, a, b, L)
+    sh.theta_reset()
+    df, ddf = sh.branch_derv(ops[:0], a, b, L)
+    ll2 = sh.logl_from_buffer(L)
+    plh = sh.gather_pattern_lh()
+    if rank == 0:
+        np.save(out, np.concatenate([[ll, df, ddf, ll2], plh]))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_matches_single_engine(tmp_path):
+    from oracle.oracle_engine import OracleEngine
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = np.load(out)
+    tree, model, pat, freq, inv = make_case("dna_inv", ntaxa=11, nsites=900, seed=6)
+    assert pat.shape[1] > 128, "needs more than one tile to exercise two non-empty shards"
+    o = load_engine(OracleEngine, tree, model, pat, freq, inv)
+    ops, a, b, L = plan.plan_branch(tree, 3)
+    ll = o.branch_logl(ops, a, b, L)
+    o.theta_reset()
+    df, ddf = o.branch_derv(ops[:0], a, b, L)
+    assert abs(res[0] - ll) < 1e-8 and abs(res[3] - ll) < 1e-8
+    np.testing.assert_allclose(res[1:3], [df, ddf], rtol=1e-10)
+    np.testing.assert_allclose(res[4:], o.get_pattern_lh(), rtol=1e-13)
