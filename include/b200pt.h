@@ -1,0 +1,50 @@
+/*
+ * b200pt.h — C binding of the host-side PhyloTree mirror (iqtree2_b200/csrc/phylotree_b200.h) so that non-C++
+ * hosts (the Python tests, bench.py) can drive the same tree-level API the reference's callers use:
+ * PhyloTree::computeLikelihood / computeLikelihoodBranch / computeLikelihoodDerv / computeLikelihoodFromBuffer /
+ * computePatternLikelihood / optimizeOneBranch / optimizeAllBranches / clearAllPartialLH
+ * (tree/phylotree.h:899-1048, 1136, 1340; tree/phylotree.cpp:668, 1233, 1458, 2594, 2698).
+ * Branches are addressed by branch id (0 .. nbranch-1, Newick reading order); end `a`/`b` by node id.
+ * Every call returns 0 on success, <0 on error (b200pt_last_error).
+ */
+#ifndef B200PT_H_
+#define B200PT_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200pt_tree b200pt_tree;
+
+b200pt_tree *b200pt_create(int32_t device, int32_t safe_numeric, int32_t force_norm, int32_t schedule, int32_t fused_newton);
+void b200pt_destroy(b200pt_tree *t);
+const char *b200pt_last_error(const b200pt_tree *t);
+
+/* names: ntaxa NUL-terminated strings in alignment-row order; states [ntaxa][nptn] */
+int b200pt_set_alignment(b200pt_tree *t, int32_t ntaxa, const char *const *names, const uint8_t *states, int64_t nptn,
+                         const double *ptn_freq, int32_t nstates, int32_t seq_type, int32_t state_unknown);
+int b200pt_set_pattern_invar(b200pt_tree *t, const double *ptn_invar);
+int b200pt_set_model(b200pt_tree *t, int32_t ncat, int32_t nmix, int32_t fused_mix_rate, const double *eval, const double *evec,
+                     const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop);
+int b200pt_read_tree(b200pt_tree *t, const char *newick);
+int b200pt_get_tree(b200pt_tree *t, char *out, int64_t cap);
+int b200pt_num_branches(b200pt_tree *t);
+/* node ids of the two ends of every branch and the current lengths */
+int b200pt_get_branches(b200pt_tree *t, int32_t *node_a, int32_t *node_b, double *lengths);
+int b200pt_set_branch_length(b200pt_tree *t, int32_t branch, double length, int32_t clear_partials);
+
+int b200pt_clear_all_partial_lh(b200pt_tree *t);
+int b200pt_compute_likelihood(b200pt_tree *t, double *logl);
+int b200pt_compute_likelihood_branch(b200pt_tree *t, int32_t branch, double *logl);
+int b200pt_compute_likelihood_derv(b200pt_tree *t, int32_t branch, double *df, double *ddf);
+int b200pt_compute_likelihood_from_buffer(b200pt_tree *t, double *logl);
+int b200pt_compute_pattern_likelihood(b200pt_tree *t, double *pattern_lh, double *pattern_lh_cat /* may be NULL */);
+int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step);
+int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+/* number of partial-likelihood updates planned so far (PhyloTree::num_partial_lh_computations) */
+int64_t b200pt_num_partial_lh_computations(b200pt_tree *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,706 @@
+// phylotree_b200.cpp — host-side PhyloTree mirror over the C ABI (see phylotree_b200.h).
+#include "phylotree_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <sstream>
+#include <stdexcept>
+
+namespace b200 {
+
+static const double LOG_SCALING_THRESHOLD = -177.4456782233459932741;   // tree/phylotree.h:80
+
+PhyloNeighbor *PhyloNode::findNeighbor(const PhyloNode *other) const {
+    for (auto *n : neighbors)
+        if (n->node == other) return n;
+    return nullptr;
+}
+
+// tree/phylonode.cpp:22-34 — every partial that looks TOWARDS `this` through a neighbour other than dad is stale
+void PhyloNode::clearReversePartialLh(PhyloNode *dad) {
+    // iterative (trees can be caterpillars with thousands of levels)
+    std::vector<std::pair<PhyloNode *, PhyloNode *>> stack{{this, dad}};
+    while (!stack.empty()) {
+        auto [node, from] = stack.back();
+        stack.pop_back();
+        for (auto *it : node->neighbors)
+            if (it->node != from) {
+                PhyloNeighbor *nei = it->node->findNeighbor(node);
+                nei->partial_lh_computed = false;
+                nei->size = 0;
+                stack.push_back({it->node, node});
+            }
+    }
+}
+
+PhyloTree::PhyloTree() {}
+PhyloTree::~PhyloTree() {
+    deleteAllPartialLh();
+    freeTree();
+}
+
+void PhyloTree::freeTree() {
+    for (auto *n : nodes_) delete n;
+    for (auto *n : neighbors_) delete n;
+    nodes_.clear();
+    neighbors_.clear();
+    branches_.clear();
+    root = nullptr;
+    current_it = current_it_back = nullptr;
+}
+
+void PhyloTree::check(int rc, const char *what) {
+    if (rc < 0) {
+        // the reference's outError() prints and exits (utils/tools.cpp:70-77); a library throws instead
+        throw std::runtime_error(std::string(what) + ": " + b200lk_last_error(engine_));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// inputs
+// ---------------------------------------------------------------------------------------------------------------
+void PhyloTree::setAlignment(const std::vector<std::string> &names, const uint8_t *states, int64_t nptn, const double *ptn_freq,
+                             int nstates, int seq_type, int state_unknown) {
+    deleteAllPartialLh();
+    taxa_ = names;
+    nptn_ = nptn;
+    nstates_ = nstates;
+    seq_type_ = seq_type;
+    state_unknown_ = state_unknown;
+    states_.assign(states, states + (size_t)names.size() * nptn);
+    ptn_freq_.assign(ptn_freq, ptn_freq + nptn);
+    ptn_invar_.assign(nptn, 0.0);
+}
+
+void PhyloTree::setPatternInvar(const double *ptn_invar) {
+    ptn_invar_.assign(ptn_invar, ptn_invar + nptn_);
+    if (engine_) {
+        check(b200lk_set_pattern_invar(engine_, ptn_invar_.data()), "set_pattern_invar");
+        clearAllPartialLH();
+    }
+}
+
+void PhyloTree::setModel(int ncat, int nmix, bool fused, const double *eval, const double *evec, const double *inv_evec,
+                         const double *mix_weight, const double *cat_rate, const double *cat_prop) {
+    const bool reshape = engine_ && (ncat != ncat_ || nmix != nmix_ || fused != fused_);
+    if (reshape) deleteAllPartialLh();
+    ncat_ = ncat; nmix_ = nmix; fused_ = fused;
+    const int n = nstates_;
+    eval_.assign(eval, eval + (size_t)nmix * n);
+    evec_.assign(evec, evec + (size_t)nmix * n * n);
+    inv_evec_.assign(inv_evec, inv_evec + (size_t)nmix * n * n);
+    mix_weight_.assign(mix_weight, mix_weight + nmix);
+    cat_rate_.assign(cat_rate, cat_rate + ncat);
+    cat_prop_.assign(cat_prop, cat_prop + ncat);
+    if (engine_) {
+        // a model change invalidates every partial (ModelMarkov::targetFunk: decomposeRateMatrix + clearAllPartialLH,
+        // model/modelmarkov.cpp:1091) and the tip table (tip_partial_lh_computed, tree/phylotree.cpp:668-677)
+        check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
+        check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
+        clearAllPartialLH();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Newick I/O (MTree::readTree / printTree, tree/mtree.cpp:686-877): unrooted, leaf ids = alignment rows,
+// internal ids = leafNum.. in creation order, root = the leaf read first
+// ---------------------------------------------------------------------------------------------------------------
+void PhyloTree::readTreeString(const std::string &newick) {
+    deleteAllPartialLh();
+    freeTree();
+    std::map<std::string, int> row;
+    for (size_t i = 0; i < taxa_.size(); i++) row[taxa_[i]] = (int)i;
+    size_t pos = 0;
+    const std::string &s = newick;
+    auto skip = [&]() { while (pos < s.size() && isspace((unsigned char)s[pos])) pos++; };
+    int next_internal = (int)taxa_.size();
+    int next_branch = 0;
+    auto new_node = [&]() { nodes_.push_back(new PhyloNode()); return nodes_.back(); };
+    auto connect = [&](PhyloNode *a, PhyloNode *b, double len) {
+        auto *ab = new PhyloNeighbor(), *ba = new PhyloNeighbor();
+        ab->node = b; ba->node = a;
+        ab->length = ba->length = len;
+        ab->id = ba->id = next_branch++;
+        a->neighbors.push_back(ab);
+        b->neighbors.push_back(ba);
+        neighbors_.push_back(ab); neighbors_.push_back(ba);
+        branches_.push_back({ab, ba});
+    };
+    PhyloNode *first_leaf = nullptr;
+    // recursive descent; returns (node, branch length to parent)
+    std::function<std::pair<PhyloNode *, double>()> parse = [&]() -> std::pair<PhyloNode *, double> {
+        skip();
+        PhyloNode *node = new_node();
+        if (pos < s.size() && s[pos] == '(') {
+            pos++;
+            std::vector<std::pair<PhyloNode *, double>> kids;
+            for (;;) {
+                kids.push_back(parse());
+                skip();
+                if (pos < s.size() && s[pos] == ',') { pos++; continue; }
+                if (pos < s.size() && s[pos] == ')') { pos++; break; }
+                throw std::runtime_error("readTreeString: expected ',' or ')'");
+            }
+            node->id = next_internal++;
+            for (auto &k : kids) connect(node, k.first, k.second);
+            skip();
+            // optional internal label
+            size_t b = pos;
+            while (pos < s.size() && s[pos] != ':' && s[pos] != ',' && s[pos] != ')' && s[pos] != ';') pos++;
+            node->name = s.substr(b, pos - b);
+        } else {
+            size_t b = pos;
+            while (pos < s.size() && s[pos] != ':' && s[pos] != ',' && s[pos] != ')' && s[pos] != ';' && !isspace((unsigned char)s[pos])) pos++;
+            node->name = s.substr(b, pos - b);
+            auto it = row.find(node->name);
+            if (it == row.end()) throw std::runtime_error("readTreeString: taxon '" + node->name + "' is not in the alignment");
+            node->id = it->second;
+            if (!first_leaf) first_leaf = node;
+        }
+        skip();
+        double len = -1.0;
+        if (pos < s.size() && s[pos] == ':') {
+            pos++;
+            size_t used = 0;
+            len = std::stod(s.substr(pos), &used);
+            pos += used;
+        }
+        return {node, len};
+    };
+    auto top = parse();
+    PhyloNode *top_node = top.first;
+    if (top_node->neighbors.size() == 2) {
+        // rooted input with a bifurcating root: suppress the root node (MTree::convertToUnrooted)
+        PhyloNeighbor *a = top_node->neighbors[0], *b = top_node->neighbors[1];
+        PhyloNode *na = a->node, *nb = b->node;
+        PhyloNeighbor *back_a = na->findNeighbor(top_node), *back_b = nb->findNeighbor(top_node);
+        const double len = std::max(a->length, 0.0) + std::max(b->length, 0.0);
+        back_a->node = nb; back_b->node = na;
+        back_a->length = back_b->length = len;
+        // merge branch ids: keep a's id, drop b's
+        const int keep = a->id, drop = b->id;
+        back_b->id = keep;
+        branches_[keep] = {back_a, back_b};
+        branches_.erase(branches_.begin() + drop);
+        for (size_t k = 0; k < branches_.size(); k++) branches_[k].first->id = branches_[k].second->id = (int)k;
+        nodes_.erase(std::find(nodes_.begin(), nodes_.end(), top_node));
+        neighbors_.erase(std::find(neighbors_.begin(), neighbors_.end(), a));
+        neighbors_.erase(std::find(neighbors_.begin(), neighbors_.end(), b));
+        delete a; delete b; delete top_node;
+        // re-number internal ids densely
+        int k = (int)taxa_.size();
+        for (auto *n : nodes_) if (!n->isLeaf()) n->id = k++;
+    }
+    leafNum = 0;
+    for (auto *n : nodes_) if (n->isLeaf()) leafNum++;
+    nodeNum = (int)nodes_.size();
+    if (leafNum != (int)taxa_.size()) throw std::runtime_error("readTreeString: tree and alignment have different taxon sets");
+    for (auto *n : nodes_)
+        if (!n->isLeaf() && n->neighbors.size() != 3) throw std::runtime_error("readTreeString: multifurcating trees are not supported yet");
+    for (auto &br : branches_)
+        if (br.first->length < 0) br.first->length = br.second->length = params.min_branch_length;
+    root = first_leaf;
+}
+
+std::string PhyloTree::getTreeString(int precision) const {
+    std::ostringstream out;
+    out.precision(precision);
+    std::function<void(PhyloNode *, PhyloNode *)> rec = [&](PhyloNode *node, PhyloNode *dad) {
+        if (node->isLeaf() && dad) { out << node->name; return; }
+        out << "(";
+        bool first = true;
+        if (!dad) {   // root is a leaf: print it as the first child of its only neighbour
+            out << node->name << ":" << node->neighbors[0]->length;
+            first = false;
+            PhyloNode *inner = node->neighbors[0]->node;
+            for (auto *it : inner->neighbors)
+                if (it->node != node) { out << ","; rec(it->node, inner); out << ":" << it->length; }
+            out << ")";
+            return;
+        }
+        for (auto *it : node->neighbors)
+            if (it->node != dad) {
+                if (!first) out << ",";
+                first = false;
+                rec(it->node, node);
+                out << ":" << it->length;
+            }
+        out << ")";
+    };
+    rec(root, nullptr);
+    out << ";";
+    return out.str();
+}
+
+PhyloNode *PhyloTree::findNodeName(const std::string &name) const {
+    for (auto *n : nodes_) if (n->name == name) return n;
+    return nullptr;
+}
+
+void PhyloTree::getBranches(std::vector<PhyloNode *> &nodes, std::vector<PhyloNode *> &nodes2) const {
+    nodes.clear(); nodes2.clear();
+    for (auto &br : branches_) { nodes.push_back(br.second->node); nodes2.push_back(br.first->node); }
+}
+
+void PhyloTree::saveBranchLengths(std::vector<double> &lenvec) const {
+    lenvec.resize(branches_.size());
+    for (size_t k = 0; k < branches_.size(); k++) lenvec[k] = branches_[k].first->length;
+}
+void PhyloTree::restoreBranchLengths(const std::vector<double> &lenvec) {
+    for (size_t k = 0; k < branches_.size(); k++) branches_[k].first->length = branches_[k].second->length = lenvec[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// buffers
+// ---------------------------------------------------------------------------------------------------------------
+void PhyloTree::deleteAllPartialLh() {
+    if (engine_) b200lk_destroy(engine_);
+    engine_ = nullptr;
+    for (auto *n : neighbors_) { n->slot = -1; n->partial_lh_computed = false; }
+    theta_computed = false;
+}
+
+void PhyloTree::initializeAllPartialLh() {
+    if (engine_) return;
+    if (!root || taxa_.empty() || ncat_ == 0) throw std::runtime_error("initializeAllPartialLh: alignment, model and tree must be set first");
+    b200lk_config cfg{};
+    cfg.nstates = nstates_; cfg.ncat = ncat_; cfg.nmix = nmix_; cfg.fused_mix_rate = fused_;
+    // setLikelihoodKernel: SAFE_LH iff -safe, or >= 2000 sequences, or a state count without a fixed-state kernel
+    // (tree/phylotreesse.cpp:95-96)
+    bool safe = params.safe_numeric || leafNum >= 2000 || (nstates_ != 4 && nstates_ != 20);
+    if (params.force_norm) safe = false;
+    cfg.safe_numeric = safe;
+    cfg.seq_type = seq_type_; cfg.state_unknown = state_unknown_;
+    cfg.ntaxa = leafNum; cfg.nptn = nptn_;
+    cfg.nslots = (nodeNum - leafNum) + 2;   // one per internal node (LM_PER_NODE) + nni_partial_lh (tree/phylotree.cpp:1071-1076)
+    cfg.device = params.device;
+    int rc = b200lk_create(&cfg, &engine_);
+    if (rc != 0) throw std::runtime_error(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
+    check(b200lk_set_schedule(engine_, params.schedule), "set_schedule");
+    check(b200lk_set_tip_states(engine_, states_.data()), "set_tip_states");
+    check(b200lk_set_pattern_freq(engine_, ptn_freq_.data()), "set_pattern_freq");
+    check(b200lk_set_pattern_invar(engine_, ptn_invar_.data()), "set_pattern_invar");
+    check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
+    check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
+    // slot assignment: pre-order from the root; the neighbour dad->node of every internal node gets the next slot
+    // (tree/phylotree.cpp:1143-1157)
+    int indexlh = 0;
+    std::vector<std::pair<PhyloNode *, PhyloNode *>> stack{{root, nullptr}};
+    while (!stack.empty()) {
+        auto [node, dad] = stack.back();
+        stack.pop_back();
+        if (dad && !node->isLeaf()) dad->findNeighbor(node)->slot = indexlh++;
+        for (auto it = node->neighbors.rbegin(); it != node->neighbors.rend(); ++it)
+            if ((*it)->node != dad) stack.push_back({(*it)->node, node});
+    }
+    clearAllPartialLH();
+}
+
+void PhyloTree::clearAllPartialLH() {
+    for (auto *n : neighbors_) { n->partial_lh_computed = false; n->size = 0; }
+    theta_computed = false;
+    current_it = current_it_back = nullptr;
+    if (engine_) b200lk_theta_reset(engine_);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// traversal planning
+// ---------------------------------------------------------------------------------------------------------------
+int PhyloTree::computeSize(PhyloNeighbor *nei, PhyloNode *dad) {
+    if (nei->size > 0) return nei->size;
+    // iterative post-order over the subtree below nei
+    struct Fr { PhyloNeighbor *nei; PhyloNode *dad; size_t k; int acc; };
+    std::vector<Fr> st{{nei, dad, 0, 1}};
+    while (!st.empty()) {
+        Fr &f = st.back();
+        PhyloNode *node = f.nei->node;
+        if (f.k < node->neighbors.size()) {
+            PhyloNeighbor *c = node->neighbors[f.k++];
+            if (c->node == f.dad) continue;
+            if (c->size > 0) f.acc += c->size;
+            else st.push_back({c, node, 0, 1});
+        } else {
+            f.nei->size = f.acc;
+            int s = f.acc;
+            st.pop_back();
+            if (!st.empty()) st.back().acc += s;
+        }
+    }
+    return nei->size;
+}
+
+void PhyloTree::reorientPartialLh(PhyloNeighbor *dad_branch, PhyloNode *dad) {
+    if (dad_branch->slot >= 0) return;
+    PhyloNode *node = dad_branch->node;
+    for (auto *it : node->neighbors)
+        if (it->node != dad) {
+            PhyloNeighbor *backnei = it->node->findNeighbor(node);
+            if (backnei->slot >= 0) {
+                // MemSlotVector::takeover (tree/memslot.cpp:206-223)
+                dad_branch->slot = backnei->slot;
+                backnei->slot = -1;
+                backnei->partial_lh_computed = false;
+                break;
+            }
+        }
+    if (dad_branch->slot < 0) throw std::runtime_error("partial_lh is not re-oriented");
+}
+
+// tree/phylotree.cpp:5918-6028 — post-order list of stale directed partials below dad_branch
+bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_dad) {
+    struct Fr { PhyloNeighbor *dad_branch; PhyloNode *dad; std::vector<PhyloNeighbor *> kids; size_t k; };
+    std::vector<Fr> st;
+    auto push = [&](PhyloNeighbor *db, PhyloNode *dad) {
+        PhyloNode *node = db->node;
+        if (db->partial_lh_computed || node->isLeaf()) return;
+        Fr f{db, dad, {}, 0};
+        for (auto *it : node->neighbors) if (it->node != dad) f.kids.push_back(it);
+        for (auto *it : f.kids) computeSize(it, node);
+        // sort neighbours in descending subtree size (:5931-5942)
+        std::stable_sort(f.kids.begin(), f.kids.end(), [](PhyloNeighbor *a, PhyloNeighbor *b) { return a->size > b->size; });
+        st.push_back(std::move(f));
+    };
+    push(top_branch, top_dad);
+    while (!st.empty()) {
+        Fr &f = st.back();
+        if (f.k < f.kids.size()) {
+            PhyloNeighbor *c = f.kids[f.k++];
+            PhyloNode *node = f.dad_branch->node;
+            push(c, node);
+            continue;
+        }
+        PhyloNeighbor *dad_branch = f.dad_branch;
+        PhyloNode *dad = f.dad, *node = dad_branch->node;
+        dad_branch->partial_lh_computed = true;
+        reorientPartialLh(dad_branch, dad);
+        b200lk_op op{};
+        op.dst_slot = dad_branch->slot;
+        // children in NEIGHBOUR order (FOR_NEIGHBOR_IT, tree/phylokernelnew.h:1343-1350), not in the sorted visiting order
+        b200lk_child *ch[2] = {&op.left, &op.right};
+        int k = 0;
+        for (auto *it : node->neighbors)
+            if (it->node != dad) {
+                ch[k]->kind = it->node->isLeaf() ? 0 : 1;
+                ch[k]->id = it->node->isLeaf() ? it->node->id : it->slot;
+                ch[k]->length = it->length;
+                k++;
+            }
+        traversal_info.push_back(op);
+        num_partial_lh_computations++;
+        st.pop_back();
+    }
+    return false;
+}
+
+// tree/phylokernelnew.h:1150-1281 (the part that builds the list; execution happens inside the engine call)
+void PhyloTree::computeTraversalInfo(PhyloNode *node, PhyloNode *dad) {
+    traversal_info.clear();
+    PhyloNeighbor *dad_branch = dad->findNeighbor(node);
+    PhyloNeighbor *node_branch = node->findNeighbor(dad);
+    computeTraversalInfo(dad_branch, dad);
+    computeTraversalInfo(node_branch, node);
+}
+
+void PhyloTree::branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &node_slot, int &dad_kind, int &dad_id) {
+    PhyloNode *node = dad_branch->node;
+    PhyloNeighbor *node_branch = node->findNeighbor(dad);
+    if (node->isLeaf()) {   // swap so that `dad` is the leaf (tree/phylokernelnew.h:2654-2661)
+        std::swap(dad, node);
+        std::swap(dad_branch, node_branch);
+    }
+    if (node->isLeaf()) throw std::runtime_error("a branch between two leaves has no internal CLV");
+    computeTraversalInfo(node, dad);
+    node_slot = dad_branch->slot;
+    if (dad->isLeaf()) { dad_kind = 0; dad_id = dad->id; }
+    else { dad_kind = 1; dad_id = node_branch->slot; }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the likelihood API
+// ---------------------------------------------------------------------------------------------------------------
+double PhyloTree::computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
+    initializeAllPartialLh();
+    int node_slot, dad_kind, dad_id;
+    const double length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    double logl = 0.0;
+    if (!traversal_info.empty()) theta_computed = false;
+    check(b200lk_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
+                             save_log_value, &logl), "branch_logl");
+    traversal_info.clear();
+    return logl;
+}
+
+void PhyloTree::computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *dad) {
+    initializeAllPartialLh();
+    traversal_info.clear();
+    computeTraversalInfo(dad_branch, dad);
+    if (!traversal_info.empty()) theta_computed = false;
+    check(b200lk_update_partials(engine_, traversal_info.data(), (int)traversal_info.size()), "update_partials");
+    traversal_info.clear();
+}
+
+void PhyloTree::computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf) {
+    initializeAllPartialLh();
+    int node_slot, dad_kind, dad_id;
+    const double length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    if (!traversal_info.empty()) theta_computed = false;
+    if (!theta_computed) b200lk_theta_reset(engine_);
+    check(b200lk_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length, df, ddf),
+          "branch_derv");
+    traversal_info.clear();
+    theta_computed = true;
+}
+
+double PhyloTree::computeLikelihoodFromBuffer() {
+    if (!theta_computed || !current_it) throw std::runtime_error("computeLikelihoodFromBuffer: theta_all is not computed");
+    double logl = 0.0;
+    check(b200lk_logl_from_buffer(engine_, current_it->length, &logl), "logl_from_buffer");
+    return logl;
+}
+
+// tree/phylotree.cpp:1233-1274
+double PhyloTree::computeLikelihood(double *pattern_lh, bool save_log_value) {
+    initializeAllPartialLh();
+    if (!current_it) {
+        PhyloNode *leaf = findFarthestLeaf();
+        current_it = leaf->neighbors[0];
+        current_it_back = current_it->node->findNeighbor(leaf);
+    }
+    double score = computeLikelihoodBranch(current_it, current_it_back->node, save_log_value);
+    if (pattern_lh) check(b200lk_get_pattern_lh(engine_, pattern_lh), "get_pattern_lh");
+    curScore = score;
+    return score;
+}
+
+void PhyloTree::computePatternLhCat(double *out) {
+    if (!current_it) computeLikelihood();
+    else computeLikelihoodBranch(current_it, current_it_back->node);
+    check(b200lk_get_pattern_lh_cat(engine_, out), "get_pattern_lh_cat");   // already in [p][c] order (transformPatternLhCat)
+}
+
+// tree/phylotree.cpp:1458-1603
+void PhyloTree::computePatternLikelihood(double *ptn_lh, double *cur_logl, double *ptn_lh_cat) {
+    const int C = fused_ ? ncat_ : ncat_ * nmix_;
+    std::vector<double> lh_cat;
+    double score;
+    if (ptn_lh_cat) {
+        lh_cat.resize((size_t)nptn_ * C);
+        computePatternLhCat(lh_cat.data());
+        score = curScore;
+    }
+    if (!current_it) score = computeLikelihood();
+    else score = computeLikelihoodBranch(current_it, current_it_back->node);
+    (void)score;
+    if (ptn_lh) check(b200lk_get_pattern_lh(engine_, ptn_lh), "get_pattern_lh");
+    if (cur_logl) {
+        // sanity sum as PhyloSuperTree does (tree/phylosupertree.cpp:748-761)
+    }
+    if (!ptn_lh_cat) return;
+    PhyloNeighbor *nei1 = current_it, *nei2 = current_it_back;
+    if (!nei1->node->isLeaf() && nei2->node->isLeaf()) std::swap(nei1, nei2);
+    b200lk_config cfg{};
+    const bool safe = params.safe_numeric || leafNum >= 2000 || (nstates_ != 4 && nstates_ != 20);
+    const bool per_cat = safe && !params.force_norm;
+    const size_t S = per_cat ? C : 1;
+    (void)cfg;
+    std::vector<uint16_t> s1, s2((size_t)nptn_ * S);
+    check(b200lk_get_scale_num(engine_, nei2->slot, s2.data()), "get_scale_num");
+    if (!nei1->node->isLeaf()) {
+        s1.resize((size_t)nptn_ * S);
+        check(b200lk_get_scale_num(engine_, nei1->slot, s1.data()), "get_scale_num");
+    }
+    for (int64_t p = 0; p < nptn_; p++)
+        for (int c = 0; c < C; c++) {
+            const size_t si = per_cat ? (size_t)p * C + c : (size_t)p;
+            const double scale = ((s1.empty() ? 0 : s1[si]) + s2[si]) * LOG_SCALING_THRESHOLD;
+            ptn_lh_cat[p * C + c] = std::log(lh_cat[p * C + c]) + scale;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// branch-length optimisation
+// ---------------------------------------------------------------------------------------------------------------
+double PhyloTree::computeFunction(double value) {   // tree/phylotree.cpp:2514-2520
+    current_it->length = value;
+    current_it_back->length = value;
+    return -computeLikelihoodBranch(current_it, current_it_back->node);
+}
+
+void PhyloTree::computeFuncDerv(double value, double &df, double &ddf) {   // tree/phylotree.cpp:2529-2536
+    current_it->length = value;
+    current_it_back->length = value;
+    computeLikelihoodDerv(current_it, current_it_back->node, &df, &ddf);
+    df = -df;
+    ddf = -ddf;
+}
+
+// utils/optimization.cpp:422-499, statement for statement
+double PhyloTree::minimizeNewton(double x1, double xguess, double x2, double xacc, double &d2l, int maxNRStep) {
+    double df, dx, dxold, f, temp, xh, xl, rts, rts_old;
+    rts = xguess;
+    if (rts < x1) rts = x1;
+    if (rts > x2) rts = x2;
+    computeFuncDerv(rts, f, df);
+    d2l = df;
+    if (!std::isfinite(f) || !std::isfinite(df)) throw std::runtime_error("Wrong computeFuncDerv");
+    if (df >= 0.0 && std::fabs(f) < xacc) return rts;
+    if (f < 0.0) { xl = rts; xh = x2; } else { xh = rts; xl = x1; }
+    dx = dxold = std::fabs(xh - xl);
+    for (int j = 1; j <= maxNRStep; j++) {
+        rts_old = rts;
+        if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)) {
+            dxold = dx;
+            dx = 0.5 * (xh - xl);
+            rts = xl + dx;
+            d2l = df;
+            if (xl == rts) return rts;
+        } else {
+            dxold = dx;
+            dx = f / df;
+            temp = rts;
+            rts -= dx;
+            d2l = df;
+            if (temp == rts) return rts;
+        }
+        if (std::fabs(dx) < xacc || (j == maxNRStep)) return rts_old;
+        computeFuncDerv(rts, f, df);
+        if (!std::isfinite(f) || !std::isfinite(df)) throw std::runtime_error("Wrong computeFuncDerv");
+        if (df > 0.0 && std::fabs(f) < xacc) { d2l = df; return rts; }
+        if (f < 0.0) xl = rts;
+        else if (f > 0.0) xh = rts;
+    }
+    (void)dxold;
+    d2l = 0.0;
+    return 0.0;
+}
+
+// tree/phylotree.cpp:2594-2646
+void PhyloTree::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH, int maxNRStep) {
+    initializeAllPartialLh();
+    current_it = node1->findNeighbor(node2);
+    current_it_back = node2->findNeighbor(node1);
+    const double current_len = current_it->length;
+    theta_computed = false;
+    b200lk_theta_reset(engine_);
+    double optx;
+    if (params.fused_newton) {
+        // same iteration, run inside the library on the resident theta buffer
+        PhyloNeighbor *dad_branch = current_it;
+        PhyloNode *dad = current_it_back->node;
+        int node_slot, dad_kind, dad_id;
+        branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+        int steps = 0;
+        check(b200lk_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
+                                   params.min_branch_length, current_len, params.max_branch_length, params.min_branch_length,
+                                   maxNRStep, &optx, &steps), "newton_branch");
+        traversal_info.clear();
+        theta_computed = true;
+    } else {
+        double negative_lh;
+        optx = minimizeNewton(params.min_branch_length, current_len, params.max_branch_length, params.min_branch_length, negative_lh, maxNRStep);
+    }
+    if (optx > params.max_branch_length * 0.95) {   // Newton-Raphson diverged: keep the better of the two (:2616-2625)
+        current_it->length = current_it_back->length = optx;
+        const double opt_lh = computeLikelihoodFromBuffer();
+        current_it->length = current_it_back->length = current_len;
+        const double orig_lh = computeLikelihoodFromBuffer();
+        if (orig_lh > opt_lh) optx = current_len;
+    }
+    current_it->length = optx;
+    current_it_back->length = optx;
+    if (clearLH && current_len != optx) {
+        node1->clearReversePartialLh(node2);
+        node2->clearReversePartialLh(node1);
+    }
+}
+
+// tree/mtree.cpp:3040-3060 (height in branches; ties keep the first neighbour reached)
+PhyloNode *PhyloTree::findFarthestLeaf(PhyloNode *node, PhyloNode *dad) {
+    if (!node) node = root;
+    struct Fr { PhyloNode *node, *dad; size_t k; PhyloNode *res; };
+    std::vector<Fr> st{{node, dad, 0, nullptr}};
+    PhyloNode *result = nullptr;
+    while (!st.empty()) {
+        Fr &f = st.back();
+        if (f.k == 0) {
+            f.node->height = 0.0;
+            if (f.dad && f.node->isLeaf()) {
+                PhyloNode *leaf = f.node;
+                st.pop_back();
+                if (st.empty()) return leaf;
+                Fr &p = st.back();
+                if (p.node->height < leaf->height + 1) { p.node->height = leaf->height + 1; p.res = leaf; }
+                continue;
+            }
+        }
+        bool pushed = false;
+        while (f.k < f.node->neighbors.size()) {
+            PhyloNeighbor *it = f.node->neighbors[f.k++];
+            if (it->node == f.dad) continue;
+            st.push_back({it->node, f.node, 0, nullptr});
+            pushed = true;
+            break;
+        }
+        if (pushed) continue;
+        PhyloNode *n = f.node, *res = f.res;
+        st.pop_back();
+        if (st.empty()) { result = res; break; }
+        Fr &p = st.back();
+        if (p.node->height < n->height + 1) { p.node->height = n->height + 1; p.res = res; }
+    }
+    return result;
+}
+
+// tree/mtree.cpp:3062-3082
+void PhyloTree::getPreOrderBranches(std::vector<PhyloNode *> &nodes, std::vector<PhyloNode *> &nodes2, PhyloNode *node, PhyloNode *dad) {
+    std::vector<std::pair<PhyloNode *, PhyloNode *>> st{{node, dad}};
+    while (!st.empty()) {
+        auto [nd, dd] = st.back();
+        st.pop_back();
+        if (dd) { nodes.push_back(nd); nodes2.push_back(dd); }
+        std::vector<PhyloNeighbor *> neivec = nd->neighbors;
+        for (size_t i1 = 0; i1 < neivec.size(); i1++)
+            for (size_t i2 = i1 + 1; i2 < neivec.size(); i2++)
+                if (neivec[i1]->node->height > neivec[i2]->node->height) std::swap(neivec[i1], neivec[i2]);
+        for (auto it = neivec.rbegin(); it != neivec.rend(); ++it)
+            if ((*it)->node != dd) st.push_back({(*it)->node, nd});
+    }
+}
+
+// tree/phylotree.cpp:2698-2774
+double PhyloTree::optimizeAllBranches(int my_iterations, double tolerance, int maxNRStep) {
+    initializeAllPartialLh();
+    std::vector<PhyloNode *> nodes, nodes2;
+    // computeBestTraversal (:2688-2696): double call to the farthest leaf finds the longest path
+    PhyloNode *farleaf = findFarthestLeaf();
+    findFarthestLeaf(farleaf);
+    getPreOrderBranches(nodes, nodes2, farleaf);
+    double tree_lh = computeLikelihoodBranch(nodes[0]->findNeighbor(nodes2[0]), nodes[0]);
+    std::vector<double> lenvec;
+    for (int i = 0; i < my_iterations; i++) {
+        saveBranchLengths(lenvec);
+        for (size_t j = 0; j < nodes.size(); j++) optimizeOneBranch(nodes[j], nodes2[j], true, maxNRStep);
+        double new_tree_lh = computeLikelihoodFromBuffer();
+        if (new_tree_lh < tree_lh - tolerance * 0.1) {
+            // rare: the log-likelihood decreased; restore the branch lengths and stop (:2733-2759)
+            clearAllPartialLH();
+            restoreBranchLengths(lenvec);
+            new_tree_lh = computeLikelihood();
+            return new_tree_lh;
+        }
+        if (tree_lh <= new_tree_lh && new_tree_lh <= tree_lh + tolerance) {
+            curScore = new_tree_lh;
+            return new_tree_lh;
+        }
+        tree_lh = new_tree_lh;
+    }
+    curScore = tree_lh;
+    return tree_lh;
+}
+
+}  // namespace b200

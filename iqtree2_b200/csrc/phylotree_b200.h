@@ -1,0 +1,143 @@
+// phylotree_b200.h — host-side mirror of the reference's PhyloTree likelihood interface, driving the C ABI
+// (include/b200lk.h).  Same member names, argument meaning and invalidation semantics as tree/phylotree.h:899-1048,
+// tree/phylonode.h:28-185 so that the shim in INTEGRATION.md is a field-for-field mapping:
+//
+//   reference                                            here
+//   PhyloNeighbor::partial_lh / scale_num (views)   ->   PhyloNeighbor::slot (device CLV slot handle, -1 = none)
+//   PhyloNeighbor::partial_lh_computed              ->   same flag, same clearing rules
+//   PhyloTree::traversal_info (vector<TraversalInfo>) ->  std::vector<b200lk_op> handed to the engine per call
+//   central_partial_lh / nni_partial_lh              ->   engine slots [0, T-2) + 2 NNI spares, resident in HBM
+//   theta_all / theta_computed                       ->   engine theta buffer + the same flag
+//
+// The tree, branch lengths and flags live on the host; CLVs never leave the GPU (b200lk_get_partial serves the few
+// readers outside the kernels).
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "b200lk.h"
+
+namespace b200 {
+
+const double TOL_BRANCH_LEN = 0.000001;   // tree/phylotree.h:62
+const double TOL_LIKELIHOOD = 0.001;      // tree/phylotree.h:63
+
+struct PhyloNode;
+
+// directed branch dad -> node: carries the partial likelihood of the subtree rooted at `node` seen from dad
+struct PhyloNeighbor {
+    PhyloNode *node = nullptr;
+    double length = 0.0;
+    int id = -1;                      // branch id
+    int slot = -1;                    // device CLV slot (the reference's partial_lh pointer)
+    bool partial_lh_computed = false;
+    int size = 0;                     // subtree size (PhyloNeighbor::size), 0 = unknown
+};
+
+struct PhyloNode {
+    int id = -1;                      // leaves: alignment row (tree/phylokernelnew.h:1691-1711); internal: >= ntaxa
+    std::string name;
+    std::vector<PhyloNeighbor *> neighbors;
+    double height = 0.0;
+    bool isLeaf() const { return neighbors.size() <= 1; }
+    PhyloNeighbor *findNeighbor(const PhyloNode *other) const;
+    void clearReversePartialLh(PhyloNode *dad);   // tree/phylonode.cpp:22-34
+};
+
+struct Params {
+    double min_branch_length = 1e-6;   // utils/tools.cpp:1235 (reset to 0.1/nsites-style values by the caller if wanted)
+    double max_branch_length = 10.0;   // utils/tools.cpp:1238
+    int device = 0;
+    bool safe_numeric = false;         // -safe; forced for ntaxa >= 2000 or nstates not in {4,20} (phylotreesse.cpp:95-96)
+    bool force_norm = false;           // test hook: keep NORM_LH where the reference would switch to SAFE_LH
+    int schedule = 0;
+    bool fused_newton = true;          // optimizeOneBranch through b200lk_newton_branch (one C call per branch)
+};
+
+class PhyloTree {
+public:
+    PhyloTree();
+    ~PhyloTree();
+    PhyloTree(const PhyloTree &) = delete;
+
+    // ---- inputs (what aln / model / site_rate supply in the reference) ----------------------------------------
+    // taxa names in alignment-row order + pattern-compressed tip states [ntaxa][nptn] + ptn_freq
+    void setAlignment(const std::vector<std::string> &names, const uint8_t *states, int64_t nptn, const double *ptn_freq,
+                      int nstates, int seq_type, int state_unknown);
+    void setPatternInvar(const double *ptn_invar);
+    void setModel(int ncat, int nmix, bool fused_mix_rate, const double *eval, const double *evec, const double *inv_evec,
+                  const double *mix_weight, const double *cat_rate, const double *cat_prop);
+    void readTreeString(const std::string &newick);   // MTree::readTree; leaf ids := alignment rows
+    std::string getTreeString(int precision = 10) const;
+
+    // ---- buffers ------------------------------------------------------------------------------------------------
+    void initializeAllPartialLh();    // tree/phylotree.cpp:893-939, 1060-1188 (LM_PER_NODE slot assignment)
+    void deleteAllPartialLh();
+    void clearAllPartialLH();         // tree/phylotree.cpp:668-677
+
+    // ---- the likelihood API (tree/phylotree.h:899-1048, 1136, 1340) ----------------------------------------------
+    double computeLikelihood(double *pattern_lh = nullptr, bool save_log_value = true);   // tree/phylotree.cpp:1233-1274
+    double computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true);
+    void computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf);
+    double computeLikelihoodFromBuffer();
+    void computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *dad);   // flush the stale partials below one directed branch
+    void computePatternLikelihood(double *pattern_lh, double *cur_logl = nullptr, double *pattern_lh_cat = nullptr);
+    void computePatternLhCat(double *pattern_lh_cat);
+
+    // ---- branch-length optimisation (tree/phylotree.cpp:2514-2774, utils/optimization.cpp:422-499) ---------------
+    double computeFunction(double value);
+    void computeFuncDerv(double value, double &df, double &ddf);
+    double minimizeNewton(double x1, double xguess, double x2, double xacc, double &d2l, int maxNRStep = 100);
+    void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100);
+    double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);
+
+    // ---- tree access ----------------------------------------------------------------------------------------------
+    PhyloNode *findNodeName(const std::string &name) const;
+    PhyloNode *findFarthestLeaf(PhyloNode *node = nullptr, PhyloNode *dad = nullptr);   // tree/mtree.cpp:3040-3060
+    void getPreOrderBranches(std::vector<PhyloNode *> &nodes, std::vector<PhyloNode *> &nodes2, PhyloNode *node,
+                             PhyloNode *dad = nullptr);                               // tree/mtree.cpp:3062-3082
+    void getBranches(std::vector<PhyloNode *> &nodes, std::vector<PhyloNode *> &nodes2) const;   // by branch id
+    void saveBranchLengths(std::vector<double> &lenvec) const;
+    void restoreBranchLengths(const std::vector<double> &lenvec);
+    int numBranches() const { return (int)branches_.size(); }
+
+    // diagnostics for parity tests
+    int64_t num_partial_lh_computations = 0;   // tree/phylotree.h:2127
+    b200lk_engine *engine() const { return engine_; }
+    const std::vector<b200lk_op> &lastTraversal() const { return traversal_info; }
+
+    Params params;
+    PhyloNode *root = nullptr;
+    PhyloNeighbor *current_it = nullptr, *current_it_back = nullptr;
+    bool theta_computed = false;
+    double curScore = 0.0;
+    int leafNum = 0, nodeNum = 0;
+
+private:
+    bool computeTraversalInfo(PhyloNeighbor *dad_branch, PhyloNode *dad);   // tree/phylotree.cpp:5918-6028
+    void computeTraversalInfo(PhyloNode *node, PhyloNode *dad);             // tree/phylokernelnew.h:1150-1281
+    void reorientPartialLh(PhyloNeighbor *dad_branch, PhyloNode *dad);      // tree/phylotree.cpp:5898-5912
+    int computeSize(PhyloNeighbor *nei, PhyloNode *dad);
+    void check(int rc, const char *what);
+    void freeTree();
+    void branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &node_slot, int &dad_kind, int &dad_id);
+
+    std::vector<PhyloNode *> nodes_;
+    std::vector<PhyloNeighbor *> neighbors_;
+    std::vector<std::pair<PhyloNeighbor *, PhyloNeighbor *>> branches_;   // by branch id: (a->b, b->a)
+    std::vector<std::string> taxa_;
+    std::vector<uint8_t> states_;
+    std::vector<double> ptn_freq_, ptn_invar_;
+    int64_t nptn_ = 0;
+    int nstates_ = 0, seq_type_ = 0, state_unknown_ = 0;
+    int ncat_ = 0, nmix_ = 1;
+    bool fused_ = false;
+    std::vector<double> eval_, evec_, inv_evec_, mix_weight_, cat_rate_, cat_prop_;
+    b200lk_engine *engine_ = nullptr;
+    std::vector<b200lk_op> traversal_info;
+    std::vector<double> pattern_lh_;
+};
+
+}  // namespace b200

@@ -1,0 +1,119 @@
+// phylotree_capi.cpp — extern "C" binding of b200::PhyloTree (include/b200pt.h).
+#include <cstring>
+#include <exception>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "b200pt.h"
+#include "phylotree_b200.h"
+
+struct b200pt_tree {
+    b200::PhyloTree tree;
+    std::string err;
+};
+
+static thread_local std::string g_err;
+
+#define GUARD(...)                                    \
+    try { __VA_ARGS__; return 0; }                    \
+    catch (const std::exception &ex) { t->err = ex.what(); return -1; }
+
+extern "C" {
+
+b200pt_tree *b200pt_create(int32_t device, int32_t safe_numeric, int32_t force_norm, int32_t schedule, int32_t fused_newton) {
+    auto *t = new b200pt_tree();
+    t->tree.params.device = device;
+    t->tree.params.safe_numeric = safe_numeric != 0;
+    t->tree.params.force_norm = force_norm != 0;
+    t->tree.params.schedule = schedule;
+    t->tree.params.fused_newton = fused_newton != 0;
+    return t;
+}
+void b200pt_destroy(b200pt_tree *t) { delete t; }
+const char *b200pt_last_error(const b200pt_tree *t) { return t ? t->err.c_str() : g_err.c_str(); }
+
+int b200pt_set_alignment(b200pt_tree *t, int32_t ntaxa, const char *const *names, const uint8_t *states, int64_t nptn,
+                         const double *ptn_freq, int32_t nstates, int32_t seq_type, int32_t state_unknown) {
+    GUARD({
+        std::vector<std::string> nm(names, names + ntaxa);
+        t->tree.setAlignment(nm, states, nptn, ptn_freq, nstates, seq_type, state_unknown);
+    })
+}
+int b200pt_set_pattern_invar(b200pt_tree *t, const double *ptn_invar) { GUARD(t->tree.setPatternInvar(ptn_invar)) }
+int b200pt_set_model(b200pt_tree *t, int32_t ncat, int32_t nmix, int32_t fused, const double *eval, const double *evec,
+                     const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop) {
+    GUARD(t->tree.setModel(ncat, nmix, fused != 0, eval, evec, inv_evec, mix_weight, cat_rate, cat_prop))
+}
+int b200pt_read_tree(b200pt_tree *t, const char *newick) { GUARD(t->tree.readTreeString(newick)) }
+int b200pt_get_tree(b200pt_tree *t, char *out, int64_t cap) {
+    GUARD({
+        std::string s = t->tree.getTreeString();
+        if ((int64_t)s.size() + 1 > cap) throw std::runtime_error("buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+    })
+}
+int b200pt_num_branches(b200pt_tree *t) { return t->tree.numBranches(); }
+int b200pt_get_branches(b200pt_tree *t, int32_t *node_a, int32_t *node_b, double *lengths) {
+    GUARD({
+        std::vector<b200::PhyloNode *> a, b;
+        t->tree.getBranches(a, b);
+        std::vector<double> len;
+        t->tree.saveBranchLengths(len);
+        for (size_t k = 0; k < a.size(); k++) { node_a[k] = a[k]->id; node_b[k] = b[k]->id; lengths[k] = len[k]; }
+    })
+}
+static void ends(b200pt_tree *t, int branch, b200::PhyloNode *&a, b200::PhyloNode *&b) {
+    std::vector<b200::PhyloNode *> na, nb;
+    t->tree.getBranches(na, nb);
+    if (branch < 0 || branch >= (int)na.size()) throw std::runtime_error("branch id out of range");
+    a = na[branch]; b = nb[branch];
+}
+int b200pt_set_branch_length(b200pt_tree *t, int32_t branch, double length, int32_t clear_partials) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        ends(t, branch, a, b);
+        a->findNeighbor(b)->length = length;
+        b->findNeighbor(a)->length = length;
+        if (clear_partials) { a->clearReversePartialLh(b); b->clearReversePartialLh(a); t->tree.theta_computed = false; }
+    })
+}
+int b200pt_clear_all_partial_lh(b200pt_tree *t) { GUARD(t->tree.clearAllPartialLH()) }
+int b200pt_compute_likelihood(b200pt_tree *t, double *logl) { GUARD(*logl = t->tree.computeLikelihood()) }
+int b200pt_compute_likelihood_branch(b200pt_tree *t, int32_t branch, double *logl) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        ends(t, branch, a, b);
+        t->tree.current_it = a->findNeighbor(b);
+        t->tree.current_it_back = b->findNeighbor(a);
+        *logl = t->tree.computeLikelihoodBranch(t->tree.current_it, a);
+    })
+}
+int b200pt_compute_likelihood_derv(b200pt_tree *t, int32_t branch, double *df, double *ddf) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        ends(t, branch, a, b);
+        b200::PhyloNeighbor *it = a->findNeighbor(b);
+        if (t->tree.current_it != it && t->tree.current_it_back != it) t->tree.theta_computed = false;
+        t->tree.current_it = it;
+        t->tree.current_it_back = b->findNeighbor(a);
+        t->tree.computeLikelihoodDerv(it, a, df, ddf);
+    })
+}
+int b200pt_compute_likelihood_from_buffer(b200pt_tree *t, double *logl) { GUARD(*logl = t->tree.computeLikelihoodFromBuffer()) }
+int b200pt_compute_pattern_likelihood(b200pt_tree *t, double *pattern_lh, double *pattern_lh_cat) {
+    GUARD(t->tree.computePatternLikelihood(pattern_lh, nullptr, pattern_lh_cat))
+}
+int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        ends(t, branch, a, b);
+        t->tree.optimizeOneBranch(a, b, clear_lh != 0, max_nr_step);
+    })
+}
+int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl) {
+    GUARD(*logl = t->tree.optimizeAllBranches(iterations, tolerance, max_nr_step))
+}
+int64_t b200pt_num_partial_lh_computations(b200pt_tree *t) { return t->tree.num_partial_lh_computations; }
+
+}  // extern "C"

@@ -1,0 +1,121 @@
+"""PhyloTree — Python face of the C++ host mirror (include/b200pt.h): the tree-level likelihood API the reference's
+callers use, over the CUDA engine.  No fallback: constructing a tree on a box without the CUDA library/GPU fails
+at the first likelihood call."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .engine import SEQ_TYPES, EngineError, load_library
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PhyloTree:
+    def __init__(self, device=0, safe_numeric=False, force_norm=False, schedule=0, fused_newton=True):
+        self.lib = load_library()
+        self.lib.b200pt_create.restype = C.c_void_p
+        self.lib.b200pt_last_error.restype = C.c_char_p
+        self.lib.b200pt_last_error.argtypes = [C.c_void_p]
+        self.lib.b200pt_destroy.argtypes = [C.c_void_p]
+        self.lib.b200pt_num_partial_lh_computations.restype = C.c_int64
+        self.lib.b200pt_num_partial_lh_computations.argtypes = [C.c_void_p]
+        self._h = C.c_void_p(self.lib.b200pt_create(device, int(safe_numeric), int(force_norm), schedule, int(fused_newton)))
+        self.nptn = 0
+        self.ncat_mix = 0
+
+    def _check(self, rc):
+        if rc < 0:
+            raise EngineError(self.lib.b200pt_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b200pt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- inputs -----------------------------------------------------------------------------------------------
+    def set_alignment(self, names, patterns, ptn_freq, model):
+        pat = np.ascontiguousarray(patterns, dtype=np.uint8)
+        freq = np.ascontiguousarray(ptn_freq, dtype=np.float64)
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        self.nptn = pat.shape[1]
+        self._check(self.lib.b200pt_set_alignment(self._h, len(names), arr, _dp(pat), C.c_int64(self.nptn), _dp(freq),
+                                                  model.nstates, SEQ_TYPES[model.seq_type], model.state_unknown))
+
+    def set_pattern_invar(self, inv):
+        inv = np.ascontiguousarray(inv, dtype=np.float64)
+        self._check(self.lib.b200pt_set_pattern_invar(self._h, _dp(inv)))
+
+    def set_model(self, model):
+        f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        arrs = [f(model.eval), f(model.evec), f(model.inv_evec), f(model.mix_weight), f(model.cat_rate), f(model.cat_prop)]
+        self.ncat_mix = model.ncat_mix
+        self._check(self.lib.b200pt_set_model(self._h, model.ncat, model.nmix, int(model.fused_mix_rate), *[_dp(a) for a in arrs]))
+
+    def read_tree(self, newick: str):
+        self._check(self.lib.b200pt_read_tree(self._h, newick.encode()))
+
+    def get_tree(self) -> str:
+        buf = C.create_string_buffer(1 << 22)
+        self._check(self.lib.b200pt_get_tree(self._h, buf, C.c_int64(len(buf))))
+        return buf.value.decode()
+
+    def branches(self):
+        n = self.lib.b200pt_num_branches(self._h)
+        a = np.zeros(n, dtype=np.int32); b = np.zeros(n, dtype=np.int32); ln = np.zeros(n)
+        self._check(self.lib.b200pt_get_branches(self._h, _dp(a), _dp(b), _dp(ln)))
+        return a, b, ln
+
+    def set_branch_length(self, branch, length, clear_partials=True):
+        self._check(self.lib.b200pt_set_branch_length(self._h, branch, C.c_double(length), int(clear_partials)))
+
+    # ---- likelihood API ---------------------------------------------------------------------------------------
+    def clear_all_partial_lh(self):
+        self._check(self.lib.b200pt_clear_all_partial_lh(self._h))
+
+    def compute_likelihood(self):
+        out = C.c_double()
+        self._check(self.lib.b200pt_compute_likelihood(self._h, C.byref(out)))
+        return out.value
+
+    def compute_likelihood_branch(self, branch):
+        out = C.c_double()
+        self._check(self.lib.b200pt_compute_likelihood_branch(self._h, branch, C.byref(out)))
+        return out.value
+
+    def compute_likelihood_derv(self, branch):
+        df, ddf = C.c_double(), C.c_double()
+        self._check(self.lib.b200pt_compute_likelihood_derv(self._h, branch, C.byref(df), C.byref(ddf)))
+        return df.value, ddf.value
+
+    def compute_likelihood_from_buffer(self):
+        out = C.c_double()
+        self._check(self.lib.b200pt_compute_likelihood_from_buffer(self._h, C.byref(out)))
+        return out.value
+
+    def compute_pattern_likelihood(self, with_cat=False):
+        lh = np.zeros(self.nptn)
+        cat = np.zeros((self.nptn, self.ncat_mix)) if with_cat else None
+        self._check(self.lib.b200pt_compute_pattern_likelihood(self._h, _dp(lh), _dp(cat) if with_cat else None))
+        return (lh, cat) if with_cat else lh
+
+    def optimize_one_branch(self, branch, clear_lh=True, max_nr_step=100):
+        self._check(self.lib.b200pt_optimize_one_branch(self._h, branch, int(clear_lh), max_nr_step))
+
+    def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
+        out = C.c_double()
+        self._check(self.lib.b200pt_optimize_all_branches(self._h, iterations, C.c_double(tolerance), max_nr_step, C.byref(out)))
+        return out.value
+
+    @property
+    def num_partial_lh_computations(self):
+        return int(self.lib.b200pt_num_partial_lh_computations(self._h))

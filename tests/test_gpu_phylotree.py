@@ -1,0 +1,103 @@
+"""GPU: the tree-level API (C++ host mirror over the CUDA engine) against the Python restatement over the CPU oracle.
+BASELINE config 1 is example.phy + a committed NJ tree + GTR+G4: fixed-tree logL and branch-length optimisation.
+Bars: tree logL 1e-6, per-pattern logL 1e-11 relative, optimised branch lengths 1e-6."""
+import numpy as np
+import pytest
+
+from iqtree2_b200.phylotree import PhyloTree
+from test_tree_logic_cpu import example_case, make_pytree
+
+pytestmark = pytest.mark.gpu
+
+
+def make_gpu_tree(names, pat, freq, model, newick, **kw):
+    t = PhyloTree(**kw)
+    t.set_alignment(names, pat, freq, model)
+    t.set_model(model)
+    t.read_tree(newick)
+    return t
+
+
+def test_config1_fixed_tree_logl_and_pattern_lh():
+    names, pat, freq, model, newick = example_case()
+    g = make_gpu_tree(names, pat, freq, model, newick)
+    o = make_pytree(names, pat, freq, model, newick)
+    ll_g, ll_o = g.compute_likelihood(), o.compute_likelihood()
+    assert abs(ll_g - ll_o) < 1e-6
+    plh, cat = g.compute_pattern_likelihood(with_cat=True)
+    np.testing.assert_allclose(plh, o.engine.get_pattern_lh(), rtol=1e-11)
+    assert abs(float((plh * freq).sum()) - ll_g) < 1e-7
+    # per-category log-likelihoods recombine to the pattern log-likelihood
+    np.testing.assert_allclose(np.log(np.exp(cat - plh[:, None]).sum(axis=1)), 0.0, atol=1e-9)
+    a, b, ln = g.branches()
+    for br in range(0, len(ln), 4):
+        assert abs(g.compute_likelihood_branch(br) - ll_o) < 1e-6
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_config1_branch_length_optimisation(fused):
+    names, pat, freq, model, newick = example_case()
+    g = make_gpu_tree(names, pat, freq, model, newick, fused_newton=fused)
+    o = make_pytree(names, pat, freq, model, newick)
+    ll_g = g.optimize_all_branches(iterations=100, tolerance=0.001)
+    ll_o = o.optimize_all_branches(iterations=100, tolerance=0.001)
+    assert abs(ll_g - ll_o) < 1e-6, (ll_g, ll_o)
+    _, _, ln = g.branches()
+    np.testing.assert_allclose(ln, o.lengths(), rtol=0, atol=1e-6)
+    # same amount of partial-likelihood work as the reference's planner would schedule
+    assert g.num_partial_lh_computations == o.num_partial
+    # and a fresh full evaluation at the optimised lengths agrees
+    g.clear_all_partial_lh(); o.clear_all()
+    assert abs(g.compute_likelihood() - o.compute_likelihood()) < 1e-6
+
+
+def test_incremental_invalidation_matches_full_recompute():
+    names, pat, freq, model, newick = example_case()
+    g = make_gpu_tree(names, pat, freq, model, newick)
+    ll0 = g.compute_likelihood()
+    n0 = g.num_partial_lh_computations
+    assert n0 == 15   # 17 taxa -> 15 internal CLVs
+    g.optimize_one_branch(7)
+    g.optimize_one_branch(20)
+    ll_inc = g.compute_likelihood_branch(3)
+    assert g.num_partial_lh_computations - n0 < 3 * 15
+    newick2 = g.get_tree()
+    g2 = make_gpu_tree(names, pat, freq, model, newick2)
+    # get_tree prints 10 significant digits; compare at that resolution
+    assert abs(g2.compute_likelihood() - ll_inc) < 1e-4
+    assert ll_inc >= ll0 - 1e-9
+
+
+def test_model_change_invalidates_everything():
+    from iqtree2_b200 import models
+    names, pat, freq, model, newick = example_case()
+    g = make_gpu_tree(names, pat, freq, model, newick)
+    ll0 = g.compute_likelihood()
+    model2 = models.make_gtr_gamma(rates6=(1.0, 2.0, 1.0, 1.0, 2.0, 1.0), pi=(0.25, 0.25, 0.25, 0.25), alpha=1.0)
+    g.set_model(model2)
+    ll1 = g.compute_likelihood()
+    o = make_pytree(names, pat, freq, model2, newick)
+    assert abs(ll1 - o.compute_likelihood()) < 1e-6
+    assert abs(ll1 - ll0) > 1.0
+
+
+def test_protein_tree_api_and_safe_kernel():
+    from cases import make_case
+    tree, model, pat, freq, inv = make_case("aa", ntaxa=14, nsites=300, seed=8)
+    newick = tree.to_newick()
+    for safe in (False, True):
+        g = make_gpu_tree(tree.names, pat, freq, model, newick, safe_numeric=safe)
+        g.set_pattern_invar(inv)
+        from oracle.oracle_engine import OracleEngine
+        from pytree import PyTree
+
+        def factory(ntaxa, nslots):
+            e = OracleEngine(model, ntaxa, pat.shape[1], nslots=nslots, safe_numeric=safe)
+            e.set_tip_states(pat); e.set_pattern_freq(freq); e.set_pattern_invar(inv)
+            return e
+        o = PyTree(factory, tree.names, newick)
+        assert abs(g.compute_likelihood() - o.compute_likelihood()) < 1e-6
+        ll_g = g.optimize_all_branches(iterations=3)
+        ll_o = o.optimize_all_branches(iterations=3)
+        assert abs(ll_g - ll_o) < 1e-6
+        np.testing.assert_allclose(g.branches()[2], o.lengths(), atol=1e-6)
