@@ -58,10 +58,14 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
+            t0 = time.time()
+            while not self.lines and time.time() - t0 < 2.0:   # nvidia-smi needs a moment before its first line
+                time.sleep(0.02)
+            self.lines.clear()                                  # keep only samples taken inside the timed region
         except Exception:
             self.proc = None
 
@@ -125,9 +129,25 @@ def make_inputs(ntaxa, nptn, model, seed_tree=1, seed_seq=2, block=262_144):
 
 
 def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, warmup):
-    """The reference's CPU algorithm (oracle port, OpenMP over pattern packets) on a bounded pattern sample."""
-    from oracle.oracle_engine import OracleEngine
+    """The reference's CPU implementation of one eval on a bounded pattern sample, all host threads.
+
+    Preferred: oracle/_ref/libiqref.so = IQ-TREE 2.4.0's own AVX+FMA Vec4d OpenMP kernel (its TUs compiled in place by
+    oracle/build_ref.sh; the prebuilt .so travels with the snapshot)  -> kind "reference".
+    Otherwise the scalar C restatement oracle/lk_oracle.c (OpenMP over pattern packets) -> kind "port"."""
+    from oracle import ref_engine
     sample_ptn = int(min(sample_ptn, tips.shape[1]))
+    if ref_engine.available():
+        threads = min(ref_engine.max_threads(), os.cpu_count() or 1)
+        r = ref_engine.RefTree(tree, model, np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], nthreads=threads)
+        if warmup:
+            r.time_eval(0, warmup)
+        t = r.time_eval(0, steps)
+        info = r.info()
+        r.close()
+        return {"sec_per_sample_eval": t["mean_sec"], "best_sec": t["best_sec"], "sample_ptn": sample_ptn, "cores": info["num_threads"],
+                "logl": t["logl"], "df": t["df"], "ddf": t["ddf"], "kind": "reference",
+                "what": "IQ-TREE 2.4.0 phylokernelnew.h, Vec4d AVX+FMA, OpenMP (compiled from the reference's own TUs)"}
+    from oracle.oracle_engine import OracleEngine
     o = OracleEngine(model, tree.ntaxa, sample_ptn, safe_numeric=False)
     o.set_tip_states(np.ascontiguousarray(tips[:, :sample_ptn]))
     o.set_pattern_freq(freq[:sample_ptn])
@@ -141,13 +161,27 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
         times.append(time.perf_counter() - t0)
     t = times[warmup:]
     return {"sec_per_sample_eval": float(np.mean(t)), "best_sec": float(np.min(t)), "sample_ptn": sample_ptn,
-            "cores": OracleEngine.num_threads(), "logl": ll, "df": df, "ddf": ddf}
+            "cores": OracleEngine.num_threads(), "logl": ll, "df": df, "ddf": ddf, "kind": "port",
+            "what": "scalar C restatement of phylokernelnew.h (oracle/lk_oracle.c), OpenMP"}
+
+
+def cpu_sample_size(nops, B, nstates, ntaxa, budget_flop, nptn):
+    """patterns in the bounded CPU sample: ~budget_flop of kernel work per eval, capped so that the reference's
+    per-node CLVs (LM_PER_NODE: (ntaxa-2) x sample x B doubles) stay under a quarter of the free host memory"""
+    sample = max(256, int(budget_flop / (nops * B * nstates * 6)))
+    try:
+        import psutil
+        cap = int(psutil.virtual_memory().available * 0.25 / (max(ntaxa - 2, 1) * B * 8))
+        sample = min(sample, max(256, cap))
+    except Exception:
+        sample = min(sample, 50_000)
+    return min(sample, nptn) // 8 * 8 or min(sample, nptn)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS))
@@ -181,18 +215,18 @@ def main():
             return 0
         tree, tips, freq, data = make_inputs(ntaxa, min(nptn, 65536), model)
         ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
-        # bounded sample: about 1.5 s of CPU work per step
-        sample = args.cpu_sample or max(256, int(4.0e9 / (len(ops) * B * model.nstates * 6)))
-        sample = min(sample, tips.shape[1])
+        # bounded sample per step (an eval over `sample` of the nptn patterns)
+        sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, tips.shape[1])
         r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, args.steps, max(1, args.warmup))
         evals = (sample / nptn) / r["sec_per_sample_eval"]
         line = {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s",
                 "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / evals,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
                 "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "NORM_LH"},
-                "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": "port",
+                "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
                                  "sample": f"{sample} of {nptn} patterns per step, all {len(ops)} partial updates + root + derivative; "
                                            f"throughput scaled by {sample}/{nptn}"},
+                "result": {"logl_sample": r["logl"], "df_sample": r["df"], "ddf_sample": r["ddf"]},
                 "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return 0
@@ -321,13 +355,12 @@ def main():
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample or max(256, int(2.0e10 / (len(ops) * B * model.nstates * 6)))
-        sample = min(sample, my_nptn)
-        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 3, 1)
+        sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, my_nptn)
+        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 5, 1)
         cpu_evals = (sample / nptn) / r["sec_per_sample_eval"]
-        line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": "port",
+        line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
                                 "sample": f"first {sample} of {nptn} patterns, all {len(ops)} partial updates + root + derivative, "
-                                          f"3 timed evals after 1 warm-up; throughput scaled by {sample}/{nptn}",
+                                          f"5 timed evals after 1 warm-up; throughput scaled by {sample}/{nptn}",
                                 "sec_per_sample_eval": r["sec_per_sample_eval"]}
     if rank == 0:
         print(json.dumps(line))

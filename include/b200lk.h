@@ -85,6 +85,12 @@ const char *b200lk_last_error(const b200lk_engine *e); /* e may be NULL: error o
 int64_t b200lk_device_bytes(const b200lk_engine *e);
 /* run on a caller-owned stream (cudaStream_t as void*); NULL restores the engine's own stream */
 int b200lk_set_stream(b200lk_engine *e, void *cuda_stream);
+/* Reference defects that change results; OFF by default (the engine computes the intended mathematics), ON to
+ * reproduce the reference bit for bit in parity tests.
+ *   B200LK_QUIRK_DOTTRIPLE_ODD: computeLikelihoodDerv's dotProductTriple counts the last theta element twice when
+ *   nstates is odd and nstates*ncat_mix is even (tree/phylokernelnew.h:700-714; e.g. codon 61 x G4, 5 states x 6). */
+#define B200LK_QUIRK_DOTTRIPLE_ODD 1
+int b200lk_set_reference_quirks(b200lk_engine *e, int32_t mask);
 /* schedule for multi-op traversals: 0 = auto, 1 = one levelled launch per tree depth, 2 = pattern-tile walker */
 int b200lk_set_schedule(b200lk_engine *e, int schedule);
 

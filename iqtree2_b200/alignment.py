@@ -75,24 +75,66 @@ def compress(states: np.ndarray):
     return compress_patterns(states)
 
 
+_AMBI_AA = (4 + 8, 32 + 64, 512 + 1024)   # B = N|D, Z = Q|E, J = I|L as state bitmasks
+
+
+def state_appearance(nstates: int, state_unknown: int, seq_type: str) -> np.ndarray:
+    """Alignment::getAppearance (alignment/alignment.cpp:4769-4810) as a table: bitmask of states per tip code."""
+    app = np.zeros(state_unknown + 1, dtype=np.uint64)
+    full = (1 << nstates) - 1
+    for s in range(state_unknown + 1):
+        if s == state_unknown:
+            app[s] = full
+        elif s < nstates:
+            app[s] = 1 << s
+        elif seq_type == "DNA":
+            app[s] = (s - (nstates - 1)) & full
+        elif seq_type == "AA":
+            app[s] = _AMBI_AA[s - 20] if s < 23 else 0
+        else:
+            app[s] = full
+    return app
+
+
+def const_char(patterns: np.ndarray, nstates: int, state_unknown: int, seq_type="DNA") -> np.ndarray:
+    """Pattern::const_char as Alignment::computeConst sets it (alignment/alignment.cpp:925-1013): the intersection of
+    the state sets of all characters of a pattern; STATE_UNKNOWN+1 = not constant, STATE_UNKNOWN = all gaps, a state,
+    or the ambiguity code of the intersection."""
+    app = state_appearance(nstates, state_unknown, seq_type)
+    inter = np.bitwise_and.reduce(app[patterns], axis=0)
+    nptn = patterns.shape[1]
+    out = np.full(nptn, state_unknown + 1, dtype=np.int64)
+    full = (1 << nstates) - 1
+    for p in np.nonzero(inter)[0]:
+        m = int(inter[p])
+        if m == full:
+            out[p] = state_unknown
+        elif m & (m - 1) == 0:
+            out[p] = m.bit_length() - 1
+        elif seq_type == "DNA":
+            out[p] = nstates - 1 + m
+        elif seq_type == "AA":
+            out[p] = nstates + (0 if (m >> 2) & 3 == 3 else 1 if (m >> 5) & 3 == 3 else 2)
+    return out
+
+
 def ptn_invar(patterns: np.ndarray, state_freq: np.ndarray, pinvar: float, nstates: int, state_unknown: int, seq_type="DNA"):
-    """computePtnInvar (tree/phylotreesse.cpp:549-612)."""
+    """computePtnInvar (tree/phylotreesse.cpp:549-612): p_invar x frequency mass of the pattern's constant state set."""
     nptn = patterns.shape[1]
     out = np.zeros(nptn)
     if pinvar == 0.0:
         return out
-    for p in range(nptn):
-        col = patterns[:, p]
-        # Pattern::const_char: the single state all non-gap characters share (ambiguity codes by intersection are
-        # not reproduced here: patterns with ambiguity codes are treated as non-constant unless all entries agree)
-        known = col[col != state_unknown]
-        if known.size == 0:
+    cc = const_char(patterns, nstates, state_unknown, seq_type)
+    for p in np.nonzero(cc <= state_unknown)[0]:
+        c = int(cc[p])
+        if c == state_unknown:
             out[p] = pinvar
-        elif (known == known[0]).all():
-            s = int(known[0])
-            if s < nstates:
-                out[p] = pinvar * state_freq[s]
-            elif seq_type == "DNA":
-                c = s - nstates + 1
-                out[p] = pinvar * sum(state_freq[x] for x in range(nstates) if c & (1 << x))
+        elif c < nstates:
+            out[p] = pinvar * state_freq[c]
+        elif seq_type == "DNA":
+            m = c - nstates + 1
+            out[p] = pinvar * sum(state_freq[x] for x in range(nstates) if m & (1 << x))
+        elif seq_type == "AA":
+            m = _AMBI_AA[c - nstates]
+            out[p] = pinvar * sum(state_freq[x] for x in range(11) if m & (1 << x))
     return out

@@ -215,6 +215,12 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
     return 0;
 }
 
+extern "C" int b200lk_set_reference_quirks(b200lk_engine *e, int32_t mask) {
+    if (mask & ~B200LK_QUIRK_DOTTRIPLE_ODD) return fail(e, B200LK_ERR_INVALID, "unknown quirk bit");
+    e->d.quirks = mask;
+    return 0;
+}
+
 extern "C" int b200lk_set_profiling(b200lk_engine *e, int32_t on) { e->profiling = on != 0; return 0; }
 
 extern "C" int b200lk_last_timing(b200lk_engine *e, float ms[5], int32_t launches[3]) {

@@ -37,6 +37,7 @@ struct ChildJob {
 
 struct Dev {
     int n, C, ncat, nmix, denom, B, S, su;
+    int quirks;              // B200LK_QUIRK_* (include/b200lk.h)
     long long P, Ppad;
     long long slot_stride;   // Ppad * B   doubles per CLV slot
     long long scale_stride;  // Ppad * S   uint16 per slot
@@ -840,6 +841,11 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red) {
     if (k < B) {
         double t = theta[(long long)k * kWarp];
         lh = fma(__ldg(v0 + k), t, lh); df = fma(__ldg(v1 + k), t, df); ddf = fma(__ldg(v2 + k), t, ddf);
+    } else if ((D.quirks & 1) && (D.n & 1)) {
+        // B200LK_QUIRK_DOTTRIPLE_ODD: the reference's dotProductTriple takes its odd-length branch on nstates&1 and, when
+        // the block is even, adds the last element a second time (tree/phylokernelnew.h:700-714)
+        double t = theta[(long long)(B - 1) * kWarp];
+        lh = fma(__ldg(v0 + B - 1), t, lh); df = fma(__ldg(v1 + B - 1), t, df); ddf = fma(__ldg(v2 + B - 1), t, ddf);
     }
     lh = fabs(lh) + D.invar[p];
     double acc[2] = {0.0, 0.0};

@@ -23,7 +23,7 @@ ABI_SYMBOLS = [
     "b200lk_newton_branch", "b200lk_get_pattern_lh", "b200lk_get_pattern_scaling", "b200lk_get_pattern_lh_cat",
     "b200lk_get_theta", "b200lk_get_buffer_scale_all", "b200lk_get_scale_num", "b200lk_get_partial",
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
-    "b200lk_launch_count",
+    "b200lk_launch_count", "b200lk_set_reference_quirks",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -135,6 +135,9 @@ class LikelihoodEngine:
 
     def set_schedule(self, schedule):
         self._check(self.lib.b200lk_set_schedule(self._h, C.c_int(schedule)))
+
+    def set_reference_quirks(self, mask):
+        self._check(self.lib.b200lk_set_reference_quirks(self._h, C.c_int32(int(mask))))
 
     def set_profiling(self, on=True):
         self._check(self.lib.b200lk_set_profiling(self._h, C.c_int32(int(on))))

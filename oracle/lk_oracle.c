@@ -60,6 +60,7 @@ typedef struct {
     uint16_t *scale;        /* [nslots][nptn*S] */
     double *theta, *buffer_scale_all, *pattern_lh, *pattern_lh_cat, *pattern_scaling;
     int theta_computed;
+    int quirks; /* orc_set_reference_quirks */
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
     char err[256];
 } orc_engine;
@@ -230,24 +231,25 @@ static inline double dot3(const double *A, const double *B, const double *C, siz
     }
 }
 
-/* dotProductTriple<ADD=false> — phylokernelnew.h:666-725.  NOTE: for odd nstates the reference loop
- * `for (i = 2; i < N-1; i += 2)` with an EVEN total N (= block) visits index N-1 inside the loop and again in
- * the trailing mul_add, double-counting the last element; this restatement sums every element exactly once
- * (the intended mathematics) and DESIGN.md lists the discrepancy. For even nstates and for odd N it is
- * lane-for-lane identical to the reference. */
-static inline void dot_triple(const double *A, const double *B, const double *C, const double *D, size_t N,
+/* dotProductTriple<ADD=false> — phylokernelnew.h:666-725.  NOTE: the reference picks its odd-length branch on
+ * `nstates & 1`, not on N (= block = nstates*ncat_mix).  With odd nstates and an EVEN block (e.g. 61-state codon
+ * x 4 categories, 5 states x 6) the loop `for (i = 2; i < N-1; i += 2)` visits index N-1 and the trailing mul_add
+ * adds it again: the last element is counted twice (verified against the compiled reference, oracle/_ref).
+ * `odd` selects the branch: the caller passes nstates&1 to reproduce the reference bit for bit (quirk bit 0,
+ * orc_set_reference_quirks) or N&1 for the intended mathematics (every element once). */
+static inline void dot_triple(const double *A, const double *B, const double *C, const double *D, size_t N, int odd,
                               double *X, double *Y, double *Z) {
     double AD[2], BD[2], CD[2];
     size_t i, j;
     for (j = 0; j < 2; j++) { AD[j] = A[j] * D[j]; BD[j] = B[j] * D[j]; CD[j] = C[j] * D[j]; }
-    size_t stop = N - (N & 1);
+    size_t stop = odd ? N - 1 : N;
     for (i = 2; i < stop; i += 2)
         for (j = 0; j < 2; j++) {
             AD[j] = fma(A[i + j], D[i + j], AD[j]);
             BD[j] = fma(B[i + j], D[i + j], BD[j]);
             CD[j] = fma(C[i + j], D[i + j], CD[j]);
         }
-    if ((N & 1) == 0) {
+    if (!odd) {
         *X = AD[0] + AD[1]; *Y = BD[0] + BD[1]; *Z = CD[0] + CD[1];
     } else {
         *X = fma(A[N - 1], D[N - 1], AD[0] + AD[1]);
@@ -750,6 +752,8 @@ static void build_theta(orc_engine *e, int node_slot, int dad_kind, int dad_id) 
 }
 
 int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
+/* bit 0: reproduce dotProductTriple's double-counted last element for odd nstates x even block (see dot_triple) */
+int orc_set_reference_quirks(orc_engine *e, int mask) { e->quirks = mask; return 0; }
 
 /* computeLikelihoodDerv(Generic)SIMD — phylokernelnew.h:2233-2633 (joint branch length, no +ASC) */
 int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
@@ -761,10 +765,11 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
     double *val0 = (double *)malloc(sizeof(double) * 3 * B), *val1 = val0 + B, *val2 = val1 + B;
     compute_vals(e, length, val0, val1, val2);
     double all_df = 0.0, all_ddf = 0.0;
+    const int odd = (e->quirks & 1) ? (e->cfg.nstates & 1) : (B & 1);
 #pragma omp parallel for schedule(static) reduction(+ : all_df, all_ddf)
     for (size_t p = 0; p < P; p++) {
         double lh_ptn, df_ptn, ddf_ptn;
-        dot_triple(val0, val1, val2, e->theta + p * B, B, &lh_ptn, &df_ptn, &ddf_ptn);
+        dot_triple(val0, val1, val2, e->theta + p * B, B, odd, &lh_ptn, &df_ptn, &ddf_ptn);
         lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
         lh_ptn = 1.0 / lh_ptn;
         double df_frac = df_ptn * lh_ptn, ddf_frac = ddf_ptn * lh_ptn;

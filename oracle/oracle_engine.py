@@ -116,6 +116,9 @@ class OracleEngine:
     def theta_reset(self):
         lib().orc_theta_reset(self._h)
 
+    def set_reference_quirks(self, mask):
+        lib().orc_set_reference_quirks(self._h, C.c_int(int(mask)))
+
     def branch_derv(self, ops, end_a, end_b, length):
         ops = np.ascontiguousarray(ops)
         df, ddf = C.c_double(), C.c_double()

@@ -1,0 +1,177 @@
+"""ctypes wrapper around oracle/_ref/libiqref.so — TEST INFRASTRUCTURE.
+
+The library is the UNMODIFIED reference likelihood path (IQ-TREE 2.4.0 TUs compiled in place by oracle/build_ref.sh)
+behind oracle/ref_harness.cpp.  Used to pin oracle/lk_oracle.c and the CUDA engine against the real kernel (tests/)
+and as bench.py's CPU baseline ("kind": "reference").  Never imported by the product package.  /root/reference is NOT
+needed at run time: the prebuilt .so travels with the gpurun snapshot.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(_HERE, "_ref", "libiqref.so")
+SEQ_TYPES = {"GENERIC": 0, "DNA": 1, "AA": 2}
+
+
+class _Desc(C.Structure):
+    _fields_ = [("nstates", C.c_int32), ("ncat", C.c_int32), ("nmix", C.c_int32), ("fused_mix_rate", C.c_int32),
+                ("safe_numeric", C.c_int32), ("seq_type", C.c_int32), ("state_unknown", C.c_int32), ("ntaxa", C.c_int32),
+                ("nptn", C.c_int64), ("nthreads", C.c_int32), ("reserved", C.c_int32),
+                ("states", C.c_void_p), ("ptn_freq", C.c_void_p), ("newick", C.c_char_p),
+                ("eval", C.c_void_p), ("evec", C.c_void_p), ("inv_evec", C.c_void_p), ("mix_weight", C.c_void_p),
+                ("state_freq", C.c_void_p), ("cat_rate", C.c_void_p), ("cat_prop", C.c_void_p), ("pinvar", C.c_double)]
+
+
+def available() -> bool:
+    return os.path.exists(LIB)
+
+
+def build() -> bool:
+    """(Re)build when /root/reference is mounted; otherwise keep whatever prebuilt library is there."""
+    subprocess.call(["bash", os.path.join(_HERE, "build_ref.sh")])
+    return available()
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not available():
+            raise FileNotFoundError(LIB + " (run oracle/build_ref.sh where /root/reference is mounted)")
+        _lib = C.CDLL(LIB)
+        _lib.iqref_create.restype = C.c_void_p
+        for f in ("iqref_branch_logl", "iqref_compute_likelihood", "iqref_logl_from_buffer", "iqref_time_eval",
+                  "iqref_optimize_all_branches"):
+            getattr(_lib, f).restype = C.c_double
+    return _lib
+
+
+def max_threads() -> int:
+    return int(lib().iqref_max_threads())
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class RefTree:
+    """One reference PhyloTree (alignment patterns + tree + harness-supplied eigensystem)."""
+
+    def __init__(self, tree, model, pat, freq, safe_numeric=False, nthreads=1, newick=None, names=None):
+        """tree: treesim.Tree, or None with `newick` + `names` (leaf names replaced by their alignment rows)."""
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.model, self.tree = model, tree
+        self.ntaxa, self.nptn = int(pat.shape[0]), int(pat.shape[1])
+        self.n, self.Cmix = model.nstates, model.ncat_mix
+        self.B = self.n * self.Cmix
+        self.safe = bool(safe_numeric)
+        self._keep = [np.ascontiguousarray(pat, dtype=np.uint8), np.ascontiguousarray(np.rint(freq), dtype=np.int32),
+                      f64(model.eval), f64(model.evec), f64(model.inv_evec), f64(model.mix_weight), f64(model.state_freq),
+                      f64(model.cat_rate), f64(model.cat_prop)]
+        assert np.allclose(self._keep[1], freq), "the reference stores integer pattern frequencies"
+        if newick is not None:
+            import re
+            row = {nm: str(i) for i, nm in enumerate(names)}
+            nwk = re.sub(r"(?<=[(,])\s*([^():,;\s]+)(?=\s*[:,)])", lambda m: row[m.group(1)], newick)
+        else:
+            old = tree.names
+            tree.names = ["%d" % i for i in range(self.ntaxa)]   # readTreeString takes alignment row ids as leaf names
+            try:
+                nwk = tree.to_newick(fmt="%.17g")
+            finally:
+                tree.names = old
+        k = self._keep
+        d = _Desc(self.n, model.ncat, model.nmix, int(model.fused_mix_rate), int(self.safe), SEQ_TYPES[model.seq_type],
+                  model.state_unknown, self.ntaxa, self.nptn, int(nthreads), 0, _p(k[0]), _p(k[1]), nwk.encode(),
+                  _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), float(model.pinvar))
+        self._h = C.c_void_p(lib().iqref_create(C.byref(d)))
+        if not self._h:
+            raise RuntimeError("iqref_create failed")
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().iqref_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def info(self):
+        out = (C.c_int32 * 6)()
+        lib().iqref_info(self._h, out)
+        return dict(vector_size=out[0], safe_numeric=bool(out[1]), num_threads=out[2], num_packets=out[3], kernel=out[4],
+                    partial_computations=out[5])
+
+    def clear_all_partial_lh(self):
+        lib().iqref_clear_all_partial_lh(self._h)
+
+    def branch_logl(self, leaf=0, want_cat=False):
+        """computeLikelihoodBranch on the pendant branch of alignment row `leaf` -> (logL, pattern_lh[, pattern_lh_cat])."""
+        plh = np.empty(self.nptn)
+        cat = np.empty((self.nptn, self.Cmix)) if want_cat else None
+        ll = lib().iqref_branch_logl(self._h, int(leaf), _p(plh), _p(cat) if want_cat else None)
+        return (ll, plh, cat) if want_cat else (ll, plh)
+
+    def compute_likelihood(self):
+        plh = np.empty(self.nptn)
+        return lib().iqref_compute_likelihood(self._h, _p(plh)), plh
+
+    def branch_derv(self, leaf=0):
+        df, ddf = C.c_double(), C.c_double()
+        lib().iqref_branch_derv(self._h, int(leaf), C.byref(df), C.byref(ddf))
+        return df.value, ddf.value
+
+    def logl_from_buffer(self):
+        return lib().iqref_logl_from_buffer(self._h)
+
+    def theta(self):
+        th, bs = np.empty((self.nptn, self.B)), np.empty(self.nptn)
+        lib().iqref_get_theta(self._h, _p(th), _p(bs))
+        return th, bs
+
+    def tip_partial_lh(self):
+        out = np.empty((self.model.state_unknown + 1, self.model.nmix, self.n))
+        lib().iqref_get_tip_partial_lh(self._h, _p(out))
+        return out
+
+    def ptn_invar(self):
+        out = np.empty(self.nptn)
+        lib().iqref_get_ptn_invar(self._h, _p(out))
+        return out
+
+    def directed_partials(self, want_partial=True):
+        """{frozenset(leaves of the subtree): (partial_lh [nptn][B] or None, scale_num)} for every computed directed CLV."""
+        res = {}
+        S = self.Cmix if self.safe else 1
+        for k in range(lib().iqref_num_directed(self._h)):
+            mask = np.zeros(self.ntaxa, dtype=np.uint8)
+            part = np.empty((self.nptn, self.B)) if want_partial else None
+            sc = np.empty((self.nptn, S), dtype=np.uint16)
+            if lib().iqref_get_directed(self._h, k, _p(mask), _p(part) if want_partial else None, _p(sc)):
+                res[frozenset(np.nonzero(mask)[0].tolist())] = (part, sc)
+        return res
+
+    def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
+        return lib().iqref_optimize_all_branches(self._h, C.c_int(int(iterations)), C.c_double(float(tolerance)), C.c_int(int(max_nr_step)))
+
+    def branches(self):
+        """{frozenset(side not containing taxon 0): length}"""
+        nb = 2 * self.ntaxa - 3
+        masks, lens = np.zeros((nb, self.ntaxa), dtype=np.uint8), np.zeros(nb)
+        k = lib().iqref_get_branches(self._h, _p(masks), _p(lens))
+        return {frozenset(np.nonzero(masks[b])[0].tolist()): float(lens[b]) for b in range(k)}
+
+    def time_eval(self, leaf=0, reps=3):
+        ll, df, ddf, mean = C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        best = lib().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))
+        return dict(best_sec=best, mean_sec=mean.value, logl=ll.value, df=df.value, ddf=ddf.value)
+
+    def last_traversal_size(self):
+        """partial updates the last branch_logl / branch_derv call scheduled (traversal_info.size())"""
+        return int(lib().iqref_last_traversal_size(self._h))

@@ -1,0 +1,442 @@
+// ref_harness.cpp — TEST INFRASTRUCTURE.  Drives the UNMODIFIED reference likelihood kernel
+// (IQ-TREE 2.4.0, tree/phylokernelnew.h instantiated by tree/phylokernelfma.cpp for Vec4d + FMA, dispatched
+// through PhyloTree's five pointers-to-member, tree/phylotreesse.cpp:91-236) behind a small C interface, so that
+//   (a) oracle/lk_oracle.c (the scalar restatement) and the CUDA engine can be pinned against the real thing, and
+//   (b) bench.py can time the reference's own AVX2/FMA OpenMP path on the host cores ("cpu_baseline.kind": "reference").
+//
+// Nothing here is reference source: this file only #includes the reference's headers where they lie under
+// /root/reference and calls its public members.  It is compiled by oracle/build_ref.sh together with the reference
+// TUs (compiled in place, objects and the .so go to oracle/_ref/, git-ignored).  Only tests/, smoke() and bench.py's
+// CPU arms may load the result.
+//
+// What the harness supplies itself (and why that is legitimate for a *kernel* oracle):
+//   * HModel / HRate: ModelSubst / RateHeterogeneity subclasses that return a caller-provided eigensystem
+//     (eval, evec, inv_evec per mixture class), mixture weights, state frequencies, category rates/proportions and
+//     p_invar.  The C ABI of the product takes the eigensystem as an input as well (the default
+//     eigensolver is Eigen3, absent here, and eigenvector sign/order is solver dependent), so parity is defined for
+//     identical eigensystems.  computeTipLikelihood's 0/1 indicator vectors follow model/modelsubst.cpp:197,
+//     model/modeldna.cpp:462, model/modelprotein.cpp:1149 (those TUs need ModelMarkov -> Eigen3).
+//   * link-time stubs for PhyloTree members defined in TUs that are not compiled (SSE/AVX kernel TUs).
+// Everything downstream — Alignment/Pattern, MTree::readTree, initializeAllPartialLh, computeTipPartialLikelihood,
+// computePtnFreq/Invar, computeTraversalInfo, computePartialInfo, the partial/branch/derv/from-buffer kernels,
+// optimizeOneBranch/optimizeAllBranches + minimizeNewton — is the reference's compiled code.
+#include <cstdint>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "alignment/alignment.h"
+#include "model/modelfactory.h"
+#include "model/modelsubst.h"
+#include "model/rateheterogeneity.h"
+#include "tree/phylotree.h"
+#include "utils/starttree.h"
+#include "utils/timeutil.h"
+#include "utils/tools.h"
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+
+namespace {
+
+// the kernels load eval/evec/inv_evec with aligned SIMD loads (the reference allocates them with aligned_alloc_double)
+struct AVec {
+    double *p = nullptr;
+    size_t n = 0;
+    ~AVec() { free(p); }
+    void assign(const double *a, const double *b) {
+        free(p);
+        n = (size_t)(b - a);
+        if (posix_memalign((void **)&p, 64, sizeof(double) * (n + 8)) != 0) abort();
+        memcpy(p, a, sizeof(double) * n);
+    }
+    double *data() const { return p; }
+    double &operator[](size_t i) const { return p[i]; }
+};
+
+struct HModel : public ModelSubst {
+    int nmix, seqtype;   // seqtype: 0 generic, 1 DNA, 2 protein (include/b200lk.h B200LK_SEQ_*)
+    int state_unknown;
+    AVec eval, evec, inv_evec;
+    std::vector<double> weight, freq;
+    HModel(int n, int nmix_, int seqtype_, int su) : ModelSubst(n), nmix(nmix_), seqtype(seqtype_), state_unknown(su) {
+        name = "HARNESS";
+        full_name = "harness-supplied eigensystem";
+    }
+    bool isReversible() override { return true; }
+    bool isMixture() override { return nmix > 1; }
+    int getNMixtures() override { return nmix; }
+    double getMixtureWeight(int cat) override { return weight[cat]; }
+    double *getEigenvalues() const override { return eval.data(); }
+    double *getEigenvectors() const override { return evec.data(); }
+    double *getInverseEigenvectors() const override { return inv_evec.data(); }
+    void getStateFrequency(double *f, int mixture = 0) override {
+        // mixture -1: weighted average over classes (ModelMixture::getStateFrequency, model/modelmixture.cpp)
+        if (mixture >= 0) { memcpy(f, &freq[(size_t)mixture * num_states], sizeof(double) * num_states); return; }
+        for (int i = 0; i < num_states; i++) f[i] = 0.0;
+        for (int m = 0; m < nmix; m++)
+            for (int i = 0; i < num_states; i++) f[i] += weight[m] * freq[(size_t)m * num_states + i];
+    }
+    void computeTipLikelihood(PML::StateType state, double *lk) override {
+        const int n = num_states;
+        for (int i = 0; i < n; i++) lk[i] = 0.0;
+        if ((int)state < n) { lk[state] = 1.0; return; }
+        if ((int)state == state_unknown) { for (int i = 0; i < n; i++) lk[i] = 1.0; return; }
+        if (seqtype == 1) {
+            int cstate = (int)state - n + 1;
+            for (int i = 0; i < n; i++) if ((cstate >> i) & 1) lk[i] = 1.0;
+        } else if (seqtype == 2) {
+            static const int ambi_aa[] = {4 + 8, 32 + 64, 512 + 1024};
+            int cstate = (int)state - n;
+            for (int i = 0; i < 11; i++) if (ambi_aa[cstate] & (1 << i)) lk[i] = 1.0;
+        } else {
+            for (int i = 0; i < n; i++) lk[i] = 1.0;
+        }
+    }
+    void startCheckpoint() override {}
+    void saveCheckpoint() override {}
+    void restoreCheckpoint() override {}
+};
+
+struct HRate : public RateHeterogeneity {
+    std::vector<double> rate, prop;
+    double pinv = 0.0;
+    int getNRate() override { return (int)rate.size(); }
+    int getNDiscreteRate() override { return (int)rate.size(); }
+    double getRate(int c) override { return rate[c]; }
+    double getProp(int c) override { return prop[c]; }
+    double getPInvar() override { return pinv; }
+    void startCheckpoint() override {}
+    void saveCheckpoint() override {}
+    void restoreCheckpoint() override {}
+};
+
+struct Handle {
+    Alignment *aln = nullptr;
+    PhyloTree *tree = nullptr;
+    HModel *model = nullptr;
+    HRate *rate = nullptr;
+    ModelFactory *fac = nullptr;
+    int n = 0, C = 0, B = 0, ntaxa = 0;
+    size_t nptn = 0;
+    std::vector<PhyloNode *> leaf;   // by alignment row
+    std::string err;
+};
+
+bool g_params_ready = false;
+
+// IQREF_DEBUG=1: print a symbolised backtrace on SIGSEGV (no debugger in the image)
+void segv_backtrace(int sig) {
+    void *frames[64];
+    int nf = backtrace(frames, 64);
+    backtrace_symbols_fd(frames, nf, 2);
+    _exit(128 + sig);
+}
+
+void init_params(int nthreads) {
+    Params &p = Params::getInstance();
+    if (!g_params_ready) {
+        if (getenv("IQREF_DEBUG")) signal(SIGSEGV, segv_backtrace);
+        char a0[] = "iqtree2", a1[] = "-s", a2[] = "harness.phy", a3[] = "-quiet";
+        char *argv[] = {a0, a1, a2, a3, nullptr};
+        parseArg(4, argv, p);
+        g_params_ready = true;
+    }
+    p.num_threads = nthreads;
+#ifdef _OPENMP
+    omp_set_num_threads(nthreads);
+#endif
+}
+
+PhyloNeighbor *nei_towards(PhyloNode *from, PhyloNode *to) { return (PhyloNeighbor *)from->findNeighbor(to); }
+
+void collect_leaves(Node *node, Node *dad, std::vector<uint8_t> &mask) {
+    if (node->isLeaf()) { mask[node->id] = 1; return; }
+    FOR_NEIGHBOR_IT(node, dad, it) collect_leaves((*it)->node, node, mask);
+}
+
+struct Directed { PhyloNeighbor *nei; PhyloNode *node, *dad; };   // nei = dad->findNeighbor(node): CLV of node's subtree seen from dad
+
+void collect_directed(PhyloNode *node, PhyloNode *dad, std::vector<Directed> &out) {
+    FOR_NEIGHBOR_IT(node, dad, it) {
+        PhyloNode *child = (PhyloNode *)(*it)->node;
+        // both directions of edge (node, child)
+        out.push_back({(PhyloNeighbor *)(*it), child, node});
+        out.push_back({nei_towards(child, node), node, child});
+        collect_directed(child, node, out);
+    }
+}
+
+}  // namespace
+
+// ---- link-time stubs for members whose TUs (phylokernelsse.cpp, phylotreeavx.cpp) are not compiled -------------
+void PhyloTree::setParsimonyKernelSSE() {}   // parsimony is not on the likelihood path
+void PhyloTree::setParsimonyKernelAVX() {}
+void PhyloTree::setDotProductSSE() {}
+void PhyloTree::setDotProductAVX() {}
+void PhyloTree::setLikelihoodKernelSSE() { outError("harness: SSE kernel TU not linked"); }
+void PhyloTree::setLikelihoodKernelAVX() { outError("harness: AVX kernel TU not linked"); }
+
+// parseArg (utils/tools.cpp:1015) asks the distance-tree factory for the name of its default builder (utils/starttree.cpp pulls
+// in every NJ/BIONJ implementation; none is on the likelihood path)
+const std::string &StartTree::Factory::getNameOfDefaultTreeBuilder() {
+    static const std::string name = "NONE";
+    return name;
+}
+
+extern "C" {
+
+struct iqref_desc {
+    int32_t nstates, ncat, nmix, fused_mix_rate, safe_numeric, seq_type, state_unknown, ntaxa;
+    int64_t nptn;
+    int32_t nthreads, reserved;
+    const uint8_t *states;      // [ntaxa][nptn]
+    const int32_t *ptn_freq;    // [nptn]
+    const char *newick;         // leaf names are alignment row numbers (PhyloTree::readTreeString)
+    const double *eval, *evec, *inv_evec, *mix_weight, *state_freq, *cat_rate, *cat_prop;
+    double pinvar;
+};
+
+void iqref_destroy(void *hv);
+
+void *iqref_create(const iqref_desc *d) {
+    init_params(d->nthreads > 0 ? d->nthreads : 1);
+    Params &params = Params::getInstance();
+    params.lk_safe_scaling = d->safe_numeric != 0;
+    Handle *h = new Handle();
+    const int n = d->nstates;
+    h->n = n; h->ntaxa = d->ntaxa; h->nptn = (size_t)d->nptn;
+    h->C = d->fused_mix_rate ? d->ncat : d->ncat * d->nmix;
+    h->B = n * h->C;
+
+    Alignment *aln = h->aln = new Alignment();
+    aln->num_states = n;
+    aln->seq_type = d->seq_type == 1 ? SEQ_DNA : d->seq_type == 2 ? SEQ_PROTEIN : SEQ_MORPH;
+    aln->STATE_UNKNOWN = (StateType)d->state_unknown;
+    for (int t = 0; t < d->ntaxa; t++) aln->seq_names.push_back("T" + std::to_string(t));
+    // one site per pattern occurrence is not needed by the kernel: site_pattern maps site -> pattern; we register
+    // each pattern once at its own site and carry the multiplicity in Pattern::frequency (alignment/pattern.h)
+    aln->site_pattern.resize(d->nptn, -1);
+    aln->reserve(d->nptn);
+    for (int64_t p = 0; p < d->nptn; p++) {
+        Pattern pat;
+        pat.resize(d->ntaxa);
+        for (int t = 0; t < d->ntaxa; t++) pat[t] = d->states[(size_t)t * d->nptn + p];
+        pat.frequency = d->ptn_freq ? d->ptn_freq[p] : 1;
+        aln->computeConst(pat);
+        aln->push_back(pat);             // no pattern merging: caller's pattern order is kept
+        aln->site_pattern[p] = (int)p;
+    }
+
+    HModel *m = h->model = new HModel(n, d->nmix, d->seq_type, d->state_unknown);
+    m->eval.assign(d->eval, d->eval + (size_t)d->nmix * n);
+    m->evec.assign(d->evec, d->evec + (size_t)d->nmix * n * n);
+    m->inv_evec.assign(d->inv_evec, d->inv_evec + (size_t)d->nmix * n * n);
+    m->weight.assign(d->mix_weight, d->mix_weight + d->nmix);
+    m->freq.assign(d->state_freq, d->state_freq + (size_t)d->nmix * n);
+    HRate *r = h->rate = new HRate();
+    r->rate.assign(d->cat_rate, d->cat_rate + d->ncat);
+    r->prop.assign(d->cat_prop, d->cat_prop + d->ncat);
+    r->pinv = d->pinvar;
+    ModelFactory *fac = h->fac = new ModelFactory();
+    fac->model = m;
+    fac->site_rate = r;
+    fac->fused_mix_rate = d->fused_mix_rate != 0;
+
+    PhyloTree *tree = h->tree = new PhyloTree();
+    tree->params = &params;
+    tree->aln = aln;                       // readTreeString -> assignLeafNames needs it only for named leaves
+    tree->readTreeString(std::string(d->newick));
+    tree->setAlignment(aln);
+    tree->setRootNode(params.root);
+    tree->sse = LK_AVX_FMA;
+    tree->num_threads = d->nthreads > 0 ? d->nthreads : 1;
+    tree->setModelFactory(fac);            // -> setLikelihoodKernel(sse) + setNumThreads
+    r->setTree(tree);
+    tree->initializeAllPartialLh();
+    h->leaf.assign(d->ntaxa, nullptr);
+    NodeVector taxa;
+    tree->getTaxa(taxa);
+    for (Node *x : taxa) if (x->id >= 0 && x->id < d->ntaxa) h->leaf[x->id] = (PhyloNode *)x;
+    for (auto *x : h->leaf) if (!x) { h->err = "leaf missing"; }
+    return h;
+}
+
+void iqref_destroy(void *hv) {
+    Handle *h = (Handle *)hv;
+    if (!h) return;
+    // the tree does not own model/rate here (model_factory is ours); detach before deletion
+    if (h->tree) { h->tree->model_factory = nullptr; h->tree->model = nullptr; h->tree->site_rate = nullptr; delete h->tree; }
+    delete h->fac; delete h->model; delete h->rate; delete h->aln;
+    delete h;
+}
+
+int iqref_info(void *hv, int32_t out[6]) {
+    Handle *h = (Handle *)hv;
+    out[0] = (int)h->tree->vector_size;
+    out[1] = h->tree->safe_numeric ? 1 : 0;
+    out[2] = h->tree->num_threads;
+    out[3] = h->tree->num_packets;
+    out[4] = (int)h->tree->sse;
+    out[5] = (int)h->tree->num_partial_lh_computations;
+    return 0;
+}
+
+void iqref_set_rates(void *hv, const double *rate, const double *prop, double pinvar) {
+    Handle *h = (Handle *)hv;
+    h->rate->rate.assign(rate, rate + h->rate->rate.size());
+    h->rate->prop.assign(prop, prop + h->rate->prop.size());
+    h->rate->pinv = pinvar;
+    h->tree->clearAllPartialLH();
+}
+
+void iqref_clear_all_partial_lh(void *hv) { ((Handle *)hv)->tree->clearAllPartialLH(); }
+
+// computeLikelihoodBranch on the pendant branch of alignment row `leaf` (dad = the leaf, dad_branch = leaf -> inner)
+double iqref_branch_logl(void *hv, int leaf, double *pattern_lh, double *pattern_lh_cat) {
+    Handle *h = (Handle *)hv;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
+    h->tree->current_it = nb;
+    h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    double ll = h->tree->computeLikelihoodBranch(nb, L);
+    if (pattern_lh) memcpy(pattern_lh, h->tree->_pattern_lh, sizeof(double) * h->nptn);
+    if (pattern_lh_cat) {
+        // _pattern_lh_cat is V-interleaved until transformPatternLhCat (tree/phylotree.cpp:1313); de-interleave here
+        const size_t V = h->tree->vector_size, C = h->C;
+        for (size_t p = 0; p < h->nptn; p++)
+            for (size_t c = 0; c < C; c++) pattern_lh_cat[p * C + c] = h->tree->_pattern_lh_cat[(p / V) * C * V + c * V + p % V];
+    }
+    return ll;
+}
+
+// PhyloTree::computeLikelihood (tree/phylotree.cpp:1233): the tree picks the branch itself
+double iqref_compute_likelihood(void *hv, double *pattern_lh) { return ((Handle *)hv)->tree->computeLikelihood(pattern_lh); }
+
+void iqref_branch_derv(void *hv, int leaf, double *df, double *ddf) {
+    Handle *h = (Handle *)hv;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
+    h->tree->current_it = nb;
+    h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    h->tree->theta_computed = false;
+    h->tree->computeLikelihoodDerv(nb, L, df, ddf);
+}
+
+double iqref_logl_from_buffer(void *hv) { return ((Handle *)hv)->tree->computeLikelihoodFromBuffer(); }
+
+// one full evaluation of SURVEY §8(d): clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv;
+// returns seconds (getRealTime, utils/timeutil.h:138), best of `reps`
+double iqref_time_eval(void *hv, int leaf, int reps, double *logl, double *df, double *ddf, double *mean_sec) {
+    Handle *h = (Handle *)hv;
+    double best = 1e300, sum = 0.0;
+    for (int r = 0; r < reps; r++) {
+        double t0 = getRealTime();
+        h->tree->clearAllPartialLH();
+        *logl = iqref_branch_logl(hv, leaf, nullptr, nullptr);
+        iqref_branch_derv(hv, leaf, df, ddf);
+        double t = getRealTime() - t0;
+        sum += t;
+        if (t < best) best = t;
+    }
+    if (mean_sec) *mean_sec = sum / reps;
+    return best;
+}
+
+// every directed CLV that is currently computed: count, then fetch k-th as (leaf mask of the subtree, partial_lh
+// de-interleaved to [p][B], scale_num [p] (NORM) or [p][C] (SAFE))
+static void all_directed(Handle *h, std::vector<Directed> &v) {
+    PhyloNode *root = (PhyloNode *)h->tree->root;
+    collect_directed(root, nullptr, v);
+}
+
+int iqref_num_directed(void *hv) {
+    Handle *h = (Handle *)hv;
+    std::vector<Directed> v;
+    all_directed(h, v);
+    return (int)v.size();
+}
+
+// returns 1 if the k-th directed CLV is an internal node's and is computed (outputs filled), else 0
+int iqref_get_directed(void *hv, int k, uint8_t *leafmask, double *partial, uint16_t *scale) {
+    Handle *h = (Handle *)hv;
+    std::vector<Directed> v;
+    all_directed(h, v);
+    const Directed &d = v[k];
+    if (d.node->isLeaf() || !d.nei->partial_lh || !(d.nei->partial_lh_computed & 1)) return 0;
+    std::vector<uint8_t> mask(h->ntaxa, 0);
+    collect_leaves(d.node, d.dad, mask);
+    memcpy(leafmask, mask.data(), h->ntaxa);
+    const size_t V = h->tree->vector_size, B = h->B, C = h->C;
+    if (partial)
+        for (size_t p = 0; p < h->nptn; p++)
+            for (size_t k2 = 0; k2 < B; k2++) partial[p * B + k2] = d.nei->partial_lh[(p / V) * B * V + k2 * V + p % V];
+    if (scale) {
+        if (h->tree->safe_numeric) memcpy(scale, d.nei->scale_num, sizeof(uint16_t) * h->nptn * C);
+        else memcpy(scale, d.nei->scale_num, sizeof(uint16_t) * h->nptn);
+    }
+    return 1;
+}
+
+int iqref_get_theta(void *hv, double *theta, double *buffer_scale_all) {
+    Handle *h = (Handle *)hv;
+    const size_t V = h->tree->vector_size, B = h->B;
+    for (size_t p = 0; p < h->nptn; p++)
+        for (size_t k = 0; k < B; k++) theta[p * B + k] = h->tree->theta_all[(p / V) * B * V + k * V + p % V];
+    if (buffer_scale_all) memcpy(buffer_scale_all, h->tree->buffer_scale_all, sizeof(double) * h->nptn);
+    return 0;
+}
+
+int iqref_get_tip_partial_lh(void *hv, double *out) {
+    Handle *h = (Handle *)hv;
+    h->tree->computeTipPartialLikelihood();
+    memcpy(out, h->tree->tip_partial_lh, sizeof(double) * (h->model->state_unknown + 1) * h->model->nmix * h->n);
+    return 0;
+}
+
+int iqref_get_ptn_invar(void *hv, double *out) {
+    Handle *h = (Handle *)hv;
+    h->tree->computeTipPartialLikelihood();
+    memcpy(out, h->tree->ptn_invar, sizeof(double) * h->nptn);
+    return 0;
+}
+
+// PhyloTree::optimizeAllBranches (tree/phylotree.cpp:2698); returns the tree log-likelihood
+double iqref_optimize_all_branches(void *hv, int iterations, double tolerance, int max_nr_step) {
+    Handle *h = (Handle *)hv;
+    return h->tree->optimizeAllBranches(iterations, tolerance, max_nr_step);
+}
+
+// branch lengths keyed by split: for each branch, mask[ntaxa] of the side NOT containing taxon 0, and its length
+int iqref_get_branches(void *hv, uint8_t *masks /* [nbranch][ntaxa] */, double *lengths) {
+    Handle *h = (Handle *)hv;
+    NodeVector n1, n2;
+    h->tree->getBranches(n1, n2);
+    for (size_t b = 0; b < n1.size(); b++) {
+        std::vector<uint8_t> mask(h->ntaxa, 0);
+        collect_leaves(n2[b], n1[b], mask);
+        if (mask[0]) for (auto &x : mask) x = !x;
+        memcpy(masks + b * h->ntaxa, mask.data(), h->ntaxa);
+        lengths[b] = n1[b]->findNeighbor(n2[b])->length;
+    }
+    return (int)n1.size();
+}
+
+// entries of traversal_info left by the last computeLikelihoodBranch / computeLikelihoodDerv call (= partial updates it ran;
+// the new kernel does not maintain num_partial_lh_computations)
+int iqref_last_traversal_size(void *hv) { return (int)((Handle *)hv)->tree->traversal_info.size(); }
+
+int iqref_max_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+}  // extern "C"

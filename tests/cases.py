@@ -7,23 +7,11 @@ from iqtree2_b200 import models, treesim
 
 
 def ptn_invar_for(model, pat):
-    """computePtnInvar (tree/phylotreesse.cpp:549-612) for unambiguous constant patterns and all-gap patterns."""
-    nptn = pat.shape[1]
-    inv = np.zeros(nptn)
-    if model.pinvar == 0:
-        return inv
-    freq = model.state_freq.reshape(model.nmix, model.nstates)[0]
-    for p in range(nptn):
-        col = pat[:, p]
-        real = col[col < model.nstates]
-        other = col[col >= model.nstates]
-        if not (other == model.state_unknown).all():
-            continue
-        if real.size == 0:
-            inv[p] = model.pinvar
-        elif (real == real[0]).all():
-            inv[p] = model.pinvar * freq[real[0]]
-    return inv
+    """computePtnInvar (tree/phylotreesse.cpp:549-612) with Pattern::const_char from Alignment::computeConst; +I uses
+    the mixture-averaged state frequencies (getStateFrequency(.., -1))."""
+    from iqtree2_b200 import alignment
+    freq = (model.mix_weight[:, None] * model.state_freq.reshape(model.nmix, model.nstates)).sum(axis=0)
+    return alignment.ptn_invar(pat, freq, model.pinvar, model.nstates, model.state_unknown, model.seq_type)
 
 
 def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, tree_kind="yule", mean_len=0.1):

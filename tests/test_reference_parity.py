@@ -1,0 +1,135 @@
+"""CPU: the oracle (oracle/lk_oracle.c) and the host-side tree logic pinned against the REAL reference kernel —
+IQ-TREE 2.4.0's own translation units compiled in place into oracle/_ref/libiqref.so (oracle/build_ref.sh) and driven
+through PhyloTree's public members by oracle/ref_harness.cpp.  Bars (BASELINE.json north_star): scale_num bit-exact,
+per-pattern logL 1e-11 relative, tree logL 1e-6, optimised branch lengths 1e-6.  The oracle follows the reference's
+summation orders, so the observed differences are at the 1e-14 level and the asserts are set far tighter than the bars."""
+import numpy as np
+import pytest
+
+from cases import load_engine, make_case
+from iqtree2_b200 import plan
+from oracle import ref_engine
+from oracle.oracle_engine import OracleEngine
+from refmap import branch_splits, pytree_splits, slot_leafsets
+from test_tree_logic_cpu import example_case, make_pytree
+
+pytestmark = pytest.mark.skipif(not ref_engine.available(), reason="oracle/_ref/libiqref.so not built (needs /root/reference)")
+
+# (kind, safe) — safe is what the reference itself would pick (tree/phylotreesse.cpp:95-96: SAFE unless nstates in {4,20}),
+# plus explicit -safe runs for DNA / protein
+CASES = [("dna", False), ("dna", True), ("dna_inv", False), ("dna_g1", False), ("dna_g8", False), ("aa", False), ("aa", True),
+         ("aa_c4", False), ("bin", True), ("codon", True), ("n5mix", True), ("n7", True)]
+
+
+def run_pair(kind, safe, ntaxa=14, nsites=400, leaf=0, **kw):
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=ntaxa, nsites=nsites, **kw)
+    r = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe)
+    assert r.info()["safe_numeric"] == safe and r.info()["vector_size"] == 4
+    o = load_engine(OracleEngine, tree, model, pat, freq, inv, safe=safe)
+    o.set_reference_quirks(1)
+    br = plan.pendant_branch_of(tree, leaf)
+    ops, a, b, L = plan.plan_branch(tree, br)
+    return tree, model, pat, freq, inv, r, o, br, ops, a, b, L
+
+
+@pytest.mark.parametrize("kind,safe", CASES)
+def test_oracle_matches_reference_kernel(kind, safe):
+    tree, model, pat, freq, inv, r, o, br, ops, a, b, L = run_pair(kind, safe)
+    np.testing.assert_array_equal(r.ptn_invar(), inv)                      # computePtnInvar + computeConst
+    np.testing.assert_allclose(o.get_tip_partial_lh().ravel(), r.tip_partial_lh().ravel(), rtol=1e-13, atol=1e-15)
+    ll_r, plh_r, cat_r = r.branch_logl(0, want_cat=True)
+    ll_o = o.branch_logl(ops, a, b, L)
+    assert abs(ll_o - ll_r) < 1e-9, (ll_o, ll_r)
+    np.testing.assert_allclose(o.get_pattern_lh(), plh_r, rtol=1e-12)
+    cmax = np.abs(cat_r).max(axis=1, keepdims=True)   # categories that contribute nothing to a pattern carry cancellation noise
+    np.testing.assert_allclose(o.get_pattern_lh_cat().reshape(cat_r.shape) / cmax, cat_r / cmax, rtol=1e-11, atol=1e-13)
+    assert r.last_traversal_size() == len(ops)
+    # every CLV of the traversal: scale_num bit-exact, partial_lh to 1e-12 of the pattern's largest entry
+    ref = r.directed_partials()
+    sets = slot_leafsets(tree, br)
+    assert len(ops) == tree.ntaxa - 2
+    for op in ops:
+        slot = int(op["dst_slot"])
+        part_r, sc_r = ref[sets[slot]]
+        np.testing.assert_array_equal(o.get_scale_num(slot).reshape(sc_r.shape), sc_r)
+        part_o = o.get_partial(slot).reshape(part_r.shape)
+        scale = np.abs(part_r).max(axis=1, keepdims=True)
+        np.testing.assert_allclose(part_o / scale, part_r / scale, rtol=0, atol=1e-12)
+    # derivatives (theta buffer, df, ddf) and the from-buffer likelihood
+    df_r, ddf_r = r.branch_derv(0)
+    df_o, ddf_o = o.branch_derv(ops[:0], a, b, L)
+    assert abs(df_o - df_r) <= 1e-9 * max(1.0, abs(df_r)), (df_o, df_r)
+    assert abs(ddf_o - ddf_r) <= 1e-9 * max(1.0, abs(ddf_r)), (ddf_o, ddf_r)
+    th_r, bs_r = r.theta()
+    th_o = o.get_theta().reshape(th_r.shape)
+    scale = np.abs(th_r).max(axis=1, keepdims=True) + 1e-300
+    np.testing.assert_allclose(th_o / scale, th_r / scale, rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(o.get_buffer_scale_all(), bs_r)
+    assert abs(o.logl_from_buffer(L) - r.logl_from_buffer()) < 1e-9
+
+
+def test_reference_dotproducttriple_double_counts_last_element():
+    """Documents the reference defect behind B200LK_QUIRK_DOTTRIPLE_ODD: with odd nstates and an even block the
+    reference's (df, ddf) are NOT the derivatives of its own logL; without the quirk the oracle's are."""
+    tree, model, pat, freq, inv, r, o, br, ops, a, b, L = run_pair("n5mix", True)
+    assert model.nstates % 2 == 1 and (model.nstates * model.ncat_mix) % 2 == 0
+    o.branch_logl(ops, a, b, L)
+    df_q, _ = o.branch_derv(ops[:0], a, b, L)
+    df_r, _ = r.branch_derv(0)
+    assert abs(df_q - df_r) <= 1e-9 * max(1.0, abs(df_r))
+    o.set_reference_quirks(0)
+    o.theta_reset()
+    df_m, ddf_m = o.branch_derv(ops[:0], a, b, L)
+    h = 1e-6
+    num = (o.logl_from_buffer(L + h) - o.logl_from_buffer(L - h)) / (2 * h)
+    assert abs(df_m - num) < 1e-4 * max(1.0, abs(num))
+    assert abs(df_r - num) > 1e-2 * max(1.0, abs(num))
+
+
+@pytest.mark.parametrize("kind,safe", [("dna", False), ("dna", True), ("aa", False)])
+def test_scale_num_parity_on_deep_trees(kind, safe):
+    """caterpillar trees with long branches: scale_num climbs well above 1 and must stay bit-exact"""
+    tree, model, pat, freq, inv, r, o, br, ops, a, b, L = run_pair(kind, safe, ntaxa=500 if kind == "dna" else 200, nsites=40,
+                                                               tree_kind="caterpillar", mean_len=1.5, gaps=0.0, ambig=0.0)
+    ll_r, plh_r = r.branch_logl(0)
+    ll_o = o.branch_logl(ops, a, b, L)
+    ref = r.directed_partials(want_partial=False)
+    sets = slot_leafsets(tree, br)
+    top = 0
+    for op in ops:
+        slot = int(op["dst_slot"])
+        sc_o = o.get_scale_num(slot)
+        np.testing.assert_array_equal(sc_o.reshape(ref[sets[slot]][1].shape), ref[sets[slot]][1])
+        top = max(top, int(sc_o.max()))
+    assert top >= 2, top
+    np.testing.assert_allclose(o.get_pattern_lh(), plh_r, rtol=1e-12)
+    assert abs(ll_o - ll_r) < 1e-8 * max(1.0, abs(ll_r) * 1e-3)
+
+
+def test_reference_threads_agree():
+    tree, model, pat, freq, inv = make_case("dna", ntaxa=20, nsites=3000)
+    r1 = ref_engine.RefTree(tree, model, pat, freq, nthreads=1)
+    r4 = ref_engine.RefTree(tree, model, pat, freq, nthreads=4)
+    assert r4.info()["num_threads"] == 4
+    (l1, p1), (l4, p4) = r1.branch_logl(3), r4.branch_logl(3)
+    np.testing.assert_array_equal(p1, p4)
+    assert abs(l1 - l4) < 1e-8
+
+
+def test_config1_tree_level_logic_matches_reference():
+    """BASELINE config 1 (example.phy + NJ tree, GTR+G4): computeLikelihood and optimizeAllBranches of the compiled
+    reference against the Python restatement of the tree logic over the oracle."""
+    names, pat, freq, model, newick = example_case()
+    r = ref_engine.RefTree(None, model, pat, freq, newick=newick, names=names)
+    t = make_pytree(names, pat, freq, model, newick)
+    ll_r, plh_r = r.compute_likelihood()
+    ll_t = t.compute_likelihood()
+    assert abs(ll_t - ll_r) < 1e-8
+    np.testing.assert_allclose(t.engine.get_pattern_lh(), plh_r, rtol=1e-12)
+    assert r.last_traversal_size() == t.num_partial == 15
+    ll_r = r.optimize_all_branches(100, 0.001, 100)
+    ll_t = t.optimize_all_branches(100, 0.001, 100)
+    assert abs(ll_t - ll_r) < 1e-6, (ll_t, ll_r)
+    ref_len = r.branches()
+    for split, ln in zip(pytree_splits(t), t.lengths()):
+        assert abs(ref_len[split] - ln) < 1e-6, (sorted(split), ref_len[split], ln)
