@@ -106,7 +106,7 @@ void PhyloTree::setModel(int ncat, int nmix, bool fused, const double *eval, con
 
 // ---------------------------------------------------------------------------------------------------------------
 // Newick I/O (MTree::readTree / printTree, tree/mtree.cpp:686-877): unrooted, leaf ids = alignment rows,
-// internal ids = leafNum.. in creation order, root = the leaf read first
+// internal ids = leafNum.. in creation order, root = the leaf of alignment row 0
 // ---------------------------------------------------------------------------------------------------------------
 void PhyloTree::readTreeString(const std::string &newick) {
     deleteAllPartialLh();
@@ -202,7 +202,11 @@ void PhyloTree::readTreeString(const std::string &newick) {
         if (!n->isLeaf() && n->neighbors.size() != 3) throw std::runtime_error("readTreeString: multifurcating trees are not supported yet");
     for (auto &br : branches_)
         if (br.first->length < 0) br.first->length = br.second->length = params.min_branch_length;
+    // PhyloTree::readTreeString -> setRootNode(params.root == NULL): root = the leaf of alignment row 0
+    // (tree/phylotree.cpp:462-472)
     root = first_leaf;
+    for (auto *n : nodes_)
+        if (n->isLeaf() && n->id == 0) root = n;
 }
 
 std::string PhyloTree::getTreeString(int precision) const {

@@ -47,7 +47,7 @@ def lib():
             raise FileNotFoundError(LIB + " (run oracle/build_ref.sh where /root/reference is mounted)")
         _lib = C.CDLL(LIB)
         _lib.iqref_create.restype = C.c_void_p
-        for f in ("iqref_branch_logl", "iqref_compute_likelihood", "iqref_logl_from_buffer", "iqref_time_eval",
+        for f in ("iqref_optimize_one_branch", "iqref_branch_logl", "iqref_compute_likelihood", "iqref_logl_from_buffer", "iqref_time_eval",
                   "iqref_optimize_all_branches"):
             getattr(_lib, f).restype = C.c_double
     return _lib
@@ -159,6 +159,16 @@ class RefTree:
 
     def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
         return lib().iqref_optimize_all_branches(self._h, C.c_int(int(iterations)), C.c_double(float(tolerance)), C.c_int(int(max_nr_step)))
+
+    def optimize_one_branch(self, leaf, max_nr_step=100):
+        return lib().iqref_optimize_one_branch(self._h, C.c_int(int(leaf)), C.c_int(int(max_nr_step)))
+
+    def best_traversal(self):
+        """the branch order optimizeAllBranches walks, as splits (side not containing taxon 0)"""
+        nb = 2 * self.ntaxa - 3
+        masks = np.zeros((nb, self.ntaxa), dtype=np.uint8)
+        k = lib().iqref_best_traversal(self._h, _p(masks))
+        return [frozenset(np.nonzero(masks[b])[0].tolist()) for b in range(k)]
 
     def branches(self):
         """{frozenset(side not containing taxon 0): length}"""

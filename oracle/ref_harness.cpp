@@ -208,6 +208,13 @@ void *iqref_create(const iqref_desc *d) {
     init_params(d->nthreads > 0 ? d->nthreads : 1);
     Params &params = Params::getInstance();
     params.lk_safe_scaling = d->safe_numeric != 0;
+    // what runPhyloAnalysis does after loading the alignment (main/phyloanalysis.cpp:4424-4430): parseArg leaves
+    // min_branch_length at 0; it is also minimizeNewton's tolerance (tree/phylotree.cpp:2612)
+    {
+        double nsites = 0;
+        for (int64_t p = 0; p < d->nptn; p++) nsites += d->ptn_freq ? d->ptn_freq[p] : 1;
+        params.min_branch_length = nsites >= 100000 ? 0.1 / nsites : 1e-6;
+    }
     Handle *h = new Handle();
     const int n = d->nstates;
     h->n = n; h->ntaxa = d->ntaxa; h->nptn = (size_t)d->nptn;
@@ -410,6 +417,30 @@ int iqref_get_ptn_invar(void *hv, double *out) {
 double iqref_optimize_all_branches(void *hv, int iterations, double tolerance, int max_nr_step) {
     Handle *h = (Handle *)hv;
     return h->tree->optimizeAllBranches(iterations, tolerance, max_nr_step);
+}
+
+// PhyloTree::optimizeOneBranch (tree/phylotree.cpp:2594) on the pendant branch of alignment row `leaf`; returns the new length
+double iqref_optimize_one_branch(void *hv, int leaf, int max_nr_step) {
+    Handle *h = (Handle *)hv;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNode *inner = (PhyloNode *)L->neighbors[0]->node;
+    h->tree->optimizeOneBranch(L, inner, true, max_nr_step);
+    return L->neighbors[0]->length;
+}
+
+// the branch order optimizeAllBranches walks (computeBestTraversal, tree/phylotree.cpp:2689): for each branch the leaf
+// mask of the side not containing taxon 0
+int iqref_best_traversal(void *hv, uint8_t *masks) {
+    Handle *h = (Handle *)hv;
+    NodeVector n1, n2;
+    h->tree->computeBestTraversal(n1, n2);
+    for (size_t b = 0; b < n1.size(); b++) {
+        std::vector<uint8_t> mask(h->ntaxa, 0);
+        collect_leaves(n2[b], n1[b], mask);
+        if (mask[0]) for (auto &x : mask) x = !x;
+        memcpy(masks + b * h->ntaxa, mask.data(), h->ntaxa);
+    }
+    return (int)n1.size();
 }
 
 // branch lengths keyed by split: for each branch, mask[ntaxa] of the side NOT containing taxon 0, and its length

@@ -107,7 +107,9 @@ class PyTree:
         for ab, ba in self.branches:
             if ab.length < 0:
                 ab.length = ba.length = self.min_bl
-        self.root = first_leaf[0]
+        # PhyloTree::readTreeString -> setRootNode(params.root == NULL): root = the leaf of alignment row 0
+        # (tree/phylotree.cpp:462-472), not the leaf read first
+        self.root = next(n for n in self.nodes if n.is_leaf() and n.id == 0)
 
     def _assign_slots(self):
         idx = 0
