@@ -188,6 +188,7 @@ def main():
     ap.add_argument("--taxa", type=int, default=0, help="override taxa (debug)")
     ap.add_argument("--patterns", type=int, default=0, help="override patterns (debug)")
     ap.add_argument("--schedule", type=int, default=0, help="0 auto, 1 levelled, 2 walker")
+    ap.add_argument("--variant", type=int, default=0, help="kernel variant of the walker schedule (development A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -257,6 +258,8 @@ def main():
 
     eng = LikelihoodEngine(model, ntaxa, my_nptn, device=local_rank, schedule=args.schedule)
     stream = torch.cuda.current_stream()
+    if args.variant:
+        eng.set_schedule(10 + args.variant)
     eng.set_stream(stream.cuda_stream)
     eng.set_tip_states(tips)
     eng.set_pattern_freq(freq)

@@ -51,6 +51,9 @@ struct b200lk_engine {
     int schedule = 0;
     int num_sms = 148;
     int info_smem_optin = 0;
+    bool walk20_attr_set = false;
+    int kernel_variant = 0;   // b200lk_set_schedule(e, 10 + v): development switch between kernel variants of one schedule
+    int walk20_ctas_per_sm = 1;
     // profiling
     bool profiling = false;
     bool partials_timed = false;
@@ -210,6 +213,11 @@ extern "C" int b200lk_set_stream(b200lk_engine *e, void *cuda_stream) {
 }
 
 extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
+    if (schedule >= 10 && schedule < 20) {   // development switch: kernel variant of the walker schedule (A/B measurements)
+        e->kernel_variant = schedule - 10;
+        e->walk20_attr_set = false;
+        return 0;
+    }
     if (schedule < 0 || schedule > 2) return fail(e, B200LK_ERR_INVALID, "schedule must be 0, 1 or 2");
     e->schedule = schedule;
     return 0;
@@ -402,12 +410,86 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     return 0;
 }
 
+// the 20-state walker (k_walk_n20) serves the walker schedule of every single-class protein model, any number of categories
+static size_t walk20_smem(const b200lk_engine *e) {
+    return sizeof(double) * (2 * (size_t)e->B + 2 * (size_t)(e->cfg.state_unknown + 1) * tab20_stride(e->C));
+}
+static bool use_walk20(const b200lk_engine *e) {
+    return e->schedule != 1 && e->cfg.nstates == 20 && e->cfg.nmix == 1 && e->h_evec.size() == 400 && walk20_smem(e) <= 100 * 1024;
+}
+
+static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    const size_t stage_sz = stage20_doubles(e->C, e->cfg.state_unknown);
+    if (stage_sz * nops > e->opinfo_cap) {
+        CK(cudaStreamSynchronize(e->stream));
+        if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
+        e->d_opinfo = nullptr; e->opinfo_cap = 0;
+        int rc = dev_alloc(e, &e->d_opinfo, stage_sz * nops);
+        if (rc) return rc;
+        e->opinfo_cap = stage_sz * nops;
+        e->d.opinfo = e->d_opinfo;
+    }
+    WalkJob20 *hj = (WalkJob20 *)e->h_stage;
+    static_assert(sizeof(WalkJob20) <= sizeof(DevOp) + 2 * sizeof(ChildJob), "pinned staging buffer too small for WalkJob20");
+    CK(cudaStreamSynchronize(e->stream));   // the pinned staging buffer may still be in flight
+    for (int k = 0; k < nops; k++) {
+        const b200lk_op &op = ops[k];
+        int rc = validate_op(e, op);
+        if (rc) return rc;
+        const b200lk_child *A = &op.left, *B = &op.right;
+        WalkJob20 &j = hj[k];
+        if (A->kind == 0 && B->kind == 0) j.ncase = 0;
+        else if (A->kind == 1 && B->kind == 1) j.ncase = 2;
+        else { j.ncase = 1; if (A->kind == 1) std::swap(A, B); }   // A = the tip
+        j.lenA = A->length; j.lenB = B->length;
+        j.aid = A->id; j.bid = B->id;
+        j.dst = op.dst_slot;
+    }
+    WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
+    CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
+    k_walk_info_n20<<<nops, 256, sizeof(double) * 2 * e->B, e->stream>>>(e->d, dj, e->d_opinfo);
+    const bool use_mma = e->kernel_variant != 1;   // variant 1 = the DFMA/constant-bank kernel (kept for A/B measurements)
+    Model20 Mloc;   // 6.4 KB kernel parameter, passed by value
+    if (!use_mma) for (int k = 0; k < 400; k++) { Mloc.evec[k] = e->h_evec[k]; Mloc.inv[k] = e->h_inv_evec[k]; }
+    const long long ntiles = e->Ppad / kTile;
+    const size_t smem = walk20_smem(e);
+    if (!e->walk20_attr_set) {
+        CK(cudaFuncSetAttribute(k_walk_n20<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_walk_n20<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_walk_n20_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(k_walk_n20_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20_mma<false>, kTile, smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20<false>, kTile, smem));
+        e->walk20_ctas_per_sm = std::max(per_sm, 1);
+        e->walk20_attr_set = true;
+    }
+    const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * e->walk20_ctas_per_sm);
+    CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
+    if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+    if (use_mma) {
+        if (e->cfg.safe_numeric) k_walk_n20_mma<true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        else k_walk_n20_mma<false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+    } else {
+        if (e->cfg.safe_numeric) k_walk_n20<true><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
+        else k_walk_n20<false><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
+    }
+    if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+    e->partials_timed = e->profiling;
+    e->launches += 2;
+    e->last_launch[0] += 2;
+    CK(cudaGetLastError());
+    e->theta_computed = false;
+    return 0;
+}
+
 // Enqueue (no sync) everything computePartialLikelihood needs for the op list.
 static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     if (nops <= 0) return 0;
     int rc = ensure_op_capacity(e, nops);
     if (rc) return rc;
     if (use_walk4(e)) return enqueue_walk4(e, ops, nops);
+    if (use_walk20(e)) return enqueue_walk20(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
     DevOp *hops = (DevOp *)e->h_stage;

@@ -645,6 +645,394 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 20-state WALKER (LG/WAG/JTT... +G/+I+G/+R, single class): the FP64-bound kernel of BASELINE config 3.
+//
+// Per pattern, category and child the update is a 20x20 mat-vec; three of them per inner-inner node (two children,
+// one back-transform) = C*(6n^2+n) flops against 3*(8B+2S) bytes (about 5 flop/B): on B200 this sits on the FP64 side of
+// the ridge (64 DFMA/clk/SM = 36 TFLOP/s against 6.5 TB/s).  B200's FP64 tensor path (mma.sync m8n8k4.f64, DMMA) has the
+// SAME peak as its DFMA pipe (measured 37.2 vs 36.3 TFLOP/s, scripts/fp64_peaks.cu), and 20 is not a multiple of the
+// 8-wide MMA tile (24/20 = 17 % padding), so DMMA would be slower here; tcgen05/TMEM have no FP64 kind at all.  The
+// kernel therefore aims at the DFMA pipe's peak: one instruction per FMA, no shared-memory or register traffic for
+// the matrices:
+//   * the operator is applied factorised, evec . (exp(eval r_c t) (.) L)  (tree/phylokernelnew.h:1016-1031 builds
+//     echild = evec*exp explicitly), so that the only matrices are the model's evec and inv_evec; they travel as a
+//     6.4 KB __grid_constant__ kernel parameter, i.e. constant-bank operands of the DFMAs (SASS: DFMA R, R, c[0x0][..], R);
+//   * per-op data is 2 x C x 20 exponentials; tip children use the reference's lookup tables
+//     partial_lh_leaves[state][c][x] (:1036-1056), staged in shared memory per op;
+//   * thread per pattern, whole traversal per 128-pattern tile (same schedule as k_walk_n4c4), CLVs warp-interleaved.
+// ------------------------------------------------------------------------------------------------------------
+struct Model20 {
+    double evec[400];   // evec[x*20 + i]
+    double inv[400];    // inv_evec[i*20 + x]
+};
+
+struct WalkJob20 {
+    double lenA, lenB;
+    int32_t dst, ncase, aid, bid;   // ncase: 0 tip-tip, 1 tip(A)-inner(B), 2 inner-inner; ids: taxon row or slot
+};
+
+// staging block per op (doubles): header[4] | expA[C*20] | expB[C*20] | tabA[(su+1)][C*20 + 2] | tabB[(su+1)][C*20 + 2]
+// (table rows padded by 2 doubles: a row stride of C*20 doubles is a multiple of 32 banks for C = 4, which would put the
+// same (c, x) entry of every state in the same bank — a 20-way conflict when the lanes of a warp hold different states)
+__host__ __device__ inline int tab20_stride(int C) { return C * 20 + 2; }
+__host__ __device__ inline size_t stage20_doubles(int C, int su) { return 4 + 2 * (size_t)C * 20 + 2 * (size_t)(su + 1) * tab20_stride(C); }
+
+__global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *jobs, double *stage) {
+    extern __shared__ double s_exp20[];   // [2][C*20]
+    const int C = D.C, B = C * 20, TS = tab20_stride(C);
+    const WalkJob20 job = jobs[blockIdx.x];
+    double *st = stage + (size_t)blockIdx.x * stage20_doubles(C, D.su);
+    for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
+        const int ch = k / B, kk = k - ch * B, c = kk / 20, i = kk - c * 20;
+        const double len_child = D.cat_rate[c % D.ncat] * (ch ? job.lenB : job.lenA);   // :1017
+        const double v = exp(D.eval[i] * len_child);                                     // :1022
+        s_exp20[k] = v;
+        st[4 + k] = v;
+    }
+    if (threadIdx.x == 0) {
+        int32_t *h = reinterpret_cast<int32_t *>(st);
+        h[0] = job.dst; h[1] = job.ncase; h[2] = job.aid; h[3] = job.bid; h[4] = h[5] = h[6] = h[7] = 0;
+    }
+    __syncthreads();
+    // partial_lh_leaves[state][c][x] for tip children (:1036-1056: Vec4d lane accumulators + horizontal_add)
+    const int rows = D.su + 1;
+    for (int ch = 0; ch < 2; ch++) {
+        const bool is_tip = ch == 0 ? (job.ncase <= 1) : (job.ncase == 0);
+        if (!is_tip) continue;
+        double *tab = st + 4 + 2 * B + (size_t)ch * rows * TS;
+        const double *ex = s_exp20 + ch * B;
+        for (int k = threadIdx.x; k < rows * TS; k += blockDim.x) {
+            const int state = k / TS, cx = k - state * TS;
+            if (cx >= B) { tab[k] = 0.0; continue; }
+            const int c = cx / 20, x = cx - c * 20;
+            if (state == D.su) { tab[k] = 1.0; continue; }
+            const double *tip = D.tip_lh + state * 20;
+            const double *ev = D.evec + x * 20;
+            const double *e = ex + c * 20;
+            double a0 = (ev[0] * e[0]) * tip[0], a1 = (ev[1] * e[1]) * tip[1], a2 = (ev[2] * e[2]) * tip[2], a3 = (ev[3] * e[3]) * tip[3];
+#pragma unroll
+            for (int i = 4; i < 20; i += 4) {
+                a0 = fma(ev[i] * e[i], tip[i], a0); a1 = fma(ev[i + 1] * e[i + 1], tip[i + 1], a1);
+                a2 = fma(ev[i + 2] * e[i + 2], tip[i + 2], a2); a3 = fma(ev[i + 3] * e[i + 3], tip[i + 3], a3);
+            }
+            tab[k] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile, 2) k_walk_n20(Dev D, const __grid_constant__ Model20 M, const double *stage, int nops,
+                                                      unsigned long long *counter) {
+    extern __shared__ __align__(16) double s_dyn20[];   // exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]
+    __shared__ long long s_item;
+    __shared__ int s_hdr[4];
+    const int tid = threadIdx.x;
+    const int C = D.C, B = C * 20, rows = D.su + 1, TS = tab20_stride(C);
+    const size_t stage_sz = stage20_doubles(C, D.su);
+    double *s_exp = s_dyn20, *s_tabA = s_dyn20 + 2 * B, *s_tabB = s_tabA + (size_t)rows * TS;
+    const long long ntiles = D.Ppad / kTile;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const long long tile = s_item;
+        if (tile >= ntiles) break;
+        const long long p = tile * kTile + tid;
+        const long long pb = pbase(p, B);
+        const long long sb = SAFE ? pbase(p, C) : p;
+        const bool may_scale = D.invar[p] == 0.0;
+        for (int o = 0; o < nops; o++) {
+            const double *st = stage + (size_t)o * stage_sz;
+            __syncthreads();   // everyone is done with the previous op's shared data
+            if (tid < 4) s_hdr[tid] = reinterpret_cast<const int32_t *>(st)[tid];
+            const int ncase_g = reinterpret_cast<const int32_t *>(st)[1];
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(st + 4);
+                double2 *dst = reinterpret_cast<double2 *>(s_exp);
+                for (int k = tid; k < B; k += kTile) dst[k] = __ldg(src + k);   // 2*B doubles
+                if (ncase_g <= 1) {
+                    const double2 *ta = reinterpret_cast<const double2 *>(st + 4 + 2 * B);
+                    double2 *da = reinterpret_cast<double2 *>(s_tabA);
+                    const int nv = rows * TS / 2 * (ncase_g == 0 ? 2 : 1);   // tabB follows tabA in both layouts
+                    for (int k = tid; k < nv; k += kTile) da[k] = __ldg(ta + k);
+                }
+            }
+            __syncthreads();
+            const int dst = s_hdr[0], ncase = s_hdr[1], aid = s_hdr[2], bid = s_hdr[3];
+            // A: tip for ncase <= 1, else internal; B: tip for ncase == 0, else internal
+            const double *Ap = nullptr, *Bp = nullptr, *tA = nullptr, *tB = nullptr;
+            if (ncase == 2) Ap = D.partial + (long long)aid * D.slot_stride + pb;
+            else tA = s_tabA + (size_t)D.tips[(long long)aid * D.Ppad + p] * TS;
+            if (ncase >= 1) Bp = D.partial + (long long)bid * D.slot_stride + pb;
+            else tB = s_tabB + (size_t)D.tips[(long long)bid * D.Ppad + p] * TS;
+            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
+            unsigned norm_sc = 0;
+            if (!SAFE) {
+                if (ncase == 2) norm_sc += D.scale[(long long)aid * D.scale_stride + sb];
+                if (ncase >= 1) norm_sc += D.scale[(long long)bid * D.scale_stride + sb];
+            }
+            unsigned mhi = 0;
+            for (int c = 0; c < C; c++) {
+                double a[20], v[20], w[20];
+                // both children's loads are issued before any arithmetic
+                if (Ap) {
+#pragma unroll
+                    for (int i = 0; i < 20; i++) v[i] = Ap[(long long)(c * 20 + i) * kWarp];
+                }
+                if (Bp) {
+#pragma unroll
+                    for (int i = 0; i < 20; i++) w[i] = Bp[(long long)(c * 20 + i) * kWarp];
+                }
+                if (Ap) {
+#pragma unroll
+                    for (int i = 0; i < 20; i++) v[i] *= s_exp[c * 20 + i];
+#pragma unroll
+                    for (int x = 0; x < 20; x++) {
+                        double acc = M.evec[x * 20] * v[0];
+#pragma unroll
+                        for (int i = 1; i < 20; i++) acc = fma(M.evec[x * 20 + i], v[i], acc);
+                        a[x] = acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 20; x += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + x);
+                        a[x] = t.x; a[x + 1] = t.y;
+                    }
+                }
+                if (Bp) {
+#pragma unroll
+                    for (int i = 0; i < 20; i++) w[i] *= s_exp[B + c * 20 + i];
+#pragma unroll
+                    for (int x = 0; x < 20; x++) {
+                        double acc = M.evec[x * 20] * w[0];
+#pragma unroll
+                        for (int i = 1; i < 20; i++) acc = fma(M.evec[x * 20 + i], w[i], acc);
+                        a[x] *= acc;
+                    }
+                } else {
+#pragma unroll
+                    for (int x = 0; x < 20; x += 2) {
+                        const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + x);
+                        a[x] *= t.x; a[x + 1] *= t.y;
+                    }
+                }
+                // back-transform; values are stored unscaled, the (rare) rescale re-reads what this thread has just written
+                unsigned chi = 0;
+#pragma unroll
+                for (int i = 0; i < 20; i++) {
+                    double acc = M.inv[i * 20] * a[0];
+#pragma unroll
+                    for (int x = 1; x < 20; x++) acc = fma(M.inv[i * 20 + x], a[x], acc);
+                    Op[(long long)(c * 20 + i) * kWarp] = acc;
+                    chi = max(chi, abs_hi(acc));
+                }
+                if (SAFE) {
+                    unsigned sc = 0;
+                    if (ncase == 2) sc += D.scale[(long long)aid * D.scale_stride + sb + c * kWarp];
+                    if (ncase >= 1) sc += D.scale[(long long)bid * D.scale_stride + sb + c * kWarp];
+                    if (ncase != 0 && may_scale && chi < kThresholdHi) {
+                        for (int i = 0; i < 20; i++) Op[(long long)(c * 20 + i) * kWarp] *= kTwo256;
+                        sc += 1;
+                    }
+                    D.scale[(long long)dst * D.scale_stride + sb + c * kWarp] = (uint16_t)sc;
+                } else mhi = max(mhi, chi);
+            }
+            if (!SAFE) {
+                if (ncase != 0 && may_scale && mhi < kThresholdHi) {
+                    for (int k = 0; k < B; k++) Op[(long long)k * kWarp] *= kTwo256;
+                    norm_sc += 1;
+                }
+                D.scale[(long long)dst * D.scale_stride + sb] = (uint16_t)norm_sc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 20-state walker on the FP64 MMA path (mma.sync.m8n8k4.f64, DMMA).
+//
+// Why MMA although DMMA and DFMA share ONE FP64 pipe on B200 with the same peak (scripts/fp64_mix.cu: 36.3 / 37.1 TFLOP/s
+// alone, 36 TFLOP/s in any mix): with DFMA every FMA needs one matrix element delivered from the constant bank (k_walk_n20:
+// LDCU per 2 DFMAs; the compiler's invariant-code motion also turns the 800 constants into spills), while the MMA form keeps
+// evec and inv_evec RESIDENT IN REGISTERS as B fragments (2 x 15 doubles per lane) for the whole kernel, issues 45 DMMAs
+// instead of 1200 DFMAs + 600 constant loads per pattern-tile and category, and leaves the issue slots to the loads/stores.
+// Cost: the output-state dimension 20 is padded to three 8-wide tiles (24), so at most 20/24 = 83 % of the pipe's peak is
+// useful work.
+//
+// Mapping (PTX ISA fragment layouts, g = lane/4, q = lane%4): M = 8 patterns (row g), K = 4 eigen-indices, N = 8 states.
+//   child pass   a[p][x]  = sum_i (exp_ci * L[p][c][i]) * evec[x][i]   A = scaled CLV (row p=g, col i=4kt+q: one coalesced
+//                                                                      8-byte load per k-tile), B[k=i][n=x] = evec[x][i]
+//   product      t = a (.) b on the C fragments (p = g, x = 8nt + 2q + {0,1})
+//   re-layout    C fragment -> A fragment inside each 4-lane group: 2 shuffle rounds per state tile
+//   back pass    out[p][i] = sum_x t[p][x] * inv_evec[i][x]           B[k=x][n=i] = inv_evec[i][x]
+// A warp owns 32 consecutive patterns (4 M-tiles); a CTA of 4 warps walks the whole op list for its 128-pattern tile.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter) {
+    extern __shared__ __align__(16) double s_dyn20[];   // exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]
+    __shared__ long long s_item;
+    __shared__ int s_hdr[4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
+    const int C = D.C, B = C * 20, rows = D.su + 1, TS = tab20_stride(C);
+    const size_t stage_sz = stage20_doubles(C, D.su);
+    double *s_exp = s_dyn20, *s_tabA = s_dyn20 + 2 * B, *s_tabB = s_tabA + (size_t)rows * TS;
+    // the model's matrices as B fragments, resident for the whole kernel
+    double Be[5][3], Bi[5][3];
+#pragma unroll
+    for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) {
+            const int n = 8 * nt + g, k = 4 * kt + q;
+            Be[kt][nt] = n < 20 ? D.evec[n * 20 + k] : 0.0;
+            Bi[kt][nt] = n < 20 ? D.inv_evec[n * 20 + k] : 0.0;
+        }
+    // lanes of the 4-lane group this lane pulls from in the two re-layout rounds
+    const int src0 = (lane & ~3) | ((q & 1) ? 2 + (q >> 1) : (q >> 1));
+    const int src1 = (lane & ~3) | ((q & 1) ? (q >> 1) : 2 + (q >> 1));
+    const long long ntiles = D.Ppad / kTile;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const long long tile = s_item;
+        if (tile >= ntiles) break;
+        const long long p0 = tile * kTile + warp * 32;          // first pattern of this warp (multiple of 32)
+        const long long wbase = (p0 >> 5) * (long long)B * kWarp;   // warp-interleaved block of these 32 patterns
+        const long long sbase = SAFE ? (p0 >> 5) * (long long)C * kWarp : p0;
+        for (int o = 0; o < nops; o++) {
+            const double *st = stage + (size_t)o * stage_sz;
+            __syncthreads();   // everyone is done with the previous op's shared data
+            if (tid < 4) s_hdr[tid] = reinterpret_cast<const int32_t *>(st)[tid];
+            const int ncase_g = reinterpret_cast<const int32_t *>(st)[1];
+            {
+                const double2 *src = reinterpret_cast<const double2 *>(st + 4);
+                double2 *dst = reinterpret_cast<double2 *>(s_exp);
+                for (int k = tid; k < B; k += kTile) dst[k] = __ldg(src + k);   // 2*B doubles
+                if (ncase_g <= 1) {
+                    const double2 *ta = reinterpret_cast<const double2 *>(st + 4 + 2 * B);
+                    double2 *da = reinterpret_cast<double2 *>(s_tabA);
+                    const int nv = rows * TS / 2 * (ncase_g == 0 ? 2 : 1);   // tabB follows tabA in both layouts
+                    for (int k = tid; k < nv; k += kTile) da[k] = __ldg(ta + k);
+                }
+            }
+            __syncthreads();
+            const int dst = s_hdr[0], ncase = s_hdr[1], aid = s_hdr[2], bid = s_hdr[3];
+            const double *Aw = D.partial + (long long)aid * D.slot_stride + wbase;   // only dereferenced when internal
+            const double *Bw = D.partial + (long long)bid * D.slot_stride + wbase;
+            double *Ow = D.partial + (long long)dst * D.slot_stride + wbase;
+            for (int mt = 0; mt < 4; mt++) {
+                const int pl = 8 * mt + g;                 // this lane's pattern inside the warp's 32
+                const long long p = p0 + pl;
+                const bool may_scale = D.invar[p] == 0.0;
+                const double *tA = nullptr, *tB = nullptr;
+                if (ncase <= 1) tA = s_tabA + (size_t)D.tips[(long long)aid * D.Ppad + p] * TS;
+                if (ncase == 0) tB = s_tabB + (size_t)D.tips[(long long)bid * D.Ppad + p] * TS;
+                unsigned norm_sc = 0, mhi = 0;
+                if (!SAFE) {
+                    if (ncase == 2) norm_sc += D.scale[(long long)aid * D.scale_stride + p];
+                    if (ncase >= 1) norm_sc += D.scale[(long long)bid * D.scale_stride + p];
+                }
+                for (int c = 0; c < C; c++) {
+                    double a[3][2], b[3][2];
+                    if (ncase == 2) {
+                        double f[5];
+#pragma unroll
+                        for (int kt = 0; kt < 5; kt++) f[kt] = Aw[(long long)(c * 20 + 4 * kt + q) * kWarp + pl] * s_exp[c * 20 + 4 * kt + q];
+#pragma unroll
+                        for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
+#pragma unroll
+                        for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+                            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(a[nt][0], a[nt][1], f[kt], Be[kt][nt]);
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < 3; nt++) {
+                            const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt + 2 * q);   // nt = 2, q >= 2: row padding
+                            a[nt][0] = t.x; a[nt][1] = t.y;
+                        }
+                    }
+                    if (ncase >= 1) {
+                        double f[5];
+#pragma unroll
+                        for (int kt = 0; kt < 5; kt++) f[kt] = Bw[(long long)(c * 20 + 4 * kt + q) * kWarp + pl] * s_exp[B + c * 20 + 4 * kt + q];
+#pragma unroll
+                        for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
+#pragma unroll
+                        for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+                            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(b[nt][0], b[nt][1], f[kt], Be[kt][nt]);
+                    } else {
+#pragma unroll
+                        for (int nt = 0; nt < 3; nt++) {
+                            const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt + 2 * q);
+                            b[nt][0] = t.x; b[nt][1] = t.y;
+                        }
+                    }
+                    // product on the C fragments, then C-fragment -> A-fragment re-layout inside each 4-lane group
+                    double ft[6];
+#pragma unroll
+                    for (int nt = 0; nt < 3; nt++) {
+                        const double t0 = a[nt][0] * b[nt][0], t1 = a[nt][1] * b[nt][1];
+                        const double r0 = __shfl_sync(0xffffffffu, q >= 2 ? t1 : t0, src0);
+                        const double r1 = __shfl_sync(0xffffffffu, q >= 2 ? t0 : t1, src1);
+                        ft[2 * nt] = (q & 1) ? r1 : r0;
+                        ft[2 * nt + 1] = (q & 1) ? r0 : r1;
+                    }
+                    double out[3][2];
+#pragma unroll
+                    for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
+#pragma unroll
+                    for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+                        for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
+                    // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
+                    unsigned chi = 0;
+#pragma unroll
+                    for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
+                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
+                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
+                    if (SAFE) {
+                        unsigned sc = 0;
+                        if (ncase == 2) sc += D.scale[(long long)aid * D.scale_stride + sbase + c * kWarp + pl];
+                        if (ncase >= 1) sc += D.scale[(long long)bid * D.scale_stride + sbase + c * kWarp + pl];
+                        if (ncase != 0 && may_scale && chi < kThresholdHi) {
+#pragma unroll
+                            for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
+                            sc += 1;
+                        }
+                        if (q == 0) D.scale[(long long)dst * D.scale_stride + sbase + c * kWarp + pl] = (uint16_t)sc;
+                    } else mhi = max(mhi, chi);
+#pragma unroll
+                    for (int nt = 0; nt < 3; nt++) {
+                        if (nt < 2 || q < 2) {
+                            Ow[(long long)(c * 20 + 8 * nt + 2 * q) * kWarp + pl] = out[nt][0];
+                            Ow[(long long)(c * 20 + 8 * nt + 2 * q + 1) * kWarp + pl] = out[nt][1];
+                        }
+                    }
+                }
+                if (!SAFE) {
+                    if (ncase != 0 && may_scale && mhi < kThresholdHi) {   // rare: rescale what this lane has just written
+                        for (int c = 0; c < C; c++)
+                            for (int nt = 0; nt < 3; nt++)
+                                if (nt < 2 || q < 2) {
+                                    Ow[(long long)(c * 20 + 8 * nt + 2 * q) * kWarp + pl] *= kTwo256;
+                                    Ow[(long long)(c * 20 + 8 * nt + 2 * q + 1) * kWarp + pl] *= kTwo256;
+                                }
+                        norm_sc += 1;
+                    }
+                    if (q == 0) D.scale[(long long)dst * D.scale_stride + p] = (uint16_t)norm_sc;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // block reduction of up to 3 doubles per thread into red[blockIdx.x*3 + j]; a 1-CTA kernel sums the per-block
 // values in index order, so results are bit-reproducible for a given pattern count.
 // ------------------------------------------------------------------------------------------------------------
