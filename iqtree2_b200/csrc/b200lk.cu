@@ -415,7 +415,8 @@ static size_t walk20_smem(const b200lk_engine *e) {
     return sizeof(double) * (2 * (size_t)e->B + 2 * (size_t)(e->cfg.state_unknown + 1) * tab20_stride(e->C));
 }
 static bool use_walk20(const b200lk_engine *e) {
-    return e->schedule != 1 && e->cfg.nstates == 20 && e->cfg.nmix == 1 && e->h_evec.size() == 400 && walk20_smem(e) <= 100 * 1024;
+    return e->schedule != 1 && e->cfg.nstates == 20 && e->cfg.nmix == 1 && e->h_evec.size() == 400 &&
+           2 * stage20_doubles(e->C, e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
 }
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
@@ -452,12 +453,16 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     Model20 Mloc;   // 6.4 KB kernel parameter, passed by value
     if (!use_mma) for (int k = 0; k < 400; k++) { Mloc.evec[k] = e->h_evec[k]; Mloc.inv[k] = e->h_inv_evec[k]; }
     const long long ntiles = e->Ppad / kTile;
-    const size_t smem = walk20_smem(e);
+    // the MMA walker double-buffers whole staging blocks; the DFMA variant keeps one buffer without the header
+    const size_t smem = use_mma ? 2 * stage_sz * sizeof(double) : walk20_smem(e);
     if (!e->walk20_attr_set) {
         CK(cudaFuncSetAttribute(k_walk_n20<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_walk_n20<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_walk_n20_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_walk_n20_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
+        cudaFuncSetAttribute(k_walk_n20_mma<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_walk_n20_mma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         int per_sm = 0;
         if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20_mma<false>, kTile, smem));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20<false>, kTile, smem));

@@ -872,28 +872,205 @@ __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, do
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
+// eigen-index (K) order of the back pass: the C fragment of the product (lane (g,q) holds x = 8nt + 2q + j) is fed to the
+// MMA as an A fragment AS IT STANDS — any permutation of K is legal as long as the B fragment uses the same one — so the
+// first four k-tiles need no data movement at all; only the half-empty third state tile (x = 16..19, held by lanes q < 2)
+// is spread over the four lanes with one shuffle.  back_x(kt, q) is the state x in K-slot q of k-tile kt.
+__host__ __device__ inline int back_x(int kt, int q) {
+    return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + (q < 2 ? 2 * q : 2 * (q - 2) + 1);
+}
+
+struct Walk20Op {   // per-op, per-lane addressing state of the MMA walker
+    const double *Aq, *Bq;   // child CLVs: + (c*20 + 4kt)*32 + 8mt            (row offset q, column g folded in)
+    double *Oq;              // destination:   + (c*20 + 8nt + j)*32 + 8mt      (row offset 2q, column g folded in)
+    const uint16_t *Asc, *Bsc;
+    uint16_t *Osc;           // scale_num: NORM [p], SAFE [c*32 + p%32] inside the warp's block (column g folded in)
+    unsigned stA, stB;       // tip states of the lane's pattern in the 4 M-tiles, one byte each
+    unsigned may_mask;       // bit mt: ptn_invar == 0 (patterns that may be rescaled)
+};
+
+template <bool SAFE, int NCASE>
+__device__ __forceinline__ void walk20_mma_op(const Dev &D, const Walk20Op &W, const double (&Be)[5][3], const double (&Bi)[5][3],
+                                              const double *s_exp, const double *s_tabA, const double *s_tabB, int q) {
+    const int C = D.C, B = C * 20, TS = tab20_stride(C);
+    const double *eA = s_exp + q, *eB = s_exp + B + q;
+    // Software pipeline over the 4*C (M-tile, category) steps: the raw CLV fragments of step s+1 are in flight while step s
+    // runs its MMAs.  (Measured alternatives that were slower: a two-step-deep pipeline with two register sets — spills at
+    // the 168-register budget of 3 CTAs/SM — and 4 CTAs/SM at 128 registers.)
+    const int step_c = 20 * kWarp;                       // next category, same M-tile
+    const int step_m = 8 - (C - 1) * 20 * kWarp;         // category 0 of the next M-tile (8 patterns further)
+    double nA[5], nB[5];
+    const double *pfA = W.Aq, *pfB = W.Bq;               // fetch cursors
+    int pf_c = 0, pf_left = 4 * C;                        // category of the fetch cursor, steps still to fetch
+    auto fetch = [&](double (&dA)[5], double (&dB)[5]) {
+        if (pf_left > 0) {
+            if (NCASE == 2) {
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) dA[kt] = pfA[kt * 4 * kWarp];
+            }
+            if (NCASE >= 1) {
+#pragma unroll
+                for (int kt = 0; kt < 5; kt++) dB[kt] = pfB[kt * 4 * kWarp];
+            }
+            const int adv = pf_c + 1 < C ? step_c : step_m;
+            pfA += adv; pfB += adv;
+            pf_c = pf_c + 1 < C ? pf_c + 1 : 0;
+            pf_left--;
+        }
+    };
+    fetch(nA, nB);
+
+    int mt = 0, c = 0;
+    const double *tA = nullptr, *tB = nullptr;
+    double *pO = nullptr;
+    unsigned mhi = 0, scA = 0, scB = 0;
+    for (int s = 0; s < 4 * C; s++) {
+        if (c == 0) {   // a new M-tile (8 patterns)
+            tA = s_tabA + (size_t)((W.stA >> (8 * mt)) & 0xffu) * TS + 2 * q;
+            tB = s_tabB + (size_t)((W.stB >> (8 * mt)) & 0xffu) * TS + 2 * q;
+            pO = W.Oq + 8 * mt;
+            mhi = 0;
+            if (!SAFE) {   // children's scale counts: loaded here, first used after the last category
+                if (NCASE == 2) scA = W.Asc[8 * mt];
+                if (NCASE >= 1) scB = W.Bsc[8 * mt];
+            }
+        }
+        double fA[5], fB[5];
+        if (NCASE == 2) {
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++) fA[kt] = nA[kt] * eA[c * 20 + 4 * kt];
+        }
+        if (NCASE >= 1) {
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++) fB[kt] = nB[kt] * eB[c * 20 + 4 * kt];
+        }
+        fetch(nA, nB);   // step s+1
+        double a[3][2], b[3][2];
+        if (NCASE == 2) {
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) {
+                const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt);   // nt = 2, q >= 2: row padding
+                a[nt][0] = t.x; a[nt][1] = t.y;
+            }
+        }
+        if (NCASE >= 1) {
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
+        } else {
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) {
+                const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt);
+                b[nt][0] = t.x; b[nt][1] = t.y;
+            }
+        }
+        // child passes; the two children's accumulator chains are independent and interleaved
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) {
+                if (NCASE == 2) dmma_m8n8k4(a[nt][0], a[nt][1], fA[kt], Be[kt][nt]);
+                if (NCASE >= 1) dmma_m8n8k4(b[nt][0], b[nt][1], fB[kt], Be[kt][nt]);
+            }
+        // product on the C fragments = A fragments of the back pass (see back_x)
+        double ft[5];
+        ft[0] = a[0][0] * b[0][0]; ft[1] = a[0][1] * b[0][1];
+        ft[2] = a[1][0] * b[1][0]; ft[3] = a[1][1] * b[1][1];
+        {
+            const double t0 = a[2][0] * b[2][0], t1 = a[2][1] * b[2][1];
+            const double r = __shfl_sync(0xffffffffu, t1, (threadIdx.x & 28) | (q & 1));
+            ft[4] = q < 2 ? t0 : r;
+        }
+        double out[3][2];
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
+        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
+        unsigned chi = 0;
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
+        if (SAFE) {
+            chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
+            chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
+            unsigned sc = 0;
+            if (NCASE == 2) sc += W.Asc[c * kWarp + 8 * mt];
+            if (NCASE >= 1) sc += W.Bsc[c * kWarp + 8 * mt];
+            if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && chi < kThresholdHi) {
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
+                sc += 1;
+            }
+            if (q == 0) W.Osc[c * kWarp + 8 * mt] = (uint16_t)sc;
+        } else mhi = max(mhi, chi);   // the pattern's other three lanes are folded in once per M-tile
+        double *po = pO + c * 20 * kWarp;
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) {
+            if (nt < 2 || q < 2) {
+                po[(8 * nt) * kWarp] = out[nt][0];
+                po[(8 * nt + 1) * kWarp] = out[nt][1];
+            }
+        }
+        if (++c == C) {   // last category of this M-tile
+            if (!SAFE) {
+                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
+                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+                unsigned norm_sc = scA + scB;
+                if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has just written
+                    for (int cc = 0; cc < C; cc++)
+                        for (int nt = 0; nt < 3; nt++)
+                            if (nt < 2 || q < 2) {
+                                pO[(cc * 20 + 8 * nt) * kWarp] *= kTwo256;
+                                pO[(cc * 20 + 8 * nt + 1) * kWarp] *= kTwo256;
+                            }
+                    norm_sc += 1;
+                }
+                if (q == 0) W.Osc[8 * mt] = (uint16_t)norm_sc;
+            }
+            c = 0;
+            mt++;
+        }
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// copy the parts of one op's staging block that the op needs (header + exp always, tabA for a tip child A, tabB when both
+// children are tips) into shared memory, asynchronously
+__device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, int tid) {
+    const int n_always = (4 + 2 * B) / 2;                                   // 16-byte chunks
+    const int n_total = n_always + (ncase <= 1 ? tab_doubles / 2 : 0) * (ncase == 0 ? 2 : 1);
+    for (int k = tid; k < n_total; k += kTile) cp_async16(sdst + 2 * k, gsrc + 2 * k);
+}
+
 template <bool SAFE>
 __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter) {
-    extern __shared__ __align__(16) double s_dyn20[];   // exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]
+    // two staging buffers: header[4] | exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; op o+1 is fetched with cp.async
+    // while op o computes, so each op costs one barrier and no exposed copy
+    extern __shared__ __align__(16) double s_dyn20[];
     __shared__ long long s_item;
-    __shared__ int s_hdr[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int C = D.C, B = C * 20, rows = D.su + 1, TS = tab20_stride(C);
     const size_t stage_sz = stage20_doubles(C, D.su);
-    double *s_exp = s_dyn20, *s_tabA = s_dyn20 + 2 * B, *s_tabB = s_tabA + (size_t)rows * TS;
+    const int tab_doubles = rows * TS;
     // the model's matrices as B fragments, resident for the whole kernel
     double Be[5][3], Bi[5][3];
 #pragma unroll
     for (int kt = 0; kt < 5; kt++)
 #pragma unroll
         for (int nt = 0; nt < 3; nt++) {
-            const int n = 8 * nt + g, k = 4 * kt + q;
-            Be[kt][nt] = n < 20 ? D.evec[n * 20 + k] : 0.0;
-            Bi[kt][nt] = n < 20 ? D.inv_evec[n * 20 + k] : 0.0;
+            const int n = 8 * nt + g;
+            Be[kt][nt] = n < 20 ? D.evec[n * 20 + 4 * kt + q] : 0.0;            // B[k = i][n = x] = evec[x][i]
+            Bi[kt][nt] = n < 20 ? D.inv_evec[n * 20 + back_x(kt, q)] : 0.0;     // B[k = x][n = i] = inv_evec[i][x]
         }
-    // lanes of the 4-lane group this lane pulls from in the two re-layout rounds
-    const int src0 = (lane & ~3) | ((q & 1) ? 2 + (q >> 1) : (q >> 1));
-    const int src1 = (lane & ~3) | ((q & 1) ? (q >> 1) : 2 + (q >> 1));
     const long long ntiles = D.Ppad / kTile;
     for (;;) {
         __syncthreads();
@@ -904,130 +1081,51 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
         const long long p0 = tile * kTile + warp * 32;          // first pattern of this warp (multiple of 32)
         const long long wbase = (p0 >> 5) * (long long)B * kWarp;   // warp-interleaved block of these 32 patterns
         const long long sbase = SAFE ? (p0 >> 5) * (long long)C * kWarp : p0;
+        unsigned may_mask = 0;
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) if (D.invar[p0 + 8 * mt + g] == 0.0) may_mask |= 1u << mt;
+        // header of the NEXT op is read one op ahead from global memory, so that issuing its copy and its tip-state loads
+        // never waits on memory; its tip states (one byte per pattern and tip child) are fetched during the current op
+        auto tip_states = [&](const int4 &hd, unsigned &sA, unsigned &sB) {
+            sA = sB = 0;
+            if (hd.y <= 1) {
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) sA |= (unsigned)D.tips[(long long)hd.z * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
+            }
+            if (hd.y == 0) {
+#pragma unroll
+                for (int mt = 0; mt < 4; mt++) sB |= (unsigned)D.tips[(long long)hd.w * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
+            }
+        };
+        int4 h_next = *reinterpret_cast<const int4 *>(stage);
+        stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid);
+        unsigned stA_next, stB_next;
+        tip_states(h_next, stA_next, stB_next);
         for (int o = 0; o < nops; o++) {
-            const double *st = stage + (size_t)o * stage_sz;
-            __syncthreads();   // everyone is done with the previous op's shared data
-            if (tid < 4) s_hdr[tid] = reinterpret_cast<const int32_t *>(st)[tid];
-            const int ncase_g = reinterpret_cast<const int32_t *>(st)[1];
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(st + 4);
-                double2 *dst = reinterpret_cast<double2 *>(s_exp);
-                for (int k = tid; k < B; k += kTile) dst[k] = __ldg(src + k);   // 2*B doubles
-                if (ncase_g <= 1) {
-                    const double2 *ta = reinterpret_cast<const double2 *>(st + 4 + 2 * B);
-                    double2 *da = reinterpret_cast<double2 *>(s_tabA);
-                    const int nv = rows * TS / 2 * (ncase_g == 0 ? 2 : 1);   // tabB follows tabA in both layouts
-                    for (int k = tid; k < nv; k += kTile) da[k] = __ldg(ta + k);
-                }
+            double *sb = s_dyn20 + (size_t)(o & 1) * stage_sz;
+            const int4 h = h_next;
+            const unsigned stA = stA_next, stB = stB_next;
+            if (o + 1 < nops) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(o + 1) * stage_sz);
+            cp_async_wait_all();
+            __syncthreads();   // op o's block has landed for every thread; everyone is done with op o-1's buffer
+            if (o + 1 < nops) {
+                stage20_fetch(s_dyn20 + (size_t)((o + 1) & 1) * stage_sz, stage + (size_t)(o + 1) * stage_sz, h_next.y, B, tab_doubles, tid);
+                tip_states(h_next, stA_next, stB_next);
             }
-            __syncthreads();
-            const int dst = s_hdr[0], ncase = s_hdr[1], aid = s_hdr[2], bid = s_hdr[3];
-            const double *Aw = D.partial + (long long)aid * D.slot_stride + wbase;   // only dereferenced when internal
-            const double *Bw = D.partial + (long long)bid * D.slot_stride + wbase;
-            double *Ow = D.partial + (long long)dst * D.slot_stride + wbase;
-            for (int mt = 0; mt < 4; mt++) {
-                const int pl = 8 * mt + g;                 // this lane's pattern inside the warp's 32
-                const long long p = p0 + pl;
-                const bool may_scale = D.invar[p] == 0.0;
-                const double *tA = nullptr, *tB = nullptr;
-                if (ncase <= 1) tA = s_tabA + (size_t)D.tips[(long long)aid * D.Ppad + p] * TS;
-                if (ncase == 0) tB = s_tabB + (size_t)D.tips[(long long)bid * D.Ppad + p] * TS;
-                unsigned norm_sc = 0, mhi = 0;
-                if (!SAFE) {
-                    if (ncase == 2) norm_sc += D.scale[(long long)aid * D.scale_stride + p];
-                    if (ncase >= 1) norm_sc += D.scale[(long long)bid * D.scale_stride + p];
-                }
-                for (int c = 0; c < C; c++) {
-                    double a[3][2], b[3][2];
-                    if (ncase == 2) {
-                        double f[5];
-#pragma unroll
-                        for (int kt = 0; kt < 5; kt++) f[kt] = Aw[(long long)(c * 20 + 4 * kt + q) * kWarp + pl] * s_exp[c * 20 + 4 * kt + q];
-#pragma unroll
-                        for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
-#pragma unroll
-                        for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-                            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(a[nt][0], a[nt][1], f[kt], Be[kt][nt]);
-                    } else {
-#pragma unroll
-                        for (int nt = 0; nt < 3; nt++) {
-                            const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt + 2 * q);   // nt = 2, q >= 2: row padding
-                            a[nt][0] = t.x; a[nt][1] = t.y;
-                        }
-                    }
-                    if (ncase >= 1) {
-                        double f[5];
-#pragma unroll
-                        for (int kt = 0; kt < 5; kt++) f[kt] = Bw[(long long)(c * 20 + 4 * kt + q) * kWarp + pl] * s_exp[B + c * 20 + 4 * kt + q];
-#pragma unroll
-                        for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
-#pragma unroll
-                        for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-                            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(b[nt][0], b[nt][1], f[kt], Be[kt][nt]);
-                    } else {
-#pragma unroll
-                        for (int nt = 0; nt < 3; nt++) {
-                            const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt + 2 * q);
-                            b[nt][0] = t.x; b[nt][1] = t.y;
-                        }
-                    }
-                    // product on the C fragments, then C-fragment -> A-fragment re-layout inside each 4-lane group
-                    double ft[6];
-#pragma unroll
-                    for (int nt = 0; nt < 3; nt++) {
-                        const double t0 = a[nt][0] * b[nt][0], t1 = a[nt][1] * b[nt][1];
-                        const double r0 = __shfl_sync(0xffffffffu, q >= 2 ? t1 : t0, src0);
-                        const double r1 = __shfl_sync(0xffffffffu, q >= 2 ? t0 : t1, src1);
-                        ft[2 * nt] = (q & 1) ? r1 : r0;
-                        ft[2 * nt + 1] = (q & 1) ? r0 : r1;
-                    }
-                    double out[3][2];
-#pragma unroll
-                    for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
-#pragma unroll
-                    for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-                        for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
-                    // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
-                    unsigned chi = 0;
-#pragma unroll
-                    for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
-                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
-                    chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
-                    if (SAFE) {
-                        unsigned sc = 0;
-                        if (ncase == 2) sc += D.scale[(long long)aid * D.scale_stride + sbase + c * kWarp + pl];
-                        if (ncase >= 1) sc += D.scale[(long long)bid * D.scale_stride + sbase + c * kWarp + pl];
-                        if (ncase != 0 && may_scale && chi < kThresholdHi) {
-#pragma unroll
-                            for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
-                            sc += 1;
-                        }
-                        if (q == 0) D.scale[(long long)dst * D.scale_stride + sbase + c * kWarp + pl] = (uint16_t)sc;
-                    } else mhi = max(mhi, chi);
-#pragma unroll
-                    for (int nt = 0; nt < 3; nt++) {
-                        if (nt < 2 || q < 2) {
-                            Ow[(long long)(c * 20 + 8 * nt + 2 * q) * kWarp + pl] = out[nt][0];
-                            Ow[(long long)(c * 20 + 8 * nt + 2 * q + 1) * kWarp + pl] = out[nt][1];
-                        }
-                    }
-                }
-                if (!SAFE) {
-                    if (ncase != 0 && may_scale && mhi < kThresholdHi) {   // rare: rescale what this lane has just written
-                        for (int c = 0; c < C; c++)
-                            for (int nt = 0; nt < 3; nt++)
-                                if (nt < 2 || q < 2) {
-                                    Ow[(long long)(c * 20 + 8 * nt + 2 * q) * kWarp + pl] *= kTwo256;
-                                    Ow[(long long)(c * 20 + 8 * nt + 2 * q + 1) * kWarp + pl] *= kTwo256;
-                                }
-                        norm_sc += 1;
-                    }
-                    if (q == 0) D.scale[(long long)dst * D.scale_stride + p] = (uint16_t)norm_sc;
-                }
-            }
+            const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
+            const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
+            Walk20Op W;
+            W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + q * kWarp + g;   // only dereferenced when internal
+            W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + q * kWarp + g;
+            W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + 2 * q * kWarp + g;
+            W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + g;
+            W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + g;
+            W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + g;
+            W.may_mask = may_mask;
+            W.stA = stA; W.stB = stB;
+            if (ncase == 2) walk20_mma_op<SAFE, 2>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else if (ncase == 1) walk20_mma_op<SAFE, 1>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else walk20_mma_op<SAFE, 0>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
         }
     }
 }
