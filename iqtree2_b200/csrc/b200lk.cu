@@ -414,20 +414,23 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
 static size_t walk20_smem(const b200lk_engine *e) {
     return sizeof(double) * (2 * (size_t)e->B + 2 * (size_t)(e->cfg.state_unknown + 1) * tab20_stride(e->C));
 }
+static int walk20_cpb(const b200lk_engine *e) { return e->C / e->cfg.nmix; }   // categories per class block
 static bool use_walk20(const b200lk_engine *e) {
-    return e->schedule != 1 && e->cfg.nstates == 20 && e->cfg.nmix == 1 && e->h_evec.size() == 400 &&
-           2 * stage20_doubles(e->C, e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
+    return e->schedule != 1 && e->cfg.nstates == 20 && e->C % e->cfg.nmix == 0 && e->h_evec.size() == (size_t)400 * e->cfg.nmix &&
+           2 * stage20_doubles(walk20_cpb(e), e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
 }
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
-    const size_t stage_sz = stage20_doubles(e->C, e->cfg.state_unknown);
-    if (stage_sz * nops > e->opinfo_cap) {
+    const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
+    const bool mix = nblk > 1;
+    const size_t stage_sz = stage20_doubles(cpb, e->cfg.state_unknown);   // one staging block per (op, class block)
+    if (stage_sz * nops * nblk > e->opinfo_cap) {
         CK(cudaStreamSynchronize(e->stream));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
         e->d_opinfo = nullptr; e->opinfo_cap = 0;
-        int rc = dev_alloc(e, &e->d_opinfo, stage_sz * nops);
+        int rc = dev_alloc(e, &e->d_opinfo, stage_sz * nops * nblk);
         if (rc) return rc;
-        e->opinfo_cap = stage_sz * nops;
+        e->opinfo_cap = stage_sz * nops * nblk;
         e->d.opinfo = e->d_opinfo;
     }
     WalkJob20 *hj = (WalkJob20 *)e->h_stage;
@@ -448,8 +451,8 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     }
     WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
-    k_walk_info_n20<<<nops, 256, sizeof(double) * 2 * e->B, e->stream>>>(e->d, dj, e->d_opinfo);
-    const bool use_mma = e->kernel_variant != 1;   // variant 1 = the DFMA/constant-bank kernel (kept for A/B measurements)
+    k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo);
+    const bool use_mma = mix || e->kernel_variant != 1;   // variant 1 = the DFMA/constant-bank kernel (single class; A/B measurements)
     Model20 Mloc;   // 6.4 KB kernel parameter, passed by value
     if (!use_mma) for (int k = 0; k < 400; k++) { Mloc.evec[k] = e->h_evec[k]; Mloc.inv[k] = e->h_inv_evec[k]; }
     const long long ntiles = e->Ppad / kTile;
@@ -458,13 +461,15 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     if (!e->walk20_attr_set) {
         CK(cudaFuncSetAttribute(k_walk_n20<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_walk_n20<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_walk_n20_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_walk_n20_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
-        cudaFuncSetAttribute(k_walk_n20_mma<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_walk_n20_mma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        const void *mma_kernels[4] = {(const void *)k_walk_n20_mma<false, false>, (const void *)k_walk_n20_mma<true, false>,
+                                      (const void *)k_walk_n20_mma<false, true>, (const void *)k_walk_n20_mma<true, true>};
+        for (const void *f : mma_kernels) {
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         int per_sm = 0;
-        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20_mma<false>, kTile, smem));
+        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20_mma<false, false>, kTile, smem));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20<false>, kTile, smem));
         e->walk20_ctas_per_sm = std::max(per_sm, 1);
         e->walk20_attr_set = true;
@@ -473,8 +478,11 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     if (use_mma) {
-        if (e->cfg.safe_numeric) k_walk_n20_mma<true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
-        else k_walk_n20_mma<false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        const bool safe = e->cfg.safe_numeric != 0;
+        if (mix && safe) k_walk_n20_mma<true, true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        else if (mix) k_walk_n20_mma<false, true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        else if (safe) k_walk_n20_mma<true, false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        else k_walk_n20_mma<false, false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
     } else {
         if (e->cfg.safe_numeric) k_walk_n20<true><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
         else k_walk_n20<false><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);

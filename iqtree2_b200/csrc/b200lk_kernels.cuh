@@ -677,21 +677,27 @@ struct WalkJob20 {
 __host__ __device__ inline int tab20_stride(int C) { return C * 20 + 2; }
 __host__ __device__ inline size_t stage20_doubles(int C, int su) { return 4 + 2 * (size_t)C * 20 + 2 * (size_t)(su + 1) * tab20_stride(C); }
 
+// One CTA per (op, class block).  A class block is one mixture class with its cpb = C/nmix categories (all C categories
+// for a single-class model; one category per block when mixture classes are fused with the rate categories,
+// tree/phylokernelnew.h:1322-1325).  Each block gets its own staging block, so that to the walker a mixture is simply a
+// longer list of "virtual ops" with cpb categories each.
 __global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *jobs, double *stage) {
-    extern __shared__ double s_exp20[];   // [2][C*20]
-    const int C = D.C, B = C * 20, TS = tab20_stride(C);
-    const WalkJob20 job = jobs[blockIdx.x];
-    double *st = stage + (size_t)blockIdx.x * stage20_doubles(C, D.su);
+    extern __shared__ double s_exp20[];   // [2][cpb*20]
+    const int nblk = D.nmix, cpb = D.C / nblk, B = cpb * 20, TS = tab20_stride(cpb);
+    const int op = blockIdx.x / nblk, m = blockIdx.x - op * nblk;
+    const WalkJob20 job = jobs[op];
+    double *st = stage + (size_t)blockIdx.x * stage20_doubles(cpb, D.su);
     for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
-        const int ch = k / B, kk = k - ch * B, c = kk / 20, i = kk - c * 20;
+        const int ch = k / B, kk = k - ch * B, r = kk / 20, i = kk - r * 20;
+        const int c = m * cpb + r;
         const double len_child = D.cat_rate[c % D.ncat] * (ch ? job.lenB : job.lenA);   // :1017
-        const double v = exp(D.eval[i] * len_child);                                     // :1022
+        const double v = exp(D.eval[m * 20 + i] * len_child);                            // :1022
         s_exp20[k] = v;
         st[4 + k] = v;
     }
     if (threadIdx.x == 0) {
         int32_t *h = reinterpret_cast<int32_t *>(st);
-        h[0] = job.dst; h[1] = job.ncase; h[2] = job.aid; h[3] = job.bid; h[4] = h[5] = h[6] = h[7] = 0;
+        h[0] = job.dst; h[1] = job.ncase; h[2] = job.aid; h[3] = job.bid; h[4] = m; h[5] = h[6] = h[7] = 0;
     }
     __syncthreads();
     // partial_lh_leaves[state][c][x] for tip children (:1036-1056: Vec4d lane accumulators + horizontal_add)
@@ -704,11 +710,11 @@ __global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *j
         for (int k = threadIdx.x; k < rows * TS; k += blockDim.x) {
             const int state = k / TS, cx = k - state * TS;
             if (cx >= B) { tab[k] = 0.0; continue; }
-            const int c = cx / 20, x = cx - c * 20;
+            const int r = cx / 20, x = cx - r * 20;
             if (state == D.su) { tab[k] = 1.0; continue; }
-            const double *tip = D.tip_lh + state * 20;
-            const double *ev = D.evec + x * 20;
-            const double *e = ex + c * 20;
+            const double *tip = D.tip_lh + ((size_t)state * D.nmix + m) * 20;
+            const double *ev = D.evec + (size_t)m * 400 + x * 20;
+            const double *e = ex + r * 20;
             double a0 = (ev[0] * e[0]) * tip[0], a1 = (ev[1] * e[1]) * tip[1], a2 = (ev[2] * e[2]) * tip[2], a3 = (ev[3] * e[3]) * tip[3];
 #pragma unroll
             for (int i = 4; i < 20; i += 4) {
@@ -880,19 +886,24 @@ __host__ __device__ inline int back_x(int kt, int q) {
     return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + (q < 2 ? 2 * q : 2 * (q - 2) + 1);
 }
 
-struct Walk20Op {   // per-op, per-lane addressing state of the MMA walker
+struct Walk20Op {   // per-(op, class block), per-lane addressing state of the MMA walker
     const double *Aq, *Bq;   // child CLVs: + (c*20 + 4kt)*32 + 8mt            (row offset q, column g folded in)
     double *Oq;              // destination:   + (c*20 + 8nt + j)*32 + 8mt      (row offset 2q, column g folded in)
     const uint16_t *Asc, *Bsc;
     uint16_t *Osc;           // scale_num: NORM [p], SAFE [c*32 + p%32] inside the warp's block (column g folded in)
     unsigned stA, stB;       // tip states of the lane's pattern in the 4 M-tiles, one byte each
     unsigned may_mask;       // bit mt: ptn_invar == 0 (patterns that may be rescaled)
+    // mixtures (NORM_LH): the underflow test spans ALL classes of a pattern, the classes are walked one after the other
+    int first_class, last_class;   // this block is the first / last class block of its op
+    int class_off;                 // doubles between the op's class-0 block and this one inside a CLV (m*cpb*20*32)
+    int Ctot;                      // categories of the whole CLV (rare rescale path)
+    unsigned *s_mhi;               // per-lane running max exponent word, [4 M-tiles][128 threads] in shared memory
 };
 
-template <bool SAFE, int NCASE>
-__device__ __forceinline__ void walk20_mma_op(const Dev &D, const Walk20Op &W, const double (&Be)[5][3], const double (&Bi)[5][3],
+template <bool SAFE, bool MIX, int NCASE>
+__device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, const double (&Be)[5][3], const double (&Bi)[5][3],
                                               const double *s_exp, const double *s_tabA, const double *s_tabB, int q) {
-    const int C = D.C, B = C * 20, TS = tab20_stride(C);
+    const int B = C * 20, TS = tab20_stride(C);   // C = categories of this class block
     const double *eA = s_exp + q, *eB = s_exp + B + q;
     // Software pipeline over the 4*C (M-tile, category) steps: the raw CLV fragments of step s+1 are in flight while step s
     // runs its MMAs.  (Measured alternatives that were slower: a two-step-deep pipeline with two register sets — spills at
@@ -1019,17 +1030,25 @@ __device__ __forceinline__ void walk20_mma_op(const Dev &D, const Walk20Op &W, c
             if (!SAFE) {
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
-                unsigned norm_sc = scA + scB;
-                if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has just written
-                    for (int cc = 0; cc < C; cc++)
-                        for (int nt = 0; nt < 3; nt++)
-                            if (nt < 2 || q < 2) {
-                                pO[(cc * 20 + 8 * nt) * kWarp] *= kTwo256;
-                                pO[(cc * 20 + 8 * nt + 1) * kWarp] *= kTwo256;
-                            }
-                    norm_sc += 1;
+                if (MIX) {   // fold in the classes walked before this one (each lane owns its slot: no synchronisation)
+                    unsigned *slot = W.s_mhi + mt * kTile + threadIdx.x;
+                    if (!W.first_class) mhi = max(mhi, *slot);
+                    if (!W.last_class) *slot = mhi;
                 }
-                if (q == 0) W.Osc[8 * mt] = (uint16_t)norm_sc;
+                if (!MIX || W.last_class) {
+                    unsigned norm_sc = scA + scB;
+                    if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has written
+                        double *pAll = pO - W.class_off;
+                        for (int cc = 0; cc < W.Ctot; cc++)
+                            for (int nt = 0; nt < 3; nt++)
+                                if (nt < 2 || q < 2) {
+                                    pAll[(cc * 20 + 8 * nt) * kWarp] *= kTwo256;
+                                    pAll[(cc * 20 + 8 * nt + 1) * kWarp] *= kTwo256;
+                                }
+                        norm_sc += 1;
+                    }
+                    if (q == 0) W.Osc[8 * mt] = (uint16_t)norm_sc;
+                }
             }
             c = 0;
             mt++;
@@ -1051,26 +1070,33 @@ __device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, 
     for (int k = tid; k < n_total; k += kTile) cp_async16(sdst + 2 * k, gsrc + 2 * k);
 }
 
-template <bool SAFE>
+template <bool SAFE, bool MIX>
 __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter) {
-    // two staging buffers: header[4] | exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; op o+1 is fetched with cp.async
-    // while op o computes, so each op costs one barrier and no exposed copy
+    // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
+    // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
     extern __shared__ __align__(16) double s_dyn20[];
     __shared__ long long s_item;
+    __shared__ unsigned s_mhi[MIX ? 4 * kTile : 1];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-    const int C = D.C, B = C * 20, rows = D.su + 1, TS = tab20_stride(C);
-    const size_t stage_sz = stage20_doubles(C, D.su);
+    const int nblk = MIX ? D.nmix : 1, cpb = D.C / nblk;   // class blocks per op, categories per block
+    const int Btot = D.C * 20, B = cpb * 20, rows = D.su + 1, TS = tab20_stride(cpb);
+    const size_t stage_sz = stage20_doubles(cpb, D.su);
     const int tab_doubles = rows * TS;
-    // the model's matrices as B fragments, resident for the whole kernel
+    const int nvo = nops * nblk;                            // "virtual ops": (op, class block) pairs, class-minor
+    // the model's matrices as B fragments: resident for the whole kernel (single class) or reloaded per class block
     double Be[5][3], Bi[5][3];
+    auto load_frags = [&](int m) {
+        const double *ev = D.evec + (size_t)m * 400, *iv = D.inv_evec + (size_t)m * 400;
 #pragma unroll
-    for (int kt = 0; kt < 5; kt++)
+        for (int kt = 0; kt < 5; kt++)
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++) {
-            const int n = 8 * nt + g;
-            Be[kt][nt] = n < 20 ? D.evec[n * 20 + 4 * kt + q] : 0.0;            // B[k = i][n = x] = evec[x][i]
-            Bi[kt][nt] = n < 20 ? D.inv_evec[n * 20 + back_x(kt, q)] : 0.0;     // B[k = x][n = i] = inv_evec[i][x]
-        }
+            for (int nt = 0; nt < 3; nt++) {
+                const int n = 8 * nt + g;
+                Be[kt][nt] = n < 20 ? ev[n * 20 + 4 * kt + q] : 0.0;            // B[k = i][n = x] = evec[x][i]
+                Bi[kt][nt] = n < 20 ? iv[n * 20 + back_x(kt, q)] : 0.0;         // B[k = x][n = i] = inv_evec[i][x]
+            }
+    };
+    if (!MIX) load_frags(0);
     const long long ntiles = D.Ppad / kTile;
     for (;;) {
         __syncthreads();
@@ -1079,13 +1105,13 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
         const long long tile = s_item;
         if (tile >= ntiles) break;
         const long long p0 = tile * kTile + warp * 32;          // first pattern of this warp (multiple of 32)
-        const long long wbase = (p0 >> 5) * (long long)B * kWarp;   // warp-interleaved block of these 32 patterns
-        const long long sbase = SAFE ? (p0 >> 5) * (long long)C * kWarp : p0;
+        const long long wbase = (p0 >> 5) * (long long)Btot * kWarp;   // warp-interleaved block of these 32 patterns
+        const long long sbase = SAFE ? (p0 >> 5) * (long long)D.C * kWarp : p0;
         unsigned may_mask = 0;
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) if (D.invar[p0 + 8 * mt + g] == 0.0) may_mask |= 1u << mt;
-        // header of the NEXT op is read one op ahead from global memory, so that issuing its copy and its tip-state loads
-        // never waits on memory; its tip states (one byte per pattern and tip child) are fetched during the current op
+        // header of the NEXT block is read one block ahead from global memory, so that issuing its copy and its tip-state
+        // loads never waits on memory; its tip states (one byte per pattern and tip child) are fetched during the current block
         auto tip_states = [&](const int4 &hd, unsigned &sA, unsigned &sB) {
             sA = sB = 0;
             if (hd.y <= 1) {
@@ -1101,31 +1127,38 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
         stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid);
         unsigned stA_next, stB_next;
         tip_states(h_next, stA_next, stB_next);
-        for (int o = 0; o < nops; o++) {
-            double *sb = s_dyn20 + (size_t)(o & 1) * stage_sz;
+        int m = 0;
+        for (int v = 0; v < nvo; v++) {
+            double *sb = s_dyn20 + (size_t)(v & 1) * stage_sz;
             const int4 h = h_next;
             const unsigned stA = stA_next, stB = stB_next;
-            if (o + 1 < nops) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(o + 1) * stage_sz);
+            if (v + 1 < nvo) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 1) * stage_sz);
+            if (MIX) load_frags(m);
             cp_async_wait_all();
-            __syncthreads();   // op o's block has landed for every thread; everyone is done with op o-1's buffer
-            if (o + 1 < nops) {
-                stage20_fetch(s_dyn20 + (size_t)((o + 1) & 1) * stage_sz, stage + (size_t)(o + 1) * stage_sz, h_next.y, B, tab_doubles, tid);
-                tip_states(h_next, stA_next, stB_next);
+            __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
+            if (v + 1 < nvo) {
+                stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid);
+                if (!MIX || m + 1 == nblk) tip_states(h_next, stA_next, stB_next);   // the tips change with the op, not with the class
             }
             const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
             const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
+            const int class_off = m * B * kWarp;
             Walk20Op W;
-            W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + q * kWarp + g;   // only dereferenced when internal
-            W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + q * kWarp + g;
-            W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + 2 * q * kWarp + g;
-            W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + g;
-            W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + g;
-            W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + g;
+            W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + class_off + q * kWarp + g;   // only dereferenced when internal
+            W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + class_off + q * kWarp + g;
+            W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + class_off + 2 * q * kWarp + g;
+            const int sc_off = SAFE ? m * cpb * kWarp : 0;
+            W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + sc_off + g;
+            W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + sc_off + g;
+            W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + sc_off + g;
             W.may_mask = may_mask;
             W.stA = stA; W.stB = stB;
-            if (ncase == 2) walk20_mma_op<SAFE, 2>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else if (ncase == 1) walk20_mma_op<SAFE, 1>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else walk20_mma_op<SAFE, 0>(D, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            W.first_class = m == 0; W.last_class = m + 1 == nblk;
+            W.class_off = class_off; W.Ctot = D.C; W.s_mhi = s_mhi;
+            if (ncase == 2) walk20_mma_op<SAFE, MIX, 2>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else walk20_mma_op<SAFE, MIX, 0>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            if (MIX && ++m == nblk) m = 0;
         }
     }
 }
