@@ -27,6 +27,11 @@ def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, t
         model = models.make_lg_gamma()
     elif kind == "aa_c4":  # small LG+C60-style mixture: 4 classes x 4 rates
         model = models.make_lg_c60_gamma(nclasses=4)
+    elif kind == "aa_c60":  # the full LG+C60+G4 of BASELINE config 4: 60 classes x 4 rates = 240 categories, block 4800
+        model = models.make_lg_c60_gamma()
+    elif kind == "aa_fused":  # 4 classes fused with the 4 rate categories (LG4X-style; ModelFactory::fused_mix_rate)
+        model = models.make_lg_c60_gamma(nclasses=4)
+        model.fused_mix_rate = True
     elif kind == "bin":
         model = models.make_random_reversible(2, ncat=4, seed=seed)
     elif kind == "n5mix":

@@ -36,6 +36,8 @@ GOLDEN_CASES = {
     "aa_norm": ("aa", False, dict(ntaxa=14, nsites=400)),
     "aa_safe": ("aa", True, dict(ntaxa=14, nsites=400)),
     "aa_c4mix": ("aa_c4", False, dict(ntaxa=12, nsites=200)),
+    "aa_fused": ("aa_fused", False, dict(ntaxa=12, nsites=200)),
+    "aa_c4mix_safe": ("aa_c4", True, dict(ntaxa=10, nsites=150)),
     "bin_safe": ("bin", True, dict(ntaxa=14, nsites=400)),
     "codon_safe": ("codon", True, dict(ntaxa=10, nsites=120)),
     "n5mix_safe": ("n5mix", True, dict(ntaxa=14, nsites=400)),

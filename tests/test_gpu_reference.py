@@ -49,7 +49,8 @@ needs_ref = pytest.mark.skipif(not ref_engine.available(), reason="oracle/_ref/l
 
 @needs_ref
 @pytest.mark.parametrize("kind,safe,ntaxa,nsites", [("dna", False, 64, 6000), ("dna", True, 64, 3000), ("dna_inv", False, 40, 4000),
-                                                    ("aa", False, 48, 1500), ("aa_c4", False, 20, 600), ("codon", True, 12, 300)])
+                                                    ("aa", False, 48, 1500), ("aa", True, 30, 700), ("aa_c4", False, 20, 600), ("aa_c4", True, 16, 300),
+                                                    ("aa_fused", False, 20, 600), ("aa_c60", False, 9, 200), ("codon", True, 12, 300)])
 def test_cuda_engine_against_live_reference(kind, safe, ntaxa, nsites):
     tree, model, pat, freq, inv = make_case(kind, ntaxa=ntaxa, nsites=nsites, seed=11)
     r = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, nthreads=4)

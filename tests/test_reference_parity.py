@@ -18,10 +18,13 @@ pytestmark = pytest.mark.skipif(not ref_engine.available(), reason="oracle/_ref/
 # (kind, safe) — safe is what the reference itself would pick (tree/phylotreesse.cpp:95-96: SAFE unless nstates in {4,20}),
 # plus explicit -safe runs for DNA / protein
 CASES = [("dna", False), ("dna", True), ("dna_inv", False), ("dna_g1", False), ("dna_g8", False), ("aa", False), ("aa", True),
-         ("aa_c4", False), ("bin", True), ("codon", True), ("n5mix", True), ("n7", True)]
+         ("aa_c4", False), ("aa_c4", True), ("aa_fused", False), ("aa_c60", False), ("bin", True), ("codon", True), ("n5mix", True),
+         ("n7", True)]
 
 
 def run_pair(kind, safe, ntaxa=14, nsites=400, leaf=0, **kw):
+    if kind == "aa_c60":
+        ntaxa, nsites = 8, 60
     tree, model, pat, freq, inv = make_case(kind, ntaxa=ntaxa, nsites=nsites, **kw)
     r = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe)
     assert r.info()["safe_numeric"] == safe and r.info()["vector_size"] == 4
