@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="kernel variant of the walker schedule (development A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mem", type=float, default=-1.0,
+                    help="-mem of the reference (LM_MEM_SAVE): fraction of the T-2 CLV slots to keep (0 = log2(T)+1 slots); "
+                         "default: only when one slot per internal node does not fit the device")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3
@@ -270,7 +273,31 @@ def main():
     br = plan.pendant_branch_of(tree, 0)
     ops, a, b, L = plan.plan_branch(tree, br)
 
-    eng = LikelihoodEngine(model, ntaxa, my_nptn, device=local_rank, schedule=args.schedule)
+    # CLV slots: one per internal node (LM_PER_NODE) when that fits the device; otherwise the reference's -mem mode
+    # (LM_MEM_SAVE, tree/phylotree.cpp:999-1021): the host mirror's planner recycles a bounded number of slots
+    nslots, mem_mode = None, "LM_PER_NODE"
+    slot_bytes = ((my_nptn + 127) // 128 * 128) * (8 * B + 2 * S)
+    dev_total = torch.cuda.get_device_properties(local_rank).total_memory
+    mem_frac = args.mem
+    if mem_frac < 0 and (ntaxa + 2) * slot_bytes > 0.85 * dev_total:
+        mem_frac = min(1.0, (0.70 * dev_total / slot_bytes - 2) / (ntaxa - 2))
+    if mem_frac >= 0:
+        from iqtree2_b200.phylotree import PhyloTree
+        pt = PhyloTree()
+        pt.set_plan_only(True)
+        pt.set_alignment(tree.names, np.zeros((ntaxa, 1), dtype=np.uint8), np.ones(1), model)   # planning needs no patterns
+        pt.set_model(model)
+        pt.read_tree(tree.to_newick())
+        pt.set_mem_save(True, mem_frac)
+        nslots = pt.max_lh_slots + 2
+        pa, pb, _ = pt.branches()
+        pbr = [k for k in range(len(pa)) if min(pa[k], pb[k]) == 0][0]   # the pendant branch of alignment row 0
+        ops, a, b, L = pt.plan_branch(pbr)
+        assert len(ops) == ntaxa - 2
+        pt.close()
+        mem_mode = f"LM_MEM_SAVE ({nslots - 2} of {ntaxa - 2} CLV slots recycled by the host planner)"
+
+    eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, device=local_rank, schedule=args.schedule)
     stream = torch.cuda.current_stream()
     if args.variant:
         eng.set_schedule(10 + args.variant)
@@ -347,9 +374,12 @@ def main():
     achieved = my_bytes_partials / ker_s / 1e9
     n_ii, n_ti, n_tt = plan.count_node_cases(ops)
 
-    kernel_name = {(4, True): "k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)",
-                   (20, True): "k_walk_n20_mma (pattern-tile walker, FP64 MMA m8n8k4)"}.get(
-        (model.nstates, model.nmix == 1 and args.schedule != 1 and (model.nstates != 4 or model.ncat_mix == 4)), "k_partials_generic")
+    if args.schedule != 1 and model.nstates == 20:
+        kernel_name = "k_walk_n20_mma (pattern-tile walker, FP64 MMA m8n8k4)"
+    elif args.schedule != 1 and model.nstates == 4 and model.nmix == 1 and model.ncat_mix == 4:
+        kernel_name = "k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)"
+    else:
+        kernel_name = "k_partials_generic"
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": my_bytes_partials,
                 "launch_ms": ker_s * 1e3, "partial_lh_GBps": achieved}
@@ -371,7 +401,7 @@ def main():
                    "kernel": "NORM_LH", "nstates": model.nstates, "ncat_mix": model.ncat_mix, "partial_updates_per_eval": len(ops),
                    "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
                    "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}.get(args.schedule, f"variant{args.schedule}"),
-                   "clv_bytes_resident": eng.device_bytes, "l2": "inputs (CLVs) far larger than L2; no flush needed",
+                   "clv_bytes_resident": eng.device_bytes, "clv_slots": mem_mode, "l2": "inputs (CLVs) far larger than L2; no flush needed",
                    "parallelism": f"pattern-sharded x{world}" if world > 1 else "single GPU",
                    "algorithmic_GB_per_eval": bytes_eval / 1e9},
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -10,6 +10,7 @@
 #ifndef B200PT_H_
 #define B200PT_H_
 #include <stdint.h>
+#include "b200lk.h"
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -43,6 +44,19 @@ int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh,
 int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
 /* number of partial-likelihood updates planned so far (PhyloTree::num_partial_lh_computations) */
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t);
+
+
+/* -mem (Params::lh_mem_save = LM_MEM_SAVE, tree/phylotree.cpp:999-1021; slot table tree/memslot.cpp): recycle
+ * max_lh_slots CLV slots instead of one per internal node.  max_mem_size: 0 = the minimum log2(T)+1 slots, <= 1 = that
+ * fraction of the T-2 slots, > 1 = bytes of device memory for the slots.  Drops the current buffers. */
+int b200pt_set_mem_save(b200pt_tree *t, int32_t on, double max_mem_size);
+int b200pt_max_lh_slots(b200pt_tree *t);
+/* Planning without execution: no engine is created; b200pt_plan_branch returns the traversal_info list of
+ * computeLikelihoodBranch(branch) (ops in post-order, the slot of the node end, kind/id of the dad end, the branch
+ * length) and updates every partial_lh_computed flag and slot as if the list had been executed. */
+int b200pt_set_plan_only(b200pt_tree *t, int32_t on);
+int b200pt_plan_branch(b200pt_tree *t, int32_t branch, b200lk_op *ops, int32_t cap, int32_t *nops, int32_t *node_slot,
+                       int32_t *dad_kind, int32_t *dad_id, double *length);
 
 #ifdef __cplusplus
 }

@@ -420,6 +420,15 @@ static bool use_walk20(const b200lk_engine *e) {
            2 * stage20_doubles(walk20_cpb(e), e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
 }
 
+// [VAR*4 + MIX*2 + SAFE]; VAR 0 = base, 1 = DFMA tail (measured slower: 8.4 vs 6.7 ms, kept for A/B), 2 = split-K accumulators
+static const void *const walk20_mma_kernels[12] = {
+    (const void *)k_walk_n20_mma<false, false, 0>, (const void *)k_walk_n20_mma<true, false, 0>,
+    (const void *)k_walk_n20_mma<false, true, 0>,  (const void *)k_walk_n20_mma<true, true, 0>,
+    (const void *)k_walk_n20_mma<false, false, 1>, (const void *)k_walk_n20_mma<true, false, 1>,
+    (const void *)k_walk_n20_mma<false, true, 1>,  (const void *)k_walk_n20_mma<true, true, 1>,
+    (const void *)k_walk_n20_mma<false, false, 2>, (const void *)k_walk_n20_mma<true, false, 2>,
+    (const void *)k_walk_n20_mma<false, true, 2>,  (const void *)k_walk_n20_mma<true, true, 2>};
+
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
     const bool mix = nblk > 1;
@@ -453,6 +462,7 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
     k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo);
     const bool use_mma = mix || e->kernel_variant != 1;   // variant 1 = the DFMA/constant-bank kernel (single class; A/B measurements)
+    const int var = e->kernel_variant == 3 ? 1 : e->kernel_variant == 4 ? 2 : 0;   // variants 3 / 4: A/B switches (see walk20_mma_kernels)
     Model20 Mloc;   // 6.4 KB kernel parameter, passed by value
     if (!use_mma) for (int k = 0; k < 400; k++) { Mloc.evec[k] = e->h_evec[k]; Mloc.inv[k] = e->h_inv_evec[k]; }
     const long long ntiles = e->Ppad / kTile;
@@ -461,15 +471,13 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     if (!e->walk20_attr_set) {
         CK(cudaFuncSetAttribute(k_walk_n20<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CK(cudaFuncSetAttribute(k_walk_n20<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const void *mma_kernels[4] = {(const void *)k_walk_n20_mma<false, false>, (const void *)k_walk_n20_mma<true, false>,
-                                      (const void *)k_walk_n20_mma<false, true>, (const void *)k_walk_n20_mma<true, true>};
-        for (const void *f : mma_kernels) {
+        for (const void *f : walk20_mma_kernels) {
             CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         int per_sm = 0;
-        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20_mma<false, false>, kTile, smem));
+        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk20_mma_kernels[var * 4], kTile, smem));
         else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20<false>, kTile, smem));
         e->walk20_ctas_per_sm = std::max(per_sm, 1);
         e->walk20_attr_set = true;
@@ -479,10 +487,8 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     if (use_mma) {
         const bool safe = e->cfg.safe_numeric != 0;
-        if (mix && safe) k_walk_n20_mma<true, true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
-        else if (mix) k_walk_n20_mma<false, true><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
-        else if (safe) k_walk_n20_mma<true, false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
-        else k_walk_n20_mma<false, false><<<grid, kTile, smem, e->stream>>>(e->d, e->d_opinfo, nops, e->d_counter);
+        void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
+        CK(cudaLaunchKernel(walk20_mma_kernels[var * 4 + (mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, smem, e->stream));
     } else {
         if (e->cfg.safe_numeric) k_walk_n20<true><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
         else k_walk_n20<false><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
@@ -509,7 +515,10 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
     ChildJob *hjobs = (ChildJob *)((char *)e->h_stage + e->ops_cap * sizeof(DevOp));
     // the pinned staging buffer may still be in flight from the previous call on this stream
     CK(cudaStreamSynchronize(e->stream));
-    std::vector<int> level_of_slot(e->cfg.nslots, -1);
+    // level_of_slot: level of the latest writer; last_touch: highest level of any op that has read or written the slot.
+    // With recycled slots (LM_MEM_SAVE: one slot serves several nodes of one traversal) an op must also run after
+    // every earlier reader/writer of its destination (WAR / WAW), not only after its producers.
+    std::vector<int> level_of_slot(e->cfg.nslots, -1), last_touch(e->cfg.nslots, -1);
     std::vector<int> level(nops, 0);
     int max_level = 0;
     bool ordered_levels = true;
@@ -541,8 +550,11 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
         d.leafR = ch[b].kind == 0 ? loff[b] : -1;
         int lv = 0;
         for (auto &c : ch) if (c.kind == 1 && level_of_slot[c.id] >= 0) lv = std::max(lv, level_of_slot[c.id] + 1);
+        lv = std::max(lv, last_touch[op.dst_slot] + 1);
+        for (auto &c : ch) if (c.kind == 1) last_touch[c.id] = std::max(last_touch[c.id], lv);
         level[k] = lv;
         level_of_slot[op.dst_slot] = lv;
+        last_touch[op.dst_slot] = lv;
         max_level = std::max(max_level, lv);
         if (k > 0 && level[k] < level[k - 1]) ordered_levels = false;
     }

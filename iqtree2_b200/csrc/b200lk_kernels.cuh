@@ -886,6 +886,20 @@ __host__ __device__ inline int back_x(int kt, int q) {
     return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + (q < 2 ? 2 * q : 2 * (q - 2) + 1);
 }
 
+// TAIL variant (k_walk_n20_mma<.., TAIL=true>): states 16..19 are NOT padded to a third 8-wide MMA tile (which wastes 4/24
+// of the pipe) but handled by DFMAs: lane (g,q) forms the partial sums over ITS five K values for the four tail states, then a
+// 3-shuffle reduce-scatter inside the 4-lane group leaves the total for state 16+q in lane q.  The tail matrix elements come
+// from shared memory as s_tail[kt][q][s], slot s <-> state 16 + (s ^ q): the xor order makes the reduce-scatter select-free.
+// In the back pass the product for x = 16+q sits in lane q, so K-slot q of k-tile 4 is x = 16+q and no shuffle is needed.
+__host__ __device__ inline int back_x_tail(int kt, int q) { return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + q; }
+constexpr int kTail20 = 5 * 4 * 4;   // doubles per tail matrix
+
+__device__ __forceinline__ double reduce_scatter4(double s0, double s1, double s2, double s3) {
+    const double u0 = s0 + __shfl_xor_sync(0xffffffffu, s1, 1);
+    const double u2 = s2 + __shfl_xor_sync(0xffffffffu, s3, 1);
+    return u0 + __shfl_xor_sync(0xffffffffu, u2, 2);
+}
+
 struct Walk20Op {   // per-(op, class block), per-lane addressing state of the MMA walker
     const double *Aq, *Bq;   // child CLVs: + (c*20 + 4kt)*32 + 8mt            (row offset q, column g folded in)
     double *Oq;              // destination:   + (c*20 + 8nt + j)*32 + 8mt      (row offset 2q, column g folded in)
@@ -898,11 +912,16 @@ struct Walk20Op {   // per-(op, class block), per-lane addressing state of the M
     int class_off;                 // doubles between the op's class-0 block and this one inside a CLV (m*cpb*20*32)
     int Ctot;                      // categories of the whole CLV (rare rescale path)
     unsigned *s_mhi;               // per-lane running max exponent word, [4 M-tiles][128 threads] in shared memory
+    const double *tail_e, *tail_i; // TAIL: this lane's rows of the tail matrices in shared memory (+ kt*16 doubles per k-tile)
 };
 
-template <bool SAFE, bool MIX, int NCASE>
+template <bool SAFE, bool MIX, int NCASE, int VAR>
 __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, const double (&Be)[5][3], const double (&Bi)[5][3],
                                               const double *s_exp, const double *s_tabA, const double *s_tabB, int q) {
+    constexpr bool TAIL = (VAR & 1) != 0;     // states 16..19 by DFMA + reduce-scatter instead of a padded third MMA tile
+    constexpr bool SPLITK = (VAR & 2) != 0;   // two accumulator sets per output tile (even / odd k-tiles) where a pass has
+                                              // only three dependent DMMA chains: the back pass, and the child pass of a
+                                              // tip-inner node
     const int B = C * 20, TS = tab20_stride(C);   // C = categories of this class block
     const double *eA = s_exp + q, *eB = s_exp + B + q;
     // Software pipeline over the 4*C (M-tile, category) steps: the raw CLV fragments of step s+1 are in flight while step s
@@ -956,55 +975,120 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
             for (int kt = 0; kt < 5; kt++) fB[kt] = nB[kt] * eB[c * 20 + 4 * kt];
         }
         fetch(nA, nB);   // step s+1
+        constexpr int NTM = TAIL ? 2 : 3;   // state tiles on the MMA path
         double a[3][2], b[3][2];
+        double at = 0.0, bt = 0.0;          // TAIL: child values for state 16+q
         if (NCASE == 2) {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
+            for (int nt = 0; nt < NTM; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
         } else {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
+            for (int nt = 0; nt < NTM; nt++) {
                 const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt);   // nt = 2, q >= 2: row padding
                 a[nt][0] = t.x; a[nt][1] = t.y;
             }
+            if (TAIL) at = tA[c * 20 + 16 - q];   // tA carries +2q
         }
         if (NCASE >= 1) {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
+            for (int nt = 0; nt < NTM; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
         } else {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
+            for (int nt = 0; nt < NTM; nt++) {
                 const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt);
                 b[nt][0] = t.x; b[nt][1] = t.y;
             }
+            if (TAIL) bt = tB[c * 20 + 16 - q];
         }
         // child passes; the two children's accumulator chains are independent and interleaved
+        double sA[4], sB[4];
+        if (TAIL && NCASE >= 1) {
 #pragma unroll
-        for (int kt = 0; kt < 5; kt++)
+            for (int j = 0; j < 4; j++) { sA[j] = 0.0; sB[j] = 0.0; }
+        }
+        double b2[3][2];   // SPLITK, tip-inner: odd k-tiles of the single child pass
+        if (SPLITK && NCASE == 1) {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
+            for (int nt = 0; nt < NTM; nt++) { b2[nt][0] = 0.0; b2[nt][1] = 0.0; }
+        }
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++) {
+#pragma unroll
+            for (int nt = 0; nt < NTM; nt++) {
                 if (NCASE == 2) dmma_m8n8k4(a[nt][0], a[nt][1], fA[kt], Be[kt][nt]);
-                if (NCASE >= 1) dmma_m8n8k4(b[nt][0], b[nt][1], fB[kt], Be[kt][nt]);
+                if (NCASE >= 1) {
+                    if (SPLITK && NCASE == 1 && (kt & 1)) dmma_m8n8k4(b2[nt][0], b2[nt][1], fB[kt], Be[kt][nt]);
+                    else dmma_m8n8k4(b[nt][0], b[nt][1], fB[kt], Be[kt][nt]);
+                }
             }
-        // product on the C fragments = A fragments of the back pass (see back_x)
+            if (TAIL && NCASE >= 1) {
+                const double2 e01 = *reinterpret_cast<const double2 *>(W.tail_e + kt * 16);
+                const double2 e23 = *reinterpret_cast<const double2 *>(W.tail_e + kt * 16 + 2);
+                if (NCASE == 2) {
+                    sA[0] = fma(fA[kt], e01.x, sA[0]); sA[1] = fma(fA[kt], e01.y, sA[1]);
+                    sA[2] = fma(fA[kt], e23.x, sA[2]); sA[3] = fma(fA[kt], e23.y, sA[3]);
+                }
+                sB[0] = fma(fB[kt], e01.x, sB[0]); sB[1] = fma(fB[kt], e01.y, sB[1]);
+                sB[2] = fma(fB[kt], e23.x, sB[2]); sB[3] = fma(fB[kt], e23.y, sB[3]);
+            }
+        }
+        if (SPLITK && NCASE == 1) {
+#pragma unroll
+            for (int nt = 0; nt < NTM; nt++) { b[nt][0] += b2[nt][0]; b[nt][1] += b2[nt][1]; }
+        }
+        if (TAIL) {
+            if (NCASE == 2) at = reduce_scatter4(sA[0], sA[1], sA[2], sA[3]);
+            if (NCASE >= 1) bt = reduce_scatter4(sB[0], sB[1], sB[2], sB[3]);
+        }
+        // product on the C fragments = A fragments of the back pass (see back_x / back_x_tail)
         double ft[5];
         ft[0] = a[0][0] * b[0][0]; ft[1] = a[0][1] * b[0][1];
         ft[2] = a[1][0] * b[1][0]; ft[3] = a[1][1] * b[1][1];
-        {
+        if (TAIL) ft[4] = at * bt;
+        else {
             const double t0 = a[2][0] * b[2][0], t1 = a[2][1] * b[2][1];
             const double r = __shfl_sync(0xffffffffu, t1, (threadIdx.x & 28) | (q & 1));
             ft[4] = q < 2 ? t0 : r;
         }
         double out[3][2];
+        double ot = 0.0;                    // TAIL: out[p][16+q]
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
+        for (int nt = 0; nt < NTM; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
+        if (TAIL) {
+            double so[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-        for (int kt = 0; kt < 5; kt++)
+            for (int kt = 0; kt < 5; kt++) {
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
-        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
-        unsigned chi = 0;
+                for (int nt = 0; nt < NTM; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
+                const double2 i01 = *reinterpret_cast<const double2 *>(W.tail_i + kt * 16);
+                const double2 i23 = *reinterpret_cast<const double2 *>(W.tail_i + kt * 16 + 2);
+                so[0] = fma(ft[kt], i01.x, so[0]); so[1] = fma(ft[kt], i01.y, so[1]);
+                so[2] = fma(ft[kt], i23.x, so[2]); so[3] = fma(ft[kt], i23.y, so[3]);
+            }
+            ot = reduce_scatter4(so[0], so[1], so[2], so[3]);
+        } else if (SPLITK) {
+            double o2[3][2];
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
+            for (int nt = 0; nt < 3; nt++) { o2[nt][0] = 0.0; o2[nt][1] = 0.0; }
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) {
+                    if (kt & 1) dmma_m8n8k4(o2[nt][0], o2[nt][1], ft[kt], Bi[kt][nt]);
+                    else dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
+                }
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) { out[nt][0] += o2[nt][0]; out[nt][1] += o2[nt][1]; }
+        } else {
+#pragma unroll
+            for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+                for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
+        }
+        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros (TAIL: i = 16+q in ot)
+        unsigned chi = TAIL ? abs_hi(ot) : 0u;
+#pragma unroll
+        for (int nt = 0; nt < NTM; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
         if (SAFE) {
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
@@ -1013,19 +1097,21 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
             if (NCASE >= 1) sc += W.Bsc[c * kWarp + 8 * mt];
             if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && chi < kThresholdHi) {
 #pragma unroll
-                for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
+                for (int nt = 0; nt < NTM; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
+                ot *= kTwo256;
                 sc += 1;
             }
             if (q == 0) W.Osc[c * kWarp + 8 * mt] = (uint16_t)sc;
         } else mhi = max(mhi, chi);   // the pattern's other three lanes are folded in once per M-tile
         double *po = pO + c * 20 * kWarp;
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++) {
+        for (int nt = 0; nt < NTM; nt++) {
             if (nt < 2 || q < 2) {
                 po[(8 * nt) * kWarp] = out[nt][0];
                 po[(8 * nt + 1) * kWarp] = out[nt][1];
             }
         }
+        if (TAIL) po[(16 - q) * kWarp] = ot;   // pO carries +2q rows: row 16+q
         if (++c == C) {   // last category of this M-tile
             if (!SAFE) {
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
@@ -1039,12 +1125,14 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
                     unsigned norm_sc = scA + scB;
                     if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has written
                         double *pAll = pO - W.class_off;
-                        for (int cc = 0; cc < W.Ctot; cc++)
-                            for (int nt = 0; nt < 3; nt++)
+                        for (int cc = 0; cc < W.Ctot; cc++) {
+                            for (int nt = 0; nt < NTM; nt++)
                                 if (nt < 2 || q < 2) {
                                     pAll[(cc * 20 + 8 * nt) * kWarp] *= kTwo256;
                                     pAll[(cc * 20 + 8 * nt + 1) * kWarp] *= kTwo256;
                                 }
+                            if (TAIL) pAll[(cc * 20 + 16 - q) * kWarp] *= kTwo256;
+                        }
                         norm_sc += 1;
                     }
                     if (q == 0) W.Osc[8 * mt] = (uint16_t)norm_sc;
@@ -1070,13 +1158,15 @@ __device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, 
     for (int k = tid; k < n_total; k += kTile) cp_async16(sdst + 2 * k, gsrc + 2 * k);
 }
 
-template <bool SAFE, bool MIX>
+template <bool SAFE, bool MIX, int VAR>
 __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter) {
     // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
     // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
     extern __shared__ __align__(16) double s_dyn20[];
     __shared__ long long s_item;
     __shared__ unsigned s_mhi[MIX ? 4 * kTile : 1];
+    constexpr bool TAIL = (VAR & 1) != 0;
+    __shared__ __align__(16) double s_tail[TAIL ? (MIX ? 2 : 1) * 2 * kTail20 : 2];   // [buffer][evec | inv_evec][kt][q][slot]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int nblk = MIX ? D.nmix : 1, cpb = D.C / nblk;   // class blocks per op, categories per block
     const int Btot = D.C * 20, B = cpb * 20, rows = D.su + 1, TS = tab20_stride(cpb);
@@ -1093,10 +1183,17 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
             for (int nt = 0; nt < 3; nt++) {
                 const int n = 8 * nt + g;
                 Be[kt][nt] = n < 20 ? ev[n * 20 + 4 * kt + q] : 0.0;            // B[k = i][n = x] = evec[x][i]
-                Bi[kt][nt] = n < 20 ? iv[n * 20 + back_x(kt, q)] : 0.0;         // B[k = x][n = i] = inv_evec[i][x]
+                Bi[kt][nt] = n < 20 ? iv[n * 20 + (TAIL ? back_x_tail(kt, q) : back_x(kt, q))] : 0.0;   // B[k = x][n = i] = inv_evec[i][x]
             }
     };
-    if (!MIX) load_frags(0);
+    auto load_tails = [&](int m, int buf) {   // TAIL: rows 16..19 of evec / inv_evec in the lanes' K order
+        if (tid < kTail20) {
+            const int kt = tid >> 4, qq = (tid >> 2) & 3, sl = tid & 3, x = 16 + (sl ^ qq);
+            s_tail[buf * 2 * kTail20 + tid] = D.evec[(size_t)m * 400 + x * 20 + 4 * kt + qq];
+            s_tail[buf * 2 * kTail20 + kTail20 + tid] = D.inv_evec[(size_t)m * 400 + x * 20 + back_x_tail(kt, qq)];
+        }
+    };
+    if (!MIX) { load_frags(0); if (TAIL) load_tails(0, 0); }
     const long long ntiles = D.Ppad / kTile;
     for (;;) {
         __syncthreads();
@@ -1133,7 +1230,7 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
             const int4 h = h_next;
             const unsigned stA = stA_next, stB = stB_next;
             if (v + 1 < nvo) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 1) * stage_sz);
-            if (MIX) load_frags(m);
+            if (MIX) { load_frags(m); if (TAIL) load_tails(m, v & 1); }
             cp_async_wait_all();
             __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
             if (v + 1 < nvo) {
@@ -1155,9 +1252,11 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
             W.stA = stA; W.stB = stB;
             W.first_class = m == 0; W.last_class = m + 1 == nblk;
             W.class_off = class_off; W.Ctot = D.C; W.s_mhi = s_mhi;
-            if (ncase == 2) walk20_mma_op<SAFE, MIX, 2>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else walk20_mma_op<SAFE, MIX, 0>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            W.tail_e = s_tail + (MIX ? (v & 1) * 2 * kTail20 : 0) + q * 4;
+            W.tail_i = W.tail_e + kTail20;
+            if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            else walk20_mma_op<SAFE, MIX, 0, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
             if (MIX && ++m == nblk) m = 0;
         }
     }

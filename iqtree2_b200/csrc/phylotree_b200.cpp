@@ -36,6 +36,94 @@ void PhyloNode::clearReversePartialLh(PhyloNode *dad) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// MemSlotVector — tree/memslot.cpp.  Every member is a no-op unless the tree runs in LM_MEM_SAVE (`enabled`), as in
+// the reference (each of its members starts with `if (lh_mem_save != LM_MEM_SAVE) return`).
+// ---------------------------------------------------------------------------------------------------------------
+static const int MEM_LOCKED = 1, MEM_SPECIAL = 2;
+
+void MemSlotVector::init(int num_slot) {
+    clear();
+    if (!enabled) return;
+    resize(num_slot);
+    reset();
+}
+void MemSlotVector::reset() {
+    if (!enabled) return;
+    for (auto &ms : *this) { ms.status = 0; ms.nei = nullptr; }
+    nei_id_map.clear();
+    free_count = 0;
+}
+int MemSlotVector::findNei(PhyloNeighbor *nei) const {
+    auto it = nei_id_map.find(nei);
+    if (it == nei_id_map.end()) throw std::runtime_error("MemSlotVector::findNei: neighbour has no slot");
+    return it->second;
+}
+void MemSlotVector::addNei(PhyloNeighbor *nei, int id) {
+    nei->slot = id;
+    (*this)[id].nei = nei;
+    nei_id_map[nei] = id;
+}
+bool MemSlotVector::lock(PhyloNeighbor *nei) {
+    if (!enabled || nei->node->isLeaf()) return false;
+    MemSlot &ms = (*this)[findNei(nei)];
+    if (ms.status & MEM_SPECIAL) return false;
+    if (ms.status & MEM_LOCKED) throw std::runtime_error("MemSlotVector::lock: slot already locked");
+    ms.status |= MEM_LOCKED;
+    return true;
+}
+void MemSlotVector::unlock(PhyloNeighbor *nei) {
+    if (!enabled || nei->node->isLeaf()) return;
+    MemSlot &ms = (*this)[findNei(nei)];
+    if (ms.status & MEM_SPECIAL) return;
+    if (!(ms.status & MEM_LOCKED)) throw std::runtime_error("MemSlotVector::unlock: slot is not locked");
+    ms.status &= ~MEM_LOCKED;
+}
+bool MemSlotVector::locked(PhyloNeighbor *nei) {
+    if (!enabled || nei->node->isLeaf()) return false;
+    const MemSlot &ms = (*this)[findNei(nei)];
+    if (ms.status & MEM_SPECIAL) return false;
+    return (ms.status & MEM_LOCKED) != 0;
+}
+int MemSlotVector::allocate(PhyloNeighbor *nei) {
+    if (!enabled) return -1;
+    if (free_count < (int)size() && ((*this)[free_count].status & MEM_SPECIAL) == 0) {   // a slot never used so far
+        addNei(nei, free_count);
+        return free_count++;
+    }
+    int min_size = INT32_MAX, best = -1;
+    for (int id = 0; id < (int)size(); id++) {   // the unlocked slot whose neighbour has the smallest subtree
+        const MemSlot &ms = (*this)[id];
+        if ((ms.status & (MEM_LOCKED | MEM_SPECIAL)) == 0 && min_size > ms.nei->size) {
+            best = id;
+            min_size = ms.nei->size;
+            if (min_size == 2) break;
+        }
+    }
+    if (best < 0) return -1;
+    (*this)[best].nei->partial_lh_computed = false;   // clearPartialLh: the evicted CLV is gone
+    addNei(nei, best);
+    return best;
+}
+void MemSlotVector::update(PhyloNeighbor *nei) {
+    if (!enabled) return;
+    const int id = findNei(nei);
+    if ((*this)[id].nei != nei) {
+        (*this)[id].nei->partial_lh_computed = false;
+        addNei(nei, id);
+    }
+}
+void MemSlotVector::takeover(PhyloNeighbor *nei, PhyloNeighbor *taken) {
+    nei->slot = taken->slot;
+    taken->slot = -1;
+    taken->partial_lh_computed = false;
+    if (!enabled) return;
+    const int id = findNei(taken);
+    nei_id_map.erase(taken);
+    nei_id_map[nei] = id;
+    if ((*this)[id].nei == taken) (*this)[id].nei = nei;
+}
+
 PhyloTree::PhyloTree() {}
 PhyloTree::~PhyloTree() {
     deleteAllPartialLh();
@@ -263,12 +351,13 @@ void PhyloTree::restoreBranchLengths(const std::vector<double> &lenvec) {
 void PhyloTree::deleteAllPartialLh() {
     if (engine_) b200lk_destroy(engine_);
     engine_ = nullptr;
+    initialized_ = false;
     for (auto *n : neighbors_) { n->slot = -1; n->partial_lh_computed = false; }
     theta_computed = false;
 }
 
 void PhyloTree::initializeAllPartialLh() {
-    if (engine_) return;
+    if (initialized_) return;
     if (!root || taxa_.empty() || ncat_ == 0) throw std::runtime_error("initializeAllPartialLh: alignment, model and tree must be set first");
     b200lk_config cfg{};
     cfg.nstates = nstates_; cfg.ncat = ncat_; cfg.nmix = nmix_; cfg.fused_mix_rate = fused_;
@@ -279,21 +368,41 @@ void PhyloTree::initializeAllPartialLh() {
     cfg.safe_numeric = safe;
     cfg.seq_type = seq_type_; cfg.state_unknown = state_unknown_;
     cfg.ntaxa = leafNum; cfg.nptn = nptn_;
-    cfg.nslots = (nodeNum - leafNum) + 2;   // one per internal node (LM_PER_NODE) + nni_partial_lh (tree/phylotree.cpp:1071-1076)
+    // getMemoryRequired (tree/phylotree.cpp:999-1021): LM_PER_NODE keeps one slot per internal node; LM_MEM_SAVE (-mem)
+    // anything between log2(T)+1 slots and that
+    max_lh_slots = leafNum - 2;
+    if (params.lh_mem_save == LM_MEM_SAVE) {
+        const int min_lh_slots = (int)std::log2((double)leafNum) + 1;
+        if (params.max_mem_size == 0.0) max_lh_slots = min_lh_slots;
+        else if (params.max_mem_size <= 1.0) max_lh_slots = (int)std::floor(params.max_mem_size * (leafNum - 2));
+        else {
+            const int C = fused_ ? ncat_ : ncat_ * nmix_;
+            const double ppad = (double)((nptn_ + 127) / 128 * 128);
+            const double lh_scale_size = ppad * ((double)nstates_ * C * sizeof(double) + (safe ? C : 1) * sizeof(uint16_t));
+            max_lh_slots = (int)std::min<double>(leafNum - 2, params.max_mem_size / lh_scale_size - 2);
+        }
+        max_lh_slots = std::min(std::max(max_lh_slots, min_lh_slots), leafNum - 2);
+    }
+    cfg.nslots = max_lh_slots + 2;   // + nni_partial_lh (tree/phylotree.cpp:1071-1076)
     cfg.device = params.device;
-    int rc = b200lk_create(&cfg, &engine_);
-    if (rc != 0) throw std::runtime_error(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
-    check(b200lk_set_schedule(engine_, params.schedule), "set_schedule");
-    check(b200lk_set_tip_states(engine_, states_.data()), "set_tip_states");
-    check(b200lk_set_pattern_freq(engine_, ptn_freq_.data()), "set_pattern_freq");
-    check(b200lk_set_pattern_invar(engine_, ptn_invar_.data()), "set_pattern_invar");
-    check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
-    check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
+    if (!params.plan_only) {
+        int rc = b200lk_create(&cfg, &engine_);
+        if (rc != 0) throw std::runtime_error(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
+        check(b200lk_set_schedule(engine_, params.schedule), "set_schedule");
+        check(b200lk_set_tip_states(engine_, states_.data()), "set_tip_states");
+        check(b200lk_set_pattern_freq(engine_, ptn_freq_.data()), "set_pattern_freq");
+        check(b200lk_set_pattern_invar(engine_, ptn_invar_.data()), "set_pattern_invar");
+        check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
+        check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
+    }
+    initialized_ = true;
     // slot assignment: pre-order from the root; the neighbour dad->node of every internal node gets the next slot
     // (tree/phylotree.cpp:1143-1157)
+    mem_slots.enabled = params.lh_mem_save == LM_MEM_SAVE;
+    mem_slots.init(max_lh_slots);
     int indexlh = 0;
     std::vector<std::pair<PhyloNode *, PhyloNode *>> stack{{root, nullptr}};
-    while (!stack.empty()) {
+    while (!mem_slots.enabled && !stack.empty()) {   // LM_MEM_SAVE: slots are handed out by the traversals (:1158-1165)
         auto [node, dad] = stack.back();
         stack.pop_back();
         if (dad && !node->isLeaf()) dad->findNeighbor(node)->slot = indexlh++;
@@ -316,8 +425,9 @@ void PhyloTree::clearAllPartialLH() {
 int PhyloTree::computeSize(PhyloNeighbor *nei, PhyloNode *dad) {
     if (nei->size > 0) return nei->size;
     // iterative post-order over the subtree below nei
+    // PhyloNode::computeSize (tree/phylonode.cpp:91-105): number of LEAVES below the neighbour (a cherry has size 2)
     struct Fr { PhyloNeighbor *nei; PhyloNode *dad; size_t k; int acc; };
-    std::vector<Fr> st{{nei, dad, 0, 1}};
+    std::vector<Fr> st{{nei, dad, 0, nei->node->isLeaf() ? 1 : 0}};
     while (!st.empty()) {
         Fr &f = st.back();
         PhyloNode *node = f.nei->node;
@@ -325,7 +435,7 @@ int PhyloTree::computeSize(PhyloNeighbor *nei, PhyloNode *dad) {
             PhyloNeighbor *c = node->neighbors[f.k++];
             if (c->node == f.dad) continue;
             if (c->size > 0) f.acc += c->size;
-            else st.push_back({c, node, 0, 1});
+            else st.push_back({c, node, 0, c->node->isLeaf() ? 1 : 0});
         } else {
             f.nei->size = f.acc;
             int s = f.acc;
@@ -343,43 +453,50 @@ void PhyloTree::reorientPartialLh(PhyloNeighbor *dad_branch, PhyloNode *dad) {
         if (it->node != dad) {
             PhyloNeighbor *backnei = it->node->findNeighbor(node);
             if (backnei->slot >= 0) {
-                // MemSlotVector::takeover (tree/memslot.cpp:206-223)
-                dad_branch->slot = backnei->slot;
-                backnei->slot = -1;
-                backnei->partial_lh_computed = false;
+                mem_slots.takeover(dad_branch, backnei);   // tree/memslot.cpp:206-223
                 break;
             }
         }
-    if (dad_branch->slot < 0) throw std::runtime_error("partial_lh is not re-oriented");
+    if (params.lh_mem_save == LM_PER_NODE && dad_branch->slot < 0) throw std::runtime_error("partial_lh is not re-oriented");
 }
 
-// tree/phylotree.cpp:5918-6028 — post-order list of stale directed partials below dad_branch
+// tree/phylotree.cpp:5918-6028 — post-order list of stale directed partials below dad_branch.  Returns whether the
+// slot of dad_branch was locked for the caller (LM_MEM_SAVE; always false otherwise).
 bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_dad) {
-    struct Fr { PhyloNeighbor *dad_branch; PhyloNode *dad; std::vector<PhyloNeighbor *> kids; size_t k; };
+    struct Fr { PhyloNeighbor *dad_branch; PhyloNode *dad; std::vector<PhyloNeighbor *> kids; std::vector<char> locked; size_t k; };
     std::vector<Fr> st;
-    auto push = [&](PhyloNeighbor *db, PhyloNode *dad) {
+    bool ret = false;   // result of the call that has just returned
+    // returns true when the call finished at once (ret is set), false when a frame was pushed
+    auto call = [&](PhyloNeighbor *db, PhyloNode *dad) -> bool {
         PhyloNode *node = db->node;
-        if (db->partial_lh_computed || node->isLeaf()) return;
-        Fr f{db, dad, {}, 0};
+        if (db->partial_lh_computed || node->isLeaf()) { ret = mem_slots.lock(db); return true; }
+        Fr f{db, dad, {}, {}, 0};
         for (auto *it : node->neighbors) if (it->node != dad) f.kids.push_back(it);
         for (auto *it : f.kids) computeSize(it, node);
         // sort neighbours in descending subtree size (:5931-5942)
         std::stable_sort(f.kids.begin(), f.kids.end(), [](PhyloNeighbor *a, PhyloNeighbor *b) { return a->size > b->size; });
+        f.locked.assign(f.kids.size(), 0);
         st.push_back(std::move(f));
+        return false;
     };
-    push(top_branch, top_dad);
+    if (call(top_branch, top_dad)) return ret;
     while (!st.empty()) {
         Fr &f = st.back();
         if (f.k < f.kids.size()) {
-            PhyloNeighbor *c = f.kids[f.k++];
-            PhyloNode *node = f.dad_branch->node;
-            push(c, node);
+            const size_t k = f.k++;
+            if (call(f.kids[k], f.dad_branch->node)) st.back().locked[k] = ret;   // (`f` may dangle after a push)
             continue;
         }
         PhyloNeighbor *dad_branch = f.dad_branch;
         PhyloNode *dad = f.dad, *node = dad_branch->node;
         dad_branch->partial_lh_computed = true;
         reorientPartialLh(dad_branch, dad);
+        if (dad_branch->slot < 0 || mem_slots.locked(dad_branch)) {   // memory-saving technique (:5962-5997)
+            if (mem_slots.allocate(dad_branch) < 0) throw std::runtime_error("No free/unlocked mem slot found!");
+        } else mem_slots.update(dad_branch);
+        if (mem_slots.enabled)
+            for (size_t k = 0; k < f.kids.size(); k++)
+                if (!f.kids[k]->node->isLeaf() && f.locked[k]) mem_slots.unlock(f.kids[k]);
         b200lk_op op{};
         op.dst_slot = dad_branch->slot;
         // children in NEIGHBOUR order (FOR_NEIGHBOR_IT, tree/phylokernelnew.h:1343-1350), not in the sorted visiting order
@@ -394,18 +511,26 @@ bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_d
             }
         traversal_info.push_back(op);
         num_partial_lh_computations++;
+        ret = mem_slots.lock(dad_branch);
         st.pop_back();
+        if (!st.empty()) { Fr &p = st.back(); p.locked[p.k - 1] = ret; }
     }
-    return false;
+    return ret;
 }
 
 // tree/phylokernelnew.h:1150-1281 (the part that builds the list; execution happens inside the engine call)
 void PhyloTree::computeTraversalInfo(PhyloNode *node, PhyloNode *dad) {
     traversal_info.clear();
+    if (params.lh_mem_save == LM_MEM_SAVE) {   // the larger side first (tree/phylokernelnew.h:1171-1186)
+        const int node_size = computeSize(dad->findNeighbor(node), dad), dad_size = computeSize(node->findNeighbor(dad), node);
+        if (node_size < dad_size) std::swap(node, dad);
+    }
     PhyloNeighbor *dad_branch = dad->findNeighbor(node);
     PhyloNeighbor *node_branch = node->findNeighbor(dad);
-    computeTraversalInfo(dad_branch, dad);
-    computeTraversalInfo(node_branch, node);
+    const bool dad_locked = computeTraversalInfo(dad_branch, dad);
+    const bool node_locked = computeTraversalInfo(node_branch, node);
+    if (dad_locked) mem_slots.unlock(dad_branch);
+    if (node_locked) mem_slots.unlock(node_branch);
 }
 
 void PhyloTree::branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &node_slot, int &dad_kind, int &dad_id) {
@@ -420,6 +545,17 @@ void PhyloTree::branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &nod
     node_slot = dad_branch->slot;
     if (dad->isLeaf()) { dad_kind = 0; dad_id = dad->id; }
     else { dad_kind = 1; dad_id = node_branch->slot; }
+}
+
+// Planning without execution (Params::plan_only; CPU tests and hosts that run the op list themselves): the traversal
+// of computeLikelihoodBranch(dad_branch, dad) with every flag and slot updated exactly as if it had been executed.
+void PhyloTree::planBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, std::vector<b200lk_op> &ops, int &node_slot, int &dad_kind,
+                           int &dad_id, double &length) {
+    initializeAllPartialLh();
+    length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    ops = traversal_info;
+    traversal_info.clear();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

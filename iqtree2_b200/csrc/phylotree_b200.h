@@ -46,7 +46,12 @@ struct PhyloNode {
     void clearReversePartialLh(PhyloNode *dad);   // tree/phylonode.cpp:22-34
 };
 
+enum LhMemSave { LM_PER_NODE = 0, LM_MEM_SAVE = 1 };   // utils/tools.h (LikelihoodMemSave; -mem option)
+
 struct Params {
+    LhMemSave lh_mem_save = LM_PER_NODE;   // -mem: LM_MEM_SAVE recycles max_lh_slots CLV slots (tree/phylotree.cpp:999-1021)
+    double max_mem_size = 0.0;             // LM_MEM_SAVE: 0 = the minimum log2(T)+1 slots, <= 1 = fraction of the T-2 slots,
+                                           // > 1 = bytes of device memory for CLV slots (incl. the 2 NNI spares)
     double min_branch_length = 1e-6;   // utils/tools.cpp:1235 (reset to 0.1/nsites-style values by the caller if wanted)
     double max_branch_length = 10.0;   // utils/tools.cpp:1238
     int device = 0;
@@ -54,6 +59,31 @@ struct Params {
     bool force_norm = false;           // test hook: keep NORM_LH where the reference would switch to SAFE_LH
     int schedule = 0;
     bool fused_newton = true;          // optimizeOneBranch through b200lk_newton_branch (one C call per branch)
+    bool plan_only = false;            // no engine: traversals are planned (flags, slots, op lists) but not executed
+};
+
+// tree/memslot.h, tree/memslot.cpp: the slot table of the memory-saving mode.  Same operations, same eviction rule
+// (the unlocked slot whose neighbour has the smallest subtree); a slot is a device CLV slot index instead of a pointer pair.
+struct MemSlot {
+    int status = 0;
+    PhyloNeighbor *nei = nullptr;
+};
+class MemSlotVector : public std::vector<MemSlot> {
+public:
+    bool enabled = false;
+    void init(int num_slot);                                   // memslot.cpp:28-40
+    void reset();                                              // :42-51
+    bool lock(PhyloNeighbor *nei);                             // :92-104
+    void unlock(PhyloNeighbor *nei);                           // :106-117
+    bool locked(PhyloNeighbor *nei);                           // :119-135
+    int allocate(PhyloNeighbor *nei);                          // :137-176
+    void update(PhyloNeighbor *nei);                           // :178-192
+    void takeover(PhyloNeighbor *nei, PhyloNeighbor *taken);   // :211-229
+    int findNei(PhyloNeighbor *nei) const;                     // :54-59
+private:
+    void addNei(PhyloNeighbor *nei, int id);                   // :61-67
+    std::map<PhyloNeighbor *, int> nei_id_map;
+    int free_count = 0;
 };
 
 class PhyloTree {
@@ -83,6 +113,8 @@ public:
     void computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf);
     double computeLikelihoodFromBuffer();
     void computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *dad);   // flush the stale partials below one directed branch
+    void planBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, std::vector<b200lk_op> &ops, int &node_slot, int &dad_kind,
+                    int &dad_id, double &length);
     void computePatternLikelihood(double *pattern_lh, double *cur_logl = nullptr, double *pattern_lh_cat = nullptr);
     void computePatternLhCat(double *pattern_lh_cat);
 
@@ -114,6 +146,8 @@ public:
     bool theta_computed = false;
     double curScore = 0.0;
     int leafNum = 0, nodeNum = 0;
+    int max_lh_slots = 0;             // tree/phylotree.h (set by initializeAllPartialLh; T-2 for LM_PER_NODE)
+    MemSlotVector mem_slots;
 
 private:
     bool computeTraversalInfo(PhyloNeighbor *dad_branch, PhyloNode *dad);   // tree/phylotree.cpp:5918-6028
@@ -136,6 +170,7 @@ private:
     bool fused_ = false;
     std::vector<double> eval_, evec_, inv_evec_, mix_weight_, cat_rate_, cat_prop_;
     b200lk_engine *engine_ = nullptr;
+    bool initialized_ = false;
     std::vector<b200lk_op> traversal_info;
     std::vector<double> pattern_lh_;
 };

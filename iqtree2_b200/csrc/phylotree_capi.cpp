@@ -116,4 +116,35 @@ int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tole
 }
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t) { return t->tree.num_partial_lh_computations; }
 
+int b200pt_set_mem_save(b200pt_tree *t, int32_t on, double max_mem_size) {
+    GUARD({
+        t->tree.deleteAllPartialLh();
+        t->tree.params.lh_mem_save = on ? b200::LM_MEM_SAVE : b200::LM_PER_NODE;
+        t->tree.params.max_mem_size = max_mem_size;
+    })
+}
+int b200pt_set_plan_only(b200pt_tree *t, int32_t on) {
+    GUARD({
+        t->tree.deleteAllPartialLh();
+        t->tree.params.plan_only = on != 0;
+    })
+}
+int b200pt_max_lh_slots(b200pt_tree *t) {
+    try { t->tree.initializeAllPartialLh(); return t->tree.max_lh_slots; }
+    catch (const std::exception &ex) { t->err = ex.what(); return -1; }
+}
+int b200pt_plan_branch(b200pt_tree *t, int32_t branch, b200lk_op *ops, int32_t cap, int32_t *nops, int32_t *node_slot,
+                       int32_t *dad_kind, int32_t *dad_id, double *length) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        ends(t, branch, a, b);
+        std::vector<b200lk_op> v;
+        int ns, dk, di;
+        t->tree.planBranch(a->findNeighbor(b), a, v, ns, dk, di, *length);
+        if ((int)v.size() > cap) throw std::runtime_error("op buffer too small");
+        std::memcpy(ops, v.data(), v.size() * sizeof(b200lk_op));
+        *nops = (int)v.size(); *node_slot = ns; *dad_kind = dk; *dad_id = di;
+    })
+}
+
 }  // extern "C"

@@ -116,6 +116,32 @@ class PhyloTree:
         self._check(self.lib.b200pt_optimize_all_branches(self._h, iterations, C.c_double(tolerance), max_nr_step, C.byref(out)))
         return out.value
 
+    # ---- -mem (LM_MEM_SAVE) and planning without execution ------------------------------------------------------
+    def set_mem_save(self, on=True, max_mem_size=0.0):
+        """Params::lh_mem_save / max_mem_size (tree/phylotree.cpp:999-1021): recycle a bounded number of CLV slots."""
+        self._check(self.lib.b200pt_set_mem_save(self._h, int(on), C.c_double(max_mem_size)))
+
+    def set_plan_only(self, on=True):
+        self._check(self.lib.b200pt_set_plan_only(self._h, int(on)))
+
+    @property
+    def max_lh_slots(self):
+        n = self.lib.b200pt_max_lh_slots(self._h)
+        self._check(n)
+        return n
+
+    def plan_branch(self, branch):
+        """(ops, (kind, id) of the node end, (kind, id) of the dad end, length): the traversal of
+        computeLikelihoodBranch(branch); flags and slots are updated as if it had been executed."""
+        from . import plan
+        cap = 4 * max(self.lib.b200pt_num_branches(self._h), 4)
+        ops = np.zeros(cap, dtype=plan.OP_DTYPE)
+        nops, ns, dk, di = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        ln = C.c_double()
+        self._check(self.lib.b200pt_plan_branch(self._h, branch, _dp(ops), cap, C.byref(nops), C.byref(ns), C.byref(dk),
+                                                C.byref(di), C.byref(ln)))
+        return ops[:nops.value].copy(), (plan.KIND_SLOT, ns.value), (dk.value, di.value), ln.value
+
     @property
     def num_partial_lh_computations(self):
         return int(self.lib.b200pt_num_partial_lh_computations(self._h))

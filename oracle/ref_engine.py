@@ -53,6 +53,11 @@ def lib():
     return _lib
 
 
+def set_mem_save(on: bool, max_mem_size: float = 0.0):
+    """Params::lh_mem_save / max_mem_size (-mem) for the trees created afterwards."""
+    lib().iqref_set_mem_save(int(bool(on)), C.c_double(float(max_mem_size)))
+
+
 def max_threads() -> int:
     return int(lib().iqref_max_threads())
 
@@ -181,6 +186,10 @@ class RefTree:
         ll, df, ddf, mean = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         best = lib().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))
         return dict(best_sec=best, mean_sec=mean.value, logl=ll.value, df=df.value, ddf=ddf.value)
+
+    @property
+    def max_lh_slots(self):
+        return int(lib().iqref_max_lh_slots(self._h))
 
     def last_traversal_size(self):
         """partial updates the last branch_logl / branch_derv call scheduled (traversal_info.size())"""

@@ -462,6 +462,15 @@ int iqref_get_branches(void *hv, uint8_t *masks /* [nbranch][ntaxa] */, double *
 // the new kernel does not maintain num_partial_lh_computations)
 int iqref_last_traversal_size(void *hv) { return (int)((Handle *)hv)->tree->traversal_info.size(); }
 
+// -mem: Params::lh_mem_save / max_mem_size as parseArg sets them (utils/tools.cpp, "-mem"); applies to trees created
+// AFTERWARDS (getMemoryRequired / MemSlotVector::init read the global Params)
+void iqref_set_mem_save(int on, double max_mem_size) {
+    init_params(Params::getInstance().num_threads > 0 ? Params::getInstance().num_threads : 1);
+    Params::getInstance().lh_mem_save = on ? LM_MEM_SAVE : LM_PER_NODE;
+    Params::getInstance().max_mem_size = max_mem_size;
+}
+int iqref_max_lh_slots(void *hv) { return (int)((Handle *)hv)->tree->max_lh_slots; }
+
 int iqref_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

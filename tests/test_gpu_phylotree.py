@@ -101,3 +101,32 @@ def test_protein_tree_api_and_safe_kernel():
         ll_o = o.optimize_all_branches(iterations=3)
         assert abs(ll_g - ll_o) < 1e-6
         np.testing.assert_allclose(g.branches()[2], o.lengths(), atol=1e-6)
+
+
+@pytest.mark.parametrize("kind,schedule,mem", [("dna", 0, 0.0), ("dna", 1, 0.0), ("dna", 0, 0.5), ("aa", 0, 0.0), ("aa", 1, 0.3),
+                                               ("aa_c4", 0, 0.0), ("n7", 0, 0.0)])
+def test_mem_save_slot_recycling_on_gpu(kind, schedule, mem):
+    """-mem (LM_MEM_SAVE): a bounded number of recycled CLV slots gives the same likelihoods as one slot per node, for
+    the walker kernels (in-order op list, register chaining) and the levelled schedule (WAR/WAW-aware levels)."""
+    from cases import make_case
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=28, nsites=260, seed=11)
+    newick = tree.to_newick()
+    full = make_gpu_tree(tree.names, pat, freq, model, newick)
+    full.set_pattern_invar(inv)
+    ms = make_gpu_tree(tree.names, pat, freq, model, newick, schedule=schedule)
+    ms.set_mem_save(True, mem)
+    ms.set_pattern_invar(inv)
+    assert ms.max_lh_slots == max(int(np.log2(28)) + 1, int(np.floor(mem * 26)))
+    nbr = len(full.branches()[0])
+    for br in np.random.default_rng(3).permutation(nbr)[:12]:
+        ll_f, ll_m = full.compute_likelihood_branch(int(br)), ms.compute_likelihood_branch(int(br))
+        assert abs(ll_f - ll_m) < 1e-9 * abs(ll_f), (br, ll_f, ll_m)
+        np.testing.assert_allclose(ms.compute_pattern_likelihood(), full.compute_pattern_likelihood(), rtol=1e-12)
+        d_f, d_m = full.compute_likelihood_derv(int(br)), ms.compute_likelihood_derv(int(br))
+        np.testing.assert_allclose(d_m, d_f, rtol=1e-9)
+    assert ms.num_partial_lh_computations >= full.num_partial_lh_computations
+    # branch-length optimisation under the slot budget reaches the same optimum
+    ll_f = full.optimize_all_branches(iterations=2)
+    ll_m = ms.optimize_all_branches(iterations=2)
+    assert abs(ll_f - ll_m) < 1e-6
+    np.testing.assert_allclose(ms.branches()[2], full.branches()[2], atol=1e-6)

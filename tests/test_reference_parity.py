@@ -158,3 +158,37 @@ def test_branch_optimisation_order_and_lengths_on_a_larger_tree():
     ref_len = r.branches()
     for split, ln in zip(spl, t.lengths()):
         assert abs(ref_len[split] - ln) < 1e-9
+
+
+@pytest.mark.parametrize("mem,tree_kind", [(0.0, "yule"), (0.4, "yule"), (0.0, "caterpillar")])
+def test_mem_save_slot_table_matches_reference(mem, tree_kind):
+    """-mem (LM_MEM_SAVE): the host mirror's MemSlotVector against the reference's (tree/memslot.cpp) — same slot budget,
+    the same number of partial updates for every move of the evaluation branch, and the reference's own logL is unchanged
+    by the mode (so an op list that recomputes the same directed partials is the same computation)."""
+    from iqtree2_b200.phylotree import PhyloTree
+    tree, model, pat, freq, inv = make_case("dna", ntaxa=26, nsites=80, tree_kind=tree_kind)
+    r_full = ref_engine.RefTree(tree, model, pat, freq)
+    ll_true = r_full.branch_logl(0)[0]
+    r_full.close()
+    ref_engine.set_mem_save(True, mem)   # a process-wide switch (Params::getInstance()): it must stay on while r lives
+    try:
+        r = ref_engine.RefTree(tree, model, pat, freq)
+        t = PhyloTree()
+        t.set_plan_only(True)
+        t.set_alignment(tree.names, pat, freq, model)
+        t.set_model(model)
+        t.read_tree(tree.to_newick())
+        t.set_mem_save(True, mem)
+        assert t.max_lh_slots == r.max_lh_slots
+        o = load_engine(OracleEngine, tree, model, pat, freq, inv, nslots=t.max_lh_slots + 2)
+        pa, pb, _ = t.branches()
+        pendant = {int(min(x, y)): k for k, (x, y) in enumerate(zip(pa, pb)) if min(x, y) < tree.ntaxa}
+        for leaf in [0, 7, 19, 3, 3, 25, 12, 0, 1, 24, 8]:
+            ll_r = r.branch_logl(leaf)[0]
+            assert abs(ll_r - ll_true) < 1e-8
+            ops, a, b, L = t.plan_branch(pendant[leaf])
+            assert len(ops) == r.last_traversal_size(), (leaf, len(ops), r.last_traversal_size())
+            assert abs(o.branch_logl(ops, a, b, L) - ll_r) < 1e-8
+        r.close(); o.close(); t.close()
+    finally:
+        ref_engine.set_mem_save(False)
