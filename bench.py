@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS))
     ap.add_argument("--taxa", type=int, default=0, help="override taxa (debug)")
     ap.add_argument("--patterns", type=int, default=0, help="override patterns (debug)")
+    ap.add_argument("--ncat", type=int, default=0, help="override the number of Gamma categories (debug; single-class workloads)")
     ap.add_argument("--schedule", type=int, default=0, help="0 auto, 1 levelled, 2 walker")
     ap.add_argument("--variant", type=int, default=0, help="kernel variant of the walker schedule (development A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the CPU-baseline sample (0 = auto)")
@@ -222,8 +223,10 @@ def main():
     if args.patterns:
         nptn = args.patterns
     model = mk()
+    if args.ncat:
+        model = {"dna_1000x1M_gtr_g4": models.make_gtr_gamma, "aa_200x100k_lg_g4": models.make_lg_gamma}[args.workload](ncat=args.ncat)
     B, S = model.nstates * model.ncat_mix, 1
-    workload_name = args.workload if not (args.taxa or args.patterns) else f"{args.workload}[override {ntaxa}x{nptn}]"
+    workload_name = args.workload if not (args.taxa or args.patterns or args.ncat) else f"{args.workload}[override {ntaxa}x{nptn} ncat={model.ncat_mix}]"
 
     # ---------------------------------------------------------------------------------------------------------
     # reference arm: the reference's own CPU algorithm on the host cores (rank 0 only)

@@ -18,6 +18,7 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
     "-diag-suppress", "550",
+    *(["-DB200LK_DIAG"] if os.environ.get("B200LK_DIAG") else []),
     "-shared",
 ]
 

@@ -180,6 +180,7 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     Dev &d = e->d;
     d.n = n; d.C = e->C; d.ncat = cfg->ncat; d.nmix = cfg->nmix; d.denom = e->denom; d.B = e->B; d.S = e->S;
     d.su = cfg->state_unknown; d.P = e->P; d.Ppad = Ppad;
+    d.clv_f20 = (n == 20 && e->C % cfg->nmix == 0) ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
     d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
     d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
     double *m = e->d_model;
@@ -399,8 +400,14 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * 4);   // 4 resident CTAs per SM (128 regs/thread)
     CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
-    if (e->cfg.safe_numeric) k_walk_n4c4<true><<<grid, kTile, 0, e->stream>>>(e->d, M, e->d_opinfo, nops, e->d_counter);
-    else k_walk_n4c4<false><<<grid, kTile, 0, e->stream>>>(e->d, M, e->d_opinfo, nops, e->d_counter);
+    {   // kernel_variant 1 (A/B): one burst of 16 stores at the end of the op instead of per-category stores
+        const bool safe = e->cfg.safe_numeric != 0;
+        static const void *const kernels[4] = {(const void *)k_walk_n4c4<false, true>, (const void *)k_walk_n4c4<true, true>,
+                                               (const void *)k_walk_n4c4<false, false>, (const void *)k_walk_n4c4<true, false>};
+        const int v = e->kernel_variant == 1 ? 1 : 0;
+        void *args[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
+        CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, 0, e->stream));
+    }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;
     e->launches += 2;
@@ -410,24 +417,33 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     return 0;
 }
 
-// the 20-state walker (k_walk_n20) serves the walker schedule of every single-class protein model, any number of categories
-static size_t walk20_smem(const b200lk_engine *e) {
-    return sizeof(double) * (2 * (size_t)e->B + 2 * (size_t)(e->cfg.state_unknown + 1) * tab20_stride(e->C));
-}
+// the 20-state FP64-MMA walker serves the walker schedule of every protein model: any number of categories, mixtures,
+// fused classes
 static int walk20_cpb(const b200lk_engine *e) { return e->C / e->cfg.nmix; }   // categories per class block
 static bool use_walk20(const b200lk_engine *e) {
     return e->schedule != 1 && e->cfg.nstates == 20 && e->C % e->cfg.nmix == 0 && e->h_evec.size() == (size_t)400 * e->cfg.nmix &&
            2 * stage20_doubles(walk20_cpb(e), e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
 }
 
-// [VAR*4 + MIX*2 + SAFE]; VAR 0 = base, 1 = DFMA tail (measured slower: 8.4 vs 6.7 ms, kept for A/B), 2 = split-K accumulators
-static const void *const walk20_mma_kernels[12] = {
-    (const void *)k_walk_n20_mma<false, false, 0>, (const void *)k_walk_n20_mma<true, false, 0>,
-    (const void *)k_walk_n20_mma<false, true, 0>,  (const void *)k_walk_n20_mma<true, true, 0>,
-    (const void *)k_walk_n20_mma<false, false, 1>, (const void *)k_walk_n20_mma<true, false, 1>,
-    (const void *)k_walk_n20_mma<false, true, 1>,  (const void *)k_walk_n20_mma<true, true, 1>,
-    (const void *)k_walk_n20_mma<false, false, 2>, (const void *)k_walk_n20_mma<true, false, 2>,
-    (const void *)k_walk_n20_mma<false, true, 2>,  (const void *)k_walk_n20_mma<true, true, 2>};
+// k_walk_n20_mma configurations: {warps per CTA, kernels [MIX*2 + SAFE]}; index = kernel_variant (b200lk_set_schedule(e, 10 + v))
+struct Walk20Cfg { int nw; const void *f[4]; };
+#define W20CFG(NW, BSM, MINB)                                                                                          \
+    { NW, { (const void *)k_walk_n20_mma<false, false, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, false, NW, BSM, MINB>, \
+            (const void *)k_walk_n20_mma<false, true, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, true, NW, BSM, MINB> } }
+static const Walk20Cfg walk20_cfgs[] = {
+    W20CFG(4, 0, 3),     // 0: 12 warps/SM, both matrices as register-resident B fragments
+    W20CFG(8, 2, 2),     // 1: 16 warps/SM, inv_evec fragments from shared memory
+    W20CFG(8, 3, 2),     // 2: 16 warps/SM, both matrices from shared memory
+    W20CFG(6, 3, 3),     // 3: 18 warps/SM
+    W20CFG(4, 0, 3),     // 4: as 0 with fixed 128-pattern tiles (A/B of the balanced tiling)
+    W20CFG(10, 3, 2),    // 5: 20 warps/SM
+#ifdef B200LK_DIAG
+#define W20DBG(DBG) { 4, { (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, \
+                           (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG> } }
+    W20DBG(1), W20DBG(2), W20DBG(3), W20DBG(4),   // 6: no stores, 7: no loads, 8: neither, 9: no DMMAs (wrong results; diagnosis)
+#endif
+};
+constexpr int kNumWalk20Cfgs = (int)(sizeof(walk20_cfgs) / sizeof(walk20_cfgs[0]));
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
@@ -461,37 +477,32 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
     k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo);
-    const bool use_mma = mix || e->kernel_variant != 1;   // variant 1 = the DFMA/constant-bank kernel (single class; A/B measurements)
-    const int var = e->kernel_variant == 3 ? 1 : e->kernel_variant == 4 ? 2 : 0;   // variants 3 / 4: A/B switches (see walk20_mma_kernels)
-    Model20 Mloc;   // 6.4 KB kernel parameter, passed by value
-    if (!use_mma) for (int k = 0; k < 400; k++) { Mloc.evec[k] = e->h_evec[k]; Mloc.inv[k] = e->h_inv_evec[k]; }
-    const long long ntiles = e->Ppad / kTile;
-    // the MMA walker double-buffers whole staging blocks; the DFMA variant keeps one buffer without the header
-    const size_t smem = use_mma ? 2 * stage_sz * sizeof(double) : walk20_smem(e);
+    const Walk20Cfg &cfg = walk20_cfgs[(e->kernel_variant >= 0 && e->kernel_variant < kNumWalk20Cfgs) ? e->kernel_variant : 0];
+    const int tile_ptn = cfg.nw * 32;
+    const size_t smem = 2 * stage_sz * sizeof(double);   // the walker double-buffers whole staging blocks
     if (!e->walk20_attr_set) {
-        CK(cudaFuncSetAttribute(k_walk_n20<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(k_walk_n20<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        for (const void *f : walk20_mma_kernels) {
+        for (const void *f : cfg.f) {
             CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         int per_sm = 0;
-        if (use_mma) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, walk20_mma_kernels[var * 4], kTile, smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_walk_n20<false>, kTile, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.f[0], tile_ptn, smem));
         e->walk20_ctas_per_sm = std::max(per_sm, 1);
         e->walk20_attr_set = true;
     }
-    const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * e->walk20_ctas_per_sm);
+    // balanced tiles (see the kernel): whole waves of the resident CTAs, each tile floor/ceil(nblocks/ntiles) <= nw warp blocks
+    const long long nblocks = e->Ppad / 32, slots = (long long)e->num_sms * e->walk20_ctas_per_sm;
+    const long long waves = (nblocks + cfg.nw * slots - 1) / (cfg.nw * slots);
+    int ntiles = (int)std::min<long long>(waves * slots, nblocks);
+    if (e->kernel_variant == 4) ntiles = (int)((nblocks + cfg.nw - 1) / cfg.nw);   // A/B: fixed full tiles
+    const int grid = (int)std::min<long long>(ntiles, slots);
     CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
-    if (use_mma) {
+    {
         const bool safe = e->cfg.safe_numeric != 0;
-        void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
-        CK(cudaLaunchKernel(walk20_mma_kernels[var * 4 + (mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, smem, e->stream));
-    } else {
-        if (e->cfg.safe_numeric) k_walk_n20<true><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
-        else k_walk_n20<false><<<grid, kTile, smem, e->stream>>>(e->d, Mloc, e->d_opinfo, nops, e->d_counter);
+        void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter, (void *)&ntiles};
+        CK(cudaLaunchKernel(cfg.f[(mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(tile_ptn), args, smem, e->stream));
     }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;
@@ -860,7 +871,18 @@ extern "C" int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) { return
 extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_theta, e->B, out); }
 extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
-    return read_interleaved_f64(e, e->d_partial + (size_t)slot * e->d.slot_stride, e->B, out);
+    const double *src = e->d_partial + (size_t)slot * e->d.slot_stride;
+    if (!e->d.clv_f20) return read_interleaved_f64(e, src, e->B, out);
+    cudaSetDevice(e->cfg.device);
+    const size_t total = (size_t)e->P * e->B;
+    int rc = ensure_scratch(e, total * sizeof(double));
+    if (rc) return rc;
+    k_deinterleave_clv<<<(unsigned)((total + 255) / 256), 256, 0, e->stream>>>(e->d, src, e->d_scratch);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
 }
 extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out) {
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");

@@ -38,6 +38,7 @@ struct ChildJob {
 struct Dev {
     int n, C, ncat, nmix, denom, B, S, su;
     int quirks;              // B200LK_QUIRK_* (include/b200lk.h)
+    int clv_f20;             // CLV slots use the 20-state fragment-major layout (clv20_off) instead of the warp-interleaved one
     long long P, Ppad;
     long long slot_stride;   // Ppad * B   doubles per CLV slot
     long long scale_stride;  // Ppad * S   uint16 per slot
@@ -54,6 +55,28 @@ struct Dev {
 __device__ __forceinline__ long long pbase(long long p, int width) {
     return (p >> 5) * (long long)width * kWarp + (p & 31);
 }
+
+// 20-state engines keep their CLV slots FRAGMENT-MAJOR (the order the FP64-MMA walker produces and consumes them in, see
+// k_walk_n20_mma): a 32-pattern block is [M-tile mt = 4][category c = C][160 doubles], and the 160 doubles of 8 patterns x 20
+// eigen-indices are  i < 16: (i/8)*64 + ((i%8)/2)*16 + g*2 + i%2   (C-fragment order of an 8x8 state tile, g = pattern%8),
+//                    i >= 16: 128 + g*4 + (i-16).
+// Same size as the warp-interleaved layout (B*32 doubles per 32 patterns); theta, _pattern_lh_cat and scale_num keep pbase().
+constexpr int kClv20Step = 160;
+__host__ __device__ __forceinline__ int clv20_off(int i, int g) {
+    return i < 16 ? (i >> 3) * 64 + ((i & 7) >> 1) * 16 + g * 2 + (i & 1) : 128 + g * 4 + (i - 16);
+}
+// element (category c, index i) of pattern p inside a CLV slot, for the thread-per-pattern kernels
+struct ClvIdx {
+    long long base;
+    int g, n, f20;
+    __device__ __forceinline__ ClvIdx(const Dev &D, long long p) {
+        f20 = D.clv_f20; n = D.n; g = (int)(p & 7);
+        base = f20 ? (p >> 5) * (long long)D.B * kWarp + ((p >> 3) & 3) * (long long)D.C * kClv20Step : pbase(p, D.B);
+    }
+    __device__ __forceinline__ long long operator()(int c, int i) const {
+        return base + (f20 ? c * kClv20Step + clv20_off(i, g) : (c * n + i) * kWarp);
+    }
+};
 
 // ------------------------------------------------------------------------------------------------------------
 // computePartialInfo (tree/phylokernelnew.h:900-1110): echild = evec * exp(eval * rate_c * len) and, for leaf
@@ -205,12 +228,12 @@ __device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op
     constexpr int NMAX = NT ? NT : 64;
     const int n = NT ? NT : D.n;
     const int C = D.C, B = D.B;
-    const long long pb = pbase(p, B);
+    const ClvIdx at(D, p);
     const long long sb = SAFE ? pbase(p, C) : p;
-    double *out = D.partial + (long long)op.dst * D.slot_stride + pb;
+    double *out = D.partial + (long long)op.dst * D.slot_stride;
     uint16_t *osc = D.scale + (long long)op.dst * D.scale_stride + sb;
-    const double *Lp = (op.ncase == 2) ? D.partial + (long long)op.lid * D.slot_stride + pb : nullptr;
-    const double *Rp = (op.ncase >= 1) ? D.partial + (long long)op.rid * D.slot_stride + pb : nullptr;
+    const double *Lp = (op.ncase == 2) ? D.partial + (long long)op.lid * D.slot_stride : nullptr;
+    const double *Rp = (op.ncase >= 1) ? D.partial + (long long)op.rid * D.slot_stride : nullptr;
     const uint16_t *lsc = (op.ncase == 2) ? D.scale + (long long)op.lid * D.scale_stride + sb : nullptr;
     const uint16_t *rsc = (op.ncase >= 1) ? D.scale + (long long)op.rid * D.scale_stride + sb : nullptr;
     const double *leafL = nullptr, *leafR = nullptr;
@@ -228,11 +251,11 @@ __device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op
         const double *inv = D.inv_evec + (long long)m * n * n;
         if (Lp) {
 #pragma unroll
-            for (int i = 0; i < n; i++) lv[i] = Lp[(long long)(c * n + i) * kWarp];
+            for (int i = 0; i < n; i++) lv[i] = Lp[at(c, i)];
         }
         if (Rp) {
 #pragma unroll
-            for (int i = 0; i < n; i++) rv[i] = Rp[(long long)(c * n + i) * kWarp];
+            for (int i = 0; i < n; i++) rv[i] = Rp[at(c, i)];
         }
 #pragma unroll
         for (int x = 0; x < n; x++) {
@@ -259,11 +282,12 @@ __device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op
             lh_max = fmax(lh_max, cmax);
         }
 #pragma unroll
-        for (int i = 0; i < n; i++) out[(long long)(c * n + i) * kWarp] = lv[i];
+        for (int i = 0; i < n; i++) out[at(c, i)] = lv[i];
     }
     if (!SAFE) {
         if (check && lh_max < kScalingThreshold) {
-            for (int k = 0; k < B; k++) out[(long long)k * kWarp] *= kTwo256;   // rare path: re-scale own output
+            for (int c = 0; c < C; c++)
+                for (int i = 0; i < n; i++) out[at(c, i)] *= kTwo256;   // rare path: re-scale own output
             norm_scale += 1;
         }
         osc[0] = (uint16_t)norm_scale;
@@ -466,7 +490,7 @@ constexpr unsigned kThresholdHi = (1023u - 256u) << 20;   // high word of 2^-256
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <bool SAFE>
+template <bool SAFE, bool ESTORE = true>
 __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_constant__ Model4 M, const double *stage, int nops,
                                                        unsigned long long *counter) {
     // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
@@ -559,6 +583,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 }
             }
             const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
+            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
             unsigned mhi = 0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -623,18 +648,30 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                         cursc[c] += 1;
                     }
                 } else mhi = max(mhi, chi);
+                // store this category now: the LSU drains four stores per thread while the next category computes, instead
+                // of a burst of 16 at the end of the op that the next op's first FP64 instruction then waits behind (ncu:
+                // 18 % of all stall samples sat on the register hand-over of that burst)
+                if (ESTORE) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) Op[(c * 4 + i) * kWarp] = cur[c * 4 + i];
+                }
             }
             if (!SAFE) {
                 cursc[0] += scB[0];
-                if (ncase != 0 && may_scale && mhi < kThresholdHi) {
+                if (ncase != 0 && may_scale && mhi < kThresholdHi) {   // rare: all 16 values underflowed; rescale and store again
 #pragma unroll
                     for (int k = 0; k < 16; k++) cur[k] *= kTwo256;
                     cursc[0] += 1;
+                    if (ESTORE) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) Op[k * kWarp] = cur[k];
+                    }
                 }
             }
-            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
+            if (!ESTORE) {
 #pragma unroll
-            for (int k = 0; k < 16; k++) Op[k * kWarp] = cur[k];
+                for (int k = 0; k < 16; k++) Op[k * kWarp] = cur[k];
+            }
 #pragma unroll
             for (int c = 0; c < (SAFE ? 4 : 1); c++)
                 D.scale[(long long)dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
@@ -645,27 +682,18 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 20-state WALKER (LG/WAG/JTT... +G/+I+G/+R, single class): the FP64-bound kernel of BASELINE config 3.
+// 20-state WALKER (LG/WAG/JTT... +G/+I+G/+R, C10-C60 mixtures, fused classes): the kernel of BASELINE configs 3 and 4.
 //
 // Per pattern, category and child the update is a 20x20 mat-vec; three of them per inner-inner node (two children,
-// one back-transform) = C*(6n^2+n) flops against 3*(8B+2S) bytes (about 5 flop/B): on B200 this sits on the FP64 side of
-// the ridge (64 DFMA/clk/SM = 36 TFLOP/s against 6.5 TB/s).  B200's FP64 tensor path (mma.sync m8n8k4.f64, DMMA) has the
-// SAME peak as its DFMA pipe (measured 37.2 vs 36.3 TFLOP/s, scripts/fp64_peaks.cu), and 20 is not a multiple of the
-// 8-wide MMA tile (24/20 = 17 % padding), so DMMA would be slower here; tcgen05/TMEM have no FP64 kind at all.  The
-// kernel therefore aims at the DFMA pipe's peak: one instruction per FMA, no shared-memory or register traffic for
-// the matrices:
-//   * the operator is applied factorised, evec . (exp(eval r_c t) (.) L)  (tree/phylokernelnew.h:1016-1031 builds
-//     echild = evec*exp explicitly), so that the only matrices are the model's evec and inv_evec; they travel as a
-//     6.4 KB __grid_constant__ kernel parameter, i.e. constant-bank operands of the DFMAs (SASS: DFMA R, R, c[0x0][..], R);
-//   * per-op data is 2 x C x 20 exponentials; tip children use the reference's lookup tables
-//     partial_lh_leaves[state][c][x] (:1036-1056), staged in shared memory per op;
-//   * thread per pattern, whole traversal per 128-pattern tile (same schedule as k_walk_n4c4), CLVs warp-interleaved.
+// one back-transform) = C*(6n^2+n) flops against 3*(8B+2S) bytes (about 5 flop/B): on B200 this sits at the ridge between
+// the FP64 pipe (36-37 TFLOP/s measured, DFMA and DMMA share it) and HBM (6.5 TB/s).
+//
+// The operator is applied factorised, evec . (exp(eval r_c t) (.) L)  (tree/phylokernelnew.h:1016-1031 builds
+// echild = evec*exp explicitly), so the only matrices are the model's evec and inv_evec; per-op data is 2 x C x 20
+// exponentials; tip children use the reference's lookup tables partial_lh_leaves[state][c][x] (:1036-1056), staged in shared
+// memory per op.  History (config 3, ms per evaluation): generic thread-per-pattern kernel 30.6; DFMA with constant-bank
+// operands 11.4; DMMA with register-resident B fragments 8.4 -> 6.7; fragment-major CLV layout (below): see DESIGN.md.
 // ------------------------------------------------------------------------------------------------------------
-struct Model20 {
-    double evec[400];   // evec[x*20 + i]
-    double inv[400];    // inv_evec[i*20 + x]
-};
-
 struct WalkJob20 {
     double lenA, lenB;
     int32_t dst, ncase, aid, bid;   // ncase: 0 tip-tip, 1 tip(A)-inner(B), 2 inner-inner; ids: taxon row or slot
@@ -726,221 +754,108 @@ __global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *j
     }
 }
 
-template <bool SAFE>
-__global__ void __launch_bounds__(kTile, 2) k_walk_n20(Dev D, const __grid_constant__ Model20 M, const double *stage, int nops,
-                                                      unsigned long long *counter) {
-    extern __shared__ __align__(16) double s_dyn20[];   // exp[2][C*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]
-    __shared__ long long s_item;
-    __shared__ int s_hdr[4];
-    const int tid = threadIdx.x;
-    const int C = D.C, B = C * 20, rows = D.su + 1, TS = tab20_stride(C);
-    const size_t stage_sz = stage20_doubles(C, D.su);
-    double *s_exp = s_dyn20, *s_tabA = s_dyn20 + 2 * B, *s_tabB = s_tabA + (size_t)rows * TS;
-    const long long ntiles = D.Ppad / kTile;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
-        __syncthreads();
-        const long long tile = s_item;
-        if (tile >= ntiles) break;
-        const long long p = tile * kTile + tid;
-        const long long pb = pbase(p, B);
-        const long long sb = SAFE ? pbase(p, C) : p;
-        const bool may_scale = D.invar[p] == 0.0;
-        for (int o = 0; o < nops; o++) {
-            const double *st = stage + (size_t)o * stage_sz;
-            __syncthreads();   // everyone is done with the previous op's shared data
-            if (tid < 4) s_hdr[tid] = reinterpret_cast<const int32_t *>(st)[tid];
-            const int ncase_g = reinterpret_cast<const int32_t *>(st)[1];
-            {
-                const double2 *src = reinterpret_cast<const double2 *>(st + 4);
-                double2 *dst = reinterpret_cast<double2 *>(s_exp);
-                for (int k = tid; k < B; k += kTile) dst[k] = __ldg(src + k);   // 2*B doubles
-                if (ncase_g <= 1) {
-                    const double2 *ta = reinterpret_cast<const double2 *>(st + 4 + 2 * B);
-                    double2 *da = reinterpret_cast<double2 *>(s_tabA);
-                    const int nv = rows * TS / 2 * (ncase_g == 0 ? 2 : 1);   // tabB follows tabA in both layouts
-                    for (int k = tid; k < nv; k += kTile) da[k] = __ldg(ta + k);
-                }
-            }
-            __syncthreads();
-            const int dst = s_hdr[0], ncase = s_hdr[1], aid = s_hdr[2], bid = s_hdr[3];
-            // A: tip for ncase <= 1, else internal; B: tip for ncase == 0, else internal
-            const double *Ap = nullptr, *Bp = nullptr, *tA = nullptr, *tB = nullptr;
-            if (ncase == 2) Ap = D.partial + (long long)aid * D.slot_stride + pb;
-            else tA = s_tabA + (size_t)D.tips[(long long)aid * D.Ppad + p] * TS;
-            if (ncase >= 1) Bp = D.partial + (long long)bid * D.slot_stride + pb;
-            else tB = s_tabB + (size_t)D.tips[(long long)bid * D.Ppad + p] * TS;
-            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
-            unsigned norm_sc = 0;
-            if (!SAFE) {
-                if (ncase == 2) norm_sc += D.scale[(long long)aid * D.scale_stride + sb];
-                if (ncase >= 1) norm_sc += D.scale[(long long)bid * D.scale_stride + sb];
-            }
-            unsigned mhi = 0;
-            for (int c = 0; c < C; c++) {
-                double a[20], v[20], w[20];
-                // both children's loads are issued before any arithmetic
-                if (Ap) {
-#pragma unroll
-                    for (int i = 0; i < 20; i++) v[i] = Ap[(long long)(c * 20 + i) * kWarp];
-                }
-                if (Bp) {
-#pragma unroll
-                    for (int i = 0; i < 20; i++) w[i] = Bp[(long long)(c * 20 + i) * kWarp];
-                }
-                if (Ap) {
-#pragma unroll
-                    for (int i = 0; i < 20; i++) v[i] *= s_exp[c * 20 + i];
-#pragma unroll
-                    for (int x = 0; x < 20; x++) {
-                        double acc = M.evec[x * 20] * v[0];
-#pragma unroll
-                        for (int i = 1; i < 20; i++) acc = fma(M.evec[x * 20 + i], v[i], acc);
-                        a[x] = acc;
-                    }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 20; x += 2) {
-                        const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + x);
-                        a[x] = t.x; a[x + 1] = t.y;
-                    }
-                }
-                if (Bp) {
-#pragma unroll
-                    for (int i = 0; i < 20; i++) w[i] *= s_exp[B + c * 20 + i];
-#pragma unroll
-                    for (int x = 0; x < 20; x++) {
-                        double acc = M.evec[x * 20] * w[0];
-#pragma unroll
-                        for (int i = 1; i < 20; i++) acc = fma(M.evec[x * 20 + i], w[i], acc);
-                        a[x] *= acc;
-                    }
-                } else {
-#pragma unroll
-                    for (int x = 0; x < 20; x += 2) {
-                        const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + x);
-                        a[x] *= t.x; a[x + 1] *= t.y;
-                    }
-                }
-                // back-transform; values are stored unscaled, the (rare) rescale re-reads what this thread has just written
-                unsigned chi = 0;
-#pragma unroll
-                for (int i = 0; i < 20; i++) {
-                    double acc = M.inv[i * 20] * a[0];
-#pragma unroll
-                    for (int x = 1; x < 20; x++) acc = fma(M.inv[i * 20 + x], a[x], acc);
-                    Op[(long long)(c * 20 + i) * kWarp] = acc;
-                    chi = max(chi, abs_hi(acc));
-                }
-                if (SAFE) {
-                    unsigned sc = 0;
-                    if (ncase == 2) sc += D.scale[(long long)aid * D.scale_stride + sb + c * kWarp];
-                    if (ncase >= 1) sc += D.scale[(long long)bid * D.scale_stride + sb + c * kWarp];
-                    if (ncase != 0 && may_scale && chi < kThresholdHi) {
-                        for (int i = 0; i < 20; i++) Op[(long long)(c * 20 + i) * kWarp] *= kTwo256;
-                        sc += 1;
-                    }
-                    D.scale[(long long)dst * D.scale_stride + sb + c * kWarp] = (uint16_t)sc;
-                } else mhi = max(mhi, chi);
-            }
-            if (!SAFE) {
-                if (ncase != 0 && may_scale && mhi < kThresholdHi) {
-                    for (int k = 0; k < B; k++) Op[(long long)k * kWarp] *= kTwo256;
-                    norm_sc += 1;
-                }
-                D.scale[(long long)dst * D.scale_stride + sb] = (uint16_t)norm_sc;
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------------------------------------------------
-// 20-state walker on the FP64 MMA path (mma.sync.m8n8k4.f64, DMMA).
+// The FP64 MMA walker (mma.sync.m8n8k4.f64, DMMA).
 //
 // Why MMA although DMMA and DFMA share ONE FP64 pipe on B200 with the same peak (scripts/fp64_mix.cu: 36.3 / 37.1 TFLOP/s
-// alone, 36 TFLOP/s in any mix): with DFMA every FMA needs one matrix element delivered from the constant bank (k_walk_n20:
-// LDCU per 2 DFMAs; the compiler's invariant-code motion also turns the 800 constants into spills), while the MMA form keeps
-// evec and inv_evec RESIDENT IN REGISTERS as B fragments (2 x 15 doubles per lane) for the whole kernel, issues 45 DMMAs
-// instead of 1200 DFMAs + 600 constant loads per pattern-tile and category, and leaves the issue slots to the loads/stores.
-// Cost: the output-state dimension 20 is padded to three 8-wide tiles (24), so at most 20/24 = 83 % of the pipe's peak is
-// useful work.
+// alone, 36 TFLOP/s in any mix): with DFMA every FMA needs one matrix element delivered from the constant bank or shared
+// memory, while the MMA form keeps evec and inv_evec RESIDENT IN REGISTERS as B fragments (2 x 15 doubles per lane) for the
+// whole kernel and issues 45 DMMAs instead of 1200 DFMAs + 600 operand loads per 8 patterns and category.  Cost: the
+// output-state dimension 20 is padded to three 8-wide tiles (24), so at most 20/24 = 83 % of the pipe's peak is useful.
 //
 // Mapping (PTX ISA fragment layouts, g = lane/4, q = lane%4): M = 8 patterns (row g), K = 4 eigen-indices, N = 8 states.
-//   child pass   a[p][x]  = sum_i (exp_ci * L[p][c][i]) * evec[x][i]   A = scaled CLV (row p=g, col i=4kt+q: one coalesced
-//                                                                      8-byte load per k-tile), B[k=i][n=x] = evec[x][i]
+//   child pass   a[p][x]  = sum_i (exp_ci * L[p][c][i]) * evec[x][i]   A = scaled CLV, B[k=i][n=x] = evec[x][i]
 //   product      t = a (.) b on the C fragments (p = g, x = 8nt + 2q + {0,1})
-//   re-layout    C fragment -> A fragment inside each 4-lane group: 2 shuffle rounds per state tile
 //   back pass    out[p][i] = sum_x t[p][x] * inv_evec[i][x]           B[k=x][n=i] = inv_evec[i][x]
-// A warp owns 32 consecutive patterns (4 M-tiles); a CTA of 4 warps walks the whole op list for its 128-pattern tile.
+// The MMA's K index may be permuted freely as long as A and B fragments use the same permutation.  That is used twice:
+//   * the product's C fragments ARE the back pass's A fragments (K-slot q of k-tile kt holds x = back_x(kt,q)); only the
+//     half-empty third state tile needs one shuffle;
+//   * CLVs are STORED in C-fragment order (clv20_off below: the "fragment-major" layout) — a lane writes its two
+//     accumulators of a state tile with one 16-byte store, the warp 512 contiguous bytes — and are LOADED back as A fragments
+//     with one 16-byte load per two k-tiles in the permuted K order clv_k(kt,q); evec's B fragments use the same order.
+//     ncu on the previous warp-interleaved layout (8-byte accesses to 4 rows x 64 bytes per instruction) showed the LSU data
+//     pipe, not the FP64 pipe, as the binding unit: 8 wavefronts per LDG/STG, 88 per step, 64 % of the LSU peak with the FP64
+//     pipe stuck at 68 %; the fragment-major layout needs 30.
+// A warp owns 32 consecutive patterns (4 M-tiles); a CTA of NW warps walks the whole op list for its 32*NW-pattern tile.
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// eigen-index (K) order of the back pass: the C fragment of the product (lane (g,q) holds x = 8nt + 2q + j) is fed to the
-// MMA as an A fragment AS IT STANDS — any permutation of K is legal as long as the B fragment uses the same one — so the
-// first four k-tiles need no data movement at all; only the half-empty third state tile (x = 16..19, held by lanes q < 2)
-// is spread over the four lanes with one shuffle.  back_x(kt, q) is the state x in K-slot q of k-tile kt.
+// state x in K-slot q of k-tile kt of the BACK pass (the product's C fragment used as A fragment as it stands; the
+// half-empty third tile, held by lanes q < 2, is spread over the four lanes with one shuffle)
 __host__ __device__ inline int back_x(int kt, int q) {
     return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + (q < 2 ? 2 * q : 2 * (q - 2) + 1);
 }
+// eigen-index i in K-slot q of k-tile kt of the CHILD pass = what the fragment-major layout delivers to lane (g, q)
+__host__ __device__ inline int clv_k(int kt, int q) { return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + q; }
 
-// TAIL variant (k_walk_n20_mma<.., TAIL=true>): states 16..19 are NOT padded to a third 8-wide MMA tile (which wastes 4/24
-// of the pipe) but handled by DFMAs: lane (g,q) forms the partial sums over ITS five K values for the four tail states, then a
-// 3-shuffle reduce-scatter inside the 4-lane group leaves the total for state 16+q in lane q.  The tail matrix elements come
-// from shared memory as s_tail[kt][q][s], slot s <-> state 16 + (s ^ q): the xor order makes the reduce-scatter select-free.
-// In the back pass the product for x = 16+q sits in lane q, so K-slot q of k-tile 4 is x = 16+q and no shuffle is needed.
-__host__ __device__ inline int back_x_tail(int kt, int q) { return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + q; }
-constexpr int kTail20 = 5 * 4 * 4;   // doubles per tail matrix
-
-__device__ __forceinline__ double reduce_scatter4(double s0, double s1, double s2, double s3) {
-    const double u0 = s0 + __shfl_xor_sync(0xffffffffu, s1, 1);
-    const double u2 = s2 + __shfl_xor_sync(0xffffffffu, s3, 1);
-    return u0 + __shfl_xor_sync(0xffffffffu, u2, 2);
-}
+template <bool SM>
+struct BFrag20 {   // one B-fragment element of the lane: from the register copy or from shared memory
+    const double (&r)[5][3];
+    const double *s;
+    __device__ __forceinline__ double operator()(int kt, int nt) const {
+        if (SM) return s[(kt * 3 + nt) * kWarp];
+        return r[kt][nt];
+    }
+};
 
 struct Walk20Op {   // per-(op, class block), per-lane addressing state of the MMA walker
-    const double *Aq, *Bq;   // child CLVs: + (c*20 + 4kt)*32 + 8mt            (row offset q, column g folded in)
-    double *Oq;              // destination:   + (c*20 + 8nt + j)*32 + 8mt      (row offset 2q, column g folded in)
+    const double *Aq, *Bq;   // child CLVs, first category of this class block in M-tile 0 of the warp's 32-pattern block
+    double *Oq;              // destination, same position
     const uint16_t *Asc, *Bsc;
     uint16_t *Osc;           // scale_num: NORM [p], SAFE [c*32 + p%32] inside the warp's block (column g folded in)
     unsigned stA, stB;       // tip states of the lane's pattern in the 4 M-tiles, one byte each
     unsigned may_mask;       // bit mt: ptn_invar == 0 (patterns that may be rescaled)
     // mixtures (NORM_LH): the underflow test spans ALL classes of a pattern, the classes are walked one after the other
     int first_class, last_class;   // this block is the first / last class block of its op
-    int class_off;                 // doubles between the op's class-0 block and this one inside a CLV (m*cpb*20*32)
-    int Ctot;                      // categories of the whole CLV (rare rescale path)
-    unsigned *s_mhi;               // per-lane running max exponent word, [4 M-tiles][128 threads] in shared memory
-    const double *tail_e, *tail_i; // TAIL: this lane's rows of the tail matrices in shared memory (+ kt*16 doubles per k-tile)
+    int class_off;                 // doubles between the op's class-0 block and this one inside an M-tile block (m*cpb*160)
+    int Ctot;                      // categories of the whole CLV
+    unsigned *s_mhi;               // per-lane running max exponent word, [4 M-tiles][threads] in shared memory
+    const double *sBe, *sBi;       // BSM: the lane's B-fragment elements in shared memory, [(kt*3 + nt)*32] (lane folded in)
 };
 
-template <bool SAFE, bool MIX, int NCASE, int VAR>
-__device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, const double (&Be)[5][3], const double (&Bi)[5][3],
-                                              const double *s_exp, const double *s_tabA, const double *s_tabB, int q) {
-    constexpr bool TAIL = (VAR & 1) != 0;     // states 16..19 by DFMA + reduce-scatter instead of a padded third MMA tile
-    constexpr bool SPLITK = (VAR & 2) != 0;   // two accumulator sets per output tile (even / odd k-tiles) where a pass has
-                                              // only three dependent DMMA chains: the back pass, and the child pass of a
-                                              // tip-inner node
+// DBG (diagnosis builds only, results are wrong): bit 0 no CLV stores, bit 1 no CLV loads, bit 2 DMMAs replaced by one DFMA
+template <bool SAFE, bool MIX, int NCASE, int BSM, int DBG = 0>
+__device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, const double (&Be_r)[5][3], const double (&Bi_r)[5][3],
+                                              const double *s_exp, const double *s_tabA, const double *s_tabB, int lane) {
+    // BSM bit 0 / bit 1: the evec / inv_evec B fragments are read from shared memory at each use (one conflict-free 8-byte
+    // load per lane and DMMA) instead of living in 30 registers each
+    const BFrag20<(BSM & 1) != 0> Be{Be_r, W.sBe};
+    const BFrag20<(BSM & 2) != 0> Bi{Bi_r, W.sBi};
+    const int g = lane >> 2, q = lane & 3;
+    auto MMA = [](double &d0, double &d1, double a, double b) {
+        if (DBG & 4) { d0 = fma(a, b, d0); d1 += d0; } else dmma_m8n8k4(d0, d1, a, b);
+    };
     const int B = C * 20, TS = tab20_stride(C);   // C = categories of this class block
-    const double *eA = s_exp + q, *eB = s_exp + B + q;
-    // Software pipeline over the 4*C (M-tile, category) steps: the raw CLV fragments of step s+1 are in flight while step s
-    // runs its MMAs.  (Measured alternatives that were slower: a two-step-deep pipeline with two register sets — spills at
-    // the 168-register budget of 3 CTAs/SM — and 4 CTAs/SM at 128 registers.)
-    const int step_c = 20 * kWarp;                       // next category, same M-tile
-    const int step_m = 8 - (C - 1) * 20 * kWarp;         // category 0 of the next M-tile (8 patterns further)
+    const double *eA = s_exp + 2 * q, *eB = s_exp + B + 2 * q;
+    const int lo2 = (q * 8 + g) * 2;               // the lane's pair inside a 64-double state tile
+    const int lot = 128 + g * 4 + 2 * q;           // store position of the tail pair (lanes q < 2)
+    // Software pipeline over the 4*C (M-tile, category) steps — consecutive in memory, 160 doubles each: the raw CLV
+    // fragments of step s+1 are in flight while step s runs its MMAs.
+    const int step_c = kClv20Step;                                // next category, same M-tile
+    const int step_m = (W.Ctot - (C - 1)) * kClv20Step;           // category 0 of this class block in the next M-tile
     double nA[5], nB[5];
     const double *pfA = W.Aq, *pfB = W.Bq;               // fetch cursors
     int pf_c = 0, pf_left = 4 * C;                        // category of the fetch cursor, steps still to fetch
     auto fetch = [&](double (&dA)[5], double (&dB)[5]) {
         if (pf_left > 0) {
-            if (NCASE == 2) {
+            if (DBG & 2) {
 #pragma unroll
-                for (int kt = 0; kt < 5; kt++) dA[kt] = pfA[kt * 4 * kWarp];
+                for (int k = 0; k < 5; k++) { dA[k] = 1.0 + pf_left; dB[k] = 2.0 + pf_left; }
+            } else {
+            if (NCASE == 2) {
+                const double2 v0 = *reinterpret_cast<const double2 *>(pfA + lo2);
+                const double2 v1 = *reinterpret_cast<const double2 *>(pfA + 64 + lo2);
+                dA[0] = v0.x; dA[1] = v0.y; dA[2] = v1.x; dA[3] = v1.y;
+                dA[4] = pfA[128 + lane];
             }
             if (NCASE >= 1) {
-#pragma unroll
-                for (int kt = 0; kt < 5; kt++) dB[kt] = pfB[kt * 4 * kWarp];
+                const double2 v0 = *reinterpret_cast<const double2 *>(pfB + lo2);
+                const double2 v1 = *reinterpret_cast<const double2 *>(pfB + 64 + lo2);
+                dB[0] = v0.x; dB[1] = v0.y; dB[2] = v1.x; dB[3] = v1.y;
+                dB[4] = pfB[128 + lane];
+            }
             }
             const int adv = pf_c + 1 < C ? step_c : step_m;
             pfA += adv; pfB += adv;
@@ -958,137 +873,76 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
         if (c == 0) {   // a new M-tile (8 patterns)
             tA = s_tabA + (size_t)((W.stA >> (8 * mt)) & 0xffu) * TS + 2 * q;
             tB = s_tabB + (size_t)((W.stB >> (8 * mt)) & 0xffu) * TS + 2 * q;
-            pO = W.Oq + 8 * mt;
+            pO = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
             mhi = 0;
             if (!SAFE) {   // children's scale counts: loaded here, first used after the last category
                 if (NCASE == 2) scA = W.Asc[8 * mt];
                 if (NCASE >= 1) scB = W.Bsc[8 * mt];
             }
         }
+        // exp(eval_i r_c t) for the lane's five K-slots (clv_k order): two 16-byte and one 8-byte shared-memory load per child
         double fA[5], fB[5];
         if (NCASE == 2) {
-#pragma unroll
-            for (int kt = 0; kt < 5; kt++) fA[kt] = nA[kt] * eA[c * 20 + 4 * kt];
+            const double2 e0 = *reinterpret_cast<const double2 *>(eA + c * 20), e1 = *reinterpret_cast<const double2 *>(eA + c * 20 + 8);
+            fA[0] = nA[0] * e0.x; fA[1] = nA[1] * e0.y; fA[2] = nA[2] * e1.x; fA[3] = nA[3] * e1.y;
+            fA[4] = nA[4] * eA[c * 20 + 16 - q];    // eA carries +2q: element 16 + q
         }
         if (NCASE >= 1) {
-#pragma unroll
-            for (int kt = 0; kt < 5; kt++) fB[kt] = nB[kt] * eB[c * 20 + 4 * kt];
+            const double2 e0 = *reinterpret_cast<const double2 *>(eB + c * 20), e1 = *reinterpret_cast<const double2 *>(eB + c * 20 + 8);
+            fB[0] = nB[0] * e0.x; fB[1] = nB[1] * e0.y; fB[2] = nB[2] * e1.x; fB[3] = nB[3] * e1.y;
+            fB[4] = nB[4] * eB[c * 20 + 16 - q];
         }
         fetch(nA, nB);   // step s+1
-        constexpr int NTM = TAIL ? 2 : 3;   // state tiles on the MMA path
         double a[3][2], b[3][2];
-        double at = 0.0, bt = 0.0;          // TAIL: child values for state 16+q
         if (NCASE == 2) {
 #pragma unroll
-            for (int nt = 0; nt < NTM; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
+            for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
         } else {
 #pragma unroll
-            for (int nt = 0; nt < NTM; nt++) {
+            for (int nt = 0; nt < 3; nt++) {
                 const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt);   // nt = 2, q >= 2: row padding
                 a[nt][0] = t.x; a[nt][1] = t.y;
             }
-            if (TAIL) at = tA[c * 20 + 16 - q];   // tA carries +2q
         }
         if (NCASE >= 1) {
 #pragma unroll
-            for (int nt = 0; nt < NTM; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
+            for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
         } else {
 #pragma unroll
-            for (int nt = 0; nt < NTM; nt++) {
+            for (int nt = 0; nt < 3; nt++) {
                 const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt);
                 b[nt][0] = t.x; b[nt][1] = t.y;
             }
-            if (TAIL) bt = tB[c * 20 + 16 - q];
         }
         // child passes; the two children's accumulator chains are independent and interleaved
-        double sA[4], sB[4];
-        if (TAIL && NCASE >= 1) {
-#pragma unroll
-            for (int j = 0; j < 4; j++) { sA[j] = 0.0; sB[j] = 0.0; }
-        }
-        double b2[3][2];   // SPLITK, tip-inner: odd k-tiles of the single child pass
-        if (SPLITK && NCASE == 1) {
-#pragma unroll
-            for (int nt = 0; nt < NTM; nt++) { b2[nt][0] = 0.0; b2[nt][1] = 0.0; }
-        }
 #pragma unroll
         for (int kt = 0; kt < 5; kt++) {
 #pragma unroll
-            for (int nt = 0; nt < NTM; nt++) {
-                if (NCASE == 2) dmma_m8n8k4(a[nt][0], a[nt][1], fA[kt], Be[kt][nt]);
-                if (NCASE >= 1) {
-                    if (SPLITK && NCASE == 1 && (kt & 1)) dmma_m8n8k4(b2[nt][0], b2[nt][1], fB[kt], Be[kt][nt]);
-                    else dmma_m8n8k4(b[nt][0], b[nt][1], fB[kt], Be[kt][nt]);
-                }
-            }
-            if (TAIL && NCASE >= 1) {
-                const double2 e01 = *reinterpret_cast<const double2 *>(W.tail_e + kt * 16);
-                const double2 e23 = *reinterpret_cast<const double2 *>(W.tail_e + kt * 16 + 2);
-                if (NCASE == 2) {
-                    sA[0] = fma(fA[kt], e01.x, sA[0]); sA[1] = fma(fA[kt], e01.y, sA[1]);
-                    sA[2] = fma(fA[kt], e23.x, sA[2]); sA[3] = fma(fA[kt], e23.y, sA[3]);
-                }
-                sB[0] = fma(fB[kt], e01.x, sB[0]); sB[1] = fma(fB[kt], e01.y, sB[1]);
-                sB[2] = fma(fB[kt], e23.x, sB[2]); sB[3] = fma(fB[kt], e23.y, sB[3]);
+            for (int nt = 0; nt < 3; nt++) {
+                if (NCASE == 2) MMA(a[nt][0], a[nt][1], fA[kt], Be(kt, nt));
+                if (NCASE >= 1) MMA(b[nt][0], b[nt][1], fB[kt], Be(kt, nt));
             }
         }
-        if (SPLITK && NCASE == 1) {
-#pragma unroll
-            for (int nt = 0; nt < NTM; nt++) { b[nt][0] += b2[nt][0]; b[nt][1] += b2[nt][1]; }
-        }
-        if (TAIL) {
-            if (NCASE == 2) at = reduce_scatter4(sA[0], sA[1], sA[2], sA[3]);
-            if (NCASE >= 1) bt = reduce_scatter4(sB[0], sB[1], sB[2], sB[3]);
-        }
-        // product on the C fragments = A fragments of the back pass (see back_x / back_x_tail)
+        // product on the C fragments = A fragments of the back pass (see back_x)
         double ft[5];
         ft[0] = a[0][0] * b[0][0]; ft[1] = a[0][1] * b[0][1];
         ft[2] = a[1][0] * b[1][0]; ft[3] = a[1][1] * b[1][1];
-        if (TAIL) ft[4] = at * bt;
-        else {
+        {
             const double t0 = a[2][0] * b[2][0], t1 = a[2][1] * b[2][1];
-            const double r = __shfl_sync(0xffffffffu, t1, (threadIdx.x & 28) | (q & 1));
+            const double r = __shfl_sync(0xffffffffu, t1, (lane & 28) | (q & 1));
             ft[4] = q < 2 ? t0 : r;
         }
         double out[3][2];
-        double ot = 0.0;                    // TAIL: out[p][16+q]
 #pragma unroll
-        for (int nt = 0; nt < NTM; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
-        if (TAIL) {
-            double so[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
 #pragma unroll
-            for (int kt = 0; kt < 5; kt++) {
+        for (int kt = 0; kt < 5; kt++)
 #pragma unroll
-                for (int nt = 0; nt < NTM; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
-                const double2 i01 = *reinterpret_cast<const double2 *>(W.tail_i + kt * 16);
-                const double2 i23 = *reinterpret_cast<const double2 *>(W.tail_i + kt * 16 + 2);
-                so[0] = fma(ft[kt], i01.x, so[0]); so[1] = fma(ft[kt], i01.y, so[1]);
-                so[2] = fma(ft[kt], i23.x, so[2]); so[3] = fma(ft[kt], i23.y, so[3]);
-            }
-            ot = reduce_scatter4(so[0], so[1], so[2], so[3]);
-        } else if (SPLITK) {
-            double o2[3][2];
+            for (int nt = 0; nt < 3; nt++) MMA(out[nt][0], out[nt][1], ft[kt], Bi(kt, nt));
+        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
+        unsigned chi = 0u;
 #pragma unroll
-            for (int nt = 0; nt < 3; nt++) { o2[nt][0] = 0.0; o2[nt][1] = 0.0; }
-#pragma unroll
-            for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-                for (int nt = 0; nt < 3; nt++) {
-                    if (kt & 1) dmma_m8n8k4(o2[nt][0], o2[nt][1], ft[kt], Bi[kt][nt]);
-                    else dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
-                }
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) { out[nt][0] += o2[nt][0]; out[nt][1] += o2[nt][1]; }
-        } else {
-#pragma unroll
-            for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-                for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(out[nt][0], out[nt][1], ft[kt], Bi[kt][nt]);
-        }
-        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros (TAIL: i = 16+q in ot)
-        unsigned chi = TAIL ? abs_hi(ot) : 0u;
-#pragma unroll
-        for (int nt = 0; nt < NTM; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
+        for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
         if (SAFE) {
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
@@ -1097,27 +951,23 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
             if (NCASE >= 1) sc += W.Bsc[c * kWarp + 8 * mt];
             if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && chi < kThresholdHi) {
 #pragma unroll
-                for (int nt = 0; nt < NTM; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
-                ot *= kTwo256;
+                for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
                 sc += 1;
             }
             if (q == 0) W.Osc[c * kWarp + 8 * mt] = (uint16_t)sc;
         } else mhi = max(mhi, chi);   // the pattern's other three lanes are folded in once per M-tile
-        double *po = pO + c * 20 * kWarp;
-#pragma unroll
-        for (int nt = 0; nt < NTM; nt++) {
-            if (nt < 2 || q < 2) {
-                po[(8 * nt) * kWarp] = out[nt][0];
-                po[(8 * nt + 1) * kWarp] = out[nt][1];
-            }
+        double *po = pO + c * kClv20Step;
+        if (!(DBG & 1) || out[0][0] == 1.2345e-300) {
+        *reinterpret_cast<double2 *>(po + lo2) = make_double2(out[0][0], out[0][1]);
+        *reinterpret_cast<double2 *>(po + 64 + lo2) = make_double2(out[1][0], out[1][1]);
+        if (q < 2) *reinterpret_cast<double2 *>(po + lot) = make_double2(out[2][0], out[2][1]);
         }
-        if (TAIL) po[(16 - q) * kWarp] = ot;   // pO carries +2q rows: row 16+q
         if (++c == C) {   // last category of this M-tile
             if (!SAFE) {
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
                 if (MIX) {   // fold in the classes walked before this one (each lane owns its slot: no synchronisation)
-                    unsigned *slot = W.s_mhi + mt * kTile + threadIdx.x;
+                    unsigned *slot = W.s_mhi + mt * blockDim.x + threadIdx.x;
                     if (!W.first_class) mhi = max(mhi, *slot);
                     if (!W.last_class) *slot = mhi;
                 }
@@ -1125,13 +975,17 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
                     unsigned norm_sc = scA + scB;
                     if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has written
                         double *pAll = pO - W.class_off;
-                        for (int cc = 0; cc < W.Ctot; cc++) {
-                            for (int nt = 0; nt < NTM; nt++)
-                                if (nt < 2 || q < 2) {
-                                    pAll[(cc * 20 + 8 * nt) * kWarp] *= kTwo256;
-                                    pAll[(cc * 20 + 8 * nt + 1) * kWarp] *= kTwo256;
-                                }
-                            if (TAIL) pAll[(cc * 20 + 16 - q) * kWarp] *= kTwo256;
+                        for (int cc = 0; cc < W.Ctot; cc++, pAll += kClv20Step) {
+                            double2 *p0 = reinterpret_cast<double2 *>(pAll + lo2), *p1 = reinterpret_cast<double2 *>(pAll + 64 + lo2);
+                            double2 v0 = *p0, v1 = *p1;
+                            v0.x *= kTwo256; v0.y *= kTwo256; v1.x *= kTwo256; v1.y *= kTwo256;
+                            *p0 = v0; *p1 = v1;
+                            if (q < 2) {
+                                double2 *p2 = reinterpret_cast<double2 *>(pAll + lot);
+                                double2 v2 = *p2;
+                                v2.x *= kTwo256; v2.y *= kTwo256;
+                                *p2 = v2;
+                            }
                         }
                         norm_sc += 1;
                     }
@@ -1152,65 +1006,82 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // copy the parts of one op's staging block that the op needs (header + exp always, tabA for a tip child A, tabB when both
 // children are tips) into shared memory, asynchronously
-__device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, int tid) {
+__device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, int tid, int nthreads) {
     const int n_always = (4 + 2 * B) / 2;                                   // 16-byte chunks
     const int n_total = n_always + (ncase <= 1 ? tab_doubles / 2 : 0) * (ncase == 0 ? 2 : 1);
-    for (int k = tid; k < n_total; k += kTile) cp_async16(sdst + 2 * k, gsrc + 2 * k);
+    for (int k = tid; k < n_total; k += nthreads) cp_async16(sdst + 2 * k, gsrc + 2 * k);
 }
 
-template <bool SAFE, bool MIX, int VAR>
-__global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter) {
+// NW  warps per CTA (tile = 32*NW patterns; the two staging buffers are per CTA, so larger CTAs leave room for more warps);
+// BSM the evec (bit 0) / inv_evec (bit 1) B fragments come from shared memory (7.7 KB per CTA) instead of 2 x 30 registers;
+// MINB minimum resident CTAs per SM (register cap).  Warps whose 32 patterns lie beyond Ppad (a multiple of 128, not of
+// 32*NW) idle through the barriers.
+template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0>
+__global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter,
+                                                                 int ntiles) {
+    constexpr int NT = NW * 32;
     // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
     // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
     extern __shared__ __align__(16) double s_dyn20[];
     __shared__ long long s_item;
-    __shared__ unsigned s_mhi[MIX ? 4 * kTile : 1];
-    constexpr bool TAIL = (VAR & 1) != 0;
-    __shared__ __align__(16) double s_tail[TAIL ? (MIX ? 2 : 1) * 2 * kTail20 : 2];   // [buffer][evec | inv_evec][kt][q][slot]
+    __shared__ unsigned s_mhi[MIX ? 4 * NT : 1];
+    __shared__ __align__(16) double s_B[BSM ? (MIX ? 2 : 1) * 960 : 2];   // [buffer][evec | inv_evec][kt][nt][lane]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int nblk = MIX ? D.nmix : 1, cpb = D.C / nblk;   // class blocks per op, categories per block
-    const int Btot = D.C * 20, B = cpb * 20, rows = D.su + 1, TS = tab20_stride(cpb);
+    const int B = cpb * 20, rows = D.su + 1, TS = tab20_stride(cpb);
     const size_t stage_sz = stage20_doubles(cpb, D.su);
     const int tab_doubles = rows * TS;
     const int nvo = nops * nblk;                            // "virtual ops": (op, class block) pairs, class-minor
     // the model's matrices as B fragments: resident for the whole kernel (single class) or reloaded per class block
     double Be[5][3], Bi[5][3];
-    auto load_frags = [&](int m) {
+    auto load_frags = [&](int m) {   // register copies (only the matrices not served from shared memory)
         const double *ev = D.evec + (size_t)m * 400, *iv = D.inv_evec + (size_t)m * 400;
 #pragma unroll
         for (int kt = 0; kt < 5; kt++)
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
                 const int n = 8 * nt + g;
-                Be[kt][nt] = n < 20 ? ev[n * 20 + 4 * kt + q] : 0.0;            // B[k = i][n = x] = evec[x][i]
-                Bi[kt][nt] = n < 20 ? iv[n * 20 + (TAIL ? back_x_tail(kt, q) : back_x(kt, q))] : 0.0;   // B[k = x][n = i] = inv_evec[i][x]
+                if (!(BSM & 1)) Be[kt][nt] = n < 20 ? ev[n * 20 + clv_k(kt, q)] : 0.0;    // B[k = i][n = x] = evec[x][i]
+                if (!(BSM & 2)) Bi[kt][nt] = n < 20 ? iv[n * 20 + back_x(kt, q)] : 0.0;   // B[k = x][n = i] = inv_evec[i][x]
             }
     };
-    auto load_tails = [&](int m, int buf) {   // TAIL: rows 16..19 of evec / inv_evec in the lanes' K order
-        if (tid < kTail20) {
-            const int kt = tid >> 4, qq = (tid >> 2) & 3, sl = tid & 3, x = 16 + (sl ^ qq);
-            s_tail[buf * 2 * kTail20 + tid] = D.evec[(size_t)m * 400 + x * 20 + 4 * kt + qq];
-            s_tail[buf * 2 * kTail20 + kTail20 + tid] = D.inv_evec[(size_t)m * 400 + x * 20 + back_x_tail(kt, qq)];
+    auto load_frags_smem = [&](int m, int buf) {
+        const double *ev = D.evec + (size_t)m * 400, *iv = D.inv_evec + (size_t)m * 400;
+        for (int k = tid; k < 960; k += NT) {
+            const int mat = k / 480, r = k - mat * 480, kt = r / 96, nt = (r >> 5) % 3, ln = r & 31, gg = ln >> 2, qq = ln & 3;
+            const int n = 8 * nt + gg;
+            double v = 0.0;
+            if (n < 20) v = mat == 0 ? ev[n * 20 + clv_k(kt, qq)] : iv[n * 20 + back_x(kt, qq)];
+            s_B[buf * 960 + k] = v;
         }
     };
-    if (!MIX) { load_frags(0); if (TAIL) load_tails(0, 0); }
-    const long long ntiles = D.Ppad / kTile;
+    if (!MIX) { if (BSM != 3) load_frags(0); if (BSM) load_frags_smem(0, 0); }
+    // BALANCED TILES: the Ppad/32 warp blocks are dealt out as `ntiles` tiles of floor or ceil(nblocks/ntiles) <= NW blocks each,
+    // with ntiles a multiple of the resident CTAs (host: enqueue_walk20).  A tile is a whole traversal (milliseconds of work),
+    // so with fixed 32*NW-pattern tiles the last wave leaves SMs idle (config 3: 782 tiles on 444 CTAs = 1.76 waves, SMs 88 %
+    // active); evenly smaller tiles keep every SM busy to the end at the price of a few idle warps per CTA.
+    const long long nblocks = D.Ppad >> 5;
     for (;;) {
         __syncthreads();
         if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
         __syncthreads();
         const long long tile = s_item;
         if (tile >= ntiles) break;
-        const long long p0 = tile * kTile + warp * 32;          // first pattern of this warp (multiple of 32)
-        const long long wbase = (p0 >> 5) * (long long)Btot * kWarp;   // warp-interleaved block of these 32 patterns
+        const long long b0 = tile * nblocks / ntiles, b1 = (tile + 1) * nblocks / ntiles;
+        const long long p0 = (b0 + warp) * 32;                   // first pattern of this warp (multiple of 32)
+        const bool active = b0 + warp < b1;
+        const long long wbase = (p0 >> 5) * (long long)D.B * kWarp;   // the warp's 32-pattern block inside a CLV
         const long long sbase = SAFE ? (p0 >> 5) * (long long)D.C * kWarp : p0;
         unsigned may_mask = 0;
+        if (active) {
 #pragma unroll
-        for (int mt = 0; mt < 4; mt++) if (D.invar[p0 + 8 * mt + g] == 0.0) may_mask |= 1u << mt;
+            for (int mt = 0; mt < 4; mt++) if (D.invar[p0 + 8 * mt + g] == 0.0) may_mask |= 1u << mt;
+        }
         // header of the NEXT block is read one block ahead from global memory, so that issuing its copy and its tip-state
         // loads never waits on memory; its tip states (one byte per pattern and tip child) are fetched during the current block
         auto tip_states = [&](const int4 &hd, unsigned &sA, unsigned &sB) {
             sA = sB = 0;
+            if (!active) return;
             if (hd.y <= 1) {
 #pragma unroll
                 for (int mt = 0; mt < 4; mt++) sA |= (unsigned)D.tips[(long long)hd.z * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
@@ -1221,7 +1092,7 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
             }
         };
         int4 h_next = *reinterpret_cast<const int4 *>(stage);
-        stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid);
+        stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid, NT);
         unsigned stA_next, stB_next;
         tip_states(h_next, stA_next, stB_next);
         int m = 0;
@@ -1230,33 +1101,35 @@ __global__ void __launch_bounds__(kTile, 3) k_walk_n20_mma(Dev D, const double *
             const int4 h = h_next;
             const unsigned stA = stA_next, stB = stB_next;
             if (v + 1 < nvo) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 1) * stage_sz);
-            if (MIX) { load_frags(m); if (TAIL) load_tails(m, v & 1); }
+            if (MIX) { if (BSM != 3) load_frags(m); if (BSM) load_frags_smem(m, v & 1); }
             cp_async_wait_all();
             __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
             if (v + 1 < nvo) {
-                stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid);
+                stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid, NT);
                 if (!MIX || m + 1 == nblk) tip_states(h_next, stA_next, stB_next);   // the tips change with the op, not with the class
             }
-            const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
-            const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
-            const int class_off = m * B * kWarp;
-            Walk20Op W;
-            W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + class_off + q * kWarp + g;   // only dereferenced when internal
-            W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + class_off + q * kWarp + g;
-            W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + class_off + 2 * q * kWarp + g;
-            const int sc_off = SAFE ? m * cpb * kWarp : 0;
-            W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + sc_off + g;
-            W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + sc_off + g;
-            W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + sc_off + g;
-            W.may_mask = may_mask;
-            W.stA = stA; W.stB = stB;
-            W.first_class = m == 0; W.last_class = m + 1 == nblk;
-            W.class_off = class_off; W.Ctot = D.C; W.s_mhi = s_mhi;
-            W.tail_e = s_tail + (MIX ? (v & 1) * 2 * kTail20 : 0) + q * 4;
-            W.tail_i = W.tail_e + kTail20;
-            if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
-            else walk20_mma_op<SAFE, MIX, 0, VAR>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, q);
+            if (active) {
+                const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
+                const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
+                const int class_off = m * cpb * kClv20Step;
+                Walk20Op W;
+                W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + class_off;   // only dereferenced when internal
+                W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + class_off;
+                W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + class_off;
+                const int sc_off = SAFE ? m * cpb * kWarp : 0;
+                W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + sc_off + g;
+                W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + sc_off + g;
+                W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + sc_off + g;
+                W.may_mask = may_mask;
+                W.stA = stA; W.stB = stB;
+                W.first_class = m == 0; W.last_class = m + 1 == nblk;
+                W.class_off = class_off; W.Ctot = D.C; W.s_mhi = s_mhi;
+                W.sBe = s_B + (MIX ? (v & 1) * 960 : 0) + lane;
+                W.sBi = W.sBe + 480;
+                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
+                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
+                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
+            }
             if (MIX && ++m == nblk) m = 0;
         }
     }
@@ -1322,14 +1195,15 @@ template <bool SAFE>
 __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red) {
     const int n = D.n, C = D.C, B = D.B;
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
-    const long long pb = pbase(p, B), cb = pbase(p, C);
+    const long long cb = pbase(p, C);
     const long long sb = SAFE ? cb : p;
-    const double *dad = D.partial + (long long)node_slot * D.slot_stride + pb;       // dad_branch->partial_lh
+    const ClvIdx at(D, p);
+    const double *dad = D.partial + (long long)node_slot * D.slot_stride;       // dad_branch->partial_lh
     const uint16_t *dsc = D.scale + (long long)node_slot * D.scale_stride + sb;
     const double *node = nullptr, *tip = nullptr;
     const uint16_t *nsc = nullptr;
     if (dad_kind == 1) {
-        node = D.partial + (long long)dad_id * D.slot_stride + pb;
+        node = D.partial + (long long)dad_id * D.slot_stride;
         nsc = D.scale + (long long)dad_id * D.scale_stride + sb;
     } else {
         tip = D.tip_lh + (long long)D.tips[(long long)dad_id * D.Ppad + p] * (n * D.nmix);
@@ -1345,16 +1219,16 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
         for (; i + 3 < n; i += 4) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                double f = __ldg(val + i + j) * (node ? node[(long long)(c * n + i + j) * kWarp] : __ldg(tp + i + j));
-                double d = dad[(long long)(c * n + i + j) * kWarp];
+                double f = __ldg(val + i + j) * (node ? node[at(c, i + j)] : __ldg(tp + i + j));
+                double d = dad[at(c, i + j)];
                 if (j == 0) a0 = fma(f, d, a0); else if (j == 1) a1 = fma(f, d, a1);
                 else if (j == 2) a2 = fma(f, d, a2); else a3 = fma(f, d, a3);
             }
         }
         double s = (a0 + a1) + (a2 + a3);
         for (; i < n; i++) {
-            double f = __ldg(val + i) * (node ? node[(long long)(c * n + i) * kWarp] : __ldg(tp + i));
-            s = fma(f, dad[(long long)(c * n + i) * kWarp], s);
+            double f = __ldg(val + i) * (node ? node[at(c, i)] : __ldg(tp + i));
+            s = fma(f, dad[at(c, i)], s);
         }
         if (SAFE) {
             unsigned sc = dsc[c * kWarp] + (nsc ? nsc[c * kWarp] : 0u);
@@ -1404,12 +1278,13 @@ __global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_k
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
     const long long pb = pbase(p, B);
     const long long sb = SAFE ? pbase(p, C) : p;
-    const double *dad = D.partial + (long long)node_slot * D.slot_stride + pb;
+    const ClvIdx at(D, p);
+    const double *dad = D.partial + (long long)node_slot * D.slot_stride;
     const uint16_t *dsc = D.scale + (long long)node_slot * D.scale_stride + sb;
     const double *node = nullptr, *tip = nullptr;
     const uint16_t *nsc = nullptr;
     if (dad_kind == 1) {
-        node = D.partial + (long long)dad_id * D.slot_stride + pb;
+        node = D.partial + (long long)dad_id * D.slot_stride;
         nsc = D.scale + (long long)dad_id * D.scale_stride + sb;
     } else {
         tip = D.tip_lh + (long long)D.tips[(long long)dad_id * D.Ppad + p] * (n * D.nmix);
@@ -1428,8 +1303,8 @@ __global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_k
         }
         const double *tp = tip ? tip + (c / D.denom) * n : nullptr;
         for (int i = 0; i < n; i++) {
-            const long long k = (long long)(c * n + i) * kWarp;
-            double t = (node ? node[k] : __ldg(tp + i)) * dad[k];
+            const long long k = (long long)(c * n + i) * kWarp, kc = at(c, i);
+            double t = (node ? node[kc] : __ldg(tp + i)) * dad[kc];
             if (SAFE) t = zero ? 0.0 : (f != 1.0 ? t * f : t);
             theta[k] = t;
         }
@@ -1512,6 +1387,14 @@ __global__ void k_deinterleave_f64(const double *src, double *dst, long long P, 
     long long p = idx / W;
     int k = (int)(idx - p * W);
     dst[idx] = src[pbase(p, W) + (long long)k * kWarp];
+}
+__global__ void k_deinterleave_clv(Dev D, const double *src, double *dst) {   // one CLV slot -> [p][c*n + i]
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= D.P * D.B) return;
+    long long p = idx / D.B;
+    int k = (int)(idx - p * D.B);
+    const ClvIdx at(D, p);
+    dst[idx] = src[at(k / D.n, k % D.n)];
 }
 __global__ void k_deinterleave_u16(const uint16_t *src, uint16_t *dst, long long P, int W) {
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
