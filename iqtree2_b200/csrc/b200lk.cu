@@ -400,13 +400,23 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * 4);   // 4 resident CTAs per SM (128 regs/thread)
     CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
-    {   // kernel_variant 1 (A/B): one burst of 16 stores at the end of the op instead of per-category stores
+    {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
         const bool safe = e->cfg.safe_numeric != 0;
-        static const void *const kernels[4] = {(const void *)k_walk_n4c4<false, true>, (const void *)k_walk_n4c4<true, true>,
-                                               (const void *)k_walk_n4c4<false, false>, (const void *)k_walk_n4c4<true, false>};
-        const int v = e->kernel_variant == 1 ? 1 : 0;
+        static const void *const kernels[6] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
+                                               (const void *)k_walk_n4c4<false, 2>, (const void *)k_walk_n4c4<true, 2>,
+                                               (const void *)k_walk_n4c4<false, 0>, (const void *)k_walk_n4c4<true, 0>};
+        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : 0;
+#ifdef B200LK_DIAG
+        static const void *const dbg_kernels[3] = {(const void *)k_walk_n4c4<false, 2, 1>, (const void *)k_walk_n4c4<false, 2, 2>,
+                                                   (const void *)k_walk_n4c4<false, 2, 3>};   // variants 6..8: no stores / no loads / neither
+        if (e->kernel_variant >= 6 && e->kernel_variant <= 8) {
+            void *dargs[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
+            CK(cudaLaunchKernel(dbg_kernels[e->kernel_variant - 6], dim3(grid), dim3(kTile), dargs, 0, e->stream));
+            v = -1;
+        }
+#endif
         void *args[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
-        CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, 0, e->stream));
+        if (v >= 0) CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, 0, e->stream));
     }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;

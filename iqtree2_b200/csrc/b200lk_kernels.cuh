@@ -490,7 +490,23 @@ constexpr unsigned kThresholdHi = (1023u - 256u) << 20;   // high word of 2^-256
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-template <bool SAFE, bool ESTORE = true>
+// TMA bulk store helpers (cp.async.bulk shared::cta -> global, bulk async-groups)
+__device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, unsigned bytes) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(sa), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// STORE: 0 = one burst of 16 global stores per thread at the end of the op; 1 = four stores after each category;
+//        2 = the CLV goes to shared memory category by category and leaves the SM as ONE 16 KB TMA bulk store per (tile, op),
+//            issued by one thread after the next op's barrier: no thread ever waits for the LSU to drain its stores (with
+//            direct stores ncu shows the next op's first FP64 instruction stalled on the register hand-over of the burst, and
+//            the kernel's time ~ compute + store time instead of their maximum).  CLV loads then bypass L1 (ld.global.cg): the
+//            bulk store writes through the async proxy, and the slot's lines may sit in this SM's L1 from an earlier read.
+// DBG (diagnosis builds, wrong results): bit 0 no CLV stores, bit 1 no sibling loads
+template <bool SAFE, int STORE = 2, int DBG = 0>
 __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_constant__ Model4 M, const double *stage, int nops,
                                                        unsigned long long *counter) {
     // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
@@ -498,7 +514,12 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
     __shared__ __align__(16) double s_stage[3][kStage4];
     __shared__ double s_tip[kMaxLeafRows4 * 4];
     __shared__ long long s_item;
+    constexpr bool TST = STORE == 2, ESTORE = STORE >= 1;
+    __shared__ __align__(128) double s_out[TST ? 2 : 1][TST ? 16 * kTile : 2];   // [buffer][warp][k][lane] = the tile's 16 KB of a slot
     const int tid = threadIdx.x;
+    const int so = (tid >> 5) * 16 * kWarp + (tid & 31);
+    int prev_dst = -1;
+    long long prev_tile_off = 0;
     for (int k = tid; k < (D.su + 1) * 4; k += kTile) s_tip[k] = D.tip_lh[k];
     const long long ntiles = D.Ppad / kTile;
     constexpr int kStageVec = kStage4 / 2;   // double2 elements per staging block
@@ -531,7 +552,14 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 
         int buf = 0;
         for (int o = 0; o < nops; o++) {
+            if (TST) {
+                // every bulk store issued so far has completed: its buffer may be rewritten, its CLV is visible in L2
+                if (tid == 0) bulk_store_wait_all();
+                fence_proxy_async_smem();   // this thread's shared-memory writes of the previous op, for the async proxy
+            }
             __syncthreads();
+            if (TST && tid == 0 && prev_dst >= 0 && !(DBG & 1))
+                bulk_store_issue(D.partial + (long long)prev_dst * D.slot_stride + prev_tile_off, s_out[(o + 1) & 1], 16 * kTile * sizeof(double));
             const double *st = s_stage[buf];
             const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
             const int4 h0 = *reinterpret_cast<const int4 *>(st);
@@ -547,7 +575,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             if (ncase == 2) {
                 const double *Bp = D.partial + (long long)bid * D.slot_stride + pb;
 #pragma unroll
-                for (int k = 0; k < 16; k++) X[k] = Bp[k * kWarp];
+                for (int k = 0; k < 16; k++) X[k] = (DBG & 2) ? cur[15 - k] + 1e-3 : TST ? __ldcg(Bp + k * kWarp) : Bp[k * kWarp];
 #pragma unroll
                 for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = D.scale[(long long)bid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
             } else {
@@ -560,7 +588,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             } else if (h_loadA) {
                 const double *Ap = D.partial + (long long)aid * D.slot_stride + pb;
 #pragma unroll
-                for (int k = 0; k < 16; k++) cur[k] = Ap[k * kWarp];
+                for (int k = 0; k < 16; k++) cur[k] = TST ? __ldcg(Ap + k * kWarp) : Ap[k * kWarp];
 #pragma unroll
                 for (int c = 0; c < (SAFE ? 4 : 1); c++) cursc[c] = D.scale[(long long)aid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
             }
@@ -574,12 +602,12 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 if (hn.y == 2) {
                     const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) prefetch_l1(Bn + k * kWarp);
+                    for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(Bn + k * kWarp);
                 }
                 if (hn.y >= 1 && n_loadA) {
                     const double *An = D.partial + (long long)hn.z * D.slot_stride + pb;
 #pragma unroll
-                    for (int k = 0; k < 16; k++) prefetch_l1(An + k * kWarp);
+                    for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(An + k * kWarp);
                 }
             }
             const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
@@ -651,7 +679,10 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 // store this category now: the LSU drains four stores per thread while the next category computes, instead
                 // of a burst of 16 at the end of the op that the next op's first FP64 instruction then waits behind (ncu:
                 // 18 % of all stall samples sat on the register hand-over of that burst)
-                if (ESTORE) {
+                if (TST) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s_out[o & 1][so + (c * 4 + i) * kWarp] = cur[c * 4 + i];
+                } else if (ESTORE) {
 #pragma unroll
                     for (int i = 0; i < 4; i++) Op[(c * 4 + i) * kWarp] = cur[c * 4 + i];
                 }
@@ -662,7 +693,10 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
                     for (int k = 0; k < 16; k++) cur[k] *= kTwo256;
                     cursc[0] += 1;
-                    if (ESTORE) {
+                    if (TST) {
+#pragma unroll
+                        for (int k = 0; k < 16; k++) s_out[o & 1][so + k * kWarp] = cur[k];
+                    } else if (ESTORE) {
 #pragma unroll
                         for (int k = 0; k < 16; k++) Op[k * kWarp] = cur[k];
                     }
@@ -677,6 +711,17 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 D.scale[(long long)dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
             if (do_pre) reinterpret_cast<double2 *>(s_stage[buf2])[tid] = pre;
             buf = buf1;
+            prev_dst = dst;
+            prev_tile_off = tile * (16LL * kTile);
+        }
+        if (TST) {   // the tile's last CLV
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0 && prev_dst >= 0 && !(DBG & 1)) {
+                bulk_store_issue(D.partial + (long long)prev_dst * D.slot_stride + prev_tile_off, s_out[(nops + 1) & 1], 16 * kTile * sizeof(double));
+                bulk_store_wait_all();
+            }
+            prev_dst = -1;
         }
     }
 }
