@@ -137,6 +137,20 @@ int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, i
                          int32_t dad_id, double min_len, double guess, double max_len, double tolerance,
                          int32_t max_steps, double *length_out, int32_t *steps_out);
 
+/* ---- asynchronous forms (partition models) ----------------------------------------------------------------------
+ * PhyloSuperTree evaluates its partition trees inside `#pragma omp parallel for` (tree/phylosupertree.cpp:716-723,
+ * tree/phylosupertreeplen.cpp:321-345, 380-409) and sums the scalars.  On the device the partitions are independent engines
+ * on independent streams: the enqueue_* calls queue exactly the work of their synchronous namesakes and return without
+ * waiting; b200lk_finish waits for the engine's stream and hands out what was queued (logL from enqueue_branch_logl /
+ * enqueue_logl_from_buffer, df and ddf from enqueue_branch_derv; a derv call may be queued behind a logL call).  The
+ * synchronous entry points above are enqueue + finish.  NULL output pointers are allowed. */
+int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                               int32_t dad_id, double length, int32_t save_log_value);
+int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                               int32_t dad_id, double length);
+int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length);
+int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf);
+
 /* ---- read-backs (computePatternLikelihood & friends, tree/phylotree.cpp:1458-1603; parity dumps) -------------- */
 int b200lk_get_pattern_lh(b200lk_engine *e, double *out /* [nptn] */);
 int b200lk_get_pattern_scaling(b200lk_engine *e, double *out /* [nptn] */);

@@ -58,6 +58,42 @@ int b200pt_set_plan_only(b200pt_tree *t, int32_t on);
 int b200pt_plan_branch(b200pt_tree *t, int32_t branch, b200lk_op *ops, int32_t cap, int32_t *nops, int32_t *node_slot,
                        int32_t *dad_kind, int32_t *dad_id, double *length);
 
+
+/* ---- edge-linked partition model: PhyloSuperTreePlen (tree/phylosupertreeplen.cpp:243-412, tree/phylosupertree.cpp:697-726) ----
+ * A super tree over `ntaxa` taxa and any number of partition trees (one device engine each, own alignment and model) whose
+ * branch lengths are the super tree's times part_rate.  logL = sum_p logL_p, df = sum_p rate_p df_p, ddf = sum_p rate_p^2 ddf_p.
+ * A taxon without data in a partition is a row of state_unknown.  All partitions are evaluated concurrently (one CUDA stream
+ * per partition, work queued from num_threads host threads; 0 = OpenMP default). */
+typedef struct b200st_tree b200st_tree;
+b200st_tree *b200st_create(int32_t ntaxa, const char *const *names, int32_t num_threads);
+void b200st_destroy(b200st_tree *t);
+const char *b200st_last_error(const b200st_tree *t);
+/* alignment + model of one partition (arguments as b200pt_set_alignment / b200pt_set_pattern_invar / b200pt_set_model);
+ * returns the partition index (>= 0) or -1 */
+int b200st_add_partition(b200st_tree *t, int32_t device, int32_t safe_numeric, int32_t schedule, const uint8_t *states, int64_t nptn,
+                         const double *ptn_freq, const double *ptn_invar, int32_t nstates, int32_t seq_type, int32_t state_unknown,
+                         int32_t ncat, int32_t nmix, int32_t fused_mix_rate, const double *eval, const double *evec,
+                         const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop,
+                         double part_rate);
+int b200st_read_tree(b200st_tree *t, const char *newick);
+int b200st_get_tree(b200st_tree *t, char *out, int64_t cap);
+int b200st_num_partitions(b200st_tree *t);
+int b200st_num_branches(b200st_tree *t);
+int b200st_get_branches(b200st_tree *t, int32_t *node_a, int32_t *node_b, double *lengths);
+int b200st_set_branch_length(b200st_tree *t, int32_t branch, double length, int32_t clear_partials);
+int b200st_set_part_rate(b200st_tree *t, int32_t part, double rate);
+int b200st_clear_all_partial_lh(b200st_tree *t);
+int b200st_compute_likelihood(b200st_tree *t, double *logl);
+int b200st_compute_likelihood_branch(b200st_tree *t, int32_t branch, double *logl);
+/* derivatives of logL with respect to the super branch length, evaluated at `length` (computeFuncDerv with the signs of logL) */
+int b200st_compute_likelihood_derv(b200st_tree *t, int32_t branch, double length, double *df, double *ddf);
+int b200st_optimize_one_branch(b200st_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step);
+int b200st_optimize_all_branches(b200st_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+/* part_info[p].cur_score of the last evaluation */
+int b200st_get_part_scores(b200st_tree *t, double *scores);
+int64_t b200st_launch_count(b200st_tree *t);
+int64_t b200st_device_bytes(b200st_tree *t);
+
 #ifdef __cplusplus
 }
 #endif

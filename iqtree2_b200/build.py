@@ -16,7 +16,7 @@ LIB = os.path.join(PKG, "libb200lk.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-Xcompiler", "-fopenmp",
     "-diag-suppress", "550",
     *(["-DB200LK_DIAG"] if os.environ.get("B200LK_DIAG") else []),
     "-shared",

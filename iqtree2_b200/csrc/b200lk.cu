@@ -61,6 +61,7 @@ struct b200lk_engine {
     float last_ms[5] = {0, 0, 0, 0, 0};
     int last_launch[3] = {0, 0, 0};
     int64_t launches = 0;
+    int pending = 0, pending_marks = 0;   // results queued by b200lk_enqueue_*, collected by b200lk_finish
     std::string err;
 };
 
@@ -684,8 +685,11 @@ static int repair_pattern_lh(b200lk_engine *e, bool save_log, double *logl) {
     return B200LK_WARN_UNDERFLOW;
 }
 
-extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
-                                  int32_t dad_id, double length, int32_t save_log_value, double *logl) {
+// pending results of the enqueue_* entry points (b200lk_finish collects them)
+enum { PEND_LOGL = 1, PEND_DERV = 2, PEND_SAVE_LOG = 4 };
+
+extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                          int32_t dad_id, double length, int32_t save_log_value) {
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
@@ -703,11 +707,45 @@ extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_
     prof_mark(e, 2);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    prof_end(e, 2);
-    *logl = e->h_result[0];
-    if (!std::isfinite(*logl)) return repair_pattern_lh(e, save_log_value != 0, logl);
+    e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);
+    e->pending_marks = 2;
     return 0;
+}
+
+extern "C" int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf) {
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->pending_marks) prof_end(e, e->pending_marks);
+    e->pending_marks = 0;
+    const int pending = e->pending;
+    e->pending = 0;
+    int status = 0;
+    if (pending & PEND_DERV) {
+        double f = e->h_result[1], g = e->h_result[2];
+        if (!std::isfinite(f)) {   // phylokernelnew.h:2629-2632 (the NORM_LH outError at :2577 is the caller's policy)
+            f = g = 0.0;
+            status = B200LK_WARN_DERV_UNDERFLOW;
+        }
+        if (df) *df = f;
+        if (ddf) *ddf = g;
+    }
+    if (pending & PEND_LOGL) {
+        double l = e->h_result[0];
+        if (!std::isfinite(l)) {
+            int rc = repair_pattern_lh(e, (pending & PEND_SAVE_LOG) != 0, &l);
+            if (rc < 0) return rc;
+            status = rc;
+        }
+        if (logl) *logl = l;
+    }
+    return status;
+}
+
+extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                  int32_t dad_id, double length, int32_t save_log_value, double *logl) {
+    int rc = b200lk_enqueue_branch_logl(e, ops, nops, node_slot, dad_kind, dad_id, length, save_log_value);
+    if (rc) return rc;
+    return b200lk_finish(e, logl, nullptr, nullptr);
 }
 
 static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_id) {
@@ -726,41 +764,42 @@ static void enqueue_derv(b200lk_engine *e, double length) {
     if (e->B == 16) k_derv<16><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
     else if (e->B == 80) k_derv<80><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
     else k_derv<0><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    k_final_reduce<2><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
+    k_final_reduce<2><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result + 1);
     e->launches += 3;
     e->last_launch[2] += 3;
 }
 
 extern "C" int b200lk_theta_reset(b200lk_engine *e) { e->theta_computed = false; return 0; }
 
-extern "C" int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
-                                  int32_t dad_id, double length, double *df, double *ddf) {
+extern "C" int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                          int32_t dad_id, double length) {
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
-    prof_begin(e);
+    const bool chained = (e->pending & PEND_LOGL) != 0;   // queued behind a logL call: keep its profiling marks
+    if (!chained) prof_begin(e);
     if (nops > 0) e->theta_computed = false;
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
-    prof_mark(e, 1);
-    prof_mark(e, 2);
+    if (!chained) { prof_mark(e, 1); prof_mark(e, 2); }
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
     enqueue_derv(e, length);
     prof_mark(e, 3);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_result, e->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    prof_end(e, 3);
-    *df = e->h_result[0];
-    *ddf = e->h_result[1];
-    if (!std::isfinite(*df)) {   // phylokernelnew.h:2629-2632 (the NORM_LH outError at :2577 is the caller's policy)
-        *df = *ddf = 0.0;
-        return B200LK_WARN_DERV_UNDERFLOW;
-    }
+    CK(cudaMemcpyAsync(e->h_result + 1, e->d_result + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+    e->pending |= PEND_DERV;
+    e->pending_marks = 3;
     return 0;
 }
 
-extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *logl) {
+extern "C" int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                  int32_t dad_id, double length, double *df, double *ddf) {
+    int rc = b200lk_enqueue_branch_derv(e, ops, nops, node_slot, dad_kind, dad_id, length);
+    if (rc) return rc;
+    return b200lk_finish(e, nullptr, df, ddf);
+}
+
+extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) {
     cudaSetDevice(e->cfg.device);
     if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
     prof_begin(e);
@@ -776,11 +815,15 @@ extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *
     prof_mark(e, 2);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    prof_end(e, 2);
-    *logl = e->h_result[0];
-    if (!std::isfinite(*logl)) return repair_pattern_lh(e, true, logl);
+    e->pending = PEND_LOGL | PEND_SAVE_LOG;
+    e->pending_marks = 2;
     return 0;
+}
+
+extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *logl) {
+    int rc = b200lk_enqueue_logl_from_buffer(e, length);
+    if (rc) return rc;
+    return b200lk_finish(e, logl, nullptr, nullptr);
 }
 
 // Optimization::minimizeNewton (utils/optimization.cpp:422-499) with f = -df, f' = -ddf (computeFuncDerv,
@@ -798,11 +841,11 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     int nsteps = 0;
     auto func_derv = [&](double x, double &f, double &df) -> int {
         enqueue_derv(e, x);
-        cudaError_t ce = cudaMemcpyAsync(e->h_result, e->d_result, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        cudaError_t ce = cudaMemcpyAsync(e->h_result + 1, e->d_result + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
         if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
-        f = -e->h_result[0];
-        df = -e->h_result[1];
+        f = -e->h_result[1];
+        df = -e->h_result[2];
         nsteps++;
         return 0;
     };

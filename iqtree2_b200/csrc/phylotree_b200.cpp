@@ -596,6 +596,45 @@ void PhyloTree::computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad,
     theta_computed = true;
 }
 
+void PhyloTree::enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
+    initializeAllPartialLh();
+    int node_slot, dad_kind, dad_id;
+    const double length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    if (!traversal_info.empty()) theta_computed = false;
+    check(b200lk_enqueue_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
+                                     save_log_value), "enqueue_branch_logl");
+    traversal_info.clear();
+}
+
+void PhyloTree::enqueueLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad) {
+    initializeAllPartialLh();
+    int node_slot, dad_kind, dad_id;
+    const double length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    if (!traversal_info.empty()) theta_computed = false;
+    if (!theta_computed) b200lk_theta_reset(engine_);
+    check(b200lk_enqueue_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length),
+          "enqueue_branch_derv");
+    traversal_info.clear();
+    theta_computed = true;
+}
+
+void PhyloTree::enqueueLikelihoodFromBuffer() {
+    if (!theta_computed || !current_it) throw std::runtime_error("computeLikelihoodFromBuffer: theta_all is not computed");
+    check(b200lk_enqueue_logl_from_buffer(engine_, current_it->length), "enqueue_logl_from_buffer");
+}
+
+void PhyloTree::finish(double *logl, double *df, double *ddf) { check(b200lk_finish(engine_, logl, df, ddf), "finish"); }
+
+PhyloNeighbor *PhyloTree::branchNeighbor(int branch_id, int to_node_id) const {
+    if (branch_id < 0 || branch_id >= (int)branches_.size()) return nullptr;
+    const auto &br = branches_[branch_id];
+    if (br.first->node->id == to_node_id) return br.first;
+    if (br.second->node->id == to_node_id) return br.second;
+    return nullptr;
+}
+
 double PhyloTree::computeLikelihoodFromBuffer() {
     if (!theta_computed || !current_it) throw std::runtime_error("computeLikelihoodFromBuffer: theta_all is not computed");
     double logl = 0.0;
@@ -726,7 +765,7 @@ void PhyloTree::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clear
     current_it_back = node2->findNeighbor(node1);
     const double current_len = current_it->length;
     theta_computed = false;
-    b200lk_theta_reset(engine_);
+    if (engine_) b200lk_theta_reset(engine_);
     double optx;
     if (params.fused_newton) {
         // same iteration, run inside the library on the resident theta buffer

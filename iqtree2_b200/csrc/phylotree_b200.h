@@ -89,7 +89,7 @@ private:
 class PhyloTree {
 public:
     PhyloTree();
-    ~PhyloTree();
+    virtual ~PhyloTree();
     PhyloTree(const PhyloTree &) = delete;
 
     // ---- inputs (what aln / model / site_rate supply in the reference) ----------------------------------------
@@ -105,13 +105,19 @@ public:
     // ---- buffers ------------------------------------------------------------------------------------------------
     void initializeAllPartialLh();    // tree/phylotree.cpp:893-939, 1060-1188 (LM_PER_NODE slot assignment)
     void deleteAllPartialLh();
-    void clearAllPartialLH();         // tree/phylotree.cpp:668-677
+    virtual void clearAllPartialLH();   // tree/phylotree.cpp:668-677
 
     // ---- the likelihood API (tree/phylotree.h:899-1048, 1136, 1340) ----------------------------------------------
     double computeLikelihood(double *pattern_lh = nullptr, bool save_log_value = true);   // tree/phylotree.cpp:1233-1274
-    double computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true);
+    virtual double computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true);
     void computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf);
-    double computeLikelihoodFromBuffer();
+    virtual double computeLikelihoodFromBuffer();
+    // asynchronous forms for partition models (b200lk_enqueue_* / b200lk_finish): same planning and flag updates as the
+    // synchronous members, the device work is only queued on the engine's stream; finish() waits and returns the scalars
+    void enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true);
+    void enqueueLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad);
+    void enqueueLikelihoodFromBuffer();
+    void finish(double *logl, double *df, double *ddf);
     void computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *dad);   // flush the stale partials below one directed branch
     void planBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, std::vector<b200lk_op> &ops, int &node_slot, int &dad_kind,
                     int &dad_id, double &length);
@@ -119,11 +125,11 @@ public:
     void computePatternLhCat(double *pattern_lh_cat);
 
     // ---- branch-length optimisation (tree/phylotree.cpp:2514-2774, utils/optimization.cpp:422-499) ---------------
-    double computeFunction(double value);
-    void computeFuncDerv(double value, double &df, double &ddf);
+    virtual double computeFunction(double value);
+    virtual void computeFuncDerv(double value, double &df, double &ddf);
     double minimizeNewton(double x1, double xguess, double x2, double xacc, double &d2l, int maxNRStep = 100);
-    void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100);
-    double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);
+    virtual void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100);
+    virtual double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);
 
     // ---- tree access ----------------------------------------------------------------------------------------------
     PhyloNode *findNodeName(const std::string &name) const;
@@ -132,8 +138,12 @@ public:
                              PhyloNode *dad = nullptr);                               // tree/mtree.cpp:3062-3082
     void getBranches(std::vector<PhyloNode *> &nodes, std::vector<PhyloNode *> &nodes2) const;   // by branch id
     void saveBranchLengths(std::vector<double> &lenvec) const;
-    void restoreBranchLengths(const std::vector<double> &lenvec);
+    virtual void restoreBranchLengths(const std::vector<double> &lenvec);
+    // the directed neighbour of branch `branch_id` that points TO the node with id `to_node_id` (nullptr if neither end has it)
+    PhyloNeighbor *branchNeighbor(int branch_id, int to_node_id) const;
     int numBranches() const { return (int)branches_.size(); }
+    int64_t getAlnNPattern() const { return nptn_; }
+    int getNumStates() const { return nstates_; }
 
     // diagnostics for parity tests
     int64_t num_partial_lh_computations = 0;   // tree/phylotree.h:2127
@@ -149,7 +159,7 @@ public:
     int max_lh_slots = 0;             // tree/phylotree.h (set by initializeAllPartialLh; T-2 for LM_PER_NODE)
     MemSlotVector mem_slots;
 
-private:
+protected:
     bool computeTraversalInfo(PhyloNeighbor *dad_branch, PhyloNode *dad);   // tree/phylotree.cpp:5918-6028
     void computeTraversalInfo(PhyloNode *node, PhyloNode *dad);             // tree/phylokernelnew.h:1150-1281
     void reorientPartialLh(PhyloNeighbor *dad_branch, PhyloNode *dad);      // tree/phylotree.cpp:5898-5912

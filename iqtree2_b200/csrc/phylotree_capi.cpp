@@ -7,6 +7,7 @@
 
 #include "b200pt.h"
 #include "phylotree_b200.h"
+#include "supertree_b200.h"
 
 struct b200pt_tree {
     b200::PhyloTree tree;
@@ -145,6 +146,127 @@ int b200pt_plan_branch(b200pt_tree *t, int32_t branch, b200lk_op *ops, int32_t c
         std::memcpy(ops, v.data(), v.size() * sizeof(b200lk_op));
         *nops = (int)v.size(); *node_slot = ns; *dad_kind = dk; *dad_id = di;
     })
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// PhyloSuperTreePlen
+// ---------------------------------------------------------------------------------------------------------------
+struct b200st_tree {
+    b200::PhyloSuperTreePlen tree;
+    std::vector<std::string> names;
+    std::string err;
+};
+
+b200st_tree *b200st_create(int32_t ntaxa, const char *const *names, int32_t num_threads) {
+    auto *t = new b200st_tree();
+    try {
+        t->names.assign(names, names + ntaxa);
+        t->tree.setTaxa(t->names);
+        t->tree.num_threads = num_threads;
+    } catch (const std::exception &ex) { g_err = ex.what(); delete t; return nullptr; }
+    return t;
+}
+void b200st_destroy(b200st_tree *t) { delete t; }
+const char *b200st_last_error(const b200st_tree *t) { return t ? t->err.c_str() : g_err.c_str(); }
+
+int b200st_add_partition(b200st_tree *t, int32_t device, int32_t safe_numeric, int32_t schedule, const uint8_t *states, int64_t nptn,
+                         const double *ptn_freq, const double *ptn_invar, int32_t nstates, int32_t seq_type, int32_t state_unknown,
+                         int32_t ncat, int32_t nmix, int32_t fused, const double *eval, const double *evec, const double *inv_evec,
+                         const double *mix_weight, const double *cat_rate, const double *cat_prop, double part_rate) {
+    b200::PhyloTree *p = nullptr;
+    try {
+        p = new b200::PhyloTree();
+        p->params.device = device;
+        p->params.safe_numeric = safe_numeric != 0;
+        p->params.schedule = schedule;
+        p->setAlignment(t->names, states, nptn, ptn_freq, nstates, seq_type, state_unknown);
+        if (ptn_invar) p->setPatternInvar(ptn_invar);
+        p->setModel(ncat, nmix, fused != 0, eval, evec, inv_evec, mix_weight, cat_rate, cat_prop);
+        return t->tree.addPartition(p, part_rate);
+    } catch (const std::exception &ex) { t->err = ex.what(); delete p; return -1; }
+}
+int b200st_read_tree(b200st_tree *t, const char *newick) { GUARD(t->tree.readSuperTree(newick)) }
+int b200st_get_tree(b200st_tree *t, char *out, int64_t cap) {
+    GUARD({
+        std::string s = t->tree.getTreeString();
+        if ((int64_t)s.size() + 1 > cap) throw std::runtime_error("buffer too small");
+        std::memcpy(out, s.c_str(), s.size() + 1);
+    })
+}
+int b200st_num_partitions(b200st_tree *t) { return t->tree.numPartitions(); }
+int b200st_num_branches(b200st_tree *t) { return t->tree.numBranches(); }
+int b200st_get_branches(b200st_tree *t, int32_t *node_a, int32_t *node_b, double *lengths) {
+    GUARD({
+        std::vector<b200::PhyloNode *> a, b;
+        t->tree.getBranches(a, b);
+        std::vector<double> len;
+        t->tree.saveBranchLengths(len);
+        for (size_t k = 0; k < a.size(); k++) { node_a[k] = a[k]->id; node_b[k] = b[k]->id; lengths[k] = len[k]; }
+    })
+}
+static void st_ends(b200st_tree *t, int branch, b200::PhyloNode *&a, b200::PhyloNode *&b) {
+    std::vector<b200::PhyloNode *> na, nb;
+    t->tree.getBranches(na, nb);
+    if (branch < 0 || branch >= (int)na.size()) throw std::runtime_error("branch id out of range");
+    a = na[branch]; b = nb[branch];
+}
+int b200st_set_branch_length(b200st_tree *t, int32_t branch, double length, int32_t clear_partials) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        st_ends(t, branch, a, b);
+        a->findNeighbor(b)->length = length;
+        b->findNeighbor(a)->length = length;
+        for (int p = 0; p < t->tree.numPartitions(); p++) {
+            b200::PhyloTree *pt = t->tree.parts[p];
+            b200::PhyloNeighbor *n1 = pt->branchNeighbor(branch, b->id), *n2 = pt->branchNeighbor(branch, a->id);
+            n1->length = n2->length = length * t->tree.part_rate[p];
+            if (clear_partials) { n2->node->clearReversePartialLh(n1->node); n1->node->clearReversePartialLh(n2->node); pt->theta_computed = false; }
+        }
+    })
+}
+int b200st_set_part_rate(b200st_tree *t, int32_t part, double rate) { GUARD(t->tree.setPartRate(part, rate)) }
+int b200st_clear_all_partial_lh(b200st_tree *t) { GUARD(t->tree.clearAllPartialLH()) }
+int b200st_compute_likelihood(b200st_tree *t, double *logl) { GUARD(*logl = t->tree.computeLikelihood()) }
+int b200st_compute_likelihood_branch(b200st_tree *t, int32_t branch, double *logl) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        st_ends(t, branch, a, b);
+        *logl = t->tree.computeLikelihoodBranch(a->findNeighbor(b), a);
+    })
+}
+int b200st_compute_likelihood_derv(b200st_tree *t, int32_t branch, double length, double *df, double *ddf) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        st_ends(t, branch, a, b);
+        b200::PhyloNeighbor *it = a->findNeighbor(b);
+        if (t->tree.current_it != it)
+            for (auto *p : t->tree.parts) p->theta_computed = false;
+        t->tree.current_it = it;
+        t->tree.current_it_back = b->findNeighbor(a);
+        double f, g;
+        t->tree.computeFuncDerv(length, f, g);
+        *df = -f; *ddf = -g;
+    })
+}
+int b200st_optimize_one_branch(b200st_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step) {
+    GUARD({
+        b200::PhyloNode *a, *b;
+        st_ends(t, branch, a, b);
+        t->tree.optimizeOneBranch(a, b, clear_lh != 0, max_nr_step);
+    })
+}
+int b200st_optimize_all_branches(b200st_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl) {
+    GUARD(*logl = t->tree.optimizeAllBranches(iterations, tolerance, max_nr_step))
+}
+int b200st_get_part_scores(b200st_tree *t, double *scores) {
+    GUARD(for (int p = 0; p < t->tree.numPartitions(); p++) scores[p] = t->tree.cur_score[p])
+}
+int64_t b200st_launch_count(b200st_tree *t) { return t->tree.launches(); }
+int64_t b200st_device_bytes(b200st_tree *t) {
+    int64_t n = 0;
+    for (auto *p : t->tree.parts) if (p->engine()) n += b200lk_device_bytes(p->engine());
+    return n;
 }
 
 }  // extern "C"

@@ -1,0 +1,224 @@
+// supertree_b200.cpp — see supertree_b200.h.  Reference: tree/phylosupertreeplen.cpp, tree/phylosupertree.cpp (IQ-TREE 2.4.0).
+#include "supertree_b200.h"
+
+#include <algorithm>
+#include <cmath>
+#include <exception>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace b200 {
+
+PhyloSuperTreePlen::PhyloSuperTreePlen() {
+    params.plan_only = true;        // the super tree owns no device buffers: topology, linked lengths, flags only
+    params.fused_newton = false;    // Newton-Raphson runs on the host over the summed derivatives (minimizeNewton)
+}
+
+PhyloSuperTreePlen::~PhyloSuperTreePlen() {
+    for (auto *p : parts) delete p;
+}
+
+void PhyloSuperTreePlen::setTaxa(const std::vector<std::string> &names) {
+    // a one-pattern placeholder alignment: the super tree needs the names (leaf ids = alignment rows), never the data
+    std::vector<uint8_t> st(names.size(), 0);
+    const double one = 1.0;
+    setAlignment(names, st.data(), 1, &one, 4, B200LK_SEQ_GENERIC, 4);
+    const double ev[4] = {0, 0, 0, 0}, m[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1}, w = 1.0, r = 1.0, pr = 1.0;
+    setModel(1, 1, false, ev, m, m, &w, &r, &pr);
+}
+
+int PhyloSuperTreePlen::addPartition(PhyloTree *part, double rate) {
+    parts.push_back(part);
+    part_rate.push_back(rate);
+    cur_score.push_back(0.0);
+    part_order.clear();
+    return (int)parts.size() - 1;
+}
+
+void PhyloSuperTreePlen::setPartRate(int part, double rate) {
+    part_rate.at(part) = rate;
+    parts[part]->clearAllPartialLH();
+    mapTrees();
+}
+
+void PhyloSuperTreePlen::readSuperTree(const std::string &newick) {
+    readTreeString(newick);
+    for (auto *p : parts) {
+        p->readTreeString(newick);
+        if (p->numBranches() != numBranches() || p->nodeNum != nodeNum) throw std::runtime_error("partition tree does not match the super tree");
+    }
+    mapTrees();
+}
+
+void PhyloSuperTreePlen::mapTrees() {
+    std::vector<double> len, plen;
+    saveBranchLengths(len);
+    plen.resize(len.size());
+    for (size_t p = 0; p < parts.size(); p++) {
+        for (size_t b = 0; b < len.size(); b++) plen[b] = len[b] * part_rate[p];
+        parts[p]->restoreBranchLengths(plen);
+    }
+}
+
+void PhyloSuperTreePlen::restoreBranchLengths(const std::vector<double> &lenvec) {
+    PhyloTree::restoreBranchLengths(lenvec);
+    mapTrees();
+}
+
+void PhyloSuperTreePlen::clearAllPartialLH() {
+    PhyloTree::clearAllPartialLH();
+    for (auto *p : parts) p->clearAllPartialLH();
+    std::fill(cur_score.begin(), cur_score.end(), 0.0);
+}
+
+// PhyloSuperTree::computePartitionOrder (tree/phylosupertree.cpp:653-695): most expensive partitions first
+void PhyloSuperTreePlen::computePartitionOrder() {
+    if (part_order.size() == parts.size()) return;
+    part_order.resize(parts.size());
+    std::iota(part_order.begin(), part_order.end(), 0);
+    std::vector<double> cost(parts.size());
+    for (size_t p = 0; p < parts.size(); p++) cost[p] = (double)parts[p]->leafNum * (double)parts[p]->getAlnNPattern() * parts[p]->getNumStates();
+    std::stable_sort(part_order.begin(), part_order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+}
+
+// the partition's two directed neighbours of the super tree's current branch: SuperNeighbor::link_neighbors[part]
+void PhyloSuperTreePlen::linkBranch(int part, PhyloNeighbor *&nei1_part, PhyloNeighbor *&nei2_part) const {
+    // nei1 = current_it (at node1, pointing to node2), nei2 = current_it_back (phylosupertreeplen.cpp:318-320)
+    nei1_part = parts[part]->branchNeighbor(current_it->id, current_it->node->id);
+    nei2_part = parts[part]->branchNeighbor(current_it->id, current_it_back->node->id);
+    if (!nei1_part || !nei2_part) throw std::runtime_error("partition tree is not linked to the super tree's branch");
+}
+
+void PhyloSuperTreePlen::setPartLengths(double value) {
+    current_it->length = value;
+    current_it_back->length = value;
+    for (size_t p = 0; p < parts.size(); p++) {
+        PhyloNeighbor *n1, *n2;
+        linkBranch((int)p, n1, n2);
+        // the reference adds lambda * part_rate to the partition branch (:337-338); with linked lengths that is value * rate
+        n1->length = n2->length = value * part_rate[p];
+        parts[p]->current_it = n1;
+        parts[p]->current_it_back = n2;
+    }
+}
+
+namespace {
+// run f(part) for every partition from OpenMP threads (the reference's `omp parallel for schedule(dynamic)` over part_order),
+// carrying the first exception out of the parallel region
+template <class F>
+void for_each_partition(const std::vector<int> &order, int num_threads, F f) {
+    std::exception_ptr err;
+    const int n = (int)order.size();
+#ifdef _OPENMP
+    const int nt = num_threads > 0 ? num_threads : std::min(omp_get_max_threads(), 16);
+#pragma omp parallel for schedule(dynamic) num_threads(nt) if (n > 1 && nt > 1)
+#endif
+    for (int j = 0; j < n; j++) {
+        try { f(order[j]); }
+        catch (...) {
+#ifdef _OPENMP
+#pragma omp critical(b200_supertree_err)
+#endif
+            if (!err) err = std::current_exception();
+        }
+    }
+    (void)num_threads;
+    if (err) std::rethrow_exception(err);
+}
+}  // namespace
+
+double PhyloSuperTreePlen::computeFunction(double value) {
+    computePartitionOrder();
+    setPartLengths(value);
+    for_each_partition(part_order, num_threads, [&](int p) {
+        parts[p]->enqueueLikelihoodBranch(parts[p]->current_it_back, parts[p]->current_it->node);   // (nei2_part, nei1_part->node), :339
+    });
+    double tree_lh = 0.0;
+    for (size_t p = 0; p < parts.size(); p++) {   // summed in partition order: reproducible whatever the thread count
+        parts[p]->finish(&cur_score[p], nullptr, nullptr);
+        tree_lh += cur_score[p];
+    }
+    return -tree_lh;
+}
+
+double PhyloSuperTreePlen::computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool) {
+    current_it = dad_branch;
+    current_it_back = dad_branch->node->findNeighbor(dad);
+    return -computeFunction(dad_branch->length);
+}
+
+double PhyloSuperTreePlen::computeLikelihood() {
+    if (!current_it) {
+        PhyloNode *leaf = findFarthestLeaf();
+        current_it = leaf->neighbors[0];
+        current_it_back = current_it->node->findNeighbor(leaf);
+    }
+    curScore = computeLikelihoodBranch(current_it, current_it_back->node);
+    return curScore;
+}
+
+double PhyloSuperTreePlen::computeLikelihoodFromBuffer() {
+    double score = 0.0;
+    for (double s : cur_score) score += s;
+    return score;
+}
+
+void PhyloSuperTreePlen::computeFuncDerv(double value, double &df_ret, double &ddf_ret) {
+    computePartitionOrder();
+    setPartLengths(value);
+    for_each_partition(part_order, num_threads, [&](int p) {
+        parts[p]->enqueueLikelihoodDerv(parts[p]->current_it_back, parts[p]->current_it->node);   // :397
+    });
+    double df = 0.0, ddf = 0.0;
+    for (size_t p = 0; p < parts.size(); p++) {
+        double df_aux = 0.0, ddf_aux = 0.0;
+        parts[p]->finish(nullptr, &df_aux, &ddf_aux);
+        df += part_rate[p] * df_aux;                     // :398-399
+        ddf += part_rate[p] * part_rate[p] * ddf_aux;
+    }
+    df_ret = -df;
+    ddf_ret = -ddf;
+}
+
+void PhyloSuperTreePlen::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH, int maxNRStep) {
+    current_it = node1->findNeighbor(node2);
+    current_it_back = node2->findNeighbor(node1);
+    const double current_len = current_it->length;
+    for (auto *p : parts) {   // :271-273
+        p->theta_computed = false;
+        if (p->engine()) b200lk_theta_reset(p->engine());
+    }
+    PhyloTree::optimizeOneBranch(node1, node2, false, maxNRStep);   // :276
+    // minimizeNewton may return the point BEFORE the last one it evaluated; bring the partition branches to the final length
+    // (the reference leaves them at the last evaluated point, a drift below the Newton tolerance)
+    setPartLengths(current_it->length);
+    computePartitionOrder();
+    for_each_partition(part_order, num_threads, [&](int p) { parts[p]->enqueueLikelihoodFromBuffer(); });   // :283-290
+    for (size_t p = 0; p < parts.size(); p++) parts[p]->finish(&cur_score[p], nullptr, nullptr);
+    if (clearLH && current_len != current_it->length) {   // :292-302
+        for (size_t p = 0; p < parts.size(); p++) {
+            PhyloNeighbor *n1, *n2;
+            linkBranch((int)p, n1, n2);
+            n1->node->clearReversePartialLh(n2->node);
+            n2->node->clearReversePartialLh(n1->node);
+        }
+    }
+}
+
+double PhyloSuperTreePlen::optimizeAllBranches(int my_iterations, double tolerance, int maxNRStep) {
+    std::fill(cur_score.begin(), cur_score.end(), 0.0);   // :246-248
+    return PhyloTree::optimizeAllBranches(my_iterations, tolerance, maxNRStep);
+}
+
+int64_t PhyloSuperTreePlen::launches() const {
+    int64_t n = 0;
+    for (auto *p : parts) if (p->engine()) n += b200lk_launch_count(p->engine());
+    return n;
+}
+
+}  // namespace b200

@@ -1,0 +1,64 @@
+// supertree_b200.h — host-side mirror of the reference's edge-linked partition model, PhyloSuperTreePlen
+// (tree/phylosupertreeplen.h, tree/phylosupertreeplen.cpp:243-412; PhyloSuperTree::computeLikelihood,
+// tree/phylosupertree.cpp:697-726), over per-partition b200::PhyloTree objects = per-partition device engines.
+//
+// Like the reference's class it IS a PhyloTree: the super tree carries the topology and the linked branch lengths and inherits
+// optimizeOneBranch / optimizeAllBranches / minimizeNewton unchanged; what it overrides is where the numbers come from —
+// computeFunction / computeFuncDerv / computeLikelihoodBranch / computeLikelihoodFromBuffer sum over the partition trees:
+//     logL = sum_p logL_p,     df = sum_p rate_p df_p,     ddf = sum_p rate_p^2 ddf_p        (phylosupertreeplen.cpp:307-412)
+// with every partition branch at length super_length * part_rate.  Where the reference fans the partitions out over OpenMP
+// threads that each block in their partition's kernel, here every partition's work is QUEUED on its own CUDA stream
+// (b200lk_enqueue_*), from OpenMP threads as well, and collected with one b200lk_finish per partition: the GPU sees hundreds
+// of small independent traversals at once instead of one at a time.
+//
+// Scope of this mirror: every partition tree has the super tree's topology over the full taxon set; a taxon without data in a
+// partition is a row of STATE_UNKNOWN there (mathematically the likelihood of the reference's induced subtree, whose merged
+// branches have the summed lengths: an all-gap leaf contributes the factor 1).  SuperNeighbor::link_neighbors therefore is the
+// identity on branch ids, and `if (nei1_part && nei2_part)` is always true.
+#pragma once
+#include <vector>
+
+#include "phylotree_b200.h"
+
+namespace b200 {
+
+class PhyloSuperTreePlen : public PhyloTree {
+public:
+    PhyloSuperTreePlen();
+    ~PhyloSuperTreePlen() override;
+
+    // partition tree with alignment and model already set (same taxon names, same order as the super tree); takes ownership
+    int addPartition(PhyloTree *part, double part_rate);
+    // the super tree's taxa (alignment-row order); must precede readSuperTree
+    void setTaxa(const std::vector<std::string> &names);
+    // reads the topology into the super tree and every partition tree, then mapTrees()
+    void readSuperTree(const std::string &newick);
+    // partition branch lengths := super branch lengths * part_rate (PhyloSuperTreePlen::mapTrees, phylosupertreeplen.cpp:119-160)
+    void mapTrees();
+    void setPartRate(int part, double rate);
+
+    double computeLikelihood();                                                                  // phylosupertree.cpp:697-726
+    double computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true) override;   // plen.cpp:355-359
+    double computeLikelihoodFromBuffer() override;                                               // plen.cpp:361-370
+    double computeFunction(double value) override;                                               // plen.cpp:307-353
+    void computeFuncDerv(double value, double &df, double &ddf) override;                        // plen.cpp:372-412
+    void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100) override;   // plen.cpp:253-305
+    double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100) override;   // plen.cpp:243-251
+    void clearAllPartialLH() override;
+    void restoreBranchLengths(const std::vector<double> &lenvec) override;
+
+    int numPartitions() const { return (int)parts.size(); }
+    std::vector<PhyloTree *> parts;
+    std::vector<double> part_rate;
+    std::vector<double> cur_score;   // part_info[part].cur_score
+    int num_threads = 0;             // host threads that queue partition work (0 = OpenMP default)
+    int64_t launches() const;        // kernel launches of all partition engines
+
+private:
+    void linkBranch(int part, PhyloNeighbor *&nei1_part, PhyloNeighbor *&nei2_part) const;
+    void setPartLengths(double value);
+    std::vector<int> part_order;     // PhyloSuperTree::computePartitionOrder: decreasing cost
+    void computePartitionOrder();
+};
+
+}  // namespace b200

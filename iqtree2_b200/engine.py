@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "b200lk_get_theta", "b200lk_get_buffer_scale_all", "b200lk_get_scale_num", "b200lk_get_partial",
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
+    "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2

@@ -1,0 +1,17 @@
+#!/bin/bash
+# session 8 evidence: traffic at full size, launch lists, full captures of both walkers, bench lines
+O=gpurun_out/s8g; mkdir -p $O
+B="python bench.py --steps 1 --warmup 3 --no-cpu-baseline"
+M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
+timeout 600 ncu --metrics $M --clock-control none -k regex:k_walk_n4c4 -s 2 -c 1 --csv --log-file $O/traffic_cfg2.csv $B > $O/traffic_cfg2.log 2>&1
+timeout 600 ncu --metrics $M --clock-control none -k regex:k_walk_n20_mma -s 2 -c 1 --csv --log-file $O/traffic_cfg3.csv $B --workload aa_200x100k_lg_g4 > $O/traffic_cfg3.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_cfg2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $O/launches_cfg2.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_cfg3.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --workload aa_200x100k_lg_g4 > $O/launches_cfg3.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_walk_n20_mma -s 2 -c 1 -o $O/n20_full $B --workload aa_200x100k_lg_g4 > $O/n20_full.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_walk_n4c4 -s 2 -c 1 -o $O/n4_full $B --patterns 262144 > $O/n4_full.log 2>&1
+timeout 600 python bench.py > $O/bench_cfg2.json 2> $O/bench_cfg2.err
+timeout 600 python bench.py --workload aa_200x100k_lg_g4 > $O/bench_cfg3.json 2> $O/bench_cfg3.err
+timeout 900 python bench.py --workload aa_100x50k_lg_c60_g4 --steps 5 --no-cpu-baseline > $O/bench_cfg4.json 2> $O/bench_cfg4.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref_cfg2.json 2> $O/bench_ref_cfg2.err
+cut -c1-300 $O/bench_cfg2.json $O/bench_cfg3.json $O/bench_cfg4.json $O/bench_ref_cfg2.json
+ls $O

@@ -17,6 +17,21 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(b200lk_[a-z0-9_]+)\s*\(", src)))
 
 
+def declared_tree_symbols():
+    src = open(os.path.join(ROOT, "include", "b200pt.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200(?:pt|st)_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_tree_level_symbols_exported():
+    """include/b200pt.h: the PhyloTree mirror (b200pt_*) and the partition model (b200st_*)"""
+    lib = ctypes.CDLL(blk.build())
+    syms = declared_tree_symbols()
+    assert len([s for s in syms if s.startswith("b200st_")]) >= 20
+    for sym in syms:
+        assert hasattr(lib, sym), sym
+
+
 def test_header_symbols_match_binding_list():
     assert declared_symbols() == sorted(engine.ABI_SYMBOLS)
 
