@@ -38,6 +38,169 @@ WORKLOADS = {
 }
 
 
+SUPER_WORKLOAD = "super_500part_100taxa"   # BASELINE.json configs[4]
+
+
+def make_super_inputs(ntaxa=100, nparts=500, seed=5):
+    """500 partitions, lengths ~ LogNormal(median 1000), 80 % DNA GTR+G4 / 20 % protein LG+G4,
+    per-partition rate ~ Gamma(2, 0.5), 10 % of the taxa without data in each partition (rows of STATE_UNKNOWN)."""
+    rng = np.random.default_rng(seed)
+    tree = treesim.yule_tree(ntaxa, seed=1)
+    parts = []
+    for p in range(nparts):
+        aa = rng.random() < 0.2
+        if aa:
+            model = models.make_lg_gamma(alpha=0.5 + rng.random())
+        else:
+            model = models.make_gtr_gamma(rates6=tuple(0.5 + 3.0 * rng.random(6)), pi=tuple(rng.dirichlet([8, 8, 8, 8])), alpha=0.3 + rng.random())
+        rate = float(rng.gamma(2.0, 0.5)) + 0.02
+        nptn = int(np.clip(rng.lognormal(np.log(1000.0), 0.6), 100, 8000))
+        scaled = treesim.Tree(tree.ntaxa, tree.edges, tree.lengths * rate, tree.names)
+        pat = treesim.evolve_patterns_fast(scaled, model.nstates, nptn, seed=1000 + p)
+        absent = rng.random(ntaxa) < 0.10
+        pat[absent, :] = model.state_unknown
+        parts.append(dict(model=model, rate=rate, pat=np.ascontiguousarray(pat), freq=np.ones(nptn), aa=bool(aa)))
+    return tree, parts
+
+
+def super_algorithmic(parts, ntaxa):
+    """algorithmic bytes / flops of one evaluation summed over the partitions (SURVEY §8d per-pattern figures, all T-2 updates)"""
+    by = fl = 0.0
+    for p in parts:
+        n, C = p["model"].nstates, p["model"].ncat_mix
+        B = n * C
+        nptn = p["pat"].shape[1]
+        by += nptn * (2.0 * (ntaxa - 2) * (8 * B + 2) + ntaxa + 16 + 8 + 2 * 8 * B + 16)
+        fl += nptn * C * (4.0 * n * n + n) * (ntaxa - 2)   # a mid estimate of the node mix (tip-inner everywhere)
+    return by, fl
+
+
+def run_super(args, rank, world, local_rank):
+    """BASELINE config 5 through the partition-model API (include/b200pt.h b200st_*): one step = clearAllPartialLH on every
+    partition tree -> computeLikelihoodBranch (sum of the partition logLs) -> computeFuncDerv at that branch.  Partitions are
+    dealt round-robin (in cost order) to the ranks; the only exchange is the all-reduce of (logL, df, ddf)."""
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per partition stream as far as the driver allows
+    import torch
+    import torch.distributed as dist
+    from iqtree2_b200.supertree import PhyloSuperTree
+    ntaxa, nparts = args.taxa or 100, args.parts or 500
+    tree, parts = make_super_inputs(ntaxa, nparts)
+    cost = [-(p["pat"].shape[1] * p["model"].nstates) for p in parts]
+    order = np.argsort(cost, kind="stable")
+    mine = [int(i) for k, i in enumerate(order) if k % world == rank]
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import ref_engine
+        nsample = min(args.cpu_sample or 48, nparts)
+        sample = [int(i) for i in order[:: max(1, nparts // nsample)][:nsample]]
+        threads = min(os.cpu_count() or 1, ref_engine.max_threads())
+        refs = []
+        for i in sample:
+            p = parts[i]
+            scaled = treesim.Tree(tree.ntaxa, tree.edges, tree.lengths * p["rate"], tree.names)
+            refs.append(ref_engine.RefTree(scaled, p["model"], p["pat"], p["freq"], nthreads=1))
+        def one(r):
+            return r.time_eval(0, 1)
+        with ThreadPoolExecutor(threads) as ex:
+            for _ in range(max(1, args.warmup)):
+                list(ex.map(one, refs))
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                out = list(ex.map(one, refs))
+            dt = (time.perf_counter() - t0) / args.steps
+        frac = sum(parts[i]["pat"].shape[1] * parts[i]["model"].nstates ** 2 for i in sample) / sum(p["pat"].shape[1] * p["model"].nstates ** 2 for p in parts)
+        evals = frac / dt
+        line = {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / evals, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": SUPER_WORKLOAD, "ntaxa": ntaxa, "npartitions": nparts},
+                "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": threads, "kind": "reference",
+                                 "what": "IQ-TREE 2.4.0 kernel per partition tree (Vec4d AVX+FMA), partitions spread over the host threads as PhyloSuperTree's omp parallel for does",
+                                 "sample": f"{len(sample)} of {nparts} partitions (every {max(1, nparts // nsample)}th in cost order), whole evaluations; throughput scaled by their share {frac:.4f} of the n^2-weighted pattern count"},
+                "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        for r in refs:
+            r.close()
+        print(json.dumps(line))
+        return 0
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the likelihood engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    st = PhyloSuperTree(tree.names, num_threads=args.host_threads)
+    for i in mine:
+        p = parts[i]
+        st.add_partition(p["pat"], p["freq"], p["model"], part_rate=p["rate"], device=local_rank)
+    st.read_tree(tree.to_newick(fmt="%.17g"))
+    br = 0
+    _, _, ln = st.branches()
+    scal = torch.zeros(3, dtype=torch.float64, device="cuda")
+
+    def one_eval():
+        st.clear_all_partial_lh()
+        ll = st.compute_likelihood_branch(br)
+        df, ddf = st.compute_likelihood_derv(br, float(ln[br]))
+        if world > 1:
+            scal.copy_(torch.tensor([ll, df, ddf], dtype=torch.float64))
+            dist.all_reduce(scal)
+            ll, df, ddf = scal.tolist()
+        return ll, df, ddf
+
+    for _ in range(args.warmup):
+        res = one_eval()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    l0 = st.launch_count
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res = one_eval()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = st.launch_count - l0
+    if world > 1:
+        t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        wall = float(t.item())
+    K = args.steps
+    value = K / wall
+    by, fl = super_algorithmic(parts, ntaxa)
+    peak, peak_src = load_peaks()
+    nbytes_h2d = sum((ntaxa - 2) * 40 + 8 * (2 * p["model"].nstates ** 2 + 32) for p in (parts[i] for i in mine))
+    line = {
+        "metric": "full_tree_logl_deriv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": wall * 1e3 / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic: Yule-Harding tree (seed 1); per partition tree-evolved columns at the partition's rate, every column its own pattern; "
+                "10 % of the taxa per partition without data (rows of STATE_UNKNOWN)",
+        "config": {"workload": SUPER_WORKLOAD, "ntaxa": ntaxa, "npartitions": nparts, "partitions_per_gpu": len(mine),
+                   "npatterns_total": int(sum(p["pat"].shape[1] for p in parts)), "protein_partitions": int(sum(p["aa"] for p in parts)),
+                   "model": "edge-linked proportional partition model (PhyloSuperTreePlen), GTR+G4 / LG+G4 per partition",
+                   "host_threads": args.host_threads, "clv_bytes_resident": st.device_bytes, "algorithmic_GB_per_eval": by / 1e9,
+                   "l2": "each evaluation rewrites every CLV of every partition (working set > L2)",
+                   "parallelism": f"partition-sharded x{world}" if world > 1 else "single GPU", "timing": "wall clock around K steps, device idle on both sides (the step is host-driven: one stream per partition)"},
+        "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": int(nbytes_h2d), "d2h_bytes_per_step": 24 * len(mine),
+                "ms_per_step": wall * 1e3 / K, "what": "the b200st_* calls a PhyloSuperTree host makes: per partition the op list with branch lengths goes up and (logL, df, ddf) come back every step; identical to `value` (there is no resident-input variant of a host-driven partition sweep)"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_walk_n4c4 / k_walk_n20_mma, one launch per partition on its own stream (concurrent)",
+                     "achieved": by / (wall / K) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (wall / K) / 1e9 / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_step": by,
+                     "note": "launch- and latency-bound regime: the figure is the whole step (all partitions, all kernels), not one launch"},
+        "result": {"logl": res[0], "df": res[1], "ddf": res[2]},
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -198,7 +361,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS) + [SUPER_WORKLOAD])
+    ap.add_argument("--parts", type=int, default=0, help="override the number of partitions of the partition workload (debug)")
+    ap.add_argument("--host-threads", type=int, default=0, help="host threads that queue partition work (0 = OpenMP default)")
     ap.add_argument("--taxa", type=int, default=0, help="override taxa (debug)")
     ap.add_argument("--patterns", type=int, default=0, help="override patterns (debug)")
     ap.add_argument("--ncat", type=int, default=0, help="override the number of Gamma categories (debug; single-class workloads)")
@@ -217,6 +382,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.workload == SUPER_WORKLOAD:
+        return run_super(args, rank, world, local_rank)
     ntaxa, nptn, mk, desc = WORKLOADS[args.workload]
     if args.taxa:
         ntaxa = args.taxa

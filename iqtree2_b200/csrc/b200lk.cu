@@ -40,7 +40,8 @@ struct b200lk_engine {
     size_t h_stage_cap = 0;
     double *d_red = nullptr;   // per-block partial sums
     double *d_result = nullptr;
-    double *h_result = nullptr;   // pinned, 8 doubles
+    double *h_result = nullptr;   // pinned + mapped, 8 doubles: the final reductions write the scalars straight into it
+    unsigned *d_ticket = nullptr;  // last-block ticket of the fused final reductions
     unsigned long long *d_counter = nullptr;
     double *d_scratch = nullptr;   // read-back conversion buffer
     size_t scratch_cap = 0;
@@ -106,7 +107,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
-    cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_result); cudaFree(e->d_counter); cudaFree(e->d_scratch);
+    cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -167,10 +168,12 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     TRY(dev_alloc(e, &e->d_pattern_scaling, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_lh_cat, (size_t)Ppad * e->C));
     TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 3));
-    TRY(dev_alloc(e, &e->d_result, 8));
+    TRY(dev_alloc(e, &e->d_ticket, 4));
     TRY(dev_alloc(e, &e->d_counter, 8));
 #undef TRY
-    if (cudaMallocHost((void **)&e->h_result, 8 * sizeof(double)) != cudaSuccess) { e->err = "cudaMallocHost failed"; return bail(B200LK_ERR_CUDA); }
+    if (cudaHostAlloc((void **)&e->h_result, 8 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&e->d_result, e->h_result, 0) != cudaSuccess) { e->err = "cudaHostAlloc(mapped) failed"; return bail(B200LK_ERR_CUDA); }
+    cudaMemsetAsync(e->d_ticket, 0, 4 * sizeof(unsigned), e->stream);
     cudaMemsetAsync(e->d_tips, cfg->state_unknown, (size_t)cfg->ntaxa * Ppad, e->stream);
     cudaMemsetAsync(e->d_freq, 0, sizeof(double) * Ppad, e->stream);
     cudaMemsetAsync(e->d_invar, 0, sizeof(double) * Ppad, e->stream);
@@ -394,12 +397,11 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     }
     WalkJob4 *dj = (WalkJob4 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob4) * nops, cudaMemcpyHostToDevice, e->stream));
-    k_walk_info_n4c4<<<nops, 64, 0, e->stream>>>(e->d, dj, e->d_opinfo);
+    k_walk_info_n4c4<<<nops, 64, 0, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
     Model4 M;
     for (int k = 0; k < 16; k++) { M.evec[k] = e->h_evec[k]; M.inv[k] = e->h_inv_evec[k]; }
     const long long ntiles = e->Ppad / kTile;
     const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * 4);   // 4 resident CTAs per SM (128 regs/thread)
-    CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
         const bool safe = e->cfg.safe_numeric != 0;
@@ -487,7 +489,7 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     }
     WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
-    k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo);
+    k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
     const Walk20Cfg &cfg = walk20_cfgs[(e->kernel_variant >= 0 && e->kernel_variant < kNumWalk20Cfgs) ? e->kernel_variant : 0];
     const int tile_ptn = cfg.nw * 32;
     const size_t smem = 2 * stage_sz * sizeof(double);   // the walker double-buffers whole staging blocks
@@ -508,7 +510,6 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     int ntiles = (int)std::min<long long>(waves * slots, nblocks);
     if (e->kernel_variant == 4) ntiles = (int)((nblocks + cfg.nw - 1) / cfg.nw);   // A/B: fixed full tiles
     const int grid = (int)std::min<long long>(ntiles, slots);
-    CK(cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream));
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {
         const bool safe = e->cfg.safe_numeric != 0;
@@ -698,15 +699,15 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     if (rc) return rc;
     prof_mark(e, 1);
     const int nblocks = (int)(e->Ppad / kTile);
-    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0);
-    if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red);
-    else k_root<false><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red);
-    k_final_reduce<1><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
-    e->launches += 3;
-    e->last_launch[1] += 3;
+    const int fuse = e->B <= kFuseValsMaxB;
+    const size_t vsm = fuse ? sizeof(double) * e->B : 0;
+    if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
+    if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    else k_root<false><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    e->launches += 1;
+    e->last_launch[1] += 1;
     prof_mark(e, 2);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);
     e->pending_marks = 2;
     return 0;
@@ -760,13 +761,14 @@ static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_
 
 static void enqueue_derv(b200lk_engine *e, double length) {
     const int nblocks = (int)(e->Ppad / kTile);
-    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 1);
-    if (e->B == 16) k_derv<16><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    else if (e->B == 80) k_derv<80><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    else k_derv<0><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    k_final_reduce<2><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result + 1);
-    e->launches += 3;
-    e->last_launch[2] += 3;
+    const int fuse = e->B <= kFuseValsMaxB;
+    const size_t vsm = fuse ? sizeof(double) * 3 * e->B : 0;
+    if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 1); e->launches++; e->last_launch[2]++; }
+    if (e->B == 16) k_derv<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
+    else if (e->B == 80) k_derv<80><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
+    else k_derv<0><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
+    e->launches += 1;
+    e->last_launch[2] += 1;
 }
 
 extern "C" int b200lk_theta_reset(b200lk_engine *e) { e->theta_computed = false; return 0; }
@@ -786,7 +788,6 @@ extern "C" int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops
     enqueue_derv(e, length);
     prof_mark(e, 3);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_result + 1, e->d_result + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     e->pending |= PEND_DERV;
     e->pending_marks = 3;
     return 0;
@@ -805,16 +806,16 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     prof_begin(e);
     prof_mark(e, 1);
     const int nblocks = (int)(e->Ppad / kTile);
-    k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0);
-    if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    else if (e->B == 80) k_from_buffer<80><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    else k_from_buffer<0><<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_red);
-    k_final_reduce<1><<<1, 256, 0, e->stream>>>(e->d_red, nblocks, e->d_result);
-    e->launches += 3;
-    e->last_launch[1] += 3;
+    const int fuse = e->B <= kFuseValsMaxB;
+    const size_t vsm = fuse ? sizeof(double) * e->B : 0;
+    if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
+    if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    else if (e->B == 80) k_from_buffer<80><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    else k_from_buffer<0><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    e->launches += 1;
+    e->last_launch[1] += 1;
     prof_mark(e, 2);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(e->h_result, e->d_result, sizeof(double), cudaMemcpyDeviceToHost, e->stream));
     e->pending = PEND_LOGL | PEND_SAVE_LOG;
     e->pending_marks = 2;
     return 0;
@@ -841,7 +842,7 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     int nsteps = 0;
     auto func_derv = [&](double x, double &f, double &df) -> int {
         enqueue_derv(e, x);
-        cudaError_t ce = cudaMemcpyAsync(e->h_result + 1, e->d_result + 1, 2 * sizeof(double), cudaMemcpyDeviceToHost, e->stream);
+        cudaError_t ce = cudaSuccess;
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
         if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
         f = -e->h_result[1];

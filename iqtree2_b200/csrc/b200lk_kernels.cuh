@@ -174,6 +174,31 @@ __global__ void k_vals(Dev D, double length, int with_derv) {
     }
 }
 
+// The same values computed by every CTA of a consumer kernel into its own shared memory (small blocks only: 16 or 80 exps per
+// CTA cost nothing, a separate k_vals launch costs a launch — a third of a Newton-Raphson step on a small partition).
+__device__ __forceinline__ const double *stage_vals(const Dev &D, double length, int with_derv, double *s_val) {
+    const int n = D.n;
+    for (int k = threadIdx.x; k < D.B; k += blockDim.x) {
+        int c = k / n, i = k - c * n;
+        int m = c / D.denom, r = c % D.ncat;
+        double prop = D.cat_prop[r] * D.mix_weight[m];
+        if (with_derv) {
+            double cof = D.eval[m * n + i] * D.cat_rate[r];
+            double val = exp(cof * length) * prop;
+            double v1 = cof * val;
+            s_val[k] = val;
+            s_val[D.B + k] = v1;
+            s_val[2 * D.B + k] = cof * v1;
+        } else {
+            double len = D.cat_rate[r] * length;
+            s_val[k] = exp(D.eval[m * n + i] * len) * prop;
+        }
+    }
+    __syncthreads();
+    return s_val;
+}
+constexpr int kFuseValsMaxB = 512;   // consumer kernels compute val0/1/2 themselves up to this block size
+
 // ------------------------------------------------------------------------------------------------------------
 // work distribution shared by the partial-likelihood kernels.
 //   walk = 1 : "pattern-tile walker" — a work item is one tile of kTile patterns; the CTA walks the whole
@@ -451,7 +476,8 @@ struct StageHdr4 { int32_t dst, ncase, aid, bid, loadA, pad0, pad1, pad2; };
 
 // child A is the CLV that lives in registers (`cur`: chained from the previous op, or loaded when loadA), child B the
 // other one: an internal CLV loaded from memory (ncase 2) or a tip (ncase <= 1); ncase 0: both are tips.
-__global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jobs, double *stage) {
+__global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jobs, double *stage, unsigned long long *counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ULL;   // the walker's tile queue (next launch on this stream)
     __shared__ double s_exp[2][16];
     const WalkJob4 job = jobs[blockIdx.x];
     double *st = stage + (size_t)blockIdx.x * kStage4;
@@ -754,7 +780,8 @@ __host__ __device__ inline size_t stage20_doubles(int C, int su) { return 4 + 2 
 // for a single-class model; one category per block when mixture classes are fused with the rate categories,
 // tree/phylokernelnew.h:1322-1325).  Each block gets its own staging block, so that to the walker a mixture is simply a
 // longer list of "virtual ops" with cpb categories each.
-__global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *jobs, double *stage) {
+__global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *jobs, double *stage, unsigned long long *counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ULL;   // the walker's tile queue (next launch on this stream)
     extern __shared__ double s_exp20[];   // [2][cpb*20]
     const int nblk = D.nmix, cpb = D.C / nblk, B = cpb * 20, TS = tab20_stride(cpb);
     const int op = blockIdx.x / nblk, m = blockIdx.x - op * nblk;
@@ -1208,6 +1235,46 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red)
     }
 }
 
+// block_reduce_store + the final sum by the LAST block to arrive (ticket counter), in exactly k_final_reduce's order (256
+// virtual threads, thread t sums blocks t, t+256, ... in order, then a binary tree): bit-identical to the two-launch form, one
+// launch fewer.  `result` may be mapped host memory: the scalars land in the caller's buffer without a copy.
+template <int NV>
+__device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red, unsigned *ticket, double *result) {
+    block_reduce_store<NV>(v, red);
+    __shared__ bool s_last;
+    __shared__ double s_fin[NV][256];
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nblocks = gridDim.x;
+    for (int vt = threadIdx.x; vt < 256; vt += blockDim.x) {
+        double acc[NV];
+#pragma unroll
+        for (int j = 0; j < NV; j++) acc[j] = 0.0;
+        for (int b = vt; b < nblocks; b += 256)
+#pragma unroll
+            for (int j = 0; j < NV; j++) acc[j] += __ldcg(red + (long long)b * NV + j);
+#pragma unroll
+        for (int j = 0; j < NV; j++) s_fin[j][vt] = acc[j];
+    }
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        for (int vt = threadIdx.x; vt < off; vt += blockDim.x)
+#pragma unroll
+            for (int j = 0; j < NV; j++) s_fin[j][vt] += s_fin[j][vt + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int j = 0; j < NV; j++) result[j] = s_fin[j][0];
+        *ticket = 0;
+    }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(256) k_final_reduce(const double *red, int nblocks, double *result) {
     __shared__ double s[NV][256];
@@ -1237,7 +1304,10 @@ __global__ void __launch_bounds__(256) k_final_reduce(const double *red, int nbl
 // the evaluation branch, _pattern_lh / _pattern_lh_cat, and the frequency-weighted sum.
 // ------------------------------------------------------------------------------------------------------------
 template <bool SAFE>
-__global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red) {
+__global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red,
+                                                unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    const double *vals = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
     const int n = D.n, C = D.C, B = D.B;
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
     const long long cb = pbase(p, C);
@@ -1257,14 +1327,14 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
     double lh_ptn = 0.0;
     unsigned min_scale = 0xffffffffu;
     for (int c = 0; c < C; c++) {
-        const double *val = D.val + c * n;
+        const double *val = vals + c * n;
         const double *tp = tip ? tip + (c / D.denom) * n : nullptr;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int i = 0;
         for (; i + 3 < n; i += 4) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                double f = __ldg(val + i + j) * (node ? node[at(c, i + j)] : __ldg(tp + i + j));
+                double f = val[i + j] * (node ? node[at(c, i + j)] : __ldg(tp + i + j));
                 double d = dad[at(c, i + j)];
                 if (j == 0) a0 = fma(f, d, a0); else if (j == 1) a1 = fma(f, d, a1);
                 else if (j == 2) a2 = fma(f, d, a2); else a3 = fma(f, d, a3);
@@ -1272,7 +1342,7 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
         }
         double s = (a0 + a1) + (a2 + a3);
         for (; i < n; i++) {
-            double f = __ldg(val + i) * (node ? node[at(c, i)] : __ldg(tp + i));
+            double f = val[i] * (node ? node[at(c, i)] : __ldg(tp + i));
             s = fma(f, dad[at(c, i)], s);
         }
         if (SAFE) {
@@ -1313,7 +1383,7 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
         else { D.pattern_lh[p] = lh_ptn; D.pattern_scaling[p] = vc_min_scale; }
         acc[0] = lg * D.freq[p];
     }
-    block_reduce_store<1>(acc, red);
+    block_reduce_finish<1>(acc, red, ticket, result);
 }
 
 // computeLikelihoodBuffer{,Generic}SIMD (tree/phylokernelnew.h:2091-2230): theta_all and buffer_scale_all
@@ -1360,30 +1430,32 @@ __global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_k
 
 // computeLikelihoodDerv{,Generic}SIMD pattern loop (tree/phylokernelnew.h:2463-2505): (lh, df, ddf) = val{0,1,2}.theta
 template <int BT>
-__global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red) {
+__global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    const double *vals = fuse_vals ? stage_vals(D, length, 1, s_vals_dyn) : D.val;
     const int B = BT ? BT : D.B;
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
     const double *theta = D.theta + pbase(p, B);
-    const double *v0 = D.val, *v1 = D.val + B, *v2 = D.val + 2 * B;
+    const double *v0 = vals, *v1 = vals + B, *v2 = vals + 2 * B;
     // dotProductTriple: two lane accumulators (even / odd k)
     double ad[2] = {0, 0}, bd[2] = {0, 0}, cd[2] = {0, 0};
     int k = 0;
 #pragma unroll 8
     for (; k + 1 < B; k += 2) {
         double t0 = theta[(long long)k * kWarp], t1 = theta[(long long)(k + 1) * kWarp];
-        ad[0] = fma(__ldg(v0 + k), t0, ad[0]); ad[1] = fma(__ldg(v0 + k + 1), t1, ad[1]);
-        bd[0] = fma(__ldg(v1 + k), t0, bd[0]); bd[1] = fma(__ldg(v1 + k + 1), t1, bd[1]);
-        cd[0] = fma(__ldg(v2 + k), t0, cd[0]); cd[1] = fma(__ldg(v2 + k + 1), t1, cd[1]);
+        ad[0] = fma(v0[k], t0, ad[0]); ad[1] = fma(v0[k + 1], t1, ad[1]);
+        bd[0] = fma(v1[k], t0, bd[0]); bd[1] = fma(v1[k + 1], t1, bd[1]);
+        cd[0] = fma(v2[k], t0, cd[0]); cd[1] = fma(v2[k + 1], t1, cd[1]);
     }
     double lh = ad[0] + ad[1], df = bd[0] + bd[1], ddf = cd[0] + cd[1];
     if (k < B) {
         double t = theta[(long long)k * kWarp];
-        lh = fma(__ldg(v0 + k), t, lh); df = fma(__ldg(v1 + k), t, df); ddf = fma(__ldg(v2 + k), t, ddf);
+        lh = fma(v0[k], t, lh); df = fma(v1[k], t, df); ddf = fma(v2[k], t, ddf);
     } else if ((D.quirks & 1) && (D.n & 1)) {
         // B200LK_QUIRK_DOTTRIPLE_ODD: the reference's dotProductTriple takes its odd-length branch on nstates&1 and, when
         // the block is even, adds the last element a second time (tree/phylokernelnew.h:700-714)
         double t = theta[(long long)(B - 1) * kWarp];
-        lh = fma(__ldg(v0 + B - 1), t, lh); df = fma(__ldg(v1 + B - 1), t, df); ddf = fma(__ldg(v2 + B - 1), t, ddf);
+        lh = fma(v0[B - 1], t, lh); df = fma(v1[B - 1], t, df); ddf = fma(v2[B - 1], t, ddf);
     }
     lh = fabs(lh) + D.invar[p];
     double acc[2] = {0.0, 0.0};
@@ -1395,12 +1467,14 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red) {
         acc[0] = tmp1;
         acc[1] = fma(-tmp1, df_frac, tmp2);   // nmul_add(tmp1, df_frac, tmp2) :2505
     }
-    block_reduce_store<2>(acc, red);
+    block_reduce_finish<2>(acc, red, ticket, result);
 }
 
 // computeLikelihoodFromBuffer{,Generic}SIMD pattern loop (tree/phylokernelnew.h:3313-3368)
 template <int BT>
-__global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red) {
+__global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    const double *val0 = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
     const int B = BT ? BT : D.B;
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
     const double *theta = D.theta + pbase(p, B);
@@ -1408,13 +1482,13 @@ __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red) {
     int k = 0;
 #pragma unroll 4
     for (; k + 3 < B; k += 4) {
-        a0 = fma(__ldg(D.val + k), theta[(long long)k * kWarp], a0);
-        a1 = fma(__ldg(D.val + k + 1), theta[(long long)(k + 1) * kWarp], a1);
-        a2 = fma(__ldg(D.val + k + 2), theta[(long long)(k + 2) * kWarp], a2);
-        a3 = fma(__ldg(D.val + k + 3), theta[(long long)(k + 3) * kWarp], a3);
+        a0 = fma(val0[k], theta[(long long)k * kWarp], a0);
+        a1 = fma(val0[k + 1], theta[(long long)(k + 1) * kWarp], a1);
+        a2 = fma(val0[k + 2], theta[(long long)(k + 2) * kWarp], a2);
+        a3 = fma(val0[k + 3], theta[(long long)(k + 3) * kWarp], a3);
     }
     double lh = (a0 + a1) + (a2 + a3);
-    for (; k < B; k++) lh = fma(__ldg(D.val + k), theta[(long long)k * kWarp], lh);
+    for (; k < B; k++) lh = fma(val0[k], theta[(long long)k * kWarp], lh);
     lh = fabs(lh) + D.invar[p];
     double acc[1] = {0.0};
     if (p < D.P) {
@@ -1422,7 +1496,7 @@ __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red) {
         D.pattern_lh[p] = lg;
         acc[0] = lg * D.freq[p];
     }
-    block_reduce_store<1>(acc, red);
+    block_reduce_finish<1>(acc, red, ticket, result);
 }
 
 // layout converters for read-backs: device warp-interleaved -> reference V=1 layout [p*W + k]
