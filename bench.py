@@ -262,6 +262,19 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_traffic(workload, overridden, my_nptn):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed
+    ncu capture of this workload at full size (profiles/traffic.json), scaled by this rank's share of the patterns; None
+    for workloads / overrides without a capture."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if overridden or not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get(workload)
+    if not t:
+        return None, None
+    return (t["dram_bytes_read"] + t["dram_bytes_write"]) * (my_nptn / t["npatterns"]), t["source"]
+
+
 def load_fp64_peak():
     p = os.path.join(ROOT, "profiles", "fp64_peaks_b200.json")
     if os.path.exists(p):
@@ -563,6 +576,12 @@ def main():
                     "traffic": None, "peak_source": fsrc, "algorithmic_flops_per_launch": flops, "launch_ms": ker_s * 1e3,
                     "hbm": {"achieved_GBps": achieved, "peak_GBps": peak, "frac": achieved / peak,
                             "algorithmic_bytes_per_launch": my_bytes_partials}, "partial_lh_GBps": achieved}
+    traffic, traffic_src = load_traffic(args.workload, bool(args.taxa or args.patterns or args.ncat or args.variant or args.schedule), my_nptn)
+    roofline["traffic"] = traffic
+    if traffic:
+        roofline["traffic_source"] = traffic_src
+        roofline["dram_GBps"] = traffic / ker_s / 1e9     # what the DRAM pins see: chained CLVs are never re-read
+        roofline["dram_frac_of_hbm_peak"] = traffic / ker_s / 1e9 / peak
     line = {
         "metric": "full_tree_logl_deriv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
         "warmup": args.warmup, "ms_per_step": res_run["event_ms"] / K, "kernel_ms_per_step": res_run["device_ms"] / K,
