@@ -163,6 +163,17 @@ int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out /* [(state_unknown+1
 /* device pointer of _pattern_lh (length >= nptn doubles) for on-device consumers (UFBoot RELL) */
 void *b200lk_pattern_lh_dev(b200lk_engine *e);
 
+/* ---- UFBoot RELL on the device (IQTree::saveCurrentTree, tree/iqtree.cpp:3551-3637) --------------------------------
+ * boot_samples: the resampled pattern frequencies of every bootstrap replicate, [nboot][nptn] floats (IQTree::boot_samples,
+ * BootValType = float, tree/phylotree.h:54); uploaded once and kept resident (nboot = 0 frees them).
+ * b200lk_rell: rell[b] = dotProduct((float)_pattern_lh, boot_samples[b], nptn) (PhyloTree::dotProductSIMD<float>,
+ * tree/phylokernel.h:64-70) for all replicates, on the _pattern_lh left by the last computeLikelihoodBranch /
+ * computeLikelihoodFromBuffer — 4*nboot bytes come back instead of 8*nptn going out per candidate tree.  Products in float as
+ * in the reference, accumulated in double in a fixed order. The accept/replace bookkeeping (boot_logl, boot_counts, the
+ * random tie-break) stays with the caller. */
+int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot);
+int b200lk_rell(b200lk_engine *e, float *rell /* [nboot] */);
+
 /* ---- measurement --------------------------------------------------------------------------------------------- */
 /* When enabled, every call brackets its kernel groups with CUDA events on the engine stream. */
 int b200lk_set_profiling(b200lk_engine *e, int32_t on);

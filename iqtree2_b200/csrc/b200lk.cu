@@ -62,6 +62,10 @@ struct b200lk_engine {
     float last_ms[5] = {0, 0, 0, 0, 0};
     int last_launch[3] = {0, 0, 0};
     int64_t launches = 0;
+    float *d_boot = nullptr, *d_rell = nullptr;   // UFBoot: resampled pattern frequencies [nboot][boot_stride], RELL scores
+    int nboot = 0;
+    long long boot_stride = 0;
+    size_t boot_bytes = 0;
     int pending = 0, pending_marks = 0;   // results queued by b200lk_enqueue_*, collected by b200lk_finish
     std::string err;
 };
@@ -108,6 +112,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
+    cudaFree(e->d_boot); cudaFree(e->d_rell);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -957,3 +962,40 @@ extern "C" int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out) {
     return read_plain(e, e->d.tip_lh, sizeof(double) * (e->cfg.state_unknown + 1) * e->cfg.nmix * e->cfg.nstates, out);
 }
 extern "C" void *b200lk_pattern_lh_dev(b200lk_engine *e) { return e->d_pattern_lh; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// UFBoot RELL on the device
+// ---------------------------------------------------------------------------------------------------------------
+extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot) {
+    cudaSetDevice(e->cfg.device);
+    if (nboot < 0) return fail(e, B200LK_ERR_INVALID, "nboot < 0");
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->d_boot) { cudaFree(e->d_boot); e->device_bytes -= (int64_t)e->boot_bytes; e->d_boot = nullptr; }
+    if (e->d_rell) { cudaFree(e->d_rell); e->d_rell = nullptr; }
+    e->nboot = 0; e->boot_bytes = 0;
+    if (nboot == 0) return 0;
+    e->boot_stride = (e->P + 3) / 4 * 4;   // rows 16-byte aligned
+    const size_t n = (size_t)nboot * e->boot_stride;
+    int rc = dev_alloc(e, &e->d_boot, n);
+    if (rc) return rc;
+    e->boot_bytes = n * sizeof(float);
+    rc = dev_alloc(e, &e->d_rell, (size_t)nboot);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(e->d_boot, 0, n * sizeof(float), e->stream));
+    CK(cudaMemcpy2DAsync(e->d_boot, e->boot_stride * sizeof(float), boot_samples, e->P * sizeof(float), e->P * sizeof(float), nboot,
+                         cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    e->nboot = nboot;
+    return 0;
+}
+
+extern "C" int b200lk_rell(b200lk_engine *e, float *rell) {
+    cudaSetDevice(e->cfg.device);
+    if (e->nboot <= 0) return fail(e, B200LK_ERR_STATE, "rell: no bootstrap samples set");
+    k_rell<<<e->nboot, 256, 0, e->stream>>>(e->d_pattern_lh, e->d_boot, e->P, e->boot_stride, e->d_rell);
+    e->launches++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(rell, e->d_rell, sizeof(float) * e->nboot, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}

@@ -1507,6 +1507,37 @@ __global__ void k_deinterleave_f64(const double *src, double *dst, long long P, 
     int k = (int)(idx - p * W);
     dst[idx] = src[pbase(p, W) + (long long)k * kWarp];
 }
+// ------------------------------------------------------------------------------------------------------------
+// UFBoot RELL (IQTree::saveCurrentTree, tree/iqtree.cpp:3551-3637): rell[b] = sum_p (float)_pattern_lh[p] * boot_sample[b][p]
+// for every bootstrap replicate — the reference's dotProductSIMD<float> (tree/phylokernel.h:64-70) over BootValType = float
+// arrays, once per candidate tree.  One CTA per replicate streams that replicate's resampled frequencies (16-byte loads);
+// _pattern_lh stays on the device (L2-resident across the CTAs).  Products in float as in the reference, accumulated in double
+// in a fixed order (thread t takes elements 4(t + 256 j) .. +3), so the result is reproducible and at least as accurate as the
+// reference's 8-lane float accumulation.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rell(const double *pattern_lh, const float *boot, long long nptn, long long stride, float *out) {
+    const float *row = boot + (long long)blockIdx.x * stride;
+    double acc = 0.0;
+    const long long n4 = nptn >> 2;
+    for (long long k = threadIdx.x; k < n4; k += 256) {
+        const float4 f = __ldcs(reinterpret_cast<const float4 *>(row) + k);
+        const double2 l0 = *reinterpret_cast<const double2 *>(pattern_lh + 4 * k), l1 = *reinterpret_cast<const double2 *>(pattern_lh + 4 * k + 2);
+        acc += (double)((float)l0.x * f.x);
+        acc += (double)((float)l0.y * f.y);
+        acc += (double)((float)l1.x * f.z);
+        acc += (double)((float)l1.y * f.w);
+    }
+    for (long long p = (n4 << 2) + threadIdx.x; p < nptn; p += 256) acc += (double)((float)pattern_lh[p] * row[p]);
+    __shared__ double s[256];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+        if (threadIdx.x < off) s[threadIdx.x] += s[threadIdx.x + off];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = (float)s[0];
+}
+
 __global__ void k_deinterleave_clv(Dev D, const double *src, double *dst) {   // one CLV slot -> [p][c*n + i]
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= D.P * D.B) return;

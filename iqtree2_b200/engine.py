@@ -25,6 +25,7 @@ ABI_SYMBOLS = [
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
+    "b200lk_set_boot_samples", "b200lk_rell",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -228,6 +229,19 @@ class LikelihoodEngine:
 
     def get_pattern_lh(self):
         return self._get("b200lk_get_pattern_lh", self.nptn)
+
+    def set_boot_samples(self, boot_samples):
+        """UFBoot: resampled pattern frequencies [nboot][nptn] (float32), kept resident on the device."""
+        b = np.ascontiguousarray(boot_samples, dtype=np.float32)
+        assert b.ndim == 2 and b.shape[1] == self.nptn
+        self._nboot = b.shape[0]
+        self._check(self.lib.b200lk_set_boot_samples(self._h, b.ctypes.data_as(C.c_void_p), C.c_int32(b.shape[0])))
+
+    def rell(self):
+        """RELL log-likelihood of every bootstrap replicate for the tree of the last branch_logl / logl_from_buffer."""
+        out = np.zeros(self._nboot, dtype=np.float32)
+        self._check(self.lib.b200lk_rell(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
 
     def get_pattern_scaling(self):
         return self._get("b200lk_get_pattern_scaling", self.nptn)
