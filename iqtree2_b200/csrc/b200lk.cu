@@ -66,6 +66,7 @@ struct b200lk_engine {
     int nboot = 0;
     long long boot_stride = 0;
     size_t boot_bytes = 0;
+    int newton_grid = 0;   // co-resident CTAs of k_newton_coop
     int pending = 0, pending_marks = 0;   // results queued by b200lk_enqueue_*, collected by b200lk_finish
     std::string err;
 };
@@ -172,7 +173,7 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     TRY(dev_alloc(e, &e->d_pattern_lh, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_scaling, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_lh_cat, (size_t)Ppad * e->C));
-    TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 3));
+    TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 4));   // per-block partial sums: 3 values, or k_newton_coop's two buffers of 2
     TRY(dev_alloc(e, &e->d_ticket, 4));
     TRY(dev_alloc(e, &e->d_counter, 8));
 #undef TRY
@@ -844,6 +845,29 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
+    if (e->B <= kFuseValsMaxB && e->kernel_variant != 9) {
+        // the whole iteration in one cooperative launch (k_newton_coop); variant 9 keeps the host-driven loop below for A/B
+        const void *kern = e->B == 16 ? (const void *)k_newton_coop<16> : e->B == 80 ? (const void *)k_newton_coop<80> : (const void *)k_newton_coop<0>;
+        const size_t vsm = sizeof(double) * 3 * e->B;
+        if (e->newton_grid == 0) {
+            int per_sm = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, vsm));
+            e->newton_grid = std::max(1, per_sm) * e->num_sms;
+        }
+        const int nblocks = (int)(e->Ppad / kTile);
+        const int grid = std::min(nblocks, std::min(e->newton_grid, (int)(e->Ppad / kTile)));   // d_red holds 3 doubles per tile: room for 2 x 2 x grid
+        int maxs = maxNRStep;
+        void *args[] = {(void *)&e->d, (void *)&e->d_red, (void *)&e->d_result, (void *)&x1, (void *)&xguess, (void *)&x2, (void *)&xacc, (void *)&maxs};
+        // d_result is mapped host memory; slots 4..6 = (length, evaluations, status)
+        double *io = e->d_result + 4;
+        args[2] = (void *)&io;
+        CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTile), args, vsm, e->stream));
+        e->launches++;
+        CK(cudaStreamSynchronize(e->stream));
+        *length_out = e->h_result[4];
+        if (steps_out) *steps_out = (int)e->h_result[5];
+        return e->h_result[6] != 0.0 ? B200LK_WARN_DERV_UNDERFLOW : 0;
+    }
     int nsteps = 0;
     auto func_derv = [&](double x, double &f, double &df) -> int {
         enqueue_derv(e, x);

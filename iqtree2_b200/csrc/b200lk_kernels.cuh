@@ -7,6 +7,7 @@
 // transition matrices are warp-uniform operands, and per-pattern reductions (scaling max, lh, df, ddf) never
 // leave the thread.  Patterns are padded to a multiple of kTile with all-unknown states and zero frequency.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -1468,6 +1469,112 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ti
         acc[1] = fma(-tmp1, df_frac, tmp2);   // nmul_add(tmp1, df_frac, tmp2) :2505
     }
     block_reduce_finish<2>(acc, red, ticket, result);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// The whole Newton-Raphson iteration of optimizeOneBranch on the device: Optimization::minimizeNewton
+// (utils/optimization.cpp:422-499, statement for statement) driving computeFuncDerv (tree/phylotree.cpp:2529-2536) =
+// the (df, ddf) pass of computeLikelihoodDerv on the resident theta buffer (k_derv's arithmetic).  One COOPERATIVE launch:
+// every NR step is a grid-stride pass over the patterns, per-block partial sums, one grid barrier, and the same fixed-order
+// final sum in every CTA — so every thread holds the same (f, df) and walks the same control flow; no host round trip per
+// step (a host-driven step costs a launch, a synchronisation and ~10 us of latency; a 60-taxon x 4 000-pattern sweep spent
+// 90 us per branch that way).  Results go to mapped host memory: io[0] = optimised length, io[1] = derv evaluations,
+// io[2] = status (0 ok, 2 = non-finite derivative: df = ddf = 0 semantics of tree/phylokernelnew.h:2629-2632).
+// ------------------------------------------------------------------------------------------------------------
+template <int BT>
+__global__ void __launch_bounds__(kTile) k_newton_coop(Dev D, double *red, double *io, double x1, double xguess, double x2, double xacc,
+                                                       int maxNRStep) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double s_vals_dyn[];
+    __shared__ double s_fin[2][256];
+    const int B = BT ? BT : D.B;
+    int nevals = 0;
+    auto func_derv = [&](double x, double &f, double &df) {
+        const double *vals = stage_vals(D, x, 1, s_vals_dyn);
+        const double *v0 = vals, *v1 = vals + B, *v2 = vals + 2 * B;
+        double acc[2] = {0.0, 0.0};
+        for (long long p = (long long)blockIdx.x * kTile + threadIdx.x; p < D.Ppad; p += (long long)gridDim.x * kTile) {
+            const double *theta = D.theta + pbase(p, B);
+            double ad[2] = {0, 0}, bd[2] = {0, 0}, cd[2] = {0, 0};
+            int k = 0;
+#pragma unroll 8
+            for (; k + 1 < B; k += 2) {
+                double t0 = theta[(long long)k * kWarp], t1 = theta[(long long)(k + 1) * kWarp];
+                ad[0] = fma(v0[k], t0, ad[0]); ad[1] = fma(v0[k + 1], t1, ad[1]);
+                bd[0] = fma(v1[k], t0, bd[0]); bd[1] = fma(v1[k + 1], t1, bd[1]);
+                cd[0] = fma(v2[k], t0, cd[0]); cd[1] = fma(v2[k + 1], t1, cd[1]);
+            }
+            double lh = ad[0] + ad[1], d1 = bd[0] + bd[1], d2 = cd[0] + cd[1];
+            if (k < B) {
+                double t = theta[(long long)k * kWarp];
+                lh = fma(v0[k], t, lh); d1 = fma(v1[k], t, d1); d2 = fma(v2[k], t, d2);
+            } else if ((D.quirks & 1) && (D.n & 1)) {
+                double t = theta[(long long)(B - 1) * kWarp];
+                lh = fma(v0[B - 1], t, lh); d1 = fma(v1[B - 1], t, d1); d2 = fma(v2[B - 1], t, d2);
+            }
+            lh = fabs(lh) + D.invar[p];
+            if (p < D.P) {
+                double inv = 1.0 / lh;
+                double df_frac = d1 * inv, ddf_frac = d2 * inv;
+                double freq = D.freq[p];
+                double tmp1 = df_frac * freq, tmp2 = ddf_frac * freq;
+                acc[0] += tmp1;
+                acc[1] += fma(-tmp1, df_frac, tmp2);
+            }
+        }
+        double *r = red + (size_t)(nevals & 1) * 2 * gridDim.x;   // double-buffered by evaluation parity: one barrier per step
+        block_reduce_store<2>(acc, r);
+        __threadfence();
+        grid.sync();
+        const int nblocks = gridDim.x;
+        for (int vt = threadIdx.x; vt < 256; vt += blockDim.x) {
+            double a0 = 0.0, a1 = 0.0;
+            for (int b = vt; b < nblocks; b += 256) { a0 += __ldcg(r + 2 * b); a1 += __ldcg(r + 2 * b + 1); }
+            s_fin[0][vt] = a0; s_fin[1][vt] = a1;
+        }
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            for (int vt = threadIdx.x; vt < off; vt += blockDim.x) { s_fin[0][vt] += s_fin[0][vt + off]; s_fin[1][vt] += s_fin[1][vt + off]; }
+            __syncthreads();
+        }
+        f = -s_fin[0][0];      // computeFuncDerv returns -df, -ddf
+        df = -s_fin[1][0];
+        __syncthreads();
+        nevals++;
+    };
+    auto finish = [&](double x, double status) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { io[0] = x; io[1] = (double)nevals; io[2] = status; }
+    };
+    double df, dx, f, temp, xh, xl, rts, rts_old;
+    rts = xguess;
+    if (rts < x1) rts = x1;
+    if (rts > x2) rts = x2;
+    func_derv(rts, f, df);
+    if (!isfinite(f) || !isfinite(df)) { finish(rts, 2.0); return; }
+    if (df >= 0.0 && fabs(f) < xacc) { finish(rts, 0.0); return; }
+    if (f < 0.0) { xl = rts; xh = x2; } else { xh = rts; xl = x1; }
+    dx = fabs(xh - xl);
+    for (int j = 1; j <= maxNRStep; j++) {
+        rts_old = rts;
+        if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)) {
+            dx = 0.5 * (xh - xl);
+            rts = xl + dx;
+            if (xl == rts) { finish(rts, 0.0); return; }
+        } else {
+            dx = f / df;
+            temp = rts;
+            rts -= dx;
+            if (temp == rts) { finish(rts, 0.0); return; }
+        }
+        if (fabs(dx) < xacc || (j == maxNRStep)) { finish(rts_old, 0.0); return; }
+        func_derv(rts, f, df);
+        if (!isfinite(f) || !isfinite(df)) { finish(rts, 2.0); return; }
+        if (df > 0.0 && fabs(f) < xacc) { finish(rts, 0.0); return; }
+        if (f < 0.0) xl = rts;
+        else if (f > 0.0) xh = rts;
+    }
+    finish(rts, 0.0);
 }
 
 // computeLikelihoodFromBuffer{,Generic}SIMD pattern loop (tree/phylokernelnew.h:3313-3368)
