@@ -463,6 +463,9 @@ static const Walk20Cfg walk20_cfgs[] = {
 #endif
 };
 constexpr int kNumWalk20Cfgs = (int)(sizeof(walk20_cfgs) / sizeof(walk20_cfgs[0]));
+// category-split form for small problems (single class, >= 2 categories, fewer 32-pattern blocks than resident CTAs) [SAFE]
+static const void *const walk20_csp[2] = {(const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, true>,
+                                          (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, true>};
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
@@ -505,6 +508,10 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
             // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
+        for (const void *f : walk20_csp) {
+            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.f[0], tile_ptn, smem));
         e->walk20_ctas_per_sm = std::max(per_sm, 1);
@@ -515,12 +522,16 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     const long long waves = (nblocks + cfg.nw * slots - 1) / (cfg.nw * slots);
     int ntiles = (int)std::min<long long>(waves * slots, nblocks);
     if (e->kernel_variant == 4) ntiles = (int)((nblocks + cfg.nw - 1) / cfg.nw);   // A/B: fixed full tiles
+    // small problems: one 32-pattern block per CTA, its categories split over the CTA's warps (k_walk_n20_mma<.., CSP>): a
+    // traversal's latency drops by min(C, 4); worth it only while every block still gets its own resident CTA
+    const bool csp = !mix && e->C >= 2 && e->kernel_variant == 0 && cfg.nw == 4 && nblocks <= slots;
+    if (csp) ntiles = (int)nblocks;
     const int grid = (int)std::min<long long>(ntiles, slots);
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {
         const bool safe = e->cfg.safe_numeric != 0;
         void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter, (void *)&ntiles};
-        CK(cudaLaunchKernel(cfg.f[(mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(tile_ptn), args, smem, e->stream));
+        CK(cudaLaunchKernel(csp ? walk20_csp[safe ? 1 : 0] : cfg.f[(mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(tile_ptn), args, smem, e->stream));
     }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;

@@ -889,9 +889,13 @@ struct Walk20Op {   // per-(op, class block), per-lane addressing state of the M
 };
 
 // DBG (diagnosis builds only, results are wrong): bit 0 no CLV stores, bit 1 no CLV loads, bit 2 DMMAs replaced by one DFMA
-template <bool SAFE, bool MIX, int NCASE, int BSM, int DBG = 0>
-__device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, const double (&Be_r)[5][3], const double (&Bi_r)[5][3],
-                                              const double *s_exp, const double *s_tabA, const double *s_tabB, int lane) {
+// CSP (category split, small problems): the warp processes categories 0, cstep, 2*cstep, ... (C of them) of a CLV whose other
+// categories belong to the CTA's other warps; the NORM_LH underflow decision, which spans all categories of a pattern, is then
+// taken after a CTA barrier by walk20_csplit_finish — here the warp only leaves its running maximum in shared memory.
+template <bool SAFE, bool MIX, int NCASE, int BSM, int DBG = 0, bool CSP = false>
+__device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, const Walk20Op &W, const double (&Be_r)[5][3],
+                                              const double (&Bi_r)[5][3], const double *s_expA, const double *s_expB,
+                                              const double *s_tabA, const double *s_tabB, const int TS, int lane) {
     // BSM bit 0 / bit 1: the evec / inv_evec B fragments are read from shared memory at each use (one conflict-free 8-byte
     // load per lane and DMMA) instead of living in 30 registers each
     const BFrag20<(BSM & 1) != 0> Be{Be_r, W.sBe};
@@ -900,14 +904,14 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
     auto MMA = [](double &d0, double &d1, double a, double b) {
         if (DBG & 4) { d0 = fma(a, b, d0); d1 += d0; } else dmma_m8n8k4(d0, d1, a, b);
     };
-    const int B = C * 20, TS = tab20_stride(C);   // C = categories of this class block
-    const double *eA = s_exp + 2 * q, *eB = s_exp + B + 2 * q;
+    const double *eA = s_expA + 2 * q, *eB = s_expB + 2 * q;
+    const int c20 = cstep * 20, cclv = cstep * kClv20Step, csc = cstep * kWarp;   // strides between the warp's categories
     const int lo2 = (q * 8 + g) * 2;               // the lane's pair inside a 64-double state tile
     const int lot = 128 + g * 4 + 2 * q;           // store position of the tail pair (lanes q < 2)
     // Software pipeline over the 4*C (M-tile, category) steps — consecutive in memory, 160 doubles each: the raw CLV
     // fragments of step s+1 are in flight while step s runs its MMAs.
-    const int step_c = kClv20Step;                                // next category, same M-tile
-    const int step_m = (W.Ctot - (C - 1)) * kClv20Step;           // category 0 of this class block in the next M-tile
+    const int step_c = cclv;                                      // next category of this warp, same M-tile
+    const int step_m = W.Ctot * kClv20Step - (C - 1) * cclv;      // its first category in the next M-tile
     double nA[5], nB[5];
     const double *pfA = W.Aq, *pfB = W.Bq;               // fetch cursors
     int pf_c = 0, pf_left = 4 * C;                        // category of the fetch cursor, steps still to fetch
@@ -956,14 +960,14 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
         // exp(eval_i r_c t) for the lane's five K-slots (clv_k order): two 16-byte and one 8-byte shared-memory load per child
         double fA[5], fB[5];
         if (NCASE == 2) {
-            const double2 e0 = *reinterpret_cast<const double2 *>(eA + c * 20), e1 = *reinterpret_cast<const double2 *>(eA + c * 20 + 8);
+            const double2 e0 = *reinterpret_cast<const double2 *>(eA + c * c20), e1 = *reinterpret_cast<const double2 *>(eA + c * c20 + 8);
             fA[0] = nA[0] * e0.x; fA[1] = nA[1] * e0.y; fA[2] = nA[2] * e1.x; fA[3] = nA[3] * e1.y;
-            fA[4] = nA[4] * eA[c * 20 + 16 - q];    // eA carries +2q: element 16 + q
+            fA[4] = nA[4] * eA[c * c20 + 16 - q];    // eA carries +2q: element 16 + q
         }
         if (NCASE >= 1) {
-            const double2 e0 = *reinterpret_cast<const double2 *>(eB + c * 20), e1 = *reinterpret_cast<const double2 *>(eB + c * 20 + 8);
+            const double2 e0 = *reinterpret_cast<const double2 *>(eB + c * c20), e1 = *reinterpret_cast<const double2 *>(eB + c * c20 + 8);
             fB[0] = nB[0] * e0.x; fB[1] = nB[1] * e0.y; fB[2] = nB[2] * e1.x; fB[3] = nB[3] * e1.y;
-            fB[4] = nB[4] * eB[c * 20 + 16 - q];
+            fB[4] = nB[4] * eB[c * c20 + 16 - q];
         }
         fetch(nA, nB);   // step s+1
         double a[3][2], b[3][2];
@@ -973,7 +977,7 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
         } else {
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
-                const double2 t = *reinterpret_cast<const double2 *>(tA + c * 20 + 8 * nt);   // nt = 2, q >= 2: row padding
+                const double2 t = *reinterpret_cast<const double2 *>(tA + c * c20 + 8 * nt);   // nt = 2, q >= 2: row padding
                 a[nt][0] = t.x; a[nt][1] = t.y;
             }
         }
@@ -983,7 +987,7 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
         } else {
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
-                const double2 t = *reinterpret_cast<const double2 *>(tB + c * 20 + 8 * nt);
+                const double2 t = *reinterpret_cast<const double2 *>(tB + c * c20 + 8 * nt);
                 b[nt][0] = t.x; b[nt][1] = t.y;
             }
         }
@@ -1020,23 +1024,27 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
             chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
             unsigned sc = 0;
-            if (NCASE == 2) sc += W.Asc[c * kWarp + 8 * mt];
-            if (NCASE >= 1) sc += W.Bsc[c * kWarp + 8 * mt];
+            if (NCASE == 2) sc += W.Asc[c * csc + 8 * mt];
+            if (NCASE >= 1) sc += W.Bsc[c * csc + 8 * mt];
             if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && chi < kThresholdHi) {
 #pragma unroll
                 for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
                 sc += 1;
             }
-            if (q == 0) W.Osc[c * kWarp + 8 * mt] = (uint16_t)sc;
+            if (q == 0) W.Osc[c * csc + 8 * mt] = (uint16_t)sc;
         } else mhi = max(mhi, chi);   // the pattern's other three lanes are folded in once per M-tile
-        double *po = pO + c * kClv20Step;
+        double *po = pO + c * cclv;
         if (!(DBG & 1) || out[0][0] == 1.2345e-300) {
         *reinterpret_cast<double2 *>(po + lo2) = make_double2(out[0][0], out[0][1]);
         *reinterpret_cast<double2 *>(po + 64 + lo2) = make_double2(out[1][0], out[1][1]);
         if (q < 2) *reinterpret_cast<double2 *>(po + lot) = make_double2(out[2][0], out[2][1]);
         }
         if (++c == C) {   // last category of this M-tile
-            if (!SAFE) {
+            if (!SAFE && CSP) {
+                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
+                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
+                W.s_mhi[mt * kWarp + lane] = mhi;   // this warp's slot; the decision follows the barrier
+            } else if (!SAFE) {
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
                 if (MIX) {   // fold in the classes walked before this one (each lane owns its slot: no synchronisation)
@@ -1071,6 +1079,41 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const Walk20Op &W, co
     }
 }
 
+// category split, NORM_LH: after the barrier every warp folds the CTA's maxima (all categories of the pattern), rescales what IT
+// wrote if the pattern underflowed (tree/phylokernelnew.h:2015-2029) and warp 0 writes the pattern's scale count
+__device__ __forceinline__ void walk20_csplit_finish(const Walk20Op &W, const int C, const int cstep, const int ncase, const int nwarps,
+                                                     const unsigned *s_mhi_all, const int warp, const int lane) {
+    const int g = lane >> 2, q = lane & 3;
+    (void)g;
+    const int lo2 = (q * 8 + (lane >> 2)) * 2, lot = 128 + (lane >> 2) * 4 + 2 * q;
+    for (int mt = 0; mt < 4; mt++) {
+        unsigned mhi = 0;
+        for (int w = 0; w < nwarps; w++) mhi = max(mhi, s_mhi_all[(w * 4 + mt) * kWarp + lane]);
+        const bool scale = ncase != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi;
+        if (scale) {
+            double *pc = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
+            for (int j = 0; j < C; j++, pc += cstep * kClv20Step) {
+                double2 *p0 = reinterpret_cast<double2 *>(pc + lo2), *p1 = reinterpret_cast<double2 *>(pc + 64 + lo2);
+                double2 v0 = *p0, v1 = *p1;
+                v0.x *= kTwo256; v0.y *= kTwo256; v1.x *= kTwo256; v1.y *= kTwo256;
+                *p0 = v0; *p1 = v1;
+                if (q < 2) {
+                    double2 *p2 = reinterpret_cast<double2 *>(pc + lot);
+                    double2 v2 = *p2;
+                    v2.x *= kTwo256; v2.y *= kTwo256;
+                    *p2 = v2;
+                }
+            }
+        }
+        if (warp == 0 && q == 0) {
+            unsigned sc = scale ? 1u : 0u;
+            if (ncase == 2) sc += W.Asc[8 * mt];
+            if (ncase >= 1) sc += W.Bsc[8 * mt];
+            W.Osc[8 * mt] = (uint16_t)sc;
+        }
+    }
+}
+
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
@@ -1089,15 +1132,16 @@ __device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, 
 // BSM the evec (bit 0) / inv_evec (bit 1) B fragments come from shared memory (7.7 KB per CTA) instead of 2 x 30 registers;
 // MINB minimum resident CTAs per SM (register cap).  Warps whose 32 patterns lie beyond Ppad (a multiple of 128, not of
 // 32*NW) idle through the barriers.
-template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0>
+template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0, bool CSP = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter,
                                                                  int ntiles) {
+    static_assert(!(CSP && MIX), "category split serves single-class models");
     constexpr int NT = NW * 32;
     // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
     // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
     extern __shared__ __align__(16) double s_dyn20[];
     __shared__ long long s_item;
-    __shared__ unsigned s_mhi[MIX ? 4 * NT : 1];
+    __shared__ unsigned s_mhi[(MIX || CSP) ? 4 * NT : 1];
     __shared__ __align__(16) double s_B[BSM ? (MIX ? 2 : 1) * 960 : 2];   // [buffer][evec | inv_evec][kt][nt][lane]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int nblk = MIX ? D.nmix : 1, cpb = D.C / nblk;   // class blocks per op, categories per block
@@ -1140,9 +1184,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
         __syncthreads();
         const long long tile = s_item;
         if (tile >= ntiles) break;
-        const long long b0 = tile * nblocks / ntiles, b1 = (tile + 1) * nblocks / ntiles;
-        const long long p0 = (b0 + warp) * 32;                   // first pattern of this warp (multiple of 32)
-        const bool active = b0 + warp < b1;
+        // CSP (small problems: fewer 32-pattern blocks than resident CTAs): a tile is ONE block and the CTA's warps split its
+        // categories (warp w takes w, w+NW, ...), so that a traversal's latency drops by the number of categories in flight
+        const long long b0 = CSP ? tile : tile * nblocks / ntiles, b1 = CSP ? tile + 1 : (tile + 1) * nblocks / ntiles;
+        const long long p0 = CSP ? b0 * 32 : (b0 + warp) * 32;   // first pattern of this warp (multiple of 32)
+        const int csp_ncat = CSP ? (D.C - warp + NW - 1) / NW : 0;   // categories of this warp
+        const bool active = CSP ? csp_ncat > 0 : b0 + warp < b1;
         const long long wbase = (p0 >> 5) * (long long)D.B * kWarp;   // the warp's 32-pattern block inside a CLV
         const long long sbase = SAFE ? (p0 >> 5) * (long long)D.C * kWarp : p0;
         unsigned may_mask = 0;
@@ -1184,24 +1231,32 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
             if (active) {
                 const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
                 const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
-                const int class_off = m * cpb * kClv20Step;
+                const int class_off = CSP ? warp * kClv20Step : m * cpb * kClv20Step;
                 Walk20Op W;
                 W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + class_off;   // only dereferenced when internal
                 W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + class_off;
                 W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + class_off;
-                const int sc_off = SAFE ? m * cpb * kWarp : 0;
+                const int sc_off = SAFE ? (CSP ? warp : m * cpb) * kWarp : 0;
                 W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + sc_off + g;
                 W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + sc_off + g;
                 W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + sc_off + g;
                 W.may_mask = may_mask;
                 W.stA = stA; W.stB = stB;
                 W.first_class = m == 0; W.last_class = m + 1 == nblk;
-                W.class_off = class_off; W.Ctot = D.C; W.s_mhi = s_mhi;
+                W.class_off = class_off; W.Ctot = D.C; W.s_mhi = CSP ? s_mhi + warp * 4 * kWarp : s_mhi;
                 W.sBe = s_B + (MIX ? (v & 1) * 960 : 0) + lane;
                 W.sBi = W.sBe + 480;
-                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
-                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
-                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG>(cpb, W, Be, Bi, s_exp, s_tabA, s_tabB, lane);
+                const int nc = CSP ? csp_ncat : cpb, cstep = CSP ? NW : 1, coff = CSP ? warp * 20 : 0;
+                const double *eAp = s_exp + coff, *eBp = s_exp + B + coff, *tAp = s_tabA + coff, *tBp = s_tabB + coff;
+                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
+                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
+                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
+                if (CSP && !SAFE) {
+                    __syncthreads();   // every warp of the CTA is active or has no category at all (D.C < NW): see below
+                    walk20_csplit_finish(W, nc, cstep, ncase, D.C < NW ? D.C : NW, s_mhi, warp, lane);
+                }
+            } else if (CSP && !SAFE) {
+                __syncthreads();
             }
             if (MIX && ++m == nblk) m = 0;
         }

@@ -105,7 +105,11 @@ class RefTree:
             lib().iqref_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:   # interpreter shutdown: module globals may already be gone
+            pass
 
     def info(self):
         out = (C.c_int32 * 6)()
