@@ -1211,7 +1211,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
                 for (int mt = 0; mt < 4; mt++) sB |= (unsigned)D.tips[(long long)hd.w * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
             }
         };
+        // headers travel TWO blocks ahead: block v+1's header steers the copy and the tip-state loads issued right after the
+        // barrier of block v, so it must already sit in registers there (loaded one block ahead it exposed an L2 round trip
+        // per op: the long-scoreboard stalls of the per-op code in the ncu source view)
         int4 h_next = *reinterpret_cast<const int4 *>(stage);
+        int4 h_next2 = nvo > 1 ? *reinterpret_cast<const int4 *>(stage + stage_sz) : h_next;
         stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid, NT);
         unsigned stA_next, stB_next;
         tip_states(h_next, stA_next, stB_next);
@@ -1220,7 +1224,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
             double *sb = s_dyn20 + (size_t)(v & 1) * stage_sz;
             const int4 h = h_next;
             const unsigned stA = stA_next, stB = stB_next;
-            if (v + 1 < nvo) h_next = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 1) * stage_sz);
+            h_next = h_next2;
+            if (v + 2 < nvo) h_next2 = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 2) * stage_sz);
             if (MIX) { if (BSM != 3) load_frags(m); if (BSM) load_frags_smem(m, v & 1); }
             cp_async_wait_all();
             __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
