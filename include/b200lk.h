@@ -70,7 +70,9 @@ typedef struct b200lk_child {
  * (slot dst_slot) from the two children in neighbour order. echildren / partial_lh_leaves are built on device. */
 typedef struct b200lk_op {
     int32_t dst_slot;
-    int32_t reserved;
+    int32_t reserved; /* 0 for a bifurcating node; k > 0: a multifurcating node (node->degree() > 3,
+                         tree/phylokernelnew.h:1407-1631) whose third ... (k+2)-th children, in neighbour order, are the next k
+                         entries of the array handed to b200lk_set_extra_children */
     b200lk_child left, right;
 } b200lk_op;
 
@@ -112,6 +114,9 @@ int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat
 /* computePartialLikelihood over a traversal_info list in post-order
  * (computeTraversalInfo<VC>(node, dad, compute_partial_lh=true), tree/phylokernelnew.h:1150-1281, 1289-2039) */
 int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops);
+/* the extra children of the multifurcating ops of the NEXT call that takes an op list, in op order (copied; consumed by
+ * that call).  Op lists with multifurcating nodes run on the thread-per-pattern kernel. */
+int b200lk_set_extra_children(b200lk_engine *e, const b200lk_child *children, int32_t n);
 
 /* computeLikelihoodBranch(dad_branch, dad, save_log_value) (tree/phylokernelnew.h:2641-3223): flush `ops`, then the
  * branch between CLV slot `node_slot` and the other end (dad_kind 0: leaf `dad_id`; 1: slot `dad_id`).

@@ -67,6 +67,9 @@ struct b200lk_engine {
     long long boot_stride = 0;
     size_t boot_bytes = 0;
     int newton_grid = 0;   // co-resident CTAs of k_newton_coop
+    std::vector<b200lk_child> extra_children;   // b200lk_set_extra_children: consumed by the next call that takes ops
+    MultiChild *d_mchild = nullptr;
+    bool has_multi = false;
     int pending = 0, pending_marks = 0;   // results queued by b200lk_enqueue_*, collected by b200lk_finish
     std::string err;
 };
@@ -113,7 +116,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_boot); cudaFree(e->d_rell);
+    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -234,6 +237,12 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
     return 0;
 }
 
+extern "C" int b200lk_set_extra_children(b200lk_engine *e, const b200lk_child *children, int32_t n) {
+    if (n < 0 || (n > 0 && !children)) return fail(e, B200LK_ERR_INVALID, "set_extra_children: invalid arguments");
+    e->extra_children.assign(children, children + n);
+    return 0;
+}
+
 extern "C" int b200lk_set_reference_quirks(b200lk_engine *e, int32_t mask) {
     if (mask & ~B200LK_QUIRK_DOTTRIPLE_ODD) return fail(e, B200LK_ERR_INVALID, "unknown quirk bit");
     e->d.quirks = mask;
@@ -325,15 +334,18 @@ static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
     }
     if (nops > e->ops_cap) {
         CK(cudaStreamSynchronize(e->stream));
-        cudaFree(e->d_ops); cudaFree(e->d_jobs);
+        cudaFree(e->d_ops); cudaFree(e->d_jobs); cudaFree(e->d_mchild);
         if (e->h_stage) cudaFreeHost(e->h_stage);
-        e->d_ops = nullptr; e->d_jobs = nullptr; e->h_stage = nullptr;
+        e->d_ops = nullptr; e->d_jobs = nullptr; e->h_stage = nullptr; e->d_mchild = nullptr;
         size_t cap = std::max<size_t>(nops, 16);
         int rc = dev_alloc(e, &e->d_ops, cap);
         if (rc) return rc;
         rc = dev_alloc(e, &e->d_jobs, cap * 2);
         if (rc) return rc;
-        e->h_stage_cap = cap * (sizeof(DevOp) + 2 * sizeof(ChildJob));
+        rc = dev_alloc(e, &e->d_mchild, cap * 2);
+        if (rc) return rc;
+        e->d.mchild = e->d_mchild;
+        e->h_stage_cap = cap * (sizeof(DevOp) + 2 * sizeof(ChildJob) + 2 * sizeof(MultiChild));
         CK(cudaMallocHost(&e->h_stage, e->h_stage_cap));
         e->ops_cap = cap;
     }
@@ -344,7 +356,7 @@ template <bool SAFE>
 static void launch_partials(b200lk_engine *e, int op_begin, int op_end, int walk, int grid) {
     const int n = e->cfg.nstates, C = e->C;
     cudaMemsetAsync(e->d_counter, 0, sizeof(unsigned long long), e->stream);
-    if (n == 4 && C == 4 && e->cfg.nmix == 1 && e->cfg.state_unknown < kMaxLeafRows4)
+    if (n == 4 && C == 4 && e->cfg.nmix == 1 && e->cfg.state_unknown < kMaxLeafRows4 && !e->has_multi)
         k_partials_n4c4<SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
     else if (n == 4)
         k_partials_generic<4, SAFE><<<grid, kTile, 0, e->stream>>>(e->d, e->d_ops, op_begin, op_end, walk, e->d_counter);
@@ -545,14 +557,25 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
 // Enqueue (no sync) everything computePartialLikelihood needs for the op list.
 static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     if (nops <= 0) return 0;
-    int rc = ensure_op_capacity(e, nops);
+    // multifurcating ops (reserved = number of children beyond left/right, taken in op order from b200lk_set_extra_children)
+    int nextra = 0;
+    for (int k = 0; k < nops; k++) {
+        if (ops[k].reserved < 0) return fail(e, B200LK_ERR_INVALID, "op: negative number of extra children");
+        nextra += ops[k].reserved;
+    }
+    if (nextra > (int)e->extra_children.size()) return fail(e, B200LK_ERR_INVALID, "multifurcating ops: not enough extra children set (b200lk_set_extra_children)");
+    const std::vector<b200lk_child> extra(e->extra_children.begin(), e->extra_children.begin() + nextra);
+    e->extra_children.clear();
+    int rc = ensure_op_capacity(e, (size_t)nops + (nextra + 1) / 2);
     if (rc) return rc;
-    if (use_walk4(e)) return enqueue_walk4(e, ops, nops);
-    if (use_walk20(e)) return enqueue_walk20(e, ops, nops);
+    if (nextra == 0 && use_walk4(e)) return enqueue_walk4(e, ops, nops);
+    if (nextra == 0 && use_walk20(e)) return enqueue_walk20(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
     DevOp *hops = (DevOp *)e->h_stage;
     ChildJob *hjobs = (ChildJob *)((char *)e->h_stage + e->ops_cap * sizeof(DevOp));
+    MultiChild *hmc = (MultiChild *)((char *)hjobs + e->ops_cap * 2 * sizeof(ChildJob));
+    int xcur = 0, nmc = 0;   // cursor into `extra`, MultiChild records written
     // the pinned staging buffer may still be in flight from the previous call on this stream
     CK(cudaStreamSynchronize(e->stream));
     // level_of_slot: level of the latest writer; last_touch: highest level of any op that has read or written the slot.
@@ -583,15 +606,37 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
         if (ch[0].kind != 0 && ch[1].kind == 0) { a = 1; b = 0; }
         DevOp &d = hops[k];
         d.dst = op.dst_slot;
+        d.nchild = 2; d.pad_ = 0; d.mc_off = 0;
         d.ncase = (ch[a].kind == 0 && ch[b].kind == 0) ? 0 : (ch[a].kind == 0 ? 1 : 2);
+        std::vector<b200lk_child> more;
+        if (op.reserved > 0) {   // multifurcating node: all children in neighbour order (phylokernelnew.h:1407-1631)
+            d.ncase = 3;
+            d.nchild = 2 + op.reserved;
+            d.mc_off = nmc;
+            for (int s = 0; s < 2; s++) hmc[nmc++] = MultiChild{ch[s].kind, ch[s].id, eoff[s], ch[s].kind == 0 ? loff[s] : -1};
+            for (int x = 0; x < op.reserved; x++) {
+                const b200lk_child &c = extra[xcur];
+                if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
+                else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
+                else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+                const int64_t eo = (int64_t)((size_t)nops * 2 * (e_sz + leaf_sz) + (size_t)xcur * (e_sz + leaf_sz));
+                ChildJob &j = hjobs[2 * nops + xcur];
+                j.length = c.length; j.e_off = eo; j.leaf_off = c.kind == 0 ? eo + (int64_t)e_sz : -1;
+                hmc[nmc++] = MultiChild{c.kind, c.id, j.e_off, j.leaf_off};
+                more.push_back(c);
+                xcur++;
+            }
+        }
         d.lid = ch[a].id; d.rid = ch[b].id;
         d.eL = eoff[a]; d.eR = eoff[b];
         d.leafL = ch[a].kind == 0 ? loff[a] : -1;
         d.leafR = ch[b].kind == 0 ? loff[b] : -1;
         int lv = 0;
         for (auto &c : ch) if (c.kind == 1 && level_of_slot[c.id] >= 0) lv = std::max(lv, level_of_slot[c.id] + 1);
+        for (auto &c : more) if (c.kind == 1 && level_of_slot[c.id] >= 0) lv = std::max(lv, level_of_slot[c.id] + 1);
         lv = std::max(lv, last_touch[op.dst_slot] + 1);
         for (auto &c : ch) if (c.kind == 1) last_touch[c.id] = std::max(last_touch[c.id], lv);
+        for (auto &c : more) if (c.kind == 1) last_touch[c.id] = std::max(last_touch[c.id], lv);
         level[k] = lv;
         level_of_slot[op.dst_slot] = lv;
         last_touch[op.dst_slot] = lv;
@@ -616,8 +661,10 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
         level_start.push_back(nops);
     }
     CK(cudaMemcpyAsync(e->d_ops, hops, sizeof(DevOp) * nops, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaMemcpyAsync(e->d_jobs, hjobs, sizeof(ChildJob) * 2 * nops, cudaMemcpyHostToDevice, e->stream));
-    k_partial_info<<<2 * nops, 256, sizeof(double) * e->B, e->stream>>>(e->d, e->d_jobs);
+    CK(cudaMemcpyAsync(e->d_jobs, hjobs, sizeof(ChildJob) * (2 * nops + nextra), cudaMemcpyHostToDevice, e->stream));
+    if (nmc) CK(cudaMemcpyAsync(e->d_mchild, hmc, sizeof(MultiChild) * nmc, cudaMemcpyHostToDevice, e->stream));
+    e->has_multi = nmc > 0;
+    k_partial_info<<<2 * nops + nextra, 256, sizeof(double) * e->B, e->stream>>>(e->d, e->d_jobs);
     e->launches++;
     e->last_launch[0]++;
     const long long ntiles = e->Ppad / kTile;

@@ -21,13 +21,21 @@ constexpr double kTwo256 = 0x1p256;                          // ldexp(x, SCALING
 
 // one TraversalInfo after host-side normalisation (a single leaf child is always `left`,
 // tree/phylokernelnew.h:1395-1405)
+struct MultiChild {   // one child of a multifurcating node (all of its children, in neighbour order)
+    int32_t kind, id;     // 0 = tip (taxon row), 1 = CLV slot
+    int64_t e_off;        // echild[c][x][i] block inside opinfo
+    int64_t leaf_off;     // partial_lh_leaves table inside opinfo, -1 for an internal child
+};
+
 struct DevOp {
     int32_t dst;     // destination CLV slot
-    int32_t ncase;   // 0 tip-tip, 1 tip-inner, 2 inner-inner
+    int32_t ncase;   // 0 tip-tip, 1 tip-inner, 2 inner-inner, 3 multifurcating (children in Dev::mchild[mc_off .. mc_off+nchild))
     int32_t lid;     // taxon row (tip) or slot
     int32_t rid;
     int64_t eL, eR;        // offsets (in doubles) of echild[c][x][i] blocks inside opinfo
     int64_t leafL, leafR;  // offsets of partial_lh_leaves[state][c][x] tables, -1 if the child is internal
+    int32_t nchild, pad_;
+    int64_t mc_off;
 };
 
 struct ChildJob {
@@ -51,6 +59,7 @@ struct Dev {
     double *opinfo;
     double *theta, *buffer_scale, *pattern_lh, *pattern_scaling, *pattern_lh_cat;
     double *val;             // val0 | val1 | val2, B doubles each
+    const MultiChild *mchild;   // children of the multifurcating ops of the current call
 };
 
 __device__ __forceinline__ long long pbase(long long p, int width) {
@@ -320,6 +329,78 @@ __device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op
     }
 }
 
+// Multifurcating node (node->degree() > 3, tree/phylokernelnew.h:1407-1631): the running product over the children lives in the
+// ORIGINAL state space, the 2^-256 test follows EVERY child on that product (:1557-1605), the inverse-eigenvector transform
+// comes last without a further test (:1610-1628).  The destination CLV itself is the workspace for the running product.
+template <int NT, bool SAFE>
+__device__ __forceinline__ void process_op_multi(const Dev &D, const DevOp &op, long long p) {
+    constexpr int NMAX = NT ? NT : 64;
+    const int n = NT ? NT : D.n;
+    const int C = D.C;
+    const ClvIdx at(D, p);
+    const long long sb = SAFE ? pbase(p, C) : p;
+    double *out = D.partial + (long long)op.dst * D.slot_stride;
+    uint16_t *osc = D.scale + (long long)op.dst * D.scale_stride + sb;
+    const bool may = D.invar[p] == 0.0;
+    for (int c = 0; c < C; c++) {
+        for (int x = 0; x < n; x++) out[at(c, x)] = 1.0;
+        if (SAFE) osc[c * kWarp] = 0;
+    }
+    unsigned norm_scale = 0;
+    double lv[NMAX];
+    for (int k = 0; k < op.nchild; k++) {
+        const MultiChild ch = D.mchild[op.mc_off + k];
+        const double *leaf = nullptr, *Lp = nullptr;
+        const uint16_t *csc = nullptr;
+        if (ch.kind == 0) leaf = D.opinfo + ch.leaf_off + (long long)D.tips[(long long)ch.id * D.Ppad + p] * D.B;
+        else {
+            Lp = D.partial + (long long)ch.id * D.slot_stride;
+            csc = D.scale + (long long)ch.id * D.scale_stride + sb;
+            if (!SAFE) norm_scale += csc[0];
+        }
+        double lh_max = 0.0;
+        for (int c = 0; c < C; c++) {
+            double cmax = 0.0;
+            if (Lp) {
+                for (int i = 0; i < n; i++) lv[i] = Lp[at(c, i)];
+                const double *ep = D.opinfo + ch.e_off + (long long)c * n * n;
+                for (int x = 0; x < n; x++) {
+                    double v = __ldg(ep + x * n) * lv[0];   // :1542-1546: sequential mul_add
+                    for (int i = 1; i < n; i++) v = fma(__ldg(ep + x * n + i), lv[i], v);
+                    const double r = out[at(c, x)] * v;
+                    out[at(c, x)] = r;
+                    cmax = fmax(cmax, fabs(r));
+                }
+            } else {
+                for (int x = 0; x < n; x++) {
+                    const double r = out[at(c, x)] * leaf[c * n + x];
+                    out[at(c, x)] = r;
+                    cmax = fmax(cmax, fabs(r));
+                }
+            }
+            if (SAFE) {
+                unsigned sc = osc[c * kWarp] + (csc ? csc[c * kWarp] : 0u);
+                if (may && cmax < kScalingThreshold) {
+                    for (int x = 0; x < n; x++) out[at(c, x)] *= kTwo256;
+                    sc += 1;
+                }
+                osc[c * kWarp] = (uint16_t)sc;
+            } else lh_max = fmax(lh_max, cmax);
+        }
+        if (!SAFE && may && lh_max < kScalingThreshold) {
+            for (int c = 0; c < C; c++)
+                for (int x = 0; x < n; x++) out[at(c, x)] *= kTwo256;
+            norm_scale += 1;
+        }
+    }
+    if (!SAFE) osc[0] = (uint16_t)norm_scale;
+    for (int c = 0; c < C; c++) {
+        const double *inv = D.inv_evec + (long long)(c / D.denom) * n * n;
+        for (int x = 0; x < n; x++) lv[x] = out[at(c, x)];
+        for (int i = 0; i < n; i++) out[at(c, i)] = dot4acc<NT>(inv + i * n, lv, n);
+    }
+}
+
 template <int NT, bool SAFE>
 __global__ void __launch_bounds__(kTile) k_partials_generic(Dev D, const DevOp *ops, int op_begin, int op_end, int walk,
                                                             unsigned long long *counter) {
@@ -328,7 +409,10 @@ __global__ void __launch_bounds__(kTile) k_partials_generic(Dev D, const DevOp *
     WorkItem w;
     while (next_item(counter, &s_item, ntiles, op_begin, op_end, walk, w)) {
         const long long p = w.tile * kTile + threadIdx.x;
-        for (int o = w.o0; o < w.o1; o++) process_op_generic<NT, SAFE>(D, ops[o], p);
+        for (int o = w.o0; o < w.o1; o++) {
+            if (ops[o].ncase == 3) process_op_multi<NT, SAFE>(D, ops[o], p);
+            else process_op_generic<NT, SAFE>(D, ops[o], p);
+        }
     }
 }
 
@@ -1369,7 +1453,7 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
                                                 unsigned *ticket, double *result, double length, int fuse_vals) {
     extern __shared__ double s_vals_dyn[];
     const double *vals = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
-    const int n = D.n, C = D.C, B = D.B;
+    const int n = D.n, C = D.C;
     const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
     const long long cb = pbase(p, C);
     const long long sb = SAFE ? cb : p;

@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
-    "b200lk_set_boot_samples", "b200lk_rell",
+    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -229,6 +229,11 @@ class LikelihoodEngine:
 
     def get_pattern_lh(self):
         return self._get("b200lk_get_pattern_lh", self.nptn)
+
+    def set_extra_children(self, children):
+        """third, fourth ... children of the multifurcating ops (op['pad'] = their number) of the NEXT call, in op order"""
+        ch = np.ascontiguousarray(children)
+        self._check(self.lib.b200lk_set_extra_children(self._h, ch.ctypes.data_as(C.c_void_p), C.c_int32(len(ch))))
 
     def set_boot_samples(self, boot_samples):
         """UFBoot: resampled pattern frequencies [nboot][nptn] (float32), kept resident on the device."""

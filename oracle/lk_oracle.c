@@ -47,7 +47,9 @@ typedef struct {
 } orc_config;
 
 typedef struct { int32_t kind; int32_t id; double length; } orc_child; /* kind 0 = tip (id = taxon), 1 = slot */
-typedef struct { int32_t dst_slot; int32_t pad_; orc_child left, right; } orc_op;
+/* nextra > 0: a multifurcating node (node->degree() > 3, phylokernelnew.h:1407-1631): its third, fourth ... children in
+ * neighbour order are taken, in op order, from the array handed to orc_set_extra_children before the call */
+typedef struct { int32_t dst_slot; int32_t nextra; orc_child left, right; } orc_op;
 
 typedef struct {
     orc_config cfg;
@@ -61,6 +63,8 @@ typedef struct {
     double *theta, *buffer_scale_all, *pattern_lh, *pattern_lh_cat, *pattern_scaling;
     int theta_computed;
     int quirks; /* orc_set_reference_quirks */
+    orc_child *extra; /* pending extra children of multifurcating ops (consumed by the next call that takes ops) */
+    int nextra;
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
     char err[256];
 } orc_engine;
@@ -311,7 +315,7 @@ void orc_destroy(orc_engine *e) {
     free(e->tips); free(e->ptn_freq); free(e->ptn_invar); free(e->eval); free(e->evec); free(e->inv_evec);
     free(e->mix_weight); free(e->cat_rate); free(e->cat_prop); free(e->tip_partial_lh); free(e->partial);
     free(e->scale); free(e->theta); free(e->buffer_scale_all); free(e->pattern_lh); free(e->pattern_scaling);
-    free(e->pattern_lh_cat); free(e);
+    free(e->pattern_lh_cat); free(e->extra); free(e);
 }
 
 const char *orc_last_error(orc_engine *e) { return e->err; }
@@ -432,12 +436,35 @@ typedef struct {
     double *echildren;    /* owns eleft+eright */
     double *leaves;       /* owns leaf tables */
     double *eleft, *eright, *leafL, *leafR;
+    /* multifurcating node: all children in neighbour order, echild / leaf table per child (NULL for internal children) */
+    int nchild;
+    orc_child *child;
+    double **mechild, **mleaf;
 } orc_opinfo;
 
 /* per-op precompute = computePartialInfo for one TraversalInfo (:1243-1260) */
+static void opinfo_init_multi(const orc_engine *e, const orc_op *op_in, const orc_child *extra, orc_opinfo *oi) {
+    int n = e->cfg.nstates, B = e->B;
+    size_t info_sz = (size_t)B * n, leaf_sz = (size_t)(e->cfg.state_unknown + 1) * B;
+    oi->op = *op_in;
+    oi->nchild = 2 + op_in->nextra;
+    oi->child = (orc_child *)malloc(sizeof(orc_child) * oi->nchild);
+    oi->child[0] = op_in->left; oi->child[1] = op_in->right;
+    for (int k = 0; k < op_in->nextra; k++) oi->child[2 + k] = extra[k];
+    oi->mechild = (double **)calloc(oi->nchild, sizeof(double *));
+    oi->mleaf = (double **)calloc(oi->nchild, sizeof(double *));
+    oi->echildren = oi->leaves = NULL;
+    for (int k = 0; k < oi->nchild; k++) {
+        oi->mechild[k] = (double *)malloc(sizeof(double) * info_sz);
+        if (oi->child[k].kind == 0) oi->mleaf[k] = (double *)malloc(sizeof(double) * leaf_sz);
+        partial_info_child(e, &oi->child[k], oi->mechild[k], oi->mleaf[k]);
+    }
+}
+
 static void opinfo_init(const orc_engine *e, const orc_op *op_in, orc_opinfo *oi) {
     int n = e->cfg.nstates, B = e->B;
     oi->op = *op_in;
+    oi->nchild = 2; oi->child = NULL; oi->mechild = oi->mleaf = NULL;
     size_t info_sz = (size_t)B * n;
     oi->echildren = (double *)malloc(sizeof(double) * 2 * info_sz);
     size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * B;
@@ -457,12 +484,79 @@ static void opinfo_init(const orc_engine *e, const orc_op *op_in, orc_opinfo *oi
         oi->leafL = oi->leafR; oi->leafR = NULL;
     }
 }
-static void opinfo_free(orc_opinfo *oi) { free(oi->echildren); free(oi->leaves); }
+static void opinfo_free(orc_opinfo *oi) {
+    free(oi->echildren); free(oi->leaves);
+    if (oi->child) {
+        for (int k = 0; k < oi->nchild; k++) { free(oi->mechild[k]); free(oi->mleaf[k]); }
+        free(oi->child); free(oi->mechild); free(oi->mleaf);
+    }
+}
 
 #define ORC_MAX_STATES 256
 
+/* multifurcating node, normal models — phylokernelnew.h:1407-1631: the running product over the children lives in the
+ * ORIGINAL state space (partial_lh_all), the 2^-256 test follows EVERY child (:1557-1605) on that product, and the
+ * inverse-eigenvector transform comes last without a further test (:1610-1628) */
+static void compute_partial_multi(orc_engine *e, const orc_opinfo *oi, size_t lo, size_t hi) {
+    int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric;
+    size_t P = (size_t)e->cfg.nptn, S = S_of(e);
+    double *dad_lh = e->partial + (size_t)oi->op.dst_slot * P * B;
+    uint16_t *dad_sc = e->scale + (size_t)oi->op.dst_slot * P * S;
+    double *all = (double *)malloc(sizeof(double) * B);
+    for (size_t p = lo; p < hi; p++) {
+        for (int i = 0; i < B; i++) all[i] = 1.0;
+        uint16_t *sc = dad_sc + p * S;
+        memset(sc, 0, sizeof(uint16_t) * S);
+        for (int k = 0; k < oi->nchild; k++) {
+            const orc_child *ch = &oi->child[k];
+            if (ch->kind == 0) {
+                const double *child_lh = oi->mleaf[k] + (size_t)tip_state(e, ch->id, p) * B;
+                for (int c = 0; c < B; c++) all[c] *= child_lh[c]; /* :1520-1523 */
+            } else {
+                const double *plc = e->partial + (size_t)ch->id * P * B + p * B;
+                const uint16_t *csc = e->scale + (size_t)ch->id * P * S + p * S;
+                if (!safe) sc[0] = (uint16_t)(sc[0] + csc[0]); /* :1529-1532 */
+                const double *ep = oi->mechild[k];
+                for (int c = 0; c < C; c++) {
+                    if (safe) sc[c] = (uint16_t)(sc[c] + csc[c]); /* :1536-1539 */
+                    for (int x = 0; x < n; x++) {
+                        double v = ep[0] * plc[c * n]; /* :1542-1546: sequential mul_add */
+                        for (int i = 1; i < n; i++) v = fma(ep[i], plc[c * n + i], v);
+                        ep += n;
+                        all[c * n + x] *= v;
+                    }
+                }
+            }
+            if (safe) { /* :1558-1580 */
+                for (int c = 0; c < C; c++) {
+                    double lh_max = 0.0;
+                    for (int x = 0; x < n; x++) lh_max = fmax(lh_max, fabs(all[c * n + x]));
+                    if (lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                        for (int x = 0; x < n; x++) all[c * n + x] = ldexp(all[c * n + x], SCALING_THRESHOLD_EXP);
+                        sc[c] += 1;
+                    }
+                }
+            } else { /* :1581-1603 */
+                double lh_max = 0.0;
+                for (int x = 0; x < B; x++) lh_max = fmax(lh_max, fabs(all[x]));
+                if (lh_max < SCALING_THRESHOLD && e->ptn_invar[p] == 0.0) {
+                    for (int x = 0; x < B; x++) all[x] = ldexp(all[x], SCALING_THRESHOLD_EXP);
+                    sc[0] += 1;
+                }
+            }
+        }
+        double *out = dad_lh + p * B;
+        for (int c = 0; c < C; c++) {
+            const double *inv = e->inv_evec + (size_t)(c / e->denom) * n * n;
+            prod_vec_mat(all + c * n, inv, out + c * n, NULL, n); /* :1622-1624 */
+        }
+    }
+    free(all);
+}
+
 /* one TraversalInfo over the pattern range [lo, hi) — the body of computePartialLikelihood(info, lo, hi, packet) */
 static void compute_partial_range(orc_engine *e, const orc_opinfo *oi, size_t lo, size_t hi) {
+    if (oi->child) { compute_partial_multi(e, oi, lo, hi); return; }
     int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric;
     size_t P = (size_t)e->cfg.nptn, S = S_of(e);
     const orc_op *op = &oi->op;
@@ -550,8 +644,22 @@ int orc_update_partials(orc_engine *e, const orc_op *ops, int nops) {
     if (nops <= 0) return 0;
     if (e->cfg.nstates > ORC_MAX_STATES) { snprintf(e->err, sizeof e->err, "nstates > %d", ORC_MAX_STATES); return -1; }
     orc_opinfo *info = (orc_opinfo *)malloc(sizeof(orc_opinfo) * nops);
+    /* extra children of multifurcating ops: consumed in op order */
+    int *xoff = (int *)malloc(sizeof(int) * (nops + 1));
+    xoff[0] = 0;
+    for (int k = 0; k < nops; k++) xoff[k + 1] = xoff[k] + (ops[k].nextra > 0 ? ops[k].nextra : 0);
+    if (xoff[nops] > e->nextra) {
+        snprintf(e->err, sizeof e->err, "multifurcating ops need %d extra children, %d set", xoff[nops], e->nextra);
+        free(xoff); free(info);
+        return -1;
+    }
 #pragma omp parallel for schedule(static) if (nops >= 3)
-    for (int k = 0; k < nops; k++) opinfo_init(e, &ops[k], &info[k]);
+    for (int k = 0; k < nops; k++) {
+        if (ops[k].nextra > 0) opinfo_init_multi(e, &ops[k], e->extra + xoff[k], &info[k]);
+        else opinfo_init(e, &ops[k], &info[k]);
+    }
+    free(xoff);
+    e->nextra = 0;
     size_t P = (size_t)e->cfg.nptn;
     long npacket = (long)((P + ORC_PACKET - 1) / ORC_PACKET);
 #pragma omp parallel for schedule(dynamic, 1)
@@ -754,6 +862,16 @@ static void build_theta(orc_engine *e, int node_slot, int dad_kind, int dad_id) 
 int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
 /* bit 0: reproduce dotProductTriple's double-counted last element for odd nstates x even block (see dot_triple) */
 int orc_set_reference_quirks(orc_engine *e, int mask) { e->quirks = mask; return 0; }
+
+int orc_set_extra_children(orc_engine *e, const orc_child *children, int n) {
+    free(e->extra);
+    e->extra = NULL; e->nextra = 0;
+    if (n <= 0) return 0;
+    e->extra = (orc_child *)malloc(sizeof(orc_child) * n);
+    memcpy(e->extra, children, sizeof(orc_child) * n);
+    e->nextra = n;
+    return 0;
+}
 
 /* computeLikelihoodDerv(Generic)SIMD — phylokernelnew.h:2233-2633 (joint branch length, no +ASC) */
 int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,

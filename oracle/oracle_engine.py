@@ -96,6 +96,11 @@ class OracleEngine:
         lib().orc_set_pattern_invar(self._h, _dp(f))
 
     # ---- compute ------------------------------------------------------------------------------
+    def set_extra_children(self, children):
+        """third, fourth ... children of the multifurcating ops (op['pad'] = their number) of the NEXT call, in op order"""
+        ch = np.ascontiguousarray(children)
+        lib().orc_set_extra_children(self._h, _dp(ch), C.c_int(len(ch)))
+
     def update_partials(self, ops):
         ops = np.ascontiguousarray(ops)
         rc = lib().orc_update_partials(self._h, _dp(ops), C.c_int(len(ops)))
