@@ -110,6 +110,15 @@ int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, c
 /* site_rate->getRate(c) / getProp(c) */
 int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop);
 
+/* +ASC, Lewis' ascertainment-bias correction (ModelFactory::ASC_type = ASC_VARIANT / ASC_INFORMATIVE;
+ * tree/phylokernelnew.h:3076-3091, 3198-3221, 2506-2535, 2618-2626, 3342-3356, 3412-3426): the LAST num_unobserved of the
+ * engine's nptn patterns are ModelFactory::unobserved_ptns (their ptn_freq is ignored, their ptn_invar is the caller's);
+ * nsite = aln->getNSite().  logL, _pattern_lh, df and ddf come back corrected.  asc_type 0 switches it off.  Holder's
+ * missing-data forms (ASC_*_MISSING) are not implemented: the call fails for them.  With pattern sharding the correction is
+ * not separable per rank (it needs the global prob_const): use one engine, or replicate the unobserved block and combine
+ * on the host. */
+int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
+
 /* ---- the five kernel entry points --------------------------------------------------------------------------- */
 /* computePartialLikelihood over a traversal_info list in post-order
  * (computeTraversalInfo<VC>(node, dad, compute_partial_lh=true), tree/phylokernelnew.h:1150-1281, 1289-2039) */

@@ -176,11 +176,11 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     TRY(dev_alloc(e, &e->d_pattern_lh, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_scaling, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_lh_cat, (size_t)Ppad * e->C));
-    TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 4));   // per-block partial sums: 3 values, or k_newton_coop's two buffers of 2
+    TRY(dev_alloc(e, &e->d_red, (size_t)(Ppad / kTile) * 5));   // per-block partial sums: up to 5 values (+ASC derivative pass); k_newton_coop: two buffers of 2
     TRY(dev_alloc(e, &e->d_ticket, 4));
     TRY(dev_alloc(e, &e->d_counter, 8));
 #undef TRY
-    if (cudaHostAlloc((void **)&e->h_result, 8 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
+    if (cudaHostAlloc((void **)&e->h_result, 16 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&e->d_result, e->h_result, 0) != cudaSuccess) { e->err = "cudaHostAlloc(mapped) failed"; return bail(B200LK_ERR_CUDA); }
     cudaMemsetAsync(e->d_ticket, 0, 4 * sizeof(unsigned), e->stream);
     cudaMemsetAsync(e->d_tips, cfg->state_unknown, (size_t)cfg->ntaxa * Ppad, e->stream);
@@ -193,6 +193,7 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     Dev &d = e->d;
     d.n = n; d.C = e->C; d.ncat = cfg->ncat; d.nmix = cfg->nmix; d.denom = e->denom; d.B = e->B; d.S = e->S;
     d.su = cfg->state_unknown; d.P = e->P; d.Ppad = Ppad;
+    d.asc = 0; d.Pobs = e->P; d.asc_nsite = 0;
     d.clv_f20 = (n == 20 && e->C % cfg->nmix == 0) ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
     d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
     d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
@@ -234,6 +235,18 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
     }
     if (schedule < 0 || schedule > 2) return fail(e, B200LK_ERR_INVALID, "schedule must be 0, 1 or 2");
     e->schedule = schedule;
+    return 0;
+}
+
+extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
+    if (asc_type < 0 || asc_type > 1) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE); Holder's missing-data forms are not implemented");
+    if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
+    cudaSetDevice(e->cfg.device);
+    CK(cudaStreamSynchronize(e->stream));
+    e->d.asc = asc_type;
+    e->d.Pobs = asc_type ? e->P - num_unobserved : e->P;
+    e->d.asc_nsite = nsite;
+    e->theta_computed = false;
     return 0;
 }
 
@@ -766,7 +779,13 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
-    if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    if (e->d.asc) {   // +ASC: (tree_lh, prob_const) into slots 8..9, then the correction
+        if (e->cfg.safe_numeric) k_root<true, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
+        else k_root<false, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
+        k_asc_finish_logl<<<std::min(nblocks, 296), 256, 0, e->stream>>>(e->d, e->d_result + 8, e->d_result);
+        e->launches += 1;
+        e->last_launch[1] += 1;
+    } else if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
     else k_root<false><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
     e->launches += 1;
     e->last_launch[1] += 1;
@@ -828,7 +847,12 @@ static void enqueue_derv(b200lk_engine *e, double length) {
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * 3 * e->B : 0;
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 1); e->launches++; e->last_launch[2]++; }
-    if (e->B == 16) k_derv<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
+    if (e->d.asc) {   // +ASC: (df, ddf, prob_const, df_const, ddf_const) into slots 10..14, then the correction
+        k_derv<0, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 10, length, fuse);
+        k_asc_finish_derv<<<1, 1, 0, e->stream>>>(e->d, e->d_result + 10, e->d_result + 1);
+        e->launches += 1;
+        e->last_launch[2] += 1;
+    } else if (e->B == 16) k_derv<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
     else if (e->B == 80) k_derv<80><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
     else k_derv<0><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
     e->launches += 1;
@@ -873,7 +897,12 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
-    if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
+    if (e->d.asc) {
+        k_from_buffer<0, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
+        k_asc_finish_logl<<<std::min(nblocks, 296), 256, 0, e->stream>>>(e->d, e->d_result + 8, e->d_result);
+        e->launches += 1;
+        e->last_launch[1] += 1;
+    } else if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
     else if (e->B == 80) k_from_buffer<80><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
     else k_from_buffer<0><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);
     e->launches += 1;
@@ -903,7 +932,7 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
-    if (e->B <= kFuseValsMaxB && e->kernel_variant != 9) {
+    if (e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc) {
         // the whole iteration in one cooperative launch (k_newton_coop); variant 9 keeps the host-driven loop below for A/B
         const void *kern = e->B == 16 ? (const void *)k_newton_coop<16> : e->B == 80 ? (const void *)k_newton_coop<80> : (const void *)k_newton_coop<0>;
         const size_t vsm = sizeof(double) * 3 * e->B;

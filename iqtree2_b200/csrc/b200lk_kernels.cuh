@@ -47,6 +47,8 @@ struct ChildJob {
 struct Dev {
     int n, C, ncat, nmix, denom, B, S, su;
     int quirks;              // B200LK_QUIRK_* (include/b200lk.h)
+    int asc;                 // +ASC: 1 = Lewis' correction; patterns [Pobs, P) are the unobserved constant patterns
+    long long Pobs, asc_nsite;   // Pobs = P without +ASC; asc_nsite = aln->getNSite()
     int clv_f20;             // CLV slots use the 20-state fragment-major layout (clv20_off) instead of the warp-interleaved one
     long long P, Ppad;
     long long slot_stride;   // Ppad * B   doubles per CLV slot
@@ -1448,7 +1450,10 @@ __global__ void __launch_bounds__(256) k_final_reduce(const double *red, int nbl
 // computeLikelihoodBranch{,Generic}SIMD root stage (tree/phylokernelnew.h:2753-3104): per-pattern likelihood across
 // the evaluation branch, _pattern_lh / _pattern_lh_cat, and the frequency-weighted sum.
 // ------------------------------------------------------------------------------------------------------------
-template <bool SAFE>
+// ASC (Lewis' ascertainment-bias correction, tree/phylokernelnew.h:3076-3091): the unobserved constant patterns [Pobs, P)
+// contribute their likelihood (un-scaled once if their scale count is non-zero) to prob_const instead of to the tree logL; the
+// reduction then carries (tree_lh, prob_const) and k_asc_finish_logl applies logL -= nsite*log(1-prob_const) (:3198-3221).
+template <bool SAFE, bool ASC = false>
 __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red,
                                                 unsigned *ticket, double *result, double length, int fuse_vals) {
     extern __shared__ double s_vals_dyn[];
@@ -1522,13 +1527,29 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
     vc_min_scale *= kLogScalingThreshold;
     lh_ptn = fabs(lh_ptn) + D.invar[p];
     double lg = log(lh_ptn) + vc_min_scale;
-    double acc[1] = {0.0};
-    if (p < D.P) {
+    double acc[ASC ? 2 : 1] = {0.0};
+    if (p < D.Pobs) {
         if (save_log) D.pattern_lh[p] = lg;
         else { D.pattern_lh[p] = lh_ptn; D.pattern_scaling[p] = vc_min_scale; }
         acc[0] = lg * D.freq[p];
+    } else if (ASC && p < D.P) {
+        acc[ASC ? 1 : 0] = vc_min_scale != 0.0 ? lh_ptn * kScalingThreshold : lh_ptn;
+        D.pattern_lh[p] = 0.0;
     }
-    block_reduce_finish<1>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);
+}
+
+// +ASC epilogues: raw = (tree_lh, prob_const) -> result[0] = logL, _pattern_lh -= log(1 - prob_const) (:3198-3221, 3412-3426);
+// raw = (df, ddf, prob_const, df_const, ddf_const) -> result[0..1] = (df, ddf) (:2618-2626)
+__global__ void __launch_bounds__(256) k_asc_finish_logl(Dev D, const double *raw, double *result) {
+    const double corr = log(1.0 - raw[1]);
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < D.Pobs; p += (long long)gridDim.x * blockDim.x) D.pattern_lh[p] -= corr;
+    if (blockIdx.x == 0 && threadIdx.x == 0) result[0] = raw[0] - (double)D.asc_nsite * corr;
+}
+__global__ void k_asc_finish_derv(Dev D, const double *raw, double *result) {
+    const double all = 1.0 - raw[2], df_frac = raw[3] / all, ddf_frac = raw[4] / all;
+    result[0] = raw[0] + (double)D.asc_nsite * df_frac;
+    result[1] = raw[1] + (double)D.asc_nsite * (ddf_frac + df_frac * df_frac);
 }
 
 // computeLikelihoodBuffer{,Generic}SIMD (tree/phylokernelnew.h:2091-2230): theta_all and buffer_scale_all
@@ -1574,7 +1595,7 @@ __global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_k
 }
 
 // computeLikelihoodDerv{,Generic}SIMD pattern loop (tree/phylokernelnew.h:2463-2505): (lh, df, ddf) = val{0,1,2}.theta
-template <int BT>
+template <int BT, bool ASC = false>
 __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
     extern __shared__ double s_vals_dyn[];
     const double *vals = fuse_vals ? stage_vals(D, length, 1, s_vals_dyn) : D.val;
@@ -1603,16 +1624,19 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ti
         lh = fma(v0[B - 1], t, lh); df = fma(v1[B - 1], t, df); ddf = fma(v2[B - 1], t, ddf);
     }
     lh = fabs(lh) + D.invar[p];
-    double acc[2] = {0.0, 0.0};
-    if (p < D.P) {
+    double acc[ASC ? 5 : 2] = {0.0, 0.0};
+    if (p < D.Pobs) {
         double inv = 1.0 / lh;
         double df_frac = df * inv, ddf_frac = ddf * inv;
         double freq = D.freq[p];
         double tmp1 = df_frac * freq, tmp2 = ddf_frac * freq;
         acc[0] = tmp1;
         acc[1] = fma(-tmp1, df_frac, tmp2);   // nmul_add(tmp1, df_frac, tmp2) :2505
+    } else if (ASC && p < D.P) {   // :2506-2535
+        const double f = D.buffer_scale[p] != 0.0 ? kScalingThreshold : 1.0;
+        acc[ASC ? 2 : 0] = lh * f; acc[ASC ? 3 : 0] = df * f; acc[ASC ? 4 : 0] = ddf * f;
     }
-    block_reduce_finish<2>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 5 : 2>(acc, red, ticket, result);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1722,7 +1746,7 @@ __global__ void __launch_bounds__(kTile) k_newton_coop(Dev D, double *red, doubl
 }
 
 // computeLikelihoodFromBuffer{,Generic}SIMD pattern loop (tree/phylokernelnew.h:3313-3368)
-template <int BT>
+template <int BT, bool ASC = false>
 __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
     extern __shared__ double s_vals_dyn[];
     const double *val0 = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
@@ -1741,13 +1765,16 @@ __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsig
     double lh = (a0 + a1) + (a2 + a3);
     for (; k < B; k++) lh = fma(val0[k], theta[(long long)k * kWarp], lh);
     lh = fabs(lh) + D.invar[p];
-    double acc[1] = {0.0};
-    if (p < D.P) {
+    double acc[ASC ? 2 : 1] = {0.0};
+    if (p < D.Pobs) {
         double lg = log(fabs(lh)) + D.buffer_scale[p];
         D.pattern_lh[p] = lg;
         acc[0] = lg * D.freq[p];
+    } else if (ASC && p < D.P) {   // :3342-3356
+        acc[ASC ? 1 : 0] = D.buffer_scale[p] != 0.0 ? lh * kScalingThreshold : lh;
+        D.pattern_lh[p] = 0.0;
     }
-    block_reduce_finish<1>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);
 }
 
 // layout converters for read-backs: device warp-interleaved -> reference V=1 layout [p*W + k]

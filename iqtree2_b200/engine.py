@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
-    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children",
+    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -229,6 +229,10 @@ class LikelihoodEngine:
 
     def get_pattern_lh(self):
         return self._get("b200lk_get_pattern_lh", self.nptn)
+
+    def set_ascertainment(self, asc_type, num_unobserved, nsite):
+        """+ASC (1 = Lewis): the last num_unobserved patterns are the unobserved constant patterns, nsite = aln->getNSite()"""
+        self._check(self.lib.b200lk_set_ascertainment(self._h, C.c_int32(asc_type), C.c_int64(num_unobserved), C.c_int64(nsite)))
 
     def set_extra_children(self, children):
         """third, fourth ... children of the multifurcating ops (op['pad'] = their number) of the NEXT call, in op order"""

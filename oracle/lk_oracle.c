@@ -63,6 +63,9 @@ typedef struct {
     double *theta, *buffer_scale_all, *pattern_lh, *pattern_lh_cat, *pattern_scaling;
     int theta_computed;
     int quirks; /* orc_set_reference_quirks */
+    /* +ASC, Lewis' correction (phylokernelnew.h:3076-3091, 3198-3221, 2506-2535, 2618-2626, 3342-3356, 3412-3426): the last
+     * asc_nunobs patterns are model_factory->unobserved_ptns; asc_nsite = aln->getNSite() */
+    int asc_type; int64_t asc_nunobs, asc_nsite;
     orc_child *extra; /* pending extra children of multifurcating ops (consumed by the next call that takes ops) */
     int nextra;
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
@@ -710,7 +713,8 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
     /* naming follows the reference after its leaf swap: dad_branch->partial_lh is the slot side */
     const double *dad_lh = e->partial + (size_t)node_slot * P * B;
     const uint16_t *dad_sc = e->scale + (size_t)node_slot * P * S;
-    double tree_lh = 0.0;
+    double tree_lh = 0.0, prob_const = 0.0;
+    const size_t Pobs = e->asc_type ? P - (size_t)e->asc_nunobs : P;   /* orig_nptn */
     if (dad_kind == 0) {
         /* TIP-INNER :2753-2965 : partial_lh_node[state][c][i] = val[c][i]*tip_partial_lh[state][m][i] */
         int su = e->cfg.state_unknown;
@@ -721,7 +725,7 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
                 for (int i = 0; i < n; i++)
                     plnode[(size_t)state * B + c * n + i] = val[c * n + i] * e->tip_partial_lh[(size_t)state * nmix * n + m * n + i];
             }
-#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh, prob_const)
         for (size_t p = 0; p < P; p++) {
             const double *lh_node = plnode + (size_t)tip_state(e, dad_id, p) * B;
             const double *pd = dad_lh + p * B;
@@ -745,6 +749,11 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             } else min_scale_d = dad_sc[p];
             min_scale_d *= LOG_SCALING_THRESHOLD;
             lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+            if (p >= Pobs) { /* unobserved constant pattern: :3076-3091 */
+                if (min_scale_d != 0.0) lh_ptn *= SCALING_THRESHOLD;
+                prob_const += lh_ptn;
+                continue;
+            }
             double lg = log(lh_ptn) + min_scale_d;
             if (save_log_value) e->pattern_lh[p] = lg;
             else { e->pattern_lh[p] = lh_ptn; e->pattern_scaling[p] = min_scale_d; }
@@ -755,7 +764,7 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         /* INNER-INNER :2966-3104 */
         const double *node_lh = e->partial + (size_t)dad_id * P * B;
         const uint16_t *node_sc = e->scale + (size_t)dad_id * P * S;
-#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh, prob_const)
         for (size_t p = 0; p < P; p++) {
             const double *pd = dad_lh + p * B, *pn = node_lh + p * B;
             double *lh_cat = e->pattern_lh_cat + p * C;
@@ -779,6 +788,11 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             } else min_scale_d = (double)(dad_sc[p] + node_sc[p]);
             min_scale_d *= LOG_SCALING_THRESHOLD;
             lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+            if (p >= Pobs) { /* unobserved constant pattern: :3076-3091 */
+                if (min_scale_d != 0.0) lh_ptn *= SCALING_THRESHOLD;
+                prob_const += lh_ptn;
+                continue;
+            }
             double lg = log(lh_ptn) + min_scale_d;
             if (save_log_value) e->pattern_lh[p] = lg;
             else { e->pattern_lh[p] = lh_ptn; e->pattern_scaling[p] = min_scale_d; }
@@ -791,7 +805,7 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         /* NaN repair :3115-3132 */
         status = 1;
         tree_lh = 0.0;
-        for (size_t p = 0; p < P; p++) {
+        for (size_t p = 0; p < Pobs; p++) {
             double ptn_lh = e->pattern_lh[p];
             if (!isfinite(ptn_lh)) {
                 if (save_log_value) e->pattern_lh[p] = LOG_SCALING_THRESHOLD * 4;
@@ -800,6 +814,12 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             }
             tree_lh += ptn_lh * e->ptn_freq[p];
         }
+    }
+    if (e->asc_type == 1) { /* Lewis :3198-3221 */
+        double corr = log(1.0 - prob_const);
+        for (size_t p = 0; p < Pobs; p++) e->pattern_lh[p] -= corr;
+        for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
+        tree_lh -= (double)e->asc_nsite * corr;
     }
     *logl_out = tree_lh;
     return status;
@@ -863,6 +883,13 @@ int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
 /* bit 0: reproduce dotProductTriple's double-counted last element for odd nstates x even block (see dot_triple) */
 int orc_set_reference_quirks(orc_engine *e, int mask) { e->quirks = mask; return 0; }
 
+int orc_set_ascertainment(orc_engine *e, int asc_type, int64_t nunobs, int64_t nsite) {
+    if (asc_type < 0 || asc_type > 1 || nunobs < 0 || nunobs > e->cfg.nptn) { snprintf(e->err, sizeof e->err, "bad +ASC arguments"); return -1; }
+    e->asc_type = asc_type; e->asc_nunobs = asc_type ? nunobs : 0; e->asc_nsite = nsite;
+    e->theta_computed = 0;
+    return 0;
+}
+
 int orc_set_extra_children(orc_engine *e, const orc_child *children, int n) {
     free(e->extra);
     e->extra = NULL; e->nextra = 0;
@@ -882,13 +909,19 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
     size_t P = (size_t)e->cfg.nptn;
     double *val0 = (double *)malloc(sizeof(double) * 3 * B), *val1 = val0 + B, *val2 = val1 + B;
     compute_vals(e, length, val0, val1, val2);
-    double all_df = 0.0, all_ddf = 0.0;
+    double all_df = 0.0, all_ddf = 0.0, prob_const = 0.0, df_const = 0.0, ddf_const = 0.0;
+    const size_t Pobs = e->asc_type ? P - (size_t)e->asc_nunobs : P;
     const int odd = (e->quirks & 1) ? (e->cfg.nstates & 1) : (B & 1);
-#pragma omp parallel for schedule(static) reduction(+ : all_df, all_ddf)
+#pragma omp parallel for schedule(static) reduction(+ : all_df, all_ddf, prob_const, df_const, ddf_const)
     for (size_t p = 0; p < P; p++) {
         double lh_ptn, df_ptn, ddf_ptn;
         dot_triple(val0, val1, val2, e->theta + p * B, B, odd, &lh_ptn, &df_ptn, &ddf_ptn);
         lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+        if (p >= Pobs) { /* :2506-2535 */
+            if (e->buffer_scale_all[p] != 0.0) { lh_ptn *= SCALING_THRESHOLD; df_ptn *= SCALING_THRESHOLD; ddf_ptn *= SCALING_THRESHOLD; }
+            prob_const += lh_ptn; df_const += df_ptn; ddf_const += ddf_ptn;
+            continue;
+        }
         lh_ptn = 1.0 / lh_ptn;
         double df_frac = df_ptn * lh_ptn, ddf_frac = ddf_ptn * lh_ptn;
         double freq = e->ptn_freq[p];
@@ -897,6 +930,11 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         all_ddf += fma(-tmp1, df_frac, tmp2); /* nmul_add(tmp1, df_frac, tmp2) :2505 */
     }
     free(val0);
+    if (e->asc_type == 1) { /* :2618-2626 */
+        double all = 1.0 - prob_const, df_frac = df_const / all, ddf_frac = ddf_const / all;
+        all_df += (double)e->asc_nsite * df_frac;
+        all_ddf += (double)e->asc_nsite * (ddf_frac + df_frac * df_frac);
+    }
     *df_out = all_df;
     *ddf_out = all_ddf;
     if (!isfinite(all_df)) { *df_out = *ddf_out = 0.0; return 1; } /* :2629-2632 */
@@ -910,11 +948,17 @@ int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
     size_t P = (size_t)e->cfg.nptn;
     double *val0 = (double *)malloc(sizeof(double) * B);
     compute_vals(e, length, val0, NULL, NULL);
-    double tree_lh = 0.0;
-#pragma omp parallel for schedule(static) reduction(+ : tree_lh)
+    double tree_lh = 0.0, prob_const = 0.0;
+    const size_t Pobs = e->asc_type ? P - (size_t)e->asc_nunobs : P;
+#pragma omp parallel for schedule(static) reduction(+ : tree_lh, prob_const)
     for (size_t p = 0; p < P; p++) {
         double lh_ptn = dot_vec(val0, e->theta + p * B, B); /* dotProductVec over the whole block :3329 */
         lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
+        if (p >= Pobs) { /* :3342-3356 */
+            if (e->buffer_scale_all[p] != 0.0) lh_ptn *= SCALING_THRESHOLD;
+            prob_const += lh_ptn;
+            continue;
+        }
         lh_ptn = log(fabs(lh_ptn)) + e->buffer_scale_all[p];
         e->pattern_lh[p] = lh_ptn;
         tree_lh += lh_ptn * e->ptn_freq[p];
@@ -924,10 +968,16 @@ int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
     if (!isfinite(tree_lh)) {
         status = 1;
         tree_lh = 0.0;
-        for (size_t p = 0; p < P; p++) {
+        for (size_t p = 0; p < Pobs; p++) {
             if (!isfinite(e->pattern_lh[p])) e->pattern_lh[p] = LOG_SCALING_THRESHOLD * 4;
             tree_lh += e->pattern_lh[p] * e->ptn_freq[p];
         }
+    }
+    if (e->asc_type == 1) { /* :3412-3426 */
+        double corr = log(1.0 - prob_const);
+        for (size_t p = 0; p < Pobs; p++) e->pattern_lh[p] -= corr;
+        for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
+        tree_lh -= (double)e->asc_nsite * corr;
     }
     *logl_out = tree_lh;
     return status;

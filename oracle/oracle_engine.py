@@ -96,6 +96,12 @@ class OracleEngine:
         lib().orc_set_pattern_invar(self._h, _dp(f))
 
     # ---- compute ------------------------------------------------------------------------------
+    def set_ascertainment(self, asc_type, num_unobserved, nsite):
+        """+ASC (1 = Lewis): the last num_unobserved patterns are the unobserved constant patterns, nsite = aln->getNSite()"""
+        rc = lib().orc_set_ascertainment(self._h, C.c_int(asc_type), C.c_int64(num_unobserved), C.c_int64(nsite))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+
     def set_extra_children(self, children):
         """third, fourth ... children of the multifurcating ops (op['pad'] = their number) of the NEXT call, in op order"""
         ch = np.ascontiguousarray(children)

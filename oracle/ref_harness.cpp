@@ -204,6 +204,16 @@ struct iqref_desc {
 
 void iqref_destroy(void *hv);
 
+// +ASC for the NEXT iqref_create: ModelFactory::ASC_type and ModelFactory::unobserved_ptns (what ModelFactory's constructor
+// fills from Alignment::getUnobservedConstPatterns, model/modelfactory.cpp) — unobs is [nunobs][ntaxa] state codes
+static int g_asc_type = 0;
+static std::vector<std::vector<uint8_t>> g_unobs;
+void iqref_set_asc_next(int asc_type, const uint8_t *unobs, int nunobs, int ntaxa) {
+    g_asc_type = asc_type;
+    g_unobs.clear();
+    for (int u = 0; u < nunobs; u++) g_unobs.emplace_back(unobs + (size_t)u * ntaxa, unobs + (size_t)(u + 1) * ntaxa);
+}
+
 void *iqref_create(const iqref_desc *d) {
     init_params(d->nthreads > 0 ? d->nthreads : 1);
     Params &params = Params::getInstance();
@@ -254,6 +264,14 @@ void *iqref_create(const iqref_desc *d) {
     fac->model = m;
     fac->site_rate = r;
     fac->fused_mix_rate = d->fused_mix_rate != 0;
+    fac->ASC_type = (ASCType)g_asc_type;
+    for (auto &u : g_unobs) {
+        Pattern pt;
+        pt.assign(u.begin(), u.end());
+        fac->unobserved_ptns.push_back(pt);
+    }
+    g_asc_type = 0;
+    g_unobs.clear();
 
     PhyloTree *tree = h->tree = new PhyloTree();
     tree->params = &params;
