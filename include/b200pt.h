@@ -25,6 +25,8 @@ const char *b200pt_last_error(const b200pt_tree *t);
 int b200pt_set_alignment(b200pt_tree *t, int32_t ntaxa, const char *const *names, const uint8_t *states, int64_t nptn,
                          const double *ptn_freq, int32_t nstates, int32_t seq_type, int32_t state_unknown);
 int b200pt_set_pattern_invar(b200pt_tree *t, const double *ptn_invar);
+/* +ASC (Lewis): the last num_unobserved patterns of the alignment are ModelFactory::unobserved_ptns; nsite = aln->getNSite() */
+int b200pt_set_ascertainment(b200pt_tree *t, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
 int b200pt_set_model(b200pt_tree *t, int32_t ncat, int32_t nmix, int32_t fused_mix_rate, const double *eval, const double *evec,
                      const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop);
 int b200pt_read_tree(b200pt_tree *t, const char *newick);

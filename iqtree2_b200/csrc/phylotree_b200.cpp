@@ -287,7 +287,7 @@ void PhyloTree::readTreeString(const std::string &newick) {
     nodeNum = (int)nodes_.size();
     if (leafNum != (int)taxa_.size()) throw std::runtime_error("readTreeString: tree and alignment have different taxon sets");
     for (auto *n : nodes_)
-        if (!n->isLeaf() && n->neighbors.size() != 3) throw std::runtime_error("readTreeString: multifurcating trees are not supported yet");
+        if (!n->isLeaf() && n->neighbors.size() < 3) throw std::runtime_error("readTreeString: internal node of degree 2");
     for (auto &br : branches_)
         if (br.first->length < 0) br.first->length = br.second->length = params.min_branch_length;
     // PhyloTree::readTreeString -> setRootNode(params.root == NULL): root = the leaf of alignment row 0
@@ -394,6 +394,7 @@ void PhyloTree::initializeAllPartialLh() {
         check(b200lk_set_pattern_invar(engine_, ptn_invar_.data()), "set_pattern_invar");
         check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
         check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
+        if (asc_type_) check(b200lk_set_ascertainment(engine_, asc_type_, asc_nunobs_, asc_nsite_), "set_ascertainment");
     }
     initialized_ = true;
     // slot assignment: pre-order from the root; the neighbour dad->node of every internal node gets the next slot
@@ -499,14 +500,18 @@ bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_d
                 if (!f.kids[k]->node->isLeaf() && f.locked[k]) mem_slots.unlock(f.kids[k]);
         b200lk_op op{};
         op.dst_slot = dad_branch->slot;
-        // children in NEIGHBOUR order (FOR_NEIGHBOR_IT, tree/phylokernelnew.h:1343-1350), not in the sorted visiting order
-        b200lk_child *ch[2] = {&op.left, &op.right};
+        // children in NEIGHBOUR order (FOR_NEIGHBOR_IT, tree/phylokernelnew.h:1343-1350), not in the sorted visiting order;
+        // a multifurcating node (degree > 3, :1407) hands its third and later children to the engine as extra children
         int k = 0;
         for (auto *it : node->neighbors)
             if (it->node != dad) {
-                ch[k]->kind = it->node->isLeaf() ? 0 : 1;
-                ch[k]->id = it->node->isLeaf() ? it->node->id : it->slot;
-                ch[k]->length = it->length;
+                b200lk_child c;
+                c.kind = it->node->isLeaf() ? 0 : 1;
+                c.id = it->node->isLeaf() ? it->node->id : it->slot;
+                c.length = it->length;
+                if (k == 0) op.left = c;
+                else if (k == 1) op.right = c;
+                else { traversal_extra.push_back(c); op.reserved++; }
                 k++;
             }
         traversal_info.push_back(op);
@@ -521,6 +526,7 @@ bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_d
 // tree/phylokernelnew.h:1150-1281 (the part that builds the list; execution happens inside the engine call)
 void PhyloTree::computeTraversalInfo(PhyloNode *node, PhyloNode *dad) {
     traversal_info.clear();
+    traversal_extra.clear();
     if (params.lh_mem_save == LM_MEM_SAVE) {   // the larger side first (tree/phylokernelnew.h:1171-1186)
         const int node_size = computeSize(dad->findNeighbor(node), dad), dad_size = computeSize(node->findNeighbor(dad), node);
         if (node_size < dad_size) std::swap(node, dad);
@@ -556,6 +562,8 @@ void PhyloTree::planBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, std::vecto
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     ops = traversal_info;
     traversal_info.clear();
+    last_plan_extra_ = traversal_extra;
+    traversal_extra.clear();
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -568,17 +576,32 @@ double PhyloTree::computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     double logl = 0.0;
     if (!traversal_info.empty()) theta_computed = false;
+    pushExtraChildren();
     check(b200lk_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
                              save_log_value, &logl), "branch_logl");
     traversal_info.clear();
     return logl;
 }
 
+void PhyloTree::pushExtraChildren() {
+    if (!traversal_extra.empty()) check(b200lk_set_extra_children(engine_, traversal_extra.data(), (int)traversal_extra.size()), "set_extra_children");
+    traversal_extra.clear();
+}
+
+// +ASC (Lewis): the last num_unobserved patterns of the alignment handed to setAlignment are ModelFactory::unobserved_ptns
+void PhyloTree::setAscertainment(int asc_type, int64_t num_unobserved, int64_t nsite) {
+    asc_type_ = asc_type; asc_nunobs_ = num_unobserved; asc_nsite_ = nsite;
+    if (engine_) check(b200lk_set_ascertainment(engine_, asc_type, num_unobserved, nsite), "set_ascertainment");
+    theta_computed = false;
+}
+
 void PhyloTree::computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *dad) {
     initializeAllPartialLh();
     traversal_info.clear();
+    traversal_extra.clear();
     computeTraversalInfo(dad_branch, dad);
     if (!traversal_info.empty()) theta_computed = false;
+    pushExtraChildren();
     check(b200lk_update_partials(engine_, traversal_info.data(), (int)traversal_info.size()), "update_partials");
     traversal_info.clear();
 }
@@ -590,6 +613,7 @@ void PhyloTree::computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad,
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     if (!traversal_info.empty()) theta_computed = false;
     if (!theta_computed) b200lk_theta_reset(engine_);
+    pushExtraChildren();
     check(b200lk_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length, df, ddf),
           "branch_derv");
     traversal_info.clear();
@@ -602,6 +626,7 @@ void PhyloTree::enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *da
     const double length = dad_branch->length;
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     if (!traversal_info.empty()) theta_computed = false;
+    pushExtraChildren();
     check(b200lk_enqueue_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
                                      save_log_value), "enqueue_branch_logl");
     traversal_info.clear();
@@ -614,6 +639,7 @@ void PhyloTree::enqueueLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad)
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     if (!traversal_info.empty()) theta_computed = false;
     if (!theta_computed) b200lk_theta_reset(engine_);
+    pushExtraChildren();
     check(b200lk_enqueue_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length),
           "enqueue_branch_derv");
     traversal_info.clear();
@@ -774,7 +800,8 @@ void PhyloTree::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clear
         int node_slot, dad_kind, dad_id;
         branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
         int steps = 0;
-        check(b200lk_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
+        pushExtraChildren();
+    check(b200lk_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
                                    params.min_branch_length, current_len, params.max_branch_length, params.min_branch_length,
                                    maxNRStep, &optx, &steps), "newton_branch");
         traversal_info.clear();

@@ -97,6 +97,7 @@ public:
     void setAlignment(const std::vector<std::string> &names, const uint8_t *states, int64_t nptn, const double *ptn_freq,
                       int nstates, int seq_type, int state_unknown);
     void setPatternInvar(const double *ptn_invar);
+    void setAscertainment(int asc_type, int64_t num_unobserved, int64_t nsite);   // ModelFactory::ASC_type / unobserved_ptns (+ASC, Lewis)
     void setModel(int ncat, int nmix, bool fused_mix_rate, const double *eval, const double *evec, const double *inv_evec,
                   const double *mix_weight, const double *cat_rate, const double *cat_prop);
     void readTreeString(const std::string &newick);   // MTree::readTree; leaf ids := alignment rows
@@ -149,6 +150,7 @@ public:
     int64_t num_partial_lh_computations = 0;   // tree/phylotree.h:2127
     b200lk_engine *engine() const { return engine_; }
     const std::vector<b200lk_op> &lastTraversal() const { return traversal_info; }
+    const std::vector<b200lk_child> &lastPlanExtraChildren() const { return last_plan_extra_; }
 
     Params params;
     PhyloNode *root = nullptr;
@@ -182,6 +184,11 @@ protected:
     b200lk_engine *engine_ = nullptr;
     bool initialized_ = false;
     std::vector<b200lk_op> traversal_info;
+    std::vector<b200lk_child> traversal_extra;   // third and later children of multifurcating nodes, in op order
+    std::vector<b200lk_child> last_plan_extra_;
+    int asc_type_ = 0;
+    int64_t asc_nunobs_ = 0, asc_nsite_ = 0;
+    void pushExtraChildren();
     std::vector<double> pattern_lh_;
 };
 

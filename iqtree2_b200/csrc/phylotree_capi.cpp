@@ -42,6 +42,9 @@ int b200pt_set_alignment(b200pt_tree *t, int32_t ntaxa, const char *const *names
     })
 }
 int b200pt_set_pattern_invar(b200pt_tree *t, const double *ptn_invar) { GUARD(t->tree.setPatternInvar(ptn_invar)) }
+int b200pt_set_ascertainment(b200pt_tree *t, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
+    GUARD(t->tree.setAscertainment(asc_type, num_unobserved, nsite))
+}
 int b200pt_set_model(b200pt_tree *t, int32_t ncat, int32_t nmix, int32_t fused, const double *eval, const double *evec,
                      const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop) {
     GUARD(t->tree.setModel(ncat, nmix, fused != 0, eval, evec, inv_evec, mix_weight, cat_rate, cat_prop))

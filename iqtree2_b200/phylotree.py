@@ -55,6 +55,9 @@ class PhyloTree:
         inv = np.ascontiguousarray(inv, dtype=np.float64)
         self._check(self.lib.b200pt_set_pattern_invar(self._h, _dp(inv)))
 
+    def set_ascertainment(self, asc_type, num_unobserved, nsite):
+        self._check(self.lib.b200pt_set_ascertainment(self._h, asc_type, C.c_int64(num_unobserved), C.c_int64(nsite)))
+
     def set_model(self, model):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         arrs = [f(model.eval), f(model.evec), f(model.inv_evec), f(model.mix_weight), f(model.cat_rate), f(model.cat_prop)]
