@@ -165,6 +165,18 @@ int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t n
 int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length);
 int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf);
 
+/* A whole optimizeAllBranches sweep without a host round trip per branch (tree/phylotree.cpp:2698-2774).  Per branch the
+ * caller queues b200lk_enqueue_newton_branch — partial updates, theta buffer, the complete minimizeNewton iteration and the
+ * divergence test of optimizeOneBranch (:2616-2625), all on the device — and goes on planning the next branch; the optimised
+ * length lands in slot `len_slot` (0 .. 2*ntaxa-1) of a device-resident length table.  Ops queued later in the same sweep
+ * refer to it with a NEGATIVE child length: length = -(len_slot) - 1.  b200lk_sweep_finish waits once and returns, per slot,
+ * the length, the number of derivative evaluations and the status of the iteration.  B200LK_ERR_STATE from the enqueue call
+ * means "use b200lk_newton_branch" (blocks above 512 doubles, +ASC). */
+int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                 int32_t dad_id, double min_len, double guess, double max_len, double tolerance,
+                                 int32_t max_steps, int32_t len_slot);
+int b200lk_sweep_finish(b200lk_engine *e, int32_t nslots, double *lengths, int32_t *evaluations, int32_t *status);
+
 /* ---- read-backs (computePatternLikelihood & friends, tree/phylotree.cpp:1458-1603; parity dumps) -------------- */
 int b200lk_get_pattern_lh(b200lk_engine *e, double *out /* [nptn] */);
 int b200lk_get_pattern_scaling(b200lk_engine *e, double *out /* [nptn] */);

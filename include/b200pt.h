@@ -44,6 +44,8 @@ int b200pt_compute_likelihood_from_buffer(b200pt_tree *t, double *logl);
 int b200pt_compute_pattern_likelihood(b200pt_tree *t, double *pattern_lh, double *pattern_lh_cat /* may be NULL */);
 int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step);
 int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+/* optimizeAllBranches queues each sweep as a whole (b200lk_enqueue_newton_branch): one synchronisation per sweep */
+int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on);
 /* number of partial-likelihood updates planned so far (PhyloTree::num_partial_lh_computations) */
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t);
 

@@ -36,8 +36,9 @@ struct b200lk_engine {
     DevOp *d_ops = nullptr;
     ChildJob *d_jobs = nullptr;
     size_t ops_cap = 0;
-    void *h_stage = nullptr;   // pinned staging: ops + jobs
-    size_t h_stage_cap = 0;
+    void *h_stage = nullptr;   // pinned staging: a ring of stage_ring segments of stage_seg bytes (ops + jobs of one call each)
+    size_t h_stage_cap = 0, stage_seg = 0;
+    int stage_ring = 32, stage_next = 0, stage_used = 0;
     double *d_red = nullptr;   // per-block partial sums
     double *d_result = nullptr;
     double *h_result = nullptr;   // pinned + mapped, 8 doubles: the final reductions write the scalars straight into it
@@ -67,6 +68,10 @@ struct b200lk_engine {
     long long boot_stride = 0;
     size_t boot_bytes = 0;
     int newton_grid = 0;   // co-resident CTAs of k_newton_coop
+    double *d_lens = nullptr;      // device-resident branch lengths of an asynchronous sweep (slots)
+    double *h_sweep = nullptr;     // mapped host table [nlen_slots][3]: (length, evaluations, status) per slot
+    double *d_sweep = nullptr;     // its device alias
+    int nlen_slots = 0;
     std::vector<b200lk_child> extra_children;   // b200lk_set_extra_children: consumed by the next call that takes ops
     MultiChild *d_mchild = nullptr;
     bool has_multi = false;
@@ -84,6 +89,23 @@ static thread_local std::string g_create_err;
             return B200LK_ERR_CUDA;                                                                   \
         }                                                                                             \
     } while (0)
+
+// every stream synchronisation goes through here: the pinned staging ring is free again afterwards
+static cudaError_t sync_stream(b200lk_engine *e) {
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    e->stage_used = 0;
+    return ce;
+}
+
+// Host staging for op lists travels through a RING of pinned segments, so that several calls can be queued without waiting
+// for the previous call's host-to-device copy (the asynchronous branch sweep); the ring wraps only after a synchronisation.
+static void *stage_acquire(b200lk_engine *e) {
+    if (e->stage_used == e->stage_ring) sync_stream(e);
+    void *p = (char *)e->h_stage + (size_t)(e->stage_next % e->stage_ring) * e->stage_seg;
+    e->stage_next++;
+    e->stage_used++;
+    return p;
+}
 
 static int fail(b200lk_engine *e, int code, const std::string &msg) {
     e->err = msg;
@@ -111,12 +133,13 @@ extern "C" int64_t b200lk_launch_count(const b200lk_engine *e) { return e->launc
 extern "C" void b200lk_destroy(b200lk_engine *e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
-    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->stream) sync_stream(e);
     cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild);
+    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens);
+    if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
     for (auto &ev : e->ev) if (ev) cudaEventDestroy(ev);
@@ -183,6 +206,10 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     if (cudaHostAlloc((void **)&e->h_result, 16 * sizeof(double), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void **)&e->d_result, e->h_result, 0) != cudaSuccess) { e->err = "cudaHostAlloc(mapped) failed"; return bail(B200LK_ERR_CUDA); }
     cudaMemsetAsync(e->d_ticket, 0, 4 * sizeof(unsigned), e->stream);
+    e->nlen_slots = 2 * cfg->ntaxa;
+    if (dev_alloc(e, &e->d_lens, (size_t)e->nlen_slots) != 0) return bail(B200LK_ERR_NOMEM);
+    if (cudaHostAlloc((void **)&e->h_sweep, sizeof(double) * 3 * e->nlen_slots, cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void **)&e->d_sweep, e->h_sweep, 0) != cudaSuccess) { e->err = "cudaHostAlloc(mapped) failed"; return bail(B200LK_ERR_CUDA); }
     cudaMemsetAsync(e->d_tips, cfg->state_unknown, (size_t)cfg->ntaxa * Ppad, e->stream);
     cudaMemsetAsync(e->d_freq, 0, sizeof(double) * Ppad, e->stream);
     cudaMemsetAsync(e->d_invar, 0, sizeof(double) * Ppad, e->stream);
@@ -207,6 +234,8 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     d.tip_lh = m; m += n_tip;
     d.val = m;
     d.opinfo = nullptr;
+    d.dev_len = e->d_lens;
+    d.mchild = nullptr;
     d.theta = e->d_theta; d.buffer_scale = e->d_buffer_scale; d.pattern_lh = e->d_pattern_lh;
     d.pattern_scaling = e->d_pattern_scaling; d.pattern_lh_cat = e->d_pattern_lh_cat;
 
@@ -216,13 +245,13 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
         if (info_smem > 200 * 1024) { e->err = "ncat_mix*nstates too large for k_partial_info"; return bail(B200LK_ERR_INVALID); }
         cudaFuncSetAttribute(k_partial_info, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)info_smem);
     }
-    if (cudaStreamSynchronize(e->stream) != cudaSuccess) { e->err = "initialisation failed"; return bail(B200LK_ERR_CUDA); }
+    if (sync_stream(e) != cudaSuccess) { e->err = "initialisation failed"; return bail(B200LK_ERR_CUDA); }
     *out = e;
     return 0;
 }
 
 extern "C" int b200lk_set_stream(b200lk_engine *e, void *cuda_stream) {
-    cudaStreamSynchronize(e->stream);
+    sync_stream(e);
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return 0;
 }
@@ -242,7 +271,7 @@ extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int6
     if (asc_type < 0 || asc_type > 1) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE); Holder's missing-data forms are not implemented");
     if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
     cudaSetDevice(e->cfg.device);
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     e->d.asc = asc_type;
     e->d.Pobs = asc_type ? e->P - num_unobserved : e->P;
     e->d.asc_nsite = nsite;
@@ -279,7 +308,7 @@ extern "C" int b200lk_set_tip_states(b200lk_engine *e, const uint8_t *states) {
     for (size_t k = 0; k < total; k++)
         if (states[k] > e->cfg.state_unknown) return fail(e, B200LK_ERR_INVALID, "tip state > STATE_UNKNOWN");
     CK(cudaMemcpy2DAsync(e->d_tips, e->Ppad, states, e->P, e->P, e->cfg.ntaxa, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 
@@ -287,14 +316,14 @@ extern "C" int b200lk_set_pattern_freq(b200lk_engine *e, const double *f) {
     cudaSetDevice(e->cfg.device);
     e->h_freq.assign(f, f + e->P);
     CK(cudaMemcpyAsync(e->d_freq, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 
 extern "C" int b200lk_set_pattern_invar(b200lk_engine *e, const double *f) {
     cudaSetDevice(e->cfg.device);
     CK(cudaMemcpyAsync(e->d_invar, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     e->theta_computed = false;
     return 0;
 }
@@ -314,7 +343,7 @@ extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const doub
     e->launches++;
     CK(cudaGetLastError());
     // pageable host sources: make sure the copies have consumed them before returning
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     e->theta_computed = false;
     return 0;
 }
@@ -323,7 +352,7 @@ extern "C" int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const 
     cudaSetDevice(e->cfg.device);
     CK(cudaMemcpyAsync((void *)e->d.cat_rate, cat_rate, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync((void *)e->d.cat_prop, cat_prop, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     e->theta_computed = false;
     return 0;
 }
@@ -336,7 +365,7 @@ static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
     const size_t need_info = nops * 2 * (e_sz + leaf_sz);
     if (need_info > e->opinfo_cap) {
-        CK(cudaStreamSynchronize(e->stream));
+        CK(sync_stream(e));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
         e->d_opinfo = nullptr; e->opinfo_cap = 0;
         size_t cap = std::max(need_info, (size_t)4 * 2 * (e_sz + leaf_sz));
@@ -346,7 +375,7 @@ static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
         e->d.opinfo = e->d_opinfo;
     }
     if (nops > e->ops_cap) {
-        CK(cudaStreamSynchronize(e->stream));
+        CK(sync_stream(e));
         cudaFree(e->d_ops); cudaFree(e->d_jobs); cudaFree(e->d_mchild);
         if (e->h_stage) cudaFreeHost(e->h_stage);
         e->d_ops = nullptr; e->d_jobs = nullptr; e->h_stage = nullptr; e->d_mchild = nullptr;
@@ -358,8 +387,10 @@ static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
         rc = dev_alloc(e, &e->d_mchild, cap * 2);
         if (rc) return rc;
         e->d.mchild = e->d_mchild;
-        e->h_stage_cap = cap * (sizeof(DevOp) + 2 * sizeof(ChildJob) + 2 * sizeof(MultiChild));
+        e->stage_seg = (cap * (sizeof(DevOp) + 2 * sizeof(ChildJob) + 2 * sizeof(MultiChild)) + 255) / 256 * 256;
+        e->h_stage_cap = e->stage_seg * e->stage_ring;
         CK(cudaMallocHost(&e->h_stage, e->h_stage_cap));
+        e->stage_next = e->stage_used = 0;
         e->ops_cap = cap;
     }
     return 0;
@@ -384,6 +415,13 @@ static void launch_partials(b200lk_engine *e, int op_begin, int op_end, int walk
 }
 
 
+// a child length is a number >= 0, or -(k)-1 = slot k of the device length table (b200lk_enqueue_newton_branch)
+static bool length_ok(const b200lk_engine *e, double len) {
+    if (len >= 0.0) return true;
+    const double k = -len - 1.0;
+    return k >= 0.0 && k < (double)e->nlen_slots && k == std::floor(k);
+}
+
 static int validate_op(b200lk_engine *e, const b200lk_op &op) {
     if (op.dst_slot < 0 || op.dst_slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "op: dst_slot out of range");
     const b200lk_child ch[2] = {op.left, op.right};
@@ -391,6 +429,7 @@ static int validate_op(b200lk_engine *e, const b200lk_op &op) {
         if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
         else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
         else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+        if (!length_ok(e, c.length)) return fail(e, B200LK_ERR_INVALID, "op: child length must be >= 0 or -(len_slot)-1 of the device length table");
     }
     return 0;
 }
@@ -402,8 +441,7 @@ static bool use_walk4(const b200lk_engine *e) {
 }
 
 static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
-    WalkJob4 *hj = (WalkJob4 *)e->h_stage;
-    CK(cudaStreamSynchronize(e->stream));   // the pinned staging buffer may still be in flight
+    WalkJob4 *hj = (WalkJob4 *)stage_acquire(e);
     int prev_dst = -1;
     for (int k = 0; k < nops; k++) {
         const b200lk_op &op = ops[k];
@@ -497,7 +535,7 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     const bool mix = nblk > 1;
     const size_t stage_sz = stage20_doubles(cpb, e->cfg.state_unknown);   // one staging block per (op, class block)
     if (stage_sz * nops * nblk > e->opinfo_cap) {
-        CK(cudaStreamSynchronize(e->stream));
+        CK(sync_stream(e));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
         e->d_opinfo = nullptr; e->opinfo_cap = 0;
         int rc = dev_alloc(e, &e->d_opinfo, stage_sz * nops * nblk);
@@ -505,9 +543,8 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
         e->opinfo_cap = stage_sz * nops * nblk;
         e->d.opinfo = e->d_opinfo;
     }
-    WalkJob20 *hj = (WalkJob20 *)e->h_stage;
     static_assert(sizeof(WalkJob20) <= sizeof(DevOp) + 2 * sizeof(ChildJob), "pinned staging buffer too small for WalkJob20");
-    CK(cudaStreamSynchronize(e->stream));   // the pinned staging buffer may still be in flight
+    WalkJob20 *hj = (WalkJob20 *)stage_acquire(e);
     for (int k = 0; k < nops; k++) {
         const b200lk_op &op = ops[k];
         int rc = validate_op(e, op);
@@ -585,12 +622,11 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
     if (nextra == 0 && use_walk20(e)) return enqueue_walk20(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
-    DevOp *hops = (DevOp *)e->h_stage;
-    ChildJob *hjobs = (ChildJob *)((char *)e->h_stage + e->ops_cap * sizeof(DevOp));
+    char *seg = (char *)stage_acquire(e);
+    DevOp *hops = (DevOp *)seg;
+    ChildJob *hjobs = (ChildJob *)(seg + e->ops_cap * sizeof(DevOp));
     MultiChild *hmc = (MultiChild *)((char *)hjobs + e->ops_cap * 2 * sizeof(ChildJob));
     int xcur = 0, nmc = 0;   // cursor into `extra`, MultiChild records written
-    // the pinned staging buffer may still be in flight from the previous call on this stream
-    CK(cudaStreamSynchronize(e->stream));
     // level_of_slot: level of the latest writer; last_touch: highest level of any op that has read or written the slot.
     // With recycled slots (LM_MEM_SAVE: one slot serves several nodes of one traversal) an op must also run after
     // every earlier reader/writer of its destination (WAR / WAW), not only after its producers.
@@ -606,6 +642,7 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
             if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
             else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
             else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+            if (!length_ok(e, c.length)) return fail(e, B200LK_ERR_INVALID, "op: child length must be >= 0 or -(len_slot)-1 of the device length table");
         }
         const size_t base = (size_t)k * 2 * (e_sz + leaf_sz);
         int64_t eoff[2] = {(int64_t)base, (int64_t)(base + e_sz)};
@@ -726,7 +763,7 @@ extern "C" int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, in
     int rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     prof_mark(e, 1);
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     prof_end(e, 1);
     return 0;
 }
@@ -798,7 +835,7 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
 
 extern "C" int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf) {
     cudaSetDevice(e->cfg.device);
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     if (e->pending_marks) prof_end(e, e->pending_marks);
     e->pending_marks = 0;
     const int pending = e->pending;
@@ -920,6 +957,58 @@ extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *
     return b200lk_finish(e, logl, nullptr, nullptr);
 }
 
+static bool newton_coop_ok(const b200lk_engine *e) { return e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc; }
+
+static int launch_newton_coop(b200lk_engine *e, double x1, double xguess, double x2, double xacc, int maxNRStep, double *io,
+                              double *len_out, int check_divergence) {
+    const void *kern = e->B == 16 ? (const void *)k_newton_coop<16> : e->B == 80 ? (const void *)k_newton_coop<80> : (const void *)k_newton_coop<0>;
+    const size_t vsm = sizeof(double) * 3 * e->B;
+    if (e->newton_grid == 0) {
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, vsm));
+        e->newton_grid = std::max(1, per_sm) * e->num_sms;
+    }
+    const int grid = std::min((int)(e->Ppad / kTile), e->newton_grid);   // d_red holds 5 doubles per tile: room for 2 x 2 x grid
+    void *args[] = {(void *)&e->d, (void *)&e->d_red, (void *)&io, (void *)&x1, (void *)&xguess, (void *)&x2, (void *)&xacc,
+                    (void *)&maxNRStep, (void *)&len_out, (void *)&check_divergence};
+    CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTile), args, vsm, e->stream));
+    e->launches++;
+    return 0;
+}
+
+// The asynchronous form of b200lk_newton_branch for a whole optimizeAllBranches sweep: nothing waits.  The optimised length
+// goes to slot `len_slot` of the engine's device length table, where later ops of the same sweep pick it up (a child length
+// of -(len_slot)-1 in a b200lk_op), and — with the number of derivative evaluations and the status — to a host-mapped table
+// that b200lk_sweep_finish hands out after one synchronisation.  The Newton-Raphson divergence test of optimizeOneBranch
+// (tree/phylotree.cpp:2616-2625) runs on the device too.  Returns B200LK_ERR_STATE when this engine's configuration has no
+// device-resident Newton iteration (block > 512 doubles, +ASC): the caller then uses the synchronous call.
+extern "C" int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                            int32_t dad_id, double x1, double xguess, double x2, double xacc, int32_t maxNRStep,
+                                            int32_t len_slot) {
+    cudaSetDevice(e->cfg.device);
+    if (!newton_coop_ok(e)) return fail(e, B200LK_ERR_STATE, "enqueue_newton_branch: no device-resident Newton iteration for this configuration");
+    if (len_slot < 0 || len_slot >= e->nlen_slots) return fail(e, B200LK_ERR_INVALID, "len_slot out of range");
+    int rc = check_branch(e, node_slot, dad_kind, dad_id);
+    if (rc) return rc;
+    e->theta_computed = false;
+    rc = enqueue_partials(e, ops, nops);
+    if (rc) return rc;
+    enqueue_theta(e, node_slot, dad_kind, dad_id);
+    return launch_newton_coop(e, x1, xguess, x2, xacc, maxNRStep, e->d_sweep + 3 * (size_t)len_slot, e->d_lens + len_slot, 1);
+}
+
+extern "C" int b200lk_sweep_finish(b200lk_engine *e, int32_t nslots, double *lengths, int32_t *evaluations, int32_t *status) {
+    cudaSetDevice(e->cfg.device);
+    if (nslots < 0 || nslots > e->nlen_slots) return fail(e, B200LK_ERR_INVALID, "nslots out of range");
+    CK(sync_stream(e));
+    for (int k = 0; k < nslots; k++) {
+        if (lengths) lengths[k] = e->h_sweep[3 * k];
+        if (evaluations) evaluations[k] = (int)e->h_sweep[3 * k + 1];
+        if (status) status[k] = e->h_sweep[3 * k + 2] != 0.0 ? B200LK_WARN_DERV_UNDERFLOW : 0;
+    }
+    return 0;
+}
+
 // Optimization::minimizeNewton (utils/optimization.cpp:422-499) with f = -df, f' = -ddf (computeFuncDerv,
 // tree/phylotree.cpp:2529-2536), evaluated on the resident theta buffer.
 extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
@@ -932,25 +1021,12 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
-    if (e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc) {
+    if (newton_coop_ok(e)) {
         // the whole iteration in one cooperative launch (k_newton_coop); variant 9 keeps the host-driven loop below for A/B
-        const void *kern = e->B == 16 ? (const void *)k_newton_coop<16> : e->B == 80 ? (const void *)k_newton_coop<80> : (const void *)k_newton_coop<0>;
-        const size_t vsm = sizeof(double) * 3 * e->B;
-        if (e->newton_grid == 0) {
-            int per_sm = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kTile, vsm));
-            e->newton_grid = std::max(1, per_sm) * e->num_sms;
-        }
-        const int nblocks = (int)(e->Ppad / kTile);
-        const int grid = std::min(nblocks, std::min(e->newton_grid, (int)(e->Ppad / kTile)));   // d_red holds 3 doubles per tile: room for 2 x 2 x grid
-        int maxs = maxNRStep;
-        void *args[] = {(void *)&e->d, (void *)&e->d_red, (void *)&e->d_result, (void *)&x1, (void *)&xguess, (void *)&x2, (void *)&xacc, (void *)&maxs};
-        // d_result is mapped host memory; slots 4..6 = (length, evaluations, status)
-        double *io = e->d_result + 4;
-        args[2] = (void *)&io;
-        CK(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(kTile), args, vsm, e->stream));
-        e->launches++;
-        CK(cudaStreamSynchronize(e->stream));
+        double *io = e->d_result + 4;   // mapped host memory; slots 4..6 = (length, evaluations, status)
+        rc = launch_newton_coop(e, x1, xguess, x2, xacc, maxNRStep, io, nullptr, 0);
+        if (rc) return rc;
+        CK(sync_stream(e));
         *length_out = e->h_result[4];
         if (steps_out) *steps_out = (int)e->h_result[5];
         return e->h_result[6] != 0.0 ? B200LK_WARN_DERV_UNDERFLOW : 0;
@@ -959,7 +1035,7 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     auto func_derv = [&](double x, double &f, double &df) -> int {
         enqueue_derv(e, x);
         cudaError_t ce = cudaSuccess;
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(e->stream);
+        if (ce == cudaSuccess) ce = sync_stream(e);
         if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
         f = -e->h_result[1];
         df = -e->h_result[2];
@@ -1023,14 +1099,14 @@ static int read_interleaved_f64(b200lk_engine *e, const double *src, int W, doub
     e->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 
 static int read_plain(b200lk_engine *e, const void *src, size_t bytes, void *out) {
     cudaSetDevice(e->cfg.device);
     CK(cudaMemcpyAsync(out, src, bytes, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 
@@ -1051,7 +1127,7 @@ extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     e->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out) {
@@ -1066,7 +1142,7 @@ extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *ou
     e->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, e->d_scratch, total * sizeof(uint16_t), cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 extern "C" int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out) {
@@ -1080,7 +1156,7 @@ extern "C" void *b200lk_pattern_lh_dev(b200lk_engine *e) { return e->d_pattern_l
 extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot) {
     cudaSetDevice(e->cfg.device);
     if (nboot < 0) return fail(e, B200LK_ERR_INVALID, "nboot < 0");
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     if (e->d_boot) { cudaFree(e->d_boot); e->device_bytes -= (int64_t)e->boot_bytes; e->d_boot = nullptr; }
     if (e->d_rell) { cudaFree(e->d_rell); e->d_rell = nullptr; }
     e->nboot = 0; e->boot_bytes = 0;
@@ -1095,7 +1171,7 @@ extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_sampl
     CK(cudaMemsetAsync(e->d_boot, 0, n * sizeof(float), e->stream));
     CK(cudaMemcpy2DAsync(e->d_boot, e->boot_stride * sizeof(float), boot_samples, e->P * sizeof(float), e->P * sizeof(float), nboot,
                          cudaMemcpyHostToDevice, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     e->nboot = nboot;
     return 0;
 }
@@ -1107,6 +1183,6 @@ extern "C" int b200lk_rell(b200lk_engine *e, float *rell) {
     e->launches++;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(rell, e->d_rell, sizeof(float) * e->nboot, cudaMemcpyDeviceToHost, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
+    CK(sync_stream(e));
     return 0;
 }

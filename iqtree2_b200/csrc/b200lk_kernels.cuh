@@ -62,7 +62,11 @@ struct Dev {
     double *theta, *buffer_scale, *pattern_lh, *pattern_scaling, *pattern_lh_cat;
     double *val;             // val0 | val1 | val2, B doubles each
     const MultiChild *mchild;   // children of the multifurcating ops of the current call
+    const double *dev_len;      // device-resident branch lengths (asynchronous branch sweep): a child length < 0 in an op means
+                                // "slot -(length) - 1 of this table", written by an earlier k_newton_coop of the same sweep
 };
+
+__device__ __forceinline__ double resolve_len(const Dev &D, double len) { return len >= 0.0 ? len : D.dev_len[(int)(-len) - 1]; }
 
 __device__ __forceinline__ long long pbase(long long p, int width) {
     return (p >> 5) * (long long)width * kWarp + (p & 31);
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(256) k_partial_info(Dev D, const ChildJob *job
     for (int k = threadIdx.x; k < B; k += blockDim.x) {
         int c = k / n, i = k - c * n;
         int m = c / D.denom, r = c % D.ncat;
-        double len_child = D.cat_rate[r] * job.length;           // :1017
+        double len_child = D.cat_rate[r] * resolve_len(D, job.length);           // :1017
         s_exp[k] = exp(D.eval[m * n + i] * len_child);           // :1022
     }
     __syncthreads();
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
     const int t = threadIdx.x;
     if (t < 32) {
         const int ch = t >> 4, k = t & 15, c = k >> 2, i = k & 3;
-        const double len_child = D.cat_rate[c] * (ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
         const double v = exp(D.eval[i] * len_child);                           // :1022
         s_exp[ch][k] = v;
         st[4 + ch * 16 + k] = v;
@@ -877,7 +881,7 @@ __global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *j
     for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
         const int ch = k / B, kk = k - ch * B, r = kk / 20, i = kk - r * 20;
         const int c = m * cpb + r;
-        const double len_child = D.cat_rate[c % D.ncat] * (ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c % D.ncat] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
         const double v = exp(D.eval[m * 20 + i] * len_child);                            // :1022
         s_exp20[k] = v;
         st[4 + k] = v;
@@ -1651,7 +1655,7 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ti
 // ------------------------------------------------------------------------------------------------------------
 template <int BT>
 __global__ void __launch_bounds__(kTile) k_newton_coop(Dev D, double *red, double *io, double x1, double xguess, double x2, double xacc,
-                                                       int maxNRStep) {
+                                                       int maxNRStep, double *len_out, int check_divergence) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double s_vals_dyn[];
@@ -1711,8 +1715,53 @@ __global__ void __launch_bounds__(kTile) k_newton_coop(Dev D, double *red, doubl
         __syncthreads();
         nevals++;
     };
+    // computeLikelihoodFromBuffer's sum at length x (tree/phylokernelnew.h:3313-3340) for the divergence test below; does not
+    // touch _pattern_lh
+    auto logl_at = [&](double x) -> double {
+        const double *vals = stage_vals(D, x, 0, s_vals_dyn);
+        double acc[2] = {0.0, 0.0};
+        for (long long p = (long long)blockIdx.x * kTile + threadIdx.x; p < D.P; p += (long long)gridDim.x * kTile) {
+            const double *theta = D.theta + pbase(p, B);
+            double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            int k = 0;
+            for (; k + 3 < B; k += 4) {
+                a0 = fma(vals[k], theta[(long long)k * kWarp], a0); a1 = fma(vals[k + 1], theta[(long long)(k + 1) * kWarp], a1);
+                a2 = fma(vals[k + 2], theta[(long long)(k + 2) * kWarp], a2); a3 = fma(vals[k + 3], theta[(long long)(k + 3) * kWarp], a3);
+            }
+            double lh = (a0 + a1) + (a2 + a3);
+            for (; k < B; k++) lh = fma(vals[k], theta[(long long)k * kWarp], lh);
+            lh = fabs(lh) + D.invar[p];
+            acc[0] += (log(fabs(lh)) + D.buffer_scale[p]) * D.freq[p];
+        }
+        double *r = red + (size_t)(nevals & 1) * 2 * gridDim.x;
+        block_reduce_store<2>(acc, r);
+        __threadfence();
+        grid.sync();
+        for (int vt = threadIdx.x; vt < 256; vt += blockDim.x) {
+            double a = 0.0;
+            for (int b = vt; b < (int)gridDim.x; b += 256) a += __ldcg(r + 2 * b);
+            s_fin[0][vt] = a;
+        }
+        __syncthreads();
+        for (int off = 128; off > 0; off >>= 1) {
+            for (int vt = threadIdx.x; vt < off; vt += blockDim.x) s_fin[0][vt] += s_fin[0][vt + off];
+            __syncthreads();
+        }
+        const double v = s_fin[0][0];
+        __syncthreads();
+        nevals++;
+        return v;
+    };
     auto finish = [&](double x, double status) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { io[0] = x; io[1] = (double)nevals; io[2] = status; }
+        // PhyloTree::optimizeOneBranch, tree/phylotree.cpp:2616-2625: Newton-Raphson diverged — keep the better of the two
+        if (check_divergence && status == 0.0 && x > x2 * 0.95) {
+            const double opt_lh = logl_at(x), orig_lh = logl_at(xguess);
+            if (orig_lh > opt_lh) x = xguess;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            io[0] = x; io[1] = (double)nevals; io[2] = status;
+            if (len_out) *len_out = x;
+        }
     };
     double df, dx, f, temp, xh, xl, rts, rts_old;
     rts = xguess;

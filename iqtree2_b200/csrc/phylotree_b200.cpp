@@ -508,7 +508,8 @@ bool PhyloTree::computeTraversalInfo(PhyloNeighbor *top_branch, PhyloNode *top_d
                 b200lk_child c;
                 c.kind = it->node->isLeaf() ? 0 : 1;
                 c.id = it->node->isLeaf() ? it->node->id : it->slot;
-                c.length = it->length;
+                // a branch optimised earlier in a pipelined sweep: its length is still on the device (slot = branch id)
+                c.length = (!dev_len_valid_.empty() && dev_len_valid_[it->id]) ? -(double)it->id - 1.0 : it->length;
                 if (k == 0) op.left = c;
                 else if (k == 1) op.right = c;
                 else { traversal_extra.push_back(c); op.reserved++; }
@@ -825,6 +826,53 @@ void PhyloTree::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clear
     }
 }
 
+// One sweep of optimizeAllBranches (tree/phylotree.cpp:2718-2722) queued as a whole: per branch the traversal is planned on the
+// host exactly as optimizeOneBranch plans it, but the partial updates, the theta buffer, the Newton-Raphson iteration and the
+// divergence test run on the device without the host waiting; the new length stays in the engine's length table, and ops
+// planned later in the sweep refer to it by slot.  Every branch is treated as changed (clearReversePartialLh), which is what
+// the reference does unless the optimum equals the old length bit for bit.  Returns false, having done nothing, when the
+// engine has no device-resident Newton iteration for this model.
+bool PhyloTree::sweepPipelined(const std::vector<PhyloNode *> &nodes, const std::vector<PhyloNode *> &nodes2, int maxNRStep) {
+    dev_len_valid_.assign(branches_.size(), 0);
+    bool any = false;
+    for (size_t j = 0; j < nodes.size(); j++) {
+        PhyloNode *node1 = nodes[j], *node2 = nodes2[j];
+        current_it = node1->findNeighbor(node2);
+        current_it_back = node2->findNeighbor(node1);
+        const double current_len = current_it->length;
+        theta_computed = false;
+        b200lk_theta_reset(engine_);
+        PhyloNeighbor *dad_branch = current_it;
+        PhyloNode *dad = current_it_back->node;
+        int node_slot, dad_kind, dad_id;
+        branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+        pushExtraChildren();
+        const int rc = b200lk_enqueue_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
+                                                    params.min_branch_length, current_len, params.max_branch_length,
+                                                    params.min_branch_length, maxNRStep, current_it->id);
+        if (rc == B200LK_ERR_STATE && !any) {   // not available for this configuration: undo the planning of this branch
+            traversal_info.clear();
+            dev_len_valid_.clear();
+            clearAllPartialLH();
+            return false;
+        }
+        check(rc, "enqueue_newton_branch");
+        traversal_info.clear();
+        any = true;
+        theta_computed = true;
+        dev_len_valid_[current_it->id] = 1;
+        node1->clearReversePartialLh(node2);
+        node2->clearReversePartialLh(node1);
+    }
+    std::vector<double> len(branches_.size());
+    std::vector<int32_t> status(branches_.size());
+    check(b200lk_sweep_finish(engine_, (int)branches_.size(), len.data(), nullptr, status.data()), "sweep_finish");
+    for (size_t b = 0; b < branches_.size(); b++)
+        if (dev_len_valid_[b]) branches_[b].first->length = branches_[b].second->length = len[b];
+    dev_len_valid_.clear();
+    return true;
+}
+
 // tree/mtree.cpp:3040-3060 (height in branches; ties keep the first neighbour reached)
 PhyloNode *PhyloTree::findFarthestLeaf(PhyloNode *node, PhyloNode *dad) {
     if (!node) node = root;
@@ -890,7 +938,8 @@ double PhyloTree::optimizeAllBranches(int my_iterations, double tolerance, int m
     std::vector<double> lenvec;
     for (int i = 0; i < my_iterations; i++) {
         saveBranchLengths(lenvec);
-        for (size_t j = 0; j < nodes.size(); j++) optimizeOneBranch(nodes[j], nodes2[j], true, maxNRStep);
+        if (!(params.pipelined_sweep && params.fused_newton && engine_ && sweepPipelined(nodes, nodes2, maxNRStep)))
+            for (size_t j = 0; j < nodes.size(); j++) optimizeOneBranch(nodes[j], nodes2[j], true, maxNRStep);
         double new_tree_lh = computeLikelihoodFromBuffer();
         if (new_tree_lh < tree_lh - tolerance * 0.1) {
             // rare: the log-likelihood decreased; restore the branch lengths and stop (:2733-2759)

@@ -59,6 +59,8 @@ struct Params {
     bool force_norm = false;           // test hook: keep NORM_LH where the reference would switch to SAFE_LH
     int schedule = 0;
     bool fused_newton = true;          // optimizeOneBranch through b200lk_newton_branch (one C call per branch)
+    bool pipelined_sweep = false;      // optimizeAllBranches queues the whole sweep (b200lk_enqueue_newton_branch): branch lengths
+                                       // stay on the device between branches, one synchronisation per sweep
     bool plan_only = false;            // no engine: traversals are planned (flags, slots, op lists) but not executed
 };
 
@@ -189,6 +191,8 @@ protected:
     int asc_type_ = 0;
     int64_t asc_nunobs_ = 0, asc_nsite_ = 0;
     void pushExtraChildren();
+    bool sweepPipelined(const std::vector<PhyloNode *> &nodes, const std::vector<PhyloNode *> &nodes2, int maxNRStep);
+    std::vector<char> dev_len_valid_;   // by branch id: the current length lives in the engine's device length table
     std::vector<double> pattern_lh_;
 };
 

@@ -118,6 +118,7 @@ int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh,
 int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl) {
     GUARD(*logl = t->tree.optimizeAllBranches(iterations, tolerance, max_nr_step))
 }
+int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on) { t->tree.params.pipelined_sweep = on != 0; return 0; }
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t) { return t->tree.num_partial_lh_computations; }
 
 int b200pt_set_mem_save(b200pt_tree *t, int32_t on, double max_mem_size) {

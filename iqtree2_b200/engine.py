@@ -26,6 +26,7 @@ ABI_SYMBOLS = [
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
     "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment",
+    "b200lk_enqueue_newton_branch", "b200lk_sweep_finish",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2

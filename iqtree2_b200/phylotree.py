@@ -114,6 +114,10 @@ class PhyloTree:
     def optimize_one_branch(self, branch, clear_lh=True, max_nr_step=100):
         self._check(self.lib.b200pt_optimize_one_branch(self._h, branch, int(clear_lh), max_nr_step))
 
+    def set_pipelined_sweep(self, on=True):
+        """queue every optimizeAllBranches sweep as a whole on the device (one synchronisation per sweep)"""
+        self._check(self.lib.b200pt_set_pipelined_sweep(self._h, int(on)))
+
     def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
         out = C.c_double()
         self._check(self.lib.b200pt_optimize_all_branches(self._h, iterations, C.c_double(tolerance), max_nr_step, C.byref(out)))

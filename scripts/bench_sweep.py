@@ -18,6 +18,7 @@ ap.add_argument("--kind", default="dna")
 ap.add_argument("--iterations", type=int, default=1)
 ap.add_argument("--cpu-patterns", type=int, default=0, help="pattern sample for the reference arm (0 = same as --patterns)")
 ap.add_argument("--no-reference", action="store_true")
+ap.add_argument("--pipelined", action="store_true", help="queue every sweep as a whole on the device")
 a = ap.parse_args()
 model = models.make_gtr_gamma() if a.kind == "dna" else models.make_lg_gamma()
 tree = treesim.yule_tree(a.taxa, seed=1)
@@ -26,6 +27,8 @@ freq = np.ones(a.patterns)
 nwk = tree.to_newick(fmt="%.17g")
 g = PhyloTree()
 g.set_alignment(tree.names, pat, freq, model); g.set_model(model); g.read_tree(nwk)
+if a.pipelined:
+    g.set_pipelined_sweep(True)
 ll0 = g.compute_likelihood()
 g.read_tree(nwk); g.clear_all_partial_lh(); g.compute_likelihood()      # warm (allocations, first launches)
 import torch
@@ -34,7 +37,7 @@ t0 = time.perf_counter()
 ll1 = g.optimize_all_branches(iterations=a.iterations, tolerance=0.001)
 torch.cuda.synchronize()
 tg = time.perf_counter() - t0
-out = {"what": "one optimizeAllBranches call", "taxa": a.taxa, "patterns": a.patterns, "kind": a.kind, "iterations": a.iterations,
+out = {"what": "one optimizeAllBranches call", "taxa": a.taxa, "patterns": a.patterns, "kind": a.kind, "iterations": a.iterations, "pipelined": a.pipelined,
        "gpu_sec": tg, "logl_before": ll0, "logl_after": ll1, "partial_lh_updates": g.num_partial_lh_computations,
        "branches": int(len(g.branches()[2]))}
 if not a.no_reference:
