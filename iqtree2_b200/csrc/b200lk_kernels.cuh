@@ -985,7 +985,7 @@ struct Walk20Op {   // per-(op, class block), per-lane addressing state of the M
 template <bool SAFE, bool MIX, int NCASE, int BSM, int DBG = 0, bool CSP = false>
 __device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, const Walk20Op &W, const double (&Be_r)[5][3],
                                               const double (&Bi_r)[5][3], const double *s_expA, const double *s_expB,
-                                              const double *s_tabA, const double *s_tabB, const int TS, int lane) {
+                                              const double *s_tabA, const double *s_tabB, const int TS, int lane, unsigned (&csp_sc)[4]) {
     // BSM bit 0 / bit 1: the evec / inv_evec B fragments are read from shared memory at each use (one conflict-free 8-byte
     // load per lane and DMMA) instead of living in 30 registers each
     const BFrag20<(BSM & 1) != 0> Be{Be_r, W.sBe};
@@ -1134,6 +1134,7 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, cons
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
                 W.s_mhi[mt * kWarp + lane] = mhi;   // this warp's slot; the decision follows the barrier
+                csp_sc[mt] = scA + scB;            // children's scale counts, loaded at the head of the M-tile
             } else if (!SAFE) {
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
                 mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
@@ -1172,10 +1173,11 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, cons
 // category split, NORM_LH: after the barrier every warp folds the CTA's maxima (all categories of the pattern), rescales what IT
 // wrote if the pattern underflowed (tree/phylokernelnew.h:2015-2029) and warp 0 writes the pattern's scale count
 __device__ __forceinline__ void walk20_csplit_finish(const Walk20Op &W, const int C, const int cstep, const int ncase, const int nwarps,
-                                                     const unsigned *s_mhi_all, const int warp, const int lane) {
+                                                     const unsigned *s_mhi_all, const int warp, const int lane, const unsigned (&csp_sc)[4]) {
     const int g = lane >> 2, q = lane & 3;
     (void)g;
     const int lo2 = (q * 8 + (lane >> 2)) * 2, lot = 128 + (lane >> 2) * 4 + 2 * q;
+#pragma unroll
     for (int mt = 0; mt < 4; mt++) {
         unsigned mhi = 0;
         for (int w = 0; w < nwarps; w++) mhi = max(mhi, s_mhi_all[(w * 4 + mt) * kWarp + lane]);
@@ -1195,12 +1197,7 @@ __device__ __forceinline__ void walk20_csplit_finish(const Walk20Op &W, const in
                 }
             }
         }
-        if (warp == 0 && q == 0) {
-            unsigned sc = scale ? 1u : 0u;
-            if (ncase == 2) sc += W.Asc[8 * mt];
-            if (ncase >= 1) sc += W.Bsc[8 * mt];
-            W.Osc[8 * mt] = (uint16_t)sc;
-        }
+        if (warp == 0 && q == 0) W.Osc[8 * mt] = (uint16_t)(csp_sc[mt] + (scale ? 1u : 0u));
     }
 }
 
@@ -1343,12 +1340,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
                 W.sBi = W.sBe + 480;
                 const int nc = CSP ? csp_ncat : cpb, cstep = CSP ? NW : 1, coff = CSP ? warp * 20 : 0;
                 const double *eAp = s_exp + coff, *eBp = s_exp + B + coff, *tAp = s_tabA + coff, *tBp = s_tabB + coff;
-                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
-                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
-                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane);
+                unsigned csp_sc[4] = {0, 0, 0, 0};
+                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
+                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
+                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
                 if (CSP && !SAFE) {
                     __syncthreads();   // every warp of the CTA is active or has no category at all (D.C < NW): see below
-                    walk20_csplit_finish(W, nc, cstep, ncase, D.C < NW ? D.C : NW, s_mhi, warp, lane);
+                    walk20_csplit_finish(W, nc, cstep, ncase, D.C < NW ? D.C : NW, s_mhi, warp, lane, csp_sc);
                 }
             } else if (CSP && !SAFE) {
                 __syncthreads();
