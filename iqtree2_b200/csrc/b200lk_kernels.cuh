@@ -1384,9 +1384,8 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red)
     }
 }
 
-// block_reduce_store + the final sum by the LAST block to arrive (ticket counter), in exactly k_final_reduce's order (256
-// virtual threads, thread t sums blocks t, t+256, ... in order, then a binary tree): bit-identical to the two-launch form, one
-// launch fewer.  `result` may be mapped host memory: the scalars land in the caller's buffer without a copy.
+// block_reduce_store + the final sum by the LAST block to arrive (ticket counter) in a fixed order (256 virtual threads, thread t
+// sums blocks t, t+256, ... in order, then a binary tree): bit-identical to the separate final-reduction launch it replaced.  `result` may be mapped host memory: the scalars land in the caller's buffer without a copy.
 template <int NV>
 __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red, unsigned *ticket, double *result) {
     block_reduce_store<NV>(v, red);
@@ -1422,30 +1421,6 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red
         for (int j = 0; j < NV; j++) result[j] = s_fin[j][0];
         *ticket = 0;
     }
-}
-
-template <int NV>
-__global__ void __launch_bounds__(256) k_final_reduce(const double *red, int nblocks, double *result) {
-    __shared__ double s[NV][256];
-    double acc[NV];
-#pragma unroll
-    for (int j = 0; j < NV; j++) acc[j] = 0.0;
-    // fixed assignment: thread t sums blocks t, t+256, ... in order
-    for (int b = threadIdx.x; b < nblocks; b += 256)
-#pragma unroll
-        for (int j = 0; j < NV; j++) acc[j] += red[(long long)b * NV + j];
-#pragma unroll
-    for (int j = 0; j < NV; j++) s[j][threadIdx.x] = acc[j];
-    __syncthreads();
-    for (int off = 128; off > 0; off >>= 1) {
-        if (threadIdx.x < off)
-#pragma unroll
-            for (int j = 0; j < NV; j++) s[j][threadIdx.x] += s[j][threadIdx.x + off];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0)
-#pragma unroll
-        for (int j = 0; j < NV; j++) result[j] = s[j][0];
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,12 @@ def test_baseline_config_at_full_size(workload):
     if torch.cuda.get_device_properties(0).total_memory < need:
         pytest.skip("device memory too small for the full-size workload")
     tree, tips, freq, _ = bench.make_inputs(ntaxa, nptn, model)
-    g = LikelihoodEngine(model, ntaxa, nptn)
+    try:
+        g = LikelihoodEngine(model, ntaxa, nptn)
+    except Exception as ex:   # another process holds device memory: nothing to learn from an allocation failure
+        if "cudaMalloc" in str(ex) or "memory" in str(ex).lower():
+            pytest.skip(f"device memory not available for the full-size workload: {ex}")
+        raise
     g.set_tip_states(tips); g.set_pattern_freq(freq); g.set_pattern_invar(np.zeros(nptn))
     br = plan.pendant_branch_of(tree, 0)
     ops, a, b, L = plan.plan_branch(tree, br)
