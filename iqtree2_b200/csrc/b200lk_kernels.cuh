@@ -606,6 +606,11 @@ __device__ __forceinline__ unsigned abs_hi(double v) { return (unsigned)__double
 constexpr unsigned kThresholdHi = (1023u - 256u) << 20;   // high word of 2^-256: |v| < 2^-256  <=>  abs_hi(v) < this
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // TMA bulk store helpers (cp.async.bulk shared::cta -> global, bulk async-groups)
 __device__ __forceinline__ void bulk_store_issue(void *gdst, const void *ssrc, unsigned bytes) {
@@ -674,6 +679,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 if (tid == 0) bulk_store_wait_all();
                 fence_proxy_async_smem();   // this thread's shared-memory writes of the previous op, for the async proxy
             }
+            cp_async_wait_all();   // staging block o (copied asynchronously during op o-2) has landed for this thread
             __syncthreads();
             if (TST && tid == 0 && prev_dst >= 0 && !(DBG & 1))
                 bulk_store_issue(D.partial + (long long)prev_dst * D.slot_stride + prev_tile_off, s_out[(o + 1) & 1], 16 * kTile * sizeof(double));
@@ -682,9 +688,10 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             const int4 h0 = *reinterpret_cast<const int4 *>(st);
             const int h_loadA = *reinterpret_cast<const int *>(st + 2);
             const int dst = h0.x, ncase = h0.y, aid = h0.z, bid = h0.w;
-            const bool do_pre = (tid < kStageVec) && (o + 2 < nops);
-            double2 pre;
-            if (do_pre) pre = __ldg(reinterpret_cast<const double2 *>(stage + (size_t)(o + 2) * kStage4) + tid);
+            // staging block o+2 travels global -> shared with cp.async (no registers held across the op); its ring slot was
+            // op o-1's, which every thread has left (barrier above)
+            if ((tid < kStageVec) && (o + 2 < nops))
+                cp_async16(&s_stage[buf2][2 * tid], stage + (size_t)(o + 2) * kStage4 + 2 * tid);
             const int sA = sA_next, sB = sB_next;
 
             double X[16];
@@ -826,7 +833,6 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
             for (int c = 0; c < (SAFE ? 4 : 1); c++)
                 D.scale[(long long)dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
-            if (do_pre) reinterpret_cast<double2 *>(s_stage[buf2])[tid] = pre;
             buf = buf1;
             prev_dst = dst;
             prev_tile_off = tile * (16LL * kTile);
@@ -1201,11 +1207,6 @@ __device__ __forceinline__ void walk20_csplit_finish(const Walk20Op &W, const in
     }
 }
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // copy the parts of one op's staging block that the op needs (header + exp always, tabA for a tip child A, tabB when both
 // children are tips) into shared memory, asynchronously
