@@ -85,9 +85,10 @@ def run_super(args, rank, world, local_rank):
     from iqtree2_b200.supertree import PhyloSuperTree
     ntaxa, nparts = args.taxa or 100, args.parts or 500
     tree, parts = make_super_inputs(ntaxa, nparts)
-    cost = [-(p["pat"].shape[1] * p["model"].nstates) for p in parts]
-    order = np.argsort(cost, kind="stable")
-    mine = [int(i) for k, i in enumerate(order) if k % world == rank]
+    from iqtree2_b200.sharded import deal_partitions
+    cost = [p["pat"].shape[1] * p["model"].nstates for p in parts]
+    order = np.argsort(-np.asarray(cost, dtype=np.float64), kind="stable")
+    mine = deal_partitions(cost, world, rank)
     if args.impl == "reference":
         if rank != 0:
             return 0

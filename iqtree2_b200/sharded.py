@@ -100,3 +100,13 @@ class ShardedLikelihood:
     def close(self):
         if self.engine:
             self.engine.close()
+
+
+def deal_partitions(costs, world: int, rank: int):
+    """Partition model (PartitionModel / PhyloSuperTree): whole partitions go to ranks, most expensive first (the cost order of
+    PhyloSuperTree::computePartitionOrder, tree/phylosupertree.cpp:653-695: taxa x patterns x states), round-robin, so that
+    every rank gets the same mix.  Returns the partition indices of `rank`.  The only exchange of a partition-sharded
+    evaluation is the sum of the ranks' (logL, df, ddf)."""
+    import numpy as np
+    order = np.argsort(-np.asarray(costs, dtype=np.float64), kind="stable")
+    return [int(i) for k, i in enumerate(order) if k % world == rank]
