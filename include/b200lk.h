@@ -200,6 +200,14 @@ void *b200lk_pattern_lh_dev(b200lk_engine *e);
 int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot);
 int b200lk_rell(b200lk_engine *e, float *rell /* [nboot] */);
 
+/* ---- alignment -> site patterns (Alignment::addPattern, alignment/alignment.cpp:1092-1133; buildPattern :1725) ------
+ * states: [ntaxa][nsite] state codes, sequence-major.  Returns the distinct columns in FIRST-OCCURRENCE order as
+ * patterns [ntaxa][nptn] (row stride nptn; capacity ntaxa*nsite), their frequencies ptn_freq [nptn] (capacity nsite) and
+ * site_pattern [nsite] — what the reference's hash-map loop builds one site at a time; all-gap columns are kept, as there.
+ * Stand-alone (no engine).  B200LK_ERR_STATE: four hash seeds in a row produced a 64-bit collision (never observed). */
+int b200lk_compress_patterns(int32_t device, const uint8_t *states, int32_t ntaxa, int64_t nsite, uint8_t *patterns,
+                             double *ptn_freq, int32_t *site_pattern, int64_t *nptn);
+
 /* ---- measurement --------------------------------------------------------------------------------------------- */
 /* When enabled, every call brackets its kernel groups with CUDA events on the engine stream. */
 int b200lk_set_profiling(b200lk_engine *e, int32_t on);

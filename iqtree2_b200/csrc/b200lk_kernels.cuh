@@ -1073,7 +1073,10 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, cons
         } else {
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
-                const double2 t = *reinterpret_cast<const double2 *>(tA + c * c20 + 8 * nt);   // nt = 2, q >= 2: row padding
+                // the third state tile holds states 16..19 only: lanes q >= 2 would read past the category (and, for the last
+                // category of the last row, past the table: compute-sanitizer) — their values are never used
+                double2 t = make_double2(0.0, 0.0);
+                if (nt < 2 || q < 2) t = *reinterpret_cast<const double2 *>(tA + c * c20 + 8 * nt);
                 a[nt][0] = t.x; a[nt][1] = t.y;
             }
         }
@@ -1083,7 +1086,8 @@ __device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, cons
         } else {
 #pragma unroll
             for (int nt = 0; nt < 3; nt++) {
-                const double2 t = *reinterpret_cast<const double2 *>(tB + c * c20 + 8 * nt);
+                double2 t = make_double2(0.0, 0.0);
+                if (nt < 2 || q < 2) t = *reinterpret_cast<const double2 *>(tB + c * c20 + 8 * nt);
                 b[nt][0] = t.x; b[nt][1] = t.y;
             }
         }

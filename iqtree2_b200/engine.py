@@ -26,7 +26,7 @@ ABI_SYMBOLS = [
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
     "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment",
-    "b200lk_enqueue_newton_branch", "b200lk_sweep_finish",
+    "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -274,6 +274,24 @@ class LikelihoodEngine:
 
     def get_tip_partial_lh(self):
         return self._get("b200lk_get_tip_partial_lh", (self.model.state_unknown + 1) * self.nmix * self.n)
+
+
+def compress_patterns(states, device=0):
+    """Site-pattern compression on the device (b200lk_compress_patterns): distinct columns of states [ntaxa][nsite] in
+    first-occurrence order -> (patterns [ntaxa][nptn], ptn_freq [nptn], site_pattern [nsite])."""
+    lib = load_library()
+    st = np.ascontiguousarray(states, dtype=np.uint8)
+    ntaxa, nsite = st.shape
+    pat = np.zeros(ntaxa * nsite, dtype=np.uint8)
+    freq = np.zeros(nsite)
+    sp = np.zeros(nsite, dtype=np.int32)
+    nptn = C.c_int64()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.b200lk_compress_patterns(C.c_int32(device), p(st), C.c_int32(ntaxa), C.c_int64(nsite), p(pat), p(freq), p(sp), C.byref(nptn))
+    if rc != 0:
+        raise EngineError(f"b200lk_compress_patterns failed ({rc}); there is no CPU fallback")
+    n = nptn.value
+    return pat[: ntaxa * n].reshape(ntaxa, n).copy(), freq[:n].copy(), sp
 
 
 def to_simd_layout(partial_v1: np.ndarray, V: int) -> np.ndarray:
