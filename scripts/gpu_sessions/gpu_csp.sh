@@ -13,4 +13,4 @@ PY
 done; done
 python scripts/bench_sweep.py --taxa 100 --patterns 20000 --kind aa --no-reference | cut -c1-200
 python scripts/bench_sweep.py --taxa 100 --patterns 2000 --kind aa --no-reference | cut -c1-200
-HT=8 bash scripts/gpu_super.sh
+HT=8 bash scripts/gpu_sessions/gpu_super.sh
