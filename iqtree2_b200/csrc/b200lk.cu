@@ -513,22 +513,25 @@ struct Walk20Cfg { int nw; const void *f[4]; };
     { NW, { (const void *)k_walk_n20_mma<false, false, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, false, NW, BSM, MINB>, \
             (const void *)k_walk_n20_mma<false, true, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, true, NW, BSM, MINB> } }
 static const Walk20Cfg walk20_cfgs[] = {
-    W20CFG(4, 0, 3),     // 0: 12 warps/SM, both matrices as register-resident B fragments
+    { 4, { (const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, false, true>, (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, false, true>,
+           (const void *)k_walk_n20_mma<false, true, 4, 0, 3, 0, false, true>, (const void *)k_walk_n20_mma<true, true, 4, 0, 3, 0, false, true> } },
+                         // 0 (default): 12 warps/SM, both matrices as register-resident B fragments, staging by TMA bulk load
     W20CFG(8, 2, 2),     // 1: 16 warps/SM, inv_evec fragments from shared memory
     W20CFG(8, 3, 2),     // 2: 16 warps/SM, both matrices from shared memory
     W20CFG(6, 3, 3),     // 3: 18 warps/SM
     W20CFG(4, 0, 3),     // 4: as 0 with fixed 128-pattern tiles (A/B of the balanced tiling)
     W20CFG(10, 3, 2),    // 5: 20 warps/SM
+    W20CFG(4, 0, 3),     // 6: as 0 with cp.async staging (16-byte copies by every thread; 6.63 vs 6.50 ms on config 3)
 #ifdef B200LK_DIAG
 #define W20DBG(DBG) { 4, { (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, \
                            (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG> } }
-    W20DBG(1), W20DBG(2), W20DBG(3), W20DBG(4),   // 6: no stores, 7: no loads, 8: neither, 9: no DMMAs (wrong results; diagnosis)
+    W20DBG(1), W20DBG(2), W20DBG(3), W20DBG(4),   // 7: no stores, 8: no loads, 9: neither, 10: no DMMAs (wrong results; diagnosis)
 #endif
 };
 constexpr int kNumWalk20Cfgs = (int)(sizeof(walk20_cfgs) / sizeof(walk20_cfgs[0]));
 // category-split form for small problems (single class, >= 2 categories, fewer 32-pattern blocks than resident CTAs) [SAFE]
-static const void *const walk20_csp[2] = {(const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, true>,
-                                          (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, true>};
+static const void *const walk20_csp[2] = {(const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, true, true>,
+                                          (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, true, true>};
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);

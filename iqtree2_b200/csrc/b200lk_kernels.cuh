@@ -1220,14 +1220,46 @@ __device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, 
     for (int k = tid; k < n_total; k += nthreads) cp_async16(sdst + 2 * k, gsrc + 2 * k);
 }
 
+// The same copy as ONE TMA bulk load (cp.async.bulk global -> shared, completion on an mbarrier): the needed part of a staging
+// block is a contiguous prefix (header | exp | tabA | tabB), so a single thread issues one instruction per op instead of up to
+// 16 cp.async per thread, and the consumers wait on the mbarrier's phase instead of on their own copy groups.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void stage20_fetch_tma(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, unsigned long long *bar) {
+    const unsigned bytes = (unsigned)(((4 + 2 * B) + (ncase <= 1 ? tab_doubles : 0) * (ncase == 0 ? 2 : 1)) * sizeof(double));
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
+
 // NW  warps per CTA (tile = 32*NW patterns; the two staging buffers are per CTA, so larger CTAs leave room for more warps);
 // BSM the evec (bit 0) / inv_evec (bit 1) B fragments come from shared memory (7.7 KB per CTA) instead of 2 x 30 registers;
 // MINB minimum resident CTAs per SM (register cap).  Warps whose 32 patterns lie beyond Ppad (a multiple of 128, not of
 // 32*NW) idle through the barriers.
-template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0, bool CSP = false>
+template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0, bool CSP = false, bool TMA = false>
 __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter,
                                                                  int ntiles) {
     static_assert(!(CSP && MIX), "category split serves single-class models");
+    __shared__ __align__(8) unsigned long long s_bar[2];   // TMA: one mbarrier per staging buffer
+    unsigned seq = 0;                                      // staging blocks fetched so far by this CTA: block -> buffer seq & 1
+    if (TMA) {
+        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+    }
     constexpr int NT = NW * 32;
     // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
     // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
@@ -1308,21 +1340,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const dou
         // per op: the long-scoreboard stalls of the per-op code in the ncu source view)
         int4 h_next = *reinterpret_cast<const int4 *>(stage);
         int4 h_next2 = nvo > 1 ? *reinterpret_cast<const int4 *>(stage + stage_sz) : h_next;
-        stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid, NT);
+        if (TMA) { if (tid == 0) stage20_fetch_tma(s_dyn20 + (size_t)(seq & 1) * stage_sz, stage, h_next.y, B, tab_doubles, &s_bar[seq & 1]); }
+        else stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid, NT);
         unsigned stA_next, stB_next;
         tip_states(h_next, stA_next, stB_next);
         int m = 0;
-        for (int v = 0; v < nvo; v++) {
-            double *sb = s_dyn20 + (size_t)(v & 1) * stage_sz;
+        for (int v = 0; v < nvo; v++, seq++) {
+            double *sb = s_dyn20 + (size_t)((TMA ? seq : (unsigned)v) & 1) * stage_sz;
             const int4 h = h_next;
             const unsigned stA = stA_next, stB = stB_next;
             h_next = h_next2;
             if (v + 2 < nvo) h_next2 = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 2) * stage_sz);
             if (MIX) { if (BSM != 3) load_frags(m); if (BSM) load_frags_smem(m, v & 1); }
-            cp_async_wait_all();
+            if (TMA) mbar_wait(&s_bar[seq & 1], (seq >> 1) & 1);   // block v has landed (the mbarrier's phase of this use)
+            else cp_async_wait_all();
             __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
             if (v + 1 < nvo) {
-                stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid, NT);
+                if (TMA) {
+                    if (tid == 0)
+                        stage20_fetch_tma(s_dyn20 + (size_t)((seq + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles,
+                                          &s_bar[(seq + 1) & 1]);
+                } else
+                    stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid, NT);
                 if (!MIX || m + 1 == nblk) tip_states(h_next, stA_next, stB_next);   // the tips change with the op, not with the class
             }
             if (active) {

@@ -2,7 +2,7 @@
 # A/B of the 20-state walker variants on config 3 (and a C60 slice): kernel ms, logL
 mkdir -p gpurun_out/s8
 for v in ${VARIANTS:-0 5 6 7 8 9}; do
-  timeout 300 python bench.py --workload aa_200x100k_lg_g4 --steps 10 --warmup 3 --no-cpu-baseline --variant $v > gpurun_out/s8/v20_$v.json 2> gpurun_out/s8/v20_$v.err
+  timeout 120 python bench.py --workload aa_200x100k_lg_g4 --steps 10 --warmup 3 --no-cpu-baseline --variant $v > gpurun_out/s8/v20_$v.json 2> gpurun_out/s8/v20_$v.err
   python - <<PY
 import json
 try:

@@ -67,8 +67,8 @@ def test_parity_small(kind, safe):
     compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_WALKER, br)
 
 
-@pytest.mark.parametrize("kind,variant", [("dna", 1), ("dna", 2), ("aa", 1), ("aa", 2), ("aa", 3), ("aa", 4), ("aa", 5),
-                                          ("aa_c4", 0), ("aa_c4", 2), ("aa_c4", 3), ("aa_fused", 1)])
+@pytest.mark.parametrize("kind,variant", [("dna", 1), ("dna", 2), ("aa", 1), ("aa", 2), ("aa", 3), ("aa", 4), ("aa", 5), ("aa", 6),
+                                          ("aa_c4", 0), ("aa_c4", 2), ("aa_c4", 3), ("aa_c4", 6), ("aa_fused", 1), ("aa_fused", 6)])
 @pytest.mark.parametrize("safe", [False, True])
 def test_parity_kernel_variants(kind, variant, safe):
     """Every selectable walker configuration (4-state: direct / TMA bulk / burst stores; 20-state: CTA shapes, B fragments in
