@@ -2,6 +2,7 @@
 #include "phylotree_b200.h"
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -956,6 +957,169 @@ double PhyloTree::optimizeAllBranches(int my_iterations, double tolerance, int m
     }
     curScore = tree_lh;
     return tree_lh;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NNI (second half): the reference evaluates both NNIs of an inner branch on throw-away copies of
+// the six neighbours whose CLVs the evaluation overwrites, backed by the two nni_partial_lh buffers; here the copies
+// are backed by the engine's two spare slots, so the evaluation is a few partial updates and Newton iterations on
+// resident CLVs and leaves nothing to recompute afterwards.
+// ---------------------------------------------------------------------------------------------------------------
+static void swapNeighbors(PhyloNode *node1, int k1, PhyloNode *node2, int k2) {   // Node::updateNeighbor x 4 (:4204-4208)
+    PhyloNeighbor *node1_nei = node1->neighbors[k1], *node2_nei = node2->neighbors[k2];
+    node1->neighbors[k1] = node2_nei;
+    node2_nei->node->findNeighbor(node2)->node = node1;
+    node2->neighbors[k2] = node1_nei;
+    node1_nei->node->findNeighbor(node1)->node = node2;
+}
+
+static int neighborPos(const PhyloNode *node, const PhyloNode *to) {
+    for (size_t k = 0; k < node->neighbors.size(); k++)
+        if (node->neighbors[k]->node == to) return (int)k;
+    throw std::runtime_error("nodes are not adjacent");
+}
+
+NNIMove PhyloTree::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves) {
+    initializeAllPartialLh();
+    if (params.plan_only || !engine_) throw std::runtime_error("getBestNNIForBran needs an engine");
+    if (params.lh_mem_save == LM_MEM_SAVE) throw std::runtime_error("getBestNNIForBran: not available with -mem");
+    if (node1->isLeaf() || node2->isLeaf() || node1->neighbors.size() != 3 || node2->neighbors.size() != 3)
+        throw std::runtime_error("getBestNNIForBran: needs an inner branch between two degree-3 nodes");
+    const int IT_NUM = params.nni5 ? 6 : 2;
+    struct Saved { PhyloNode *owner; int pos; PhyloNeighbor *nei; } saved[6];
+    int id = 0;
+    saved[id++] = {node1, neighborPos(node1, node2), nullptr};
+    saved[id++] = {node2, neighborPos(node2, node1), nullptr};
+    if (params.nni5) {
+        for (auto *it : node1->neighbors) if (it->node != node2) saved[id++] = {it->node, neighborPos(it->node, node1), nullptr};
+        for (auto *it : node2->neighbors) if (it->node != node1) saved[id++] = {it->node, neighborPos(it->node, node2), nullptr};
+    } else {
+        reorientPartialLh(node1->findNeighbor(node2), node1);
+        reorientPartialLh(node2->findNeighbor(node1), node2);
+    }
+    // save the neighbours and put copies in their place; a copy of a neighbour that holds a CLV gets a spare slot (:4127-4143)
+    int mem_id = 0;
+    PhyloNeighbor copies[6];
+    for (id = 0; id < IT_NUM; id++) {
+        Saved &sv = saved[id];
+        sv.nei = sv.owner->neighbors[sv.pos];
+        copies[id] = *sv.nei;
+        copies[id].partial_lh_computed = false;
+        copies[id].slot = -1;
+        if (sv.nei->slot >= 0) copies[id].slot = max_lh_slots + mem_id++;
+        sv.owner->neighbors[sv.pos] = &copies[id];
+    }
+    if (mem_id != 2) throw std::runtime_error("getBestNNIForBran: expected two CLVs around the branch");
+    PhyloNeighbor *node12_it = node1->findNeighbor(node2), *node21_it = node2->findNeighbor(node1);
+
+    NNIMove local[2];
+    if (!nniMoves) nniMoves = local;
+    if (!nniMoves[0].node1) {   // the first other neighbour of node1 against each other neighbour of node2 (:4168-4183)
+        int cnt = 0;
+        for (int k1 = 0; k1 < 3 && cnt == 0; k1++)
+            if (node1->neighbors[k1]->node != node2)
+                for (int k2 = 0; k2 < 3; k2++)
+                    if (node2->neighbors[k2]->node != node1) {
+                        nniMoves[cnt].node1Nei_it = k1;
+                        nniMoves[cnt].node2Nei_it = k2;
+                        cnt++;
+                    }
+    }
+    nniMoves[0].node1 = nniMoves[1].node1 = node1;
+    nniMoves[0].node2 = nniMoves[1].node2 = node2;
+    nniMoves[0].newloglh = nniMoves[1].newloglh = -DBL_MAX;
+    const double backupScore = curScore;
+
+    int swapped = -1;   // the move whose swap is in place
+    auto restore = [&]() {
+        if (swapped >= 0) swapNeighbors(node1, nniMoves[swapped].node1Nei_it, node2, nniMoves[swapped].node2Nei_it);
+        for (id = IT_NUM - 1; id >= 0; id--) {   // restore the neighbours (:4284-4299)
+            Saved &sv = saved[id];
+            if (sv.owner->neighbors[sv.pos] == current_it) current_it = sv.nei;
+            if (sv.owner->neighbors[sv.pos] == current_it_back) current_it_back = sv.nei;
+            sv.owner->neighbors[sv.pos] = sv.nei;
+        }
+        // the four outer branches: the outward neighbours were re-optimised, their saved partners still hold the old lengths
+        for (auto *it : node1->neighbors) if (it->node != node2) it->length = it->node->findNeighbor(node1)->length;
+        for (auto *it : node2->neighbors) if (it->node != node1) it->length = it->node->findNeighbor(node2)->length;
+    };
+    try {
+        for (int cnt = 0; cnt < 2; cnt++) {
+            const int k1 = nniMoves[cnt].node1Nei_it, k2 = nniMoves[cnt].node2Nei_it;
+            reorientPartialLh(node12_it, node1);
+            reorientPartialLh(node21_it, node2);
+            swapNeighbors(node1, k1, node2, k2);
+            swapped = cnt;
+            for (int step = 0; step < params.nni5_num_eval; step++) {
+                node12_it->partial_lh_computed = false;
+                node21_it->partial_lh_computed = false;
+                int i = 1;
+                if (params.nni5) {
+                    for (int k = 0; k < 3; k++) {
+                        PhyloNode *other = node1->neighbors[k]->node;
+                        if (other == node2) continue;
+                        other->findNeighbor(node1)->partial_lh_computed = false;
+                        optimizeOneBranch(node1, other, false, NNI_MAX_NR_STEP);
+                        nniMoves[cnt].newLen[i++] = node1->findNeighbor(other)->length;
+                    }
+                    node21_it->partial_lh_computed = false;
+                }
+                optimizeOneBranch(node1, node2, false, NNI_MAX_NR_STEP);
+                nniMoves[cnt].newLen[0] = node12_it->length;
+                if (params.nni5) {
+                    for (int k = 0; k < 3; k++) {
+                        PhyloNode *other = node2->neighbors[k]->node;
+                        if (other == node1) continue;
+                        other->findNeighbor(node2)->partial_lh_computed = false;
+                        optimizeOneBranch(node2, other, false, NNI_MAX_NR_STEP);
+                        nniMoves[cnt].newLen[i++] = node2->findNeighbor(other)->length;
+                    }
+                    node12_it->partial_lh_computed = false;
+                }
+            }
+            double score = computeLikelihoodFromBuffer();
+            nniMoves[cnt].newloglh = score;
+            if (nniMoves[cnt].ptnlh) computePatternLikelihood(nniMoves[cnt].ptnlh, &score);
+            reorientPartialLh(node12_it, node1);
+            reorientPartialLh(node21_it, node2);
+            swapNeighbors(node1, k1, node2, k2);   // swap back: the positions hold each other's neighbour
+            swapped = -1;
+        }
+    } catch (...) {   // leave the tree as it was (the CLV flags of the six neighbours are the saved ones)
+        restore();
+        throw;
+    }
+    restore();
+    curScore = backupScore;
+    return nniMoves[0].newloglh > nniMoves[1].newloglh ? nniMoves[0] : nniMoves[1];
+}
+
+void PhyloTree::doNNI(const NNIMove &move, bool clearLH) {
+    PhyloNode *node1 = move.node1, *node2 = move.node2;
+    if (!node1 || !node2 || node1->neighbors.size() != 3 || node2->neighbors.size() != 3) throw std::runtime_error("doNNI: bad move");
+    if (initialized_ && !mem_slots.enabled) {   // reorient partial_lh before the swap (:3978-3982)
+        reorientPartialLh(node1->findNeighbor(node2), node1);
+        reorientPartialLh(node2->findNeighbor(node1), node2);
+    }
+    swapNeighbors(node1, move.node1Nei_it, node2, move.node2Nei_it);
+    PhyloNeighbor *nei12 = node1->findNeighbor(node2), *nei21 = node2->findNeighbor(node1);
+    if (clearLH) {
+        nei12->partial_lh_computed = nei21->partial_lh_computed = false;
+        nei12->size = nei21->size = 0;
+        node2->clearReversePartialLh(node1);
+        node1->clearReversePartialLh(node2);
+    }
+    theta_computed = false;
+}
+
+void PhyloTree::changeNNIBrans(const NNIMove &move) {
+    PhyloNode *node1 = move.node1, *node2 = move.node2;
+    node1->findNeighbor(node2)->length = node2->findNeighbor(node1)->length = move.newLen[0];
+    if (params.nni5) {
+        int i = 1;
+        for (auto *it : node1->neighbors) if (it->node != node2) { it->length = it->node->findNeighbor(node1)->length = move.newLen[i]; i++; }
+        for (auto *it : node2->neighbors) if (it->node != node1) { it->length = it->node->findNeighbor(node2)->length = move.newLen[i]; i++; }
+    }
 }
 
 }  // namespace b200

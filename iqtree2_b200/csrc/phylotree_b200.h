@@ -62,6 +62,21 @@ struct Params {
     bool pipelined_sweep = false;      // optimizeAllBranches queues the whole sweep (b200lk_enqueue_newton_branch): branch lengths
                                        // stay on the device between branches, one synchronisation per sweep
     bool plan_only = false;            // no engine: traversals are planned (flags, slots, op lists) but not executed
+    bool nni5 = true;                  // utils/tools.cpp:1155: NNI evaluation re-optimises the five branches around the move
+    int nni5_num_eval = 1;             // utils/tools.cpp:1156
+};
+
+const int NNI_MAX_NR_STEP = 10;        // utils/pllnni.cpp:42
+
+// tree/phylotree.h:169-191.  The reference keeps NeighborVec iterators to the two swapped neighbours; here their positions
+// in node1->neighbors / node2->neighbors.
+struct NNIMove {
+    PhyloNode *node1 = nullptr, *node2 = nullptr;
+    int node1Nei_it = -1, node2Nei_it = -1;
+    double newloglh = 0.0;
+    double newLen[5] = {0.0, 0.0, 0.0, 0.0, 0.0};   // [0] central branch; nni5: [1..2] node1's other branches, [3..4] node2's
+    double *ptnlh = nullptr;                        // if set: pattern log-likelihoods of the swapped topology (nptn doubles)
+    bool operator<(const NNIMove &rhs) const { return newloglh > rhs.newloglh; }
 };
 
 // tree/memslot.h, tree/memslot.cpp: the slot table of the memory-saving mode.  Same operations, same eviction rule
@@ -133,6 +148,13 @@ public:
     double minimizeNewton(double x1, double xguess, double x2, double xacc, double &d2l, int maxNRStep = 100);
     virtual void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100);
     virtual double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);
+
+    // ---- NNI evaluation on the resident CLVs (tree/phylotree.cpp:3975-4322) ------------------------------------------
+    // Evaluates the two NNIs around the inner branch (node1, node2) on the engine's two spare slots (nni_partial_lh): the
+    // CLVs, flags and lengths of the current tree are untouched on return.  nniMoves: optional array of two, filled.
+    NNIMove getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves = nullptr);
+    void doNNI(const NNIMove &move, bool clearLH = true);   // :3947-4036
+    void changeNNIBrans(const NNIMove &move);               // :4038-4067
 
     // ---- tree access ----------------------------------------------------------------------------------------------
     PhyloNode *findNodeName(const std::string &name) const;

@@ -118,6 +118,56 @@ int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh,
 int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl) {
     GUARD(*logl = t->tree.optimizeAllBranches(iterations, tolerance, max_nr_step))
 }
+// node1 = end a, node2 = end b of the branch as b200pt_get_branches reports them; move m swaps the first other neighbour of
+// node1 with the m-th other neighbour of node2 (tree/phylotree.cpp:4168-4183)
+static void nniMovesOf(b200pt_tree *t, int branch, b200::NNIMove mv[2]) {
+    b200::PhyloNode *a, *b;
+    ends(t, branch, a, b);
+    if (a->isLeaf() || b->isLeaf() || a->neighbors.size() != 3 || b->neighbors.size() != 3)
+        throw std::runtime_error("NNI needs an inner branch between two degree-3 nodes");
+    int k1 = -1, cnt = 0;
+    for (int k = 0; k < 3 && k1 < 0; k++) if (a->neighbors[k]->node != b) k1 = k;
+    for (int k = 0; k < 3; k++)
+        if (b->neighbors[k]->node != a) {
+            mv[cnt].node1 = a; mv[cnt].node2 = b;
+            mv[cnt].node1Nei_it = k1; mv[cnt].node2Nei_it = k;
+            cnt++;
+        }
+}
+int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t nni5, double *score, double *new_len, int32_t *swap_nodes,
+                                 int32_t *outer_nodes, double *pattern_lh) {
+    GUARD({
+        b200::NNIMove mv[2];
+        nniMovesOf(t, branch, mv);
+        const int64_t nptn = t->tree.getAlnNPattern();
+        if (pattern_lh) { mv[0].ptnlh = pattern_lh; mv[1].ptnlh = pattern_lh + nptn; }
+        t->tree.params.nni5 = nni5 != 0;
+        b200::PhyloNode *node1 = mv[0].node1, *node2 = mv[0].node2;
+        t->tree.getBestNNIForBran(node1, node2, mv);
+        for (int m = 0; m < 2; m++) {
+            score[m] = mv[m].newloglh;
+            for (int i = 0; i < 5; i++) new_len[m * 5 + i] = (i == 0 || nni5) ? mv[m].newLen[i] : 0.0;
+            b200::PhyloNode *sa = node1->neighbors[mv[m].node1Nei_it]->node, *sc = node2->neighbors[mv[m].node2Nei_it]->node;
+            swap_nodes[m * 2] = sa->id; swap_nodes[m * 2 + 1] = sc->id;
+            int k = 0;   // the branches of newLen[1..4]: node1's other neighbours, then node2's, in the swapped topology
+            for (auto *it : node1->neighbors) if (it->node != node2) outer_nodes[m * 4 + k++] = (it->node == sa ? sc : it->node)->id;
+            for (auto *it : node2->neighbors) if (it->node != node1) outer_nodes[m * 4 + k++] = (it->node == sc ? sa : it->node)->id;
+        }
+    })
+}
+int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh) {
+    GUARD({
+        if (move < 0 || move > 1) throw std::runtime_error("move must be 0 or 1");
+        b200::NNIMove mv[2];
+        nniMovesOf(t, branch, mv);
+        t->tree.doNNI(mv[move], clear_lh != 0);
+        if (new_len) {
+            t->tree.params.nni5 = nni5 != 0;
+            for (int i = 0; i < 5; i++) mv[move].newLen[i] = (i == 0 || nni5) ? new_len[i] : 0.0;
+            t->tree.changeNNIBrans(mv[move]);
+        }
+    })
+}
 int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on) { t->tree.params.pipelined_sweep = on != 0; return 0; }
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t) { return t->tree.num_partial_lh_computations; }
 

@@ -192,6 +192,23 @@ class RefTree:
         k = lib().iqref_get_branches(self._h, _p(masks), _p(lens))
         return {frozenset(np.nonzero(masks[b])[0].tolist()): float(lens[b]) for b in range(k)}
 
+    def best_nni(self, split, nni5=True):
+        """PhyloTree::getBestNNIForBran on the inner branch with that split (side not containing taxon 0): two dicts with
+        score, new_len, swap = (leaf sets of the two swapped subtrees), outer = leaf sets of the branches of new_len[1..4]"""
+        nt = self.ntaxa
+        mask = np.zeros(nt, dtype=np.uint8)
+        mask[sorted(split)] = 1
+        score, new_len = np.zeros(2), np.zeros((2, 5))
+        sw, outer = np.zeros((2, 2, nt), dtype=np.uint8), np.zeros((2, 4, nt), dtype=np.uint8)
+        L = lib()
+        L.iqref_best_nni.restype = C.c_int
+        rc = L.iqref_best_nni(self._h, _p(mask), C.c_int(1 if nni5 else 0), _p(score), _p(new_len), _p(sw), _p(outer))
+        if rc != 0:
+            raise ValueError("no inner branch with that split")
+        fs = lambda m: frozenset(np.nonzero(m)[0].tolist())
+        return [dict(score=float(score[m]), new_len=new_len[m].tolist() if nni5 else new_len[m, :1].tolist(),
+                     swap=(fs(sw[m, 0]), fs(sw[m, 1])), outer=[fs(outer[m, k]) for k in range(4)]) for m in range(2)]
+
     def time_eval(self, leaf=0, reps=3):
         ll, df, ddf, mean = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         best = lib().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))

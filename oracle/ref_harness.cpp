@@ -189,6 +189,8 @@ const std::string &StartTree::Factory::getNameOfDefaultTreeBuilder() {
     return name;
 }
 
+int NNI_MAX_NR_STEP = 10;   // utils/pllnni.cpp:42 (PLL glue, not compiled); read by getBestNNIForBran
+
 extern "C" {
 
 struct iqref_desc {
@@ -474,6 +476,52 @@ int iqref_get_branches(void *hv, uint8_t *masks /* [nbranch][ntaxa] */, double *
         lengths[b] = n1[b]->findNeighbor(n2[b])->length;
     }
     return (int)n1.size();
+}
+
+// PhyloTree::getBestNNIForBran (tree/phylotree.cpp:4069) on the inner branch whose side without taxon 0 has leaf set `mask`,
+// with Params::nni5 = nni5.  For each of the two moves: score[m] = NNIMove::newloglh, new_len[m][5] = newLen[0..4] (only [0]
+// without nni5), swap_masks[m][2][ntaxa] = leaf sets of the two swapped subtrees (node1's, node2's), outer_masks[m][4][ntaxa] =
+// leaf sets of the subtrees on the branches newLen[1..4] belong to (node1's neighbours, then node2's, after the swap).
+// Returns 0, or -1 when no inner branch has that split.
+int iqref_best_nni(void *hv, const uint8_t *mask, int nni5, double *score, double *new_len, uint8_t *swap_masks, uint8_t *outer_masks) {
+    Handle *h = (Handle *)hv;
+    NodeVector n1, n2;
+    h->tree->getBranches(n1, n2);
+    PhyloNode *node1 = nullptr, *node2 = nullptr;
+    for (size_t b = 0; b < n1.size(); b++) {
+        if (n1[b]->isLeaf() || n2[b]->isLeaf()) continue;
+        std::vector<uint8_t> m(h->ntaxa, 0);
+        collect_leaves(n2[b], n1[b], m);
+        if (m[0]) for (auto &x : m) x = !x;
+        if (memcmp(m.data(), mask, h->ntaxa) == 0) { node1 = (PhyloNode *)n1[b]; node2 = (PhyloNode *)n2[b]; break; }
+    }
+    if (!node1) return -1;
+    Params::getInstance().nni5 = nni5 != 0;
+    NNIMove moves[2];
+    moves[0].ptnlh = moves[1].ptnlh = nullptr;
+    moves[0].node1 = nullptr;
+    h->tree->getBestNNIForBran(node1, node2, moves);
+    node1 = moves[0].node1; node2 = moves[0].node2;
+    std::vector<Node *> o1, o2;
+    FOR_NEIGHBOR_IT(node1, node2, it) o1.push_back((*it)->node);
+    FOR_NEIGHBOR_IT(node2, node1, it) o2.push_back((*it)->node);
+    auto put = [&](uint8_t *dst, Node *sub, Node *from) {
+        std::vector<uint8_t> m(h->ntaxa, 0);
+        collect_leaves(sub, from, m);
+        memcpy(dst, m.data(), h->ntaxa);
+    };
+    for (int m = 0; m < 2; m++) {
+        score[m] = moves[m].newloglh;
+        for (int i = 0; i < 5; i++) new_len[m * 5 + i] = (i == 0 || nni5) && !moves[m].newLen[i].empty() ? moves[m].newLen[i][0] : 0.0;
+        Node *a = (*moves[m].node1Nei_it)->node, *c = (*moves[m].node2Nei_it)->node;
+        put(swap_masks + (size_t)(m * 2 + 0) * h->ntaxa, a, node1);
+        put(swap_masks + (size_t)(m * 2 + 1) * h->ntaxa, c, node2);
+        // neighbour lists after the swap: a's position in node1 holds c, c's position in node2 holds a
+        int k = 0;
+        for (Node *x : o1) put(outer_masks + (size_t)(m * 4 + k++) * h->ntaxa, x == a ? c : x, x == a ? node2 : node1);
+        for (Node *x : o2) put(outer_masks + (size_t)(m * 4 + k++) * h->ntaxa, x == c ? a : x, x == c ? node1 : node2);
+    }
+    return 0;
 }
 
 // entries of traversal_info left by the last computeLikelihoodBranch / computeLikelihoodDerv call (= partial updates it ran;

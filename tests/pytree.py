@@ -3,7 +3,8 @@ slot re-orientation, traversal order, Newton-Raphson branch optimisation) over A
 in the tests, over the CPU oracle.  The C++ host mirror over the CUDA engine is checked against it.
 
 Follows tree/phylotree.cpp:1233-1274 (computeLikelihood), :2594-2774 (optimizeOneBranch / optimizeAllBranches),
-:5898-6028 (reorientPartialLh / computeTraversalInfo), tree/mtree.cpp:3040-3082, utils/optimization.cpp:422-499.
+:3975-4067 (doNNI / changeNNIBrans), :4069-4322 (getBestNNIForBran), :5898-6028 (reorientPartialLh /
+computeTraversalInfo), tree/mtree.cpp:3040-3082, utils/optimization.cpp:422-499.
 """
 from __future__ import annotations
 
@@ -337,3 +338,125 @@ class PyTree:
 
     def lengths(self):
         return np.array([ab.length for ab, _ in self.branches])
+
+    # ---- NNI (tree/phylotree.cpp:3975-4322) ---------------------------------------------------------------------
+    NNI_MAX_NR_STEP = 10   # utils/pllnni.cpp:42
+
+    @staticmethod
+    def _copy_nei(nei, slot):
+        """PhyloNeighbor::newNeighbor (tree/phylonode.h:78-95): same node / length / id / size, nothing computed"""
+        c = Nei(nei.node, nei.length, nei.id)
+        c.size, c.slot = nei.size, slot
+        return c
+
+    def get_best_nni_for_bran(self, node1, node2, nni5=True, nni5_num_eval=1):
+        """returns two moves: dict(score, new_len[5 or 1], swap=(node1 side node, node2 side node), outer=[4 nodes in
+        newLen[1..4] order]); the tree, its lengths and every flag of the original neighbours are as before on return"""
+        assert not node1.is_leaf() and not node2.is_leaf() and len(node1.neighbors) == 3 and len(node2.neighbors) == 3
+        # the six (nni5) or two neighbour objects that the evaluation may overwrite are replaced by copies on the two spare slots
+        saved = [(node1, node1.neighbors.index(node1.find(node2))), (node2, node2.neighbors.index(node2.find(node1)))]
+        if nni5:
+            for it in node1.neighbors:
+                if it.node is not node2:
+                    saved.append((it.node, it.node.neighbors.index(it.node.find(node1))))
+            for it in node2.neighbors:
+                if it.node is not node1:
+                    saved.append((it.node, it.node.neighbors.index(it.node.find(node2))))
+        else:
+            self._reorient(node1.find(node2), node1)
+            self._reorient(node2.find(node1), node2)
+        nslots = sum(1 for ab, ba in self.branches for x in (ab, ba) if x.slot >= 0)   # the T-2 regular slots
+        saved_nei, mem_id = [], 0
+        for owner, k in saved:
+            old = owner.neighbors[k]
+            saved_nei.append(old)
+            slot = -1
+            if old.slot >= 0:
+                slot = nslots + mem_id; mem_id += 1
+            owner.neighbors[k] = self._copy_nei(old, slot)
+        assert mem_id == 2
+        node12, node21 = node1.find(node2), node2.find(node1)
+        k1 = next(k for k, it in enumerate(node1.neighbors) if it.node is not node2)
+        k2s = [k for k, it in enumerate(node2.neighbors) if it.node is not node1]
+        moves = []
+        for k2 in k2s:
+            node1_nei, node2_nei = node1.neighbors[k1], node2.neighbors[k2]
+            self._reorient(node12, node1)
+            self._reorient(node21, node2)
+            # the swap (Node::updateNeighbor)
+            node1.neighbors[k1] = node2_nei
+            node2_nei.node.find(node2).node = node1
+            node2.neighbors[k2] = node1_nei
+            node1_nei.node.find(node1).node = node2
+            new_len = [0.0] * 5
+            for _ in range(nni5_num_eval):
+                node12.computed = node21.computed = False
+                i = 1
+                if nni5:
+                    for it in list(node1.neighbors):
+                        if it.node is node2:
+                            continue
+                        it.node.find(node1).computed = False
+                        self.optimize_one_branch(node1, it.node, False, self.NNI_MAX_NR_STEP)
+                        new_len[i] = node1.find(it.node).length; i += 1
+                    node21.computed = False
+                self.optimize_one_branch(node1, node2, False, self.NNI_MAX_NR_STEP)
+                new_len[0] = node12.length
+                if nni5:
+                    for it in list(node2.neighbors):
+                        if it.node is node1:
+                            continue
+                        it.node.find(node2).computed = False
+                        self.optimize_one_branch(node2, it.node, False, self.NNI_MAX_NR_STEP)
+                        new_len[i] = node2.find(it.node).length; i += 1
+                    node12.computed = False
+            score = self.from_buffer()
+            outer = [it.node for it in node1.neighbors if it.node is not node2] + [it.node for it in node2.neighbors if it.node is not node1]
+            moves.append(dict(score=score, new_len=new_len if nni5 else new_len[:1], swap=(node1_nei.node, node2_nei.node), outer=outer,
+                              k1=k1, k2=k2))
+            self._reorient(node12, node1)
+            self._reorient(node21, node2)
+            # swap back
+            node1.neighbors[k1] = node1_nei
+            node1_nei.node.find(node2).node = node1
+            node2.neighbors[k2] = node2_nei
+            node2_nei.node.find(node1).node = node2
+        for (owner, k), old in reversed(list(zip(saved, saved_nei))):
+            if owner.neighbors[k] is self.current_it:
+                self.current_it = old
+            if owner.neighbors[k] is self.current_it_back:
+                self.current_it_back = old
+            owner.neighbors[k] = old
+        # lengths of the four outer branches: the outward neighbours were optimised, their saved partners hold the old values
+        for a, b in ((node1, node2), (node2, node1)):
+            for it in a.neighbors:
+                if it.node is not b:
+                    it.length = it.node.find(a).length
+        return moves
+
+    def do_nni(self, node1, node2, move, clear_lh=True):
+        """PhyloTree::doNNI (:3975-4036) with the neighbour positions of a move from get_best_nni_for_bran, then
+        changeNNIBrans (:4038-4067) when the move carries lengths"""
+        k1, k2 = move["k1"], move["k2"]
+        self._reorient(node1.find(node2), node1)
+        self._reorient(node2.find(node1), node2)
+        node1_nei, node2_nei = node1.neighbors[k1], node2.neighbors[k2]
+        node1.neighbors[k1] = node2_nei
+        node2_nei.node.find(node2).node = node1
+        node2.neighbors[k2] = node1_nei
+        node1_nei.node.find(node1).node = node2
+        nei12, nei21 = node1.find(node2), node2.find(node1)
+        if clear_lh:
+            nei12.computed = nei21.computed = False
+            nei12.size = nei21.size = 0
+            self.clear_reverse(node2, node1)
+            self.clear_reverse(node1, node2)
+        new_len = move.get("new_len")
+        if new_len:
+            nei12.length = nei21.length = new_len[0]
+            if len(new_len) == 5:
+                i = 1
+                for a, b in ((node1, node2), (node2, node1)):
+                    for it in a.neighbors:
+                        if it.node is not b:
+                            it.length = it.node.find(a).length = new_len[i]; i += 1

@@ -67,3 +67,14 @@ def pytree_splits(t):
         s = side(ab.node, ba.node)
         res.append(allt - s if 0 in s else s)
     return res
+
+
+def pytree_leafset(node, dad):
+    """leaf set of the subtree of `node` seen from `dad` in a tests/pytree.PyTree"""
+    if node.is_leaf():
+        return frozenset([node.id])
+    s = frozenset()
+    for n in node.neighbors:
+        if n.node is not dad:
+            s |= pytree_leafset(n.node, node)
+    return s

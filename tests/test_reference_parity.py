@@ -10,7 +10,7 @@ from cases import load_engine, make_case
 from iqtree2_b200 import plan
 from oracle import ref_engine
 from oracle.oracle_engine import OracleEngine
-from refmap import branch_splits, pytree_splits, slot_leafsets
+from refmap import branch_splits, pytree_leafset, pytree_splits, slot_leafsets
 from test_tree_logic_cpu import example_case, make_pytree
 
 pytestmark = pytest.mark.skipif(not ref_engine.available(), reason="oracle/_ref/libiqref.so not built (needs /root/reference)")
@@ -192,3 +192,55 @@ def test_mem_save_slot_table_matches_reference(mem, tree_kind):
         r.close(); o.close(); t.close()
     finally:
         ref_engine.set_mem_save(False)
+
+
+@pytest.mark.parametrize("kind,nni5", [("dna", True), ("dna", False), ("aa", True)])
+def test_nni_evaluation_matches_reference(kind, nni5):
+    """PhyloTree::getBestNNIForBran (tree/phylotree.cpp:4069-4322) on every inner branch: the compiled reference against the
+    Python restatement over the oracle — same two moves (identified by the swapped subtrees), scores to 1e-6, the five
+    re-optimised lengths to 1e-6 (observed ~1e-12), and the tree, its lengths and its likelihood untouched afterwards."""
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=12, nsites=500 if kind == "dna" else 200, seed=11, gaps=0.02, ambig=0.0)
+    names = ["T%d" % i for i in range(tree.ntaxa)]
+    tree.names = names
+    newick = tree.to_newick(fmt="%.12g")
+    r = ref_engine.RefTree(None, model, pat, freq, newick=newick, names=names)
+    t = make_pytree(names, pat, freq, model, newick)
+    ll0 = t.compute_likelihood()
+    assert abs(r.compute_likelihood()[0] - ll0) < 1e-8
+    len0 = t.lengths().copy()
+    spl = pytree_splits(t)
+    inner = [(ab, ba) for ab, ba in t.branches if not ab.node.is_leaf() and not ba.node.is_leaf()]
+    assert len(inner) == tree.ntaxa - 3
+    for ab, ba in inner:
+        node1, node2 = ba.node, ab.node
+        got = t.get_best_nni_for_bran(node1, node2, nni5=nni5)
+        ref = r.best_nni(spl[ab.id], nni5=nni5)
+        key = lambda m: frozenset(m["swap"])
+        ref_by = {key(m): m for m in ref}
+        for mv in got:
+            sw = (pytree_leafset(mv["swap"][0], node1), pytree_leafset(mv["swap"][1], node2))
+            rm = ref_by[frozenset(sw)]
+            assert abs(mv["score"] - rm["score"]) < 1e-6, (mv["score"], rm["score"])
+            assert abs(mv["new_len"][0] - rm["new_len"][0]) < 1e-6
+            if nni5:
+                # outer branches keyed by the subtree they lead to (after the swap)
+                mine = {}
+                for i, x in enumerate(mv["outer"]):
+                    mine[pytree_leafset(x, node1 if node1.find(x) else node2)] = mv["new_len"][1 + i]
+                theirs = dict(zip(rm["outer"], rm["new_len"][1:]))
+                assert set(mine) == set(theirs)
+                for k2 in mine:
+                    assert abs(mine[k2] - theirs[k2]) < 1e-6, (sorted(k2), mine[k2], theirs[k2])
+        np.testing.assert_array_equal(t.lengths(), len0)
+        assert pytree_splits(t) == spl
+    # nothing is stale: the likelihood at the old branch and after a full recomputation is the old one
+    assert abs(t.compute_likelihood() - ll0) < 1e-9
+    t.clear_all()
+    assert abs(t.compute_likelihood() - ll0) < 1e-9
+    assert abs(r.compute_likelihood()[0] - ll0) < 1e-8
+    # applying the better move of the last branch gives the tree whose likelihood the evaluation promised
+    best = max(got, key=lambda m: m["score"])
+    t.do_nni(node1, node2, best)
+    assert abs(t.compute_likelihood() - best["score"]) < 1e-6
+    t.clear_all()
+    assert abs(t.compute_likelihood() - best["score"]) < 1e-6
