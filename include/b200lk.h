@@ -113,10 +113,15 @@ int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat
 /* +ASC, Lewis' ascertainment-bias correction (ModelFactory::ASC_type = ASC_VARIANT / ASC_INFORMATIVE;
  * tree/phylokernelnew.h:3076-3091, 3198-3221, 2506-2535, 2618-2626, 3342-3356, 3412-3426): the LAST num_unobserved of the
  * engine's nptn patterns are ModelFactory::unobserved_ptns (their ptn_freq is ignored, their ptn_invar is the caller's);
- * nsite = aln->getNSite().  logL, _pattern_lh, df and ddf come back corrected.  asc_type 0 switches it off.  Holder's
- * missing-data forms (ASC_*_MISSING) are not implemented: the call fails for them.  With pattern sharding the correction is
- * not separable per rank (it needs the global prob_const): use one engine, or replicate the unobserved block and combine
- * on the host. */
+ * nsite = aln->getNSite().  logL, _pattern_lh, df and ddf come back corrected.  asc_type 0 switches it off.
+ * asc_type 2 = Holder's correction for missing data (+ASC_MIS, ASC_VARIANT_MISSING; :3175-3197, 2580-2617, 3385-3410): the
+ * unobserved block is what Alignment::getUnobservedConstPatterns builds (alignment/alignment.cpp:4158-4180) — nstates groups
+ * of num_unobserved/nstates patterns (>= the observed pattern count; the reference pads it to its SIMD width), pattern p of
+ * group s = observed pattern p with every non-gap character replaced by state s; the correction is per pattern,
+ * log(1 - sum_s L(const pattern s,p)), and nsite is not used.  (ASC_INFORMATIVE_MISSING aborts in the reference itself,
+ * alignment.cpp:4198-4201.)  With pattern sharding Lewis' correction is not separable per rank (it needs the global
+ * prob_const): use one engine, or replicate the unobserved block and combine on the host; Holder's is per pattern and shards
+ * with its patterns. */
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
 
 /* ---- the five kernel entry points --------------------------------------------------------------------------- */

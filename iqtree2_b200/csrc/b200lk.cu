@@ -137,6 +137,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
+    cudaFree(e->d.asc_tmp);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
@@ -220,7 +221,7 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     Dev &d = e->d;
     d.n = n; d.C = e->C; d.ncat = cfg->ncat; d.nmix = cfg->nmix; d.denom = e->denom; d.B = e->B; d.S = e->S;
     d.su = cfg->state_unknown; d.P = e->P; d.Ppad = Ppad;
-    d.asc = 0; d.Pobs = e->P; d.asc_nsite = 0;
+    d.asc = 0; d.Pobs = e->P; d.asc_nsite = 0; d.asc_step = 0; d.asc_tmp = nullptr;
     d.clv_f20 = (n == 20 && e->C % cfg->nmix == 0) ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
     d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
     d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
@@ -268,12 +269,17 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
 }
 
 extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
-    if (asc_type < 0 || asc_type > 1) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE); Holder's missing-data forms are not implemented");
+    if (asc_type < 0 || asc_type > 2) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE), 2 = Holder (ASC_VARIANT_MISSING)");
     if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
+    if (asc_type == 2 && (num_unobserved % e->cfg.nstates != 0 || num_unobserved / e->cfg.nstates < e->P - num_unobserved))
+        return fail(e, B200LK_ERR_INVALID, "+ASC_MIS: the unobserved block must be nstates groups of at least (observed patterns) constant patterns");
     cudaSetDevice(e->cfg.device);
     CK(sync_stream(e));
+    if (e->d.asc_tmp) { cudaFree(e->d.asc_tmp); e->d.asc_tmp = nullptr; }
+    if (asc_type == 2) CK(cudaMalloc(&e->d.asc_tmp, sizeof(double) * 3 * (size_t)num_unobserved));
     e->d.asc = asc_type;
     e->d.Pobs = asc_type ? e->P - num_unobserved : e->P;
+    e->d.asc_step = asc_type == 2 ? num_unobserved / e->cfg.nstates : 0;
     e->d.asc_nsite = nsite;
     e->theta_computed = false;
     return 0;
@@ -803,6 +809,12 @@ static int repair_pattern_lh(b200lk_engine *e, bool save_log, double *logl) {
     return B200LK_WARN_UNDERFLOW;
 }
 
+// +ASC epilogue of the two log-likelihood entry points: raw (tree_lh, prob_const) in d_result[8..9] -> d_result[0], _pattern_lh
+static void asc_finish_logl(b200lk_engine *e, int nblocks) {
+    if (e->d.asc == 2) k_asc_holder_logl<<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_result + 8, e->d_red, e->d_ticket, e->d_result);
+    else k_asc_finish_logl<<<std::min(nblocks, 296), 256, 0, e->stream>>>(e->d, e->d_result + 8, e->d_result);
+}
+
 // pending results of the enqueue_* entry points (b200lk_finish collects them)
 enum { PEND_LOGL = 1, PEND_DERV = 2, PEND_SAVE_LOG = 4 };
 
@@ -822,7 +834,7 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     if (e->d.asc) {   // +ASC: (tree_lh, prob_const) into slots 8..9, then the correction
         if (e->cfg.safe_numeric) k_root<true, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
         else k_root<false, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
-        k_asc_finish_logl<<<std::min(nblocks, 296), 256, 0, e->stream>>>(e->d, e->d_result + 8, e->d_result);
+        asc_finish_logl(e, nblocks);
         e->launches += 1;
         e->last_launch[1] += 1;
     } else if (e->cfg.safe_numeric) k_root<true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
@@ -889,7 +901,8 @@ static void enqueue_derv(b200lk_engine *e, double length) {
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 1); e->launches++; e->last_launch[2]++; }
     if (e->d.asc) {   // +ASC: (df, ddf, prob_const, df_const, ddf_const) into slots 10..14, then the correction
         k_derv<0, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 10, length, fuse);
-        k_asc_finish_derv<<<1, 1, 0, e->stream>>>(e->d, e->d_result + 10, e->d_result + 1);
+        if (e->d.asc == 2) k_asc_holder_derv<<<nblocks, kTile, 0, e->stream>>>(e->d, e->d_result + 10, e->d_red, e->d_ticket, e->d_result + 1);
+        else k_asc_finish_derv<<<1, 1, 0, e->stream>>>(e->d, e->d_result + 10, e->d_result + 1);
         e->launches += 1;
         e->last_launch[2] += 1;
     } else if (e->B == 16) k_derv<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 1, length, fuse);
@@ -939,7 +952,7 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
     if (e->d.asc) {
         k_from_buffer<0, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
-        k_asc_finish_logl<<<std::min(nblocks, 296), 256, 0, e->stream>>>(e->d, e->d_result + 8, e->d_result);
+        asc_finish_logl(e, nblocks);
         e->launches += 1;
         e->last_launch[1] += 1;
     } else if (e->B == 16) k_from_buffer<16><<<nblocks, kTile, vsm, e->stream>>>(e->d, e->d_red, e->d_ticket, e->d_result, length, fuse);

@@ -47,8 +47,10 @@ struct ChildJob {
 struct Dev {
     int n, C, ncat, nmix, denom, B, S, su;
     int quirks;              // B200LK_QUIRK_* (include/b200lk.h)
-    int asc;                 // +ASC: 1 = Lewis' correction; patterns [Pobs, P) are the unobserved constant patterns
+    int asc;                 // +ASC: 1 = Lewis' correction, 2 = Holder's (+ASC_MIS); patterns [Pobs, P) are the unobserved constant patterns
     long long Pobs, asc_nsite;   // Pobs = P without +ASC; asc_nsite = aln->getNSite()
+    long long asc_step;      // Holder: the unobserved block is n groups of asc_step patterns, group s = pattern p with state s
+    double *asc_tmp;         // Holder: (lh, df, ddf) of every unobserved pattern, three arrays of P - Pobs doubles
     int clv_f20;             // CLV slots use the 20-state fragment-major layout (clv20_off) instead of the warp-interleaved one
     long long P, Ppad;
     long long slot_stride;   // Ppad * B   doubles per CLV slot
@@ -1554,7 +1556,9 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
         else { D.pattern_lh[p] = lh_ptn; D.pattern_scaling[p] = vc_min_scale; }
         acc[0] = lg * D.freq[p];
     } else if (ASC && p < D.P) {
-        acc[ASC ? 1 : 0] = vc_min_scale != 0.0 ? lh_ptn * kScalingThreshold : lh_ptn;
+        const double lhc = vc_min_scale != 0.0 ? lh_ptn * kScalingThreshold : lh_ptn;
+        if (D.asc == 2) D.asc_tmp[p - D.Pobs] = lhc;   // Holder keeps it per pattern (:3088-3089)
+        else acc[ASC ? 1 : 0] = lhc;
         D.pattern_lh[p] = 0.0;
     }
     block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);
@@ -1571,6 +1575,41 @@ __global__ void k_asc_finish_derv(Dev D, const double *raw, double *result) {
     const double all = 1.0 - raw[2], df_frac = raw[3] / all, ddf_frac = raw[4] / all;
     result[0] = raw[0] + (double)D.asc_nsite * df_frac;
     result[1] = raw[1] + (double)D.asc_nsite * (ddf_frac + df_frac * df_frac);
+}
+// Holder's correction for missing data (+ASC_MIS; :3175-3197, 3385-3410): per observed pattern p the likelihoods of the n
+// constant patterns that share p's gaps (asc_tmp[s*step + p]) give _pattern_lh[p] -= log(1 - sum_s) and
+// logL = raw[0] - sum_p freq_p log(1 - sum_s).  One thread per pattern, same grid as k_root.
+__global__ void __launch_bounds__(kTile) k_asc_holder_logl(Dev D, const double *raw, double *red, unsigned *ticket, double *result) {
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    double acc[1] = {0.0};
+    if (p < D.Pobs) {
+        double c = D.asc_tmp[p];
+        for (int s = 1; s < D.n; s++) c += D.asc_tmp[(long long)s * D.asc_step + p];
+        const double prob_variant = log(1.0 - c);
+        D.pattern_lh[p] -= prob_variant;
+        acc[0] = -prob_variant * D.freq[p];
+    }
+    if (p == 0) acc[0] += raw[0];
+    block_reduce_finish<1>(acc, red, ticket, result);
+}
+// (:2580-2617): df += sum_p freq_p df_frac, ddf += sum_p freq_p (ddf_frac + df_frac^2) with the per-pattern sums over the n groups
+__global__ void __launch_bounds__(kTile) k_asc_holder_derv(Dev D, const double *raw, double *red, unsigned *ticket, double *result) {
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long U = D.P - D.Pobs;
+    double acc[2] = {0.0, 0.0};
+    if (p < D.Pobs) {
+        double c = D.asc_tmp[p], d1 = D.asc_tmp[U + p], d2 = D.asc_tmp[2 * U + p];
+        for (int s = 1; s < D.n; s++) {
+            const long long u = (long long)s * D.asc_step + p;
+            c += D.asc_tmp[u]; d1 += D.asc_tmp[U + u]; d2 += D.asc_tmp[2 * U + u];
+        }
+        c = 1.0 - c;
+        const double df_frac = d1 / c, ddf_frac = d2 / c, freq = D.freq[p];
+        acc[0] = freq * df_frac;
+        acc[1] = freq * (ddf_frac + df_frac * df_frac);
+    }
+    if (p == 0) { acc[0] += raw[0]; acc[1] += raw[1]; }
+    block_reduce_finish<2>(acc, red, ticket, result);
 }
 
 // computeLikelihoodBuffer{,Generic}SIMD (tree/phylokernelnew.h:2091-2230): theta_all and buffer_scale_all
@@ -1655,7 +1694,12 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ti
         acc[1] = fma(-tmp1, df_frac, tmp2);   // nmul_add(tmp1, df_frac, tmp2) :2505
     } else if (ASC && p < D.P) {   // :2506-2535
         const double f = D.buffer_scale[p] != 0.0 ? kScalingThreshold : 1.0;
-        acc[ASC ? 2 : 0] = lh * f; acc[ASC ? 3 : 0] = df * f; acc[ASC ? 4 : 0] = ddf * f;
+        if (D.asc == 2) {
+            const long long U = D.P - D.Pobs, u = p - D.Pobs;
+            D.asc_tmp[u] = lh * f; D.asc_tmp[U + u] = df * f; D.asc_tmp[2 * U + u] = ddf * f;
+        } else {
+            acc[ASC ? 2 : 0] = lh * f; acc[ASC ? 3 : 0] = df * f; acc[ASC ? 4 : 0] = ddf * f;
+        }
     }
     block_reduce_finish<ASC ? 5 : 2>(acc, red, ticket, result);
 }
@@ -1837,7 +1881,9 @@ __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsig
         D.pattern_lh[p] = lg;
         acc[0] = lg * D.freq[p];
     } else if (ASC && p < D.P) {   // :3342-3356
-        acc[ASC ? 1 : 0] = D.buffer_scale[p] != 0.0 ? lh * kScalingThreshold : lh;
+        const double lhc = D.buffer_scale[p] != 0.0 ? lh * kScalingThreshold : lh;
+        if (D.asc == 2) D.asc_tmp[p - D.Pobs] = lhc;
+        else acc[ASC ? 1 : 0] = lhc;
         D.pattern_lh[p] = 0.0;
     }
     block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);

@@ -232,7 +232,8 @@ class LikelihoodEngine:
         return self._get("b200lk_get_pattern_lh", self.nptn)
 
     def set_ascertainment(self, asc_type, num_unobserved, nsite):
-        """+ASC (1 = Lewis): the last num_unobserved patterns are the unobserved constant patterns, nsite = aln->getNSite()"""
+        """+ASC (1 = Lewis, 2 = Holder's +ASC_MIS): the last num_unobserved patterns are the unobserved constant patterns
+        (Holder: nstates groups of num_unobserved/nstates), nsite = aln->getNSite()"""
         self._check(self.lib.b200lk_set_ascertainment(self._h, C.c_int32(asc_type), C.c_int64(num_unobserved), C.c_int64(nsite)))
 
     def set_extra_children(self, children):

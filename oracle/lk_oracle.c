@@ -699,8 +699,28 @@ static void compute_vals(const orc_engine *e, double len_branch, double *val0, d
     }
 }
 
+/* Holder's ascertainment-bias correction for missing data (+ASC_MIS, ASC_VARIANT_MISSING; phylokernelnew.h:3175-3197,
+ * 3385-3410): the unobserved block holds nstates groups of `step` constant patterns, group s = every observed pattern with
+ * its non-gap characters replaced by state s (Alignment::getUnobservedConstPatterns, alignment/alignment.cpp:4158-4180;
+ * step = the padded pattern count there, anything >= Pobs here).  pattern_lh[Pobs + s*step + p] holds their likelihoods.
+ * Applies _pattern_lh[p] -= log(1 - sum_s const_lh) and returns sum_p freq_p * log(1 - ...), to be subtracted from tree_lh. */
+static double holder_logl_correction(orc_engine *e, size_t Pobs) {
+    const int n = e->cfg.nstates;
+    const size_t P = (size_t)e->cfg.nptn, step = (size_t)e->asc_nunobs / (size_t)n;
+    double sum_corr = 0.0;
+    for (size_t p = 0; p < Pobs; p++) {
+        double c = e->pattern_lh[Pobs + p];
+        for (int s = 1; s < n; s++) c += e->pattern_lh[Pobs + (size_t)s * step + p];
+        const double prob_variant = log(1.0 - c);
+        e->pattern_lh[p] -= prob_variant;
+        sum_corr += prob_variant * e->ptn_freq[p];
+    }
+    for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
+    return sum_corr;
+}
+
 /* ---------------------------------------------------------------------------------------------
- * computeLikelihoodBranch(Generic)SIMD — phylokernelnew.h:2641-3223 (no +ASC, no robust-phylo)
+ * computeLikelihoodBranch(Generic)SIMD — phylokernelnew.h:2641-3223 (+ASC: Lewis and Holder; no robust-phylo)
  *   node end must be a slot; dad end is a tip (dad_kind 0) or a slot (dad_kind 1).
  * ------------------------------------------------------------------------------------------- */
 int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
@@ -751,7 +771,8 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
             if (p >= Pobs) { /* unobserved constant pattern: :3076-3091 */
                 if (min_scale_d != 0.0) lh_ptn *= SCALING_THRESHOLD;
-                prob_const += lh_ptn;
+                if (e->asc_type == 2) e->pattern_lh[p] = lh_ptn; /* Holder: kept per pattern (:3088-3089) */
+                else prob_const += lh_ptn;
                 continue;
             }
             double lg = log(lh_ptn) + min_scale_d;
@@ -790,7 +811,8 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
             if (p >= Pobs) { /* unobserved constant pattern: :3076-3091 */
                 if (min_scale_d != 0.0) lh_ptn *= SCALING_THRESHOLD;
-                prob_const += lh_ptn;
+                if (e->asc_type == 2) e->pattern_lh[p] = lh_ptn; /* Holder: kept per pattern (:3088-3089) */
+                else prob_const += lh_ptn;
                 continue;
             }
             double lg = log(lh_ptn) + min_scale_d;
@@ -820,7 +842,7 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         for (size_t p = 0; p < Pobs; p++) e->pattern_lh[p] -= corr;
         for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
         tree_lh -= (double)e->asc_nsite * corr;
-    }
+    } else if (e->asc_type == 2) tree_lh -= holder_logl_correction(e, Pobs); /* :3175-3197 */
     *logl_out = tree_lh;
     return status;
 }
@@ -884,7 +906,9 @@ int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
 int orc_set_reference_quirks(orc_engine *e, int mask) { e->quirks = mask; return 0; }
 
 int orc_set_ascertainment(orc_engine *e, int asc_type, int64_t nunobs, int64_t nsite) {
-    if (asc_type < 0 || asc_type > 1 || nunobs < 0 || nunobs > e->cfg.nptn) { snprintf(e->err, sizeof e->err, "bad +ASC arguments"); return -1; }
+    if (asc_type < 0 || asc_type > 2 || nunobs < 0 || nunobs > e->cfg.nptn) { snprintf(e->err, sizeof e->err, "bad +ASC arguments"); return -1; }
+    /* 2 = Holder: nstates groups of `step` >= (observed patterns) constant patterns */
+    if (asc_type == 2 && (nunobs % e->cfg.nstates != 0 || nunobs / e->cfg.nstates < e->cfg.nptn - nunobs)) { snprintf(e->err, sizeof e->err, "bad +ASC_MIS block"); return -1; }
     e->asc_type = asc_type; e->asc_nunobs = asc_type ? nunobs : 0; e->asc_nsite = nsite;
     e->theta_computed = 0;
     return 0;
@@ -912,6 +936,8 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
     double all_df = 0.0, all_ddf = 0.0, prob_const = 0.0, df_const = 0.0, ddf_const = 0.0;
     const size_t Pobs = e->asc_type ? P - (size_t)e->asc_nunobs : P;
     const int odd = (e->quirks & 1) ? (e->cfg.nstates & 1) : (B & 1);
+    double *const_df = NULL, *const_ddf = NULL; /* Holder: per unobserved pattern (:2371-2373, 2527-2530) */
+    if (e->asc_type == 2) { const_df = (double *)calloc(2 * (P - Pobs) + 1, sizeof(double)); const_ddf = const_df + (P - Pobs); }
 #pragma omp parallel for schedule(static) reduction(+ : all_df, all_ddf, prob_const, df_const, ddf_const)
     for (size_t p = 0; p < P; p++) {
         double lh_ptn, df_ptn, ddf_ptn;
@@ -919,7 +945,8 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
         if (p >= Pobs) { /* :2506-2535 */
             if (e->buffer_scale_all[p] != 0.0) { lh_ptn *= SCALING_THRESHOLD; df_ptn *= SCALING_THRESHOLD; ddf_ptn *= SCALING_THRESHOLD; }
-            prob_const += lh_ptn; df_const += df_ptn; ddf_const += ddf_ptn;
+            if (e->asc_type == 2) { e->pattern_lh[p] = lh_ptn; const_df[p - Pobs] = df_ptn; const_ddf[p - Pobs] = ddf_ptn; }
+            else { prob_const += lh_ptn; df_const += df_ptn; ddf_const += ddf_ptn; }
             continue;
         }
         lh_ptn = 1.0 / lh_ptn;
@@ -934,6 +961,22 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         double all = 1.0 - prob_const, df_frac = df_const / all, ddf_frac = ddf_const / all;
         all_df += (double)e->asc_nsite * df_frac;
         all_ddf += (double)e->asc_nsite * (ddf_frac + df_frac * df_frac);
+    } else if (e->asc_type == 2) { /* Holder :2580-2617 */
+        const int n = e->cfg.nstates;
+        const size_t step = (size_t)e->asc_nunobs / (size_t)n;
+        double sum_df = 0.0, sum_ddf = 0.0;
+        for (size_t p = 0; p < Pobs; p++) {
+            double c = e->pattern_lh[Pobs + p], d1 = const_df[p], d2 = const_ddf[p];
+            for (int s = 1; s < n; s++) { c += e->pattern_lh[Pobs + (size_t)s * step + p]; d1 += const_df[(size_t)s * step + p]; d2 += const_ddf[(size_t)s * step + p]; }
+            c = 1.0 - c;
+            const double df_frac = d1 / c, ddf_frac = d2 / c;
+            sum_df += e->ptn_freq[p] * df_frac;
+            sum_ddf += e->ptn_freq[p] * (ddf_frac + df_frac * df_frac);
+        }
+        for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
+        all_df += sum_df;
+        all_ddf += sum_ddf;
+        free(const_df);
     }
     *df_out = all_df;
     *ddf_out = all_ddf;
@@ -956,7 +999,8 @@ int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
         lh_ptn = fabs(lh_ptn) + e->ptn_invar[p];
         if (p >= Pobs) { /* :3342-3356 */
             if (e->buffer_scale_all[p] != 0.0) lh_ptn *= SCALING_THRESHOLD;
-            prob_const += lh_ptn;
+            if (e->asc_type == 2) e->pattern_lh[p] = lh_ptn; /* :3352-3353 */
+            else prob_const += lh_ptn;
             continue;
         }
         lh_ptn = log(fabs(lh_ptn)) + e->buffer_scale_all[p];
@@ -978,7 +1022,7 @@ int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
         for (size_t p = 0; p < Pobs; p++) e->pattern_lh[p] -= corr;
         for (size_t p = Pobs; p < P; p++) e->pattern_lh[p] = 0.0;
         tree_lh -= (double)e->asc_nsite * corr;
-    }
+    } else if (e->asc_type == 2) tree_lh -= holder_logl_correction(e, Pobs); /* :3385-3410 */
     *logl_out = tree_lh;
     return status;
 }

@@ -9,7 +9,7 @@ import pytest
 from iqtree2_b200.phylotree import PhyloTree
 from multifurc import newick
 from oracle import ref_engine
-from test_asc_cpu import asc_case
+from test_asc_cpu import asc_case, holder_case
 from test_multifurcation_cpu import polytomy_case
 
 pytestmark = pytest.mark.gpu
@@ -70,15 +70,20 @@ def test_host_mirror_on_polytomous_tree(kind):
 
 
 @pytest.mark.skipif(not ref_engine.available(), reason="oracle/_ref/libiqref.so not built")
-def test_host_mirror_with_asc():
-    tree, model, pat, freq, unobs, pat_all, freq_all = asc_case("bin", ntaxa=14, nsites=500)
+@pytest.mark.parametrize("asc_type", [1, 2])
+def test_host_mirror_with_asc(asc_type):
+    """computeLikelihood and optimizeAllBranches with +ASC (Lewis) and +ASC_MIS (Holder) against the compiled reference"""
+    if asc_type == 1:
+        tree, model, pat, freq, unobs, pat_all, freq_all = asc_case("bin", ntaxa=14, nsites=500)
+    else:
+        tree, model, pat, freq, unobs, pat_all, freq_all = holder_case("bin", ntaxa=14, nsites=500)
     nobs, U = pat.shape[1], unobs.shape[0]
     g = PhyloTree(safe_numeric=True)
     g.set_alignment(tree.names, pat_all, freq_all, model); g.set_model(model)
-    g.set_ascertainment(1, U, nobs)          # the harness alignment reports one site per pattern
+    g.set_ascertainment(asc_type, U, nobs)          # the harness alignment reports one site per pattern
     nwk = tree.to_newick(fmt="%.17g")
     g.read_tree(nwk)
-    ref_engine.set_asc_next(1, unobs)
+    ref_engine.set_asc_next(asc_type, unobs)
     r = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=True)
     ll_g, (ll_r, _) = g.compute_likelihood(), r.compute_likelihood()
     assert abs(ll_g - ll_r) < 1e-6, (ll_g, ll_r)
