@@ -124,6 +124,13 @@ int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat
  * with its patterns. */
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
 
+/* The robust-phylo variants of computeLikelihoodBranch (Params::robust_phy_keep < 1, `--robust-phy`: the log-likelihood summed
+ * over the best keep*nsite sites; Params::robust_median, `--robust-median`: the median site log-likelihood;
+ * tree/phylokernelnew.h:3134-3173): every later b200lk_branch_logl (and its enqueue form) returns that value; _pattern_lh is
+ * the uncorrected one, as in the reference; b200lk_logl_from_buffer is not affected (:3232-3428 has no such branch).
+ * (1.0, 0) switches it off.  Fails together with +ASC, as the reference does. */
+int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t median);
+
 /* ---- the five kernel entry points --------------------------------------------------------------------------- */
 /* computePartialLikelihood over a traversal_info list in post-order
  * (computeTraversalInfo<VC>(node, dad, compute_partial_lh=true), tree/phylokernelnew.h:1150-1281, 1289-2039) */

@@ -27,6 +27,8 @@ int b200pt_set_alignment(b200pt_tree *t, int32_t ntaxa, const char *const *names
 int b200pt_set_pattern_invar(b200pt_tree *t, const double *ptn_invar);
 /* +ASC (Lewis): the last num_unobserved patterns of the alignment are ModelFactory::unobserved_ptns; nsite = aln->getNSite() */
 int b200pt_set_ascertainment(b200pt_tree *t, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
+/* Params::robust_phy_keep / robust_median (--robust-phy, --robust-median): see b200lk_set_robust_phylo */
+int b200pt_set_robust_phylo(b200pt_tree *t, double keep, int32_t median);
 int b200pt_set_model(b200pt_tree *t, int32_t ncat, int32_t nmix, int32_t fused_mix_rate, const double *eval, const double *evec,
                      const double *inv_evec, const double *mix_weight, const double *cat_rate, const double *cat_prop);
 int b200pt_read_tree(b200pt_tree *t, const char *newick);

@@ -7,6 +7,9 @@
 #include "b200lk.h"
 #include "b200lk_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -54,6 +57,12 @@ struct b200lk_engine {
     int num_sms = 148;
     int info_smem_optin = 0;
     bool walk20_attr_set = false;
+    // robust phylo (b200lk_set_robust_phylo): keys / values / running site count of the sorted patterns + cub's scratch
+    double robust_keep = 1.0;
+    int robust_median = 0;
+    double *d_robust = nullptr;
+    void *d_robust_tmp = nullptr;
+    size_t robust_tmp_bytes = 0;
     int kernel_variant = 0;   // b200lk_set_schedule(e, 10 + v): development switch between kernel variants of one schedule
     int walk20_ctas_per_sm = 1;
     // profiling
@@ -137,7 +146,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
-    cudaFree(e->d.asc_tmp);
+    cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
@@ -271,6 +280,7 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
 extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
     if (asc_type < 0 || asc_type > 2) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE), 2 = Holder (ASC_VARIANT_MISSING)");
     if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
+    if (asc_type && (e->robust_keep < 1.0 || e->robust_median)) return fail(e, B200LK_ERR_INVALID, "+ASC not supported with robust phylo");
     if (asc_type == 2 && (num_unobserved % e->cfg.nstates != 0 || num_unobserved / e->cfg.nstates < e->P - num_unobserved))
         return fail(e, B200LK_ERR_INVALID, "+ASC_MIS: the unobserved block must be nstates groups of at least (observed patterns) constant patterns");
     cudaSetDevice(e->cfg.device);
@@ -282,6 +292,26 @@ extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int6
     e->d.asc_step = asc_type == 2 ? num_unobserved / e->cfg.nstates : 0;
     e->d.asc_nsite = nsite;
     e->theta_computed = false;
+    return 0;
+}
+
+// --robust-phy / --robust-median (Params::robust_phy_keep, robust_median; tree/phylokernelnew.h:3134-3173)
+extern "C" int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t median) {
+    if (!(keep > 0.0 && keep <= 1.0) || (keep < 1.0 && median)) return fail(e, B200LK_ERR_INVALID, "robust phylo: 0 < keep <= 1, and keep < 1 excludes median");
+    const bool on = keep < 1.0 || median;
+    if (on && e->d.asc) return fail(e, B200LK_ERR_INVALID, "+ASC not supported with robust phylo");   // :3136-3138
+    cudaSetDevice(e->cfg.device);
+    if (on && !e->d_robust) {
+        size_t b1 = 0, b2 = 0;
+        double *nul = nullptr;
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, nul, nul, nul, nul, (int)e->P, 0, 64, e->stream);
+        cub::DeviceScan::InclusiveSum(nullptr, b2, nul, nul, (int)e->P, e->stream);
+        e->robust_tmp_bytes = std::max(b1, b2);
+        CK(cudaMalloc(&e->d_robust, sizeof(double) * 3 * (size_t)e->P));
+        CK(cudaMalloc(&e->d_robust_tmp, e->robust_tmp_bytes));
+    }
+    e->robust_keep = keep;
+    e->robust_median = median != 0;
     return 0;
 }
 
@@ -841,6 +871,19 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     else k_root<false><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result, length, fuse);
     e->launches += 1;
     e->last_launch[1] += 1;
+    if (e->robust_keep < 1.0 || e->robust_median) {
+        // the site log-likelihoods in ascending order without expanding them: patterns sorted by _pattern_lh, the running sum of
+        // their frequencies gives every pattern its range of site ranks; k_robust_phylo weighs each pattern by the part of its
+        // range that is kept (or that holds the median).  Library sort and scan on a per-call side path, as in b200lk_patterns.cu.
+        double *keys = e->d_robust, *vals = keys + e->P, *cum = vals + e->P;
+        size_t bytes = e->robust_tmp_bytes;
+        cub::DeviceRadixSort::SortPairs(e->d_robust_tmp, bytes, e->d_pattern_lh, keys, e->d_freq, vals, (int)e->P, 0, 64, e->stream);
+        bytes = e->robust_tmp_bytes;
+        cub::DeviceScan::InclusiveSum(e->d_robust_tmp, bytes, vals, cum, (int)e->P, e->stream);
+        k_robust_phylo<<<nblocks, kTile, 0, e->stream>>>(e->P, keys, vals, cum, e->robust_keep, e->robust_median, e->d_red, e->d_ticket, e->d_result);
+        e->launches += 3;
+        e->last_launch[1] += 3;
+    }
     prof_mark(e, 2);
     CK(cudaGetLastError());
     e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);

@@ -1576,6 +1576,31 @@ __global__ void k_asc_finish_derv(Dev D, const double *raw, double *result) {
     result[0] = raw[0] + (double)D.asc_nsite * df_frac;
     result[1] = raw[1] + (double)D.asc_nsite * (ddf_frac + df_frac * df_frac);
 }
+// robust phylo (:3134-3173): lh / f = pattern log-likelihoods in ascending order with their frequencies, cum = running sum of f.
+// Pattern i holds the site ranks [cum[i] - f[i], cum[i]).  keep < 1: sum of the site log-likelihoods from rank
+// (int)((1 - keep) * sites) on; median: the site of rank sites/2 (odd) or the mean of ranks sites/2 - 1 and sites/2 (even).
+__global__ void __launch_bounds__(kTile) k_robust_phylo(long long P, const double *lh, const double *f, const double *cum, double keep,
+                                                        int median, double *red, unsigned *ticket, double *result) {
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    double acc[1] = {0.0};
+    if (p < P && f[p] > 0.0) {
+        const double sites = cum[P - 1], hi = cum[p], lo = hi - f[p];
+        if (!median) {
+            const double drop = (double)(int)((1.0 - keep) * sites);
+            const double cnt = hi - fmax(lo, drop);
+            if (cnt > 0.0) acc[0] = lh[p] * cnt;
+        } else {
+            const long long s = (long long)sites;
+            const double m = (double)(s / 2);
+            double w = 0.0;
+            if (lo <= m && m < hi) w += (s & 1) ? 1.0 : 0.5;
+            if (!(s & 1) && lo <= m - 1.0 && m - 1.0 < hi) w += 0.5;
+            if (w > 0.0) acc[0] = lh[p] * w;
+        }
+    }
+    block_reduce_finish<1>(acc, red, ticket, result);
+}
+
 // Holder's correction for missing data (+ASC_MIS; :3175-3197, 3385-3410): per observed pattern p the likelihoods of the n
 // constant patterns that share p's gaps (asc_tmp[s*step + p]) give _pattern_lh[p] -= log(1 - sum_s) and
 // logL = raw[0] - sum_p freq_p log(1 - sum_s).  One thread per pattern, same grid as k_root.

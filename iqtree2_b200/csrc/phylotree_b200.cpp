@@ -396,6 +396,8 @@ void PhyloTree::initializeAllPartialLh() {
         check(b200lk_set_model(engine_, eval_.data(), evec_.data(), inv_evec_.data(), mix_weight_.data()), "set_model");
         check(b200lk_set_rates(engine_, cat_rate_.data(), cat_prop_.data()), "set_rates");
         if (asc_type_) check(b200lk_set_ascertainment(engine_, asc_type_, asc_nunobs_, asc_nsite_), "set_ascertainment");
+        if (params.robust_phy_keep < 1.0 || params.robust_median)
+            check(b200lk_set_robust_phylo(engine_, params.robust_phy_keep, params.robust_median), "set_robust_phylo");
     }
     initialized_ = true;
     // slot assignment: pre-order from the root; the neighbour dad->node of every internal node gets the next slot

@@ -62,6 +62,8 @@ struct Params {
     bool pipelined_sweep = false;      // optimizeAllBranches queues the whole sweep (b200lk_enqueue_newton_branch): branch lengths
                                        // stay on the device between branches, one synchronisation per sweep
     bool plan_only = false;            // no engine: traversals are planned (flags, slots, op lists) but not executed
+    double robust_phy_keep = 1.0;      // --robust-phy: computeLikelihoodBranch sums the best keep*nsite sites (utils/tools.cpp:4379)
+    bool robust_median = false;        // --robust-median: ... returns the median site log-likelihood (:4392)
     bool nni5 = true;                  // utils/tools.cpp:1155: NNI evaluation re-optimises the five branches around the move
     int nni5_num_eval = 1;             // utils/tools.cpp:1156
 };

@@ -168,6 +168,14 @@ int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t move, int32_t nni5, co
         }
     })
 }
+int b200pt_set_robust_phylo(b200pt_tree *t, double keep, int32_t median) {
+    GUARD({
+        t->tree.params.robust_phy_keep = keep;
+        t->tree.params.robust_median = median != 0;
+        if (t->tree.engine() && b200lk_set_robust_phylo(t->tree.engine(), keep, median) != 0)
+            throw std::runtime_error(b200lk_last_error(t->tree.engine()));
+    })
+}
 int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on) { t->tree.params.pipelined_sweep = on != 0; return 0; }
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t) { return t->tree.num_partial_lh_computations; }
 

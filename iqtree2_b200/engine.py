@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
-    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment",
+    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment", "b200lk_set_robust_phylo",
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
 ]
 
@@ -235,6 +235,11 @@ class LikelihoodEngine:
         """+ASC (1 = Lewis, 2 = Holder's +ASC_MIS): the last num_unobserved patterns are the unobserved constant patterns
         (Holder: nstates groups of num_unobserved/nstates), nsite = aln->getNSite()"""
         self._check(self.lib.b200lk_set_ascertainment(self._h, C.c_int32(asc_type), C.c_int64(num_unobserved), C.c_int64(nsite)))
+
+    def set_robust_phylo(self, keep=1.0, median=False):
+        """Params::robust_phy_keep / robust_median: branch_logl returns the log-likelihood of the best sites / the median site"""
+        self.lib.b200lk_set_robust_phylo.argtypes = [C.c_void_p, C.c_double, C.c_int32]
+        self._check(self.lib.b200lk_set_robust_phylo(self._h, float(keep), int(bool(median))))
 
     def set_extra_children(self, children):
         """third, fourth ... children of the multifurcating ops (op['pad'] = their number) of the NEXT call, in op order"""

@@ -58,6 +58,10 @@ class PhyloTree:
     def set_ascertainment(self, asc_type, num_unobserved, nsite):
         self._check(self.lib.b200pt_set_ascertainment(self._h, asc_type, C.c_int64(num_unobserved), C.c_int64(nsite)))
 
+    def set_robust_phylo(self, keep=1.0, median=False):
+        self.lib.b200pt_set_robust_phylo.argtypes = [C.c_void_p, C.c_double, C.c_int32]
+        self._check(self.lib.b200pt_set_robust_phylo(self._h, float(keep), int(bool(median))))
+
     def set_model(self, model):
         f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         arrs = [f(model.eval), f(model.evec), f(model.inv_evec), f(model.mix_weight), f(model.cat_rate), f(model.cat_prop)]

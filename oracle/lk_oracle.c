@@ -63,6 +63,7 @@ typedef struct {
     double *theta, *buffer_scale_all, *pattern_lh, *pattern_lh_cat, *pattern_scaling;
     int theta_computed;
     int quirks; /* orc_set_reference_quirks */
+    double robust_keep; int robust_median; /* orc_set_robust_phylo: Params::robust_phy_keep (on if 0 < keep < 1) / robust_median */
     /* +ASC, Lewis' correction (phylokernelnew.h:3076-3091, 3198-3221, 2506-2535, 2618-2626, 3342-3356, 3412-3426): the last
      * asc_nunobs patterns are model_factory->unobserved_ptns; asc_nsite = aln->getNSite() */
     int asc_type; int64_t asc_nunobs, asc_nsite;
@@ -699,6 +700,11 @@ static void compute_vals(const orc_engine *e, double len_branch, double *val0, d
     }
 }
 
+static int cmp_double(const void *a, const void *b) {
+    const double x = *(const double *)a, y = *(const double *)b;
+    return x < y ? -1 : x > y ? 1 : 0;
+}
+
 /* Holder's ascertainment-bias correction for missing data (+ASC_MIS, ASC_VARIANT_MISSING; phylokernelnew.h:3175-3197,
  * 3385-3410): the unobserved block holds nstates groups of `step` constant patterns, group s = every observed pattern with
  * its non-gap characters replaced by state s (Alignment::getUnobservedConstPatterns, alignment/alignment.cpp:4158-4180;
@@ -837,6 +843,25 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
             tree_lh += ptn_lh * e->ptn_freq[p];
         }
     }
+    /* robust phylogeny project (:3134-3173): the log-likelihood of the best sites / of the median site */
+    const int robust_keep_on = e->robust_keep > 0.0 && e->robust_keep < 1.0;
+    if (robust_keep_on || e->robust_median) {
+        if (e->asc_type) { snprintf(e->err, sizeof e->err, "+ASC not supported with robust phylo"); return -1; }
+        size_t sites = 0;
+        for (size_t p = 0; p < P; p++) sites += (size_t)e->ptn_freq[p];
+        double *site_lh = (double *)malloc(sizeof(double) * (sites ? sites : 1));
+        size_t site = 0;
+        for (size_t p = 0; p < P; p++)
+            for (size_t i = 0; i < (size_t)e->ptn_freq[p]; i++) site_lh[site++] = e->pattern_lh[p];
+        qsort(site_lh, sites, sizeof(double), cmp_double); /* the reference's nth_element leaves the kept part unordered */
+        if (robust_keep_on) {
+            const size_t sites_drop = (size_t)(int)((1.0 - e->robust_keep) * (double)sites);
+            tree_lh = 0.0;
+            for (size_t i = sites_drop; i < sites; i++) tree_lh += site_lh[i];
+        } else if (sites & 1) tree_lh = site_lh[sites / 2];
+        else tree_lh = 0.5 * (site_lh[sites / 2] + site_lh[sites / 2 - 1]);
+        free(site_lh);
+    }
     if (e->asc_type == 1) { /* Lewis :3198-3221 */
         double corr = log(1.0 - prob_const);
         for (size_t p = 0; p < Pobs; p++) e->pattern_lh[p] -= corr;
@@ -904,6 +929,14 @@ static void build_theta(orc_engine *e, int node_slot, int dad_kind, int dad_id) 
 int orc_theta_reset(orc_engine *e) { e->theta_computed = 0; return 0; }
 /* bit 0: reproduce dotProductTriple's double-counted last element for odd nstates x even block (see dot_triple) */
 int orc_set_reference_quirks(orc_engine *e, int mask) { e->quirks = mask; return 0; }
+
+/* --robust-phy keep / --robust-median (utils/tools.cpp:4374-4392): orc_branch_logl returns the sum over the best keep*sites sites /
+ * the median site log-likelihood.  keep = 1 and median = 0 switch it off. */
+int orc_set_robust_phylo(orc_engine *e, double keep, int median) {
+    if (!(keep > 0.0 && keep <= 1.0) || (keep < 1.0 && median)) { snprintf(e->err, sizeof e->err, "bad robust-phylo arguments"); return -1; }
+    e->robust_keep = keep; e->robust_median = median;
+    return 0;
+}
 
 int orc_set_ascertainment(orc_engine *e, int asc_type, int64_t nunobs, int64_t nsite) {
     if (asc_type < 0 || asc_type > 2 || nunobs < 0 || nunobs > e->cfg.nptn) { snprintf(e->err, sizeof e->err, "bad +ASC arguments"); return -1; }

@@ -127,6 +127,13 @@ class OracleEngine:
     def theta_reset(self):
         lib().orc_theta_reset(self._h)
 
+    def set_robust_phylo(self, keep=1.0, median=False):
+        """Params::robust_phy_keep / robust_median: branch_logl returns the log-likelihood of the best sites / the median site"""
+        L = lib()
+        L.orc_set_robust_phylo.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        if L.orc_set_robust_phylo(self._h, float(keep), int(bool(median))) < 0:
+            raise RuntimeError(L.orc_last_error(self._h).decode())
+
     def set_reference_quirks(self, mask):
         lib().orc_set_reference_quirks(self._h, C.c_int(int(mask)))
 

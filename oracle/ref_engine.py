@@ -64,6 +64,14 @@ def set_asc_next(asc_type: int, unobserved):
     lib().iqref_set_asc_next(C.c_int(asc_type), u.ctypes.data_as(C.c_void_p), C.c_int(u.shape[0]), C.c_int(u.shape[1]))
 
 
+def set_robust(keep: float = 1.0, median: bool = False):
+    """Params::robust_phy_keep / robust_median for the trees created afterwards; (1.0, False) = off"""
+    L = lib()
+    L.iqref_set_robust.argtypes = [C.c_double, C.c_int]
+    L.iqref_set_robust.restype = None
+    L.iqref_set_robust(float(keep), int(bool(median)))
+
+
 def max_threads() -> int:
     return int(lib().iqref_max_threads())
 

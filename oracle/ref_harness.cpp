@@ -528,6 +528,14 @@ int iqref_best_nni(void *hv, const uint8_t *mask, int nni5, double *score, doubl
 // the new kernel does not maintain num_partial_lh_computations)
 int iqref_last_traversal_size(void *hv) { return (int)((Handle *)hv)->tree->traversal_info.size(); }
 
+// --robust-phy keep / --robust-median (utils/tools.cpp:4374-4392): Params::robust_phy_keep / robust_median for trees created
+// AFTERWARDS (initializeAllPartialLh allocates _site_lh when they are set, tree/phylotree.cpp:908-909); (1.0, 0) = off
+void iqref_set_robust(double keep, int median) {
+    init_params(Params::getInstance().num_threads > 0 ? Params::getInstance().num_threads : 1);
+    Params::getInstance().robust_phy_keep = keep;
+    Params::getInstance().robust_median = median != 0;
+}
+
 // -mem: Params::lh_mem_save / max_mem_size as parseArg sets them (utils/tools.cpp, "-mem"); applies to trees created
 // AFTERWARDS (getMemoryRequired / MemSlotVector::init read the global Params)
 void iqref_set_mem_save(int on, double max_mem_size) {
