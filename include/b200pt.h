@@ -113,6 +113,27 @@ int b200st_get_part_scores(b200st_tree *t, double *scores);
 int64_t b200st_launch_count(b200st_tree *t);
 int64_t b200st_device_bytes(b200st_tree *t);
 
+
+/* ---- edge-unlinked partition model: PhyloSuperTree (`-Q` / `-sp`; tree/phylosupertree.cpp:653-791) ----
+ * Every partition is a b200pt_tree of its own (own taxa, alignment, model, tree = the induced subtree, own branch lengths),
+ * configured through the b200pt_* calls and BORROWED here: it must outlive the b200ut_tree.  logL = sum_p logL_p; the partitions
+ * are evaluated concurrently, most expensive first (computePartitionOrder), from num_threads host threads (0 = OpenMP default),
+ * one device engine and stream each.  b200ut_optimize_all_branches runs every partition's optimizeAllBranches with
+ * tolerance / min(npartitions, 10) (:773-791).  pattern_lh (may be NULL in b200ut_compute_likelihood): the partitions'
+ * pattern log-likelihoods one after the other (:703-709, 736-763). */
+typedef struct b200ut_tree b200ut_tree;
+b200ut_tree *b200ut_create(int32_t num_threads);
+void b200ut_destroy(b200ut_tree *t);
+const char *b200ut_last_error(const b200ut_tree *t);
+int b200ut_add_partition(b200ut_tree *t, b200pt_tree *part);
+int b200ut_num_partitions(b200ut_tree *t);
+int64_t b200ut_num_patterns(b200ut_tree *t);
+int b200ut_clear_all_partial_lh(b200ut_tree *t);
+int b200ut_compute_likelihood(b200ut_tree *t, double *logl, double *pattern_lh);
+int b200ut_compute_pattern_likelihood(b200ut_tree *t, double *pattern_lh, double *logl);
+int b200ut_optimize_all_branches(b200ut_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+int b200ut_get_part_scores(b200ut_tree *t, double *scores);
+
 #ifdef __cplusplus
 }
 #endif

@@ -331,4 +331,32 @@ int64_t b200st_device_bytes(b200st_tree *t) {
     return n;
 }
 
+// ---- edge-unlinked partition model: PhyloSuperTree (tree/phylosupertree.cpp:653-791) ----
+struct b200ut_tree {
+    b200::PhyloSuperTree tree;
+    std::string err;
+};
+b200ut_tree *b200ut_create(int32_t num_threads) {
+    auto *t = new b200ut_tree();
+    t->tree.num_threads = num_threads;
+    return t;
+}
+void b200ut_destroy(b200ut_tree *t) { delete t; }
+const char *b200ut_last_error(const b200ut_tree *t) { return t ? t->err.c_str() : g_err.c_str(); }
+int b200ut_add_partition(b200ut_tree *t, b200pt_tree *part) {
+    try { return t->tree.addPartition(part ? &part->tree : nullptr); }
+    catch (const std::exception &ex) { t->err = ex.what(); return -1; }
+}
+int b200ut_num_partitions(b200ut_tree *t) { return t->tree.numPartitions(); }
+int64_t b200ut_num_patterns(b200ut_tree *t) { return t->tree.numPatterns(); }
+int b200ut_clear_all_partial_lh(b200ut_tree *t) { GUARD(t->tree.clearAllPartialLH()) }
+int b200ut_compute_likelihood(b200ut_tree *t, double *logl, double *pattern_lh) { GUARD(*logl = t->tree.computeLikelihood(pattern_lh)) }
+int b200ut_compute_pattern_likelihood(b200ut_tree *t, double *pattern_lh, double *logl) { GUARD(t->tree.computePatternLikelihood(pattern_lh, logl)) }
+int b200ut_optimize_all_branches(b200ut_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl) {
+    GUARD(*logl = t->tree.optimizeAllBranches(iterations, tolerance, max_nr_step))
+}
+int b200ut_get_part_scores(b200ut_tree *t, double *scores) {
+    GUARD(for (size_t p = 0; p < t->tree.cur_score.size(); p++) scores[p] = t->tree.cur_score[p])
+}
+
 }  // extern "C"

@@ -227,4 +227,67 @@ int64_t PhyloSuperTreePlen::launches() const {
     return n;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PhyloSuperTree: edge-unlinked partitions (tree/phylosupertree.cpp:653-791)
+// ---------------------------------------------------------------------------------------------------------------
+PhyloSuperTree::PhyloSuperTree() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
+int PhyloSuperTree::addPartition(PhyloTree *part) {
+    if (!part) throw std::runtime_error("addPartition: null partition tree");
+    parts.push_back(part);
+    cur_score.push_back(0.0);
+    part_order.clear();
+    return (int)parts.size() - 1;
+}
+
+void PhyloSuperTree::computePartitionOrder() {
+    if (part_order.size() == parts.size()) return;
+    part_order.resize(parts.size());
+    std::iota(part_order.begin(), part_order.end(), 0);
+    std::vector<double> cost(parts.size());
+    for (size_t p = 0; p < parts.size(); p++) cost[p] = (double)parts[p]->leafNum * (double)parts[p]->getAlnNPattern() * parts[p]->getNumStates();
+    std::stable_sort(part_order.begin(), part_order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+}
+
+int64_t PhyloSuperTree::numPatterns() const {
+    int64_t n = 0;
+    for (auto *p : parts) n += p->getAlnNPattern();
+    return n;
+}
+
+double PhyloSuperTree::computeLikelihood(double *pattern_lh) {
+    computePartitionOrder();
+    std::vector<int64_t> off(parts.size() + 1, 0);
+    for (size_t p = 0; p < parts.size(); p++) off[p + 1] = off[p] + parts[p]->getAlnNPattern();
+    for_each_partition(part_order, num_threads, [&](int p) { cur_score[p] = parts[p]->computeLikelihood(pattern_lh ? pattern_lh + off[p] : nullptr); });
+    double tree_lh = 0.0;
+    for (double x : cur_score) tree_lh += x;   // in partition order: the same sum for any number of threads
+    return tree_lh;
+}
+
+void PhyloSuperTree::computePatternLikelihood(double *pattern_lh, double *cur_logl) {
+    int64_t off = 0;
+    double sum = 0.0;
+    for (auto *p : parts) {
+        double part_logl = 0.0;
+        p->computePatternLikelihood(pattern_lh + off, &part_logl);
+        sum += part_logl;
+        off += p->getAlnNPattern();
+    }
+    if (cur_logl) *cur_logl = sum;
+}
+
+double PhyloSuperTree::optimizeAllBranches(int my_iterations, double tolerance, int maxNRStep) {
+    computePartitionOrder();
+    const double tol = tolerance / std::min<int>((int)parts.size(), 10);
+    for_each_partition(part_order, num_threads, [&](int p) { cur_score[p] = parts[p]->optimizeAllBranches(my_iterations, tol, maxNRStep); });
+    double tree_lh = 0.0;
+    for (double x : cur_score) tree_lh += x;
+    return tree_lh;
+}
+
+void PhyloSuperTree::clearAllPartialLH() {
+    for (auto *p : parts) p->clearAllPartialLH();
+}
+
 }  // namespace b200

@@ -61,4 +61,29 @@ private:
     void computePartitionOrder();
 };
 
+// The edge-unlinked partition model (PhyloSuperTree proper; `-Q` / `-sp`: every partition tree has its own topology-induced
+// subtree and its own branch lengths; tree/phylosupertree.cpp:653-791).  The partition trees are independent PhyloTree objects
+// (borrowed: the caller configures and owns them); the class is the driver: logL = sum_p logL_p with the partitions evaluated
+// concurrently, most expensive first (computePartitionOrder :653-695), one device engine and stream each, and
+// optimizeAllBranches = every partition's own optimizeAllBranches with tolerance / min(ntrees, 10) (:773-791).
+// computeBranchLengths (the super tree's lengths as averages over the partitions, :787) is display logic of the caller.
+class PhyloSuperTree {
+public:
+    PhyloSuperTree();
+    int addPartition(PhyloTree *part);
+    double computeLikelihood(double *pattern_lh = nullptr);                                                  // :697-726
+    void computePatternLikelihood(double *pattern_lh, double *cur_logl = nullptr);                           // :736-763 (concatenated)
+    double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);   // :773-791
+    void clearAllPartialLH();
+    int numPartitions() const { return (int)parts.size(); }
+    int64_t numPatterns() const;
+    std::vector<PhyloTree *> parts;
+    std::vector<double> cur_score;   // part_info[part].cur_score
+    int num_threads = 0;
+
+private:
+    std::vector<int> part_order;
+    void computePartitionOrder();
+};
+
 }  // namespace b200

@@ -122,3 +122,68 @@ class PhyloSuperTree:
     @property
     def device_bytes(self):
         return int(self.lib.b200st_device_bytes(self._h))
+
+
+class PhyloSuperTreeUnlinked:
+    """The edge-unlinked partition model (`-Q` / `-sp`; the reference's PhyloSuperTree, tree/phylosupertree.cpp:653-791;
+    include/b200pt.h, b200ut_*): a driver over independent iqtree2_b200.phylotree.PhyloTree objects, each with its own taxa,
+    alignment, model, tree and branch lengths.  The partition trees are borrowed and kept alive here."""
+
+    def __init__(self, num_threads=0):
+        self.lib = load_library()
+        L = self.lib
+        L.b200ut_create.restype = C.c_void_p
+        L.b200ut_last_error.restype = C.c_char_p
+        L.b200ut_last_error.argtypes = [C.c_void_p]
+        L.b200ut_destroy.argtypes = [C.c_void_p]
+        L.b200ut_num_patterns.restype = C.c_int64
+        L.b200ut_num_patterns.argtypes = [C.c_void_p]
+        self._h = C.c_void_p(L.b200ut_create(num_threads))
+        self.parts = []
+
+    def _check(self, rc):
+        if rc < 0:
+            raise EngineError(self.lib.b200ut_last_error(self._h).decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.b200ut_destroy(self._h)
+            self._h = None
+        self.parts = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_partition(self, tree):
+        self._check(self.lib.b200ut_add_partition(self._h, tree._h))
+        self.parts.append(tree)
+        return len(self.parts) - 1
+
+    def clear_all_partial_lh(self):
+        self._check(self.lib.b200ut_clear_all_partial_lh(self._h))
+
+    def compute_likelihood(self, want_pattern_lh=False):
+        out = C.c_double()
+        plh = np.zeros(self.lib.b200ut_num_patterns(self._h)) if want_pattern_lh else None
+        self._check(self.lib.b200ut_compute_likelihood(self._h, C.byref(out), _dp(plh)))
+        return (out.value, plh) if want_pattern_lh else out.value
+
+    def compute_pattern_likelihood(self):
+        out = C.c_double()
+        plh = np.zeros(self.lib.b200ut_num_patterns(self._h))
+        self._check(self.lib.b200ut_compute_pattern_likelihood(self._h, _dp(plh), C.byref(out)))
+        return plh, out.value
+
+    def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
+        out = C.c_double()
+        self._check(self.lib.b200ut_optimize_all_branches(self._h, C.c_int32(iterations), C.c_double(tolerance), C.c_int32(max_nr_step),
+                                                          C.byref(out)))
+        return out.value
+
+    def part_scores(self):
+        s = np.zeros(len(self.parts))
+        self._check(self.lib.b200ut_get_part_scores(self._h, _dp(s)))
+        return s

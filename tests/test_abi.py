@@ -20,7 +20,7 @@ def declared_symbols():
 def declared_tree_symbols():
     src = open(os.path.join(ROOT, "include", "b200pt.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(b200(?:pt|st)_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(b200(?:pt|st|ut)_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_tree_level_symbols_exported():
@@ -28,6 +28,7 @@ def test_tree_level_symbols_exported():
     lib = ctypes.CDLL(blk.build())
     syms = declared_tree_symbols()
     assert len([s for s in syms if s.startswith("b200st_")]) >= 20
+    assert len([s for s in syms if s.startswith("b200ut_")]) >= 11
     for sym in syms:
         assert hasattr(lib, sym), sym
 
