@@ -266,13 +266,14 @@ double PhyloSuperTree::computeLikelihood(double *pattern_lh) {
 }
 
 void PhyloSuperTree::computePatternLikelihood(double *pattern_lh, double *cur_logl) {
+    // cur_logl is an input in the reference (a sanity check against sum_p freq * pattern_lh, :748-761); here the partitions'
+    // scores of this very evaluation are handed back instead
     int64_t off = 0;
     double sum = 0.0;
-    for (auto *p : parts) {
-        double part_logl = 0.0;
-        p->computePatternLikelihood(pattern_lh + off, &part_logl);
-        sum += part_logl;
-        off += p->getAlnNPattern();
+    for (size_t p = 0; p < parts.size(); p++) {
+        cur_score[p] = parts[p]->computeLikelihood(pattern_lh + off);
+        sum += cur_score[p];
+        off += parts[p]->getAlnNPattern();
     }
     if (cur_logl) *cur_logl = sum;
 }
