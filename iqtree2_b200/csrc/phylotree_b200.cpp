@@ -1093,6 +1093,10 @@ NNIMove PhyloTree::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove
     }
     restore();
     curScore = backupScore;
+    // the theta buffer belongs to a branch of the last alternative topology: never reuse it for the restored tree (the reference
+    // leaves theta_computed set; every caller of it goes through optimizeOneBranch, which clears the flag, first)
+    theta_computed = false;
+    b200lk_theta_reset(engine_);
     return nniMoves[0].newloglh > nniMoves[1].newloglh ? nniMoves[0] : nniMoves[1];
 }
 
