@@ -49,18 +49,19 @@ int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tole
 /* optimizeAllBranches queues each sweep as a whole (b200lk_enqueue_newton_branch): one synchronisation per sweep */
 int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on);
 /* NNI evaluation on the resident CLVs — PhyloTree::getBestNNIForBran (tree/phylotree.cpp:4069-4322) on inner branch `branch`
- * (node1 = end a, node2 = end b of b200pt_get_branches) with Params::nni5 = nni5: both alternative topologies are scored on the
+ * (node1 = end a, node2 = end b of b200pt_get_branches; reverse != 0: the other way round — which end is node1 decides the
+ * order in which the five branches are re-optimised, hence the last digits of the scores) with Params::nni5 = nni5: both alternative topologies are scored on the
  * engine's two spare CLV slots (the reference's nni_partial_lh) after re-optimising the central branch (nni5: and the four
  * adjacent ones, NNI_MAX_NR_STEP Newton steps each); the tree, its lengths and its CLVs are as before on return.
  * Move m swaps the first other neighbour of node1 with the m-th other neighbour of node2.  Outputs: score[2] =
  * NNIMove::newloglh; new_len[2][5] = NNIMove::newLen ([0] central, [1..2] node1's, [3..4] node2's other branches);
  * swap_nodes[2][2] = node ids of the swapped neighbours; outer_nodes[2][4] = node ids at the far ends of the branches of
  * new_len[1..4]; pattern_lh (may be NULL): [2][nptn] pattern log-likelihoods of the two topologies (NNIMove::ptnlh). */
-int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t nni5, double *score, double *new_len, int32_t *swap_nodes,
+int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t reverse, int32_t nni5, double *score, double *new_len, int32_t *swap_nodes,
                                  int32_t *outer_nodes, double *pattern_lh);
 /* PhyloTree::doNNI (tree/phylotree.cpp:3947-4036) of move 0 / 1 of that branch, then changeNNIBrans (:4038-4067) with new_len
  * (5 doubles as returned above; NULL = keep the lengths) */
-int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh);
+int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t reverse, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh);
 /* number of partial-likelihood updates planned so far (PhyloTree::num_partial_lh_computations) */
 int64_t b200pt_num_partial_lh_computations(b200pt_tree *t);
 

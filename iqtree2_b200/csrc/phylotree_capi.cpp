@@ -1,4 +1,5 @@
 // phylotree_capi.cpp — extern "C" binding of b200::PhyloTree (include/b200pt.h).
+#include <algorithm>
 #include <cstring>
 #include <exception>
 #include <stdexcept>
@@ -120,9 +121,10 @@ int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tole
 }
 // node1 = end a, node2 = end b of the branch as b200pt_get_branches reports them; move m swaps the first other neighbour of
 // node1 with the m-th other neighbour of node2 (tree/phylotree.cpp:4168-4183)
-static void nniMovesOf(b200pt_tree *t, int branch, b200::NNIMove mv[2]) {
+static void nniMovesOf(b200pt_tree *t, int branch, int reverse, b200::NNIMove mv[2]) {
     b200::PhyloNode *a, *b;
     ends(t, branch, a, b);
+    if (reverse) std::swap(a, b);
     if (a->isLeaf() || b->isLeaf() || a->neighbors.size() != 3 || b->neighbors.size() != 3)
         throw std::runtime_error("NNI needs an inner branch between two degree-3 nodes");
     int k1 = -1, cnt = 0;
@@ -134,11 +136,11 @@ static void nniMovesOf(b200pt_tree *t, int branch, b200::NNIMove mv[2]) {
             cnt++;
         }
 }
-int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t nni5, double *score, double *new_len, int32_t *swap_nodes,
+int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t reverse, int32_t nni5, double *score, double *new_len, int32_t *swap_nodes,
                                  int32_t *outer_nodes, double *pattern_lh) {
     GUARD({
         b200::NNIMove mv[2];
-        nniMovesOf(t, branch, mv);
+        nniMovesOf(t, branch, reverse, mv);
         const int64_t nptn = t->tree.getAlnNPattern();
         if (pattern_lh) { mv[0].ptnlh = pattern_lh; mv[1].ptnlh = pattern_lh + nptn; }
         t->tree.params.nni5 = nni5 != 0;
@@ -155,11 +157,11 @@ int b200pt_get_best_nni_for_bran(b200pt_tree *t, int32_t branch, int32_t nni5, d
         }
     })
 }
-int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh) {
+int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t reverse, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh) {
     GUARD({
         if (move < 0 || move > 1) throw std::runtime_error("move must be 0 or 1");
         b200::NNIMove mv[2];
-        nniMovesOf(t, branch, mv);
+        nniMovesOf(t, branch, reverse, mv);
         t->tree.doNNI(mv[move], clear_lh != 0);
         if (new_len) {
             t->tree.params.nni5 = nni5 != 0;

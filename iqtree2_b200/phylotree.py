@@ -118,30 +118,33 @@ class PhyloTree:
     def optimize_one_branch(self, branch, clear_lh=True, max_nr_step=100):
         self._check(self.lib.b200pt_optimize_one_branch(self._h, branch, int(clear_lh), max_nr_step))
 
-    def get_best_nni_for_bran(self, branch, nni5=True, want_pattern_lh=False):
+    def get_best_nni_for_bran(self, branch, nni5=True, want_pattern_lh=False, reverse=False):
         """PhyloTree::getBestNNIForBran: the two NNIs around inner branch `branch`, evaluated on resident CLVs.  Two dicts:
-        score, new_len (5 or 1), swap = (node id on node1's side, on node2's side), outer = node ids of new_len[1..4]"""
+        score, new_len (5 or 1), swap = (node id on node1's side, on node2's side), outer = node ids of new_len[1..4].
+        node1 / node2 = ends a / b of branches(), or b / a with reverse=True"""
         score, new_len = np.zeros(2), np.zeros((2, 5))
         sw, outer = np.zeros((2, 2), dtype=np.int32), np.zeros((2, 4), dtype=np.int32)
         plh = np.zeros((2, self.nptn)) if want_pattern_lh else None
-        self._check(self.lib.b200pt_get_best_nni_for_bran(self._h, C.c_int32(int(branch)), C.c_int32(1 if nni5 else 0), _dp(score),
+        self._check(self.lib.b200pt_get_best_nni_for_bran(self._h, C.c_int32(int(branch)), C.c_int32(1 if reverse else 0),
+                                                           C.c_int32(1 if nni5 else 0), _dp(score),
                                                            _dp(new_len), sw.ctypes.data_as(C.c_void_p), outer.ctypes.data_as(C.c_void_p),
                                                            _dp(plh) if plh is not None else None))
-        moves = [dict(move=m, score=float(score[m]), new_len=new_len[m].tolist() if nni5 else new_len[m, :1].tolist(),
+        moves = [dict(move=m, reverse=bool(reverse), score=float(score[m]), new_len=new_len[m].tolist() if nni5 else new_len[m, :1].tolist(),
                       swap=(int(sw[m, 0]), int(sw[m, 1])), outer=[int(x) for x in outer[m]]) for m in range(2)]
         if plh is not None:
             for m in range(2):
                 moves[m]["pattern_lh"] = plh[m]
         return moves
 
-    def do_nni(self, branch, move, new_len=None, clear_lh=True):
+    def do_nni(self, branch, move, new_len=None, clear_lh=True, reverse=False):
         """PhyloTree::doNNI (+ changeNNIBrans when new_len is given: 5 lengths, or 1 = central branch only)"""
         nni5 = new_len is not None and len(new_len) == 5
         buf = None
         if new_len is not None:
             buf = np.zeros(5)
             buf[:len(new_len)] = new_len
-        self._check(self.lib.b200pt_do_nni(self._h, C.c_int32(int(branch)), C.c_int32(int(move)), C.c_int32(1 if nni5 else 0),
+        self._check(self.lib.b200pt_do_nni(self._h, C.c_int32(int(branch)), C.c_int32(1 if reverse else 0), C.c_int32(int(move)),
+                                            C.c_int32(1 if nni5 else 0),
                                             _dp(buf) if buf is not None else None, C.c_int32(1 if clear_lh else 0)))
 
     def set_pipelined_sweep(self, on=True):

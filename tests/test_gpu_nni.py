@@ -136,3 +136,34 @@ def test_do_nni_applies_the_evaluated_move(nni5):
     _, _, l2 = g.branches()
     np.testing.assert_array_equal(l1, l2)
     assert np.isfinite(g.compute_likelihood())
+
+
+@pytest.mark.parametrize("nni5", [True, False])
+def test_nni_against_reference_golden(nni5):
+    """the CUDA path against numbers minted from the compiled reference (tests/golden/ref_config1_nni.json): BASELINE config 1,
+    every inner branch, both moves — scores and re-optimised lengths to 1e-6"""
+    from test_nni_golden_cpu import check_moves, golden_cases
+    g, t, names, pat, freq, model, inv = build("config1")
+    nt = len(names)
+    gold_tree, cases = golden_cases(nni5)
+    by_split = {frozenset(c["split"]): c for c in cases}
+    assert abs(g.compute_likelihood() - cases[0]["logl_before"]) < 1e-6
+    a, b, _ = g.branches()
+    rec, adj = gpu_leafsets(g, nt)
+    allt = frozenset(range(nt))
+    n = 0
+    for br in range(len(a)):
+        na, nb = int(a[br]), int(b[br])
+        if na < nt or nb < nt:
+            continue
+        side = rec(nb, na)
+        case = by_split[allt - side if 0 in side else side]
+        # node1 = the end the reference's first swapped subtree hangs off
+        reverse = not frozenset(case["moves"][0]["swap"][1]) <= side
+        n1, n2 = (nb, na) if reverse else (na, nb)
+        got = g.get_best_nni_for_bran(br, nni5=nni5, reverse=reverse)
+        check_moves(got, case,
+                    lambda mv: (rec(mv["swap"][0], n1), rec(mv["swap"][1], n2)),
+                    lambda mv: [rec(x, n1 if x in adj[n1] else n2) for x in mv["outer"]], nni5)
+        n += 1
+    assert n == len(cases)
