@@ -124,6 +124,18 @@ int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat
  * with its patterns. */
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite);
 
+/* E-step of the reference's EM algorithms, on the device.  PhyloTree::computePatternLhCat(wsl) (tree/phylotree.cpp:1338-1393;
+ * wsl as SiteLoglType, utils/tools.h:555: 2 = WSL_RATECAT, 3 = WSL_MIXTURE, 4 = WSL_MIXTURE_RATECAT) takes the per-category
+ * pattern likelihoods L[p][k] of the LAST b200lk_branch_logl — for an unfused mixture summed over the mixture classes (per rate
+ * category) or over the rate categories (per class) — and the loops of RateFree::optimizeWithEM (model/ratefree.cpp:556-573,
+ * add_invar = 1) / ModelMixture::optimizeWithEM (model/modelmixture.cpp:2008-2024, add_invar = 0) turn them into
+ *     posterior[p][k] = ptn_freq[p] * L[p][k] / (add_invar * ptn_invar[p] + sum_k L[p][k]),   new_prop[k] = sum_p posterior[p][k].
+ * *ncat_out = K (getNumLhCat(wsl)); new_prop: K doubles (NULL: only K is returned); posterior (may be NULL): [nptn][K] on the
+ * host.  The posteriors stay on the device: the M-step's per-category trees (ratefree.cpp:617-650: ptn_freq := one column) take
+ * them with b200lk_set_pattern_freq_from_posterior(dst, src, k) — same pattern count, same device — without a host copy. */
+int b200lk_em_posterior(b200lk_engine *e, int32_t wsl, int32_t add_invar, double *new_prop, double *posterior, int32_t *ncat_out);
+int b200lk_set_pattern_freq_from_posterior(b200lk_engine *dst, b200lk_engine *src, int32_t k);
+
 /* The robust-phylo variants of computeLikelihoodBranch (Params::robust_phy_keep < 1, `--robust-phy`: the log-likelihood summed
  * over the best keep*nsite sites; Params::robust_median, `--robust-median`: the median site log-likelihood;
  * tree/phylokernelnew.h:3134-3173): every later b200lk_branch_logl (and its enqueue form) returns that value; _pattern_lh is

@@ -57,6 +57,10 @@ struct b200lk_engine {
     int num_sms = 148;
     int info_smem_optin = 0;
     bool walk20_attr_set = false;
+    // EM E-step (b200lk_em_posterior): posteriors [K][Ppad], per-block partial sums, the K sums
+    double *d_post = nullptr, *d_em_red = nullptr, *d_em_out = nullptr;
+    int post_K = 0;
+    bool have_lh_cat = false;   // _pattern_lh_cat holds the categories of a branch_logl call
     // robust phylo (b200lk_set_robust_phylo): keys / values / running site count of the sorted patterns + cub's scratch
     double robust_keep = 1.0;
     int robust_median = 0;
@@ -147,6 +151,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d_scale); cudaFree(e->d_theta); cudaFree(e->d_buffer_scale); cudaFree(e->d_pattern_lh);
     cudaFree(e->d_pattern_scaling); cudaFree(e->d_pattern_lh_cat); cudaFree(e->d_opinfo); cudaFree(e->d_ops);
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
+    cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
@@ -886,6 +891,7 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     }
     prof_mark(e, 2);
     CK(cudaGetLastError());
+    e->have_lh_cat = true;
     e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);
     e->pending_marks = 2;
     return 0;
@@ -1173,6 +1179,59 @@ extern "C" int b200lk_get_pattern_lh(b200lk_engine *e, double *out) { return rea
 extern "C" int b200lk_get_pattern_scaling(b200lk_engine *e, double *out) { return read_plain(e, e->d_pattern_scaling, sizeof(double) * e->P, out); }
 extern "C" int b200lk_get_buffer_scale_all(b200lk_engine *e, double *out) { return read_plain(e, e->d_buffer_scale, sizeof(double) * e->P, out); }
 extern "C" int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_pattern_lh_cat, e->C, out); }
+// PhyloTree::computePatternLhCat(wsl) + the E-step loop of RateFree / ModelMixture::optimizeWithEM, on the device
+extern "C" int b200lk_em_posterior(b200lk_engine *e, int32_t wsl, int32_t add_invar, double *new_prop, double *posterior, int32_t *ncat_out) {
+    if (wsl < 2 || wsl > 4) return fail(e, B200LK_ERR_INVALID, "wsl: 2 = WSL_RATECAT, 3 = WSL_MIXTURE, 4 = WSL_MIXTURE_RATECAT");
+    if (!e->have_lh_cat) return fail(e, B200LK_ERR_STATE, "em_posterior: needs the per-category likelihoods of a b200lk_branch_logl call");
+    const bool marginal = e->cfg.nmix > 1 && !e->cfg.fused_mix_rate && (wsl == 2 || wsl == 3);
+    const int mode = !marginal ? 0 : wsl == 2 ? 1 : 2;
+    const int K = mode == 0 ? e->C : mode == 1 ? e->cfg.ncat : e->cfg.nmix;
+    if (ncat_out) *ncat_out = K;
+    if (!new_prop) return 0;
+    cudaSetDevice(e->cfg.device);
+    const int nblocks = (int)(e->Ppad / kTile);
+    if (!e->d_post) {
+        CK(cudaMalloc(&e->d_post, sizeof(double) * (size_t)e->C * e->Ppad));
+        CK(cudaMalloc(&e->d_em_red, sizeof(double) * (size_t)e->C * nblocks));
+        CK(cudaMalloc(&e->d_em_out, sizeof(double) * (size_t)e->C));
+    }
+    const size_t smem = sizeof(double) * (kTile / 32) * K;
+    if (smem > 200 * 1024) return fail(e, B200LK_ERR_INVALID, "em_posterior: too many categories");
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(k_em_posterior, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_em_posterior<<<nblocks, kTile, smem, e->stream>>>(e->d, mode, K, add_invar != 0, e->d_post, e->d_em_red);
+    k_em_reduce<<<(K + 127) / 128, 128, 0, e->stream>>>(nblocks, K, e->d_em_red, e->d_em_out);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    e->post_K = K;
+    CK(cudaMemcpyAsync(new_prop, e->d_em_out, sizeof(double) * K, cudaMemcpyDeviceToHost, e->stream));
+    if (posterior) {   // [nptn][K] for callers that want the matrix on the host; the M-step does not need it
+        std::vector<double> col((size_t)e->Ppad);
+        for (int k = 0; k < K; k++) {
+            CK(cudaMemcpyAsync(col.data(), e->d_post + (size_t)k * e->Ppad, sizeof(double) * e->P, cudaMemcpyDeviceToHost, e->stream));
+            CK(sync_stream(e));
+            for (int64_t p = 0; p < e->P; p++) posterior[(size_t)p * K + k] = col[(size_t)p];
+        }
+    }
+    CK(sync_stream(e));
+    return 0;
+}
+
+extern "C" int b200lk_set_pattern_freq_from_posterior(b200lk_engine *dst, b200lk_engine *src, int32_t k) {
+    b200lk_engine *e = dst;   // errors are reported on the destination
+    if (!src->d_post || k < 0 || k >= src->post_K) return fail(dst, B200LK_ERR_STATE, "no posteriors for that category: call b200lk_em_posterior on the source engine first");
+    if (dst->P != src->P || dst->cfg.device != src->cfg.device) return fail(dst, B200LK_ERR_INVALID, "engines differ in pattern count or device");
+    cudaSetDevice(dst->cfg.device);
+    CK(sync_stream(src));
+    k_copy_column<<<(unsigned)((dst->P + 255) / 256), 256, 0, dst->stream>>>(dst->P, src->d_post + (size_t)k * src->Ppad, dst->d_freq);
+    dst->launches++;
+    CK(cudaGetLastError());
+    // the host copy of ptn_freq (NaN repair, robust phylo) follows
+    CK(cudaMemcpyAsync(dst->h_freq.data(), dst->d_freq, sizeof(double) * dst->P, cudaMemcpyDeviceToHost, dst->stream));
+    CK(sync_stream(dst));
+    dst->theta_computed = false;
+    return 0;
+}
+
 extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_theta, e->B, out); }
 extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");

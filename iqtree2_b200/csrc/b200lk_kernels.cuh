@@ -1576,6 +1576,63 @@ __global__ void k_asc_finish_derv(Dev D, const double *raw, double *result) {
     result[0] = raw[0] + (double)D.asc_nsite * df_frac;
     result[1] = raw[1] + (double)D.asc_nsite * (ddf_frac + df_frac * df_frac);
 }
+// E-step of the reference's EM algorithms (RateFree::optimizeWithEM, model/ratefree.cpp:556-573; ModelMixture::optimizeWithEM,
+// model/modelmixture.cpp:2008-2024) on the per-category pattern likelihoods of the last k_root, marginalised as
+// PhyloTree::computePatternLhCat(wsl) does (tree/phylotree.cpp:1366-1391): mode 0 = every category (K = C), 1 = per rate category
+// (sum over the mixture classes, K = ncat), 2 = per mixture class (sum over the rate categories, K = nmix).
+//   post[k][p] = freq_p L_pk / (invar_p*add_invar + sum_k L_pk)   (column-major: a column is a ptn_freq vector for the M-step)
+//   red[block][k] = sum over the block's patterns of post[k][p]   (k_em_reduce adds the blocks in order)
+__device__ __forceinline__ double em_marginal(const double *lh_cat, int mode, int k, int ncat, int nmix) {
+    if (mode == 0) return lh_cat[(long long)k * kWarp];
+    if (mode == 1) {
+        double v = lh_cat[(long long)k * kWarp];
+        for (int m = 1; m < nmix; m++) v += lh_cat[(long long)(m * ncat + k) * kWarp];
+        return v;
+    }
+    double v = lh_cat[(long long)(k * ncat) * kWarp];
+    for (int c = 1; c < ncat; c++) v += lh_cat[(long long)(k * ncat + c) * kWarp];
+    return v;
+}
+__global__ void __launch_bounds__(kTile) k_em_posterior(Dev D, int mode, int K, int add_invar, double *post, double *red) {
+    extern __shared__ double s_em[];   // [warps][K]
+    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool live = p < D.Pobs;
+    const double *lh_cat = D.pattern_lh_cat + pbase(p, D.C);
+    double w = 0.0;
+    if (live) {
+        double lk = add_invar ? D.invar[p] : 0.0;
+        for (int k = 0; k < K; k++) lk += em_marginal(lh_cat, mode, k, D.ncat, D.nmix);
+        w = D.freq[p] / lk;
+    }
+    for (int k = 0; k < K; k++) {
+        double v = live ? em_marginal(lh_cat, mode, k, D.ncat, D.nmix) * w : 0.0;
+        post[(long long)k * D.Ppad + p] = v;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+        if (lane == 0) s_em[wid * K + k] = v;
+    }
+    __syncthreads();
+    const int nw = blockDim.x >> 5;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double v = s_em[k];
+        for (int w2 = 1; w2 < nw; w2++) v += s_em[w2 * K + k];
+        red[(long long)blockIdx.x * K + k] = v;
+    }
+}
+__global__ void k_em_reduce(int nblocks, int K, const double *red, double *out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    double v = 0.0;
+    for (int b = 0; b < nblocks; b++) v += red[(long long)b * K + k];
+    out[k] = v;
+}
+// dst ptn_freq := one column of the posteriors (the M-step trees of the EM algorithms: ratefree.cpp:636-640)
+__global__ void k_copy_column(long long P, const double *col, double *dst) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) dst[p] = col[p];
+}
+
 // robust phylo (:3134-3173): lh / f = pattern log-likelihoods in ascending order with their frequencies, cum = running sum of f.
 // Pattern i holds the site ranks [cum[i] - f[i], cum[i]).  keep < 1: sum of the site log-likelihoods from rank
 // (int)((1 - keep) * sites) on; median: the site of rank sites/2 (odd) or the mean of ranks sites/2 - 1 and sites/2 (even).

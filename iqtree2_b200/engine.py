@@ -25,7 +25,8 @@ ABI_SYMBOLS = [
     "b200lk_get_tip_partial_lh", "b200lk_pattern_lh_dev", "b200lk_set_profiling", "b200lk_last_timing",
     "b200lk_launch_count", "b200lk_set_reference_quirks",
     "b200lk_enqueue_branch_logl", "b200lk_enqueue_branch_derv", "b200lk_enqueue_logl_from_buffer", "b200lk_finish",
-    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment", "b200lk_set_robust_phylo",
+    "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment", "b200lk_set_robust_phylo", "b200lk_em_posterior",
+    "b200lk_set_pattern_freq_from_posterior",
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
 ]
 
@@ -235,6 +236,21 @@ class LikelihoodEngine:
         """+ASC (1 = Lewis, 2 = Holder's +ASC_MIS): the last num_unobserved patterns are the unobserved constant patterns
         (Holder: nstates groups of num_unobserved/nstates), nsite = aln->getNSite()"""
         self._check(self.lib.b200lk_set_ascertainment(self._h, C.c_int32(asc_type), C.c_int64(num_unobserved), C.c_int64(nsite)))
+
+    def em_posterior(self, wsl, add_invar, want_posterior=False):
+        """E-step of RateFree / ModelMixture::optimizeWithEM on the categories of computePatternLhCat(wsl) of the last
+        branch_logl (2 = RATECAT, 3 = MIXTURE, 4 = MIXTURE_RATECAT): new_prop[K] (and posterior[nptn][K])"""
+        K = C.c_int32()
+        self._check(self.lib.b200lk_em_posterior(self._h, C.c_int32(wsl), C.c_int32(int(bool(add_invar))), None, None, C.byref(K)))
+        prop = np.zeros(K.value)
+        post = np.zeros((self.nptn, K.value)) if want_posterior else None
+        self._check(self.lib.b200lk_em_posterior(self._h, C.c_int32(wsl), C.c_int32(int(bool(add_invar))), _dp(prop),
+                                                 _dp(post) if post is not None else None, C.byref(K)))
+        return (prop, post) if want_posterior else prop
+
+    def set_pattern_freq_from_posterior(self, src, k):
+        """ptn_freq := column k of src's posteriors (device to device; the M-step trees of the EM algorithms)"""
+        self._check(self.lib.b200lk_set_pattern_freq_from_posterior(self._h, src._h, C.c_int32(int(k))))
 
     def set_robust_phylo(self, keep=1.0, median=False):
         """Params::robust_phy_keep / robust_median: branch_logl returns the log-likelihood of the best sites / the median site"""

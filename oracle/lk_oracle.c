@@ -1066,6 +1066,56 @@ int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
 int orc_get_pattern_lh(orc_engine *e, double *out) { memcpy(out, e->pattern_lh, sizeof(double) * e->cfg.nptn); return 0; }
 int orc_get_pattern_scaling(orc_engine *e, double *out) { memcpy(out, e->pattern_scaling, sizeof(double) * e->cfg.nptn); return 0; }
 int orc_get_pattern_lh_cat(orc_engine *e, double *out) { memcpy(out, e->pattern_lh_cat, sizeof(double) * e->cfg.nptn * e->C); return 0; }
+/* PhyloTree::computePatternLhCat(wsl) after computeLikelihoodBranch (tree/phylotree.cpp:1338-1393; SiteLoglType utils/tools.h:555:
+ * 2 = WSL_RATECAT, 3 = WSL_MIXTURE, 4 = WSL_MIXTURE_RATECAT): the per-category pattern likelihoods of the last orc_branch_logl,
+ * for an unfused mixture summed over the mixture classes (per rate category) or over the rate categories (per class).
+ * Returns K, the number of categories per pattern; out (may be NULL) is [nptn][K]. */
+int orc_pattern_lh_cat_wsl(orc_engine *e, int wsl, double *out) {
+    const int C = e->C, ncat = e->cfg.ncat, nmix = e->cfg.nmix;
+    const int marginal = nmix > 1 && !e->cfg.fused_mix_rate && (wsl == 2 || wsl == 3);
+    const int K = !marginal ? C : wsl == 2 ? ncat : nmix;
+    if (wsl < 2 || wsl > 4) { snprintf(e->err, sizeof e->err, "wsl: 2 = RATECAT, 3 = MIXTURE, 4 = MIXTURE_RATECAT"); return -1; }
+    if (!out) return K;
+    for (size_t p = 0; p < (size_t)e->cfg.nptn; p++) {
+        const double *lh_cat = e->pattern_lh_cat + p * C;
+        double *res = out + p * K;
+        if (!marginal) memcpy(res, lh_cat, sizeof(double) * C);
+        else if (wsl == 3) { /* :1368-1378 */
+            for (int m = 0; m < nmix; m++) {
+                double lh = lh_cat[m * ncat];
+                for (int c = 1; c < ncat; c++) lh += lh_cat[m * ncat + c];
+                res[m] = lh;
+            }
+        } else { /* :1379-1391 */
+            memcpy(res, lh_cat, sizeof(double) * ncat);
+            for (int m = 1; m < nmix; m++)
+                for (int c = 0; c < ncat; c++) res[c] += lh_cat[m * ncat + c];
+        }
+    }
+    return K;
+}
+
+/* The E-step of RateFree::optimizeWithEM (model/ratefree.cpp:556-573; add_invar = 1) and ModelMixture::optimizeWithEM
+ * (model/modelmixture.cpp:2008-2024; add_invar = 0 unless optimize_linked_gtr) on the categories of orc_pattern_lh_cat_wsl:
+ * posterior[p][k] = ptn_freq[p] * L[p][k] / (ptn_invar[p]*add_invar + sum_k L[p][k]), new_prop[k] = sum_p posterior[p][k]. */
+int orc_em_posterior(orc_engine *e, int wsl, int add_invar, double *new_prop, double *posterior) {
+    const int K = orc_pattern_lh_cat_wsl(e, wsl, NULL);
+    if (K < 0) return K;
+    const size_t P = (size_t)e->cfg.nptn;
+    double *post = posterior ? posterior : (double *)malloc(sizeof(double) * P * K);
+    orc_pattern_lh_cat_wsl(e, wsl, post);
+    for (int k = 0; k < K; k++) new_prop[k] = 0.0;
+    for (size_t p = 0; p < P; p++) {
+        double *this_lk_cat = post + p * K;
+        double lk_ptn = add_invar ? e->ptn_invar[p] : 0.0;
+        for (int k = 0; k < K; k++) lk_ptn += this_lk_cat[k];
+        lk_ptn = e->ptn_freq[p] / lk_ptn;
+        for (int k = 0; k < K; k++) { this_lk_cat[k] *= lk_ptn; new_prop[k] += this_lk_cat[k]; }
+    }
+    if (!posterior) free(post);
+    return K;
+}
+
 int orc_get_theta(orc_engine *e, double *out) { memcpy(out, e->theta, sizeof(double) * e->cfg.nptn * e->B); return 0; }
 int orc_get_buffer_scale_all(orc_engine *e, double *out) { memcpy(out, e->buffer_scale_all, sizeof(double) * e->cfg.nptn); return 0; }
 int orc_get_scale_num(orc_engine *e, int slot, uint16_t *out) {

@@ -170,6 +170,26 @@ class OracleEngine:
     def get_pattern_lh_cat(self):
         return self._get("orc_get_pattern_lh_cat", self.nptn * self.Cmix).reshape(self.nptn, self.Cmix)
 
+    def pattern_lh_cat_wsl(self, wsl):
+        """computePatternLhCat(wsl) of the last branch_logl: [nptn][K] (2 = RATECAT, 3 = MIXTURE, 4 = MIXTURE_RATECAT)"""
+        L = lib()
+        K = L.orc_pattern_lh_cat_wsl(self._h, C.c_int(wsl), None)
+        if K < 0:
+            raise RuntimeError(L.orc_last_error(self._h).decode())
+        out = np.zeros((self.nptn, K))
+        L.orc_pattern_lh_cat_wsl(self._h, C.c_int(wsl), _dp(out))
+        return out
+
+    def em_posterior(self, wsl, add_invar):
+        """E-step of RateFree / ModelMixture::optimizeWithEM: (new_prop[K], posterior[nptn][K])"""
+        L = lib()
+        K = L.orc_pattern_lh_cat_wsl(self._h, C.c_int(wsl), None)
+        if K < 0:
+            raise RuntimeError(L.orc_last_error(self._h).decode())
+        prop, post = np.zeros(K), np.zeros((self.nptn, K))
+        L.orc_em_posterior(self._h, C.c_int(wsl), C.c_int(int(bool(add_invar))), _dp(prop), _dp(post))
+        return prop, post
+
     def get_theta(self):
         return self._get("orc_get_theta", self.nptn * self.B).reshape(self.nptn, self.Cmix, self.n)
 

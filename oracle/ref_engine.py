@@ -200,6 +200,14 @@ class RefTree:
         k = lib().iqref_get_branches(self._h, _p(masks), _p(lens))
         return {frozenset(np.nonzero(masks[b])[0].tolist()): float(lens[b]) for b in range(k)}
 
+    def pattern_lh_cat_wsl(self, wsl, leaf=0):
+        """PhyloTree::computePatternLhCat(wsl) at the pendant branch of `leaf`: [nptn][getNumLhCat(wsl)]"""
+        L = lib()
+        K = L.iqref_pattern_lh_cat_wsl(self._h, C.c_int(int(leaf)), C.c_int(int(wsl)), None)
+        out = np.zeros((self.nptn, K))
+        L.iqref_pattern_lh_cat_wsl(self._h, C.c_int(int(leaf)), C.c_int(int(wsl)), _p(out))
+        return out
+
     def best_nni(self, split, nni5=True):
         """PhyloTree::getBestNNIForBran on the inner branch with that split (side not containing taxon 0): two dicts with
         score, new_len, swap = (leaf sets of the two swapped subtrees), outer = leaf sets of the branches of new_len[1..4]"""

@@ -528,6 +528,20 @@ int iqref_best_nni(void *hv, const uint8_t *mask, int nni5, double *score, doubl
 // the new kernel does not maintain num_partial_lh_computations)
 int iqref_last_traversal_size(void *hv) { return (int)((Handle *)hv)->tree->traversal_info.size(); }
 
+// PhyloTree::computePatternLhCat(wsl) (tree/phylotree.cpp:1338-1393) on the pendant branch of alignment row `leaf`: copies
+// _pattern_lh_cat, nptn x getNumLhCat(wsl), and returns getNumLhCat(wsl)
+int iqref_pattern_lh_cat_wsl(void *hv, int leaf, int wsl, double *out) {
+    Handle *h = (Handle *)hv;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
+    h->tree->current_it = nb;
+    h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    h->tree->computePatternLhCat((SiteLoglType)wsl);
+    const int K = h->tree->getNumLhCat((SiteLoglType)wsl);
+    if (out) memcpy(out, h->tree->_pattern_lh_cat, sizeof(double) * h->nptn * K);
+    return K;
+}
+
 // --robust-phy keep / --robust-median (utils/tools.cpp:4374-4392): Params::robust_phy_keep / robust_median for trees created
 // AFTERWARDS (initializeAllPartialLh allocates _site_lh when they are set, tree/phylotree.cpp:908-909); (1.0, 0) = off
 void iqref_set_robust(double keep, int median) {
