@@ -46,6 +46,13 @@ int b200pt_compute_likelihood_from_buffer(b200pt_tree *t, double *logl);
 int b200pt_compute_pattern_likelihood(b200pt_tree *t, double *pattern_lh, double *pattern_lh_cat /* may be NULL */);
 int b200pt_optimize_one_branch(b200pt_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step);
 int b200pt_optimize_all_branches(b200pt_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+/* PhyloTree::optimizeTreeLengthScaling (tree/phylotree.cpp:2457-2488): one factor for all branch lengths, Brent's method
+ * (utils/optimization.cpp:185-373) over clearAllPartialLH + computeLikelihood; *scaling in (the factor the current lengths
+ * stand for) and out; used by the M-step of RateFree::optimizeWithEM and by --tree-len-scale.  b200pt_scale_length: MTree::scaleLength
+ * + clearAllPartialLH. */
+int b200pt_optimize_tree_length_scaling(b200pt_tree *t, double min_scaling, double *scaling, double max_scaling, double gradient_epsilon,
+                                        double *logl);
+int b200pt_scale_length(b200pt_tree *t, double norm);
 /* optimizeAllBranches queues each sweep as a whole (b200lk_enqueue_newton_branch): one synchronisation per sweep */
 int b200pt_set_pipelined_sweep(b200pt_tree *t, int32_t on);
 /* NNI evaluation on the resident CLVs — PhyloTree::getBestNNIForBran (tree/phylotree.cpp:4069-4322) on inner branch `branch`

@@ -734,7 +734,15 @@ void PhyloTree::computePatternLikelihood(double *ptn_lh, double *cur_logl, doubl
 // ---------------------------------------------------------------------------------------------------------------
 // branch-length optimisation
 // ---------------------------------------------------------------------------------------------------------------
-double PhyloTree::computeFunction(double value) {   // tree/phylotree.cpp:2514-2520
+double PhyloTree::computeFunction(double value) {   // tree/phylotree.cpp:2514-2528
+    if (is_opt_scaling) {
+        if (value != current_scaling) {
+            scaleLength(value / current_scaling);
+            current_scaling = value;
+            clearAllPartialLH();
+        }
+        return -computeLikelihood();
+    }
     current_it->length = value;
     current_it_back->length = value;
     return -computeLikelihoodBranch(current_it, current_it_back->node);
@@ -959,6 +967,123 @@ double PhyloTree::optimizeAllBranches(int my_iterations, double tolerance, int m
     }
     curScore = tree_lh;
     return tree_lh;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tree-length scaling: one parameter, every evaluation a full traversal (the headline operation of bench.py).  Used by the
+// M-step of RateFree::optimizeWithEM (model/ratefree.cpp:641-643), optimizePatternRates (tree/phylotree.cpp:2558), --tree-len-scale.
+// ---------------------------------------------------------------------------------------------------------------
+void PhyloTree::scaleLength(double norm) {
+    for (auto *n : neighbors_) n->length *= norm;
+}
+
+// utils/optimization.cpp:185-316 (Brent's method as in Numerical Recipes), statement for statement
+double PhyloTree::brent_opt(double ax, double bx, double cx, double tol, double *foptx, double *f2optx, double fax, double fbx, double fcx) {
+    const int ITMAX = 100;
+    const double CGOLD = 0.3819660, ZEPS = 1.0e-10;
+    auto SIGN = [](double a, double b) { return b >= 0.0 ? std::fabs(a) : -std::fabs(a); };
+    double a, b, d = 0, etemp, fu, fv, fw, fx, p, q, r, tol1, tol2, u, v, w, x, xm, e = 0.0;
+    a = (ax < cx ? ax : cx);
+    b = (ax > cx ? ax : cx);
+    x = bx;
+    fx = fbx;
+    if (fax < fcx) { w = ax; fw = fax; v = cx; fv = fcx; }
+    else { w = cx; fw = fcx; v = ax; fv = fax; }
+    auto finish = [&]() {
+        *foptx = fx;
+        const double xw = x - w, wv = w - v, vx = v - x;
+        *f2optx = 2.0 * (fv * xw + fx * wv + fw * vx) / (v * v * xw + x * x * wv + w * w * vx);
+        return x;
+    };
+    for (int iter = 1; iter <= ITMAX; iter++) {
+        xm = 0.5 * (a + b);
+        tol2 = 2.0 * (tol1 = tol * std::fabs(x) + ZEPS);
+        if (std::fabs(x - xm) <= (tol2 - 0.5 * (b - a))) return finish();
+        if (std::fabs(e) > tol1) {
+            r = (x - w) * (fx - fv);
+            q = (x - v) * (fx - fw);
+            p = (x - v) * q - (x - w) * r;
+            q = 2.0 * (q - r);
+            if (q > 0.0) p = -p;
+            q = std::fabs(q);
+            etemp = e;
+            e = d;
+            if (std::fabs(p) >= std::fabs(0.5 * q * etemp) || p <= q * (a - x) || p >= q * (b - x))
+                d = CGOLD * (e = (x >= xm ? a - x : b - x));
+            else {
+                d = p / q;
+                u = x + d;
+                if (u - a < tol2 || b - u < tol2) d = SIGN(tol1, xm - x);
+            }
+        } else d = CGOLD * (e = (x >= xm ? a - x : b - x));
+        u = (std::fabs(d) >= tol1 ? x + d : x + SIGN(tol1, d));
+        fu = computeFunction(u);
+        if (fu <= fx) {
+            if (u >= x) a = x; else b = x;
+            v = w; w = x; x = u;
+            fv = fw; fw = fx; fx = fu;
+        } else {
+            if (u < x) a = u; else b = u;
+            if (fu <= fw || w == x) { v = w; w = u; fv = fw; fw = fu; }
+            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
+        }
+    }
+    return finish();
+}
+
+// utils/optimization.cpp:322-373
+double PhyloTree::minimizeOneDimen(double xmin, double xguess, double xmax, double tolerance, double *fx, double *f2x) {
+    if (xguess < xmin) xguess = xmin;
+    if (xguess > xmax) xguess = xmax;
+    const double eps = xguess * tolerance * 50.0;
+    double ax = xguess - eps;
+    if (ax < xmin) ax = xmin;
+    const double bx = xguess;
+    double cx = xguess + eps;
+    if (cx > xmax) cx = xmax;
+    const double fb = computeFunction(bx);
+    double fa = (ax < bx) ? computeFunction(ax) : fb;
+    double fc = (bx < cx) ? computeFunction(cx) : fb;
+    if ((fa < fb) || (fc < fb)) {   // the guess is not bracketed by its neighbourhood: use the bounds
+        if (ax != xmin) fa = computeFunction(xmin);
+        if (cx != xmax) fc = computeFunction(xmax);
+        ax = xmin;
+        cx = xmax;
+    }
+    const double optx = brent_opt(ax, bx, cx, tolerance, fx, f2x, fa, fb, fc);
+    if (*fx > fb) {   // if worse, return the initial value
+        *fx = computeFunction(bx);
+        return bx;
+    }
+    return optx;
+}
+
+// tree/phylotree.cpp:2457-2488
+double PhyloTree::optimizeTreeLengthScaling(double min_scaling, double &scaling, double max_scaling, double gradient_epsilon) {
+    const double TOL_TREE_LENGTH_SCALE = 0.001;   // :2455
+    initializeAllPartialLh();
+    is_opt_scaling = true;
+    current_scaling = scaling;
+    double negative_lh, ferror;
+    double min_brlen = params.max_branch_length, max_brlen = params.min_branch_length;
+    for (auto &br : branches_) {
+        max_brlen = std::max(max_brlen, br.first->length);
+        min_brlen = std::min(min_brlen, br.first->length);
+    }
+    if (min_brlen <= 0.0) min_brlen = params.min_branch_length;
+    if (max_scaling > 10.0 * params.max_branch_length / max_brlen) max_scaling = 10.0 * params.max_branch_length / max_brlen;
+    if (min_scaling < 0.1 * params.min_branch_length / min_brlen) min_scaling = 0.1 * params.min_branch_length / min_brlen;
+    try {
+        scaling = minimizeOneDimen(std::min(scaling, min_scaling), scaling, std::max(max_scaling, scaling),
+                                   std::max(TOL_TREE_LENGTH_SCALE, gradient_epsilon), &negative_lh, &ferror);
+    } catch (...) { is_opt_scaling = false; throw; }
+    if (scaling != current_scaling) {
+        scaleLength(scaling / current_scaling);
+        current_scaling = scaling;
+        clearAllPartialLH();
+    }
+    is_opt_scaling = false;
+    return computeLikelihood();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

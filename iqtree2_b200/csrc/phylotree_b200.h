@@ -151,6 +151,11 @@ public:
     virtual void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100);
     virtual double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100);
 
+    // ---- tree-length scaling (tree/phylotree.cpp:2455-2528; Brent's method utils/optimization.cpp:185-373) --------------
+    void scaleLength(double norm);                                                                  // tree/mtree.cpp:1835-1846
+    double minimizeOneDimen(double xmin, double xguess, double xmax, double tolerance, double *fx, double *f2x);
+    double optimizeTreeLengthScaling(double min_scaling, double &scaling, double max_scaling, double gradient_epsilon);
+
     // ---- NNI evaluation on the resident CLVs (tree/phylotree.cpp:3975-4322) ------------------------------------------
     // Evaluates the two NNIs around the inner branch (node1, node2) on the engine's two spare slots (nni_partial_lh): the
     // CLVs, flags and lengths of the current tree are untouched on return.  nniMoves: optional array of two, filled.
@@ -183,6 +188,8 @@ public:
     PhyloNeighbor *current_it = nullptr, *current_it_back = nullptr;
     bool theta_computed = false;
     double curScore = 0.0;
+    double current_scaling = 1.0;     // tree/phylotree.h: the scaling factor while optimizeTreeLengthScaling runs
+    bool is_opt_scaling = false;
     int leafNum = 0, nodeNum = 0;
     int max_lh_slots = 0;             // tree/phylotree.h (set by initializeAllPartialLh; T-2 for LM_PER_NODE)
     MemSlotVector mem_slots;
@@ -194,6 +201,7 @@ protected:
     int computeSize(PhyloNeighbor *nei, PhyloNode *dad);
     void check(int rc, const char *what);
     void freeTree();
+    double brent_opt(double ax, double bx, double cx, double tol, double *foptx, double *f2optx, double fax, double fbx, double fcx);
     void branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &node_slot, int &dad_kind, int &dad_id);
 
     std::vector<PhyloNode *> nodes_;

@@ -170,6 +170,16 @@ int b200pt_do_nni(b200pt_tree *t, int32_t branch, int32_t reverse, int32_t move,
         }
     })
 }
+int b200pt_optimize_tree_length_scaling(b200pt_tree *t, double min_scaling, double *scaling, double max_scaling, double gradient_epsilon,
+                                        double *logl) {
+    GUARD(*logl = t->tree.optimizeTreeLengthScaling(min_scaling, *scaling, max_scaling, gradient_epsilon))
+}
+int b200pt_scale_length(b200pt_tree *t, double norm) {
+    GUARD({
+        t->tree.scaleLength(norm);
+        t->tree.clearAllPartialLH();
+    })
+}
 int b200pt_set_robust_phylo(b200pt_tree *t, double keep, int32_t median) {
     GUARD({
         t->tree.params.robust_phy_keep = keep;

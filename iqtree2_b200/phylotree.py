@@ -147,6 +147,17 @@ class PhyloTree:
                                             C.c_int32(1 if nni5 else 0),
                                             _dp(buf) if buf is not None else None, C.c_int32(1 if clear_lh else 0)))
 
+    def optimize_tree_length_scaling(self, min_scaling, scaling, max_scaling, gradient_epsilon=0.001):
+        """PhyloTree::optimizeTreeLengthScaling: (logL, scaling)"""
+        sc, ll = C.c_double(float(scaling)), C.c_double()
+        self._check(self.lib.b200pt_optimize_tree_length_scaling(self._h, C.c_double(float(min_scaling)), C.byref(sc),
+                                                                 C.c_double(float(max_scaling)), C.c_double(float(gradient_epsilon)),
+                                                                 C.byref(ll)))
+        return ll.value, sc.value
+
+    def scale_length(self, norm):
+        self._check(self.lib.b200pt_scale_length(self._h, C.c_double(float(norm))))
+
     def set_pipelined_sweep(self, on=True):
         """queue every optimizeAllBranches sweep as a whole on the device (one synchronisation per sweep)"""
         self._check(self.lib.b200pt_set_pipelined_sweep(self._h, int(on)))

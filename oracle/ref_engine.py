@@ -208,6 +208,15 @@ class RefTree:
         L.iqref_pattern_lh_cat_wsl(self._h, C.c_int(int(leaf)), C.c_int(int(wsl)), _p(out))
         return out
 
+    def optimize_tree_length_scaling(self, min_scaling, scaling, max_scaling, gradient_epsilon):
+        """PhyloTree::optimizeTreeLengthScaling: (logL, scaling)"""
+        L = lib()
+        L.iqref_optimize_tree_length_scaling.restype = C.c_double
+        sc = C.c_double(float(scaling))
+        ll = L.iqref_optimize_tree_length_scaling(self._h, C.c_double(float(min_scaling)), C.byref(sc), C.c_double(float(max_scaling)),
+                                                  C.c_double(float(gradient_epsilon)))
+        return ll, sc.value
+
     def best_nni(self, split, nni5=True):
         """PhyloTree::getBestNNIForBran on the inner branch with that split (side not containing taxon 0): two dicts with
         score, new_len, swap = (leaf sets of the two swapped subtrees), outer = leaf sets of the branches of new_len[1..4]"""

@@ -528,6 +528,11 @@ int iqref_best_nni(void *hv, const uint8_t *mask, int nni5, double *score, doubl
 // the new kernel does not maintain num_partial_lh_computations)
 int iqref_last_traversal_size(void *hv) { return (int)((Handle *)hv)->tree->traversal_info.size(); }
 
+// PhyloTree::optimizeTreeLengthScaling (tree/phylotree.cpp:2457-2488): returns the log-likelihood, *scaling in/out
+double iqref_optimize_tree_length_scaling(void *hv, double min_scaling, double *scaling, double max_scaling, double gradient_epsilon) {
+    return ((Handle *)hv)->tree->optimizeTreeLengthScaling(min_scaling, *scaling, max_scaling, gradient_epsilon);
+}
+
 // PhyloTree::computePatternLhCat(wsl) (tree/phylotree.cpp:1338-1393) on the pendant branch of alignment row `leaf`: copies
 // _pattern_lh_cat, nptn x getNumLhCat(wsl), and returns getNumLhCat(wsl)
 int iqref_pattern_lh_cat_wsl(void *hv, int leaf, int wsl, double *out) {

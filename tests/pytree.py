@@ -339,6 +339,115 @@ class PyTree:
     def lengths(self):
         return np.array([ab.length for ab, _ in self.branches])
 
+    # ---- tree-length scaling (tree/phylotree.cpp:2455-2528; Brent: utils/optimization.cpp:185-373) ---------------------
+    def scale_length(self, norm):
+        for ab, ba in self.branches:
+            ab.length *= norm
+            ba.length *= norm
+
+    def _scaling_function(self, value):
+        if value != self.current_scaling:
+            self.scale_length(value / self.current_scaling)
+            self.current_scaling = value
+            self.clear_all()
+        return -self.compute_likelihood()
+
+    @staticmethod
+    def brent_opt(func, ax, bx, cx, tol, fax, fbx, fcx):
+        ITMAX, CGOLD, ZEPS = 100, 0.3819660, 1.0e-10
+        sign = lambda a, b: abs(a) if b >= 0.0 else -abs(a)
+        d = e = 0.0
+        a, b = min(ax, cx), max(ax, cx)
+        x, fx = bx, fbx
+        if fax < fcx:
+            w, fw, v, fv = ax, fax, cx, fcx
+        else:
+            w, fw, v, fv = cx, fcx, ax, fax
+        for _ in range(ITMAX):
+            xm = 0.5 * (a + b)
+            tol1 = tol * abs(x) + ZEPS
+            tol2 = 2.0 * tol1
+            if abs(x - xm) <= (tol2 - 0.5 * (b - a)):
+                return x, fx
+            if abs(e) > tol1:
+                r = (x - w) * (fx - fv)
+                q = (x - v) * (fx - fw)
+                p = (x - v) * q - (x - w) * r
+                q = 2.0 * (q - r)
+                if q > 0.0:
+                    p = -p
+                q = abs(q)
+                etemp, e = e, d
+                if abs(p) >= abs(0.5 * q * etemp) or p <= q * (a - x) or p >= q * (b - x):
+                    e = a - x if x >= xm else b - x
+                    d = CGOLD * e
+                else:
+                    d = p / q
+                    u = x + d
+                    if u - a < tol2 or b - u < tol2:
+                        d = sign(tol1, xm - x)
+            else:
+                e = a - x if x >= xm else b - x
+                d = CGOLD * e
+            u = x + d if abs(d) >= tol1 else x + sign(tol1, d)
+            fu = func(u)
+            if fu <= fx:
+                if u >= x:
+                    a = x
+                else:
+                    b = x
+                v, w, x = w, x, u
+                fv, fw, fx = fw, fx, fu
+            else:
+                if u < x:
+                    a = u
+                else:
+                    b = u
+                if fu <= fw or w == x:
+                    v, w, fv, fw = w, u, fw, fu
+                elif fu <= fv or v == x or v == w:
+                    v, fv = u, fu
+        return x, fx
+
+    def minimize_one_dimen(self, func, xmin, xguess, xmax, tolerance):
+        xguess = min(max(xguess, xmin), xmax)
+        eps = xguess * tolerance * 50.0
+        ax = max(xguess - eps, xmin)
+        bx = xguess
+        cx = min(xguess + eps, xmax)
+        fb = func(bx)
+        fa = func(ax) if ax < bx else fb
+        fc = func(cx) if bx < cx else fb
+        if fa < fb or fc < fb:
+            if ax != xmin:
+                fa = func(xmin)
+            if cx != xmax:
+                fc = func(xmax)
+            ax, cx = xmin, xmax
+        optx, fx = self.brent_opt(func, ax, bx, cx, tolerance, fa, fb, fc)
+        if fx > fb:
+            func(bx)
+            return bx
+        return optx
+
+    def optimize_tree_length_scaling(self, min_scaling, scaling, max_scaling, gradient_epsilon):
+        """returns (logL, scaling); every branch length ends up multiplied by scaling / (the scaling passed in)"""
+        self.current_scaling = scaling
+        lens = self.lengths()
+        max_brlen = max(self.min_bl, lens.max())
+        min_brlen = min(self.max_bl, lens.min())
+        if min_brlen <= 0.0:
+            min_brlen = self.min_bl
+        max_scaling = min(max_scaling, 10.0 * self.max_bl / max_brlen)
+        min_scaling = max(min_scaling, 0.1 * self.min_bl / min_brlen)
+        new = self.minimize_one_dimen(self._scaling_function, min(scaling, min_scaling), scaling, max(max_scaling, scaling),
+                                      max(0.001, gradient_epsilon))
+        if new != self.current_scaling:
+            self.scale_length(new / self.current_scaling)
+            self.current_scaling = new
+            self.clear_all()
+        return self.compute_likelihood(), new
+
     # ---- NNI (tree/phylotree.cpp:3975-4322) ---------------------------------------------------------------------
     NNI_MAX_NR_STEP = 10   # utils/pllnni.cpp:42
 

@@ -157,3 +157,30 @@ def test_pipelined_sweep_equals_branch_by_branch(kind):
     ll = b.compute_likelihood()
     b.clear_all_partial_lh()
     assert abs(b.compute_likelihood() - ll) < 1e-7
+
+
+@pytest.mark.parametrize("kind,start", [("dna", 1.0), ("aa", 0.5)])
+def test_tree_length_scaling(kind, start):
+    """PhyloTree::optimizeTreeLengthScaling (tree/phylotree.cpp:2457-2488: Brent's method, every evaluation a full traversal)
+    against the Python restatement over the oracle, which test_reference_parity.py pins against the compiled reference"""
+    from cases import make_case
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=14, nsites=500 if kind == "dna" else 200, seed=13)
+    tree.lengths = tree.lengths * 1.6
+    names, newick = tree.names, tree.to_newick(fmt="%.17g")
+    g = make_gpu_tree(names, pat, freq, model, newick)
+    g.set_pattern_invar(inv)
+    o = make_pytree(names, pat, freq, model, newick, inv=inv)
+    ll0 = g.compute_likelihood()
+    _, _, len0 = g.branches()
+    n0 = g.num_partial_lh_computations
+    ll_g, sc_g = g.optimize_tree_length_scaling(0.01, start, 100.0, 0.001)
+    ll_o, sc_o = o.optimize_tree_length_scaling(0.01, start, 100.0, 0.001)
+    assert abs(sc_g - sc_o) < 1e-6, (sc_g, sc_o)
+    assert abs(ll_g - ll_o) < 1e-6, (ll_g, ll_o)
+    assert ll_g > ll0
+    np.testing.assert_allclose(g.branches()[2], len0 * (sc_g / start), rtol=1e-12)
+    # every Brent evaluation was a full traversal (T-2 partial updates)
+    assert (g.num_partial_lh_computations - n0) % (len(names) - 2) == 0
+    g.scale_length(2.0)
+    np.testing.assert_allclose(g.branches()[2], len0 * (sc_g / start) * 2.0, rtol=1e-12)
+    assert g.compute_likelihood() < ll_g

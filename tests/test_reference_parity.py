@@ -248,3 +248,28 @@ def test_nni_evaluation_matches_reference(kind, nni5):
     assert abs(t.compute_likelihood() - best["score"]) < 1e-6
     t.clear_all()
     assert abs(t.compute_likelihood() - best["score"]) < 1e-6
+
+
+@pytest.mark.parametrize("kind,start,bounds", [("dna", 1.0, (0.01, 100.0)), ("dna", 2.5, (0.01, 100.0)), ("aa", 0.4, (1e-4, 10.0))])
+def test_tree_length_scaling_matches_reference(kind, start, bounds):
+    """PhyloTree::optimizeTreeLengthScaling (tree/phylotree.cpp:2457-2488; Brent's method over clearAllPartialLH + computeLikelihood,
+    the M-step of RateFree::optimizeWithEM and `--tree-len-scale`): same evaluation points, hence the same optimum to the last digits"""
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=12, nsites=400 if kind == "dna" else 150, seed=13)
+    tree.lengths = tree.lengths * 1.7          # a tree that is too long: the optimum is well below 1
+    names = ["T%d" % i for i in range(tree.ntaxa)]
+    tree.names = names
+    newick = tree.to_newick(fmt="%.17g")
+    r = ref_engine.RefTree(None, model, pat, freq, newick=newick, names=names)
+    t = make_pytree(names, pat, freq, model, newick)
+    ll0 = t.compute_likelihood()
+    assert abs(r.compute_likelihood()[0] - ll0) < 1e-8
+    len0 = t.lengths().copy()
+    ll_r, sc_r = r.optimize_tree_length_scaling(bounds[0], start, bounds[1], 0.001)
+    ll_t, sc_t = t.optimize_tree_length_scaling(bounds[0], start, bounds[1], 0.001)
+    assert abs(sc_r - sc_t) < 1e-9, (sc_r, sc_t)
+    assert abs(ll_r - ll_t) < 1e-7, (ll_r, ll_t)
+    assert ll_t >= ll0 - 1e-9
+    np.testing.assert_allclose(t.lengths(), len0 * (sc_t / start), rtol=1e-12)
+    ref_len = r.branches()
+    for split, ln in zip(pytree_splits(t), t.lengths()):
+        assert abs(ref_len[split] - ln) < 1e-9
