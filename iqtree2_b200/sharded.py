@@ -81,6 +81,23 @@ class ShardedLikelihood:
         v = self.engine.logl_from_buffer(length) if self.engine else 0.0
         return self._allreduce([v])[0]
 
+    def em_posterior(self, wsl, add_invar):
+        """E-step of the EM algorithms across ranks: every rank's category sums (engine.em_posterior on its pattern slice, the
+        posteriors stay on that rank's device), one all-reduce of K doubles"""
+        local = None
+        if self.engine:
+            r = self.engine.em_posterior(wsl, add_invar)
+            local = np.asarray(r[0] if isinstance(r, tuple) else r, dtype=np.float64)   # (the oracle returns the matrix as well)
+        if self.world == 1:
+            return local
+        klen = self.torch.tensor([0 if local is None else len(local)], dtype=self.torch.int64, device=self.device)
+        self.dist.all_reduce(klen, op=self.dist.ReduceOp.MAX, group=self.group)
+        t = self.torch.zeros(int(klen.item()), dtype=self.torch.float64, device=self.device)
+        if local is not None:
+            t += self.torch.from_numpy(local).to(self.device)
+        self.dist.all_reduce(t, group=self.group)
+        return t.cpu().numpy()
+
     def gather_pattern_lh(self):
         """computePatternLikelihood across ranks: all-gather of the per-rank _pattern_lh slices (8 B/pattern)."""
         local = self.engine.get_pattern_lh() if self.engine else np.zeros(0)

@@ -51,8 +51,9 @@ def _worker(rank, world, port, out):
     df, ddf = sh.branch_derv(ops[:0], a, b, L)
     ll2 = sh.logl_from_buffer(L)
     plh = sh.gather_pattern_lh()
+    prop = sh.em_posterior(2, True)          # E-step of RateFree::optimizeWithEM over both shards
     if rank == 0:
-        np.save(out, np.concatenate([[ll, df, ddf, ll2], plh]))
+        np.save(out, np.concatenate([[ll, df, ddf, ll2], prop, plh]))
     dist.destroy_process_group()
 
 
@@ -70,4 +71,5 @@ def test_two_rank_gloo_matches_single_engine(tmp_path):
     df, ddf = o.branch_derv(ops[:0], a, b, L)
     assert abs(res[0] - ll) < 1e-8 and abs(res[3] - ll) < 1e-8
     np.testing.assert_allclose(res[1:3], [df, ddf], rtol=1e-10)
-    np.testing.assert_allclose(res[4:], o.get_pattern_lh(), rtol=1e-13)
+    np.testing.assert_allclose(res[4:8], o.em_posterior(2, True)[0], rtol=1e-12)
+    np.testing.assert_allclose(res[8:], o.get_pattern_lh(), rtol=1e-13)
