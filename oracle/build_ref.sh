@@ -91,3 +91,16 @@ g++ -shared -fopenmp -o "$OUT/libiqref.so" "$OBJ"/*.o "$OUT/stub_trap.o" "$OUT/s
 rm -f "$OUT/libiqref_trial.so"
 left=$(ldd -r "$OUT/libiqref.so" 2>&1 | grep -c '^undefined symbol' || true)
 echo "build_ref.sh: $OUT/libiqref.so built ($(wc -l < "$OUT/unresolved.txt") names bound to the trap, $left still undefined)"
+
+# The reference-side binding of INTEGRATION.md, compiled for real: the same objects + ref_b200_shim.cpp (a PhyloTree whose
+# kernel pointers marshal into the product's C ABI), linked against iqtree2_b200/libb200lk.so when that has been built.
+B200LIB="$HERE/../iqtree2_b200/libb200lk.so"
+if [ -f "$B200LIB" ]; then
+  g++ "${CXXFLAGS[@]}" -I"$HERE/../include" -c "$HERE/ref_b200_shim.cpp" -o "$OUT/ref_b200_shim.o"
+  g++ -shared -fopenmp -o "$OUT/libiqref_b200.so" "$OBJ"/*.o "$OUT/ref_b200_shim.o" "$OUT/stub_trap.o" "$OUT/stub_unresolved.o" \
+      -L"$HERE/../iqtree2_b200" -lb200lk -Wl,-rpath,'$ORIGIN/../../iqtree2_b200'
+  left=$(ldd -r "$OUT/libiqref_b200.so" 2>&1 | grep -c '^undefined symbol' || true)
+  echo "build_ref.sh: $OUT/libiqref_b200.so built ($left undefined)"
+else
+  echo "build_ref.sh: iqtree2_b200/libb200lk.so not built yet; skipping libiqref_b200.so"
+fi

@@ -1,0 +1,228 @@
+// ref_b200_shim.cpp — TEST INFRASTRUCTURE: the reference-side binding of INTEGRATION.md, compiled for real.
+//
+// A PhyloTree of the UNMODIFIED reference (IQ-TREE 2.4.0, built by oracle/build_ref.sh from /root/reference) whose five
+// kernel pointers (tree/phylotree.h:900-901, 947-948, 1000-1001, 1342-1346) point at members that marshal into the product's
+// C ABI (include/b200lk.h, iqtree2_b200/libb200lk.so).  Everything above the kernels — computeTraversalInfo, reorientPartialLh,
+// optimizeOneBranch / minimizeNewton, optimizeAllBranches, getBestNNIForBran, optimizeTreeLengthScaling, computePatternLhCat — is
+// the reference's own code; only the arithmetic runs on the GPU.  PhyloNeighbor::partial_lh stays what the reference makes it:
+// a pointer into central_partial_lh / nni_partial_lh; here it is only ever converted into a slot number.
+//
+// The reference's class cannot be given new members without editing its header, so the shim members live in a derived class
+// and are stored in the base's pointers-to-member by static_cast (valid: every object they are called on is a PhyloTreeB200).
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "alignment/alignment.h"
+#include "model/modelfactory.h"
+#include "model/modelsubst.h"
+#include "model/rateheterogeneity.h"
+#include "tree/phylotree.h"
+#include "utils/tools.h"
+
+#include "b200lk.h"
+
+extern PhyloTree *(*iqref_tree_factory)();   // ref_harness.cpp: how iqref_create makes its tree
+
+namespace {
+
+class PhyloTreeB200 : public PhyloTree {
+public:
+    b200lk_engine *b200 = nullptr;
+    std::vector<b200lk_op> b200_ops;
+    std::vector<b200lk_child> b200_extra;
+    long long kernel_calls = 0;
+
+    ~PhyloTreeB200() override { if (b200) b200lk_destroy(b200); }
+
+    void check(int rc, const char *what) {
+        if (rc < 0) outError(std::string(what) + ": " + b200lk_last_error(b200));
+    }
+
+    size_t numCat() { return model_factory->fused_mix_rate ? site_rate->getNRate() : site_rate->getNRate() * model->getNMixtures(); }
+
+    // slot = (partial_lh - central_partial_lh) / block; nni_partial_lh -> the two spare slots T-2, T-1
+    int slotOf(PhyloNeighbor *nei) {
+        const size_t block = getPartialLhSize();
+        double *p = nei->partial_lh;
+        ASSERT(p);
+        if (p >= nni_partial_lh && p < nni_partial_lh + 2 * block) return (int)(leafNum - 2 + (p - nni_partial_lh) / block);
+        return (int)((p - central_partial_lh) / block);
+    }
+    b200lk_child childOf(PhyloNeighbor *nei) {
+        b200lk_child c;
+        c.kind = nei->node->isLeaf() ? 0 : 1;
+        c.id = nei->node->isLeaf() ? nei->node->id : slotOf(nei);
+        c.length = nei->length;
+        return c;
+    }
+
+    void uploadModel() {
+        const int n = aln->num_states, nmix = model->getNMixtures();
+        std::vector<double> w(nmix, 1.0);
+        if (model->isMixture()) for (int m = 0; m < nmix; m++) w[m] = model->getMixtureWeight(m);
+        check(b200lk_set_model(b200, model->getEigenvalues(), model->getEigenvectors(), model->getInverseEigenvectors(), w.data()), "set_model");
+        const int ncat = site_rate->getNRate();
+        std::vector<double> rate(ncat), prop(ncat);
+        for (int c = 0; c < ncat; c++) { rate[c] = site_rate->getRate(c); prop[c] = site_rate->getProp(c); }
+        check(b200lk_set_rates(b200, rate.data(), prop.data()), "set_rates");
+        check(b200lk_set_pattern_invar(b200, ptn_invar), "set_pattern_invar");
+        (void)n;
+    }
+
+    // after initializeAllPartialLh: create the engine, hand over the inputs, take over the kernel pointers
+    void attach() {
+        ASSERT(params->lh_mem_save == LM_PER_NODE && model_factory->unobserved_ptns.empty() && model->useRevKernel());
+        computeTipPartialLikelihood();   // also ptn_freq / ptn_invar (tree/phylotreesse.cpp:243-375, 537-612)
+        b200lk_config cfg{};
+        cfg.nstates = aln->num_states; cfg.ncat = site_rate->getNRate(); cfg.nmix = model->getNMixtures();
+        cfg.fused_mix_rate = model_factory->fused_mix_rate; cfg.safe_numeric = safe_numeric;
+        cfg.seq_type = aln->seq_type == SEQ_DNA ? 1 : aln->seq_type == SEQ_PROTEIN ? 2 : 0;
+        cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = leafNum; cfg.nptn = (int64_t)aln->size();
+        cfg.nslots = (leafNum - 2) + 2; cfg.device = 0;
+        if (b200lk_create(&cfg, &b200) != 0) outError(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
+        const size_t nptn = aln->size();
+        std::vector<uint8_t> states((size_t)leafNum * nptn);
+        for (size_t p = 0; p < nptn; p++)
+            for (int t = 0; t < (int)leafNum; t++) states[(size_t)t * nptn + p] = (uint8_t)aln->at(p)[t];
+        check(b200lk_set_tip_states(b200, states.data()), "set_tip_states");
+        check(b200lk_set_pattern_freq(b200, ptn_freq), "set_pattern_freq");
+        uploadModel();
+        // setLikelihoodKernelB200 of INTEGRATION.md
+        computeLikelihoodBranchPointer = static_cast<ComputeLikelihoodBranchType>(&PhyloTreeB200::computeLikelihoodBranchB200);
+        computeLikelihoodDervPointer = static_cast<ComputeLikelihoodDervType>(&PhyloTreeB200::computeLikelihoodDervB200);
+        computeLikelihoodFromBufferPointer = static_cast<ComputeLikelihoodFromBufferType>(&PhyloTreeB200::computeLikelihoodFromBufferB200);
+        computePartialLikelihoodPointer = static_cast<ComputePartialLikelihoodType>(&PhyloTreeB200::computePartialLikelihoodB200);
+        computeLikelihoodDervMixlenPointer = NULL;
+    }
+
+    // traversal_info (filled by the reference's own computeTraversalInfo, tree/phylotree.cpp:5918-6028) -> b200lk_op[]
+    void marshalTraversalInfo() {
+        b200_ops.clear();
+        b200_extra.clear();
+        for (auto &info : traversal_info) {
+            PhyloNode *node = (PhyloNode *)info.dad_branch->node;
+            b200lk_op op{};
+            op.dst_slot = slotOf(info.dad_branch);
+            int k = 0;
+            FOR_NEIGHBOR_IT(node, info.dad, it) {
+                b200lk_child c = childOf((PhyloNeighbor *)*it);
+                if (k == 0) op.left = c;
+                else if (k == 1) op.right = c;
+                else { b200_extra.push_back(c); op.reserved++; }
+                k++;
+            }
+            b200_ops.push_back(op);
+        }
+        traversal_info.clear();
+        if (!b200_extra.empty()) check(b200lk_set_extra_children(b200, b200_extra.data(), (int)b200_extra.size()), "set_extra_children");
+    }
+
+    // the head of every kernel of tree/phylokernelnew.h: orient the branch, list the stale partials
+    void planBranch(PhyloNeighbor *&dad_branch, PhyloNode *&dad, PhyloNeighbor *&node_branch) {
+        PhyloNode *node = (PhyloNode *)dad_branch->node;
+        node_branch = (PhyloNeighbor *)node->findNeighbor(dad);
+        if (node->isLeaf()) {   // :2654-2661
+            std::swap(dad, node);
+            std::swap(dad_branch, node_branch);
+        }
+        if ((tip_partial_lh_computed & 1) == 0) {   // the model changed (clearAllPartialLH): :1151-1152
+            computeTipPartialLikelihood();
+            uploadModel();
+        }
+        traversal_info.clear();
+        double *buffer = buffer_partial_lh;   // echildren / partial_lh_leaves are carved from it but never touched here
+        computeTraversalInfo(dad_branch, dad, buffer);
+        computeTraversalInfo(node_branch, node, buffer);
+        marshalTraversalInfo();
+        kernel_calls++;
+    }
+
+    double computeLikelihoodBranchB200(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
+        PhyloNeighbor *node_branch;
+        const double length = dad_branch->length;
+        planBranch(dad_branch, dad, node_branch);
+        double logl = 0.0;
+        int rc = b200lk_branch_logl(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
+                                    dad->isLeaf() ? dad->id : slotOf(node_branch), length, save_log_value, &logl);
+        if (rc == B200LK_WARN_UNDERFLOW) outWarning("Numerical underflow for lh-branch");
+        check(rc, "branch_logl");
+        // callers read _pattern_lh / _pattern_lh_cat on the host (computePatternLikelihood, computePatternLhCat): tests are small,
+        // so they are always brought back here; a production shim does it on demand
+        check(b200lk_get_pattern_lh(b200, _pattern_lh), "get_pattern_lh");
+        if (_pattern_lh_cat) {
+            // transformPatternLhCat (tree/phylotree.cpp:1313-1336) expects the kernel's V-interleaved layout
+            const size_t nptn = aln->size(), C = numCat(), V = vector_size;
+            std::vector<double> cat(nptn * C);
+            check(b200lk_get_pattern_lh_cat(b200, cat.data()), "get_pattern_lh_cat");
+            for (size_t p = 0; p < nptn; p++)
+                for (size_t c = 0; c < C; c++) _pattern_lh_cat[(p / V) * C * V + c * V + p % V] = cat[p * C + c];
+        }
+        return logl;
+    }
+
+    void computeLikelihoodDervB200(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf) {
+        PhyloNeighbor *node_branch;
+        const double length = dad_branch->length;
+        planBranch(dad_branch, dad, node_branch);
+        if (!b200_ops.empty()) theta_computed = false;
+        if (!theta_computed) check(b200lk_theta_reset(b200), "theta_reset");   // :2361-2389: the buffer is rebuilt
+        int rc = b200lk_branch_derv(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
+                                    dad->isLeaf() ? dad->id : slotOf(node_branch), length, df, ddf);
+        check(rc, "branch_derv");
+        theta_computed = true;
+    }
+
+    double computeLikelihoodFromBufferB200() {
+        double logl = 0.0;
+        check(b200lk_logl_from_buffer(b200, current_it->length, &logl), "logl_from_buffer");
+        check(b200lk_get_pattern_lh(b200, _pattern_lh), "get_pattern_lh");
+        return logl;
+    }
+
+    // only reached through computeTraversalInfo<VC>(..., compute_partial_lh = true) of callers outside the kernels: one op,
+    // once (the pattern range and the packet are the CPU kernel's work split)
+    void computePartialLikelihoodB200(TraversalInfo &info, size_t, size_t, int packet_id) {
+        if (packet_id > 0) return;
+        PhyloNode *node = (PhyloNode *)info.dad_branch->node;
+        b200lk_op op{};
+        op.dst_slot = slotOf(info.dad_branch);
+        int k = 0;
+        FOR_NEIGHBOR_IT(node, info.dad, it) {
+            if (k == 0) op.left = childOf((PhyloNeighbor *)*it);
+            else if (k == 1) op.right = childOf((PhyloNeighbor *)*it);
+            k++;
+        }
+        ASSERT(k == 2);
+        check(b200lk_update_partials(b200, &op, 1), "update_partials");
+    }
+};
+
+PhyloTree *make_b200_tree() { return new PhyloTreeB200(); }
+
+}  // namespace
+
+extern "C" {
+
+// trees created by iqref_create from now on are PhyloTreeB200 objects (still running the CPU kernel until attached)
+void iqref_b200_enable(int on) { iqref_tree_factory = on ? make_b200_tree : nullptr; }
+
+// switch the tree of this handle to the B200 kernel; returns 0, or -1 if it was not created as a PhyloTreeB200
+int iqref_b200_attach(PhyloTree *tree) {
+    PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
+    if (!t) return -1;
+    if (!t->b200) t->attach();
+    return 0;
+}
+
+long long iqref_b200_kernel_calls(PhyloTree *tree) {
+    PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
+    return t ? t->kernel_calls : -1;
+}
+
+long long iqref_b200_launches(PhyloTree *tree) {
+    PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
+    return t && t->b200 ? b200lk_launch_count(t->b200) : -1;
+}
+
+}

@@ -53,6 +53,28 @@ def lib():
     return _lib
 
 
+LIB_B200 = os.path.join(os.path.dirname(LIB), "libiqref_b200.so")
+_lib_b200 = None
+
+
+def available_b200() -> bool:
+    return os.path.exists(LIB_B200)
+
+
+def lib_b200():
+    """the reference + oracle/ref_b200_shim.cpp linked against iqtree2_b200/libb200lk.so (own copy of the reference's globals)"""
+    global _lib_b200
+    if _lib_b200 is None:
+        if not available_b200():
+            raise FileNotFoundError(LIB_B200 + " (run oracle/build_ref.sh after building iqtree2_b200/libb200lk.so)")
+        _lib_b200 = C.CDLL(LIB_B200)
+        _lib_b200.iqref_create.restype = C.c_void_p
+        for f in ("iqref_optimize_one_branch", "iqref_branch_logl", "iqref_compute_likelihood", "iqref_logl_from_buffer", "iqref_time_eval",
+                  "iqref_optimize_all_branches"):
+            getattr(_lib_b200, f).restype = C.c_double
+    return _lib_b200
+
+
 def set_mem_save(on: bool, max_mem_size: float = 0.0):
     """Params::lh_mem_save / max_mem_size (-mem) for the trees created afterwards."""
     lib().iqref_set_mem_save(int(bool(on)), C.c_double(float(max_mem_size)))
@@ -83,8 +105,11 @@ def _p(a):
 class RefTree:
     """One reference PhyloTree (alignment patterns + tree + harness-supplied eigensystem)."""
 
-    def __init__(self, tree, model, pat, freq, safe_numeric=False, nthreads=1, newick=None, names=None):
-        """tree: treesim.Tree, or None with `newick` + `names` (leaf names replaced by their alignment rows)."""
+    def __init__(self, tree, model, pat, freq, safe_numeric=False, nthreads=1, newick=None, names=None, b200=False):
+        """tree: treesim.Tree, or None with `newick` + `names` (leaf names replaced by their alignment rows).
+        b200=True: the same reference tree with its kernel pointers bound to the product's C ABI (oracle/ref_b200_shim.cpp,
+        libiqref_b200.so; needs a GPU): every member above the kernels is still the reference's own code."""
+        self._b200 = bool(b200)
         f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
         self.model, self.tree = model, tree
         self.ntaxa, self.nptn = int(pat.shape[0]), int(pat.shape[1])
@@ -110,13 +135,31 @@ class RefTree:
         d = _Desc(self.n, model.ncat, model.nmix, int(model.fused_mix_rate), int(self.safe), SEQ_TYPES[model.seq_type],
                   model.state_unknown, self.ntaxa, self.nptn, int(nthreads), 0, _p(k[0]), _p(k[1]), nwk.encode(),
                   _p(k[2]), _p(k[3]), _p(k[4]), _p(k[5]), _p(k[6]), _p(k[7]), _p(k[8]), float(model.pinvar))
-        self._h = C.c_void_p(lib().iqref_create(C.byref(d)))
+        if self._b200:
+            self._L().iqref_b200_enable(1)
+        self._h = C.c_void_p(self._L().iqref_create(C.byref(d)))
         if not self._h:
             raise RuntimeError("iqref_create failed")
+        if self._b200:
+            L = self._L()
+            L.iqref_b200_enable(0)
+            L.iqref_tree_ptr.restype = C.c_void_p
+            self._tree_ptr = C.c_void_p(L.iqref_tree_ptr(self._h))
+            if L.iqref_b200_attach(self._tree_ptr) != 0:
+                raise RuntimeError("iqref_b200_attach failed")
+
+    def _L(self):
+        return lib_b200() if self._b200 else lib()
+
+    def b200_kernel_calls(self):
+        L = self._L()
+        L.iqref_b200_kernel_calls.restype = C.c_longlong
+        L.iqref_b200_launches.restype = C.c_longlong
+        return int(L.iqref_b200_kernel_calls(self._tree_ptr)), int(L.iqref_b200_launches(self._tree_ptr))
 
     def close(self):
         if getattr(self, "_h", None):
-            lib().iqref_destroy(self._h)
+            self._L().iqref_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -127,82 +170,82 @@ class RefTree:
 
     def info(self):
         out = (C.c_int32 * 6)()
-        lib().iqref_info(self._h, out)
+        self._L().iqref_info(self._h, out)
         return dict(vector_size=out[0], safe_numeric=bool(out[1]), num_threads=out[2], num_packets=out[3], kernel=out[4],
                     partial_computations=out[5])
 
     def clear_all_partial_lh(self):
-        lib().iqref_clear_all_partial_lh(self._h)
+        self._L().iqref_clear_all_partial_lh(self._h)
 
     def branch_logl(self, leaf=0, want_cat=False):
         """computeLikelihoodBranch on the pendant branch of alignment row `leaf` -> (logL, pattern_lh[, pattern_lh_cat])."""
         plh = np.empty(self.nptn)
         cat = np.empty((self.nptn, self.Cmix)) if want_cat else None
-        ll = lib().iqref_branch_logl(self._h, int(leaf), _p(plh), _p(cat) if want_cat else None)
+        ll = self._L().iqref_branch_logl(self._h, int(leaf), _p(plh), _p(cat) if want_cat else None)
         return (ll, plh, cat) if want_cat else (ll, plh)
 
     def compute_likelihood(self):
         plh = np.empty(self.nptn)
-        return lib().iqref_compute_likelihood(self._h, _p(plh)), plh
+        return self._L().iqref_compute_likelihood(self._h, _p(plh)), plh
 
     def branch_derv(self, leaf=0):
         df, ddf = C.c_double(), C.c_double()
-        lib().iqref_branch_derv(self._h, int(leaf), C.byref(df), C.byref(ddf))
+        self._L().iqref_branch_derv(self._h, int(leaf), C.byref(df), C.byref(ddf))
         return df.value, ddf.value
 
     def logl_from_buffer(self):
-        return lib().iqref_logl_from_buffer(self._h)
+        return self._L().iqref_logl_from_buffer(self._h)
 
     def theta(self):
         th, bs = np.empty((self.nptn, self.B)), np.empty(self.nptn)
-        lib().iqref_get_theta(self._h, _p(th), _p(bs))
+        self._L().iqref_get_theta(self._h, _p(th), _p(bs))
         return th, bs
 
     def tip_partial_lh(self):
         out = np.empty((self.model.state_unknown + 1, self.model.nmix, self.n))
-        lib().iqref_get_tip_partial_lh(self._h, _p(out))
+        self._L().iqref_get_tip_partial_lh(self._h, _p(out))
         return out
 
     def ptn_invar(self):
         out = np.empty(self.nptn)
-        lib().iqref_get_ptn_invar(self._h, _p(out))
+        self._L().iqref_get_ptn_invar(self._h, _p(out))
         return out
 
     def directed_partials(self, want_partial=True):
         """{frozenset(leaves of the subtree): (partial_lh [nptn][B] or None, scale_num)} for every computed directed CLV."""
         res = {}
         S = self.Cmix if self.safe else 1
-        for k in range(lib().iqref_num_directed(self._h)):
+        for k in range(self._L().iqref_num_directed(self._h)):
             mask = np.zeros(self.ntaxa, dtype=np.uint8)
             part = np.empty((self.nptn, self.B)) if want_partial else None
             sc = np.empty((self.nptn, S), dtype=np.uint16)
-            if lib().iqref_get_directed(self._h, k, _p(mask), _p(part) if want_partial else None, _p(sc)):
+            if self._L().iqref_get_directed(self._h, k, _p(mask), _p(part) if want_partial else None, _p(sc)):
                 res[frozenset(np.nonzero(mask)[0].tolist())] = (part, sc)
         return res
 
     def optimize_all_branches(self, iterations=100, tolerance=0.001, max_nr_step=100):
-        return lib().iqref_optimize_all_branches(self._h, C.c_int(int(iterations)), C.c_double(float(tolerance)), C.c_int(int(max_nr_step)))
+        return self._L().iqref_optimize_all_branches(self._h, C.c_int(int(iterations)), C.c_double(float(tolerance)), C.c_int(int(max_nr_step)))
 
     def optimize_one_branch(self, leaf, max_nr_step=100):
-        return lib().iqref_optimize_one_branch(self._h, C.c_int(int(leaf)), C.c_int(int(max_nr_step)))
+        return self._L().iqref_optimize_one_branch(self._h, C.c_int(int(leaf)), C.c_int(int(max_nr_step)))
 
     def best_traversal(self):
         """the branch order optimizeAllBranches walks, as splits (side not containing taxon 0)"""
         nb = 2 * self.ntaxa - 3
         masks = np.zeros((nb, self.ntaxa), dtype=np.uint8)
-        k = lib().iqref_best_traversal(self._h, _p(masks))
+        k = self._L().iqref_best_traversal(self._h, _p(masks))
         return [frozenset(np.nonzero(masks[b])[0].tolist()) for b in range(k)]
 
     def branches(self):
         """{frozenset(side not containing taxon 0): length}"""
         nb = 2 * self.ntaxa - 3
         masks, lens = np.zeros((nb, self.ntaxa), dtype=np.uint8), np.zeros(nb)
-        k = lib().iqref_get_branches(self._h, _p(masks), _p(lens))
+        k = self._L().iqref_get_branches(self._h, _p(masks), _p(lens))
         return {frozenset(np.nonzero(masks[b])[0].tolist()): float(lens[b]) for b in range(k)}
 
     def pattern_lh_cat_wsl(self, wsl, leaf=0):
         """PhyloTree::computePatternLhCat(wsl) at the pendant branch of `leaf`: [nptn][getNumLhCat(wsl)]"""
-        L = lib()
+        L = self._L()
         K = L.iqref_pattern_lh_cat_wsl(self._h, C.c_int(int(leaf)), C.c_int(int(wsl)), None)
         out = np.zeros((self.nptn, K))
         L.iqref_pattern_lh_cat_wsl(self._h, C.c_int(int(leaf)), C.c_int(int(wsl)), _p(out))
@@ -210,7 +253,7 @@ class RefTree:
 
     def optimize_tree_length_scaling(self, min_scaling, scaling, max_scaling, gradient_epsilon):
         """PhyloTree::optimizeTreeLengthScaling: (logL, scaling)"""
-        L = lib()
+        L = self._L()
         L.iqref_optimize_tree_length_scaling.restype = C.c_double
         sc = C.c_double(float(scaling))
         ll = L.iqref_optimize_tree_length_scaling(self._h, C.c_double(float(min_scaling)), C.byref(sc), C.c_double(float(max_scaling)),
@@ -225,7 +268,7 @@ class RefTree:
         mask[sorted(split)] = 1
         score, new_len = np.zeros(2), np.zeros((2, 5))
         sw, outer = np.zeros((2, 2, nt), dtype=np.uint8), np.zeros((2, 4, nt), dtype=np.uint8)
-        L = lib()
+        L = self._L()
         L.iqref_best_nni.restype = C.c_int
         rc = L.iqref_best_nni(self._h, _p(mask), C.c_int(1 if nni5 else 0), _p(score), _p(new_len), _p(sw), _p(outer))
         if rc != 0:
@@ -236,13 +279,13 @@ class RefTree:
 
     def time_eval(self, leaf=0, reps=3):
         ll, df, ddf, mean = C.c_double(), C.c_double(), C.c_double(), C.c_double()
-        best = lib().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))
+        best = self._L().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))
         return dict(best_sec=best, mean_sec=mean.value, logl=ll.value, df=df.value, ddf=ddf.value)
 
     @property
     def max_lh_slots(self):
-        return int(lib().iqref_max_lh_slots(self._h))
+        return int(self._L().iqref_max_lh_slots(self._h))
 
     def last_traversal_size(self):
         """partial updates the last branch_logl / branch_derv call scheduled (traversal_info.size())"""
-        return int(lib().iqref_last_traversal_size(self._h))
+        return int(self._L().iqref_last_traversal_size(self._h))

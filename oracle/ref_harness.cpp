@@ -189,6 +189,9 @@ const std::string &StartTree::Factory::getNameOfDefaultTreeBuilder() {
     return name;
 }
 
+// how iqref_create makes its tree: nullptr = `new PhyloTree()`; oracle/ref_b200_shim.cpp installs a factory for its derived class
+PhyloTree *(*iqref_tree_factory)() = nullptr;
+
 int NNI_MAX_NR_STEP = 10;   // utils/pllnni.cpp:42 (PLL glue, not compiled); read by getBestNNIForBran
 
 extern "C" {
@@ -275,7 +278,7 @@ void *iqref_create(const iqref_desc *d) {
     g_asc_type = 0;
     g_unobs.clear();
 
-    PhyloTree *tree = h->tree = new PhyloTree();
+    PhyloTree *tree = h->tree = iqref_tree_factory ? iqref_tree_factory() : new PhyloTree();
     tree->params = &params;
     tree->aln = aln;                       // readTreeString -> assignLeafNames needs it only for named leaves
     tree->readTreeString(std::string(d->newick));
@@ -302,6 +305,8 @@ void iqref_destroy(void *hv) {
     delete h->fac; delete h->model; delete h->rate; delete h->aln;
     delete h;
 }
+
+void *iqref_tree_ptr(void *hv) { return ((Handle *)hv)->tree; }
 
 int iqref_info(void *hv, int32_t out[6]) {
     Handle *h = (Handle *)hv;

@@ -1,0 +1,66 @@
+"""GPU: the drop-in, end to end.  The UNMODIFIED reference's PhyloTree (compiled from /root/reference by oracle/build_ref.sh) with
+its five kernel pointers bound to the product's C ABI by oracle/ref_b200_shim.cpp — the binding INTEGRATION.md describes, compiled
+for real — against the same reference running its own AVX/FMA kernel.  Everything above the kernels is the reference's code in
+both arms: computeTraversalInfo, reorientPartialLh, optimizeOneBranch / minimizeNewton, optimizeAllBranches, getBestNNIForBran (on
+nni_partial_lh = the engine's spare slots), optimizeTreeLengthScaling, computePatternLhCat.  Bars: tree logL 1e-6, per-pattern logL
+1e-11 relative, branch lengths 1e-6."""
+import numpy as np
+import pytest
+
+from cases import make_case
+from oracle import ref_engine
+from refmap import branch_splits
+from test_tree_logic_cpu import example_case
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (ref_engine.available() and ref_engine.available_b200()), reason="oracle/_ref libraries not built")]
+
+
+def pair(kind):
+    if kind == "config1":
+        names, pat, freq, model, newick = example_case()
+        mk = lambda b200: ref_engine.RefTree(None, model, pat, freq, newick=newick, names=names, b200=b200)
+        return mk(False), mk(True), None, len(names)
+    tree, model, pat, freq, inv = make_case(kind, ntaxa=14, nsites=600 if kind.startswith("dna") else 250, seed=21, gaps=0.03, ambig=0.01)
+    safe = model.nstates not in (4, 20)
+    mk = lambda b200: ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, b200=b200)
+    return mk(False), mk(True), tree, tree.ntaxa
+
+
+@pytest.mark.parametrize("kind", ["config1", "dna_inv", "aa", "aa_c4", "bin"])
+def test_reference_control_flow_over_the_cuda_kernels(kind):
+    cpu, gpu, tree, nt = pair(kind)
+    ll_c, plh_c = cpu.compute_likelihood()
+    ll_g, plh_g = gpu.compute_likelihood()
+    assert abs(ll_c - ll_g) < 1e-6, (ll_c, ll_g)
+    np.testing.assert_allclose(plh_g, plh_c, rtol=1e-11)
+    calls, launches = gpu.b200_kernel_calls()
+    assert calls >= 1 and launches >= 2          # the GPU arm really ran on the device
+    # per-category likelihoods through the reference's own computePatternLhCat(wsl)
+    for wsl in (2, 4):
+        a, b = cpu.pattern_lh_cat_wsl(wsl), gpu.pattern_lh_cat_wsl(wsl)
+        scale = np.abs(a).max(axis=1, keepdims=True)
+        np.testing.assert_allclose(b / scale, a / scale, rtol=0, atol=1e-11)
+    # the reference's optimizeAllBranches (its minimizeNewton over the engine's derivatives)
+    oc, og = cpu.optimize_all_branches(100, 0.001, 100), gpu.optimize_all_branches(100, 0.001, 100)
+    assert abs(oc - og) < 1e-6, (oc, og)
+    bc, bg = cpu.branches(), gpu.branches()
+    assert set(bc) == set(bg)
+    for k in bc:
+        assert abs(bc[k] - bg[k]) < 1e-6, (sorted(k), bc[k], bg[k])
+    # the reference's getBestNNIForBran on every inner branch: the copies it makes point into nni_partial_lh = the spare slots
+    inner = [s for s in bc if 1 < len(s) < nt - 1]
+    assert len(inner) == nt - 3
+    for s in inner:
+        mc, mg = cpu.best_nni(s), gpu.best_nni(s)
+        for x, y in zip(mc, mg):
+            assert x["swap"] == y["swap"]
+            assert abs(x["score"] - y["score"]) < 1e-6, (sorted(s), x["score"], y["score"])
+            np.testing.assert_allclose(y["new_len"], x["new_len"], rtol=0, atol=1e-6)
+    assert abs(gpu.compute_likelihood()[0] - og) < 1e-6          # the tree is untouched after the evaluations
+    # Brent over full-tree evaluations
+    (lc, sc), (lg, sg) = cpu.optimize_tree_length_scaling(0.01, 1.0, 100.0, 0.001), gpu.optimize_tree_length_scaling(0.01, 1.0, 100.0, 0.001)
+    assert abs(sc - sg) < 1e-6 and abs(lc - lg) < 1e-6
+    calls2, launches2 = gpu.b200_kernel_calls()
+    assert calls2 > calls + 100 and launches2 > launches + 300
+    cpu.close(); gpu.close()
