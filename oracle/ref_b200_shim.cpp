@@ -32,6 +32,7 @@ public:
     std::vector<b200lk_op> b200_ops;
     std::vector<b200lk_child> b200_extra;
     long long kernel_calls = 0;
+    bool fused_newton = false;   // optimizeOneBranch through b200lk_newton_branch (the optional hook of INTEGRATION.md)
 
     ~PhyloTreeB200() override { if (b200) b200lk_destroy(b200); }
 
@@ -180,6 +181,39 @@ public:
         return logl;
     }
 
+    // Optional hook: PhyloTree::optimizeOneBranch (tree/phylotree.cpp:2594-2646) with the minimizeNewton loop replaced by ONE C call
+    // (the whole Newton-Raphson iteration runs on the device on the resident theta buffer); everything else as in the reference.
+    void optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clearLH = true, int maxNRStep = 100) override {
+        if (!b200 || !fused_newton || !optimize_by_newton) { PhyloTree::optimizeOneBranch(node1, node2, clearLH, maxNRStep); return; }
+        if (rooted && (node1 == root || node2 == root)) return;
+        current_it = (PhyloNeighbor *)node1->findNeighbor(node2);
+        current_it_back = (PhyloNeighbor *)node2->findNeighbor(node1);
+        const double current_len = current_it->length;
+        theta_computed = false;
+        check(b200lk_theta_reset(b200), "theta_reset");
+        PhyloNeighbor *dad_branch = current_it, *node_branch;
+        PhyloNode *dad = (PhyloNode *)current_it_back->node;
+        planBranch(dad_branch, dad, node_branch);
+        double optx = current_len;
+        int steps = 0;
+        check(b200lk_newton_branch(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
+                                   dad->isLeaf() ? dad->id : slotOf(node_branch), params->min_branch_length, current_len,
+                                   params->max_branch_length, params->min_branch_length, maxNRStep, &optx, &steps), "newton_branch");
+        theta_computed = true;
+        if (optx > params->max_branch_length * 0.95) {   // Newton-Raphson diverged: keep the better of the two (:2616-2625)
+            current_it->length = current_it_back->length = optx;
+            const double opt_lh = computeLikelihoodFromBuffer();
+            current_it->length = current_it_back->length = current_len;
+            if (computeLikelihoodFromBuffer() > opt_lh) optx = current_len;
+        }
+        current_it->length = optx;
+        current_it_back->length = optx;
+        if (clearLH && current_len != optx) {
+            node1->clearReversePartialLh(node2);
+            node2->clearReversePartialLh(node1);
+        }
+    }
+
     // only reached through computeTraversalInfo<VC>(..., compute_partial_lh = true) of callers outside the kernels: one op,
     // once (the pattern range and the packet are the CPU kernel's work split)
     void computePartialLikelihoodB200(TraversalInfo &info, size_t, size_t, int packet_id) {
@@ -212,6 +246,13 @@ int iqref_b200_attach(PhyloTree *tree) {
     PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
     if (!t) return -1;
     if (!t->b200) t->attach();
+    return 0;
+}
+
+int iqref_b200_set_fused_newton(PhyloTree *tree, int on) {
+    PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
+    if (!t) return -1;
+    t->fused_newton = on != 0;
     return 0;
 }
 

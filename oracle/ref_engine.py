@@ -151,6 +151,12 @@ class RefTree:
     def _L(self):
         return lib_b200() if self._b200 else lib()
 
+    def b200_set_fused_newton(self, on=True):
+        """optimizeOneBranch of the bound tree through b200lk_newton_branch (one C call per branch) instead of the reference's
+        host-side minimizeNewton loop over the derivative kernel pointer"""
+        if self._L().iqref_b200_set_fused_newton(self._tree_ptr, int(bool(on))) != 0:
+            raise RuntimeError("not a B200-bound tree")
+
     def b200_kernel_calls(self):
         L = self._L()
         L.iqref_b200_kernel_calls.restype = C.c_longlong

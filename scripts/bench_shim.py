@@ -39,6 +39,11 @@ g.close()
 g = ref_engine.RefTree(tree, model, pat, freq, nthreads=1, b200=True)
 ll_g, best_g, sweep_g, nni_g = run(g)
 calls, launches = g.b200_kernel_calls()
+g.close()
+f = ref_engine.RefTree(tree, model, pat, freq, nthreads=1, b200=True)
+f.b200_set_fused_newton(True)            # the optional hook: optimizeOneBranch -> b200lk_newton_branch
+ll_f, best_f, sweep_f, nni_f = run(f)
+f.close()
 n = min(a.cpu_patterns, a.patterns)
 c = ref_engine.RefTree(tree, model, np.ascontiguousarray(pat[:, :n]), freq[:n], nthreads=nt)
 ll_c, best_c, sweep_c, nni_c = run(c)
@@ -46,5 +51,6 @@ k = a.patterns / n
 print(json.dumps({"what": "the reference's own optimizeAllBranches (1 sweep) and getBestNNIForBran (all inner branches): AVX/FMA kernel vs kernel pointers bound to libb200lk.so",
                   "taxa": a.taxa, "patterns": a.patterns, "kind": a.kind, "inner_branches": len(inner),
                   "b200_sweep_sec": sweep_g, "b200_nni_sec": nni_g, "b200_kernel_calls": calls, "b200_launches": launches,
+                  "b200_fused_newton_sweep_sec": sweep_f, "b200_fused_newton_nni_sec": nni_f, "logl_b200_fused_newton": ll_f,
                   "cpu_threads": nt, "cpu_sample_patterns": n, "cpu_sweep_sec_scaled": sweep_c * k, "cpu_nni_sec_scaled": nni_c * k,
                   "speedup_sweep": sweep_c * k / sweep_g, "speedup_nni": nni_c * k / nni_g, "logl_b200": ll_g, "logl_cpu_sample": ll_c}))

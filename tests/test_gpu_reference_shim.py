@@ -64,3 +64,23 @@ def test_reference_control_flow_over_the_cuda_kernels(kind):
     calls2, launches2 = gpu.b200_kernel_calls()
     assert calls2 > calls + 100 and launches2 > launches + 300
     cpu.close(); gpu.close()
+
+
+@pytest.mark.parametrize("kind", ["config1", "aa"])
+def test_reference_with_the_fused_newton_hook(kind):
+    """the optional hook: the reference's optimizeOneBranch with its minimizeNewton loop replaced by one b200lk_newton_branch call;
+    its optimizeAllBranches and getBestNNIForBran then give the lengths and scores of the plain binding and of the CPU kernel"""
+    cpu, gpu, tree, nt = pair(kind)
+    gpu.b200_set_fused_newton(True)
+    assert abs(cpu.compute_likelihood()[0] - gpu.compute_likelihood()[0]) < 1e-6
+    calls0, _ = gpu.b200_kernel_calls()
+    oc, og = cpu.optimize_all_branches(100, 0.001, 100), gpu.optimize_all_branches(100, 0.001, 100)
+    assert abs(oc - og) < 1e-6, (oc, og)
+    bc, bg = cpu.branches(), gpu.branches()
+    for k in bc:
+        assert abs(bc[k] - bg[k]) < 1e-6, (sorted(k), bc[k], bg[k])
+    for s in [s for s in bc if 1 < len(s) < nt - 1][::2]:
+        for x, y in zip(cpu.best_nni(s), gpu.best_nni(s)):
+            assert abs(x["score"] - y["score"]) < 1e-6
+            np.testing.assert_allclose(y["new_len"], x["new_len"], rtol=0, atol=1e-6)
+    cpu.close(); gpu.close()
