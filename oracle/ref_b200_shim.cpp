@@ -67,28 +67,44 @@ public:
         std::vector<double> rate(ncat), prop(ncat);
         for (int c = 0; c < ncat; c++) { rate[c] = site_rate->getRate(c); prop[c] = site_rate->getProp(c); }
         check(b200lk_set_rates(b200, rate.data(), prop.data()), "set_rates");
-        check(b200lk_set_pattern_invar(b200, ptn_invar), "set_pattern_invar");
+        // ptn_invar: observed patterns, then the unobserved constant patterns of +ASC, which the reference keeps behind the
+        // padded observed block (tree/phylotreesse.cpp:585-611)
+        const size_t nobs = aln->size(), U = model_factory->unobserved_ptns.size(), max_orig = get_safe_upper_limit(nobs);
+        std::vector<double> inv(nobs + U);
+        for (size_t p = 0; p < nobs; p++) inv[p] = ptn_invar[p];
+        for (size_t u = 0; u < U; u++) inv[nobs + u] = ptn_invar[max_orig + u];
+        check(b200lk_set_pattern_invar(b200, inv.data()), "set_pattern_invar");
         (void)n;
     }
 
     // after initializeAllPartialLh: create the engine, hand over the inputs, take over the kernel pointers
     void attach() {
-        ASSERT(params->lh_mem_save == LM_PER_NODE && model_factory->unobserved_ptns.empty() && model->useRevKernel());
+        ASSERT(params->lh_mem_save == LM_PER_NODE && model->useRevKernel());
         computeTipPartialLikelihood();   // also ptn_freq / ptn_invar (tree/phylotreesse.cpp:243-375, 537-612)
         b200lk_config cfg{};
         cfg.nstates = aln->num_states; cfg.ncat = site_rate->getNRate(); cfg.nmix = model->getNMixtures();
         cfg.fused_mix_rate = model_factory->fused_mix_rate; cfg.safe_numeric = safe_numeric;
         cfg.seq_type = aln->seq_type == SEQ_DNA ? 1 : aln->seq_type == SEQ_PROTEIN ? 2 : 0;
-        cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = leafNum; cfg.nptn = (int64_t)aln->size();
+        const size_t U = model_factory->unobserved_ptns.size();   // +ASC: appended as the engine's last patterns
+        cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = leafNum; cfg.nptn = (int64_t)(aln->size() + U);
         cfg.nslots = (leafNum - 2) + 2; cfg.device = 0;
         if (b200lk_create(&cfg, &b200) != 0) outError(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
-        const size_t nptn = aln->size();
+        const size_t nobs = aln->size(), nptn = nobs + U;
         std::vector<uint8_t> states((size_t)leafNum * nptn);
-        for (size_t p = 0; p < nptn; p++)
-            for (int t = 0; t < (int)leafNum; t++) states[(size_t)t * nptn + p] = (uint8_t)aln->at(p)[t];
+        for (int t = 0; t < (int)leafNum; t++) {
+            for (size_t p = 0; p < nobs; p++) states[(size_t)t * nptn + p] = (uint8_t)aln->at(p)[t];
+            for (size_t u = 0; u < U; u++) states[(size_t)t * nptn + nobs + u] = (uint8_t)model_factory->unobserved_ptns[u][t];
+        }
         check(b200lk_set_tip_states(b200, states.data()), "set_tip_states");
-        check(b200lk_set_pattern_freq(b200, ptn_freq), "set_pattern_freq");
+        std::vector<double> freq(nptn, 0.0);
+        for (size_t p = 0; p < nobs; p++) freq[p] = ptn_freq[p];
+        check(b200lk_set_pattern_freq(b200, freq.data()), "set_pattern_freq");
         uploadModel();
+        if (U) {
+            const ASCType asc = model_factory->getASC();
+            check(b200lk_set_ascertainment(b200, (asc == ASC_VARIANT_MISSING || asc == ASC_INFORMATIVE_MISSING) ? 2 : 1, (int64_t)U,
+                                           (int64_t)aln->getNSite()), "set_ascertainment");
+        }
         // setLikelihoodKernelB200 of INTEGRATION.md
         computeLikelihoodBranchPointer = static_cast<ComputeLikelihoodBranchType>(&PhyloTreeB200::computeLikelihoodBranchB200);
         computeLikelihoodDervPointer = static_cast<ComputeLikelihoodDervType>(&PhyloTreeB200::computeLikelihoodDervB200);
@@ -139,6 +155,12 @@ public:
         kernel_calls++;
     }
 
+    void copyPatternLh() {
+        std::vector<double> plh(aln->size() + model_factory->unobserved_ptns.size());
+        check(b200lk_get_pattern_lh(b200, plh.data()), "get_pattern_lh");
+        memcpy(_pattern_lh, plh.data(), sizeof(double) * aln->size());
+    }
+
     double computeLikelihoodBranchB200(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
         PhyloNeighbor *node_branch;
         const double length = dad_branch->length;
@@ -150,8 +172,8 @@ public:
         check(rc, "branch_logl");
         // callers read _pattern_lh / _pattern_lh_cat on the host (computePatternLikelihood, computePatternLhCat): tests are small,
         // so they are always brought back here; a production shim does it on demand
-        check(b200lk_get_pattern_lh(b200, _pattern_lh), "get_pattern_lh");
-        if (_pattern_lh_cat) {
+        copyPatternLh();
+        if (_pattern_lh_cat && model_factory->unobserved_ptns.empty()) {
             // transformPatternLhCat (tree/phylotree.cpp:1313-1336) expects the kernel's V-interleaved layout
             const size_t nptn = aln->size(), C = numCat(), V = vector_size;
             std::vector<double> cat(nptn * C);
@@ -177,7 +199,7 @@ public:
     double computeLikelihoodFromBufferB200() {
         double logl = 0.0;
         check(b200lk_logl_from_buffer(b200, current_it->length, &logl), "logl_from_buffer");
-        check(b200lk_get_pattern_lh(b200, _pattern_lh), "get_pattern_lh");
+        copyPatternLh();
         return logl;
     }
 

@@ -80,10 +80,11 @@ def set_mem_save(on: bool, max_mem_size: float = 0.0):
     lib().iqref_set_mem_save(int(bool(on)), C.c_double(float(max_mem_size)))
 
 
-def set_asc_next(asc_type: int, unobserved):
-    """+ASC for the next RefTree: ModelFactory::ASC_type (1 = ASC_VARIANT, Lewis) and unobserved_ptns [nunobs][ntaxa]"""
+def set_asc_next(asc_type: int, unobserved, b200=False):
+    """+ASC for the next RefTree (of the B200-bound library with b200=True): ModelFactory::ASC_type (1 = ASC_VARIANT, Lewis;
+    2 = ASC_VARIANT_MISSING, Holder) and unobserved_ptns [nunobs][ntaxa]"""
     u = np.ascontiguousarray(unobserved, dtype=np.uint8)
-    lib().iqref_set_asc_next(C.c_int(asc_type), u.ctypes.data_as(C.c_void_p), C.c_int(u.shape[0]), C.c_int(u.shape[1]))
+    (lib_b200() if b200 else lib()).iqref_set_asc_next(C.c_int(asc_type), u.ctypes.data_as(C.c_void_p), C.c_int(u.shape[0]), C.c_int(u.shape[1]))
 
 
 def set_robust(keep: float = 1.0, median: bool = False):

@@ -84,3 +84,23 @@ def test_reference_with_the_fused_newton_hook(kind):
             assert abs(x["score"] - y["score"]) < 1e-6
             np.testing.assert_allclose(y["new_len"], x["new_len"], rtol=0, atol=1e-6)
     cpu.close(); gpu.close()
+
+
+@pytest.mark.parametrize("asc_type", [1, 2])
+def test_reference_with_asc_over_the_cuda_kernels(asc_type):
+    """+ASC (Lewis) and +ASC_MIS (Holder) through the binding: ModelFactory::unobserved_ptns become the engine's last patterns"""
+    from test_asc_cpu import asc_case, holder_case
+    tree, model, pat, freq, unobs, pat_all, freq_all = (asc_case if asc_type == 1 else holder_case)("bin", ntaxa=14, nsites=500)
+    ref_engine.set_asc_next(asc_type, unobs)
+    cpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=True)
+    ref_engine.set_asc_next(asc_type, unobs, b200=True)
+    gpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=True, b200=True)
+    (ll_c, plh_c), (ll_g, plh_g) = cpu.compute_likelihood(), gpu.compute_likelihood()
+    assert abs(ll_c - ll_g) < 1e-6, (ll_c, ll_g)
+    np.testing.assert_allclose(plh_g, plh_c, rtol=1e-11)
+    oc, og = cpu.optimize_all_branches(100, 0.001, 100), gpu.optimize_all_branches(100, 0.001, 100)
+    assert abs(oc - og) < 1e-6, (oc, og)
+    bc, bg = cpu.branches(), gpu.branches()
+    for k in bc:
+        assert abs(bc[k] - bg[k]) < 1e-6
+    cpu.close(); gpu.close()
