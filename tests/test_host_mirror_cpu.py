@@ -1,0 +1,87 @@
+"""CPU: the product's C++ host mirrors (b200::PhyloTree, PhyloSuperTreePlen, PhyloSuperTree; iqtree2_b200/csrc/*.cpp) linked against
+the CPU oracle instead of the CUDA library (oracle/b200lk_over_oracle.c -> oracle/_build/libb200pt_over_oracle.so, test
+infrastructure), so that their LOGIC — traversal planning, optimizeOneBranch / optimizeAllBranches, getBestNNIForBran on the spare
+slots, doNNI, optimizeTreeLengthScaling, the partition drivers — is covered without a GPU.  The checks are the tree-level GPU tests
+themselves, run with the library loader pointed at that build: same assertions, same bars (reference golden vectors, the Python
+restatement pinned against the compiled reference)."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "oracle", "_build", "libb200pt_over_oracle.so")
+
+
+@pytest.fixture()
+def over_oracle(monkeypatch):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+    lib = ctypes.CDLL(LIB)
+    import iqtree2_b200.phylotree as pt
+    import iqtree2_b200.supertree as st
+    monkeypatch.setattr(pt, "load_library", lambda: lib)
+    monkeypatch.setattr(st, "load_library", lambda: lib)
+    return lib
+
+
+def test_nni_against_reference_golden_on_cpu(over_oracle):
+    import test_gpu_nni as m
+    m.test_nni_against_reference_golden(True)
+    m.test_nni_against_reference_golden(False)
+
+
+@pytest.mark.parametrize("kind,nni5,safe", [("dna", True, False), ("dna", False, False), ("aa", True, False)])
+def test_nni_evaluation_on_cpu(over_oracle, kind, nni5, safe):
+    import test_gpu_nni as m
+    m.test_nni_evaluation_on_resident_clvs(kind, nni5, safe)
+
+
+@pytest.mark.parametrize("nni5", [True, False])
+def test_do_nni_on_cpu(over_oracle, nni5):
+    import test_gpu_nni as m
+    m.test_do_nni_applies_the_evaluated_move(nni5)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_config1_branch_length_optimisation_on_cpu(over_oracle, fused):
+    import test_gpu_phylotree as m
+    m.test_config1_fixed_tree_logl_and_pattern_lh()
+    m.test_config1_branch_length_optimisation(fused)
+
+
+def test_invalidation_and_scaling_on_cpu(over_oracle):
+    import test_gpu_phylotree as m
+    m.test_incremental_invalidation_matches_full_recompute()
+    m.test_model_change_invalidates_everything()
+    m.test_tree_length_scaling("dna", 1.0)
+
+
+def test_partition_drivers_on_cpu(over_oracle):
+    import test_gpu_supertree_unlinked as u
+    u.test_unlinked_partitions(2)
+
+
+@pytest.mark.parametrize("safe", [False, True])
+def test_edge_linked_supertree_on_cpu(over_oracle, safe):
+    import test_gpu_supertree as m
+    m.test_supertree_logl_scores_and_derivatives(safe)
+
+
+def test_edge_linked_supertree_optimisation_on_cpu(over_oracle):
+    import test_gpu_supertree as m
+    # (not test_supertree_thread_count_does_not_change_results: bit-identical sums for any number of queueing threads are a
+    # property of the CUDA engine's ordered reduction; the oracle's OpenMP reductions change with the threads it is given)
+    m.test_supertree_branch_length_optimisation()
+    m.test_supertree_incremental_after_one_branch()
+
+
+@pytest.mark.parametrize("asc_type", [1, 2])
+def test_polytomies_asc_and_robust_phylo_through_the_tree_api_on_cpu(over_oracle, asc_type):
+    import test_gpu_phylotree_multifurc_asc as m
+    import test_gpu_robust as r
+    from oracle import ref_engine
+    if ref_engine.available():
+        m.test_host_mirror_with_asc(asc_type)
+        m.test_host_mirror_on_polytomous_tree("dna" if asc_type == 1 else "aa")
+    r.test_robust_phylo_through_the_tree_api()
