@@ -116,6 +116,13 @@ int b200st_compute_likelihood_branch(b200st_tree *t, int32_t branch, double *log
 int b200st_compute_likelihood_derv(b200st_tree *t, int32_t branch, double length, double *df, double *ddf);
 int b200st_optimize_one_branch(b200st_tree *t, int32_t branch, int32_t clear_lh, int32_t max_nr_step);
 int b200st_optimize_all_branches(b200st_tree *t, int32_t iterations, double tolerance, int32_t max_nr_step, double *logl);
+/* NNI evaluation for the linked model (the role of PhyloSuperTreePlen::getBestNNIForBran, tree/phylosupertreeplen.cpp:1100-1500):
+ * arguments and outputs as b200pt_get_best_nni_for_bran; the move is the same swap in the super tree and in every partition tree,
+ * each partition on its own engine's spare slots, the five branches re-optimised with the linked derivatives.  b200st_do_nni
+ * applies move 0 / 1 to the super tree and every partition tree (new_len: super-tree lengths; partitions get them times their rate). */
+int b200st_get_best_nni_for_bran(b200st_tree *t, int32_t branch, int32_t reverse, int32_t nni5, double *score, double *new_len,
+                                 int32_t *swap_nodes, int32_t *outer_nodes);
+int b200st_do_nni(b200st_tree *t, int32_t branch, int32_t reverse, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh);
 /* part_info[p].cur_score of the last evaluation */
 int b200st_get_part_scores(b200st_tree *t, double *scores);
 int64_t b200st_launch_count(b200st_tree *t);

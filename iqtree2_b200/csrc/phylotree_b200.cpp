@@ -659,9 +659,13 @@ void PhyloTree::finish(double *logl, double *df, double *ddf) { check(b200lk_fin
 
 PhyloNeighbor *PhyloTree::branchNeighbor(int branch_id, int to_node_id) const {
     if (branch_id < 0 || branch_id >= (int)branches_.size()) return nullptr;
-    const auto &br = branches_[branch_id];
-    if (br.first->node->id == to_node_id) return br.first;
-    if (br.second->node->id == to_node_id) return br.second;
+    // through the node lists, not through branches_: during an NNI evaluation copies stand in for the branch's neighbours and
+    // its ends may have changed (the id travels with the neighbour objects)
+    PhyloNode *to = nodeById(to_node_id);
+    for (auto *nb : to->neighbors) {
+        PhyloNeighbor *back = nb->node->findNeighbor(to);
+        if (back && back->id == branch_id) return back;
+    }
     return nullptr;
 }
 
@@ -1106,77 +1110,105 @@ static int neighborPos(const PhyloNode *node, const PhyloNode *to) {
     throw std::runtime_error("nodes are not adjacent");
 }
 
-NNIMove PhyloTree::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves) {
+PhyloNode *PhyloTree::nodeById(int id) const {
+    if (node_by_id_.size() != nodes_.size()) {
+        node_by_id_.assign(nodes_.size(), nullptr);
+        for (auto *n : nodes_) if (n->id >= 0 && n->id < (int)nodes_.size()) node_by_id_[n->id] = n;
+    }
+    if (id < 0 || id >= (int)node_by_id_.size() || !node_by_id_[id]) throw std::runtime_error("no node with that id");
+    return node_by_id_[id];
+}
+
+void PhyloTree::nniBegin(PhyloNode *node1, PhyloNode *node2, bool nni5, NNIContext &ctx) {
     initializeAllPartialLh();
-    if (params.plan_only || !engine_) throw std::runtime_error("getBestNNIForBran needs an engine");
     if (params.lh_mem_save == LM_MEM_SAVE) throw std::runtime_error("getBestNNIForBran: not available with -mem");
     if (node1->isLeaf() || node2->isLeaf() || node1->neighbors.size() != 3 || node2->neighbors.size() != 3)
         throw std::runtime_error("getBestNNIForBran: needs an inner branch between two degree-3 nodes");
-    const int IT_NUM = params.nni5 ? 6 : 2;
-    struct Saved { PhyloNode *owner; int pos; PhyloNeighbor *nei; } saved[6];
+    ctx.node1 = node1; ctx.node2 = node2;
+    ctx.IT_NUM = nni5 ? 6 : 2;
     int id = 0;
-    saved[id++] = {node1, neighborPos(node1, node2), nullptr};
-    saved[id++] = {node2, neighborPos(node2, node1), nullptr};
-    if (params.nni5) {
-        for (auto *it : node1->neighbors) if (it->node != node2) saved[id++] = {it->node, neighborPos(it->node, node1), nullptr};
-        for (auto *it : node2->neighbors) if (it->node != node1) saved[id++] = {it->node, neighborPos(it->node, node2), nullptr};
+    ctx.saved[id++] = {node1, neighborPos(node1, node2), nullptr};
+    ctx.saved[id++] = {node2, neighborPos(node2, node1), nullptr};
+    if (nni5) {
+        for (auto *it : node1->neighbors) if (it->node != node2) ctx.saved[id++] = {it->node, neighborPos(it->node, node1), nullptr};
+        for (auto *it : node2->neighbors) if (it->node != node1) ctx.saved[id++] = {it->node, neighborPos(it->node, node2), nullptr};
     } else {
         reorientPartialLh(node1->findNeighbor(node2), node1);
         reorientPartialLh(node2->findNeighbor(node1), node2);
     }
     // save the neighbours and put copies in their place; a copy of a neighbour that holds a CLV gets a spare slot (:4127-4143)
     int mem_id = 0;
-    PhyloNeighbor copies[6];
-    for (id = 0; id < IT_NUM; id++) {
-        Saved &sv = saved[id];
+    for (id = 0; id < ctx.IT_NUM; id++) {
+        auto &sv = ctx.saved[id];
         sv.nei = sv.owner->neighbors[sv.pos];
-        copies[id] = *sv.nei;
-        copies[id].partial_lh_computed = false;
-        copies[id].slot = -1;
-        if (sv.nei->slot >= 0) copies[id].slot = max_lh_slots + mem_id++;
-        sv.owner->neighbors[sv.pos] = &copies[id];
+        ctx.copies[id] = *sv.nei;
+        ctx.copies[id].partial_lh_computed = false;
+        ctx.copies[id].slot = -1;
+        if (sv.nei->slot >= 0) ctx.copies[id].slot = max_lh_slots + mem_id++;
+        sv.owner->neighbors[sv.pos] = &ctx.copies[id];
     }
-    if (mem_id != 2) throw std::runtime_error("getBestNNIForBran: expected two CLVs around the branch");
-    PhyloNeighbor *node12_it = node1->findNeighbor(node2), *node21_it = node2->findNeighbor(node1);
+    if (mem_id != 2) {
+        for (id = ctx.IT_NUM - 1; id >= 0; id--) ctx.saved[id].owner->neighbors[ctx.saved[id].pos] = ctx.saved[id].nei;
+        ctx.IT_NUM = 0;
+        throw std::runtime_error("getBestNNIForBran: expected two CLVs around the branch");
+    }
+    ctx.node12_it = node1->findNeighbor(node2);
+    ctx.node21_it = node2->findNeighbor(node1);
+    ctx.swapped_k1 = ctx.swapped_k2 = -1;
+}
 
+void PhyloTree::nniSwap(NNIContext &ctx, int k1, int k2) {
+    reorientPartialLh(ctx.node12_it, ctx.node1);   // reorient partial_lh before the swap (:4200-4202, 4271-4273)
+    reorientPartialLh(ctx.node21_it, ctx.node2);
+    swapNeighbors(ctx.node1, k1, ctx.node2, k2);   // the same call swaps back: the positions hold each other's neighbour
+    if (ctx.swapped_k1 < 0) { ctx.swapped_k1 = k1; ctx.swapped_k2 = k2; }
+    else ctx.swapped_k1 = ctx.swapped_k2 = -1;
+}
+
+void PhyloTree::nniEnd(NNIContext &ctx) {
+    if (ctx.IT_NUM == 0) return;
+    if (ctx.swapped_k1 >= 0) { swapNeighbors(ctx.node1, ctx.swapped_k1, ctx.node2, ctx.swapped_k2); ctx.swapped_k1 = ctx.swapped_k2 = -1; }
+    for (int id = ctx.IT_NUM - 1; id >= 0; id--) {   // restore the neighbours (:4284-4299)
+        auto &sv = ctx.saved[id];
+        if (sv.owner->neighbors[sv.pos] == current_it) current_it = sv.nei;
+        if (sv.owner->neighbors[sv.pos] == current_it_back) current_it_back = sv.nei;
+        sv.owner->neighbors[sv.pos] = sv.nei;
+    }
+    // the four outer branches: the outward neighbours were re-optimised, their saved partners still hold the old lengths
+    for (auto *it : ctx.node1->neighbors) if (it->node != ctx.node2) it->length = it->node->findNeighbor(ctx.node1)->length;
+    for (auto *it : ctx.node2->neighbors) if (it->node != ctx.node1) it->length = it->node->findNeighbor(ctx.node2)->length;
+    ctx.IT_NUM = 0;
+}
+
+// the first other neighbour of node1 against each other neighbour of node2 (:4168-4183)
+void PhyloTree::defaultNNIMoves(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves) {
+    int cnt = 0;
+    for (int k1 = 0; k1 < 3 && cnt == 0; k1++)
+        if (node1->neighbors[k1]->node != node2)
+            for (int k2 = 0; k2 < 3; k2++)
+                if (node2->neighbors[k2]->node != node1) {
+                    nniMoves[cnt].node1Nei_it = k1;
+                    nniMoves[cnt].node2Nei_it = k2;
+                    cnt++;
+                }
+}
+
+NNIMove PhyloTree::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves) {
+    initializeAllPartialLh();
+    if (params.plan_only || !engine_) throw std::runtime_error("getBestNNIForBran needs an engine");
+    NNIContext ctx;
+    nniBegin(node1, node2, params.nni5, ctx);
+    PhyloNeighbor *node12_it = ctx.node12_it, *node21_it = ctx.node21_it;
     NNIMove local[2];
     if (!nniMoves) nniMoves = local;
-    if (!nniMoves[0].node1) {   // the first other neighbour of node1 against each other neighbour of node2 (:4168-4183)
-        int cnt = 0;
-        for (int k1 = 0; k1 < 3 && cnt == 0; k1++)
-            if (node1->neighbors[k1]->node != node2)
-                for (int k2 = 0; k2 < 3; k2++)
-                    if (node2->neighbors[k2]->node != node1) {
-                        nniMoves[cnt].node1Nei_it = k1;
-                        nniMoves[cnt].node2Nei_it = k2;
-                        cnt++;
-                    }
-    }
+    if (!nniMoves[0].node1) defaultNNIMoves(node1, node2, nniMoves);
     nniMoves[0].node1 = nniMoves[1].node1 = node1;
     nniMoves[0].node2 = nniMoves[1].node2 = node2;
     nniMoves[0].newloglh = nniMoves[1].newloglh = -DBL_MAX;
     const double backupScore = curScore;
-
-    int swapped = -1;   // the move whose swap is in place
-    auto restore = [&]() {
-        if (swapped >= 0) swapNeighbors(node1, nniMoves[swapped].node1Nei_it, node2, nniMoves[swapped].node2Nei_it);
-        for (id = IT_NUM - 1; id >= 0; id--) {   // restore the neighbours (:4284-4299)
-            Saved &sv = saved[id];
-            if (sv.owner->neighbors[sv.pos] == current_it) current_it = sv.nei;
-            if (sv.owner->neighbors[sv.pos] == current_it_back) current_it_back = sv.nei;
-            sv.owner->neighbors[sv.pos] = sv.nei;
-        }
-        // the four outer branches: the outward neighbours were re-optimised, their saved partners still hold the old lengths
-        for (auto *it : node1->neighbors) if (it->node != node2) it->length = it->node->findNeighbor(node1)->length;
-        for (auto *it : node2->neighbors) if (it->node != node1) it->length = it->node->findNeighbor(node2)->length;
-    };
     try {
         for (int cnt = 0; cnt < 2; cnt++) {
-            const int k1 = nniMoves[cnt].node1Nei_it, k2 = nniMoves[cnt].node2Nei_it;
-            reorientPartialLh(node12_it, node1);
-            reorientPartialLh(node21_it, node2);
-            swapNeighbors(node1, k1, node2, k2);
-            swapped = cnt;
+            nniSwap(ctx, nniMoves[cnt].node1Nei_it, nniMoves[cnt].node2Nei_it);
             for (int step = 0; step < params.nni5_num_eval; step++) {
                 node12_it->partial_lh_computed = false;
                 node21_it->partial_lh_computed = false;
@@ -1207,16 +1239,13 @@ NNIMove PhyloTree::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove
             double score = computeLikelihoodFromBuffer();
             nniMoves[cnt].newloglh = score;
             if (nniMoves[cnt].ptnlh) computePatternLikelihood(nniMoves[cnt].ptnlh, &score);
-            reorientPartialLh(node12_it, node1);
-            reorientPartialLh(node21_it, node2);
-            swapNeighbors(node1, k1, node2, k2);   // swap back: the positions hold each other's neighbour
-            swapped = -1;
+            nniSwap(ctx, nniMoves[cnt].node1Nei_it, nniMoves[cnt].node2Nei_it);   // swap back
         }
     } catch (...) {   // leave the tree as it was (the CLV flags of the six neighbours are the saved ones)
-        restore();
+        nniEnd(ctx);
         throw;
     }
-    restore();
+    nniEnd(ctx);
     curScore = backupScore;
     // the theta buffer belongs to a branch of the last alternative topology: never reuse it for the restored tree (the reference
     // leaves theta_computed set; every caller of it goes through optimizeOneBranch, which clears the flag, first)

@@ -159,7 +159,23 @@ public:
     // ---- NNI evaluation on the resident CLVs (tree/phylotree.cpp:3975-4322) ------------------------------------------
     // Evaluates the two NNIs around the inner branch (node1, node2) on the engine's two spare slots (nni_partial_lh): the
     // CLVs, flags and lengths of the current tree are untouched on return.  nniMoves: optional array of two, filled.
-    NNIMove getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves = nullptr);
+    virtual NNIMove getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves = nullptr);
+    // the pieces of it, for drivers that evaluate the same move in several trees at once (PhyloSuperTreePlen): nniBegin replaces the
+    // six (nni5) or two neighbours by copies on the spare slots, nniSwap does / undoes the swap of the neighbours at positions k1 of
+    // node1 and k2 of node2 (re-orienting the two central CLVs first), nniEnd undoes a pending swap and puts the saved neighbours back
+    struct NNIContext {
+        PhyloNode *node1 = nullptr, *node2 = nullptr;
+        int IT_NUM = 0;
+        struct Saved { PhyloNode *owner; int pos; PhyloNeighbor *nei; } saved[6];
+        PhyloNeighbor copies[6];
+        PhyloNeighbor *node12_it = nullptr, *node21_it = nullptr;
+        int swapped_k1 = -1, swapped_k2 = -1;
+    };
+    void nniBegin(PhyloNode *node1, PhyloNode *node2, bool nni5, NNIContext &ctx);
+    void nniSwap(NNIContext &ctx, int k1, int k2);
+    void nniEnd(NNIContext &ctx);
+    PhyloNode *nodeById(int id) const;
+    static void defaultNNIMoves(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves);   // :4168-4183
     void doNNI(const NNIMove &move, bool clearLH = true);   // :3947-4036
     void changeNNIBrans(const NNIMove &move);               // :4038-4067
 
@@ -226,6 +242,7 @@ protected:
     bool sweepPipelined(const std::vector<PhyloNode *> &nodes, const std::vector<PhyloNode *> &nodes2, int maxNRStep);
     std::vector<char> dev_len_valid_;   // by branch id: the current length lives in the engine's device length table
     std::vector<double> pattern_lh_;
+    mutable std::vector<PhyloNode *> node_by_id_;
 };
 
 }  // namespace b200

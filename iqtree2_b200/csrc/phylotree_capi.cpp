@@ -336,6 +336,47 @@ int b200st_optimize_all_branches(b200st_tree *t, int32_t iterations, double tole
 int b200st_get_part_scores(b200st_tree *t, double *scores) {
     GUARD(for (int p = 0; p < t->tree.numPartitions(); p++) scores[p] = t->tree.cur_score[p])
 }
+static void superNniMoves(b200st_tree *t, int branch, int reverse, b200::NNIMove mv[2]) {
+    std::vector<b200::PhyloNode *> na, nb;
+    t->tree.getBranches(na, nb);
+    if (branch < 0 || branch >= (int)na.size()) throw std::runtime_error("branch id out of range");
+    b200::PhyloNode *a = na[branch], *b = nb[branch];
+    if (reverse) std::swap(a, b);
+    if (a->isLeaf() || b->isLeaf() || a->neighbors.size() != 3 || b->neighbors.size() != 3)
+        throw std::runtime_error("NNI needs an inner branch between two degree-3 nodes");
+    b200::PhyloTree::defaultNNIMoves(a, b, mv);
+    mv[0].node1 = mv[1].node1 = a;
+    mv[0].node2 = mv[1].node2 = b;
+}
+int b200st_get_best_nni_for_bran(b200st_tree *t, int32_t branch, int32_t reverse, int32_t nni5, double *score, double *new_len,
+                                 int32_t *swap_nodes, int32_t *outer_nodes) {
+    GUARD({
+        b200::NNIMove mv[2];
+        superNniMoves(t, branch, reverse, mv);
+        t->tree.params.nni5 = nni5 != 0;
+        b200::PhyloNode *node1 = mv[0].node1, *node2 = mv[0].node2;
+        t->tree.getBestNNIForBran(node1, node2, mv);
+        for (int m = 0; m < 2; m++) {
+            score[m] = mv[m].newloglh;
+            for (int i = 0; i < 5; i++) new_len[m * 5 + i] = (i == 0 || nni5) ? mv[m].newLen[i] : 0.0;
+            b200::PhyloNode *sa = node1->neighbors[mv[m].node1Nei_it]->node, *sc = node2->neighbors[mv[m].node2Nei_it]->node;
+            swap_nodes[m * 2] = sa->id; swap_nodes[m * 2 + 1] = sc->id;
+            int k = 0;
+            for (auto *it : node1->neighbors) if (it->node != node2) outer_nodes[m * 4 + k++] = (it->node == sa ? sc : it->node)->id;
+            for (auto *it : node2->neighbors) if (it->node != node1) outer_nodes[m * 4 + k++] = (it->node == sc ? sa : it->node)->id;
+        }
+    })
+}
+int b200st_do_nni(b200st_tree *t, int32_t branch, int32_t reverse, int32_t move, int32_t nni5, const double *new_len, int32_t clear_lh) {
+    GUARD({
+        if (move < 0 || move > 1) throw std::runtime_error("move must be 0 or 1");
+        b200::NNIMove mv[2];
+        superNniMoves(t, branch, reverse, mv);
+        t->tree.params.nni5 = nni5 != 0;
+        if (new_len) for (int i = 0; i < 5; i++) mv[move].newLen[i] = (i == 0 || nni5) ? new_len[i] : 0.0;
+        t->tree.doNNIAll(mv[move], clear_lh != 0, new_len != nullptr);
+    })
+}
 int64_t b200st_launch_count(b200st_tree *t) { return t->tree.launches(); }
 int64_t b200st_device_bytes(b200st_tree *t) {
     int64_t n = 0;

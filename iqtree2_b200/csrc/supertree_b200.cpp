@@ -10,6 +10,7 @@
 
 #include <cstdlib>
 #ifdef _OPENMP
+#include <cfloat>
 #include <omp.h>
 #endif
 
@@ -225,6 +226,116 @@ int64_t PhyloSuperTreePlen::launches() const {
     int64_t n = 0;
     for (auto *p : parts) if (p->engine()) n += b200lk_launch_count(p->engine());
     return n;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// NNI for the linked model
+// ---------------------------------------------------------------------------------------------------------------
+static int posOfNodeId(const PhyloNode *node, int id) {
+    for (size_t k = 0; k < node->neighbors.size(); k++)
+        if (node->neighbors[k]->node->id == id) return (int)k;
+    throw std::runtime_error("partition tree and super tree differ in topology");
+}
+
+NNIMove PhyloSuperTreePlen::getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves) {
+    initializeAllPartialLh();
+    const size_t np = parts.size();
+    NNIContext ctx;
+    std::vector<NNIContext> pctx(np);
+    std::vector<PhyloNode *> p1(np), p2(np);
+    NNIMove local[2];
+    if (!nniMoves) nniMoves = local;
+    if (!nniMoves[0].node1) defaultNNIMoves(node1, node2, nniMoves);
+    nniMoves[0].node1 = nniMoves[1].node1 = node1;
+    nniMoves[0].node2 = nniMoves[1].node2 = node2;
+    nniMoves[0].newloglh = nniMoves[1].newloglh = -DBL_MAX;
+    const double backupScore = curScore;
+    const std::vector<double> backup_part_score = cur_score;
+    // flag of the CLV that `from` holds of the subtree behind `to`, in the super tree and in every partition tree
+    auto clearFlag = [&](PhyloNode *from, PhyloNode *to) {
+        from->findNeighbor(to)->partial_lh_computed = false;
+        for (size_t p = 0; p < np; p++) parts[p]->nodeById(from->id)->findNeighbor(parts[p]->nodeById(to->id))->partial_lh_computed = false;
+    };
+    auto endAll = [&]() {
+        nniEnd(ctx);
+        for (size_t p = 0; p < np; p++) parts[p]->nniEnd(pctx[p]);
+    };
+    try {
+        nniBegin(node1, node2, params.nni5, ctx);
+        for (size_t p = 0; p < np; p++) {
+            p1[p] = parts[p]->nodeById(node1->id);
+            p2[p] = parts[p]->nodeById(node2->id);
+            parts[p]->nniBegin(p1[p], p2[p], params.nni5, pctx[p]);
+        }
+        for (int cnt = 0; cnt < 2; cnt++) {
+            const int k1 = nniMoves[cnt].node1Nei_it, k2 = nniMoves[cnt].node2Nei_it;
+            const int a_id = node1->neighbors[k1]->node->id, c_id = node2->neighbors[k2]->node->id;
+            std::vector<int> pk1(np), pk2(np);
+            for (size_t p = 0; p < np; p++) { pk1[p] = posOfNodeId(p1[p], a_id); pk2[p] = posOfNodeId(p2[p], c_id); }
+            nniSwap(ctx, k1, k2);
+            for (size_t p = 0; p < np; p++) parts[p]->nniSwap(pctx[p], pk1[p], pk2[p]);
+            for (int step = 0; step < params.nni5_num_eval; step++) {
+                clearFlag(node1, node2);
+                clearFlag(node2, node1);
+                int i = 1;
+                if (params.nni5) {
+                    for (int k = 0; k < 3; k++) {
+                        PhyloNode *other = node1->neighbors[k]->node;
+                        if (other == node2) continue;
+                        clearFlag(other, node1);
+                        optimizeOneBranch(node1, other, false, NNI_MAX_NR_STEP);
+                        nniMoves[cnt].newLen[i++] = node1->findNeighbor(other)->length;
+                    }
+                    clearFlag(node2, node1);
+                }
+                optimizeOneBranch(node1, node2, false, NNI_MAX_NR_STEP);
+                nniMoves[cnt].newLen[0] = node1->findNeighbor(node2)->length;
+                if (params.nni5) {
+                    for (int k = 0; k < 3; k++) {
+                        PhyloNode *other = node2->neighbors[k]->node;
+                        if (other == node1) continue;
+                        clearFlag(other, node2);
+                        optimizeOneBranch(node2, other, false, NNI_MAX_NR_STEP);
+                        nniMoves[cnt].newLen[i++] = node2->findNeighbor(other)->length;
+                    }
+                    clearFlag(node1, node2);
+                }
+            }
+            nniMoves[cnt].newloglh = computeLikelihoodFromBuffer();
+            nniSwap(ctx, k1, k2);
+            for (size_t p = 0; p < np; p++) parts[p]->nniSwap(pctx[p], pk1[p], pk2[p]);
+        }
+    } catch (...) {
+        endAll();
+        throw;
+    }
+    endAll();
+    curScore = backupScore;
+    cur_score = backup_part_score;
+    for (auto *p : parts) {   // the partitions' theta buffers belong to the last alternative topology
+        p->theta_computed = false;
+        if (p->engine()) b200lk_theta_reset(p->engine());
+    }
+    return nniMoves[0].newloglh > nniMoves[1].newloglh ? nniMoves[0] : nniMoves[1];
+}
+
+void PhyloSuperTreePlen::doNNIAll(const NNIMove &move, bool clearLH, bool set_lengths) {
+    const int a_id = move.node1->neighbors[move.node1Nei_it]->node->id, c_id = move.node2->neighbors[move.node2Nei_it]->node->id;
+    for (size_t p = 0; p < parts.size(); p++) {
+        NNIMove pm = move;
+        pm.node1 = parts[p]->nodeById(move.node1->id);
+        pm.node2 = parts[p]->nodeById(move.node2->id);
+        pm.node1Nei_it = posOfNodeId(pm.node1, a_id);
+        pm.node2Nei_it = posOfNodeId(pm.node2, c_id);
+        parts[p]->doNNI(pm, clearLH);
+        if (set_lengths) {
+            for (int i = 0; i < 5; i++) pm.newLen[i] = move.newLen[i] * part_rate[p];
+            parts[p]->params.nni5 = params.nni5;
+            parts[p]->changeNNIBrans(pm);
+        }
+    }
+    doNNI(move, clearLH);
+    if (set_lengths) changeNNIBrans(move);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

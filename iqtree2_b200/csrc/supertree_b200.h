@@ -46,6 +46,12 @@ public:
     double optimizeAllBranches(int my_iterations = 100, double tolerance = TOL_LIKELIHOOD, int maxNRStep = 100) override;   // plen.cpp:243-251
     void clearAllPartialLH() override;
     void restoreBranchLengths(const std::vector<double> &lenvec) override;
+    // NNI evaluation for the linked model (the role of PhyloSuperTreePlen::getBestNNIForBran, phylosupertreeplen.cpp:1100-1500;
+    // here every partition tree has the full topology, so the move is the same swap in the super tree and in every partition
+    // tree, each on its own engine's spare slots; the five branches are re-optimised with the linked derivatives)
+    NNIMove getBestNNIForBran(PhyloNode *node1, PhyloNode *node2, NNIMove *nniMoves = nullptr) override;
+    // doNNI (+ changeNNIBrans when set_lengths) in the super tree and in every partition tree
+    void doNNIAll(const NNIMove &move, bool clearLH, bool set_lengths);
 
     int numPartitions() const { return (int)parts.size(); }
     std::vector<PhyloTree *> parts;

@@ -110,6 +110,24 @@ class PhyloSuperTree:
         self._check(self.lib.b200st_optimize_all_branches(self._h, iterations, C.c_double(tolerance), max_nr_step, C.byref(out)))
         return out.value
 
+    def get_best_nni_for_bran(self, branch, nni5=True, reverse=False):
+        """NNI evaluation for the linked model: two dicts as PhyloTree.get_best_nni_for_bran (score, new_len, swap, outer)"""
+        score, new_len = np.zeros(2), np.zeros((2, 5))
+        sw, outer = np.zeros((2, 2), dtype=np.int32), np.zeros((2, 4), dtype=np.int32)
+        self._check(self.lib.b200st_get_best_nni_for_bran(self._h, C.c_int32(int(branch)), C.c_int32(1 if reverse else 0),
+                                                          C.c_int32(1 if nni5 else 0), _dp(score), _dp(new_len), _dp(sw), _dp(outer)))
+        return [dict(move=m, reverse=bool(reverse), score=float(score[m]), new_len=new_len[m].tolist() if nni5 else new_len[m, :1].tolist(),
+                     swap=(int(sw[m, 0]), int(sw[m, 1])), outer=[int(x) for x in outer[m]]) for m in range(2)]
+
+    def do_nni(self, branch, move, new_len=None, clear_lh=True, reverse=False):
+        nni5 = new_len is not None and len(new_len) == 5
+        buf = None
+        if new_len is not None:
+            buf = np.zeros(5)
+            buf[:len(new_len)] = new_len
+        self._check(self.lib.b200st_do_nni(self._h, C.c_int32(int(branch)), C.c_int32(1 if reverse else 0), C.c_int32(int(move)),
+                                           C.c_int32(1 if nni5 else 0), _dp(buf), C.c_int32(1 if clear_lh else 0)))
+
     def part_scores(self):
         s = np.zeros(self.nparts)
         self._check(self.lib.b200st_get_part_scores(self._h, _dp(s)))

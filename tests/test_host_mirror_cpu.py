@@ -85,3 +85,10 @@ def test_polytomies_asc_and_robust_phylo_through_the_tree_api_on_cpu(over_oracle
         m.test_host_mirror_with_asc(asc_type)
         m.test_host_mirror_on_polytomous_tree("dna" if asc_type == 1 else "aa")
     r.test_robust_phylo_through_the_tree_api()
+
+
+def test_linked_partition_nni_on_cpu(over_oracle):
+    import test_gpu_supertree_nni as m
+    m.test_single_partition_equals_plain_tree(True)
+    m.test_single_partition_equals_plain_tree(False)
+    m.test_partitioned_nni_scores_are_the_likelihoods_of_the_moved_trees()
