@@ -92,3 +92,12 @@ def test_linked_partition_nni_on_cpu(over_oracle):
     m.test_single_partition_equals_plain_tree(True)
     m.test_single_partition_equals_plain_tree(False)
     m.test_partitioned_nni_scores_are_the_likelihoods_of_the_moved_trees()
+
+
+@pytest.mark.parametrize("kind,mem", [("dna", 0.0), ("aa", 0.3)])
+def test_mem_save_and_safe_kernel_through_the_tree_api_on_cpu(over_oracle, kind, mem):
+    import test_gpu_phylotree as m
+    m.test_mem_save_slot_recycling_on_gpu(kind, 0, mem)
+    if kind == "aa":
+        m.test_protein_tree_api_and_safe_kernel()
+        m.test_pipelined_sweep_equals_branch_by_branch("aa")   # no device length table here: falls back to branch by branch
