@@ -137,6 +137,7 @@ void PhyloTree::freeTree() {
     nodes_.clear();
     neighbors_.clear();
     branches_.clear();
+    node_by_id_.clear();
     root = nullptr;
     current_it = current_it_back = nullptr;
 }

@@ -101,3 +101,20 @@ def test_mem_save_and_safe_kernel_through_the_tree_api_on_cpu(over_oracle, kind,
     if kind == "aa":
         m.test_protein_tree_api_and_safe_kernel()
         m.test_pipelined_sweep_equals_branch_by_branch("aa")   # no device length table here: falls back to branch by branch
+
+
+def test_rereading_the_tree_drops_every_cached_node_pointer(over_oracle):
+    """the linked model resolves a partition's branch through its node lists (nodeById): reading a tree again must not leave
+    pointers to the old nodes behind"""
+    import numpy as np
+    from supercases import make_supercase
+    from test_gpu_supertree import make_gpu_super
+    tree, parts = make_supercase(ntaxa=10, nparts=3, seed=5)
+    g = make_gpu_super(tree, parts)
+    ll = g.compute_likelihood()
+    d = g.compute_likelihood_derv(3, 0.05)
+    for _ in range(3):
+        g.read_tree(tree.to_newick(fmt="%.17g"))
+        assert abs(g.compute_likelihood() - ll) < 1e-9
+        np.testing.assert_allclose(g.compute_likelihood_derv(3, 0.05), d, rtol=1e-10)
+    g.close()
