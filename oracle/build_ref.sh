@@ -104,3 +104,14 @@ if [ -f "$B200LIB" ]; then
 else
   echo "build_ref.sh: iqtree2_b200/libb200lk.so not built yet; skipping libiqref_b200.so"
 fi
+
+# The same binding over the CPU oracle (oracle/b200lk_over_oracle.c implements the C ABI it calls): the binding's own logic — slot
+# numbers from partial_lh pointers, marshalling of traversal_info, theta_computed, +ASC columns — is then covered by the CPU tests.
+if [ -f "$OUT/ref_b200_shim.o" ]; then
+  gcc -O3 -march=x86-64-v3 -mfma -ffp-contract=off -fopenmp -fPIC -c "$HERE/lk_oracle.c" -o "$OUT/lk_oracle.o"
+  gcc -O2 -fopenmp -fPIC -c "$HERE/b200lk_over_oracle.c" -o "$OUT/b200lk_over_oracle.o"
+  g++ -shared -fopenmp -o "$OUT/libiqref_over_oracle.so" "$OBJ"/*.o "$OUT/ref_b200_shim.o" "$OUT/lk_oracle.o" "$OUT/b200lk_over_oracle.o" \
+      "$OUT/stub_trap.o" "$OUT/stub_unresolved.o" -lm
+  left=$(ldd -r "$OUT/libiqref_over_oracle.so" 2>&1 | grep -c '^undefined symbol' || true)
+  echo "build_ref.sh: $OUT/libiqref_over_oracle.so built ($left undefined)"
+fi
