@@ -67,3 +67,51 @@ def test_two_rank_partition_sharding_matches_single_process(tmp_path):
     df, ddf = st.func_derv_at(2, 0.05)
     assert abs(res[0] - ll) < 1e-8
     np.testing.assert_allclose(res[1:], [df, ddf], rtol=1e-10)
+
+
+def _worker_cpp(rank, world, port, out):
+    """the same sharding with the product's C++ host mirror (b200::PhyloSuperTreePlen) in every rank, its C ABI served by the oracle
+    (oracle/_build/libb200pt_over_oracle.so, test infrastructure)"""
+    import ctypes
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    sys.path.insert(0, here)
+    sys.path.insert(0, root)
+    subprocess.check_call(["make", "-C", os.path.join(root, "oracle"), "-s"])
+    lib = ctypes.CDLL(os.path.join(root, "oracle", "_build", "libb200pt_over_oracle.so"))
+    import iqtree2_b200.supertree as st
+    st.load_library = lambda: lib
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    tree, parts = _case()
+    mine = deal_partitions([p["pat"].shape[1] * p["model"].nstates for p in parts], world, rank)
+    g = st.PhyloSuperTree(tree.names, num_threads=1)
+    for i in mine:
+        p = parts[i]
+        g.add_partition(p["pat"], p["freq"], p["model"], part_rate=p["rate"], ptn_invar=p["inv"])
+    g.read_tree(tree.to_newick(fmt="%.17g"))
+    ll = g.compute_likelihood()
+    df, ddf = g.compute_likelihood_derv(2, 0.05)
+    t = torch.tensor([ll, df, ddf], dtype=torch.float64)
+    dist.all_reduce(t)
+    if rank == 0:
+        np.save(out, t.numpy())
+    g.close()
+    dist.destroy_process_group()
+
+
+def test_two_rank_partition_sharding_with_the_cpp_host_mirror(tmp_path):
+    from test_supertree_cpu import make_pysuper
+    out = str(tmp_path / "res.npy")
+    mp.spawn(_worker_cpp, args=(2, _free_port(), out), nprocs=2, join=True)
+    res = np.load(out)
+    tree, parts = _case()
+    st = make_pysuper(tree, parts)
+    ll = st.compute_likelihood()
+    df, ddf = st.func_derv_at(2, 0.05)
+    assert abs(res[0] - ll) < 1e-8
+    np.testing.assert_allclose(res[1:], [df, ddf], rtol=1e-9)
