@@ -3,10 +3,14 @@
 # the CPU oracle through oracle/b200lk_over_oracle.c (test infrastructure): the tree-level tests — NNI evaluation on the spare
 # slots with its neighbour copies and swaps, doNNI, -mem slot recycling, tree-length scaling, both partition drivers — run on the
 # instrumented build.  No GPU needed.  Output: "asan run complete" or the first report.
+# SAN=undefined bash scripts/asan_host_mirror.sh runs the same under UndefinedBehaviorSanitizer.
 set -euo pipefail
 ROOT="$(cd "$(dirname "$0")/.." && pwd)"
 B="$ROOT/oracle/_build/asan"; mkdir -p "$B"
-F="-O1 -g -fsanitize=address -fno-omit-frame-pointer -fopenmp -fPIC"
+SAN="${SAN:-address}"
+F="-O1 -g -fsanitize=$SAN -fno-omit-frame-pointer -fopenmp -fPIC"
+[ "$SAN" = undefined ] && F="$F -fno-sanitize-recover=undefined"
+RT=$([ "$SAN" = undefined ] && echo libubsan.so || echo libasan.so)
 gcc $F -march=x86-64-v3 -mfma -ffp-contract=off -c "$ROOT/oracle/lk_oracle.c" -o "$B/lk_oracle.o"
 gcc $F -c "$ROOT/oracle/b200lk_over_oracle.c" -o "$B/adapter.o"
 g++ -std=c++17 $F -I"$ROOT/include" -I"$ROOT/iqtree2_b200/csrc" -shared -o "$B/libb200pt_over_oracle.so" \
@@ -33,4 +37,5 @@ sn.test_partitioned_nni_scores_are_the_likelihoods_of_the_moved_trees()
 u.test_unlinked_partitions(2)
 print("asan run complete")
 PY
-LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 OMP_NUM_THREADS=2 python "$B/run.py"
+LD_PRELOAD=$(gcc -print-file-name=$RT) ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
+    OMP_NUM_THREADS=2 python "$B/run.py"
