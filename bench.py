@@ -39,6 +39,8 @@ WORKLOADS = {
 
 
 SUPER_WORKLOAD = "super_500part_100taxa"   # BASELINE.json configs[4]
+DEFAULT_WORKLOAD = "dna_1000x1M_gtr_g4"    # BASELINE.json configs[1]: the headline line
+SECONDARY_WORKLOAD = "aa_200x100k_lg_g4"   # BASELINE.json configs[2] (the FP64-MMA path): measured in the same run, reported under "secondary"
 
 
 def make_super_inputs(ntaxa=100, nparts=500, seed=5):
@@ -96,7 +98,7 @@ def run_super(args, rank, world, local_rank):
         from oracle import ref_engine
         nsample = min(args.cpu_sample or 48, nparts)
         sample = [int(i) for i in order[:: max(1, nparts // nsample)][:nsample]]
-        threads = min(os.cpu_count() or 1, ref_engine.max_threads())
+        threads = host_threads()
         refs = []
         for i in sample:
             p = parts[i]
@@ -200,6 +202,33 @@ def run_super(args, rank, world, local_rank):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def host_threads():
+    """threads the CPU arm may use: the process's CPU affinity, NOT omp_get_max_threads() (torchrun exports OMP_NUM_THREADS=1)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def host_memory_available():
+    """bytes of host memory a CPU sample may plan with: min(what the OS reports available, what the cgroup still allows)"""
+    avail = None
+    try:
+        import psutil
+        avail = int(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    try:
+        lim = open("/sys/fs/cgroup/memory.max").read().strip()
+        if lim != "max":
+            cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+            room = int(lim) - cur
+            avail = room if avail is None else min(avail, room)
+    except Exception:
+        pass
+    return avail if avail is not None else 16 << 30
 
 
 def load_peaks():
@@ -328,7 +357,7 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
     from oracle import ref_engine
     sample_ptn = int(min(sample_ptn, tips.shape[1]))
     if ref_engine.available():
-        threads = min(ref_engine.max_threads(), os.cpu_count() or 1)
+        threads = host_threads()   # set explicitly: the harness calls omp_set_num_threads(), which overrides OMP_NUM_THREADS
         r = ref_engine.RefTree(tree, model, np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], nthreads=threads)
         if warmup:
             r.time_eval(0, warmup)
@@ -356,6 +385,53 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
             "what": "scalar C restatement of phylokernelnew.h (oracle/lk_oracle.c), OpenMP"}
 
 
+def shared_config(workload_name, ntaxa, nptn, model, desc, nops):
+    """the `config` object: identical for this framework's arm and for the reference arm of the same workload"""
+    return {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "NORM_LH", "nstates": model.nstates,
+            "ncat_mix": model.ncat_mix, "partial_updates_per_eval": nops,
+            "l2": "inputs (CLVs) far larger than L2; no flush needed"}
+
+
+def run_reference_arm(args, workload, ntaxa, nptn, model, desc, workload_name, steps=None, warmup=None):
+    """`--impl reference`: the reference's own CPU kernel (oracle/_ref/libiqref.so) on every host thread the process may use.
+    A step evaluates a SAMPLE of the workload's patterns (patterns are independent): the whole workload when the host
+    memory holds the reference's (ntaxa-2) x nptn x B doubles of CLVs, otherwise as many patterns as fit in half of the available
+    memory; `ms_per_step` is the measured time of that step, `value` scales it to the whole pattern count, `sample_fraction`
+    says by how much."""
+    steps = steps or args.steps
+    warmup = max(1, args.warmup if warmup is None else warmup)
+    B = model.nstates * model.ncat_mix
+    bytes_per_ptn = (ntaxa + 2) * (8 * B + 2) + 4 * ntaxa + 8 * (4 * B + 8)   # CLVs + scale, tip codes (u32 patterns), theta & co
+    mem_cap = int(0.5 * host_memory_available() / bytes_per_ptn)
+    sample = nptn if not args.cpu_sample else min(args.cpu_sample, nptn)
+    sample = max(256, min(sample, mem_cap))
+    # time cap: a short calibration run, then at most ~150 s for warm-up + timed steps (never below a quarter of the patterns
+    # when memory allows that)
+    tree, tips, freq, data = make_inputs(ntaxa, sample, model)
+    ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+    if not args.cpu_sample:
+        cal_n = min(sample, 8192)
+        cal = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, cal_n, 1, 1)
+        per_ptn = cal["best_sec"] / cal_n
+        by_time = int(150.0 / ((steps + warmup) * per_ptn))
+        sample = min(sample, max(by_time, min(nptn // 4, mem_cap)))
+        sample = max(256, sample // 8 * 8)
+    r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, steps, warmup)
+    frac = sample / nptn
+    evals = frac / r["sec_per_sample_eval"]
+    return {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["sec_per_sample_eval"] * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
+            "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops)),
+            "sample_fraction": frac,
+            "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
+                             "sample": f"{sample} of {nptn} patterns per step (fraction {frac:.4f}), all {len(ops)} partial updates + root + derivative; "
+                                       f"ms_per_step is that step as measured, value = fraction / seconds per step",
+                             "sample_fraction": frac},
+            "result": {"logl_sample": r["logl"], "df_sample": r["df"], "ddf_sample": r["ddf"]},
+            "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def cpu_sample_size(nops, B, nstates, ntaxa, budget_flop, nptn):
     """patterns in the bounded CPU sample: ~budget_flop of kernel work per eval, capped so that the reference's
     per-node CLVs (LM_PER_NODE: (ntaxa-2) x sample x B doubles) stay under a quarter of the free host memory"""
@@ -369,13 +445,273 @@ def cpu_sample_size(nops, B, nstates, ntaxa, budget_flop, nptn):
     return min(sample, nptn) // 8 * 8 or min(sample, nptn)
 
 
+def dram_model_bytes(ops, nptn, B, S, chained):
+    """DRAM-side model of one walker launch: every CLV (+ scale counts) written once, internal children that are not consumed
+    from registers / the same tile's previous op read once, one byte per tip child.  An upper bound of the traffic at the DRAM
+    pins (sibling reads that hit L2 never reach them) — `traffic` is the measured figure."""
+    clv = 8 * B + 2 * S
+    total, prev = 0, -1
+    for op in ops:
+        total += clv
+        kids = [op["left"], op["right"]]
+        skipped = False
+        for k in kids:
+            if k["kind"] == plan.KIND_SLOT:
+                if chained and not skipped and int(k["id"]) == prev:
+                    skipped = True      # register chaining (4-state walker): the previous op's CLV never leaves the thread
+                else:
+                    total += clv
+            else:
+                total += 1
+        prev = int(op["dst_slot"])
+    return float(total) * nptn
+
+
+def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, model, desc, workload_name, steps, warmup, cpu_baseline=True):
+    """One single-tree workload (BASELINE configs[1..3]) on this rank's pattern shard; returns the JSON line (complete on rank 0)."""
+    import torch
+    import torch.distributed as dist
+    from iqtree2_b200.engine import LikelihoodEngine
+    B, S = model.nstates * model.ncat_mix, 1
+    overridden = bool(args.taxa or args.patterns or args.ncat)
+    # pattern shard of this rank: contiguous, multiple of the 128-pattern tile except for the last rank
+    per = (nptn + world - 1) // world
+    per = (per + 127) // 128 * 128
+    lo, hi = min(rank * per, nptn), min((rank + 1) * per, nptn)
+    my_nptn = hi - lo
+    tree, tips_all, freq_all, data = make_inputs(ntaxa, nptn, model)
+    tips = np.ascontiguousarray(tips_all[:, lo:hi])
+    freq = freq_all[lo:hi]
+    br = plan.pendant_branch_of(tree, 0)
+    ops, a, b, L = plan.plan_branch(tree, br)
+
+    # CLV slots: one per internal node (LM_PER_NODE) when that fits the device; otherwise the reference's -mem mode
+    # (LM_MEM_SAVE, tree/phylotree.cpp:999-1021): the host mirror's planner recycles a bounded number of slots
+    nslots, mem_mode = None, "LM_PER_NODE"
+    slot_bytes = ((my_nptn + 127) // 128 * 128) * (8 * B + 2 * S)
+    dev_total = torch.cuda.get_device_properties(local_rank).total_memory
+    mem_frac = args.mem
+    if mem_frac < 0 and (ntaxa + 4) * slot_bytes > 0.85 * dev_total:
+        mem_frac = min(1.0, (0.70 * dev_total / slot_bytes - 4) / (ntaxa - 2))
+    if mem_frac >= 0:
+        ops, a, b, L, nslots = plan_mem_save(tree, model, ntaxa, mem_frac)
+        mem_mode = f"LM_MEM_SAVE ({nslots - 2} of {ntaxa - 2} CLV slots recycled by the host planner)"
+
+    eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, device=local_rank, schedule=args.schedule)
+    stream = torch.cuda.current_stream()
+    if args.variant:
+        eng.set_schedule(10 + args.variant)
+    eng.set_stream(stream.cuda_stream)
+    eng.set_tip_states(tips)
+    eng.set_pattern_freq(freq)
+    eng.set_pattern_invar(np.zeros(my_nptn))
+    eng.set_profiling(True)
+
+    scal = torch.zeros(3, dtype=torch.float64, device="cuda")
+    pinned_model = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in
+                    (model.eval, model.evec, model.inv_evec, model.mix_weight, model.cat_rate, model.cat_prop)]
+    h2d = int(ops.nbytes) + int(sum(t.numel() * 8 for t in pinned_model))
+    d2h = 3 * 8
+
+    def one_eval(upload_model):
+        """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
+        if upload_model:
+            eng.set_model(model)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
+        eng.theta_reset()
+        ll = eng.branch_logl(ops, a, b, L)
+        t1 = eng.last_timing()
+        df, ddf = eng.branch_derv(ops[:0], a, b, L)
+        t2 = eng.last_timing()
+        local = (ll, df, ddf)
+        if world > 1:
+            scal.copy_(torch.tensor([ll, df, ddf], dtype=torch.float64))
+            dist.all_reduce(scal)
+            ll, df, ddf = scal.tolist()
+        return (ll, df, ddf), t1, t2, local
+
+    for _ in range(warmup):
+        res, _, _, _ = one_eval(True)
+
+    def timed(upload_model):
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        t0 = time.perf_counter()
+        dev_ms = partial_ms = 0.0
+        launches0 = eng.launch_count
+        for _ in range(steps):
+            r, t1, t2, local = one_eval(upload_model)
+            dev_ms += t1["total_ms"] + t2["total_ms"]
+            partial_ms += t1["partials_kernel_ms"]
+        ev1.record(stream)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        out = {"event_ms": ev0.elapsed_time(ev1), "wall_s": wall, "device_ms": dev_ms, "partials_kernel_ms": partial_ms,
+               "launches": eng.launch_count - launches0, "result": r, "local": local, "clocks": clocks}
+        if world > 1:
+            t = torch.tensor([out["event_ms"], out["device_ms"], out["partials_kernel_ms"], wall * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            out["event_ms"], out["device_ms"], out["partials_kernel_ms"], w = t.tolist()
+            out["wall_s"] = w / 1e3
+        return out
+
+    e2e_run = timed(True)     # host buffers in every step, H2D/D2H inside the timed region
+    res_run = timed(False)    # inputs resident; device-time of the kernels only
+
+    K = steps
+    value = K / (res_run["event_ms"] * 1e-3)     # CUDA events around the K timed steps (inputs resident), max over ranks
+    e2e_value = K / (e2e_run["event_ms"] * 1e-3)
+    bytes_eval, bytes_partials = algorithmic_bytes(ops, nptn, B, S, ntaxa, n_root_slots=1 + (b[0] == plan.KIND_SLOT))
+    my_bytes_partials = bytes_partials * (my_nptn / nptn)
+    peak, peak_src = load_peaks()
+    ker_s = res_run["partials_kernel_ms"] * 1e-3 / K
+    alg_gbps = my_bytes_partials / ker_s / 1e9
+    n_ii, n_ti, n_tt = plan.count_node_cases(ops)
+    walk4 = args.schedule != 1 and model.nstates == 4 and model.nmix == 1
+    walk20 = args.schedule != 1 and model.nstates == 20
+    if walk20:
+        kernel_name = "k_walk_n20ss (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs)"
+    elif walk4:
+        kernel_name = f"k_walk_n4 (pattern-tile walker, 4 states x {model.ncat_mix} categories)"
+    else:
+        kernel_name = "k_partials_generic"
+    model_bytes = dram_model_bytes(ops, my_nptn, B, S, chained=walk4)
+    traffic, traffic_src = load_traffic(workload, overridden or bool(args.variant or args.schedule), my_nptn)
+    # roofline.frac is PHYSICAL: bytes at the DRAM pins (the committed ncu capture of this workload, else the DRAM-side model)
+    # per launch / launch time / measured copy peak.  The SURVEY 8(d) algorithmic figure (every CLV written once AND read once)
+    # is kept beside it: it exceeds the pins' traffic because chained / L2-resident CLVs are never re-read.
+    phys_bytes = traffic if traffic else model_bytes
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": phys_bytes / ker_s / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": phys_bytes / ker_s / 1e9 / peak, "frac_basis": "measured DRAM traffic (ncu)" if traffic else "DRAM-side model (upper bound of the traffic)",
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": ker_s * 1e3,
+                "dram_model_bytes_per_launch": model_bytes, "dram_model_GBps": model_bytes / ker_s / 1e9,
+                "algorithmic_bytes_per_launch": my_bytes_partials, "algorithmic_equivalent_GBps": alg_gbps, "partial_lh_GBps": alg_gbps}
+    if model.nstates >= 20:
+        # 20-state updates: the FP64-MMA pipe and HBM are both within reach of binding (SURVEY 8d: ~5 flop/B at a ridge of ~5.7).
+        # `tensor` = DMMA flops the kernel EXECUTES (state-space form: 30 / 15 / 0 DMMAs of 512 flops per 8 patterns x category
+        # for inner-inner / tip-inner / tip-tip nodes) over the measured DMMA peak; the reference-form flops (SURVEY 8d:
+        # C(6n^2+n) ...) over the same time are the `algorithmic_equivalent`.
+        fpeak, fsrc = load_fp64_peak()
+        flops_alg = algorithmic_flops(ops, my_nptn, model.nstates, model.ncat_mix)
+        steps8 = (my_nptn + 7) // 8 * model.ncat_mix
+        flops_exec = 512.0 * steps8 * (30 * n_ii + 15 * n_ti)
+        roofline["tensor"] = {"executed_TFLOPs": flops_exec / ker_s / 1e12, "peak": fpeak, "unit": "TFLOP/s", "frac": flops_exec / ker_s / 1e12 / fpeak,
+                              "peak_source": fsrc, "executed_flops_per_launch": flops_exec,
+                              "algorithmic_flops_per_launch": flops_alg, "algorithmic_equivalent_TFLOPs": flops_alg / ker_s / 1e12,
+                              "algorithmic_equivalent_frac": flops_alg / ker_s / 1e12 / fpeak}
+        if roofline["tensor"]["frac"] > roofline["frac"]:
+            roofline["bound"] = "tensor"
+    # ---- N > 1: the sharded result checks itself -------------------------------------------------------------------
+    check = None
+    if world > 1:
+        parts = torch.zeros(world * 3, dtype=torch.float64, device="cuda")
+        parts[rank * 3:(rank + 1) * 3] = torch.tensor(res_run["local"], dtype=torch.float64)
+        dist.all_reduce(parts)
+        per_rank = parts.view(world, 3).cpu().numpy()
+        tot = per_rank.sum(axis=0)
+        ok_sum = bool(abs(tot[0] - res_run["result"][0]) <= 1e-9 * abs(tot[0]))
+        # an independent engine on rank 0 recomputes the first patterns of the LAST rank's shard
+        sl = int(min(2048, nptn - min((world - 1) * per, nptn)))
+        lh_last = torch.zeros(max(sl, 1), dtype=torch.float64, device="cuda")
+        if rank == world - 1 and sl > 0:
+            lh_last.copy_(torch.from_numpy(eng.get_pattern_lh()[:sl].copy()))
+        dist.broadcast(lh_last, src=world - 1)
+        slice_diff = None
+        if rank == 0 and sl > 0:
+            lo2 = min((world - 1) * per, nptn)
+            e2 = LikelihoodEngine(model, ntaxa, sl, nslots=nslots, device=local_rank)
+            e2.set_tip_states(np.ascontiguousarray(tips_all[:, lo2:lo2 + sl])); e2.set_pattern_freq(freq_all[lo2:lo2 + sl]); e2.set_pattern_invar(np.zeros(sl))
+            e2.branch_logl(ops, a, b, L)
+            ref = e2.get_pattern_lh()
+            slice_diff = float(np.max(np.abs(ref - lh_last.cpu().numpy()) / np.abs(ref)))
+            e2.close()
+        check = {"per_rank_logl": [float(x) for x in per_rank[:, 0]], "sum_of_ranks_equals_allreduce": ok_sum,
+                 "slice_recomputed_on_rank0": {"rank": world - 1, "patterns": sl, "max_rel_diff": slice_diff}}
+        if rank == 0:
+            assert ok_sum, ("all-reduced logL differs from the sum of the per-rank values", tot[0], res_run["result"][0])
+            assert slice_diff is None or slice_diff < 1e-11, ("sharded per-pattern logL differs from an independent engine", slice_diff)
+    exp = None if overridden else load_expected(workload)
+    if exp is not None:
+        d = abs(res_run["result"][0] - exp)
+        check = dict(check or {}, expected_logl=exp, expected_abs_diff=d)
+        if rank == 0:
+            assert d <= 1e-9 * abs(exp), ("logL differs from the recorded value of this workload", res_run["result"][0], exp)
+    line = {
+        "metric": "full_tree_logl_deriv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
+        "warmup": warmup, "ms_per_step": res_run["event_ms"] / K, "kernel_ms_per_step": res_run["device_ms"] / K,
+        "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": data,
+        "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops)),
+        "detail": {"patterns_per_gpu": my_nptn, "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
+                   "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}.get(args.schedule, f"variant{args.schedule}"),
+                   "clv_bytes_resident": eng.device_bytes, "clv_slots": mem_mode,
+                   "parallelism": f"pattern-sharded x{world}" if world > 1 else "single GPU", "algorithmic_GB_per_eval": bytes_eval / 1e9},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_run["event_ms"] / K, "wall_ms_per_step": e2e_run["wall_s"] * 1e3 / K,
+                "what": "set_model+set_rates (eigensystem, rates), op list with branch lengths from host memory, "
+                        "branch_logl + branch_derv through the C ABI, (logL, df, ddf) read back each step"},
+        "gpu_launches": int(res_run["launches"]),
+        "clocks": res_run["clocks"],
+        "roofline": roofline,
+        "result": {"logl": res_run["result"][0], "df": res_run["result"][1], "ddf": res_run["result"][2]},
+    }
+    if check:
+        line["check"] = check
+    eng.close()
+    del eng
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and cpu_baseline:
+        sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, my_nptn)
+        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 5, 1)
+        cpu_evals = (sample / nptn) / r["sec_per_sample_eval"]
+        line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
+                                "sample": f"first {sample} of {nptn} patterns, all {len(ops)} partial updates + root + derivative, "
+                                          f"5 timed evals after 1 warm-up; throughput scaled by {sample}/{nptn}",
+                                "sample_fraction": sample / nptn, "sec_per_sample_eval": r["sec_per_sample_eval"]}
+    return line
+
+
+def plan_mem_save(tree, model, ntaxa, mem_frac):
+    """the op list of the headline evaluation under the reference's -mem mode, planned by the host mirror (plan-only tree)"""
+    from iqtree2_b200.phylotree import PhyloTree
+    pt = PhyloTree()
+    pt.set_plan_only(True)
+    pt.set_alignment(tree.names, np.zeros((ntaxa, 1), dtype=np.uint8), np.ones(1), model)   # planning needs no patterns
+    pt.set_model(model)
+    pt.read_tree(tree.to_newick())
+    pt.set_mem_save(True, mem_frac)
+    nslots = pt.max_lh_slots + 2
+    pa, pb, _ = pt.branches()
+    pbr = [k for k in range(len(pa)) if min(pa[k], pb[k]) == 0][0]   # the pendant branch of alignment row 0
+    ops, a, b, L = pt.plan_branch(pbr)
+    assert len(ops) == ntaxa - 2
+    pt.close()
+    return ops, a, b, L, nslots
+
+
+def load_expected(workload):
+    """logL of the full workload recorded from a single-GPU run (profiles/expected_logl.json): every N must reproduce it"""
+    p = os.path.join(ROOT, "profiles", "expected_logl.json")
+    if not os.path.exists(p):
+        return None
+    return json.load(open(p)).get(workload)
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="dna_1000x1M_gtr_g4", choices=sorted(WORKLOADS) + [SUPER_WORKLOAD])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS) + [SUPER_WORKLOAD])
     ap.add_argument("--parts", type=int, default=0, help="override the number of partitions of the partition workload (debug)")
     ap.add_argument("--host-threads", type=int, default=0, help="host threads that queue partition work (0 = OpenMP default)")
     ap.add_argument("--taxa", type=int, default=0, help="override taxa (debug)")
@@ -385,6 +721,7 @@ def main():
     ap.add_argument("--variant", type=int, default=0, help="kernel variant of the walker schedule (development A/B switch)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="patterns in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="default workload only: skip the LG+G4 `secondary` block")
     ap.add_argument("--mem", type=float, default=-1.0,
                     help="-mem of the reference (LM_MEM_SAVE): fraction of the T-2 CLV slots to keep (0 = log2(T)+1 slots); "
                          "default: only when one slot per internal node does not fit the device")
@@ -415,21 +752,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        tree, tips, freq, data = make_inputs(ntaxa, min(nptn, 65536), model)
-        ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
-        # bounded sample per step (an eval over `sample` of the nptn patterns)
-        sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, tips.shape[1])
-        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, args.steps, max(1, args.warmup))
-        evals = (sample / nptn) / r["sec_per_sample_eval"]
-        line = {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / evals,
-                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
-                "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "NORM_LH"},
-                "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
-                                 "sample": f"{sample} of {nptn} patterns per step, all {len(ops)} partial updates + root + derivative; "
-                                           f"throughput scaled by {sample}/{nptn}"},
-                "result": {"logl_sample": r["logl"], "df_sample": r["df"], "ddf_sample": r["ddf"]},
-                "e2e": {"value": evals, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        line = run_reference_arm(args, args.workload, ntaxa, nptn, model, desc, workload_name)
+        if args.workload == DEFAULT_WORKLOAD and not (args.taxa or args.patterns or args.ncat) and not args.no_secondary:
+            ntaxa2, nptn2, mk2, desc2 = WORKLOADS[SECONDARY_WORKLOAD]
+            line["secondary"] = run_reference_arm(args, SECONDARY_WORKLOAD, ntaxa2, nptn2, mk2(), desc2, SECONDARY_WORKLOAD, steps=min(args.steps, 5), warmup=1)
         print(json.dumps(line))
         return 0
 
@@ -438,184 +764,22 @@ def main():
     # ---------------------------------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
-    from iqtree2_b200.engine import LikelihoodEngine
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the likelihood engine has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    # pattern shard of this rank: contiguous, multiple of the 128-pattern tile except for the last rank
-    per = (nptn + world - 1) // world
-    per = (per + 127) // 128 * 128
-    lo, hi = min(rank * per, nptn), min((rank + 1) * per, nptn)
-    my_nptn = hi - lo
-    tree, tips, freq, data = make_inputs(ntaxa, nptn, model)
-    tips = np.ascontiguousarray(tips[:, lo:hi])
-    freq = freq[lo:hi]
-    br = plan.pendant_branch_of(tree, 0)
-    ops, a, b, L = plan.plan_branch(tree, br)
-
-    # CLV slots: one per internal node (LM_PER_NODE) when that fits the device; otherwise the reference's -mem mode
-    # (LM_MEM_SAVE, tree/phylotree.cpp:999-1021): the host mirror's planner recycles a bounded number of slots
-    nslots, mem_mode = None, "LM_PER_NODE"
-    slot_bytes = ((my_nptn + 127) // 128 * 128) * (8 * B + 2 * S)
-    dev_total = torch.cuda.get_device_properties(local_rank).total_memory
-    mem_frac = args.mem
-    if mem_frac < 0 and (ntaxa + 2) * slot_bytes > 0.85 * dev_total:
-        mem_frac = min(1.0, (0.70 * dev_total / slot_bytes - 2) / (ntaxa - 2))
-    if mem_frac >= 0:
-        from iqtree2_b200.phylotree import PhyloTree
-        pt = PhyloTree()
-        pt.set_plan_only(True)
-        pt.set_alignment(tree.names, np.zeros((ntaxa, 1), dtype=np.uint8), np.ones(1), model)   # planning needs no patterns
-        pt.set_model(model)
-        pt.read_tree(tree.to_newick())
-        pt.set_mem_save(True, mem_frac)
-        nslots = pt.max_lh_slots + 2
-        pa, pb, _ = pt.branches()
-        pbr = [k for k in range(len(pa)) if min(pa[k], pb[k]) == 0][0]   # the pendant branch of alignment row 0
-        ops, a, b, L = pt.plan_branch(pbr)
-        assert len(ops) == ntaxa - 2
-        pt.close()
-        mem_mode = f"LM_MEM_SAVE ({nslots - 2} of {ntaxa - 2} CLV slots recycled by the host planner)"
-
-    eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, device=local_rank, schedule=args.schedule)
-    stream = torch.cuda.current_stream()
-    if args.variant:
-        eng.set_schedule(10 + args.variant)
-    eng.set_stream(stream.cuda_stream)
-    eng.set_tip_states(tips)
-    eng.set_pattern_freq(freq)
-    eng.set_pattern_invar(np.zeros(my_nptn))
-    eng.set_profiling(True)
-
-    scal = torch.zeros(3, dtype=torch.float64, device="cuda")
-    pinned_model = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in
-                    (model.eval, model.evec, model.inv_evec, model.mix_weight, model.cat_rate, model.cat_prop)]
-    h2d = int(ops.nbytes) + int(sum(t.numel() * 8 for t in pinned_model))
-    d2h = 3 * 8
-
-    def one_eval(upload_model):
-        """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
-        if upload_model:
-            eng.set_model(model)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
-        eng.theta_reset()
-        ll = eng.branch_logl(ops, a, b, L)
-        t1 = eng.last_timing()
-        df, ddf = eng.branch_derv(ops[:0], a, b, L)
-        t2 = eng.last_timing()
-        if world > 1:
-            scal.copy_(torch.tensor([ll, df, ddf], dtype=torch.float64))
-            dist.all_reduce(scal)
-            ll, df, ddf = scal.tolist()
-        return (ll, df, ddf), t1, t2
-
-    for _ in range(args.warmup):
-        res, _, _ = one_eval(True)
-
-    def timed(upload_model):
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        t0 = time.perf_counter()
-        dev_ms = partial_ms = 0.0
-        launches0 = eng.launch_count
-        for _ in range(args.steps):
-            r, t1, t2 = one_eval(upload_model)
-            dev_ms += t1["total_ms"] + t2["total_ms"]
-            partial_ms += t1["partials_kernel_ms"]
-        ev1.record(stream)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        wall = time.perf_counter() - t0
-        clocks = sampler.stop()
-        out = {"event_ms": ev0.elapsed_time(ev1), "wall_s": wall, "device_ms": dev_ms, "partials_kernel_ms": partial_ms,
-               "launches": eng.launch_count - launches0, "result": r, "clocks": clocks}
-        if world > 1:
-            t = torch.tensor([out["event_ms"], out["device_ms"], out["partials_kernel_ms"], wall * 1e3], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            out["event_ms"], out["device_ms"], out["partials_kernel_ms"], w = t.tolist()
-            out["wall_s"] = w / 1e3
-        return out
-
-    e2e_run = timed(True)     # host buffers in every step, H2D/D2H inside the timed region
-    res_run = timed(False)    # inputs resident; device-time of the kernels only
-
-    K = args.steps
-    value = K / (res_run["event_ms"] * 1e-3)     # CUDA events around the K timed steps (inputs resident), max over ranks
-    e2e_value = K / (e2e_run["event_ms"] * 1e-3)
-    bytes_eval, bytes_partials = algorithmic_bytes(ops, nptn, B, S, ntaxa, n_root_slots=1 + (b[0] == plan.KIND_SLOT))
-    my_bytes_partials = bytes_partials * (my_nptn / nptn)
-    peak, peak_src = load_peaks()
-    ker_s = res_run["partials_kernel_ms"] * 1e-3 / K
-    achieved = my_bytes_partials / ker_s / 1e9
-    n_ii, n_ti, n_tt = plan.count_node_cases(ops)
-
-    if args.schedule != 1 and model.nstates == 20:
-        kernel_name = "k_walk_n20_mma (pattern-tile walker, FP64 MMA m8n8k4)"
-    elif args.schedule != 1 and model.nstates == 4 and model.nmix == 1 and model.ncat_mix == 4:
-        kernel_name = "k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)"
-    else:
-        kernel_name = "k_partials_generic"
-    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": my_bytes_partials,
-                "launch_ms": ker_s * 1e3, "partial_lh_GBps": achieved}
-    if model.nstates >= 20:
-        # 20-state updates sit on the FP64 side of the ridge (SURVEY §8d: ~5 flop/B against a ridge of ~5.5): the binding
-        # roofline is the FP64 MMA pipe; the HBM figure is kept beside it
-        fpeak, fsrc = load_fp64_peak()
-        flops = algorithmic_flops(ops, my_nptn, model.nstates, model.ncat_mix)
-        tf = flops / ker_s / 1e12
-        roofline = {"bound": "tensor", "kernel": kernel_name, "achieved": tf, "peak": fpeak, "unit": "TFLOP/s", "frac": tf / fpeak,
-                    "traffic": None, "peak_source": fsrc, "algorithmic_flops_per_launch": flops, "launch_ms": ker_s * 1e3,
-                    "hbm": {"achieved_GBps": achieved, "peak_GBps": peak, "frac": achieved / peak,
-                            "algorithmic_bytes_per_launch": my_bytes_partials}, "partial_lh_GBps": achieved}
-    traffic, traffic_src = load_traffic(args.workload, bool(args.taxa or args.patterns or args.ncat or args.variant or args.schedule), my_nptn)
-    roofline["traffic"] = traffic
-    if traffic:
-        roofline["traffic_source"] = traffic_src
-        roofline["dram_GBps"] = traffic / ker_s / 1e9     # what the DRAM pins see: chained CLVs are never re-read
-        roofline["dram_frac_of_hbm_peak"] = traffic / ker_s / 1e9 / peak
-    line = {
-        "metric": "full_tree_logl_deriv_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world, "steps": K,
-        "warmup": args.warmup, "ms_per_step": res_run["event_ms"] / K, "kernel_ms_per_step": res_run["device_ms"] / K,
-        "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f64", "data": data,
-        "config": {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "patterns_per_gpu": my_nptn, "model": desc,
-                   "kernel": "NORM_LH", "nstates": model.nstates, "ncat_mix": model.ncat_mix, "partial_updates_per_eval": len(ops),
-                   "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
-                   "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}.get(args.schedule, f"variant{args.schedule}"),
-                   "clv_bytes_resident": eng.device_bytes, "clv_slots": mem_mode, "l2": "inputs (CLVs) far larger than L2; no flush needed",
-                   "parallelism": f"pattern-sharded x{world}" if world > 1 else "single GPU",
-                   "algorithmic_GB_per_eval": bytes_eval / 1e9},
-        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_run["event_ms"] / K, "wall_ms_per_step": e2e_run["wall_s"] * 1e3 / K,
-                "what": "set_model+set_rates (eigensystem, rates), op list with branch lengths from host memory, "
-                        "branch_logl + branch_derv through the C ABI, (logL, df, ddf) read back each step"},
-        "gpu_launches": int(res_run["launches"]),
-        "clocks": res_run["clocks"],
-        "roofline": roofline,
-        "result": {"logl": res_run["result"][0], "df": res_run["result"][1], "ddf": res_run["result"][2]},
-    }
-
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, my_nptn)
-        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 5, 1)
-        cpu_evals = (sample / nptn) / r["sec_per_sample_eval"]
-        line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
-                                "sample": f"first {sample} of {nptn} patterns, all {len(ops)} partial updates + root + derivative, "
-                                          f"5 timed evals after 1 warm-up; throughput scaled by {sample}/{nptn}",
-                                "sec_per_sample_eval": r["sec_per_sample_eval"]}
+    line = run_tree_workload(args, rank, world, local_rank, args.workload, ntaxa, nptn, model, desc, workload_name, args.steps, args.warmup,
+                             cpu_baseline=not args.no_cpu_baseline)
+    if args.workload == DEFAULT_WORKLOAD and not (args.taxa or args.patterns or args.ncat or args.variant or args.schedule) and not args.no_secondary:
+        # the FP64-MMA path (BASELINE configs[2], named in north_star's target) measured in the same run: ~0.1 s of GPU time
+        ntaxa2, nptn2, mk2, desc2 = WORKLOADS[SECONDARY_WORKLOAD]
+        sec = run_tree_workload(args, rank, world, local_rank, SECONDARY_WORKLOAD, ntaxa2, nptn2, mk2(), desc2, SECONDARY_WORKLOAD,
+                                args.steps, args.warmup, cpu_baseline=not args.no_cpu_baseline)
+        line["secondary"] = sec
     if rank == 0:
         print(json.dumps(line))
-    eng.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -6,6 +6,7 @@
 // No CPU fallback: every compute entry point launches CUDA kernels or fails.
 #include "b200lk.h"
 #include "b200lk_kernels.cuh"
+#include "b200lk_walk20ss.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -13,6 +14,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -68,6 +70,14 @@ struct b200lk_engine {
     void *d_robust_tmp = nullptr;
     size_t robust_tmp_bytes = 0;
     int kernel_variant = 0;   // b200lk_set_schedule(e, 10 + v): development switch between kernel variants of one schedule
+    // state-space CLVs (20-state engines, b200lk_walk20ss.cuh): two scratch slots behind the caller's nslots hold
+    // partial_lh = inv_evec . t of the CLVs at the evaluation branch; slot_ver counts the writes of every slot
+    int nslots_total = 0;
+    double *d_inv_frag20 = nullptr;
+    std::vector<uint64_t> slot_ver;
+    int eig_src[2] = {-1, -1};
+    uint64_t eig_ver[2] = {0, 0};
+    int eig_next = 0;
     int walk20_ctas_per_sm = 1;
     // profiling
     bool profiling = false;
@@ -81,6 +91,7 @@ struct b200lk_engine {
     long long boot_stride = 0;
     size_t boot_bytes = 0;
     int newton_grid = 0;   // co-resident CTAs of k_newton_coop
+    int64_t asc_tmp_bytes = 0;
     double *d_lens = nullptr;      // device-resident branch lengths of an asynchronous sweep (slots)
     double *h_sweep = nullptr;     // mapped host table [nlen_slots][3]: (length, evaluations, status) per slot
     double *d_sweep = nullptr;     // its device alias
@@ -153,7 +164,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens);
+    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
@@ -200,6 +211,11 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     e->stream = e->own_stream;
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     const long long Ppad = e->Ppad;
+    // 20-state engines keep state-space CLVs (b200lk_walk20ss.cuh); B200LK_EIGEN20=1 keeps the eigen-space walker (A/B)
+    const bool f20 = n == 20 && e->C % cfg->nmix == 0;
+    const bool state_space = f20 && !(getenv("B200LK_EIGEN20") && atoi(getenv("B200LK_EIGEN20")) != 0);
+    e->nslots_total = cfg->nslots + (state_space ? 2 : 0);
+    e->slot_ver.assign(e->nslots_total, 0);
     TRY(dev_alloc(e, &e->d_tips, (size_t)cfg->ntaxa * Ppad));
     TRY(dev_alloc(e, &e->d_freq, Ppad));
     TRY(dev_alloc(e, &e->d_invar, Ppad));
@@ -207,8 +223,9 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     const size_t n_tip = (size_t)(cfg->state_unknown + 1) * cfg->nmix * n;
     const size_t model_doubles = n_eval + 2 * n_mat + cfg->nmix + 2 * cfg->ncat + n_tip + 3 * (size_t)e->B;
     TRY(dev_alloc(e, &e->d_model, model_doubles));
-    TRY(dev_alloc(e, &e->d_partial, (size_t)cfg->nslots * Ppad * e->B));
-    TRY(dev_alloc(e, &e->d_scale, (size_t)cfg->nslots * Ppad * e->S));
+    TRY(dev_alloc(e, &e->d_partial, (size_t)e->nslots_total * Ppad * e->B));
+    TRY(dev_alloc(e, &e->d_scale, (size_t)e->nslots_total * Ppad * e->S));
+    if (state_space) TRY(dev_alloc(e, &e->d_inv_frag20, (size_t)cfg->nmix * 480));
     TRY(dev_alloc(e, &e->d_theta, (size_t)Ppad * e->B));
     TRY(dev_alloc(e, &e->d_buffer_scale, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_lh, Ppad));
@@ -228,7 +245,7 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     cudaMemsetAsync(e->d_tips, cfg->state_unknown, (size_t)cfg->ntaxa * Ppad, e->stream);
     cudaMemsetAsync(e->d_freq, 0, sizeof(double) * Ppad, e->stream);
     cudaMemsetAsync(e->d_invar, 0, sizeof(double) * Ppad, e->stream);
-    cudaMemsetAsync(e->d_scale, 0, sizeof(uint16_t) * (size_t)cfg->nslots * Ppad * e->S, e->stream);
+    cudaMemsetAsync(e->d_scale, 0, sizeof(uint16_t) * (size_t)e->nslots_total * Ppad * e->S, e->stream);
     cudaMemsetAsync(e->d_model, 0, sizeof(double) * model_doubles, e->stream);
     e->h_freq.assign(cfg->nptn, 0.0);
 
@@ -236,7 +253,10 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     d.n = n; d.C = e->C; d.ncat = cfg->ncat; d.nmix = cfg->nmix; d.denom = e->denom; d.B = e->B; d.S = e->S;
     d.su = cfg->state_unknown; d.P = e->P; d.Ppad = Ppad;
     d.asc = 0; d.Pobs = e->P; d.asc_nsite = 0; d.asc_step = 0; d.asc_tmp = nullptr;
-    d.clv_f20 = (n == 20 && e->C % cfg->nmix == 0) ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
+    d.clv_f20 = f20 ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
+    d.clv_state = state_space ? 1 : 0;
+    d.inv_frag20 = e->d_inv_frag20;
+    d.ss_lo = 0u; d.ss_hi = 0xffffffffu;   // set_model narrows the band from the eigenvector norms
     d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
     d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
     double *m = e->d_model;
@@ -290,8 +310,12 @@ extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int6
         return fail(e, B200LK_ERR_INVALID, "+ASC_MIS: the unobserved block must be nstates groups of at least (observed patterns) constant patterns");
     cudaSetDevice(e->cfg.device);
     CK(sync_stream(e));
-    if (e->d.asc_tmp) { cudaFree(e->d.asc_tmp); e->d.asc_tmp = nullptr; }
-    if (asc_type == 2) CK(cudaMalloc(&e->d.asc_tmp, sizeof(double) * 3 * (size_t)num_unobserved));
+    if (e->d.asc_tmp) { cudaFree(e->d.asc_tmp); e->d.asc_tmp = nullptr; e->device_bytes -= e->asc_tmp_bytes; e->asc_tmp_bytes = 0; }
+    if (asc_type == 2) {
+        CK(cudaMalloc(&e->d.asc_tmp, sizeof(double) * 3 * (size_t)num_unobserved));
+        e->asc_tmp_bytes = (int64_t)(sizeof(double) * 3 * (size_t)num_unobserved);
+        e->device_bytes += e->asc_tmp_bytes;
+    }
     e->d.asc = asc_type;
     e->d.Pobs = asc_type ? e->P - num_unobserved : e->P;
     e->d.asc_step = asc_type == 2 ? num_unobserved / e->cfg.nstates : 0;
@@ -313,7 +337,11 @@ extern "C" int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t me
         cub::DeviceScan::InclusiveSum(nullptr, b2, nul, nul, (int)e->P, e->stream);
         e->robust_tmp_bytes = std::max(b1, b2);
         CK(cudaMalloc(&e->d_robust, sizeof(double) * 3 * (size_t)e->P));
-        CK(cudaMalloc(&e->d_robust_tmp, e->robust_tmp_bytes));
+        if (cudaMalloc(&e->d_robust_tmp, e->robust_tmp_bytes) != cudaSuccess) {
+            cudaFree(e->d_robust); e->d_robust = nullptr;
+            return fail(e, B200LK_ERR_NOMEM, "set_robust_phylo: cudaMalloc failed");
+        }
+        e->device_bytes += (int64_t)(sizeof(double) * 3 * (size_t)e->P + e->robust_tmp_bytes);
     }
     e->robust_keep = keep;
     e->robust_median = median != 0;
@@ -382,6 +410,25 @@ extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const doub
     const int total = (e->cfg.state_unknown + 1) * nmix * n;
     k_tip_partial_lh<<<(total + 127) / 128, 128, 0, e->stream>>>(e->d, (double *)e->d.tip_lh, e->cfg.seq_type);
     e->launches++;
+    if (e->d.clv_state) {
+        // max|t| / ||evec||_inf <= max|inv_evec . t| <= ||inv_evec||_inf . max|t|  (t = evec . W): outside the band
+        // [2^-256 / ||inv_evec||, 2^-256 . ||evec||) the reference's underflow test is decided by max|t| alone; one more
+        // binade on either side absorbs the rounding of the norms and of t
+        double r_evec = 0.0, r_inv = 0.0;
+        for (int m = 0; m < nmix; m++)
+            for (int r = 0; r < n; r++) {
+                double a = 0.0, b = 0.0;
+                for (int k = 0; k < n; k++) { a += std::fabs(evec[((size_t)m * n + r) * n + k]); b += std::fabs(inv_evec[((size_t)m * n + r) * n + k]); }
+                r_evec = std::max(r_evec, a); r_inv = std::max(r_inv, b);
+            }
+        if (!(r_evec > 0.0) || !(r_inv > 0.0) || !std::isfinite(r_evec) || !std::isfinite(r_inv)) return fail(e, B200LK_ERR_INVALID, "set_model: degenerate eigenvectors");
+        const int e_hi = (int)std::ceil(std::log2(r_evec)) + 1, e_lo = (int)std::ceil(std::log2(r_inv)) + 1;
+        e->d.ss_hi = (unsigned)std::min(2046, std::max(1, 1023 - 256 + e_hi)) << 20;
+        e->d.ss_lo = (unsigned)std::min(2046, std::max(0, 1023 - 256 - e_lo)) << 20;
+        k_inv_frag20<<<nmix, 128, 0, e->stream>>>(e->d, e->d_inv_frag20);
+        e->launches++;
+        e->eig_src[0] = e->eig_src[1] = -1;
+    }
     CK(cudaGetLastError());
     // pageable host sources: make sure the copies have consumed them before returning
     CK(sync_stream(e));
@@ -420,6 +467,8 @@ static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
         cudaFree(e->d_ops); cudaFree(e->d_jobs); cudaFree(e->d_mchild);
         if (e->h_stage) cudaFreeHost(e->h_stage);
         e->d_ops = nullptr; e->d_jobs = nullptr; e->h_stage = nullptr; e->d_mchild = nullptr;
+        e->device_bytes -= (int64_t)(e->ops_cap * (sizeof(DevOp) + 2 * sizeof(ChildJob) + 2 * sizeof(MultiChild)));
+        e->ops_cap = 0;   // set again only when all four allocations below have succeeded
         size_t cap = std::max<size_t>(nops, 16);
         int rc = dev_alloc(e, &e->d_ops, cap);
         if (rc) return rc;
@@ -543,10 +592,38 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
 // the 20-state FP64-MMA walker serves the walker schedule of every protein model: any number of categories, mixtures,
 // fused classes
 static int walk20_cpb(const b200lk_engine *e) { return e->C / e->cfg.nmix; }   // categories per class block
+static size_t walk20_stage_doubles(const b200lk_engine *e) {
+    return e->d.clv_state ? ss_stage_doubles(walk20_cpb(e), e->cfg.state_unknown) : stage20_doubles(walk20_cpb(e), e->cfg.state_unknown);
+}
 static bool use_walk20(const b200lk_engine *e) {
     return e->schedule != 1 && e->cfg.nstates == 20 && e->C % e->cfg.nmix == 0 && e->h_evec.size() == (size_t)400 * e->cfg.nmix &&
-           2 * stage20_doubles(walk20_cpb(e), e->cfg.state_unknown) * sizeof(double) <= 200 * 1024;
+           2 * walk20_stage_doubles(e) * sizeof(double) <= 200 * 1024;
 }
+
+// every op rewrites its destination slot: the eigen-space copies of state-space CLVs (eigen_slot) are keyed on these counters
+static void note_writes(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    if (!e->d.clv_state) return;
+    for (int k = 0; k < nops; k++) e->slot_ver[ops[k].dst_slot]++;
+}
+
+// state-space engines: the slot that holds partial_lh = inv_evec . t of CLV `slot` (one of two scratch slots behind the caller's;
+// converted on the stream when the cached copy is stale).  Eigen-space engines: the slot itself.
+static int eigen_slot(b200lk_engine *e, int slot, int keep = -1) {
+    if (!e->d.clv_state) return slot;
+    for (int k = 0; k < 2; k++)
+        if (e->eig_src[k] == slot && e->eig_ver[k] == e->slot_ver[slot]) return e->cfg.nslots + k;
+    int k = e->eig_next;
+    if (e->cfg.nslots + k == keep) k ^= 1;   // do not evict the other end of the same branch
+    e->eig_next = k ^ 1;
+    const long long nblocks = e->Ppad / 32;
+    const int grid = (int)std::min<long long>((nblocks + 3) / 4, (long long)e->num_sms * 8);
+    k_clv20_to_eigen<<<grid, 128, 0, e->stream>>>(e->d, slot, e->cfg.nslots + k);
+    e->launches++;
+    e->eig_src[k] = slot;
+    e->eig_ver[k] = e->slot_ver[slot];
+    return e->cfg.nslots + k;
+}
+
 
 // k_walk_n20_mma configurations: {warps per CTA, kernels [MIX*2 + SAFE]}; index = kernel_variant (b200lk_set_schedule(e, 10 + v))
 struct Walk20Cfg { int nw; const void *f[4]; };
@@ -574,10 +651,16 @@ constexpr int kNumWalk20Cfgs = (int)(sizeof(walk20_cfgs) / sizeof(walk20_cfgs[0]
 static const void *const walk20_csp[2] = {(const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, true, true>,
                                           (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, true, true>};
 
+// k_walk_n20ss [MIX*2 + SAFE], 4 warps per CTA, 3 CTAs per SM; and its category-split form [SAFE]
+static const void *const walk20ss_f[4] = {(const void *)k_walk_n20ss<false, false, 4, 3, false>, (const void *)k_walk_n20ss<true, false, 4, 3, false>,
+                                          (const void *)k_walk_n20ss<false, true, 4, 3, false>, (const void *)k_walk_n20ss<true, true, 4, 3, false>};
+static const void *const walk20ss_csp[2] = {(const void *)k_walk_n20ss<false, false, 4, 3, true>, (const void *)k_walk_n20ss<true, false, 4, 3, true>};
+
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
     const bool mix = nblk > 1;
-    const size_t stage_sz = stage20_doubles(cpb, e->cfg.state_unknown);   // one staging block per (op, class block)
+    const bool ss = e->d.clv_state != 0;
+    const size_t stage_sz = walk20_stage_doubles(e);   // one staging block per (op, class block)
     if (stage_sz * nops * nblk > e->opinfo_cap) {
         CK(sync_stream(e));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
@@ -604,8 +687,12 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     }
     WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
-    k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
-    const Walk20Cfg &cfg = walk20_cfgs[(e->kernel_variant >= 0 && e->kernel_variant < kNumWalk20Cfgs) ? e->kernel_variant : 0];
+    if (ss) k_walk_info_n20ss<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+    else k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+    note_writes(e, ops, nops);
+    static const Walk20Cfg ss_cfg = {4, {walk20ss_f[0], walk20ss_f[1], walk20ss_f[2], walk20ss_f[3]}};
+    const Walk20Cfg &cfg = ss ? ss_cfg : walk20_cfgs[(e->kernel_variant >= 0 && e->kernel_variant < kNumWalk20Cfgs) ? e->kernel_variant : 0];
+    const void *const *csp_f = ss ? walk20ss_csp : walk20_csp;
     const int tile_ptn = cfg.nw * 32;
     const size_t smem = 2 * stage_sz * sizeof(double);   // the walker double-buffers whole staging blocks
     if (!e->walk20_attr_set) {
@@ -614,9 +701,9 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
             // the staging tables must not be what limits residency: ask for the largest shared-memory carve-out
             cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
-        for (const void *f : walk20_csp) {
-            CK(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        for (int k = 0; k < 2; k++) {
+            CK(cudaFuncSetAttribute(csp_f[k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaFuncSetAttribute(csp_f[k], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         }
         int per_sm = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cfg.f[0], tile_ptn, smem));
@@ -630,14 +717,14 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     if (e->kernel_variant == 4) ntiles = (int)((nblocks + cfg.nw - 1) / cfg.nw);   // A/B: fixed full tiles
     // small problems: one 32-pattern block per CTA, its categories split over the CTA's warps (k_walk_n20_mma<.., CSP>): a
     // traversal's latency drops by min(C, 4); worth it only while every block still gets its own resident CTA
-    const bool csp = !mix && e->C >= 2 && e->kernel_variant == 0 && cfg.nw == 4 && nblocks <= slots;
+    const bool csp = !mix && e->C >= 2 && (ss ? e->kernel_variant != 4 : e->kernel_variant == 0) && cfg.nw == 4 && nblocks <= slots;
     if (csp) ntiles = (int)nblocks;
     const int grid = (int)std::min<long long>(ntiles, slots);
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {
         const bool safe = e->cfg.safe_numeric != 0;
         void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter, (void *)&ntiles};
-        CK(cudaLaunchKernel(csp ? walk20_csp[safe ? 1 : 0] : cfg.f[(mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(tile_ptn), args, smem, e->stream));
+        CK(cudaLaunchKernel(csp ? csp_f[safe ? 1 : 0] : cfg.f[(mix ? 2 : 0) + (safe ? 1 : 0)], dim3(grid), dim3(tile_ptn), args, smem, e->stream));
     }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;
@@ -713,6 +800,7 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
                 if (c.kind == 0) { if (c.id < 0 || c.id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "op: taxon id out of range"); }
                 else if (c.kind == 1) { if (c.id < 0 || c.id >= e->cfg.nslots || c.id == op.dst_slot) return fail(e, B200LK_ERR_INVALID, "op: child slot invalid"); }
                 else return fail(e, B200LK_ERR_INVALID, "op: child kind must be 0 or 1");
+                if (!length_ok(e, c.length)) return fail(e, B200LK_ERR_INVALID, "op: child length must be >= 0 or -(len_slot)-1 of the device length table");
                 const int64_t eo = (int64_t)((size_t)nops * 2 * (e_sz + leaf_sz) + (size_t)xcur * (e_sz + leaf_sz));
                 ChildJob &j = hjobs[2 * nops + xcur];
                 j.length = c.length; j.e_off = eo; j.leaf_off = c.kind == 0 ? eo + (int64_t)e_sz : -1;
@@ -754,6 +842,7 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
         for (int k = 0; k < nops; k++) if (k == 0 || level[k] != level[k - 1]) level_start.push_back(k);
         level_start.push_back(nops);
     }
+    note_writes(e, ops, nops);
     CK(cudaMemcpyAsync(e->d_ops, hops, sizeof(DevOp) * nops, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync(e->d_jobs, hjobs, sizeof(ChildJob) * (2 * nops + nextra), cudaMemcpyHostToDevice, e->stream));
     if (nmc) CK(cudaMemcpyAsync(e->d_mchild, hmc, sizeof(MultiChild) * nmc, cudaMemcpyHostToDevice, e->stream));
@@ -830,7 +919,9 @@ static int repair_pattern_lh(b200lk_engine *e, bool save_log, double *logl) {
     }
     double tree_lh = 0.0;
     for (long long p = 0; p < e->P; p++) {
-        double ptn_lh = save_log ? lh[p] : std::log(lh[p]) + sc[p];
+        // the reference tests and sums _pattern_lh[ptn] as it stands (:3119-3130) — with save_log_value = false that is the raw
+        // likelihood, not its logarithm; reproduced to the letter
+        double ptn_lh = lh[p];
         if (!std::isfinite(ptn_lh)) {
             if (save_log) lh[p] = kLogScalingThreshold * 4;
             else { lh[p] = 1.0; sc[p] = kLogScalingThreshold * 4; }
@@ -866,6 +957,10 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
     if (!fuse) { k_vals<<<1, 256, 0, e->stream>>>(e->d, length, 0); e->launches++; e->last_launch[1]++; }
+    if (e->d.clv_state) {   // the root stage reads partial_lh = inv_evec . t
+        node_slot = eigen_slot(e, node_slot);
+        if (dad_kind == 1) dad_id = eigen_slot(e, dad_id, node_slot);
+    }
     if (e->d.asc) {   // +ASC: (tree_lh, prob_const) into slots 8..9, then the correction
         if (e->cfg.safe_numeric) k_root<true, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
         else k_root<false, true><<<nblocks, kTile, vsm, e->stream>>>(e->d, node_slot, dad_kind, dad_id, save_log_value, e->d_red, e->d_ticket, e->d_result + 8, length, fuse);
@@ -935,6 +1030,10 @@ extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_
 
 static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_id) {
     const int nblocks = (int)(e->Ppad / kTile);
+    if (e->d.clv_state) {
+        node_slot = eigen_slot(e, node_slot);
+        if (dad_kind == 1) dad_id = eigen_slot(e, dad_id, node_slot);
+    }
     if (e->cfg.safe_numeric) k_theta<true><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id);
     else k_theta<false><<<nblocks, kTile, 0, e->stream>>>(e->d, node_slot, dad_kind, dad_id);
     e->launches++;
@@ -1011,7 +1110,7 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     e->last_launch[1] += 1;
     prof_mark(e, 2);
     CK(cudaGetLastError());
-    e->pending = PEND_LOGL | PEND_SAVE_LOG;
+    e->pending = (e->pending & PEND_DERV) | PEND_LOGL | PEND_SAVE_LOG;   // a queued derivative result stays collectable
     e->pending_marks = 2;
     return 0;
 }
@@ -1190,10 +1289,19 @@ extern "C" int b200lk_em_posterior(b200lk_engine *e, int32_t wsl, int32_t add_in
     if (!new_prop) return 0;
     cudaSetDevice(e->cfg.device);
     const int nblocks = (int)(e->Ppad / kTile);
-    if (!e->d_post) {
-        CK(cudaMalloc(&e->d_post, sizeof(double) * (size_t)e->C * e->Ppad));
-        CK(cudaMalloc(&e->d_em_red, sizeof(double) * (size_t)e->C * nblocks));
-        CK(cudaMalloc(&e->d_em_out, sizeof(double) * (size_t)e->C));
+    if (!e->d_post || !e->d_em_red || !e->d_em_out) {   // all three or none
+        const int64_t before = e->device_bytes;
+        cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
+        e->d_post = e->d_em_red = e->d_em_out = nullptr;
+        int rc = dev_alloc(e, &e->d_post, (size_t)e->C * e->Ppad);
+        if (!rc) rc = dev_alloc(e, &e->d_em_red, (size_t)e->C * nblocks);
+        if (!rc) rc = dev_alloc(e, &e->d_em_out, (size_t)e->C);
+        if (rc) {
+            cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
+            e->d_post = e->d_em_red = e->d_em_out = nullptr;
+            e->device_bytes = before;
+            return rc;
+        }
     }
     const size_t smem = sizeof(double) * (kTile / 32) * K;
     if (smem > 200 * 1024) return fail(e, B200LK_ERR_INVALID, "em_posterior: too many categories");
@@ -1235,9 +1343,9 @@ extern "C" int b200lk_set_pattern_freq_from_posterior(b200lk_engine *dst, b200lk
 extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_theta, e->B, out); }
 extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
-    const double *src = e->d_partial + (size_t)slot * e->d.slot_stride;
-    if (!e->d.clv_f20) return read_interleaved_f64(e, src, e->B, out);
     cudaSetDevice(e->cfg.device);
+    const double *src = e->d_partial + (size_t)eigen_slot(e, slot) * e->d.slot_stride;
+    if (!e->d.clv_f20) return read_interleaved_f64(e, src, e->B, out);
     const size_t total = (size_t)e->P * e->B;
     int rc = ensure_scratch(e, total * sizeof(double));
     if (rc) return rc;

@@ -52,6 +52,9 @@ struct Dev {
     long long asc_step;      // Holder: the unobserved block is n groups of asc_step patterns, group s = pattern p with state s
     double *asc_tmp;         // Holder: (lh, df, ddf) of every unobserved pattern, three arrays of P - Pobs doubles
     int clv_f20;             // CLV slots use the 20-state fragment-major layout (clv20_off) instead of the warp-interleaved one
+    int clv_state;           // CLV slots hold the STATE-SPACE vector t (partial_lh = inv_evec . t), see b200lk_walk20ss.cuh
+    unsigned ss_lo, ss_hi;   // exponent words: max|t| < ss_lo => max|partial_lh| < 2^-256 for sure, >= ss_hi => certainly not
+    const double *inv_frag20;   // inv_evec as DMMA B fragments, [nmix][15][32] (k_inv_frag20)
     long long P, Ppad;
     long long slot_stride;   // Ppad * B   doubles per CLV slot
     long long scale_stride;  // Ppad * S   uint16 per slot
@@ -118,7 +121,24 @@ __global__ void __launch_bounds__(256) k_partial_info(Dev D, const ChildJob *job
         int m = c / D.denom;
         E[k] = D.evec[m * nn + rem] * s_exp[c * n + i];          // :1027
     }
-    if (job.leaf_off < 0) return;
+    if (job.leaf_off < 0) {
+        if (D.clv_state) {   // the child's CLV is the state-space vector t: fold its transform in, P_c = echild_c . inv_evec
+            __syncthreads();
+            for (int row = threadIdx.x; row < C * n; row += blockDim.x) {
+                double *er = E + (long long)row * n;
+                const double *iv = D.inv_evec + (long long)((row / n) / D.denom) * nn;
+                double erow[20], prow[20];
+                for (int i = 0; i < 20; i++) erow[i] = er[i];
+                for (int y = 0; y < 20; y++) {
+                    double a0 = 0.0, a1 = 0.0;
+                    for (int i = 0; i < 20; i += 2) { a0 = fma(erow[i], iv[i * 20 + y], a0); a1 = fma(erow[i + 1], iv[(i + 1) * 20 + y], a1); }
+                    prow[y] = a0 + a1;
+                }
+                for (int y = 0; y < 20; y++) er[y] = prow[y];
+            }
+        }
+        return;
+    }
     __syncthreads();
     double *leaf = D.opinfo + job.leaf_off;
     const int tip_block = n * D.nmix;
@@ -313,6 +333,10 @@ __device__ __forceinline__ void process_op_generic(const Dev &D, const DevOp &op
             lv[i] = v;   // reuse as output staging
             cmax = fmax(cmax, fabs(v));
         }
+        if (D.clv_state) {   // the slot keeps t; the underflow test above is the reference's, on partial_lh = inv_evec . t
+#pragma unroll
+            for (int i = 0; i < n; i++) lv[i] = tmp[i];
+        }
         if (SAFE) {
             unsigned sc = (lsc ? lsc[c * kWarp] : 0u) + (rsc ? rsc[c * kWarp] : 0u);
             if (check && cmax < kScalingThreshold) {
@@ -402,6 +426,7 @@ __device__ __forceinline__ void process_op_multi(const Dev &D, const DevOp &op, 
         }
     }
     if (!SAFE) osc[0] = (uint16_t)norm_scale;
+    if (D.clv_state) return;   // the slot keeps the state-space product
     for (int c = 0; c < C; c++) {
         const double *inv = D.inv_evec + (long long)(c / D.denom) * n * n;
         for (int x = 0; x < n; x++) lv[x] = out[at(c, x)];

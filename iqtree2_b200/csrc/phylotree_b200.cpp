@@ -149,6 +149,22 @@ void PhyloTree::check(int rc, const char *what) {
     }
 }
 
+// Engine calls that CONSUME a planned traversal: computeTraversalInfo has already marked the CLVs of traversal_info as computed
+// and re-assigned / recycled their slots, and a pipelined sweep has named device-resident lengths.  When the engine refuses
+// the call (invalid op, CUDA error, out of memory while growing its op buffers) none of those CLVs was written: roll the host
+// state back to "nothing computed" before the error propagates, so that a caller that carries on never evaluates stale slots.
+void PhyloTree::checkPlanned(int rc, const char *what) {
+    if (rc >= 0) return;
+    const std::string msg = std::string(what) + ": " + b200lk_last_error(engine_);
+    traversal_info.clear();
+    traversal_extra.clear();
+    dev_len_valid_.clear();
+    clearAllPartialLH();
+    if (mem_slots.enabled) mem_slots.init(max_lh_slots);
+    for (auto *n : neighbors_) if (mem_slots.enabled) n->slot = -1;
+    throw std::runtime_error(msg);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // inputs
 // ---------------------------------------------------------------------------------------------------------------
@@ -582,7 +598,7 @@ double PhyloTree::computeLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *
     double logl = 0.0;
     if (!traversal_info.empty()) theta_computed = false;
     pushExtraChildren();
-    check(b200lk_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
+    checkPlanned(b200lk_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
                              save_log_value, &logl), "branch_logl");
     traversal_info.clear();
     return logl;
@@ -607,7 +623,7 @@ void PhyloTree::computePartialLikelihood(PhyloNeighbor *dad_branch, PhyloNode *d
     computeTraversalInfo(dad_branch, dad);
     if (!traversal_info.empty()) theta_computed = false;
     pushExtraChildren();
-    check(b200lk_update_partials(engine_, traversal_info.data(), (int)traversal_info.size()), "update_partials");
+    checkPlanned(b200lk_update_partials(engine_, traversal_info.data(), (int)traversal_info.size()), "update_partials");
     traversal_info.clear();
 }
 
@@ -619,7 +635,7 @@ void PhyloTree::computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad,
     if (!traversal_info.empty()) theta_computed = false;
     if (!theta_computed) b200lk_theta_reset(engine_);
     pushExtraChildren();
-    check(b200lk_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length, df, ddf),
+    checkPlanned(b200lk_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length, df, ddf),
           "branch_derv");
     traversal_info.clear();
     theta_computed = true;
@@ -632,7 +648,7 @@ void PhyloTree::enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *da
     branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
     if (!traversal_info.empty()) theta_computed = false;
     pushExtraChildren();
-    check(b200lk_enqueue_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
+    checkPlanned(b200lk_enqueue_branch_logl(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length,
                                      save_log_value), "enqueue_branch_logl");
     traversal_info.clear();
 }
@@ -645,7 +661,7 @@ void PhyloTree::enqueueLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad)
     if (!traversal_info.empty()) theta_computed = false;
     if (!theta_computed) b200lk_theta_reset(engine_);
     pushExtraChildren();
-    check(b200lk_enqueue_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length),
+    checkPlanned(b200lk_enqueue_branch_derv(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id, length),
           "enqueue_branch_derv");
     traversal_info.clear();
     theta_computed = true;
@@ -818,7 +834,7 @@ void PhyloTree::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, bool clear
         branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
         int steps = 0;
         pushExtraChildren();
-    check(b200lk_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
+    checkPlanned(b200lk_newton_branch(engine_, traversal_info.data(), (int)traversal_info.size(), node_slot, dad_kind, dad_id,
                                    params.min_branch_length, current_len, params.max_branch_length, params.min_branch_length,
                                    maxNRStep, &optx, &steps), "newton_branch");
         traversal_info.clear();
@@ -872,7 +888,7 @@ bool PhyloTree::sweepPipelined(const std::vector<PhyloNode *> &nodes, const std:
             clearAllPartialLH();
             return false;
         }
-        check(rc, "enqueue_newton_branch");
+        checkPlanned(rc, "enqueue_newton_branch");
         traversal_info.clear();
         any = true;
         theta_computed = true;
@@ -882,7 +898,7 @@ bool PhyloTree::sweepPipelined(const std::vector<PhyloNode *> &nodes, const std:
     }
     std::vector<double> len(branches_.size());
     std::vector<int32_t> status(branches_.size());
-    check(b200lk_sweep_finish(engine_, (int)branches_.size(), len.data(), nullptr, status.data()), "sweep_finish");
+    checkPlanned(b200lk_sweep_finish(engine_, (int)branches_.size(), len.data(), nullptr, status.data()), "sweep_finish");
     for (size_t b = 0; b < branches_.size(); b++)
         if (dev_len_valid_[b]) branches_[b].first->length = branches_[b].second->length = len[b];
     dev_len_valid_.clear();

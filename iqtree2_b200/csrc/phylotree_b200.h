@@ -216,6 +216,7 @@ protected:
     void reorientPartialLh(PhyloNeighbor *dad_branch, PhyloNode *dad);      // tree/phylotree.cpp:5898-5912
     int computeSize(PhyloNeighbor *nei, PhyloNode *dad);
     void check(int rc, const char *what);
+    void checkPlanned(int rc, const char *what);   // check() + roll the host state back when a planned traversal was refused
     void freeTree();
     double brent_opt(double ax, double bx, double cx, double tol, double *foptx, double *f2optx, double fax, double fbx, double fcx);
     void branchEnds(PhyloNeighbor *&dad_branch, PhyloNode *&dad, int &node_slot, int &dad_kind, int &dad_id);

@@ -25,8 +25,17 @@ def shard_bounds(nptn: int, world: int, rank: int, tile: int = TILE):
 
 
 class ShardedLikelihood:
-    """Same call surface as the engine (branch_logl / branch_derv / logl_from_buffer / newton_branch ...), results
-    summed over ranks.  Ranks whose slice is empty (more ranks than tiles) take part in the collectives with zeros."""
+    """branch_logl / branch_derv / logl_from_buffer / newton_branch / em_posterior / gather_pattern_lh of the engine with the
+    results combined over ranks.  Ranks whose slice is empty (more ranks than tiles) take part in the collectives with zeros.
+
+    * a numerical status of ANY rank is everybody's: the engine's warning code is all-reduced with MAX (`last_status`), and when
+      a shard's derivative was not finite the reference's df = ddf = 0 (tree/phylokernelnew.h:2629-2632) is returned on every
+      rank instead of a sum over the healthy shards;
+    * newton_branch is the reference's minimizeNewton (utils/optimization.cpp:422-499) driven from the host with one
+      all-reduce of (df, ddf) per step: every rank walks the same iterates (the device-resident iteration of a single engine
+      would diverge between ranks);
+    * Lewis' +ASC (needs the global prob_const) and robust phylo (a global sort of the site log-likelihoods) are not separable
+      per rank: the constructor refuses them when world > 1."""
 
     def __init__(self, engine_cls, model, ntaxa, tips, ptn_freq, ptn_invar=None, group=None, device=None, **engine_kw):
         import torch
@@ -46,15 +55,37 @@ class ShardedLikelihood:
             self.engine.set_pattern_freq(np.ascontiguousarray(ptn_freq[self.lo:self.hi]))
             inv = np.zeros(self.local_nptn) if ptn_invar is None else np.ascontiguousarray(ptn_invar[self.lo:self.hi])
             self.engine.set_pattern_invar(inv)
-        self._buf = torch.zeros(3, dtype=torch.float64, device=self.device)
+        self._buf = torch.zeros(4, dtype=torch.float64, device=self.device)
+        self.last_status = 0
+        if self.world > 1 and (engine_kw.get("asc_type", 0) == 1 or engine_kw.get("robust", False)):
+            raise ValueError("Lewis' +ASC and robust phylo are not separable per pattern shard: use one engine")
+
+    def set_ascertainment(self, asc_type, num_unobserved, nsite):
+        if self.world > 1 and asc_type == 1:
+            raise ValueError("Lewis' +ASC needs the global prob_const: not available with pattern sharding")
+        if self.engine:
+            self.engine.set_ascertainment(asc_type, num_unobserved, nsite)
+
+    def set_robust_phylo(self, keep, median):
+        if self.world > 1 and (keep < 1.0 or median):
+            raise ValueError("robust phylo sorts all site log-likelihoods: not available with pattern sharding")
+        if self.engine:
+            self.engine.set_robust_phylo(keep, median)
 
     def _allreduce(self, vals):
+        """sum of vals over ranks; the engines' warning status travels in the same message (MAX via a second reduce only when
+        some rank reported one is not possible without knowing it: it is summed as a count instead)"""
+        st = float(getattr(self.engine, "last_status", 0) or 0) if self.engine else 0.0
         if self.world == 1:
+            self.last_status = int(st)
             return list(vals)
         t = self._buf
         t.zero_()
         t[:len(vals)] = self.torch.tensor(list(vals), dtype=self.torch.float64)
+        t[3] = 1.0 if st > 0 else 0.0
         self.dist.all_reduce(t, group=self.group)
+        self.last_status = int(st) if t[3].item() == 0 else max(int(st), 1)
+        self._any_warn = t[3].item() > 0
         return t[:len(vals)].tolist()
 
     def set_model(self, model):
@@ -75,7 +106,53 @@ class ShardedLikelihood:
 
     def branch_derv(self, ops, end_a, end_b, length):
         v = self.engine.branch_derv(ops, end_a, end_b, length) if self.engine else (0.0, 0.0)
-        return tuple(self._allreduce(v))
+        out = tuple(self._allreduce(v))
+        if self.world > 1 and self._any_warn:   # some shard's derivative was not finite: df = ddf = 0 everywhere (:2629-2632)
+            self.last_status = 2
+            return (0.0, 0.0)
+        return out
+
+    def newton_branch(self, ops, end_a, end_b, min_len, guess, max_len, tolerance, max_steps=100):
+        """Optimization::minimizeNewton (utils/optimization.cpp:422-499) on f = -df, f' = -ddf summed over the ranks."""
+        steps = 0
+
+        def fd(x, first):
+            nonlocal steps
+            steps += 1
+            df, ddf = self.branch_derv(ops if first else ops[:0], end_a, end_b, x)
+            return -df, -ddf
+        rts = min(max(guess, min_len), max_len)
+        f, df = fd(rts, True)
+        if not (np.isfinite(f) and np.isfinite(df)) or self.last_status == 2:
+            return rts, steps
+        if df >= 0.0 and abs(f) < tolerance:
+            return rts, steps
+        xl, xh = (rts, max_len) if f < 0.0 else (min_len, rts)
+        for j in range(1, max_steps + 1):
+            rts_old = rts
+            if df <= 0.0 or ((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0:
+                dx = 0.5 * (xh - xl)
+                rts = xl + dx
+                if xl == rts:
+                    return rts, steps
+            else:
+                dx = f / df
+                temp = rts
+                rts -= dx
+                if temp == rts:
+                    return rts, steps
+            if abs(dx) < tolerance or j == max_steps:
+                return rts_old, steps
+            f, df = fd(rts, False)
+            if not (np.isfinite(f) and np.isfinite(df)) or self.last_status == 2:
+                return rts, steps
+            if df > 0.0 and abs(f) < tolerance:
+                return rts, steps
+            if f < 0.0:
+                xl = rts
+            elif f > 0.0:
+                xh = rts
+        return rts, steps
 
     def logl_from_buffer(self, length):
         v = self.engine.logl_from_buffer(length) if self.engine else 0.0

@@ -42,6 +42,15 @@ struct b200lk_engine {
 };
 
 static char g_err[256] = "";
+/* fault injection for the host mirrors' error paths (tests/test_host_mirror_cpu.py): the n-th next call that takes an op list
+ * is refused BEFORE the oracle runs, as the CUDA engine refuses an invalid op or a failed allocation */
+static int g_fail_in = 0;
+void b200lk_test_fail_op_call_in(int n) { g_fail_in = n; }
+static int refused(const b200lk_op *ops, int32_t nops) {
+    (void)ops;
+    if (g_fail_in > 0 && nops > 0 && --g_fail_in == 0) { snprintf(g_err, sizeof g_err, "injected failure"); return 1; }
+    return 0;
+}
 static int wrap(b200lk_engine *e, int rc) {   /* the oracle: < 0 error, 1 = repaired underflow */
     e->calls++;
     return rc < 0 ? B200LK_ERR_INVALID : rc;
@@ -69,13 +78,18 @@ int b200lk_set_ascertainment(b200lk_engine *e, int32_t t, int64_t n, int64_t s) 
 int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t median) { return wrap(e, orc_set_robust_phylo(e->o, keep, median)); }
 int b200lk_set_extra_children(b200lk_engine *e, const b200lk_child *c, int32_t n) { return wrap(e, orc_set_extra_children(e->o, c, n)); }
 int b200lk_theta_reset(b200lk_engine *e) { return orc_theta_reset(e->o); }
-int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) { return wrap(e, orc_update_partials(e->o, ops, nops)); }
+int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    if (refused(ops, nops)) return B200LK_ERR_INVALID;
+    return wrap(e, orc_update_partials(e->o, ops, nops));
+}
 int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind, int32_t dad_id,
                        double length, int32_t save_log_value, double *logl) {
+    if (refused(ops, nops)) return B200LK_ERR_INVALID;
     return wrap(e, orc_branch_logl(e->o, ops, nops, node_slot, dad_kind, dad_id, length, save_log_value, logl));
 }
 int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind, int32_t dad_id,
                        double length, double *df, double *ddf) {
+    if (refused(ops, nops)) return B200LK_ERR_INVALID;
     if (nops > 0) orc_theta_reset(e->o);
     return wrap(e, orc_branch_derv(e->o, ops, nops, node_slot, dad_kind, dad_id, length, df, ddf));
 }

@@ -118,3 +118,30 @@ def test_rereading_the_tree_drops_every_cached_node_pointer(over_oracle):
         assert abs(g.compute_likelihood() - ll) < 1e-9
         np.testing.assert_allclose(g.compute_likelihood_derv(3, 0.05), d, rtol=1e-10)
     g.close()
+
+
+def test_refused_engine_call_rolls_the_host_state_back(over_oracle):
+    """A b200lk_* call that refuses a planned traversal must not leave the tree believing those CLVs exist (the planner marks
+    them computed before the call): the next evaluation has to recompute everything and give the right answer."""
+    import numpy as np
+    from cases import make_case
+    from iqtree2_b200.phylotree import PhyloTree
+    tree, model, pat, freq, inv = make_case("dna", ntaxa=12, nsites=200, seed=4)
+    for mem_save in (False, True):
+        t = PhyloTree()
+        t.set_alignment(tree.names, pat, freq, model)
+        t.set_model(model)
+        t.read_tree(tree.to_newick(fmt="%.17g"))
+        if mem_save:
+            t.set_mem_save(True, 0.5)
+        ll0 = t.compute_likelihood_branch(3)
+        t.set_branch_length(7, 0.23)            # invalidates the partials that saw branch 7
+        want = None
+        over_oracle.b200lk_test_fail_op_call_in(1)
+        with pytest.raises(Exception, match="branch_logl"):
+            t.compute_likelihood_branch(3)
+        ll1 = t.compute_likelihood_branch(3)    # must not reuse never-written CLVs
+        t.clear_all_partial_lh()
+        want = t.compute_likelihood_branch(3)
+        assert abs(ll1 - want) < 1e-9 and abs(ll1 - ll0) > 1e-3
+        t.close()

@@ -52,8 +52,17 @@ def _worker(rank, world, port, out):
     ll2 = sh.logl_from_buffer(L)
     plh = sh.gather_pattern_lh()
     prop = sh.em_posterior(2, True)          # E-step of RateFree::optimizeWithEM over both shards
+    # host-driven Newton-Raphson with an all-reduce per step: both ranks must walk the same iterates
+    sh.theta_reset()
+    xopt, nsteps = sh.newton_branch(ops[:0], a, b, 1e-6, L, 10.0, 1e-6)
+    # a shard whose derivative is not finite zeroes (df, ddf) on EVERY rank (tree/phylokernelnew.h:2629-2632)
+    inv2 = inv.copy()
+    inv2[5] = np.nan                          # a pattern of rank 0's slice
+    sh2 = ShardedLikelihood(OracleEngine, model, tree.ntaxa, pat, freq, inv2)
+    d_bad = sh2.branch_derv(ops, a, b, L)
+    st_bad = sh2.last_status
     if rank == 0:
-        np.save(out, np.concatenate([[ll, df, ddf, ll2], prop, plh]))
+        np.save(out, np.concatenate([[ll, df, ddf, ll2], prop, [xopt, nsteps, d_bad[0], d_bad[1], st_bad], plh]))
     dist.destroy_process_group()
 
 
@@ -72,4 +81,11 @@ def test_two_rank_gloo_matches_single_engine(tmp_path):
     assert abs(res[0] - ll) < 1e-8 and abs(res[3] - ll) < 1e-8
     np.testing.assert_allclose(res[1:3], [df, ddf], rtol=1e-10)
     np.testing.assert_allclose(res[4:8], o.em_posterior(2, True)[0], rtol=1e-12)
-    np.testing.assert_allclose(res[8:], o.get_pattern_lh(), rtol=1e-13)
+    np.testing.assert_allclose(res[13:], o.get_pattern_lh(), rtol=1e-13)
+    # the optimum of the sharded Newton iteration is a root of the single engine's derivative
+    xopt, nsteps = res[8], res[9]
+    assert nsteps >= 2
+    d_at = o.branch_derv(ops[:0], a, b, float(xopt))
+    d_l = o.branch_derv(ops[:0], a, b, L)
+    assert abs(d_at[0]) < 1e-3 * max(1.0, abs(d_l[0])) or xopt in (1e-6, 10.0)
+    assert res[10] == 0.0 and res[11] == 0.0 and res[12] == 2
