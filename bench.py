@@ -685,7 +685,7 @@ def plan_mem_save(tree, model, ntaxa, mem_frac):
     pt.set_plan_only(True)
     pt.set_alignment(tree.names, np.zeros((ntaxa, 1), dtype=np.uint8), np.ones(1), model)   # planning needs no patterns
     pt.set_model(model)
-    pt.read_tree(tree.to_newick())
+    pt.read_tree(tree.to_newick(fmt="%.17g"))   # the exact branch lengths
     pt.set_mem_save(True, mem_frac)
     nslots = pt.max_lh_slots + 2
     pa, pb, _ = pt.branches()

@@ -15,6 +15,11 @@
  *     concurrently from different host threads (PhyloSuperTree calls partition trees in an omp parallel for,
  *     tree/phylosupertreeplen.cpp:380-409); calls on the same engine must be serialised by the caller;
  *   - there is NO CPU fallback: without a CUDA device b200lk_create fails.
+ *   - multi-device engines (cfg.device = -N): every entry point takes them; patterns are sharded, the per-evaluation scalars
+ *     are summed on the host in device order (the single-process form of the all-reduce of tree/phylokernelnew.h:2375-2379,
+ *     2747-2748); per-pattern read-backs gather.  Not separable per shard and refused with B200LK_ERR_STATE: +ASC, robust phylo,
+ *     b200lk_enqueue_newton_branch / b200lk_sweep_finish (use b200lk_newton_branch: one reduction per Newton step),
+ *     b200lk_set_stream, b200lk_set_pattern_freq_from_posterior.
  *
  * Host-visible layouts are the reference's with SIMD width V=1 (SURVEY §8a "Layout crib"):
  *   partial_lh[p*B + c*n + i], B = n*ncat_mix, c = m*ncat + r;   scale_num NORM_LH [p], SAFE_LH [p*C + c];
@@ -56,7 +61,8 @@ typedef struct b200lk_config {
     int32_t ntaxa;          /* aln->getNSeq() */
     int64_t nptn;           /* patterns owned by this engine (aln->size(), or this GPU's slice of it) */
     int32_t nslots;         /* CLV slots: (ntaxa-2) for LM_PER_NODE + 2 NNI spares (tree/phylotree.cpp:1071-1104) */
-    int32_t device;         /* CUDA device ordinal */
+    int32_t device;         /* CUDA device ordinal; -N (N >= 2): the first N devices, one engine per device over contiguous pattern
+                               slices behind this one handle (see "multi-device engines" below) */
 } b200lk_config;
 
 /* One child of a TraversalInfo entry: a leaf (kind 0, id = alignment row) or an internal CLV (kind 1, id = slot). */
@@ -200,6 +206,29 @@ int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t
                                  int32_t dad_id, double min_len, double guess, double max_len, double tolerance,
                                  int32_t max_steps, int32_t len_slot);
 int b200lk_sweep_finish(b200lk_engine *e, int32_t nslots, double *lengths, int32_t *evaluations, int32_t *status);
+
+/* ---- grouped evaluation: the partition trees of a PhyloSuperTree in O(1) launches ---------------------------------------------
+ * PhyloSuperTreePlen evaluates its partition trees from `#pragma omp parallel for` loops over one pooled arena with per-partition
+ * offsets (tree/phylosupertreeplen.cpp:282-290, 322-341, 380-409; arena :1624-1720).  A group is that arena's descriptor table:
+ * engines on ONE device, evaluated together — every call takes one op list and one evaluation branch PER MEMBER (arrays of
+ * length n, member order = creation order) and queues one launch per kernel type for all members on the group's stream;
+ * b200lk_group_finish waits once and hands out every member's scalars (NULL arrays allowed; status[k] = member k's warning code).
+ * After b200lk_group_create the members' own entry points keep working and are ordered on the group's stream too; calls on a
+ * group and its members are serialised by the caller.  A member the grouped kernels do not cover (+ASC, robust phylo, blocks
+ * above 512 doubles, state counts other than 4 and 20, multi-device engines are refused) is queued through its own entry points
+ * by the same calls: same results, its own launches.  Destroy the group before its members. */
+typedef struct b200lk_group b200lk_group;
+int b200lk_group_create(b200lk_engine *const *engines, int32_t n, b200lk_group **out);
+void b200lk_group_destroy(b200lk_group *g);
+const char *b200lk_group_last_error(const b200lk_group *g); /* g may be NULL: error of the last failed create */
+int b200lk_group_enqueue_branch_logl(b200lk_group *g, const b200lk_op *const *ops, const int32_t *nops, const int32_t *node_slot,
+                                     const int32_t *dad_kind, const int32_t *dad_id, const double *length, int32_t save_log_value);
+int b200lk_group_enqueue_branch_derv(b200lk_group *g, const b200lk_op *const *ops, const int32_t *nops, const int32_t *node_slot,
+                                     const int32_t *dad_kind, const int32_t *dad_id, const double *length);
+int b200lk_group_enqueue_logl_from_buffer(b200lk_group *g, const double *length);
+int b200lk_group_finish(b200lk_group *g, double *logl, double *df, double *ddf, int32_t *status);
+/* kernel launches issued by the group and its members since creation */
+int64_t b200lk_group_launch_count(const b200lk_group *g);
 
 /* ---- read-backs (computePatternLikelihood & friends, tree/phylotree.cpp:1458-1603; parity dumps) -------------- */
 int b200lk_get_pattern_lh(b200lk_engine *e, double *out /* [nptn] */);

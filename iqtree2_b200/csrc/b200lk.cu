@@ -7,6 +7,9 @@
 #include "b200lk.h"
 #include "b200lk_kernels.cuh"
 #include "b200lk_walk20ss.cuh"
+#include "b200lk_walk20v2.cuh"
+#include "b200lk_walk4.cuh"
+#include "b200lk_group.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -59,6 +62,7 @@ struct b200lk_engine {
     int num_sms = 148;
     int info_smem_optin = 0;
     bool walk20_attr_set = false;
+    unsigned walk20v2_attr = 0;   // bit per (NW, CS) configuration of k_walk_n20v2 whose attributes are set
     // EM E-step (b200lk_em_posterior): posteriors [K][Ppad], per-block partial sums, the K sums
     double *d_post = nullptr, *d_em_red = nullptr, *d_em_out = nullptr;
     int post_K = 0;
@@ -100,6 +104,13 @@ struct b200lk_engine {
     MultiChild *d_mchild = nullptr;
     bool has_multi = false;
     int pending = 0, pending_marks = 0;   // results queued by b200lk_enqueue_*, collected by b200lk_finish
+    int last_finish_status = 0;
+    struct b200lk_group *group = nullptr;   // the group this engine is a member of (b200lk_group.inc)
+    int group_index = -1;
+    bool last_derv_nonfinite = false;
+    // multi-device engine (b200lk_multi.inc): one shard engine per device over pattern slices [shard_lo[k], shard_lo[k+1])
+    std::vector<b200lk_engine *> shards;
+    std::vector<long long> shard_lo;
     std::string err;
 };
 
@@ -147,15 +158,22 @@ static int dev_alloc(b200lk_engine *e, T **ptr, size_t count) {
     return 0;
 }
 
+#include "b200lk_multi.inc"
+
 extern "C" int b200lk_abi_version(void) { return B200LK_ABI_VERSION; }
 
 extern "C" const char *b200lk_last_error(const b200lk_engine *e) { return e ? e->err.c_str() : g_create_err.c_str(); }
 
-extern "C" int64_t b200lk_device_bytes(const b200lk_engine *e) { return e->device_bytes; }
-extern "C" int64_t b200lk_launch_count(const b200lk_engine *e) { return e->launches; }
+extern "C" int64_t b200lk_device_bytes(const b200lk_engine *e) {
+    if (!e->shards.empty()) { int64_t t = 0; for (auto *x : e->shards) t += x->device_bytes; return t; } return e->device_bytes; }
+extern "C" int64_t b200lk_launch_count(const b200lk_engine *e) {
+    if (!e->shards.empty()) { int64_t t = 0; for (auto *x : e->shards) t += x->launches; return t; } return e->launches; }
 
+static void group_detach(b200lk_engine *e);
 extern "C" void b200lk_destroy(b200lk_engine *e) {
+    if (e && !e->shards.empty()) { mg_destroy(e); return; }
     if (!e) return;
+    if (e->group) group_detach(e);
     cudaSetDevice(e->cfg.device);
     if (e->stream) sync_stream(e);
     cudaFree(e->d_tips); cudaFree(e->d_freq); cudaFree(e->d_invar); cudaFree(e->d_model); cudaFree(e->d_partial);
@@ -174,6 +192,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
 }
 
 extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
+    if (cfg && cfg->device < 0) { *out = nullptr; if (cfg->nstates < 1 || cfg->ncat < 1 || cfg->nmix < 1 || cfg->nptn < 1) { g_create_err = "b200lk_create: invalid configuration"; return B200LK_ERR_INVALID; } return mg_create(cfg, out); }
     *out = nullptr;
     if (!cfg || cfg->nstates < 1 || cfg->ncat < 1 || cfg->nmix < 1 || cfg->ntaxa < 2 || cfg->nptn < 1 || cfg->nslots < 1 ||
         cfg->state_unknown < cfg->nstates || cfg->state_unknown > 255) {
@@ -211,9 +230,9 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     e->stream = e->own_stream;
     for (auto &ev : e->ev) cudaEventCreate(&ev);
     const long long Ppad = e->Ppad;
-    // 20-state engines keep state-space CLVs (b200lk_walk20ss.cuh); B200LK_EIGEN20=1 keeps the eigen-space walker (A/B)
+    // 20-state engines keep state-space CLVs in the fragment-major layout (b200lk_walk20ss.cuh)
     const bool f20 = n == 20 && e->C % cfg->nmix == 0;
-    const bool state_space = f20 && !(getenv("B200LK_EIGEN20") && atoi(getenv("B200LK_EIGEN20")) != 0);
+    const bool state_space = f20;
     e->nslots_total = cfg->nslots + (state_space ? 2 : 0);
     e->slot_ver.assign(e->nslots_total, 0);
     TRY(dev_alloc(e, &e->d_tips, (size_t)cfg->ntaxa * Ppad));
@@ -286,12 +305,14 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
 }
 
 extern "C" int b200lk_set_stream(b200lk_engine *e, void *cuda_stream) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "set_stream");
     sync_stream(e);
     e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
     return 0;
 }
 
 extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_schedule(e->shards[k], schedule); });
     if (schedule >= 10 && schedule < 20) {   // development switch: kernel variant of the walker schedule (A/B measurements)
         e->kernel_variant = schedule - 10;
         e->walk20_attr_set = false;
@@ -303,6 +324,7 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
 }
 
 extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
+    if (!e->shards.empty()) { if (asc_type != 0) MG_UNSUPPORTED(e, "+ASC"); return mg_each(e, [&](int k) { return b200lk_set_ascertainment(e->shards[k], 0, 0, nsite); }); }
     if (asc_type < 0 || asc_type > 2) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE), 2 = Holder (ASC_VARIANT_MISSING)");
     if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
     if (asc_type && (e->robust_keep < 1.0 || e->robust_median)) return fail(e, B200LK_ERR_INVALID, "+ASC not supported with robust phylo");
@@ -326,6 +348,7 @@ extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int6
 
 // --robust-phy / --robust-median (Params::robust_phy_keep, robust_median; tree/phylokernelnew.h:3134-3173)
 extern "C" int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t median) {
+    if (!e->shards.empty()) { if (keep < 1.0 || median) MG_UNSUPPORTED(e, "robust phylo"); return 0; }
     if (!(keep > 0.0 && keep <= 1.0) || (keep < 1.0 && median)) return fail(e, B200LK_ERR_INVALID, "robust phylo: 0 < keep <= 1, and keep < 1 excludes median");
     const bool on = keep < 1.0 || median;
     if (on && e->d.asc) return fail(e, B200LK_ERR_INVALID, "+ASC not supported with robust phylo");   // :3136-3138
@@ -349,20 +372,24 @@ extern "C" int b200lk_set_robust_phylo(b200lk_engine *e, double keep, int32_t me
 }
 
 extern "C" int b200lk_set_extra_children(b200lk_engine *e, const b200lk_child *children, int32_t n) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_extra_children(e->shards[k], children, n); });
     if (n < 0 || (n > 0 && !children)) return fail(e, B200LK_ERR_INVALID, "set_extra_children: invalid arguments");
     e->extra_children.assign(children, children + n);
     return 0;
 }
 
 extern "C" int b200lk_set_reference_quirks(b200lk_engine *e, int32_t mask) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_reference_quirks(e->shards[k], mask); });
     if (mask & ~B200LK_QUIRK_DOTTRIPLE_ODD) return fail(e, B200LK_ERR_INVALID, "unknown quirk bit");
     e->d.quirks = mask;
     return 0;
 }
 
-extern "C" int b200lk_set_profiling(b200lk_engine *e, int32_t on) { e->profiling = on != 0; return 0; }
+extern "C" int b200lk_set_profiling(b200lk_engine *e, int32_t on) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_profiling(e->shards[k], on); }); e->profiling = on != 0; return 0; }
 
 extern "C" int b200lk_last_timing(b200lk_engine *e, float ms[5], int32_t launches[3]) {
+    if (!e->shards.empty()) { for (int i = 0; i < 5; i++) ms[i] = 0.f; for (int i = 0; i < 3; i++) launches[i] = 0; for (auto *x : e->shards) { for (int i = 0; i < 5; i++) ms[i] = std::max(ms[i], x->last_ms[i]); for (int i = 0; i < 3; i++) launches[i] += x->last_launch[i]; } return 0; }
     for (int i = 0; i < 5; i++) ms[i] = e->last_ms[i];
     for (int i = 0; i < 3; i++) launches[i] = e->last_launch[i];
     return 0;
@@ -372,6 +399,7 @@ extern "C" int b200lk_last_timing(b200lk_engine *e, float ms[5], int32_t launche
 // inputs
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int b200lk_set_tip_states(b200lk_engine *e, const uint8_t *states) {
+    if (!e->shards.empty()) return mg_set_tip_states(e, states);
     cudaSetDevice(e->cfg.device);
     const size_t total = (size_t)e->cfg.ntaxa * e->P;
     for (size_t k = 0; k < total; k++)
@@ -382,6 +410,7 @@ extern "C" int b200lk_set_tip_states(b200lk_engine *e, const uint8_t *states) {
 }
 
 extern "C" int b200lk_set_pattern_freq(b200lk_engine *e, const double *f) {
+    if (!e->shards.empty()) return mg_scatter(e, f, 1, [](b200lk_engine *x, const double *p) { return b200lk_set_pattern_freq(x, p); });
     cudaSetDevice(e->cfg.device);
     e->h_freq.assign(f, f + e->P);
     CK(cudaMemcpyAsync(e->d_freq, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
@@ -390,6 +419,7 @@ extern "C" int b200lk_set_pattern_freq(b200lk_engine *e, const double *f) {
 }
 
 extern "C" int b200lk_set_pattern_invar(b200lk_engine *e, const double *f) {
+    if (!e->shards.empty()) return mg_scatter(e, f, 1, [](b200lk_engine *x, const double *p) { return b200lk_set_pattern_invar(x, p); });
     cudaSetDevice(e->cfg.device);
     CK(cudaMemcpyAsync(e->d_invar, f, sizeof(double) * e->P, cudaMemcpyHostToDevice, e->stream));
     CK(sync_stream(e));
@@ -399,6 +429,7 @@ extern "C" int b200lk_set_pattern_invar(b200lk_engine *e, const double *f) {
 
 extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec,
                                 const double *mix_weight) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_model(e->shards[k], eval, evec, inv_evec, mix_weight); });
     cudaSetDevice(e->cfg.device);
     const int n = e->cfg.nstates, nmix = e->cfg.nmix;
     CK(cudaMemcpyAsync((void *)e->d.eval, eval, sizeof(double) * nmix * n, cudaMemcpyHostToDevice, e->stream));
@@ -437,6 +468,7 @@ extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const doub
 }
 
 extern "C" int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_rates(e->shards[k], cat_rate, cat_prop); });
     cudaSetDevice(e->cfg.device);
     CK(cudaMemcpyAsync((void *)e->d.cat_rate, cat_rate, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
     CK(cudaMemcpyAsync((void *)e->d.cat_prop, cat_prop, sizeof(double) * e->cfg.ncat, cudaMemcpyHostToDevice, e->stream));
@@ -530,13 +562,25 @@ static bool use_walk4(const b200lk_engine *e) {
            e->cfg.state_unknown < kMaxLeafRows4 && e->h_evec.size() == 16;
 }
 
-static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
-    WalkJob4 *hj = (WalkJob4 *)stage_acquire(e);
+// ... and k_walk_n4<C> (b200lk_walk4.cuh) every other single-class 4-state model: no rate heterogeneity, +G8, +R2 .. +R10, ...
+struct Walk4Cfg { int C; const void *f[2]; };
+#define W4CFG(C) { C, { (const void *)k_walk_n4<C, false>, (const void *)k_walk_n4<C, true> } }
+static const Walk4Cfg walk4_cfgs[] = { W4CFG(1), W4CFG(2), W4CFG(3), W4CFG(4), W4CFG(5), W4CFG(6), W4CFG(7), W4CFG(8), W4CFG(9), W4CFG(10), W4CFG(12), W4CFG(16) };
+static const Walk4Cfg *walk4n_cfg(const b200lk_engine *e) {
+    if (e->schedule == 1 || e->cfg.nstates != 4 || e->cfg.nmix != 1 || e->cfg.state_unknown >= kMaxLeafRows4 || e->h_evec.size() != 16) return nullptr;
+    if (e->C == 4 && e->kernel_variant != 5) return nullptr;   // four categories: k_walk_n4c4 (variant 5 = the templated kernel, A/B)
+    for (const Walk4Cfg &c : walk4_cfgs) if (c.C == e->C) return &c;
+    return nullptr;
+}
+
+// b200lk_op[] -> WalkJob4[]: child A is the CLV that stays in registers (chained from the previous op when it is its parent)
+static int fill_jobs4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, WalkJob4 *hj) {
     int prev_dst = -1;
     for (int k = 0; k < nops; k++) {
         const b200lk_op &op = ops[k];
         int rc = validate_op(e, op);
         if (rc) return rc;
+        if (op.reserved != 0) return fail(e, B200LK_ERR_INVALID, "multifurcating ops are not served by the walkers");
         const b200lk_child *A = &op.left, *B = &op.right;
         WalkJob4 &j = hj[k];
         if (A->kind == 0 && B->kind == 0) { j.ncase = 0; j.loadA = 0; }
@@ -554,12 +598,34 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
         j.dst = op.dst_slot; j.pad = 0;
         prev_dst = op.dst_slot;
     }
+    return 0;
+}
+
+static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, const Walk4Cfg *wcfg) {
+    WalkJob4 *hj = (WalkJob4 *)stage_acquire(e);
+    int rcj = fill_jobs4(e, ops, nops, hj);
+    if (rcj) return rcj;
     WalkJob4 *dj = (WalkJob4 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob4) * nops, cudaMemcpyHostToDevice, e->stream));
-    k_walk_info_n4c4<<<nops, 64, 0, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
     Model4 M;
     for (int k = 0; k < 16; k++) { M.evec[k] = e->h_evec[k]; M.inv[k] = e->h_inv_evec[k]; }
     const long long ntiles = e->Ppad / kTile;
+    if (wcfg) {   // any number of categories: k_walk_n4<C>
+        k_walk_info_n4<<<nops, 128, sizeof(double) * 8 * e->C, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+        const int per_sm = e->C <= 4 ? 4 : e->C <= 8 ? 3 : 2;
+        const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * per_sm);
+        if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+        void *args[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
+        CK(cudaLaunchKernel(wcfg->f[e->cfg.safe_numeric ? 1 : 0], dim3(grid), dim3(kTile), args, 0, e->stream));
+        if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+        e->partials_timed = e->profiling;
+        e->launches += 2;
+        e->last_launch[0] += 2;
+        CK(cudaGetLastError());
+        e->theta_computed = false;
+        return 0;
+    }
+    k_walk_info_n4c4<<<nops, 64, 0, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
     const int grid = (int)std::min<long long>(ntiles, (long long)e->num_sms * 4);   // 4 resident CTAs per SM (128 regs/thread)
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
@@ -593,7 +659,7 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
 // fused classes
 static int walk20_cpb(const b200lk_engine *e) { return e->C / e->cfg.nmix; }   // categories per class block
 static size_t walk20_stage_doubles(const b200lk_engine *e) {
-    return e->d.clv_state ? ss_stage_doubles(walk20_cpb(e), e->cfg.state_unknown) : stage20_doubles(walk20_cpb(e), e->cfg.state_unknown);
+    return ss_stage_doubles(walk20_cpb(e), e->cfg.state_unknown);
 }
 static bool use_walk20(const b200lk_engine *e) {
     return e->schedule != 1 && e->cfg.nstates == 20 && e->C % e->cfg.nmix == 0 && e->h_evec.size() == (size_t)400 * e->cfg.nmix &&
@@ -608,58 +674,137 @@ static void note_writes(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
 
 // state-space engines: the slot that holds partial_lh = inv_evec . t of CLV `slot` (one of two scratch slots behind the caller's;
 // converted on the stream when the cached copy is stale).  Eigen-space engines: the slot itself.
-static int eigen_slot(b200lk_engine *e, int slot, int keep = -1) {
+// the scratch slot for `slot`; *convert = whether its content has to be (re)computed (the caller launches the conversion)
+static int eigen_slot_plan(b200lk_engine *e, int slot, int keep, bool *convert) {
+    *convert = false;
     if (!e->d.clv_state) return slot;
     for (int k = 0; k < 2; k++)
         if (e->eig_src[k] == slot && e->eig_ver[k] == e->slot_ver[slot]) return e->cfg.nslots + k;
     int k = e->eig_next;
     if (e->cfg.nslots + k == keep) k ^= 1;   // do not evict the other end of the same branch
     e->eig_next = k ^ 1;
-    const long long nblocks = e->Ppad / 32;
-    const int grid = (int)std::min<long long>((nblocks + 3) / 4, (long long)e->num_sms * 8);
-    k_clv20_to_eigen<<<grid, 128, 0, e->stream>>>(e->d, slot, e->cfg.nslots + k);
-    e->launches++;
     e->eig_src[k] = slot;
     e->eig_ver[k] = e->slot_ver[slot];
+    *convert = true;
     return e->cfg.nslots + k;
 }
+static int eigen_slot(b200lk_engine *e, int slot, int keep = -1) {
+    bool convert;
+    const int dst = eigen_slot_plan(e, slot, keep, &convert);
+    if (convert) {
+        const long long nblocks = e->Ppad / 32;
+        const int grid = (int)std::min<long long>((nblocks + 3) / 4, (long long)e->num_sms * 8);
+        k_clv20_to_eigen<<<grid, 128, 0, e->stream>>>(e->d, slot, dst);
+        e->launches++;
+    }
+    return dst;
+}
 
-
-// k_walk_n20_mma configurations: {warps per CTA, kernels [MIX*2 + SAFE]}; index = kernel_variant (b200lk_set_schedule(e, 10 + v))
 struct Walk20Cfg { int nw; const void *f[4]; };
-#define W20CFG(NW, BSM, MINB)                                                                                          \
-    { NW, { (const void *)k_walk_n20_mma<false, false, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, false, NW, BSM, MINB>, \
-            (const void *)k_walk_n20_mma<false, true, NW, BSM, MINB>, (const void *)k_walk_n20_mma<true, true, NW, BSM, MINB> } }
-static const Walk20Cfg walk20_cfgs[] = {
-    { 4, { (const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, false, true>, (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, false, true>,
-           (const void *)k_walk_n20_mma<false, true, 4, 0, 3, 0, false, true>, (const void *)k_walk_n20_mma<true, true, 4, 0, 3, 0, false, true> } },
-                         // 0 (default): 12 warps/SM, both matrices as register-resident B fragments, staging by TMA bulk load
-    W20CFG(8, 2, 2),     // 1: 16 warps/SM, inv_evec fragments from shared memory
-    W20CFG(8, 3, 2),     // 2: 16 warps/SM, both matrices from shared memory
-    W20CFG(6, 3, 3),     // 3: 18 warps/SM
-    W20CFG(4, 0, 3),     // 4: as 0 with fixed 128-pattern tiles (A/B of the balanced tiling)
-    W20CFG(10, 3, 2),    // 5: 20 warps/SM
-    W20CFG(4, 0, 3),     // 6: as 0 with cp.async staging (16-byte copies by every thread; 6.63 vs 6.50 ms on config 3)
-#ifdef B200LK_DIAG
-#define W20DBG(DBG) { 4, { (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, \
-                           (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG>, (const void *)k_walk_n20_mma<false, false, 4, 0, 3, DBG> } }
-    W20DBG(1), W20DBG(2), W20DBG(3), W20DBG(4),   // 7: no stores, 8: no loads, 9: neither, 10: no DMMAs (wrong results; diagnosis)
-#endif
+// k_walk_n20ss configurations {warps per CTA, kernels [MIX*2 + SAFE]}; index = kernel_variant (b200lk_set_schedule(e, 10 + v));
+// and the category-split form [SAFE]
+#define W20SS(NW, MINB)                                                                                                        \
+    { NW, { (const void *)k_walk_n20ss<false, false, NW, MINB, false>, (const void *)k_walk_n20ss<true, false, NW, MINB, false>, \
+            (const void *)k_walk_n20ss<false, true, NW, MINB, false>, (const void *)k_walk_n20ss<true, true, NW, MINB, false> } }
+static const Walk20Cfg walk20ss_cfgs[] = {
+    W20SS(4, 3),   // 0 (default): 4 warps per CTA, 3 CTAs per SM (168 registers)
+    W20SS(4, 2),   // 1: 8 warps per SM, no register cap pressure
+    W20SS(6, 2),   // 2: 12 warps per SM in 2 CTAs: a staging block serves 6 pattern blocks
+    W20SS(8, 1),   // 3: 8 warps per SM in one CTA
+    W20SS(4, 3),   // 4: as 0 without the category-split form for small problems (A/B)
 };
-constexpr int kNumWalk20Cfgs = (int)(sizeof(walk20_cfgs) / sizeof(walk20_cfgs[0]));
-// category-split form for small problems (single class, >= 2 categories, fewer 32-pattern blocks than resident CTAs) [SAFE]
-static const void *const walk20_csp[2] = {(const void *)k_walk_n20_mma<false, false, 4, 0, 3, 0, true, true>,
-                                          (const void *)k_walk_n20_mma<true, false, 4, 0, 3, 0, true, true>};
-
-// k_walk_n20ss [MIX*2 + SAFE], 4 warps per CTA, 3 CTAs per SM; and its category-split form [SAFE]
-static const void *const walk20ss_f[4] = {(const void *)k_walk_n20ss<false, false, 4, 3, false>, (const void *)k_walk_n20ss<true, false, 4, 3, false>,
-                                          (const void *)k_walk_n20ss<false, true, 4, 3, false>, (const void *)k_walk_n20ss<true, true, 4, 3, false>};
+constexpr int kNumWalk20ssCfgs = (int)(sizeof(walk20ss_cfgs) / sizeof(walk20ss_cfgs[0]));
 static const void *const walk20ss_csp[2] = {(const void *)k_walk_n20ss<false, false, 4, 3, true>, (const void *)k_walk_n20ss<true, false, 4, 3, true>};
+
+// k_walk_n20v2 [staging depth 3 / 2][NW index][CS index][MIX*2 + SAFE]; MIX only with CS = 1
+#define W20V2(NW, CS, SD) { (const void *)k_walk_n20v2<false, false, NW, CS, SD>, (const void *)k_walk_n20v2<true, false, NW, CS, SD>, \
+                            CS == 1 ? (const void *)k_walk_n20v2<false, true, NW, 1, SD> : nullptr, CS == 1 ? (const void *)k_walk_n20v2<true, true, NW, 1, SD> : nullptr }
+static const int walk20v2_nw[3] = {12, 8, 4};
+static const int walk20v2_cs[3] = {1, 2, 4};
+static const void *const walk20v2_f[2][3][3][4] = {
+    {{W20V2(12, 1, 3), W20V2(12, 2, 3), W20V2(12, 4, 3)}, {W20V2(8, 1, 3), W20V2(8, 2, 3), W20V2(8, 4, 3)}, {W20V2(4, 1, 3), W20V2(4, 2, 3), W20V2(4, 4, 3)}},
+    {{W20V2(12, 1, 2), W20V2(12, 2, 2), W20V2(12, 4, 2)}, {W20V2(8, 1, 2), W20V2(8, 2, 2), W20V2(8, 4, 2)}, {W20V2(4, 1, 2), W20V2(4, 2, 2), W20V2(4, 4, 2)}}};
+constexpr size_t kV2SmemBudget = 227 * 1024 - 7 * 1024;   // dynamic shared memory a v2 CTA may ask for (static: mbarriers, NORM_LH maxima <= 6.2 KB)
+
+// (NW index, staging depth) that fits: prefer 12 warps, then the deeper staging ring
+static bool walk20v2_pick(int cpb, int su, int &wi, int &sd, size_t &smem) {
+    for (wi = 0; wi < 3; wi++)
+        for (sd = 3; sd >= 2; sd--) {
+            smem = v2_smem_doubles(cpb, su, walk20v2_nw[wi], sd) * sizeof(double);
+            if (smem <= kV2SmemBudget) return true;
+        }
+    return false;
+}
+
+// the second-generation walker (b200lk_walk20v2.cuh): one CTA per SM, TMA rings; returns 1 when this engine / op list cannot use it
+static int enqueue_walk20v2(b200lk_engine *e, int32_t nops, const WalkJob20 *dj) {
+    const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
+    const bool mix = nblk > 1, safe = e->cfg.safe_numeric != 0;
+    int wi, sd;
+    size_t smem;
+    if (!walk20v2_pick(cpb, e->cfg.state_unknown, wi, sd, smem)) return 1;
+    if (e->kernel_variant == 1 && wi < 1) { wi = 1; sd = 3; smem = v2_smem_doubles(cpb, e->cfg.state_unknown, 8, 3) * sizeof(double); }   // A/B and parity coverage: 8 / 4 warps per CTA
+    if (e->kernel_variant == 2) { wi = 2; sd = 2; smem = v2_smem_doubles(cpb, e->cfg.state_unknown, 4, 2) * sizeof(double); }                 // ... and the 2-deep staging ring
+    if (smem > kV2SmemBudget) return 1;
+    const int nw = walk20v2_nw[wi];
+    const long long nblocks = e->Ppad / 32, slots = e->num_sms;
+    // small problems: split the categories of a block over 2 or 4 warps so that every warp of the machine has work
+    int ci = 0;
+    if (!mix) {
+        while (ci < 2 && walk20v2_cs[ci + 1] <= cpb && nblocks * walk20v2_cs[ci + 1] <= slots * nw) ci++;
+        if (e->kernel_variant == 3 && cpb >= 2) ci = 1;   // forced category split (parity coverage), or none
+        if (e->kernel_variant == 4) ci = cpb >= 4 ? 2 : 0;
+    }
+    const int csplit = walk20v2_cs[ci], nb = nw / csplit;
+    const void *f = walk20v2_f[3 - sd][wi][ci][(mix ? 2 : 0) + (safe ? 1 : 0)];
+    if (!f) return 1;
+    if (!(e->walk20v2_attr & (1u << ((3 - sd) * 9 + wi * 3 + ci)))) {
+        for (int k = 0; k < 4; k++) {
+            const void *fk = walk20v2_f[3 - sd][wi][ci][k];
+            if (!fk) continue;
+            CK(cudaFuncSetAttribute(fk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaFuncSetAttribute(fk, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        e->walk20v2_attr |= 1u << ((3 - sd) * 9 + wi * 3 + ci);
+    }
+    const long long waves = (nblocks + nb * slots - 1) / (nb * slots);
+    int ntiles = (int)std::min<long long>(waves * slots, nblocks);
+    const int grid = (int)std::min<long long>(ntiles, slots);
+    k_walk_info_n20ss<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+    if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+    void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter, (void *)&ntiles};
+    CK(cudaLaunchKernel(f, dim3(grid), dim3(nw * 32), args, smem, e->stream));
+    if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+    e->partials_timed = e->profiling;
+    e->launches += 2;
+    e->last_launch[0] += 2;
+    CK(cudaGetLastError());
+    e->theta_computed = false;
+    return 0;
+}
+
+// b200lk_op[] -> WalkJob20[]: a single tip child is A
+static int fill_jobs20(b200lk_engine *e, const b200lk_op *ops, int32_t nops, WalkJob20 *hj) {
+    for (int k = 0; k < nops; k++) {
+        const b200lk_op &op = ops[k];
+        int rc = validate_op(e, op);
+        if (rc) return rc;
+        if (op.reserved != 0) return fail(e, B200LK_ERR_INVALID, "multifurcating ops are not served by the walkers");
+        const b200lk_child *A = &op.left, *B = &op.right;
+        WalkJob20 &j = hj[k];
+        if (A->kind == 0 && B->kind == 0) j.ncase = 0;
+        else if (A->kind == 1 && B->kind == 1) j.ncase = 2;
+        else { j.ncase = 1; if (A->kind == 1) std::swap(A, B); }   // A = the tip
+        j.lenA = A->length; j.lenB = B->length;
+        j.aid = A->id; j.bid = B->id;
+        j.dst = op.dst_slot;
+    }
+    return 0;
+}
 
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
     const bool mix = nblk > 1;
-    const bool ss = e->d.clv_state != 0;
     const size_t stage_sz = walk20_stage_doubles(e);   // one staging block per (op, class block)
     if (stage_sz * nops * nblk > e->opinfo_cap) {
         CK(sync_stream(e));
@@ -672,27 +817,20 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     }
     static_assert(sizeof(WalkJob20) <= sizeof(DevOp) + 2 * sizeof(ChildJob), "pinned staging buffer too small for WalkJob20");
     WalkJob20 *hj = (WalkJob20 *)stage_acquire(e);
-    for (int k = 0; k < nops; k++) {
-        const b200lk_op &op = ops[k];
-        int rc = validate_op(e, op);
-        if (rc) return rc;
-        const b200lk_child *A = &op.left, *B = &op.right;
-        WalkJob20 &j = hj[k];
-        if (A->kind == 0 && B->kind == 0) j.ncase = 0;
-        else if (A->kind == 1 && B->kind == 1) j.ncase = 2;
-        else { j.ncase = 1; if (A->kind == 1) std::swap(A, B); }   // A = the tip
-        j.lenA = A->length; j.lenB = B->length;
-        j.aid = A->id; j.bid = B->id;
-        j.dst = op.dst_slot;
-    }
+    int rcj = fill_jobs20(e, ops, nops, hj);
+    if (rcj) return rcj;
     WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
     CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
-    if (ss) k_walk_info_n20ss<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
-    else k_walk_info_n20<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+    if (e->kernel_variant < 5) {   // default: the second-generation walker; variants 5.. = k_walk_n20ss configurations (A/B)
+        note_writes(e, ops, nops);
+        const int r = enqueue_walk20v2(e, nops, dj);
+        if (r <= 0) return r;
+        for (int k = 0; k < nops; k++) e->slot_ver[ops[k].dst_slot]--;   // not launched: the first-generation kernel below counts the writes
+    }
+    k_walk_info_n20ss<<<nops * nblk, 256, sizeof(double) * 2 * cpb * 20, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
     note_writes(e, ops, nops);
-    static const Walk20Cfg ss_cfg = {4, {walk20ss_f[0], walk20ss_f[1], walk20ss_f[2], walk20ss_f[3]}};
-    const Walk20Cfg &cfg = ss ? ss_cfg : walk20_cfgs[(e->kernel_variant >= 0 && e->kernel_variant < kNumWalk20Cfgs) ? e->kernel_variant : 0];
-    const void *const *csp_f = ss ? walk20ss_csp : walk20_csp;
+    const Walk20Cfg &cfg = walk20ss_cfgs[(e->kernel_variant >= 5 && e->kernel_variant - 5 < kNumWalk20ssCfgs) ? e->kernel_variant - 5 : 0];
+    const void *const *csp_f = walk20ss_csp;
     const int tile_ptn = cfg.nw * 32;
     const size_t smem = 2 * stage_sz * sizeof(double);   // the walker double-buffers whole staging blocks
     if (!e->walk20_attr_set) {
@@ -715,9 +853,9 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     const long long waves = (nblocks + cfg.nw * slots - 1) / (cfg.nw * slots);
     int ntiles = (int)std::min<long long>(waves * slots, nblocks);
     if (e->kernel_variant == 4) ntiles = (int)((nblocks + cfg.nw - 1) / cfg.nw);   // A/B: fixed full tiles
-    // small problems: one 32-pattern block per CTA, its categories split over the CTA's warps (k_walk_n20_mma<.., CSP>): a
+    // small problems: one 32-pattern block per CTA, its categories split over the CTA's warps (k_walk_n20ss<.., CSP>): a
     // traversal's latency drops by min(C, 4); worth it only while every block still gets its own resident CTA
-    const bool csp = !mix && e->C >= 2 && (ss ? e->kernel_variant != 4 : e->kernel_variant == 0) && cfg.nw == 4 && nblocks <= slots;
+    const bool csp = !mix && e->C >= 2 && e->kernel_variant <= 5 && cfg.nw == 4 && nblocks <= slots;
     if (csp) ntiles = (int)nblocks;
     const int grid = (int)std::min<long long>(ntiles, slots);
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
@@ -749,7 +887,8 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
     e->extra_children.clear();
     int rc = ensure_op_capacity(e, (size_t)nops + (nextra + 1) / 2);
     if (rc) return rc;
-    if (nextra == 0 && use_walk4(e)) return enqueue_walk4(e, ops, nops);
+    if (nextra == 0 && use_walk4(e) && e->kernel_variant != 5) return enqueue_walk4(e, ops, nops, nullptr);
+    if (nextra == 0 && walk4n_cfg(e)) return enqueue_walk4(e, ops, nops, walk4n_cfg(e));
     if (nextra == 0 && use_walk20(e)) return enqueue_walk20(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
@@ -891,6 +1030,7 @@ static void prof_end(b200lk_engine *e, int last) {
 }
 
 extern "C" int b200lk_update_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_update_partials(e->shards[k], ops, nops); });
     cudaSetDevice(e->cfg.device);
     prof_begin(e);
     int rc = enqueue_partials(e, ops, nops);
@@ -946,6 +1086,7 @@ enum { PEND_LOGL = 1, PEND_DERV = 2, PEND_SAVE_LOG = 4 };
 
 extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
                                           int32_t dad_id, double length, int32_t save_log_value) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_enqueue_branch_logl(e->shards[k], ops, nops, node_slot, dad_kind, dad_id, length, save_log_value); });
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
@@ -992,16 +1133,25 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     return 0;
 }
 
+static int finish_collect(b200lk_engine *e, double *logl, double *df, double *ddf);
 extern "C" int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf) {
+    if (!e->shards.empty()) return mg_finish(e, logl, df, ddf);
     cudaSetDevice(e->cfg.device);
     CK(sync_stream(e));
+    return finish_collect(e, logl, df, ddf);
+}
+// the stream has been synchronised: hand out what was queued (also used by b200lk_group_finish after ONE synchronisation)
+static int finish_collect(b200lk_engine *e, double *logl, double *df, double *ddf) {
+    e->stage_used = 0;
     if (e->pending_marks) prof_end(e, e->pending_marks);
     e->pending_marks = 0;
     const int pending = e->pending;
     e->pending = 0;
+    e->last_derv_nonfinite = false;
     int status = 0;
     if (pending & PEND_DERV) {
         double f = e->h_result[1], g = e->h_result[2];
+        e->last_derv_nonfinite = !std::isfinite(f);
         if (!std::isfinite(f)) {   // phylokernelnew.h:2629-2632 (the NORM_LH outError at :2577 is the caller's policy)
             f = g = 0.0;
             status = B200LK_WARN_DERV_UNDERFLOW;
@@ -1018,6 +1168,7 @@ extern "C" int b200lk_finish(b200lk_engine *e, double *logl, double *df, double 
         }
         if (logl) *logl = l;
     }
+    e->last_finish_status = status;
     return status;
 }
 
@@ -1060,10 +1211,12 @@ static void enqueue_derv(b200lk_engine *e, double length) {
     e->last_launch[2] += 1;
 }
 
-extern "C" int b200lk_theta_reset(b200lk_engine *e) { e->theta_computed = false; return 0; }
+extern "C" int b200lk_theta_reset(b200lk_engine *e) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_theta_reset(e->shards[k]); }); e->theta_computed = false; return 0; }
 
 extern "C" int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
                                           int32_t dad_id, double length) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_enqueue_branch_derv(e->shards[k], ops, nops, node_slot, dad_kind, dad_id, length); });
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
@@ -1090,6 +1243,7 @@ extern "C" int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_
 }
 
 extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) {
+    if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_enqueue_logl_from_buffer(e->shards[k], length); });
     cudaSetDevice(e->cfg.device);
     if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
     prof_begin(e);
@@ -1149,6 +1303,7 @@ static int launch_newton_coop(b200lk_engine *e, double x1, double xguess, double
 extern "C" int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
                                             int32_t dad_id, double x1, double xguess, double x2, double xacc, int32_t maxNRStep,
                                             int32_t len_slot) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "enqueue_newton_branch");
     cudaSetDevice(e->cfg.device);
     if (!newton_coop_ok(e)) return fail(e, B200LK_ERR_STATE, "enqueue_newton_branch: no device-resident Newton iteration for this configuration");
     if (len_slot < 0 || len_slot >= e->nlen_slots) return fail(e, B200LK_ERR_INVALID, "len_slot out of range");
@@ -1162,6 +1317,7 @@ extern "C" int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *o
 }
 
 extern "C" int b200lk_sweep_finish(b200lk_engine *e, int32_t nslots, double *lengths, int32_t *evaluations, int32_t *status) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "sweep_finish");
     cudaSetDevice(e->cfg.device);
     if (nslots < 0 || nslots > e->nlen_slots) return fail(e, B200LK_ERR_INVALID, "nslots out of range");
     CK(sync_stream(e));
@@ -1173,11 +1329,66 @@ extern "C" int b200lk_sweep_finish(b200lk_engine *e, int32_t nslots, double *len
     return 0;
 }
 
+// The host-driven form of the iteration (engines without a device-resident Newton loop; multi-device engines, where every step
+// sums the shards' derivatives): Optimization::minimizeNewton, utils/optimization.cpp:422-499, on f = -df, f' = -ddf.
+// func_derv(x, f, df) returns < 0 on error.
+template <typename F>
+static int host_newton(F func_derv, double x1, double xguess, double x2, double xacc, int maxNRStep, double *length_out) {
+    int rc;
+    double df, dx, f, temp, xh, xl, rts, rts_old;
+    rts = xguess;
+    if (rts < x1) rts = x1;
+    if (rts > x2) rts = x2;
+    auto done = [&](double x) { *length_out = x; return 0; };
+    if ((rc = func_derv(rts, f, df)) < 0) return rc;
+    if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; return B200LK_WARN_DERV_UNDERFLOW; }
+    if (df >= 0.0 && std::fabs(f) < xacc) return done(rts);
+    if (f < 0.0) { xl = rts; xh = x2; } else { xh = rts; xl = x1; }
+    for (int j = 1; j <= maxNRStep; j++) {
+        rts_old = rts;
+        if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)) {
+            dx = 0.5 * (xh - xl);
+            rts = xl + dx;
+            if (xl == rts) return done(rts);
+        } else {
+            dx = f / df;
+            temp = rts;
+            rts -= dx;
+            if (temp == rts) return done(rts);
+        }
+        if (std::fabs(dx) < xacc || (j == maxNRStep)) return done(rts_old);
+        if ((rc = func_derv(rts, f, df)) < 0) return rc;
+        if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; return B200LK_WARN_DERV_UNDERFLOW; }
+        if (df > 0.0 && std::fabs(f) < xacc) return done(rts);
+        if (f < 0.0) xl = rts;
+        else if (f > 0.0) xh = rts;
+    }
+    return done(rts);
+}
+
 // Optimization::minimizeNewton (utils/optimization.cpp:422-499) with f = -df, f' = -ddf (computeFuncDerv,
 // tree/phylotree.cpp:2529-2536), evaluated on the resident theta buffer.
 extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
                                     int32_t dad_id, double x1, double xguess, double x2, double xacc, int32_t maxNRStep,
                                     double *length_out, int32_t *steps_out) {
+    if (!e->shards.empty()) {   // every Newton step sums the shards' (df, ddf): the shards walk the same iterates
+        int nsteps = 0;
+        bool nonfinite = false;
+        auto fd = [&](double x, double &f, double &df) -> int {
+            double a = 0.0, b = 0.0;
+            const int r = b200lk_branch_derv(e, nsteps == 0 ? ops : nullptr, nsteps == 0 ? nops : 0, node_slot, dad_kind, dad_id, x, &a, &b);
+            if (r < 0) return r;
+            if (r == B200LK_WARN_DERV_UNDERFLOW) { nonfinite = true; a = b = std::nan(""); }
+            f = -a; df = -b;
+            nsteps++;
+            return 0;
+        };
+        if (nops > 0) b200lk_theta_reset(e);
+        int r = host_newton(fd, x1, xguess, x2, xacc, maxNRStep, length_out);
+        if (steps_out) *steps_out = nsteps;
+        (void)nonfinite;
+        return r;
+    }
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
@@ -1198,47 +1409,16 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     int nsteps = 0;
     auto func_derv = [&](double x, double &f, double &df) -> int {
         enqueue_derv(e, x);
-        cudaError_t ce = cudaSuccess;
-        if (ce == cudaSuccess) ce = sync_stream(e);
+        cudaError_t ce = sync_stream(e);
         if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
         f = -e->h_result[1];
         df = -e->h_result[2];
         nsteps++;
         return 0;
     };
-    double df, dx, dxold, f, temp, xh, xl, rts, rts_old;
-    rts = xguess;
-    if (rts < x1) rts = x1;
-    if (rts > x2) rts = x2;
-    auto done = [&](double x) { *length_out = x; if (steps_out) *steps_out = nsteps; return 0; };
-    if ((rc = func_derv(rts, f, df))) return rc;
-    if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; if (steps_out) *steps_out = nsteps; return B200LK_WARN_DERV_UNDERFLOW; }
-    if (df >= 0.0 && std::fabs(f) < xacc) return done(rts);
-    if (f < 0.0) { xl = rts; xh = x2; } else { xh = rts; xl = x1; }
-    dx = dxold = std::fabs(xh - xl);
-    for (int j = 1; j <= maxNRStep; j++) {
-        rts_old = rts;
-        if ((df <= 0.0) || (((rts - xh) * df - f) * ((rts - xl) * df - f) >= 0.0)) {
-            dxold = dx;
-            dx = 0.5 * (xh - xl);
-            rts = xl + dx;
-            if (xl == rts) return done(rts);
-        } else {
-            dxold = dx;
-            dx = f / df;
-            temp = rts;
-            rts -= dx;
-            if (temp == rts) return done(rts);
-        }
-        if (std::fabs(dx) < xacc || (j == maxNRStep)) return done(rts_old);
-        if ((rc = func_derv(rts, f, df))) return rc;
-        if (!std::isfinite(f) || !std::isfinite(df)) { *length_out = rts; if (steps_out) *steps_out = nsteps; return B200LK_WARN_DERV_UNDERFLOW; }
-        if (df > 0.0 && std::fabs(f) < xacc) return done(rts);
-        if (f < 0.0) xl = rts;
-        else if (f > 0.0) xh = rts;
-    }
-    (void)dxold;
-    return done(rts);
+    rc = host_newton(func_derv, x1, xguess, x2, xacc, maxNRStep, length_out);
+    if (steps_out) *steps_out = nsteps;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1274,12 +1454,17 @@ static int read_plain(b200lk_engine *e, const void *src, size_t bytes, void *out
     return 0;
 }
 
-extern "C" int b200lk_get_pattern_lh(b200lk_engine *e, double *out) { return read_plain(e, e->d_pattern_lh, sizeof(double) * e->P, out); }
-extern "C" int b200lk_get_pattern_scaling(b200lk_engine *e, double *out) { return read_plain(e, e->d_pattern_scaling, sizeof(double) * e->P, out); }
-extern "C" int b200lk_get_buffer_scale_all(b200lk_engine *e, double *out) { return read_plain(e, e->d_buffer_scale, sizeof(double) * e->P, out); }
-extern "C" int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_pattern_lh_cat, e->C, out); }
+extern "C" int b200lk_get_pattern_lh(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, 1, [](b200lk_engine *x, double *p) { return b200lk_get_pattern_lh(x, p); }); return read_plain(e, e->d_pattern_lh, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_pattern_scaling(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, 1, [](b200lk_engine *x, double *p) { return b200lk_get_pattern_scaling(x, p); }); return read_plain(e, e->d_pattern_scaling, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_buffer_scale_all(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, 1, [](b200lk_engine *x, double *p) { return b200lk_get_buffer_scale_all(x, p); }); return read_plain(e, e->d_buffer_scale, sizeof(double) * e->P, out); }
+extern "C" int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, (size_t)e->C, [](b200lk_engine *x, double *p) { return b200lk_get_pattern_lh_cat(x, p); }); return read_interleaved_f64(e, e->d_pattern_lh_cat, e->C, out); }
 // PhyloTree::computePatternLhCat(wsl) + the E-step loop of RateFree / ModelMixture::optimizeWithEM, on the device
 extern "C" int b200lk_em_posterior(b200lk_engine *e, int32_t wsl, int32_t add_invar, double *new_prop, double *posterior, int32_t *ncat_out) {
+    if (!e->shards.empty()) return mg_em_posterior(e, wsl, add_invar, new_prop, posterior, ncat_out);
     if (wsl < 2 || wsl > 4) return fail(e, B200LK_ERR_INVALID, "wsl: 2 = WSL_RATECAT, 3 = WSL_MIXTURE, 4 = WSL_MIXTURE_RATECAT");
     if (!e->have_lh_cat) return fail(e, B200LK_ERR_STATE, "em_posterior: needs the per-category likelihoods of a b200lk_branch_logl call");
     const bool marginal = e->cfg.nmix > 1 && !e->cfg.fused_mix_rate && (wsl == 2 || wsl == 3);
@@ -1325,6 +1510,7 @@ extern "C" int b200lk_em_posterior(b200lk_engine *e, int32_t wsl, int32_t add_in
 }
 
 extern "C" int b200lk_set_pattern_freq_from_posterior(b200lk_engine *dst, b200lk_engine *src, int32_t k) {
+    if (!dst->shards.empty() || !src->shards.empty()) { dst->err = "set_pattern_freq_from_posterior: not available on a multi-device engine"; return B200LK_ERR_STATE; }
     b200lk_engine *e = dst;   // errors are reported on the destination
     if (!src->d_post || k < 0 || k >= src->post_K) return fail(dst, B200LK_ERR_STATE, "no posteriors for that category: call b200lk_em_posterior on the source engine first");
     if (dst->P != src->P || dst->cfg.device != src->cfg.device) return fail(dst, B200LK_ERR_INVALID, "engines differ in pattern count or device");
@@ -1340,8 +1526,10 @@ extern "C" int b200lk_set_pattern_freq_from_posterior(b200lk_engine *dst, b200lk
     return 0;
 }
 
-extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) { return read_interleaved_f64(e, e->d_theta, e->B, out); }
+extern "C" int b200lk_get_theta(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, (size_t)e->B, [](b200lk_engine *x, double *p) { return b200lk_get_theta(x, p); }); return read_interleaved_f64(e, e->d_theta, e->B, out); }
 extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, (size_t)e->B, [&](b200lk_engine *x, double *p) { return b200lk_get_partial(x, slot, p); });
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
     cudaSetDevice(e->cfg.device);
     const double *src = e->d_partial + (size_t)eigen_slot(e, slot) * e->d.slot_stride;
@@ -1357,6 +1545,7 @@ extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     return 0;
 }
 extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out) {
+    if (!e->shards.empty()) return mg_gather(e, out, (size_t)e->S, [&](b200lk_engine *x, uint16_t *p) { return b200lk_get_scale_num(x, slot, p); });
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
     const uint16_t *src = e->d_scale + (size_t)slot * e->d.scale_stride;
     if (!e->cfg.safe_numeric) return read_plain(e, src, sizeof(uint16_t) * e->P, out);
@@ -1372,14 +1561,17 @@ extern "C" int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *ou
     return 0;
 }
 extern "C" int b200lk_get_tip_partial_lh(b200lk_engine *e, double *out) {
+    if (!e->shards.empty()) return b200lk_get_tip_partial_lh(e->shards[0], out);
     return read_plain(e, e->d.tip_lh, sizeof(double) * (e->cfg.state_unknown + 1) * e->cfg.nmix * e->cfg.nstates, out);
 }
-extern "C" void *b200lk_pattern_lh_dev(b200lk_engine *e) { return e->d_pattern_lh; }
+extern "C" void *b200lk_pattern_lh_dev(b200lk_engine *e) {
+    if (!e->shards.empty()) return nullptr; return e->d_pattern_lh; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // UFBoot RELL on the device
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot) {
+    if (!e->shards.empty()) return mg_set_boot_samples(e, boot_samples, nboot);
     cudaSetDevice(e->cfg.device);
     if (nboot < 0) return fail(e, B200LK_ERR_INVALID, "nboot < 0");
     CK(sync_stream(e));
@@ -1403,6 +1595,7 @@ extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_sampl
 }
 
 extern "C" int b200lk_rell(b200lk_engine *e, float *rell) {
+    if (!e->shards.empty()) return mg_rell(e, rell);
     cudaSetDevice(e->cfg.device);
     if (e->nboot <= 0) return fail(e, B200LK_ERR_STATE, "rell: no bootstrap samples set");
     k_rell<<<e->nboot, 256, 0, e->stream>>>(e->d_pattern_lh, e->d_boot, e->P, e->boot_stride, e->d_rell);
@@ -1412,3 +1605,5 @@ extern "C" int b200lk_rell(b200lk_engine *e, float *rell) {
     CK(sync_stream(e));
     return 0;
 }
+
+#include "b200lk_group.inc"

@@ -77,14 +77,18 @@ __device__ __forceinline__ long long pbase(long long p, int width) {
     return (p >> 5) * (long long)width * kWarp + (p & 31);
 }
 
-// 20-state engines keep their CLV slots FRAGMENT-MAJOR (the order the FP64-MMA walker produces and consumes them in, see
-// k_walk_n20_mma): a 32-pattern block is [M-tile mt = 4][category c = C][160 doubles], and the 160 doubles of 8 patterns x 20
-// eigen-indices are  i < 16: (i/8)*64 + ((i%8)/2)*16 + g*2 + i%2   (C-fragment order of an 8x8 state tile, g = pattern%8),
-//                    i >= 16: 128 + g*4 + (i-16).
-// Same size as the warp-interleaved layout (B*32 doubles per 32 patterns); theta, _pattern_lh_cat and scale_num keep pbase().
+// 20-state engines keep their CLV slots FRAGMENT-MAJOR (the order the FP64-MMA walkers produce and consume them in, see
+// b200lk_walk20ss.cuh): a 32-pattern block is [M-tile mt = 4][category c = C][160 doubles], and the 160 doubles of 8 patterns
+// (g = pattern % 8) x 20 values are three state tiles in C-fragment order:
+//     i < 16:  (i/8)*64 + g*8 + i%8        lane 4g+q of a warp owns values 2q, 2q+1 of a tile = the 16-byte chunk number `lane`
+//     i >= 16: 128 + g*4 + (i-16)
+// so that a lane stores its two accumulators of a state tile with one 16-byte store (the warp: 512 contiguous bytes), loads them
+// back as MMA A fragments the same way, and the same 16-byte chunks are read without bank conflicts when a step's 1280 bytes sit in
+// shared memory.  Same size as the warp-interleaved layout (B*32 doubles per 32 patterns); theta, _pattern_lh_cat and scale_num
+// keep pbase().
 constexpr int kClv20Step = 160;
 __host__ __device__ __forceinline__ int clv20_off(int i, int g) {
-    return i < 16 ? (i >> 3) * 64 + ((i & 7) >> 1) * 16 + g * 2 + (i & 1) : 128 + g * 4 + (i - 16);
+    return i < 16 ? (i >> 3) * 64 + g * 8 + (i & 7) : 128 + g * 4 + (i - 16);
 }
 // element (category c, index i) of pattern p inside a CLV slot, for the thread-per-pattern kernels
 struct ClvIdx {
@@ -877,379 +881,30 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 20-state WALKER (LG/WAG/JTT... +G/+I+G/+R, C10-C60 mixtures, fused classes): the kernel of BASELINE configs 3 and 4.
-//
-// Per pattern, category and child the update is a 20x20 mat-vec; three of them per inner-inner node (two children,
-// one back-transform) = C*(6n^2+n) flops against 3*(8B+2S) bytes (about 5 flop/B): on B200 this sits at the ridge between
-// the FP64 pipe (36-37 TFLOP/s measured, DFMA and DMMA share it) and HBM (6.5 TB/s).
-//
-// The operator is applied factorised, evec . (exp(eval r_c t) (.) L)  (tree/phylokernelnew.h:1016-1031 builds
-// echild = evec*exp explicitly), so the only matrices are the model's evec and inv_evec; per-op data is 2 x C x 20
-// exponentials; tip children use the reference's lookup tables partial_lh_leaves[state][c][x] (:1036-1056), staged in shared
-// memory per op.  History (config 3, ms per evaluation): generic thread-per-pattern kernel 30.6; DFMA with constant-bank
-// operands 11.4; DMMA with register-resident B fragments 8.4 -> 6.7; fragment-major CLV layout (below): see DESIGN.md.
+// 20-state models (LG/WAG/JTT... +G/+I+G/+R, C10-C60 mixtures, fused classes): shared pieces of the FP64-MMA walkers
+// (b200lk_walk20ss.cuh, b200lk_walk20v2.cuh).  Per pattern, category and child the update is a 20x20 mat-vec: on B200 this sits at
+// the ridge between the FP64 pipe (36-37 TFLOP/s measured, DFMA and DMMA share it) and HBM (6.5 TB/s).
+// History (config 3, ms per evaluation): generic thread-per-pattern kernel 30.6; DFMA with constant-bank operands 11.4; DMMA in
+// eigen space with register-resident B fragments (round 1) 8.4 -> 6.5; state-space CLVs (2 mat-vecs per inner node): DESIGN.md.
 // ------------------------------------------------------------------------------------------------------------
 struct WalkJob20 {
     double lenA, lenB;
     int32_t dst, ncase, aid, bid;   // ncase: 0 tip-tip, 1 tip(A)-inner(B), 2 inner-inner; ids: taxon row or slot
 };
 
-// staging block per op (doubles): header[4] | expA[C*20] | expB[C*20] | tabA[(su+1)][C*20 + 2] | tabB[(su+1)][C*20 + 2]
-// (table rows padded by 2 doubles: a row stride of C*20 doubles is a multiple of 32 banks for C = 4, which would put the
-// same (c, x) entry of every state in the same bank — a 20-way conflict when the lanes of a warp hold different states)
+// tip-table rows are padded by 2 doubles: a row stride of C*20 doubles is a multiple of 32 banks for C = 4, which would put the
+// same (c, x) entry of every state in the same bank — a 20-way conflict when the lanes of a warp hold different states
 __host__ __device__ inline int tab20_stride(int C) { return C * 20 + 2; }
-__host__ __device__ inline size_t stage20_doubles(int C, int su) { return 4 + 2 * (size_t)C * 20 + 2 * (size_t)(su + 1) * tab20_stride(C); }
 
-// One CTA per (op, class block).  A class block is one mixture class with its cpb = C/nmix categories (all C categories
-// for a single-class model; one category per block when mixture classes are fused with the rate categories,
-// tree/phylokernelnew.h:1322-1325).  Each block gets its own staging block, so that to the walker a mixture is simply a
-// longer list of "virtual ops" with cpb categories each.
-__global__ void __launch_bounds__(256) k_walk_info_n20(Dev D, const WalkJob20 *jobs, double *stage, unsigned long long *counter) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ULL;   // the walker's tile queue (next launch on this stream)
-    extern __shared__ double s_exp20[];   // [2][cpb*20]
-    const int nblk = D.nmix, cpb = D.C / nblk, B = cpb * 20, TS = tab20_stride(cpb);
-    const int op = blockIdx.x / nblk, m = blockIdx.x - op * nblk;
-    const WalkJob20 job = jobs[op];
-    double *st = stage + (size_t)blockIdx.x * stage20_doubles(cpb, D.su);
-    for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
-        const int ch = k / B, kk = k - ch * B, r = kk / 20, i = kk - r * 20;
-        const int c = m * cpb + r;
-        const double len_child = D.cat_rate[c % D.ncat] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
-        const double v = exp(D.eval[m * 20 + i] * len_child);                            // :1022
-        s_exp20[k] = v;
-        st[4 + k] = v;
-    }
-    if (threadIdx.x == 0) {
-        int32_t *h = reinterpret_cast<int32_t *>(st);
-        h[0] = job.dst; h[1] = job.ncase; h[2] = job.aid; h[3] = job.bid; h[4] = m; h[5] = h[6] = h[7] = 0;
-    }
-    __syncthreads();
-    // partial_lh_leaves[state][c][x] for tip children (:1036-1056: Vec4d lane accumulators + horizontal_add)
-    const int rows = D.su + 1;
-    for (int ch = 0; ch < 2; ch++) {
-        const bool is_tip = ch == 0 ? (job.ncase <= 1) : (job.ncase == 0);
-        if (!is_tip) continue;
-        double *tab = st + 4 + 2 * B + (size_t)ch * rows * TS;
-        const double *ex = s_exp20 + ch * B;
-        for (int k = threadIdx.x; k < rows * TS; k += blockDim.x) {
-            const int state = k / TS, cx = k - state * TS;
-            if (cx >= B) { tab[k] = 0.0; continue; }
-            const int r = cx / 20, x = cx - r * 20;
-            if (state == D.su) { tab[k] = 1.0; continue; }
-            const double *tip = D.tip_lh + ((size_t)state * D.nmix + m) * 20;
-            const double *ev = D.evec + (size_t)m * 400 + x * 20;
-            const double *e = ex + r * 20;
-            double a0 = (ev[0] * e[0]) * tip[0], a1 = (ev[1] * e[1]) * tip[1], a2 = (ev[2] * e[2]) * tip[2], a3 = (ev[3] * e[3]) * tip[3];
-#pragma unroll
-            for (int i = 4; i < 20; i += 4) {
-                a0 = fma(ev[i] * e[i], tip[i], a0); a1 = fma(ev[i + 1] * e[i + 1], tip[i + 1], a1);
-                a2 = fma(ev[i + 2] * e[i + 2], tip[i + 2], a2); a3 = fma(ev[i + 3] * e[i + 3], tip[i + 3], a3);
-            }
-            tab[k] = (a0 + a1) + (a2 + a3);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// The FP64 MMA walker (mma.sync.m8n8k4.f64, DMMA).
-//
-// Why MMA although DMMA and DFMA share ONE FP64 pipe on B200 with the same peak (scripts/fp64_mix.cu: 36.3 / 37.1 TFLOP/s
-// alone, 36 TFLOP/s in any mix): with DFMA every FMA needs one matrix element delivered from the constant bank or shared
-// memory, while the MMA form keeps evec and inv_evec RESIDENT IN REGISTERS as B fragments (2 x 15 doubles per lane) for the
-// whole kernel and issues 45 DMMAs instead of 1200 DFMAs + 600 operand loads per 8 patterns and category.  Cost: the
-// output-state dimension 20 is padded to three 8-wide tiles (24), so at most 20/24 = 83 % of the pipe's peak is useful.
-//
-// Mapping (PTX ISA fragment layouts, g = lane/4, q = lane%4): M = 8 patterns (row g), K = 4 eigen-indices, N = 8 states.
-//   child pass   a[p][x]  = sum_i (exp_ci * L[p][c][i]) * evec[x][i]   A = scaled CLV, B[k=i][n=x] = evec[x][i]
-//   product      t = a (.) b on the C fragments (p = g, x = 8nt + 2q + {0,1})
-//   back pass    out[p][i] = sum_x t[p][x] * inv_evec[i][x]           B[k=x][n=i] = inv_evec[i][x]
-// The MMA's K index may be permuted freely as long as A and B fragments use the same permutation.  That is used twice:
-//   * the product's C fragments ARE the back pass's A fragments (K-slot q of k-tile kt holds x = back_x(kt,q)); only the
-//     half-empty third state tile needs one shuffle;
-//   * CLVs are STORED in C-fragment order (clv20_off below: the "fragment-major" layout) — a lane writes its two
-//     accumulators of a state tile with one 16-byte store, the warp 512 contiguous bytes — and are LOADED back as A fragments
-//     with one 16-byte load per two k-tiles in the permuted K order clv_k(kt,q); evec's B fragments use the same order.
-//     ncu on the previous warp-interleaved layout (8-byte accesses to 4 rows x 64 bytes per instruction) showed the LSU data
-//     pipe, not the FP64 pipe, as the binding unit: 8 wavefronts per LDG/STG, 88 per step, 64 % of the LSU peak with the FP64
-//     pipe stuck at 68 %; the fragment-major layout needs 30.
-// A warp owns 32 consecutive patterns (4 M-tiles); a CTA of NW warps walks the whole op list for its 32*NW-pattern tile.
-// ------------------------------------------------------------------------------------------------------------
+// mma.sync.m8n8k4.f64 (DMMA).  Fragment layouts (PTX ISA), g = lane/4, q = lane%4: A[row g][k q], B[k q][col g],
+// C[row g][cols 2q, 2q+1].  M = 8 patterns, K = 4, N = 8 states.
 __device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
     asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
-
-// state x in K-slot q of k-tile kt of the BACK pass (the product's C fragment used as A fragment as it stands; the
-// half-empty third tile, held by lanes q < 2, is spread over the four lanes with one shuffle)
-__host__ __device__ inline int back_x(int kt, int q) {
-    return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + (q < 2 ? 2 * q : 2 * (q - 2) + 1);
-}
-// eigen-index i in K-slot q of k-tile kt of the CHILD pass = what the fragment-major layout delivers to lane (g, q)
+// value index i that lane (., q) holds in K-slot q of k-tile kt when a CLV block is loaded as A fragments: two k-tiles per
+// 16-byte load (values 2q, 2q+1 of state tile kt/2), the tail k-tile = values 16 + q
 __host__ __device__ inline int clv_k(int kt, int q) { return kt < 4 ? 8 * (kt >> 1) + 2 * q + (kt & 1) : 16 + q; }
 
-template <bool SM>
-struct BFrag20 {   // one B-fragment element of the lane: from the register copy or from shared memory
-    const double (&r)[5][3];
-    const double *s;
-    __device__ __forceinline__ double operator()(int kt, int nt) const {
-        if (SM) return s[(kt * 3 + nt) * kWarp];
-        return r[kt][nt];
-    }
-};
-
-struct Walk20Op {   // per-(op, class block), per-lane addressing state of the MMA walker
-    const double *Aq, *Bq;   // child CLVs, first category of this class block in M-tile 0 of the warp's 32-pattern block
-    double *Oq;              // destination, same position
-    const uint16_t *Asc, *Bsc;
-    uint16_t *Osc;           // scale_num: NORM [p], SAFE [c*32 + p%32] inside the warp's block (column g folded in)
-    unsigned stA, stB;       // tip states of the lane's pattern in the 4 M-tiles, one byte each
-    unsigned may_mask;       // bit mt: ptn_invar == 0 (patterns that may be rescaled)
-    // mixtures (NORM_LH): the underflow test spans ALL classes of a pattern, the classes are walked one after the other
-    int first_class, last_class;   // this block is the first / last class block of its op
-    int class_off;                 // doubles between the op's class-0 block and this one inside an M-tile block (m*cpb*160)
-    int Ctot;                      // categories of the whole CLV
-    unsigned *s_mhi;               // per-lane running max exponent word, [4 M-tiles][threads] in shared memory
-    const double *sBe, *sBi;       // BSM: the lane's B-fragment elements in shared memory, [(kt*3 + nt)*32] (lane folded in)
-};
-
-// DBG (diagnosis builds only, results are wrong): bit 0 no CLV stores, bit 1 no CLV loads, bit 2 DMMAs replaced by one DFMA
-// CSP (category split, small problems): the warp processes categories 0, cstep, 2*cstep, ... (C of them) of a CLV whose other
-// categories belong to the CTA's other warps; the NORM_LH underflow decision, which spans all categories of a pattern, is then
-// taken after a CTA barrier by walk20_csplit_finish — here the warp only leaves its running maximum in shared memory.
-template <bool SAFE, bool MIX, int NCASE, int BSM, int DBG = 0, bool CSP = false>
-__device__ __forceinline__ void walk20_mma_op(const int C, const int cstep, const Walk20Op &W, const double (&Be_r)[5][3],
-                                              const double (&Bi_r)[5][3], const double *s_expA, const double *s_expB,
-                                              const double *s_tabA, const double *s_tabB, const int TS, int lane, unsigned (&csp_sc)[4]) {
-    // BSM bit 0 / bit 1: the evec / inv_evec B fragments are read from shared memory at each use (one conflict-free 8-byte
-    // load per lane and DMMA) instead of living in 30 registers each
-    const BFrag20<(BSM & 1) != 0> Be{Be_r, W.sBe};
-    const BFrag20<(BSM & 2) != 0> Bi{Bi_r, W.sBi};
-    const int g = lane >> 2, q = lane & 3;
-    auto MMA = [](double &d0, double &d1, double a, double b) {
-        if (DBG & 4) { d0 = fma(a, b, d0); d1 += d0; } else dmma_m8n8k4(d0, d1, a, b);
-    };
-    const double *eA = s_expA + 2 * q, *eB = s_expB + 2 * q;
-    const int c20 = cstep * 20, cclv = cstep * kClv20Step, csc = cstep * kWarp;   // strides between the warp's categories
-    const int lo2 = (q * 8 + g) * 2;               // the lane's pair inside a 64-double state tile
-    const int lot = 128 + g * 4 + 2 * q;           // store position of the tail pair (lanes q < 2)
-    // Software pipeline over the 4*C (M-tile, category) steps — consecutive in memory, 160 doubles each: the raw CLV
-    // fragments of step s+1 are in flight while step s runs its MMAs.
-    const int step_c = cclv;                                      // next category of this warp, same M-tile
-    const int step_m = W.Ctot * kClv20Step - (C - 1) * cclv;      // its first category in the next M-tile
-    double nA[5], nB[5];
-    const double *pfA = W.Aq, *pfB = W.Bq;               // fetch cursors
-    int pf_c = 0, pf_left = 4 * C;                        // category of the fetch cursor, steps still to fetch
-    auto fetch = [&](double (&dA)[5], double (&dB)[5]) {
-        if (pf_left > 0) {
-            if (DBG & 2) {
-#pragma unroll
-                for (int k = 0; k < 5; k++) { dA[k] = 1.0 + pf_left; dB[k] = 2.0 + pf_left; }
-            } else {
-            if (NCASE == 2) {
-                const double2 v0 = *reinterpret_cast<const double2 *>(pfA + lo2);
-                const double2 v1 = *reinterpret_cast<const double2 *>(pfA + 64 + lo2);
-                dA[0] = v0.x; dA[1] = v0.y; dA[2] = v1.x; dA[3] = v1.y;
-                dA[4] = pfA[128 + lane];
-            }
-            if (NCASE >= 1) {
-                const double2 v0 = *reinterpret_cast<const double2 *>(pfB + lo2);
-                const double2 v1 = *reinterpret_cast<const double2 *>(pfB + 64 + lo2);
-                dB[0] = v0.x; dB[1] = v0.y; dB[2] = v1.x; dB[3] = v1.y;
-                dB[4] = pfB[128 + lane];
-            }
-            }
-            const int adv = pf_c + 1 < C ? step_c : step_m;
-            pfA += adv; pfB += adv;
-            pf_c = pf_c + 1 < C ? pf_c + 1 : 0;
-            pf_left--;
-        }
-    };
-    fetch(nA, nB);
-
-    int mt = 0, c = 0;
-    const double *tA = nullptr, *tB = nullptr;
-    double *pO = nullptr;
-    unsigned mhi = 0, scA = 0, scB = 0;
-    for (int s = 0; s < 4 * C; s++) {
-        if (c == 0) {   // a new M-tile (8 patterns)
-            tA = s_tabA + (size_t)((W.stA >> (8 * mt)) & 0xffu) * TS + 2 * q;
-            tB = s_tabB + (size_t)((W.stB >> (8 * mt)) & 0xffu) * TS + 2 * q;
-            pO = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
-            mhi = 0;
-            if (!SAFE) {   // children's scale counts: loaded here, first used after the last category
-                if (NCASE == 2) scA = W.Asc[8 * mt];
-                if (NCASE >= 1) scB = W.Bsc[8 * mt];
-            }
-        }
-        // exp(eval_i r_c t) for the lane's five K-slots (clv_k order): two 16-byte and one 8-byte shared-memory load per child
-        double fA[5], fB[5];
-        if (NCASE == 2) {
-            const double2 e0 = *reinterpret_cast<const double2 *>(eA + c * c20), e1 = *reinterpret_cast<const double2 *>(eA + c * c20 + 8);
-            fA[0] = nA[0] * e0.x; fA[1] = nA[1] * e0.y; fA[2] = nA[2] * e1.x; fA[3] = nA[3] * e1.y;
-            fA[4] = nA[4] * eA[c * c20 + 16 - q];    // eA carries +2q: element 16 + q
-        }
-        if (NCASE >= 1) {
-            const double2 e0 = *reinterpret_cast<const double2 *>(eB + c * c20), e1 = *reinterpret_cast<const double2 *>(eB + c * c20 + 8);
-            fB[0] = nB[0] * e0.x; fB[1] = nB[1] * e0.y; fB[2] = nB[2] * e1.x; fB[3] = nB[3] * e1.y;
-            fB[4] = nB[4] * eB[c * c20 + 16 - q];
-        }
-        fetch(nA, nB);   // step s+1
-        double a[3][2], b[3][2];
-        if (NCASE == 2) {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) { a[nt][0] = 0.0; a[nt][1] = 0.0; }
-        } else {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                // the third state tile holds states 16..19 only: lanes q >= 2 would read past the category (and, for the last
-                // category of the last row, past the table: compute-sanitizer) — their values are never used
-                double2 t = make_double2(0.0, 0.0);
-                if (nt < 2 || q < 2) t = *reinterpret_cast<const double2 *>(tA + c * c20 + 8 * nt);
-                a[nt][0] = t.x; a[nt][1] = t.y;
-            }
-        }
-        if (NCASE >= 1) {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) { b[nt][0] = 0.0; b[nt][1] = 0.0; }
-        } else {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                double2 t = make_double2(0.0, 0.0);
-                if (nt < 2 || q < 2) t = *reinterpret_cast<const double2 *>(tB + c * c20 + 8 * nt);
-                b[nt][0] = t.x; b[nt][1] = t.y;
-            }
-        }
-        // child passes; the two children's accumulator chains are independent and interleaved
-#pragma unroll
-        for (int kt = 0; kt < 5; kt++) {
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                if (NCASE == 2) MMA(a[nt][0], a[nt][1], fA[kt], Be(kt, nt));
-                if (NCASE >= 1) MMA(b[nt][0], b[nt][1], fB[kt], Be(kt, nt));
-            }
-        }
-        // product on the C fragments = A fragments of the back pass (see back_x)
-        double ft[5];
-        ft[0] = a[0][0] * b[0][0]; ft[1] = a[0][1] * b[0][1];
-        ft[2] = a[1][0] * b[1][0]; ft[3] = a[1][1] * b[1][1];
-        {
-            const double t0 = a[2][0] * b[2][0], t1 = a[2][1] * b[2][1];
-            const double r = __shfl_sync(0xffffffffu, t1, (lane & 28) | (q & 1));
-            ft[4] = q < 2 ? t0 : r;
-        }
-        double out[3][2];
-#pragma unroll
-        for (int nt = 0; nt < 3; nt++) { out[nt][0] = 0.0; out[nt][1] = 0.0; }
-#pragma unroll
-        for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) MMA(out[nt][0], out[nt][1], ft[kt], Bi(kt, nt));
-        // this lane holds out[p][i] for i = 8nt + 2q + {0,1}; the padded states 20..23 are exact zeros
-        unsigned chi = 0u;
-#pragma unroll
-        for (int nt = 0; nt < 3; nt++) chi = max(chi, max(abs_hi(out[nt][0]), abs_hi(out[nt][1])));
-        if (SAFE) {
-            chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 1));
-            chi = max(chi, __shfl_xor_sync(0xffffffffu, chi, 2));
-            unsigned sc = 0;
-            if (NCASE == 2) sc += W.Asc[c * csc + 8 * mt];
-            if (NCASE >= 1) sc += W.Bsc[c * csc + 8 * mt];
-            if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && chi < kThresholdHi) {
-#pragma unroll
-                for (int nt = 0; nt < 3; nt++) { out[nt][0] *= kTwo256; out[nt][1] *= kTwo256; }
-                sc += 1;
-            }
-            if (q == 0) W.Osc[c * csc + 8 * mt] = (uint16_t)sc;
-        } else mhi = max(mhi, chi);   // the pattern's other three lanes are folded in once per M-tile
-        double *po = pO + c * cclv;
-        if (!(DBG & 1) || out[0][0] == 1.2345e-300) {
-        *reinterpret_cast<double2 *>(po + lo2) = make_double2(out[0][0], out[0][1]);
-        *reinterpret_cast<double2 *>(po + 64 + lo2) = make_double2(out[1][0], out[1][1]);
-        if (q < 2) *reinterpret_cast<double2 *>(po + lot) = make_double2(out[2][0], out[2][1]);
-        }
-        if (++c == C) {   // last category of this M-tile
-            if (!SAFE && CSP) {
-                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
-                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
-                W.s_mhi[mt * kWarp + lane] = mhi;   // this warp's slot; the decision follows the barrier
-                csp_sc[mt] = scA + scB;            // children's scale counts, loaded at the head of the M-tile
-            } else if (!SAFE) {
-                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 1));
-                mhi = max(mhi, __shfl_xor_sync(0xffffffffu, mhi, 2));
-                if (MIX) {   // fold in the classes walked before this one (each lane owns its slot: no synchronisation)
-                    unsigned *slot = W.s_mhi + mt * blockDim.x + threadIdx.x;
-                    if (!W.first_class) mhi = max(mhi, *slot);
-                    if (!W.last_class) *slot = mhi;
-                }
-                if (!MIX || W.last_class) {
-                    unsigned norm_sc = scA + scB;
-                    if (NCASE != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi) {   // rare: rescale what this lane has written
-                        double *pAll = pO - W.class_off;
-                        for (int cc = 0; cc < W.Ctot; cc++, pAll += kClv20Step) {
-                            double2 *p0 = reinterpret_cast<double2 *>(pAll + lo2), *p1 = reinterpret_cast<double2 *>(pAll + 64 + lo2);
-                            double2 v0 = *p0, v1 = *p1;
-                            v0.x *= kTwo256; v0.y *= kTwo256; v1.x *= kTwo256; v1.y *= kTwo256;
-                            *p0 = v0; *p1 = v1;
-                            if (q < 2) {
-                                double2 *p2 = reinterpret_cast<double2 *>(pAll + lot);
-                                double2 v2 = *p2;
-                                v2.x *= kTwo256; v2.y *= kTwo256;
-                                *p2 = v2;
-                            }
-                        }
-                        norm_sc += 1;
-                    }
-                    if (q == 0) W.Osc[8 * mt] = (uint16_t)norm_sc;
-                }
-            }
-            c = 0;
-            mt++;
-        }
-    }
-}
-
-// category split, NORM_LH: after the barrier every warp folds the CTA's maxima (all categories of the pattern), rescales what IT
-// wrote if the pattern underflowed (tree/phylokernelnew.h:2015-2029) and warp 0 writes the pattern's scale count
-__device__ __forceinline__ void walk20_csplit_finish(const Walk20Op &W, const int C, const int cstep, const int ncase, const int nwarps,
-                                                     const unsigned *s_mhi_all, const int warp, const int lane, const unsigned (&csp_sc)[4]) {
-    const int g = lane >> 2, q = lane & 3;
-    (void)g;
-    const int lo2 = (q * 8 + (lane >> 2)) * 2, lot = 128 + (lane >> 2) * 4 + 2 * q;
-#pragma unroll
-    for (int mt = 0; mt < 4; mt++) {
-        unsigned mhi = 0;
-        for (int w = 0; w < nwarps; w++) mhi = max(mhi, s_mhi_all[(w * 4 + mt) * kWarp + lane]);
-        const bool scale = ncase != 0 && ((W.may_mask >> mt) & 1u) && mhi < kThresholdHi;
-        if (scale) {
-            double *pc = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
-            for (int j = 0; j < C; j++, pc += cstep * kClv20Step) {
-                double2 *p0 = reinterpret_cast<double2 *>(pc + lo2), *p1 = reinterpret_cast<double2 *>(pc + 64 + lo2);
-                double2 v0 = *p0, v1 = *p1;
-                v0.x *= kTwo256; v0.y *= kTwo256; v1.x *= kTwo256; v1.y *= kTwo256;
-                *p0 = v0; *p1 = v1;
-                if (q < 2) {
-                    double2 *p2 = reinterpret_cast<double2 *>(pc + lot);
-                    double2 v2 = *p2;
-                    v2.x *= kTwo256; v2.y *= kTwo256;
-                    *p2 = v2;
-                }
-            }
-        }
-        if (warp == 0 && q == 0) W.Osc[8 * mt] = (uint16_t)(csp_sc[mt] + (scale ? 1u : 0u));
-    }
-}
-
-
-// copy the parts of one op's staging block that the op needs (header + exp always, tabA for a tip child A, tabB when both
-// children are tips) into shared memory, asynchronously
-__device__ __forceinline__ void stage20_fetch(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, int tid, int nthreads) {
-    const int n_always = (4 + 2 * B) / 2;                                   // 16-byte chunks
-    const int n_total = n_always + (ncase <= 1 ? tab_doubles / 2 : 0) * (ncase == 0 ? 2 : 1);
-    for (int k = tid; k < n_total; k += nthreads) cp_async16(sdst + 2 * k, gsrc + 2 * k);
-}
-
-// The same copy as ONE TMA bulk load (cp.async.bulk global -> shared, completion on an mbarrier): the needed part of a staging
-// block is a contiguous prefix (header | exp | tabA | tabB), so a single thread issues one instruction per op instead of up to
-// 16 cp.async per thread, and the consumers wait on the mbarrier's phase instead of on their own copy groups.
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -1265,174 +920,14 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         "DONE_%=:\n"
         "}\n" ::"r"(a), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void stage20_fetch_tma(double *sdst, const double *gsrc, int ncase, int B, int tab_doubles, unsigned long long *bar) {
-    const unsigned bytes = (unsigned)(((4 + 2 * B) + (ncase <= 1 ? tab_doubles : 0) * (ncase == 0 ? 2 : 1)) * sizeof(double));
-    const unsigned b = (unsigned)__cvta_generic_to_shared(bar), d = (unsigned)__cvta_generic_to_shared(sdst);
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
-}
-
-// NW  warps per CTA (tile = 32*NW patterns; the two staging buffers are per CTA, so larger CTAs leave room for more warps);
-// BSM the evec (bit 0) / inv_evec (bit 1) B fragments come from shared memory (7.7 KB per CTA) instead of 2 x 30 registers;
-// MINB minimum resident CTAs per SM (register cap).  Warps whose 32 patterns lie beyond Ppad (a multiple of 128, not of
-// 32*NW) idle through the barriers.
-template <bool SAFE, bool MIX, int NW, int BSM, int MINB, int DBG = 0, bool CSP = false, bool TMA = false>
-__global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20_mma(Dev D, const double *stage, int nops, unsigned long long *counter,
-                                                                 int ntiles) {
-    static_assert(!(CSP && MIX), "category split serves single-class models");
-    __shared__ __align__(8) unsigned long long s_bar[2];   // TMA: one mbarrier per staging buffer
-    unsigned seq = 0;                                      // staging blocks fetched so far by this CTA: block -> buffer seq & 1
-    if (TMA) {
-        if (threadIdx.x == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncthreads();
-    }
-    constexpr int NT = NW * 32;
-    // two staging buffers: header[4] | exp[2][cpb*20] | tabA[(su+1)][TS] | tabB[(su+1)][TS]; block v+1 is fetched with
-    // cp.async while block v computes, so each (op, class block) costs one barrier and no exposed copy
-    extern __shared__ __align__(16) double s_dyn20[];
-    __shared__ long long s_item;
-    __shared__ unsigned s_mhi[(MIX || CSP) ? 4 * NT : 1];
-    __shared__ __align__(16) double s_B[BSM ? (MIX ? 2 : 1) * 960 : 2];   // [buffer][evec | inv_evec][kt][nt][lane]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
-    const int nblk = MIX ? D.nmix : 1, cpb = D.C / nblk;   // class blocks per op, categories per block
-    const int B = cpb * 20, rows = D.su + 1, TS = tab20_stride(cpb);
-    const size_t stage_sz = stage20_doubles(cpb, D.su);
-    const int tab_doubles = rows * TS;
-    const int nvo = nops * nblk;                            // "virtual ops": (op, class block) pairs, class-minor
-    // the model's matrices as B fragments: resident for the whole kernel (single class) or reloaded per class block
-    double Be[5][3], Bi[5][3];
-    auto load_frags = [&](int m) {   // register copies (only the matrices not served from shared memory)
-        const double *ev = D.evec + (size_t)m * 400, *iv = D.inv_evec + (size_t)m * 400;
-#pragma unroll
-        for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                const int n = 8 * nt + g;
-                if (!(BSM & 1)) Be[kt][nt] = n < 20 ? ev[n * 20 + clv_k(kt, q)] : 0.0;    // B[k = i][n = x] = evec[x][i]
-                if (!(BSM & 2)) Bi[kt][nt] = n < 20 ? iv[n * 20 + back_x(kt, q)] : 0.0;   // B[k = x][n = i] = inv_evec[i][x]
-            }
-    };
-    auto load_frags_smem = [&](int m, int buf) {
-        const double *ev = D.evec + (size_t)m * 400, *iv = D.inv_evec + (size_t)m * 400;
-        for (int k = tid; k < 960; k += NT) {
-            const int mat = k / 480, r = k - mat * 480, kt = r / 96, nt = (r >> 5) % 3, ln = r & 31, gg = ln >> 2, qq = ln & 3;
-            const int n = 8 * nt + gg;
-            double v = 0.0;
-            if (n < 20) v = mat == 0 ? ev[n * 20 + clv_k(kt, qq)] : iv[n * 20 + back_x(kt, qq)];
-            s_B[buf * 960 + k] = v;
-        }
-    };
-    if (!MIX) { if (BSM != 3) load_frags(0); if (BSM) load_frags_smem(0, 0); }
-    // BALANCED TILES: the Ppad/32 warp blocks are dealt out as `ntiles` tiles of floor or ceil(nblocks/ntiles) <= NW blocks each,
-    // with ntiles a multiple of the resident CTAs (host: enqueue_walk20).  A tile is a whole traversal (milliseconds of work),
-    // so with fixed 32*NW-pattern tiles the last wave leaves SMs idle (config 3: 782 tiles on 444 CTAs = 1.76 waves, SMs 88 %
-    // active); evenly smaller tiles keep every SM busy to the end at the price of a few idle warps per CTA.
-    const long long nblocks = D.Ppad >> 5;
-    for (;;) {
-        __syncthreads();
-        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
-        __syncthreads();
-        const long long tile = s_item;
-        if (tile >= ntiles) break;
-        // CSP (small problems: fewer 32-pattern blocks than resident CTAs): a tile is ONE block and the CTA's warps split its
-        // categories (warp w takes w, w+NW, ...), so that a traversal's latency drops by the number of categories in flight
-        const long long b0 = CSP ? tile : tile * nblocks / ntiles, b1 = CSP ? tile + 1 : (tile + 1) * nblocks / ntiles;
-        const long long p0 = CSP ? b0 * 32 : (b0 + warp) * 32;   // first pattern of this warp (multiple of 32)
-        const int csp_ncat = CSP ? (D.C - warp + NW - 1) / NW : 0;   // categories of this warp
-        const bool active = CSP ? csp_ncat > 0 : b0 + warp < b1;
-        const long long wbase = (p0 >> 5) * (long long)D.B * kWarp;   // the warp's 32-pattern block inside a CLV
-        const long long sbase = SAFE ? (p0 >> 5) * (long long)D.C * kWarp : p0;
-        unsigned may_mask = 0;
-        if (active) {
-#pragma unroll
-            for (int mt = 0; mt < 4; mt++) if (D.invar[p0 + 8 * mt + g] == 0.0) may_mask |= 1u << mt;
-        }
-        // header of the NEXT block is read one block ahead from global memory, so that issuing its copy and its tip-state
-        // loads never waits on memory; its tip states (one byte per pattern and tip child) are fetched during the current block
-        auto tip_states = [&](const int4 &hd, unsigned &sA, unsigned &sB) {
-            sA = sB = 0;
-            if (!active) return;
-            if (hd.y <= 1) {
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++) sA |= (unsigned)D.tips[(long long)hd.z * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
-            }
-            if (hd.y == 0) {
-#pragma unroll
-                for (int mt = 0; mt < 4; mt++) sB |= (unsigned)D.tips[(long long)hd.w * D.Ppad + p0 + 8 * mt + g] << (8 * mt);
-            }
-        };
-        // headers travel TWO blocks ahead: block v+1's header steers the copy and the tip-state loads issued right after the
-        // barrier of block v, so it must already sit in registers there (loaded one block ahead it exposed an L2 round trip
-        // per op: the long-scoreboard stalls of the per-op code in the ncu source view)
-        int4 h_next = *reinterpret_cast<const int4 *>(stage);
-        int4 h_next2 = nvo > 1 ? *reinterpret_cast<const int4 *>(stage + stage_sz) : h_next;
-        if (TMA) { if (tid == 0) stage20_fetch_tma(s_dyn20 + (size_t)(seq & 1) * stage_sz, stage, h_next.y, B, tab_doubles, &s_bar[seq & 1]); }
-        else stage20_fetch(s_dyn20, stage, h_next.y, B, tab_doubles, tid, NT);
-        unsigned stA_next, stB_next;
-        tip_states(h_next, stA_next, stB_next);
-        int m = 0;
-        for (int v = 0; v < nvo; v++, seq++) {
-            double *sb = s_dyn20 + (size_t)((TMA ? seq : (unsigned)v) & 1) * stage_sz;
-            const int4 h = h_next;
-            const unsigned stA = stA_next, stB = stB_next;
-            h_next = h_next2;
-            if (v + 2 < nvo) h_next2 = *reinterpret_cast<const int4 *>(stage + (size_t)(v + 2) * stage_sz);
-            if (MIX) { if (BSM != 3) load_frags(m); if (BSM) load_frags_smem(m, v & 1); }
-            if (TMA) mbar_wait(&s_bar[seq & 1], (seq >> 1) & 1);   // block v has landed (the mbarrier's phase of this use)
-            else cp_async_wait_all();
-            __syncthreads();   // block v has landed for every thread; everyone is done with block v-1's buffer
-            if (v + 1 < nvo) {
-                if (TMA) {
-                    if (tid == 0)
-                        stage20_fetch_tma(s_dyn20 + (size_t)((seq + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles,
-                                          &s_bar[(seq + 1) & 1]);
-                } else
-                    stage20_fetch(s_dyn20 + (size_t)((v + 1) & 1) * stage_sz, stage + (size_t)(v + 1) * stage_sz, h_next.y, B, tab_doubles, tid, NT);
-                if (!MIX || m + 1 == nblk) tip_states(h_next, stA_next, stB_next);   // the tips change with the op, not with the class
-            }
-            if (active) {
-                const int dst = h.x, ncase = h.y, aid = h.z, bid = h.w;
-                const double *s_exp = sb + 4, *s_tabA = sb + 4 + 2 * B, *s_tabB = s_tabA + tab_doubles;
-                const int class_off = CSP ? warp * kClv20Step : m * cpb * kClv20Step;
-                Walk20Op W;
-                W.Aq = D.partial + (long long)aid * D.slot_stride + wbase + class_off;   // only dereferenced when internal
-                W.Bq = D.partial + (long long)bid * D.slot_stride + wbase + class_off;
-                W.Oq = D.partial + (long long)dst * D.slot_stride + wbase + class_off;
-                const int sc_off = SAFE ? (CSP ? warp : m * cpb) * kWarp : 0;
-                W.Asc = D.scale + (long long)aid * D.scale_stride + sbase + sc_off + g;
-                W.Bsc = D.scale + (long long)bid * D.scale_stride + sbase + sc_off + g;
-                W.Osc = D.scale + (long long)dst * D.scale_stride + sbase + sc_off + g;
-                W.may_mask = may_mask;
-                W.stA = stA; W.stB = stB;
-                W.first_class = m == 0; W.last_class = m + 1 == nblk;
-                W.class_off = class_off; W.Ctot = D.C; W.s_mhi = CSP ? s_mhi + warp * 4 * kWarp : s_mhi;
-                W.sBe = s_B + (MIX ? (v & 1) * 960 : 0) + lane;
-                W.sBi = W.sBe + 480;
-                const int nc = CSP ? csp_ncat : cpb, cstep = CSP ? NW : 1, coff = CSP ? warp * 20 : 0;
-                const double *eAp = s_exp + coff, *eBp = s_exp + B + coff, *tAp = s_tabA + coff, *tBp = s_tabB + coff;
-                unsigned csp_sc[4] = {0, 0, 0, 0};
-                if (ncase == 2) walk20_mma_op<SAFE, MIX, 2, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
-                else if (ncase == 1) walk20_mma_op<SAFE, MIX, 1, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
-                else walk20_mma_op<SAFE, MIX, 0, BSM, DBG, CSP>(nc, cstep, W, Be, Bi, eAp, eBp, tAp, tBp, TS, lane, csp_sc);
-                if (CSP && !SAFE) {
-                    __syncthreads();   // every warp of the CTA is active or has no category at all (D.C < NW): see below
-                    walk20_csplit_finish(W, nc, cstep, ncase, D.C < NW ? D.C : NW, s_mhi, warp, lane, csp_sc);
-                }
-            } else if (CSP && !SAFE) {
-                __syncthreads();
-            }
-            if (MIX && ++m == nblk) m = 0;
-        }
-    }
-}
 
 // ------------------------------------------------------------------------------------------------------------
 // block reduction of up to 3 doubles per thread into red[blockIdx.x*3 + j]; a 1-CTA kernel sums the per-block
 // values in index order, so results are bit-reproducible for a given pattern count.
 // ------------------------------------------------------------------------------------------------------------
 template <int NV>
-__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red) {
+__device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red, long long blk = -1) {
+    if (blk < 0) blk = blockIdx.x;
     __shared__ double s_red[NV][32];
 #pragma unroll
     for (int j = 0; j < NV; j++)
@@ -1450,26 +945,27 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double *red)
             double x = lane < nw ? s_red[j][lane] : 0.0;
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
-            if (lane == 0) red[(long long)blockIdx.x * NV + j] = x;
+            if (lane == 0) red[blk * NV + j] = x;
         }
     }
 }
 
 // block_reduce_store + the final sum by the LAST block to arrive (ticket counter) in a fixed order (256 virtual threads, thread t
 // sums blocks t, t+256, ... in order, then a binary tree): bit-identical to the separate final-reduction launch it replaced.  `result` may be mapped host memory: the scalars land in the caller's buffer without a copy.
+// (blk, nblocks): this CTA's index among the CTAs that reduce into `result` — the whole grid, or one member of a grouped launch
 template <int NV>
-__device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red, unsigned *ticket, double *result) {
-    block_reduce_store<NV>(v, red);
+__device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red, unsigned *ticket, double *result, long long blk = -1, int nblocks = -1) {
+    if (blk < 0) { blk = blockIdx.x; nblocks = gridDim.x; }
+    block_reduce_store<NV>(v, red, blk);
     __shared__ bool s_last;
     __shared__ double s_fin[NV][256];
     if (threadIdx.x == 0) {
         __threadfence();
-        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        s_last = atomicAdd(ticket, 1u) == (unsigned)nblocks - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const int nblocks = gridDim.x;
     for (int vt = threadIdx.x; vt < 256; vt += blockDim.x) {
         double acc[NV];
 #pragma unroll
@@ -1501,13 +997,12 @@ __device__ __forceinline__ void block_reduce_finish(double (&v)[NV], double *red
 // ASC (Lewis' ascertainment-bias correction, tree/phylokernelnew.h:3076-3091): the unobserved constant patterns [Pobs, P)
 // contribute their likelihood (un-scaled once if their scale count is non-zero) to prob_const instead of to the tree logL; the
 // reduction then carries (tree_lh, prob_const) and k_asc_finish_logl applies logL -= nsite*log(1-prob_const) (:3198-3221).
-template <bool SAFE, bool ASC = false>
-__global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red,
-                                                unsigned *ticket, double *result, double length, int fuse_vals) {
-    extern __shared__ double s_vals_dyn[];
+template <bool SAFE, bool ASC>
+__device__ __forceinline__ void root_body(const Dev &D, long long blk, int nblocks, int node_slot, int dad_kind, int dad_id, int save_log, double *red,
+                                          unsigned *ticket, double *result, double length, int fuse_vals, double *s_vals_dyn) {
     const double *vals = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
     const int n = D.n, C = D.C;
-    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long p = blk * kTile + threadIdx.x;
     const long long cb = pbase(p, C);
     const long long sb = SAFE ? cb : p;
     const ClvIdx at(D, p);
@@ -1586,7 +1081,13 @@ __global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_ki
         else acc[ASC ? 1 : 0] = lhc;
         D.pattern_lh[p] = 0.0;
     }
-    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result, blk, nblocks);
+}
+template <bool SAFE, bool ASC = false>
+__global__ void __launch_bounds__(kTile) k_root(Dev D, int node_slot, int dad_kind, int dad_id, int save_log, double *red,
+                                                unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    root_body<SAFE, ASC>(D, blockIdx.x, gridDim.x, node_slot, dad_kind, dad_id, save_log, red, ticket, result, length, fuse_vals, s_vals_dyn);
 }
 
 // +ASC epilogues: raw = (tree_lh, prob_const) -> result[0] = logL, _pattern_lh -= log(1 - prob_const) (:3198-3221, 3412-3426);
@@ -1721,9 +1222,9 @@ __global__ void __launch_bounds__(kTile) k_asc_holder_derv(Dev D, const double *
 
 // computeLikelihoodBuffer{,Generic}SIMD (tree/phylokernelnew.h:2091-2230): theta_all and buffer_scale_all
 template <bool SAFE>
-__global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_kind, int dad_id) {
+__device__ __forceinline__ void theta_body(const Dev &D, long long blk, int node_slot, int dad_kind, int dad_id) {
     const int n = D.n, C = D.C, B = D.B;
-    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long p = blk * kTile + threadIdx.x;
     const long long pb = pbase(p, B);
     const long long sb = SAFE ? pbase(p, C) : p;
     const ClvIdx at(D, p);
@@ -1760,14 +1261,18 @@ __global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_k
     double bs = SAFE ? (double)min_scale : (double)(dsc[0] + (nsc ? nsc[0] : 0u));
     D.buffer_scale[p] = bs * kLogScalingThreshold;
 }
+template <bool SAFE>
+__global__ void __launch_bounds__(kTile) k_theta(Dev D, int node_slot, int dad_kind, int dad_id) {
+    theta_body<SAFE>(D, blockIdx.x, node_slot, dad_kind, dad_id);
+}
 
 // computeLikelihoodDerv{,Generic}SIMD pattern loop (tree/phylokernelnew.h:2463-2505): (lh, df, ddf) = val{0,1,2}.theta
-template <int BT, bool ASC = false>
-__global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
-    extern __shared__ double s_vals_dyn[];
+template <int BT, bool ASC>
+__device__ __forceinline__ void derv_body(const Dev &D, long long blk, int nblocks, double *red, unsigned *ticket, double *result, double length, int fuse_vals,
+                                          double *s_vals_dyn) {
     const double *vals = fuse_vals ? stage_vals(D, length, 1, s_vals_dyn) : D.val;
     const int B = BT ? BT : D.B;
-    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long p = blk * kTile + threadIdx.x;
     const double *theta = D.theta + pbase(p, B);
     const double *v0 = vals, *v1 = vals + B, *v2 = vals + 2 * B;
     // dotProductTriple: two lane accumulators (even / odd k)
@@ -1808,7 +1313,12 @@ __global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ti
             acc[ASC ? 2 : 0] = lh * f; acc[ASC ? 3 : 0] = df * f; acc[ASC ? 4 : 0] = ddf * f;
         }
     }
-    block_reduce_finish<ASC ? 5 : 2>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 5 : 2>(acc, red, ticket, result, blk, nblocks);
+}
+template <int BT, bool ASC = false>
+__global__ void __launch_bounds__(kTile) k_derv(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    derv_body<BT, ASC>(D, blockIdx.x, gridDim.x, red, ticket, result, length, fuse_vals, s_vals_dyn);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1963,12 +1473,12 @@ __global__ void __launch_bounds__(kTile) k_newton_coop(Dev D, double *red, doubl
 }
 
 // computeLikelihoodFromBuffer{,Generic}SIMD pattern loop (tree/phylokernelnew.h:3313-3368)
-template <int BT, bool ASC = false>
-__global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
-    extern __shared__ double s_vals_dyn[];
+template <int BT, bool ASC>
+__device__ __forceinline__ void from_buffer_body(const Dev &D, long long blk, int nblocks, double *red, unsigned *ticket, double *result, double length,
+                                                 int fuse_vals, double *s_vals_dyn) {
     const double *val0 = fuse_vals ? stage_vals(D, length, 0, s_vals_dyn) : D.val;
     const int B = BT ? BT : D.B;
-    const long long p = (long long)blockIdx.x * kTile + threadIdx.x;
+    const long long p = blk * kTile + threadIdx.x;
     const double *theta = D.theta + pbase(p, B);
     double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
     int k = 0;
@@ -1993,7 +1503,12 @@ __global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsig
         else acc[ASC ? 1 : 0] = lhc;
         D.pattern_lh[p] = 0.0;
     }
-    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result);
+    block_reduce_finish<ASC ? 2 : 1>(acc, red, ticket, result, blk, nblocks);
+}
+template <int BT, bool ASC = false>
+__global__ void __launch_bounds__(kTile) k_from_buffer(Dev D, double *red, unsigned *ticket, double *result, double length, int fuse_vals) {
+    extern __shared__ double s_vals_dyn[];
+    from_buffer_body<BT, ASC>(D, blockIdx.x, gridDim.x, red, ticket, result, length, fuse_vals, s_vals_dyn);
 }
 
 // layout converters for read-backs: device warp-interleaved -> reference V=1 layout [p*W + k]

@@ -18,7 +18,7 @@
 //     (a few per cent of the nodes at which a pattern rescales at all) take the exact path: W of that 8-pattern tile is
 //     computed from the just-stored t with the same 15 DMMAs the back pass used to cost everywhere.
 //
-// Fragment conventions are those of k_walk_n20_mma (b200lk_kernels.cuh): M = 8 patterns (row g = lane/4), K = 4 (slot q = lane%4),
+// Fragment conventions are those of the DMMA helpers in b200lk_kernels.cuh: M = 8 patterns (row g = lane/4), K = 4 (slot q = lane%4),
 // N = 8 states; CLVs fragment-major (clv20_off), loaded back as A fragments in the K order clv_k(kt, q).
 #pragma once
 #include "b200lk_kernels.cuh"
@@ -41,15 +41,10 @@ __host__ __device__ inline size_t ss_stage_used(int cpb, int su, int ncase) {
     return 4 + ss_part_doubles(cpb, su, ncase <= 1) + ss_part_doubles(cpb, su, ncase == 0);
 }
 
-// One CTA per (op, class block): exp(eval r_c len), the tip tables exactly as k_walk_info_n20 builds them
+// One CTA per (op, class block): exp(eval r_c len), the tip tables (the reference's partial_lh_leaves)
 // (tree/phylokernelnew.h:1036-1056), and P_c(len) = evec . diag(exp) . inv_evec for internal children.
-__global__ void __launch_bounds__(256) k_walk_info_n20ss(Dev D, const WalkJob20 *jobs, double *stage, unsigned long long *counter) {
-    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ULL;
-    extern __shared__ double s_exp20[];   // [2][cpb*20]
+__device__ __forceinline__ void walk_info20ss_body(const Dev &D, const WalkJob20 &job, double *st, const int m, double *s_exp20) {
     const int nblk = D.nmix, cpb = D.C / nblk, B = cpb * 20, TS = tab20_stride(cpb);
-    const int op = blockIdx.x / nblk, m = blockIdx.x - op * nblk;
-    const WalkJob20 job = jobs[op];
-    double *st = stage + (size_t)blockIdx.x * ss_stage_doubles(cpb, D.su);
     for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
         const int ch = k / B, kk = k - ch * B, r = kk / 20, i = kk - r * 20;
         const int c = m * cpb + r;
@@ -104,6 +99,13 @@ __global__ void __launch_bounds__(256) k_walk_info_n20ss(Dev D, const WalkJob20 
         }
     }
 }
+__global__ void __launch_bounds__(256) k_walk_info_n20ss(Dev D, const WalkJob20 *jobs, double *stage, unsigned long long *counter) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) *counter = 0ULL;
+    extern __shared__ double s_exp20[];   // [2][cpb*20]
+    const int nblk = D.nmix, cpb = D.C / nblk;
+    const int op = blockIdx.x / nblk, m = blockIdx.x - op * nblk;
+    walk_info20ss_body(D, jobs[op], stage + (size_t)blockIdx.x * ss_stage_doubles(cpb, D.su), m, s_exp20);
+}
 
 // inv_evec as B fragments of the transform W = inv_evec . t, per class: [m][(kt*3 + nt)][lane] = inv_evec_m[i = 8nt+g][x = clv_k(kt,q)]
 __global__ void k_inv_frag20(Dev D, double *frag) {
@@ -117,7 +119,7 @@ __global__ void k_inv_frag20(Dev D, double *frag) {
 // max over i of |(inv_evec . t)[p][i]| as exponent word, for the 8 patterns of one (M-tile, category) block of 160 doubles that
 // THIS warp has just written (or wrote in an earlier class block); every lane returns the value of its pattern g.
 __device__ __forceinline__ unsigned eigen_max20(const double *blk, const double *frag, int lane) {
-    const int g = lane >> 2, q = lane & 3, lo2 = (q * 8 + g) * 2;
+    const int g = lane >> 2, q = lane & 3, lo2 = lane * 2;
     const double2 v0 = *reinterpret_cast<const double2 *>(blk + lo2), v1 = *reinterpret_cast<const double2 *>(blk + 64 + lo2);
     const double f[5] = {v0.x, v0.y, v1.x, v1.y, blk[128 + lane]};
     double o[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
@@ -161,22 +163,33 @@ struct Walk20ssOp {
 };
 
 // NORM_LH decision for M-tile mt given the pattern's max|t| exponent word over ALL categories (every lane of the pattern holds
-// it): tree/phylokernelnew.h:2015-2029.  `mine(cc)` says whether this warp wrote category cc (category split: not all).
-template <typename Mine>
-__device__ __forceinline__ bool norm_decide20(const Dev &D, const Walk20ssOp &W, int mt, unsigned mhi, int lane, Mine mine) {
-    const int g = lane >> 2, q = lane & 3, lo2 = (q * 8 + g) * 2, lot = 128 + g * 4 + 2 * q;
+// it): tree/phylokernelnew.h:2015-2029.  Two steps, because with a category split the warps of a block must all have taken the
+// decision (the exact path READS every category) before any of them rescales what it wrote.
+__device__ __forceinline__ bool norm_test20(const Dev &D, const Walk20ssOp &W, int mt, unsigned mhi, int lane) {
     const bool may = (W.may_mask >> mt) & 1u;
     bool lo = may && mhi < D.ss_lo;
     const bool band = may && !lo && mhi < D.ss_hi;
-    double *tile = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
     if (__any_sync(0xffffffffu, band)) {   // exact: max|W| over every category of the pattern
+        const double *tile = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
         __syncwarp();
         unsigned chi = 0u;
         for (int cc = 0; cc < W.Ctot; cc++) chi = max(chi, eigen_max20(tile + (size_t)cc * kClv20Step, W.inv_frag + (size_t)(cc / W.cpb) * 480, lane));
         if (band) lo = chi < kThresholdHi;
     }
-    if (lo)
-        for (int cc = 0; cc < W.Ctot; cc++) if (mine(cc)) rescale20(tile + (size_t)cc * kClv20Step, lo2, lot, q);
+    return lo;
+}
+// `mine(cc)` says whether this warp wrote category cc (category split: not all)
+template <typename Mine>
+__device__ __forceinline__ void norm_apply20(const Walk20ssOp &W, int mt, bool lo, int lane, Mine mine) {
+    if (!lo) return;
+    const int g = lane >> 2, q = lane & 3, lo2 = lane * 2, lot = 128 + g * 4 + 2 * q;
+    double *tile = W.Oq + (size_t)mt * W.Ctot * kClv20Step;
+    for (int cc = 0; cc < W.Ctot; cc++) if (mine(cc)) rescale20(tile + (size_t)cc * kClv20Step, lo2, lot, q);
+}
+template <typename Mine>
+__device__ __forceinline__ bool norm_decide20(const Dev &D, const Walk20ssOp &W, int mt, unsigned mhi, int lane, Mine mine) {
+    const bool lo = norm_test20(D, W, mt, mhi, lane);
+    norm_apply20(W, mt, lo, lane, mine);
     return lo;
 }
 
@@ -187,7 +200,7 @@ template <bool SAFE, bool MIX, int NCASE, bool CSP>
 __device__ __forceinline__ void walk20ss_op(const Dev &D, const int C, const int c0, const int cstep, const Walk20ssOp &W, const double *sA,
                                             const double *sB, const int TS, const int lane, unsigned (&mhi_out)[4], unsigned (&sc_out)[4]) {
     const int g = lane >> 2, q = lane & 3;
-    const int lo2 = (q * 8 + g) * 2, lot = 128 + g * 4 + 2 * q;
+    const int lo2 = lane * 2, lot = 128 + g * 4 + 2 * q;
     const long long mt_stride = (long long)W.Ctot * kClv20Step;
     const int coff = (W.first_class ? 0 : 0);   // (class offset is folded into Aq/Bq/Oq by the caller)
     (void)coff;
@@ -329,7 +342,7 @@ __device__ __forceinline__ void walk20ss_op(const Dev &D, const int C, const int
     }
 }
 
-// NW warps per CTA; tile = up to NW 32-pattern blocks (balanced tiles, as k_walk_n20_mma) or, with CSP (small problems), ONE
+// NW warps per CTA; tile = up to NW 32-pattern blocks (balanced tiles) or, with CSP (small problems), ONE
 // block whose categories the warps split.  Staging: one TMA bulk load per (op, class block) into a 2-deep ring, completion on
 // an mbarrier per buffer.
 template <bool SAFE, bool MIX, int NW, int MINB, bool CSP>
@@ -439,18 +452,25 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20ss(Dev D, const doubl
                     for (int mt = 0; mt < 4; mt++) s_mhi[(warp * 4 + mt) * kWarp + lane] = mh[mt];
                 }
                 __syncthreads();   // also orders the warps' CLV stores for the exact path
+                bool lo4[4] = {false, false, false, false};
                 if (active) {
-                    const int nwarps = D.C < NW ? D.C : NW, q = lane & 3;
+                    const int nwarps = D.C < NW ? D.C : NW;
 #pragma unroll
                     for (int mt = 0; mt < 4; mt++) {
                         unsigned mm = 0;
                         for (int w = 0; w < nwarps; w++) mm = max(mm, s_mhi[(w * 4 + mt) * kWarp + lane]);
-                        unsigned s = sc[mt];
-                        if (ncase != 0 && norm_decide20(D, W, mt, mm, lane, [&](int cc) { return cc % NW == warp; })) s += 1;
-                        if (warp == 0 && q == 0) W.Osc[8 * mt] = (uint16_t)s;
+                        lo4[mt] = ncase != 0 && norm_test20(D, W, mt, mm, lane);
                     }
                 }
-                __syncthreads();   // s_mhi is rewritten by the next op
+                __syncthreads();   // every warp has decided (the exact path read all categories) before anyone rescales
+                if (active) {
+                    const int q = lane & 3;
+#pragma unroll
+                    for (int mt = 0; mt < 4; mt++) {
+                        norm_apply20(W, mt, lo4[mt], lane, [&](int cc) { return cc % NW == warp; });
+                        if (warp == 0 && q == 0) W.Osc[8 * mt] = (uint16_t)(sc[mt] + (lo4[mt] ? 1u : 0u));
+                    }
+                }
             }
             if (MIX && ++m == nblk) m = 0;
         }
@@ -459,43 +479,46 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_walk_n20ss(Dev D, const doubl
 
 // W = inv_evec . t for one CLV slot (same fragment-major layout) + its scale counts: what the root / theta kernels and
 // b200lk_get_partial read.  One warp per 32-pattern block.
-__global__ void __launch_bounds__(128) k_clv20_to_eigen(Dev D, int src, int dst) {
+__device__ __forceinline__ void clv20_to_eigen_block(const Dev &D, int src, int dst, long long blk) {
+    if (blk >= (D.Ppad >> 5)) return;
     const int lane = threadIdx.x & 31, g = lane >> 2, q = lane & 3;
-    const int lo2 = (q * 8 + g) * 2, lot = 128 + g * 4 + 2 * q;
-    const long long nblocks = D.Ppad >> 5;
+    const int lo2 = lane * 2, lot = 128 + g * 4 + 2 * q;
     const int cpb = D.C / D.nmix;
     const double *S = D.partial + (long long)src * D.slot_stride;
     double *O = D.partial + (long long)dst * D.slot_stride;
-    for (long long blk = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblocks; blk += (long long)gridDim.x * (blockDim.x >> 5)) {
-        const long long base = blk * (long long)D.B * kWarp;
-        for (int m = 0; m < D.nmix; m++) {
-            double Bi[5][3];
+    const long long base = blk * (long long)D.B * kWarp;
+    for (int m = 0; m < D.nmix; m++) {
+        double Bi[5][3];
 #pragma unroll
-            for (int kt = 0; kt < 5; kt++)
+        for (int kt = 0; kt < 5; kt++)
 #pragma unroll
-                for (int nt = 0; nt < 3; nt++) Bi[kt][nt] = __ldg(D.inv_frag20 + (size_t)m * 480 + (kt * 3 + nt) * kWarp + lane);
-            for (int mt = 0; mt < 4; mt++)
-                for (int r = 0; r < cpb; r++) {
-                    const long long off = base + ((long long)mt * D.C + m * cpb + r) * kClv20Step;
-                    const double *p = S + off;
-                    const double2 v0 = *reinterpret_cast<const double2 *>(p + lo2), v1 = *reinterpret_cast<const double2 *>(p + 64 + lo2);
-                    const double f[5] = {v0.x, v0.y, v1.x, v1.y, p[128 + lane]};
-                    double o[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+            for (int nt = 0; nt < 3; nt++) Bi[kt][nt] = __ldg(D.inv_frag20 + (size_t)m * 480 + (kt * 3 + nt) * kWarp + lane);
+        for (int mt = 0; mt < 4; mt++)
+            for (int r = 0; r < cpb; r++) {
+                const long long off = base + ((long long)mt * D.C + m * cpb + r) * kClv20Step;
+                const double *p = S + off;
+                const double2 v0 = *reinterpret_cast<const double2 *>(p + lo2), v1 = *reinterpret_cast<const double2 *>(p + 64 + lo2);
+                const double f[5] = {v0.x, v0.y, v1.x, v1.y, p[128 + lane]};
+                double o[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
 #pragma unroll
-                    for (int kt = 0; kt < 5; kt++)
+                for (int kt = 0; kt < 5; kt++)
 #pragma unroll
-                        for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(o[nt][0], o[nt][1], f[kt], Bi[kt][nt]);
-                    double *po = O + off;
-                    *reinterpret_cast<double2 *>(po + lo2) = make_double2(o[0][0], o[0][1]);
-                    *reinterpret_cast<double2 *>(po + 64 + lo2) = make_double2(o[1][0], o[1][1]);
-                    if (q < 2) *reinterpret_cast<double2 *>(po + lot) = make_double2(o[2][0], o[2][1]);
-                }
-        }
-        const long long sb = blk * (long long)D.S * kWarp;
-        const uint16_t *ss = D.scale + (long long)src * D.scale_stride + sb;
-        uint16_t *os = D.scale + (long long)dst * D.scale_stride + sb;
-        for (int k = lane; k < D.S * kWarp; k += kWarp) os[k] = ss[k];
+                    for (int nt = 0; nt < 3; nt++) dmma_m8n8k4(o[nt][0], o[nt][1], f[kt], Bi[kt][nt]);
+                double *po = O + off;
+                *reinterpret_cast<double2 *>(po + lo2) = make_double2(o[0][0], o[0][1]);
+                *reinterpret_cast<double2 *>(po + 64 + lo2) = make_double2(o[1][0], o[1][1]);
+                if (q < 2) *reinterpret_cast<double2 *>(po + lot) = make_double2(o[2][0], o[2][1]);
+            }
     }
+    const long long sb = blk * (long long)D.S * kWarp;
+    const uint16_t *ss = D.scale + (long long)src * D.scale_stride + sb;
+    uint16_t *os = D.scale + (long long)dst * D.scale_stride + sb;
+    for (int k = lane; k < D.S * kWarp; k += kWarp) os[k] = ss[k];
+}
+__global__ void __launch_bounds__(128) k_clv20_to_eigen(Dev D, int src, int dst) {
+    const long long nblocks = D.Ppad >> 5;
+    for (long long blk = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); blk < nblocks; blk += (long long)gridDim.x * (blockDim.x >> 5))
+        clv20_to_eigen_block(D, src, dst, blk);
 }
 
 }  // namespace b200lk

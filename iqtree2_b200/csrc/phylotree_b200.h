@@ -134,6 +134,14 @@ public:
     virtual double computeLikelihoodFromBuffer();
     // asynchronous forms for partition models (b200lk_enqueue_* / b200lk_finish): same planning and flag updates as the
     // synchronous members, the device work is only queued on the engine's stream; finish() waits and returns the scalars
+    // the same three steps for a GROUPED evaluation (b200lk_group_*: all partition trees of a super tree in O(1) launches): plan*
+    // fills traversal_info and says what to evaluate; the caller hands the plans of all members to ONE b200lk_group_enqueue_* call
+    // and then reports the outcome with planDone / planFailed (the roll-back of checkPlanned)
+    struct EvalPlan { const b200lk_op *ops; int32_t nops, node_slot, dad_kind, dad_id; double length; };
+    void planLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, EvalPlan &out);
+    void planLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad, EvalPlan &out);
+    void planDone(bool derv);
+    void planFailed();
     void enqueueLikelihoodBranch(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value = true);
     void enqueueLikelihoodDerv(PhyloNeighbor *dad_branch, PhyloNode *dad);
     void enqueueLikelihoodFromBuffer();

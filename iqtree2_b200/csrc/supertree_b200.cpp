@@ -16,6 +16,31 @@
 
 namespace b200 {
 
+namespace {
+// run f(part) for every partition from OpenMP threads (the reference's `omp parallel for schedule(dynamic)` over part_order),
+// carrying the first exception out of the parallel region
+template <class F>
+void for_each_partition(const std::vector<int> &order, int num_threads, F f) {
+    std::exception_ptr err;
+    const int n = (int)order.size();
+#ifdef _OPENMP
+    const int nt = num_threads > 0 ? num_threads : std::min(omp_get_max_threads(), 16);
+#pragma omp parallel for schedule(dynamic) num_threads(nt) if (n > 1 && nt > 1)
+#endif
+    for (int j = 0; j < n; j++) {
+        try { f(order[j]); }
+        catch (...) {
+#ifdef _OPENMP
+#pragma omp critical(b200_supertree_err)
+#endif
+            if (!err) err = std::current_exception();
+        }
+    }
+    (void)num_threads;
+    if (err) std::rethrow_exception(err);
+}
+}  // namespace
+
 PhyloSuperTreePlen::PhyloSuperTreePlen() {
     // One stream per partition only overlaps if the streams do not share hardware work queues: the driver's default is 8
     // connections, on which 500 partition streams serialise each other (config 5: 29.7 ms per evaluation against 18.9 ms with
@@ -27,7 +52,59 @@ PhyloSuperTreePlen::PhyloSuperTreePlen() {
 }
 
 PhyloSuperTreePlen::~PhyloSuperTreePlen() {
+    dropGroup();
     for (auto *p : parts) delete p;
+}
+
+void PhyloSuperTreePlen::dropGroup() {
+    if (group_) b200lk_group_destroy(group_);
+    group_ = nullptr;
+    group_engines_.clear();
+}
+
+// all partitions on one device -> one group over their engines (created by the partitions' initializeAllPartialLh)
+bool PhyloSuperTreePlen::ensureGroup() {
+    if (!use_group || parts.empty() || getenv("B200ST_NO_GROUP")) return false;
+    // a partition tree re-creates its engine when its alignment / model shape changes: the group follows
+    std::vector<b200lk_engine *> engines;
+    for (auto *p : parts) {
+        p->initializeAllPartialLh();
+        if (!p->engine() || p->params.device != parts[0]->params.device || p->params.device < 0) { dropGroup(); return false; }
+        engines.push_back(p->engine());
+    }
+    if (group_ && engines == group_engines_) return true;
+    dropGroup();
+    if (b200lk_group_create(engines.data(), (int32_t)engines.size(), &group_) != 0)
+        throw std::runtime_error(std::string("b200lk_group_create: ") + b200lk_group_last_error(nullptr));
+    group_engines_ = engines;
+    return true;
+}
+
+// what: 1 = branch logL, 2 = branch derivatives, 3 = logL from the theta buffers.  plan(p, EvalPlan&) runs on host threads.
+template <class PlanFn>
+void PhyloSuperTreePlen::groupEvaluate(int what, PlanFn plan, double *logl, double *df, double *ddf) {
+    const size_t np = parts.size();
+    std::vector<PhyloTree::EvalPlan> plans(np);
+    std::vector<const b200lk_op *> ops(np);
+    std::vector<int32_t> nops(np), node_slot(np), dad_kind(np), dad_id(np);
+    std::vector<double> length(np);
+    if (what != 3) for_each_partition(part_order, num_threads, [&](int p) { plan(p, plans[p]); });
+    for (size_t p = 0; p < np; p++) {
+        if (what == 3) { length[p] = parts[p]->current_it->length; continue; }
+        ops[p] = plans[p].ops; nops[p] = plans[p].nops; node_slot[p] = plans[p].node_slot; dad_kind[p] = plans[p].dad_kind;
+        dad_id[p] = plans[p].dad_id; length[p] = plans[p].length;
+    }
+    int rc;
+    if (what == 1) rc = b200lk_group_enqueue_branch_logl(group_, ops.data(), nops.data(), node_slot.data(), dad_kind.data(), dad_id.data(), length.data(), 1);
+    else if (what == 2) rc = b200lk_group_enqueue_branch_derv(group_, ops.data(), nops.data(), node_slot.data(), dad_kind.data(), dad_id.data(), length.data());
+    else rc = b200lk_group_enqueue_logl_from_buffer(group_, length.data());
+    if (rc >= 0) rc = b200lk_group_finish(group_, logl, df, ddf, nullptr);
+    if (rc < 0) {
+        const std::string msg = std::string("grouped evaluation: ") + b200lk_group_last_error(group_);
+        if (what != 3) for (auto *p : parts) p->planFailed();
+        throw std::runtime_error(msg);
+    }
+    if (what != 3) for (auto *p : parts) p->planDone(what == 2);
 }
 
 void PhyloSuperTreePlen::setTaxa(const std::vector<std::string> &names) {
@@ -40,6 +117,7 @@ void PhyloSuperTreePlen::setTaxa(const std::vector<std::string> &names) {
 }
 
 int PhyloSuperTreePlen::addPartition(PhyloTree *part, double rate) {
+    dropGroup();
     parts.push_back(part);
     part_rate.push_back(rate);
     cur_score.push_back(0.0);
@@ -114,34 +192,18 @@ void PhyloSuperTreePlen::setPartLengths(double value) {
     }
 }
 
-namespace {
-// run f(part) for every partition from OpenMP threads (the reference's `omp parallel for schedule(dynamic)` over part_order),
-// carrying the first exception out of the parallel region
-template <class F>
-void for_each_partition(const std::vector<int> &order, int num_threads, F f) {
-    std::exception_ptr err;
-    const int n = (int)order.size();
-#ifdef _OPENMP
-    const int nt = num_threads > 0 ? num_threads : std::min(omp_get_max_threads(), 16);
-#pragma omp parallel for schedule(dynamic) num_threads(nt) if (n > 1 && nt > 1)
-#endif
-    for (int j = 0; j < n; j++) {
-        try { f(order[j]); }
-        catch (...) {
-#ifdef _OPENMP
-#pragma omp critical(b200_supertree_err)
-#endif
-            if (!err) err = std::current_exception();
-        }
-    }
-    (void)num_threads;
-    if (err) std::rethrow_exception(err);
-}
-}  // namespace
 
 double PhyloSuperTreePlen::computeFunction(double value) {
     computePartitionOrder();
+    const bool grouped = ensureGroup();   // (may initialise the partitions' buffers: before the branch is linked)
     setPartLengths(value);
+    if (grouped) {
+        groupEvaluate(1, [&](int p, PhyloTree::EvalPlan &pl) { parts[p]->planLikelihoodBranch(parts[p]->current_it_back, parts[p]->current_it->node, pl); },
+                      cur_score.data(), nullptr, nullptr);
+        double lh = 0.0;
+        for (size_t p = 0; p < parts.size(); p++) lh += cur_score[p];   // summed in partition order
+        return -lh;
+    }
     for_each_partition(part_order, num_threads, [&](int p) {
         parts[p]->enqueueLikelihoodBranch(parts[p]->current_it_back, parts[p]->current_it->node);   // (nei2_part, nei1_part->node), :339
     });
@@ -177,7 +239,21 @@ double PhyloSuperTreePlen::computeLikelihoodFromBuffer() {
 
 void PhyloSuperTreePlen::computeFuncDerv(double value, double &df_ret, double &ddf_ret) {
     computePartitionOrder();
+    const bool grouped = ensureGroup();
     setPartLengths(value);
+    if (grouped) {
+        std::vector<double> d1(parts.size(), 0.0), d2(parts.size(), 0.0);
+        groupEvaluate(2, [&](int p, PhyloTree::EvalPlan &pl) { parts[p]->planLikelihoodDerv(parts[p]->current_it_back, parts[p]->current_it->node, pl); },
+                      nullptr, d1.data(), d2.data());
+        double gdf = 0.0, gddf = 0.0;
+        for (size_t p = 0; p < parts.size(); p++) {
+            gdf += part_rate[p] * d1[p];                     // :398-399
+            gddf += part_rate[p] * part_rate[p] * d2[p];
+        }
+        df_ret = -gdf;
+        ddf_ret = -gddf;
+        return;
+    }
     for_each_partition(part_order, num_threads, [&](int p) {
         parts[p]->enqueueLikelihoodDerv(parts[p]->current_it_back, parts[p]->current_it->node);   // :397
     });
@@ -203,10 +279,16 @@ void PhyloSuperTreePlen::optimizeOneBranch(PhyloNode *node1, PhyloNode *node2, b
     PhyloTree::optimizeOneBranch(node1, node2, false, maxNRStep);   // :276
     // minimizeNewton may return the point BEFORE the last one it evaluated; bring the partition branches to the final length
     // (the reference leaves them at the last evaluated point, a drift below the Newton tolerance)
+    const bool grouped = ensureGroup();
     setPartLengths(current_it->length);
     computePartitionOrder();
-    for_each_partition(part_order, num_threads, [&](int p) { parts[p]->enqueueLikelihoodFromBuffer(); });   // :283-290
-    for (size_t p = 0; p < parts.size(); p++) parts[p]->finish(&cur_score[p], nullptr, nullptr);
+    if (grouped) {
+        for (auto *p : parts) if (!p->theta_computed || !p->current_it) throw std::runtime_error("computeLikelihoodFromBuffer: theta_all is not computed");
+        groupEvaluate(3, [](int, PhyloTree::EvalPlan &) {}, cur_score.data(), nullptr, nullptr);
+    } else {
+        for_each_partition(part_order, num_threads, [&](int p) { parts[p]->enqueueLikelihoodFromBuffer(); });   // :283-290
+        for (size_t p = 0; p < parts.size(); p++) parts[p]->finish(&cur_score[p], nullptr, nullptr);
+    }
     if (clearLH && current_len != current_it->length) {   // :292-302
         for (size_t p = 0; p < parts.size(); p++) {
             PhyloNeighbor *n1, *n2;
@@ -223,6 +305,7 @@ double PhyloSuperTreePlen::optimizeAllBranches(int my_iterations, double toleran
 }
 
 int64_t PhyloSuperTreePlen::launches() const {
+    if (group_) return b200lk_group_launch_count(group_);
     int64_t n = 0;
     for (auto *p : parts) if (p->engine()) n += b200lk_launch_count(p->engine());
     return n;

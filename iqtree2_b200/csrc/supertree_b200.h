@@ -59,8 +59,17 @@ public:
     std::vector<double> cur_score;   // part_info[part].cur_score
     int num_threads = 0;             // host threads that queue partition work (0 = OpenMP default)
     int64_t launches() const;        // kernel launches of all partition engines
+    // grouped launches (b200lk_group_*): one launch per kernel type for all partitions instead of one stream and ~5 launches per
+    // partition.  On by default when all partitions sit on one device; B200ST_NO_GROUP=1 (or use_group = false before the first
+    // evaluation) keeps the per-partition streams.
+    bool use_group = true;
 
 private:
+    b200lk_group *group_ = nullptr;
+    std::vector<b200lk_engine *> group_engines_;   // the members the group was built over
+    bool ensureGroup();
+    void dropGroup();
+    template <class PlanFn> void groupEvaluate(int what, PlanFn plan, double *logl, double *df, double *ddf);
     void linkBranch(int part, PhyloNeighbor *&nei1_part, PhyloNeighbor *&nei2_part) const;
     void setPartLengths(double value);
     std::vector<int> part_order;     // PhyloSuperTree::computePartitionOrder: decreasing cost

@@ -28,6 +28,8 @@ ABI_SYMBOLS = [
     "b200lk_set_boot_samples", "b200lk_rell", "b200lk_set_extra_children", "b200lk_set_ascertainment", "b200lk_set_robust_phylo", "b200lk_em_posterior",
     "b200lk_set_pattern_freq_from_posterior",
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
+    "b200lk_group_create", "b200lk_group_destroy", "b200lk_group_last_error", "b200lk_group_enqueue_branch_logl",
+    "b200lk_group_enqueue_branch_derv", "b200lk_group_enqueue_logl_from_buffer", "b200lk_group_finish", "b200lk_group_launch_count",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2

@@ -176,3 +176,54 @@ int b200lk_get_pattern_lh_cat(b200lk_engine *e, double *out) { return orc_get_pa
 int b200lk_get_scale_num(b200lk_engine *e, int32_t slot, uint16_t *out) { return orc_get_scale_num(e->o, slot, out); }
 int64_t b200lk_launch_count(const b200lk_engine *e) { return e->calls; }
 int64_t b200lk_device_bytes(const b200lk_engine *e) { (void)e; return 0; }
+
+/* ---- grouped evaluation (include/b200lk.h b200lk_group_*): the checker simply loops over the members ----------------------- */
+struct b200lk_group { b200lk_engine **m; int n; int64_t calls; char err[256]; };
+int b200lk_group_create(b200lk_engine *const *engines, int32_t n, b200lk_group **out) {
+    b200lk_group *g = (b200lk_group *)calloc(1, sizeof *g);
+    g->m = (b200lk_engine **)calloc((size_t)n, sizeof *g->m);
+    for (int k = 0; k < n; k++) g->m[k] = engines[k];
+    g->n = n;
+    *out = g;
+    return 0;
+}
+void b200lk_group_destroy(b200lk_group *g) { if (g) { free(g->m); free(g); } }
+const char *b200lk_group_last_error(const b200lk_group *g) { return g ? g->err : g_err; }
+int64_t b200lk_group_launch_count(const b200lk_group *g) { int64_t t = g->calls; for (int k = 0; k < g->n; k++) t += g->m[k]->calls; return t; }
+static int gerr(b200lk_group *g, int k, int rc) { snprintf(g->err, sizeof g->err, "member %d: %s", k, b200lk_last_error(g->m[k])); return rc; }
+int b200lk_group_enqueue_branch_logl(b200lk_group *g, const b200lk_op *const *ops, const int32_t *nops, const int32_t *node_slot,
+                                     const int32_t *dad_kind, const int32_t *dad_id, const double *length, int32_t save_log_value) {
+    g->calls++;
+    for (int k = 0; k < g->n; k++) {
+        int rc = b200lk_enqueue_branch_logl(g->m[k], ops[k], nops[k], node_slot[k], dad_kind[k], dad_id[k], length[k], save_log_value);
+        if (rc < 0) return gerr(g, k, rc);
+    }
+    return 0;
+}
+int b200lk_group_enqueue_branch_derv(b200lk_group *g, const b200lk_op *const *ops, const int32_t *nops, const int32_t *node_slot,
+                                     const int32_t *dad_kind, const int32_t *dad_id, const double *length) {
+    g->calls++;
+    for (int k = 0; k < g->n; k++) {
+        int rc = b200lk_enqueue_branch_derv(g->m[k], ops[k], nops[k], node_slot[k], dad_kind[k], dad_id[k], length[k]);
+        if (rc < 0) return gerr(g, k, rc);
+    }
+    return 0;
+}
+int b200lk_group_enqueue_logl_from_buffer(b200lk_group *g, const double *length) {
+    g->calls++;
+    for (int k = 0; k < g->n; k++) {
+        int rc = b200lk_enqueue_logl_from_buffer(g->m[k], length[k]);
+        if (rc < 0) return gerr(g, k, rc);
+    }
+    return 0;
+}
+int b200lk_group_finish(b200lk_group *g, double *logl, double *df, double *ddf, int32_t *status) {
+    int worst = 0;
+    for (int k = 0; k < g->n; k++) {
+        int rc = b200lk_finish(g->m[k], logl ? logl + k : NULL, df ? df + k : NULL, ddf ? ddf + k : NULL);
+        if (rc < 0) return gerr(g, k, rc);
+        if (status) status[k] = rc;
+        if (rc > worst) worst = rc;
+    }
+    return worst;
+}

@@ -9,6 +9,7 @@
 //
 // The reference's class cannot be given new members without editing its header, so the shim members live in a derived class
 // and are stored in the base's pointers-to-member by static_cast (valid: every object they are called on is a PhyloTreeB200).
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -88,6 +89,9 @@ public:
         const size_t U = model_factory->unobserved_ptns.size();   // +ASC: appended as the engine's last patterns
         cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = leafNum; cfg.nptn = (int64_t)(aln->size() + U);
         cfg.nslots = (leafNum - 2) + 2; cfg.device = 0;
+        // Params::num_threads' counterpart for devices: B200LK_NDEV=N puts the tree on the first N GPUs (cfg.device = -N: one
+        // engine per device over pattern slices behind the same handle, include/b200lk.h)
+        if (const char *nd = getenv("B200LK_NDEV")) if (atoi(nd) > 1 && U == 0) cfg.device = -atoi(nd);
         if (b200lk_create(&cfg, &b200) != 0) outError(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
         const size_t nobs = aln->size(), nptn = nobs + U;
         std::vector<uint8_t> states((size_t)leafNum * nptn);

@@ -64,3 +64,105 @@ def test_baseline_config_at_full_size(workload):
     ll2 = g.branch_logl(ops2, a2, b2, L2)
     assert abs(ll2 - ll) < 1e-9 * abs(ll), (ll, ll2)
     g.close()
+
+
+def test_config4_c60_at_full_size_with_mem_save():
+    """BASELINE config 4 (100 taxa x 50 000 patterns, LG+C60+G4: 240 categories, 1.92 GB per CLV) as bench.py runs it: the
+    reference's -mem mode (LM_MEM_SAVE) planned by the host mirror, slots recycled inside one traversal."""
+    import torch
+    from iqtree2_b200.phylotree import PhyloTree
+    ntaxa, nptn, mk, _ = bench.WORKLOADS["aa_100x50k_lg_c60_g4"]
+    model = mk()
+    B = model.nstates * model.ncat_mix
+    slot_bytes = ((nptn + 127) // 128 * 128) * (8 * B + 2)
+    dev_total = torch.cuda.get_device_properties(0).total_memory
+    mem_frac = min(1.0, (0.70 * dev_total / slot_bytes - 4) / (ntaxa - 2))
+    if mem_frac * (ntaxa - 2) < 12:
+        pytest.skip("device memory too small for the full-size workload")
+    tree, tips, freq, _ = bench.make_inputs(ntaxa, nptn, model)
+    pt = PhyloTree()
+    pt.set_plan_only(True)
+    pt.set_alignment(tree.names, np.zeros((ntaxa, 1), dtype=np.uint8), np.ones(1), model)
+    pt.set_model(model)
+    pt.read_tree(tree.to_newick(fmt="%.17g"))   # the exact branch lengths
+    pt.set_mem_save(True, mem_frac)
+    nslots = pt.max_lh_slots + 2
+    assert nslots - 2 < ntaxa - 2, "this test is about recycled slots"
+    pa, pb, _ = pt.branches()
+    pbr = [k for k in range(len(pa)) if min(pa[k], pb[k]) == 0][0]
+    ops, a, b, L = pt.plan_branch(pbr)
+    assert len(ops) == ntaxa - 2
+    try:
+        g = LikelihoodEngine(model, ntaxa, nptn, nslots=nslots)
+    except Exception as ex:
+        if "cudaMalloc" in str(ex) or "memory" in str(ex).lower():
+            pytest.skip(f"device memory not available for the full-size workload: {ex}")
+        raise
+    g.set_tip_states(tips); g.set_pattern_freq(freq); g.set_pattern_invar(np.zeros(nptn))
+    ll = g.branch_logl(ops, a, b, L)
+    plh = g.get_pattern_lh()
+    assert np.isfinite(ll) and abs(float(plh.sum()) - ll) < 1e-9 * abs(ll)
+    sc_full = g.get_scale_num(a[1])
+    df, ddf = g.branch_derv(ops[:0], a, b, L)
+    h = 1e-4 * max(L, 1e-2)
+    lp, lm = g.branch_logl(ops[:0], a, b, L + h), g.branch_logl(ops[:0], a, b, L - h)
+    assert abs((lp - lm) / (2 * h) - df) < 1e-5 * max(1.0, abs(df)) + 1e-6 * abs(ll) * h
+    # pulley principle under slot recycling: the planner keeps track of which CLVs survived the first traversal
+    other = [k for k in range(len(pa)) if min(pa[k], pb[k]) >= ntaxa][len(pa) // 4]
+    ops2, a2, b2, L2 = pt.plan_branch(other)
+    ll2 = g.branch_logl(ops2, a2, b2, L2)
+    assert abs(ll2 - ll) < 1e-9 * abs(ll), (ll, ll2)
+    g.close()
+    pt.close()
+    # the same patterns with one slot per internal node (LM_PER_NODE) on a shard that fits: identical per-pattern results
+    SH = 4096
+    ops1, a1, b1, L1 = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+    g1 = LikelihoodEngine(model, ntaxa, SH)
+    g1.set_tip_states(np.ascontiguousarray(tips[:, :SH])); g1.set_pattern_freq(freq[:SH]); g1.set_pattern_invar(np.zeros(SH))
+    g1.branch_logl(ops1, a1, b1, L1)
+    np.testing.assert_allclose(plh[:SH], g1.get_pattern_lh(), rtol=1e-12, atol=0)
+    g1.close()
+    # the CPU oracle on a slice (240 categories x 400 flops per node: keep it small)
+    SL = 128
+    o = OracleEngine(model, ntaxa, SL)
+    o.set_tip_states(np.ascontiguousarray(tips[:, :SL])); o.set_pattern_freq(freq[:SL]); o.set_pattern_invar(np.zeros(SL))
+    o.branch_logl(ops1, a1, b1, L1)
+    np.testing.assert_allclose(plh[:SL], o.get_pattern_lh(), rtol=1e-11, atol=0)
+    assert np.array_equal(sc_full[:SL], o.get_scale_num(a1[1]))
+
+
+def test_config5_500_partitions_against_the_reference_per_partition():
+    """BASELINE config 5 as bench.py builds it (500 partitions x 100 taxa, 80 % GTR+G4 / 20 % LG+G4, 10 % of the taxa absent per
+    partition): super-tree logL, partition scores and the linked (df, ddf) against the compiled reference kernel run per partition
+    tree and combined as PhyloSuperTreePlen::computeFuncDerv does (tree/phylosupertreeplen.cpp:362-412: lengths x part_rate,
+    df += rate*df_p, ddf += rate^2*ddf_p)."""
+    from iqtree2_b200 import treesim
+    from iqtree2_b200.supertree import PhyloSuperTree
+    from oracle import ref_engine
+    if not ref_engine.available():
+        pytest.skip("oracle/_ref/libiqref.so not built")
+    ntaxa, nparts = 100, 500
+    tree, parts = bench.make_super_inputs(ntaxa, nparts)
+    st = PhyloSuperTree(tree.names)
+    for p in parts:
+        st.add_partition(p["pat"], p["freq"], p["model"], part_rate=p["rate"])
+    st.read_tree(tree.to_newick(fmt="%.17g"))
+    sa, sb, ln = st.branches()
+    br = [k for k in range(len(sa)) if min(sa[k], sb[k]) == 0][0]   # the pendant branch of taxon 0
+    ll = st.compute_likelihood_branch(br)
+    scores = st.part_scores().copy()
+    df, ddf = st.compute_likelihood_derv(br, float(ln[br]))
+    st.close()
+    ll_ref = df_ref = ddf_ref = 0.0
+    mag = 0.0
+    for k, p in enumerate(parts):
+        scaled = treesim.Tree(tree.ntaxa, tree.edges, tree.lengths * p["rate"], tree.names)
+        r = ref_engine.RefTree(scaled, p["model"], p["pat"], p["freq"], nthreads=4)
+        t = r.time_eval(0, 1)
+        r.close()
+        assert abs(scores[k] - t["logl"]) < 1e-6 + 1e-12 * abs(t["logl"]), (k, scores[k], t["logl"])
+        ll_ref += t["logl"]; df_ref += p["rate"] * t["df"]; ddf_ref += p["rate"] ** 2 * t["ddf"]
+        mag += abs(p["rate"] * t["df"])
+    assert abs(ll - ll_ref) < 1e-10 * abs(ll_ref), (ll, ll_ref)
+    assert abs(df - df_ref) < 1e-9 * max(mag, 1.0), (df, df_ref)
+    assert abs(ddf - ddf_ref) < 1e-8 * abs(ddf_ref), (ddf, ddf_ref)

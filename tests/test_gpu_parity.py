@@ -67,13 +67,15 @@ def test_parity_small(kind, safe):
     compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_WALKER, br)
 
 
-@pytest.mark.parametrize("kind,variant", [("dna", 1), ("dna", 2), ("aa", 1), ("aa", 2), ("aa", 3), ("aa", 4), ("aa", 5), ("aa", 6),
-                                          ("aa_c4", 0), ("aa_c4", 2), ("aa_c4", 3), ("aa_c4", 6), ("aa_fused", 1), ("aa_fused", 6)])
+@pytest.mark.parametrize("kind,variant", [("dna", 1), ("dna", 2), ("dna", 5), ("aa", 1), ("aa", 2), ("aa", 3), ("aa", 4), ("aa", 5), ("aa", 6),
+                                          ("aa", 7), ("aa", 8), ("aa", 9), ("aa_c4", 0), ("aa_c4", 1), ("aa_c4", 2), ("aa_c4", 5), ("aa_c4", 7),
+                                          ("aa_fused", 1), ("aa_fused", 5)])
 @pytest.mark.parametrize("safe", [False, True])
 def test_parity_kernel_variants(kind, variant, safe):
-    """Every selectable walker configuration (4-state: direct / TMA bulk / burst stores; 20-state: CTA shapes, B fragments in
-    registers or shared memory, fixed tiles) passes the same parity bars as the default, on a pattern count that is not a
-    multiple of any tile size and with a deep tree so that scaling happens."""
+    """Every selectable walker configuration (4-state: direct / TMA bulk / burst stores, the any-category template; 20-state:
+    the TMA-ring walker with 12 / 8 / 4 warps per CTA and with the categories of a block split over 2 or 4 warps (variants 0-4),
+    the first-generation state-space walker's CTA shapes (5-9)) passes the same parity bars as the default, on a pattern count
+    that is not a multiple of any tile size and with a deep tree so that scaling happens."""
     tree, model, pat, freq, inv = make_case(kind, ntaxa=40, nsites=1500 if kind == "dna" else 700, seed=11, mean_len=0.15)
     # CLV entries at 1e-10 here: on this 40-taxon case a SAFE_LH mixture category that has just been rescaled by 2^256 (all other
     # categories of the pattern 20-70 orders of magnitude below it) differs from the scalar oracle by 3e-11 of the pattern's
@@ -81,6 +83,18 @@ def test_parity_kernel_variants(kind, variant, safe):
     # ill-conditioned eigenvectors of the low-frequency classes, not a kernel difference (the default configuration shows the
     # same figure).  scale_num stays bit-exact and per-pattern logL within 1e-11.
     compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_WALKER, [3, plan.pendant_branch_of(tree, 0)], variant=variant,
+                       clv_tol=1e-10)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
+@pytest.mark.parametrize("safe", [False, True])
+def test_parity_20_state_walker_with_multi_block_tiles(variant, safe):
+    """More 32-pattern blocks than CTAs: the tiles of the TMA-ring walker hold several blocks, with and without the categories of a
+    block split over 2 / 4 warps (named barriers per block), and CTAs take more than one tile (ring and mbarrier state carried
+    over); deep tree so that patterns rescale (the ring is drained and refilled when they do)."""
+    tree, model, pat, freq, inv = make_case("aa", ntaxa=30, nsites=9000, seed=23, mean_len=0.25, gaps=0.02, ambig=0.01)
+    assert pat.shape[1] > 32 * 148
+    compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_WALKER, [plan.pendant_branch_of(tree, 0), 7], variant=variant,
                        clv_tol=1e-10)
 
 
