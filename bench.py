@@ -517,17 +517,22 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
         if upload_model:
             eng.set_model(model)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
+        # both calls are queued on the stream and waited for ONCE (the asynchronous forms of the C ABI); with several ranks the
+        # scalars go from the engine's result slot to a device buffer, through ncclAllReduce and back in the same stream order:
+        # no host round trip between the kernels and the collective
         eng.theta_reset()
-        ll = eng.branch_logl(ops, a, b, L)
-        t1 = eng.last_timing()
-        df, ddf = eng.branch_derv(ops[:0], a, b, L)
-        t2 = eng.last_timing()
-        local = (ll, df, ddf)
+        eng.enqueue_branch_logl(ops, a, b, L)
+        eng.enqueue_branch_derv(ops[:0], a, b, L)
         if world > 1:
-            scal.copy_(torch.tensor([ll, df, ddf], dtype=torch.float64))
+            eng.enqueue_results_dev(scal.data_ptr())
             dist.all_reduce(scal)
-            ll, df, ddf = scal.tolist()
-        return (ll, df, ddf), t1, t2, local
+            ll, df, ddf = scal.tolist()          # the one synchronisation of the evaluation
+            local = eng.finish()
+        else:
+            local = eng.finish()
+            ll, df, ddf = local
+        t1 = eng.last_timing()
+        return (ll, df, ddf), t1, None, local
 
     for _ in range(warmup):
         res, _, _, _ = one_eval(True)
@@ -545,7 +550,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         launches0 = eng.launch_count
         for _ in range(steps):
             r, t1, t2, local = one_eval(upload_model)
-            dev_ms += t1["total_ms"] + t2["total_ms"]
+            dev_ms += t1["total_ms"]
             partial_ms += t1["partials_kernel_ms"]
         ev1.record(stream)
         if world > 1:
@@ -577,9 +582,10 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     walk4 = args.schedule != 1 and model.nstates == 4 and model.nmix == 1
     walk20 = args.schedule != 1 and model.nstates == 20
     if walk20:
-        kernel_name = "k_walk_n20ss (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs)"
+        kernel_name = "k_walk_n20v2 (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs, cp.async rings)"
     elif walk4:
-        kernel_name = f"k_walk_n4 (pattern-tile walker, 4 states x {model.ncat_mix} categories)"
+        kernel_name = ("k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)" if model.ncat_mix == 4 else
+                       f"k_walk_n4<{model.ncat_mix}> (pattern-tile walker, 4 states x {model.ncat_mix} categories)")
     else:
         kernel_name = "k_partials_generic"
     model_bytes = dram_model_bytes(ops, my_nptn, B, S, chained=walk4)

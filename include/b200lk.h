@@ -194,6 +194,11 @@ int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_t n
                                int32_t dad_id, double length);
 int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length);
 int b200lk_finish(b200lk_engine *e, double *logl, double *df, double *ddf);
+/* Multi-process hosts (one process per GPU, each engine a pattern slice): queue, behind the calls queued so far, a copy of
+ * this engine's (logL, df, ddf) into three doubles of caller-owned DEVICE memory on the engine's stream — the input of a
+ * device-side collective (ncclAllReduce on that buffer sums the ranks' scalars: the reduction sites of
+ * tree/phylokernelnew.h:2375-2379, 2747-2748) without a host round trip per evaluation.  b200lk_finish still has to be called. */
+int b200lk_enqueue_results_dev(b200lk_engine *e, double *dev_out);
 
 /* A whole optimizeAllBranches sweep without a host round trip per branch (tree/phylotree.cpp:2698-2774).  Per branch the
  * caller queues b200lk_enqueue_newton_branch — partial updates, theta buffer, the complete minimizeNewton iteration and the
@@ -252,6 +257,19 @@ void *b200lk_pattern_lh_dev(b200lk_engine *e);
  * random tie-break) stays with the caller. */
 int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_samples, int32_t nboot);
 int b200lk_rell(b200lk_engine *e, float *rell /* [nboot] */);
+/* The accept / replace bookkeeping of the same loop on the device (tree/iqtree.cpp:3593-3632), for all replicates in one launch:
+ *     better = rell > boot_logl[b] + epsilon;   a tie (|rell - boot_logl[b]| < epsilon) wins when uniform[b] <= 1/(boot_counts[b]+1)
+ *     winner: boot_counts[b] = tie ? boot_counts[b] + 1 : 1;  boot_logl[b] = max(boot_logl[b], rell);  boot_orig_logl[b] = cur_logl
+ * on the _pattern_lh of the last evaluation (the RELL scores are recomputed; they never leave the device).  boot_logl, boot_counts
+ * and boot_orig_logl live on the device from b200lk_set_boot_samples on (-DBL_MAX, 0, -DBL_MAX: tree/iqtree.cpp:375-378;
+ * b200lk_boot_reset restores that).  uniform: the caller's random numbers in [0,1), one per replicate (the reference draws
+ * random_double(rstream) from per-thread streams, so its tie-breaks depend on the thread count; NULL: ties never win).
+ * updated[b] = 1: the caller stores the current tree for replicate b (boot_trees[b] = tree_str); nboot BYTES come back per
+ * candidate tree instead of 8*nptn going out.  epsilon = Params::ufboot_epsilon (0.5). */
+int b200lk_boot_reset(b200lk_engine *e);
+int b200lk_rell_update(b200lk_engine *e, double cur_logl, double epsilon, const double *uniform /* [nboot] or NULL */,
+                       uint8_t *updated /* [nboot] or NULL */, int32_t *nupdated);
+int b200lk_get_boot_state(b200lk_engine *e, double *boot_logl, int32_t *boot_counts, double *boot_orig_logl);
 
 /* ---- alignment -> site patterns (Alignment::addPattern, alignment/alignment.cpp:1092-1133; buildPattern :1725) ------
  * states: [ntaxa][nsite] state codes, sequence-major.  Returns the distinct columns in FIRST-OCCURRENCE order as

@@ -9,6 +9,7 @@
 #include "b200lk_walk20ss.cuh"
 #include "b200lk_walk20v2.cuh"
 #include "b200lk_walk4.cuh"
+#include "b200lk_walkgen.cuh"
 #include "b200lk_group.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -29,6 +30,7 @@ struct b200lk_engine {
     b200lk_config cfg{};
     int C = 0, B = 0, denom = 1, S = 1;
     long long P = 0, Ppad = 0;
+    long long clv_width = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     Dev d{};
     // owned device buffers
@@ -62,7 +64,9 @@ struct b200lk_engine {
     int num_sms = 148;
     int info_smem_optin = 0;
     bool walk20_attr_set = false;
-    unsigned walk20v2_attr = 0;   // bit per (NW, CS) configuration of k_walk_n20v2 whose attributes are set
+    unsigned walk20v2_attr = 0;
+    bool walkgen_attr_set = false;
+    int walkgen_ctas_per_sm = 1;   // bit per (NW, CS) configuration of k_walk_n20v2 whose attributes are set
     // EM E-step (b200lk_em_posterior): posteriors [K][Ppad], per-block partial sums, the K sums
     double *d_post = nullptr, *d_em_red = nullptr, *d_em_out = nullptr;
     int post_K = 0;
@@ -91,6 +95,7 @@ struct b200lk_engine {
     int last_launch[3] = {0, 0, 0};
     int64_t launches = 0;
     float *d_boot = nullptr, *d_rell = nullptr;   // UFBoot: resampled pattern frequencies [nboot][boot_stride], RELL scores
+    double *d_boot_state = nullptr;               // boot_logl | boot_orig_logl | uniform (3 x nboot doubles), then boot_counts, nupdated, updated
     int nboot = 0;
     long long boot_stride = 0;
     size_t boot_bytes = 0;
@@ -182,7 +187,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
+    cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_boot_state); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
     if (e->h_result) cudaFreeHost(e->h_result);
@@ -232,7 +237,11 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     const long long Ppad = e->Ppad;
     // 20-state engines keep state-space CLVs in the fragment-major layout (b200lk_walk20ss.cuh)
     const bool f20 = n == 20 && e->C % cfg->nmix == 0;
-    const bool state_space = f20;
+    // general state counts above 8 (codon models ...): the same with n padded to a multiple of 8 (b200lk_walkgen.cuh)
+    const int n8 = (n + 7) / 8 * 8;
+    const bool f8 = n > 8 && n <= 64 && n != 20 && gen_smem_doubles(n8, cfg->state_unknown) * sizeof(double) + 4096 <= 227 * 1024;
+    const bool state_space = f20 || f8;
+    e->clv_width = f8 ? (long long)e->C * n8 : (long long)e->B;   // doubles per pattern in a CLV slot
     e->nslots_total = cfg->nslots + (state_space ? 2 : 0);
     e->slot_ver.assign(e->nslots_total, 0);
     TRY(dev_alloc(e, &e->d_tips, (size_t)cfg->ntaxa * Ppad));
@@ -242,9 +251,10 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     const size_t n_tip = (size_t)(cfg->state_unknown + 1) * cfg->nmix * n;
     const size_t model_doubles = n_eval + 2 * n_mat + cfg->nmix + 2 * cfg->ncat + n_tip + 3 * (size_t)e->B;
     TRY(dev_alloc(e, &e->d_model, model_doubles));
-    TRY(dev_alloc(e, &e->d_partial, (size_t)e->nslots_total * Ppad * e->B));
+    TRY(dev_alloc(e, &e->d_partial, (size_t)e->nslots_total * Ppad * e->clv_width));
+    if (f8) cudaMemsetAsync(e->d_partial, 0, sizeof(double) * (size_t)e->nslots_total * Ppad * e->clv_width, e->stream);   // padded values stay exact zeros
     TRY(dev_alloc(e, &e->d_scale, (size_t)e->nslots_total * Ppad * e->S));
-    if (state_space) TRY(dev_alloc(e, &e->d_inv_frag20, (size_t)cfg->nmix * 480));
+    if (f20) TRY(dev_alloc(e, &e->d_inv_frag20, (size_t)cfg->nmix * 480));
     TRY(dev_alloc(e, &e->d_theta, (size_t)Ppad * e->B));
     TRY(dev_alloc(e, &e->d_buffer_scale, Ppad));
     TRY(dev_alloc(e, &e->d_pattern_lh, Ppad));
@@ -274,9 +284,10 @@ extern "C" int b200lk_create(const b200lk_config *cfg, b200lk_engine **out) {
     d.asc = 0; d.Pobs = e->P; d.asc_nsite = 0; d.asc_step = 0; d.asc_tmp = nullptr;
     d.clv_f20 = f20 ? 1 : 0;   // 20-state CLVs are fragment-major (b200lk_kernels.cuh: clv20_off)
     d.clv_state = state_space ? 1 : 0;
+    d.clv_f8 = f8 ? 1 : 0; d.n8 = n8;
     d.inv_frag20 = e->d_inv_frag20;
     d.ss_lo = 0u; d.ss_hi = 0xffffffffu;   // set_model narrows the band from the eigenvector norms
-    d.slot_stride = Ppad * e->B; d.scale_stride = Ppad * e->S;
+    d.slot_stride = Ppad * e->clv_width; d.scale_stride = Ppad * e->S;
     d.partial = e->d_partial; d.scale = e->d_scale; d.tips = e->d_tips; d.freq = e->d_freq; d.invar = e->d_invar;
     double *m = e->d_model;
     d.eval = m; m += n_eval;
@@ -456,8 +467,7 @@ extern "C" int b200lk_set_model(b200lk_engine *e, const double *eval, const doub
         const int e_hi = (int)std::ceil(std::log2(r_evec)) + 1, e_lo = (int)std::ceil(std::log2(r_inv)) + 1;
         e->d.ss_hi = (unsigned)std::min(2046, std::max(1, 1023 - 256 + e_hi)) << 20;
         e->d.ss_lo = (unsigned)std::min(2046, std::max(0, 1023 - 256 - e_lo)) << 20;
-        k_inv_frag20<<<nmix, 128, 0, e->stream>>>(e->d, e->d_inv_frag20);
-        e->launches++;
+        if (e->d.clv_f20) { k_inv_frag20<<<nmix, 128, 0, e->stream>>>(e->d, e->d_inv_frag20); e->launches++; }
         e->eig_src[0] = e->eig_src[1] = -1;
     }
     CK(cudaGetLastError());
@@ -692,9 +702,14 @@ static int eigen_slot(b200lk_engine *e, int slot, int keep = -1) {
     bool convert;
     const int dst = eigen_slot_plan(e, slot, keep, &convert);
     if (convert) {
-        const long long nblocks = e->Ppad / 32;
-        const int grid = (int)std::min<long long>((nblocks + 3) / 4, (long long)e->num_sms * 8);
-        k_clv20_to_eigen<<<grid, 128, 0, e->stream>>>(e->d, slot, dst);
+        if (e->d.clv_f8) {
+            const long long total = e->Ppad * e->C;
+            k_clv_gen_to_eigen<<<(unsigned)((total + 127) / 128), 128, 0, e->stream>>>(e->d, slot, dst);
+        } else {
+            const long long nblocks = e->Ppad / 32;
+            const int grid = (int)std::min<long long>((nblocks + 3) / 4, (long long)e->num_sms * 8);
+            k_clv20_to_eigen<<<grid, 128, 0, e->stream>>>(e->d, slot, dst);
+        }
         e->launches++;
     }
     return dst;
@@ -802,6 +817,58 @@ static int fill_jobs20(b200lk_engine *e, const b200lk_op *ops, int32_t nops, Wal
     return 0;
 }
 
+// k_walk_gen [NT8 - 2][SAFE]: 9..16, 17..24 (not 20), ... 57..64 states
+#define WGEN(NT8) { (const void *)k_walk_gen<false, NT8>, (const void *)k_walk_gen<true, NT8> }
+static const void *const walkgen_f[7][2] = { WGEN(2), WGEN(3), WGEN(4), WGEN(5), WGEN(6), WGEN(7), WGEN(8) };
+static bool use_walkgen(const b200lk_engine *e) { return e->schedule != 1 && e->d.clv_f8 && e->h_evec.size() == (size_t)e->cfg.nmix * e->cfg.nstates * e->cfg.nstates; }
+
+static int enqueue_walkgen(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
+    const int n8 = e->d.n8, C = e->C;
+    const size_t stage_sz = gen_stage_doubles(n8, e->cfg.state_unknown);   // one staging block per (op, category)
+    if (stage_sz * nops * C > e->opinfo_cap) {
+        CK(sync_stream(e));
+        if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
+        e->d_opinfo = nullptr; e->opinfo_cap = 0;
+        int rc = dev_alloc(e, &e->d_opinfo, stage_sz * nops * C);
+        if (rc) return rc;
+        e->opinfo_cap = stage_sz * nops * C;
+        e->d.opinfo = e->d_opinfo;
+    }
+    WalkJob20 *hj = (WalkJob20 *)stage_acquire(e);
+    int rcj = fill_jobs20(e, ops, nops, hj);
+    if (rcj) return rcj;
+    WalkJob20 *dj = (WalkJob20 *)e->d_jobs;
+    CK(cudaMemcpyAsync(dj, hj, sizeof(WalkJob20) * nops, cudaMemcpyHostToDevice, e->stream));
+    note_writes(e, ops, nops);
+    const void *f = walkgen_f[n8 / 8 - 2][e->cfg.safe_numeric ? 1 : 0];
+    const size_t smem = gen_smem_doubles(n8, e->cfg.state_unknown) * sizeof(double);
+    if (!e->walkgen_attr_set) {
+        for (int k = 0; k < 2; k++) {
+            CK(cudaFuncSetAttribute(walkgen_f[n8 / 8 - 2][k], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaFuncSetAttribute(walkgen_f[n8 / 8 - 2][k], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, f, kGenNW * 32, smem));
+        e->walkgen_ctas_per_sm = std::max(per_sm, 1);
+        e->walkgen_attr_set = true;
+    }
+    k_walk_info_gen<<<nops * C, 256, sizeof(double) * 2 * e->cfg.nstates, e->stream>>>(e->d, dj, e->d_opinfo, e->d_counter);
+    const long long nblocks = e->Ppad / 32, slots = (long long)e->num_sms * e->walkgen_ctas_per_sm;
+    const long long waves = (nblocks + kGenNW * slots - 1) / (kGenNW * slots);
+    int ntiles = (int)std::min<long long>(waves * slots, nblocks);
+    const int grid = (int)std::min<long long>(ntiles, slots);
+    if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
+    void *args[] = {(void *)&e->d, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter, (void *)&ntiles};
+    CK(cudaLaunchKernel(f, dim3(grid), dim3(kGenNW * 32), args, smem, e->stream));
+    if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
+    e->partials_timed = e->profiling;
+    e->launches += 2;
+    e->last_launch[0] += 2;
+    CK(cudaGetLastError());
+    e->theta_computed = false;
+    return 0;
+}
+
 static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     const int nblk = e->cfg.nmix, cpb = walk20_cpb(e);
     const bool mix = nblk > 1;
@@ -890,6 +957,7 @@ static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops
     if (nextra == 0 && use_walk4(e) && e->kernel_variant != 5) return enqueue_walk4(e, ops, nops, nullptr);
     if (nextra == 0 && walk4n_cfg(e)) return enqueue_walk4(e, ops, nops, walk4n_cfg(e));
     if (nextra == 0 && use_walk20(e)) return enqueue_walk20(e, ops, nops);
+    if (nextra == 0 && use_walkgen(e)) return enqueue_walkgen(e, ops, nops);
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
     char *seg = (char *)stage_acquire(e);
@@ -1130,6 +1198,15 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     e->have_lh_cat = true;
     e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);
     e->pending_marks = 2;
+    return 0;
+}
+
+extern "C" int b200lk_enqueue_results_dev(b200lk_engine *e, double *dev_out) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "enqueue_results_dev");
+    if (!dev_out) return fail(e, B200LK_ERR_INVALID, "enqueue_results_dev: null pointer");
+    cudaSetDevice(e->cfg.device);
+    // the final reductions write the scalars through the mapped alias of h_result; stream order makes them visible to this copy
+    CK(cudaMemcpyAsync(dev_out, e->h_result, 3 * sizeof(double), cudaMemcpyHostToDevice, e->stream));
     return 0;
 }
 
@@ -1533,7 +1610,7 @@ extern "C" int b200lk_get_partial(b200lk_engine *e, int32_t slot, double *out) {
     if (slot < 0 || slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "slot out of range");
     cudaSetDevice(e->cfg.device);
     const double *src = e->d_partial + (size_t)eigen_slot(e, slot) * e->d.slot_stride;
-    if (!e->d.clv_f20) return read_interleaved_f64(e, src, e->B, out);
+    if (!e->d.clv_f20 && !e->d.clv_f8) return read_interleaved_f64(e, src, e->B, out);
     const size_t total = (size_t)e->P * e->B;
     int rc = ensure_scratch(e, total * sizeof(double));
     if (rc) return rc;
@@ -1577,6 +1654,7 @@ extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_sampl
     CK(sync_stream(e));
     if (e->d_boot) { cudaFree(e->d_boot); e->device_bytes -= (int64_t)e->boot_bytes; e->d_boot = nullptr; }
     if (e->d_rell) { cudaFree(e->d_rell); e->d_rell = nullptr; }
+    if (e->d_boot_state) { cudaFree(e->d_boot_state); e->d_boot_state = nullptr; }
     e->nboot = 0; e->boot_bytes = 0;
     if (nboot == 0) return 0;
     e->boot_stride = (e->P + 3) / 4 * 4;   // rows 16-byte aligned
@@ -1589,8 +1667,70 @@ extern "C" int b200lk_set_boot_samples(b200lk_engine *e, const float *boot_sampl
     CK(cudaMemsetAsync(e->d_boot, 0, n * sizeof(float), e->stream));
     CK(cudaMemcpy2DAsync(e->d_boot, e->boot_stride * sizeof(float), boot_samples, e->P * sizeof(float), e->P * sizeof(float), nboot,
                          cudaMemcpyHostToDevice, e->stream));
-    CK(sync_stream(e));
+    // bookkeeping state of b200lk_rell_update: boot_logl, boot_orig_logl = -DBL_MAX, boot_counts = 0 (tree/iqtree.cpp:375-378)
+    rc = dev_alloc(e, &e->d_boot_state, (size_t)3 * nboot + (size_t)(nboot + 1) / 2 + 1 + (size_t)(nboot + 7) / 8 + 1);   // 3 double arrays | counts | nupdated | updated
+    if (rc) return rc;
     e->nboot = nboot;
+    {
+        double *bl = e->d_boot_state, *bo = bl + nboot;
+        int *bc = (int *)(bl + 3 * (size_t)nboot);
+        k_boot_reset<<<(nboot + 127) / 128, 128, 0, e->stream>>>(nboot, bl, bc, bo);
+        e->launches++;
+    }
+    CK(sync_stream(e));
+    return 0;
+}
+
+// device pointers of the bookkeeping arrays inside d_boot_state
+struct BootState { double *logl, *orig, *uniform; int *counts, *nupdated; unsigned char *updated; };
+static BootState boot_state(b200lk_engine *e) {
+    BootState b;
+    b.logl = e->d_boot_state; b.orig = b.logl + e->nboot; b.uniform = b.orig + e->nboot;
+    b.counts = (int *)(b.uniform + e->nboot); b.nupdated = b.counts + e->nboot;
+    b.updated = (unsigned char *)(b.nupdated + 2);
+    return b;
+}
+
+extern "C" int b200lk_boot_reset(b200lk_engine *e) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "boot_reset");
+    cudaSetDevice(e->cfg.device);
+    if (e->nboot <= 0) return fail(e, B200LK_ERR_STATE, "boot_reset: no bootstrap samples set");
+    BootState b = boot_state(e);
+    k_boot_reset<<<(e->nboot + 127) / 128, 128, 0, e->stream>>>(e->nboot, b.logl, b.counts, b.orig);
+    e->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200lk_rell_update(b200lk_engine *e, double cur_logl, double epsilon, const double *uniform, uint8_t *updated, int32_t *nupdated) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "rell_update");
+    cudaSetDevice(e->cfg.device);
+    if (e->nboot <= 0) return fail(e, B200LK_ERR_STATE, "rell_update: no bootstrap samples set");
+    BootState b = boot_state(e);
+    if (uniform) CK(cudaMemcpyAsync(b.uniform, uniform, sizeof(double) * e->nboot, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemsetAsync(b.nupdated, 0, sizeof(int), e->stream));
+    k_rell<<<e->nboot, 256, 0, e->stream>>>(e->d_pattern_lh, e->d_boot, e->P, e->boot_stride, e->d_rell);
+    k_rell_update<<<(e->nboot + 127) / 128, 128, 0, e->stream>>>(e->nboot, e->d_rell, cur_logl, epsilon, uniform ? b.uniform : nullptr, b.logl, b.counts, b.orig,
+                                                                 b.updated, b.nupdated);
+    e->launches += 2;
+    CK(cudaGetLastError());
+    int n = 0;
+    CK(cudaMemcpyAsync(&n, b.nupdated, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+    if (updated) CK(cudaMemcpyAsync(updated, b.updated, (size_t)e->nboot, cudaMemcpyDeviceToHost, e->stream));
+    CK(sync_stream(e));
+    if (nupdated) *nupdated = n;
+    return 0;
+}
+
+extern "C" int b200lk_get_boot_state(b200lk_engine *e, double *boot_logl, int32_t *boot_counts, double *boot_orig_logl) {
+    if (!e->shards.empty()) MG_UNSUPPORTED(e, "get_boot_state");
+    cudaSetDevice(e->cfg.device);
+    if (e->nboot <= 0) return fail(e, B200LK_ERR_STATE, "get_boot_state: no bootstrap samples set");
+    BootState b = boot_state(e);
+    if (boot_logl) CK(cudaMemcpyAsync(boot_logl, b.logl, sizeof(double) * e->nboot, cudaMemcpyDeviceToHost, e->stream));
+    if (boot_counts) CK(cudaMemcpyAsync(boot_counts, b.counts, sizeof(int) * e->nboot, cudaMemcpyDeviceToHost, e->stream));
+    if (boot_orig_logl) CK(cudaMemcpyAsync(boot_orig_logl, b.orig, sizeof(double) * e->nboot, cudaMemcpyDeviceToHost, e->stream));
+    CK(sync_stream(e));
     return 0;
 }
 

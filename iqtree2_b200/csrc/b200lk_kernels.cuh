@@ -52,6 +52,7 @@ struct Dev {
     long long asc_step;      // Holder: the unobserved block is n groups of asc_step patterns, group s = pattern p with state s
     double *asc_tmp;         // Holder: (lh, df, ddf) of every unobserved pattern, three arrays of P - Pobs doubles
     int clv_f20;             // CLV slots use the 20-state fragment-major layout (clv20_off) instead of the warp-interleaved one
+    int clv_f8, n8;          // general state counts: fragment-major layout with n padded to n8 = 8*ceil(n/8) (b200lk_walkgen.cuh)
     int clv_state;           // CLV slots hold the STATE-SPACE vector t (partial_lh = inv_evec . t), see b200lk_walk20ss.cuh
     unsigned ss_lo, ss_hi;   // exponent words: max|t| < ss_lo => max|partial_lh| < 2^-256 for sure, >= ss_hi => certainly not
     const double *inv_frag20;   // inv_evec as DMMA B fragments, [nmix][15][32] (k_inv_frag20)
@@ -93,13 +94,18 @@ __host__ __device__ __forceinline__ int clv20_off(int i, int g) {
 // element (category c, index i) of pattern p inside a CLV slot, for the thread-per-pattern kernels
 struct ClvIdx {
     long long base;
-    int g, n, f20;
+    int g, n, f20, f8, cstep;
     __device__ __forceinline__ ClvIdx(const Dev &D, long long p) {
-        f20 = D.clv_f20; n = D.n; g = (int)(p & 7);
-        base = f20 ? (p >> 5) * (long long)D.B * kWarp + ((p >> 3) & 3) * (long long)D.C * kClv20Step : pbase(p, D.B);
+        f20 = D.clv_f20; f8 = D.clv_f8; n = D.n; g = (int)(p & 7);
+        cstep = f8 ? D.n8 * 8 : kClv20Step;
+        if (f20) base = (p >> 5) * (long long)D.B * kWarp + ((p >> 3) & 3) * (long long)D.C * kClv20Step;
+        else if (f8) base = (p >> 5) * (long long)D.C * D.n8 * kWarp + ((p >> 3) & 3) * (long long)D.C * cstep;
+        else base = pbase(p, D.B);
     }
     __device__ __forceinline__ long long operator()(int c, int i) const {
-        return base + (f20 ? c * kClv20Step + clv20_off(i, g) : (c * n + i) * kWarp);
+        if (f20) return base + c * kClv20Step + clv20_off(i, g);
+        if (f8) return base + (long long)c * cstep + (i >> 3) * 64 + g * 8 + (i & 7);
+        return base + (c * n + i) * kWarp;
     }
 };
 
@@ -131,14 +137,16 @@ __global__ void __launch_bounds__(256) k_partial_info(Dev D, const ChildJob *job
             for (int row = threadIdx.x; row < C * n; row += blockDim.x) {
                 double *er = E + (long long)row * n;
                 const double *iv = D.inv_evec + (long long)((row / n) / D.denom) * nn;
-                double erow[20], prow[20];
-                for (int i = 0; i < 20; i++) erow[i] = er[i];
-                for (int y = 0; y < 20; y++) {
+                double erow[64], prow[64];
+                for (int i = 0; i < n; i++) erow[i] = er[i];
+                for (int y = 0; y < n; y++) {
                     double a0 = 0.0, a1 = 0.0;
-                    for (int i = 0; i < 20; i += 2) { a0 = fma(erow[i], iv[i * 20 + y], a0); a1 = fma(erow[i + 1], iv[(i + 1) * 20 + y], a1); }
+                    int i = 0;
+                    for (; i + 1 < n; i += 2) { a0 = fma(erow[i], iv[i * n + y], a0); a1 = fma(erow[i + 1], iv[(i + 1) * n + y], a1); }
+                    if (i < n) a0 = fma(erow[i], iv[i * n + y], a0);
                     prow[y] = a0 + a1;
                 }
-                for (int y = 0; y < 20; y++) er[y] = prow[y];
+                for (int y = 0; y < n; y++) er[y] = prow[y];
             }
         }
         return;
@@ -1548,6 +1556,34 @@ __global__ void __launch_bounds__(256) k_rell(const double *pattern_lh, const fl
         __syncthreads();
     }
     if (threadIdx.x == 0) out[blockIdx.x] = (float)s[0];
+}
+
+// UFBoot bookkeeping (IQTree::saveCurrentTree, tree/iqtree.cpp:3593-3632) for all replicates at once: one thread per replicate.
+//   better = rell > boot_logl + eps;  a tie (within eps) wins with probability 1 / (boot_counts + 1) — the caller's uniform number;
+//   a winner resets (clear win) or bumps (tie) boot_counts, boot_logl = max(boot_logl, rell), boot_orig_logl = cur_logl.
+// updated[b] = 1 tells the host to remember the current tree for replicate b (boot_trees[b] = tree_str); *nupdated counts them.
+__global__ void k_rell_update(int nboot, const float *rell, double cur_logl, double eps, const double *uniform, double *boot_logl, int *boot_counts,
+                              double *boot_orig_logl, unsigned char *updated, int *nupdated) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nboot) return;
+    const double r = (double)rell[b], cur = boot_logl[b];
+    bool better = r > cur + eps;
+    if (!better && r > cur - eps) better = (uniform ? uniform[b] : 2.0) <= 1.0 / (double)(boot_counts[b] + 1);
+    if (better) {
+        if (r <= cur + eps) boot_counts[b]++;
+        else boot_counts[b] = 1;
+        boot_logl[b] = fmax(cur, r);
+        boot_orig_logl[b] = cur_logl;
+        atomicAdd(nupdated, 1);
+    }
+    updated[b] = better ? 1 : 0;
+}
+__global__ void k_boot_reset(int nboot, double *boot_logl, int *boot_counts, double *boot_orig_logl) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nboot) return;
+    boot_logl[b] = -1.7976931348623157e308;   // -DBL_MAX (tree/iqtree.cpp:375-378)
+    boot_orig_logl[b] = -1.7976931348623157e308;
+    boot_counts[b] = 0;
 }
 
 __global__ void k_deinterleave_clv(Dev D, const double *src, double *dst) {   // one CLV slot -> [p][c*n + i]

@@ -8,6 +8,8 @@
 #include <stdexcept>
 #include <string>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #ifdef _OPENMP
 #include <cfloat>
@@ -57,6 +59,9 @@ PhyloSuperTreePlen::~PhyloSuperTreePlen() {
 }
 
 void PhyloSuperTreePlen::dropGroup() {
+    if (group_ && getenv("B200ST_TIMING") && timing_[3] > 0)
+        fprintf(stderr, "[b200st] grouped evaluations: %.0f calls; per call: host planning %.3f ms, group enqueue %.3f ms, wait %.3f ms\n", timing_[3],
+                1e3 * timing_[0] / timing_[3], 1e3 * timing_[1] / timing_[3], 1e3 * timing_[2] / timing_[3]);
     if (group_) b200lk_group_destroy(group_);
     group_ = nullptr;
     group_engines_.clear();
@@ -88,6 +93,8 @@ void PhyloSuperTreePlen::groupEvaluate(int what, PlanFn plan, double *logl, doub
     std::vector<const b200lk_op *> ops(np);
     std::vector<int32_t> nops(np), node_slot(np), dad_kind(np), dad_id(np);
     std::vector<double> length(np);
+    auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     if (what != 3) for_each_partition(part_order, num_threads, [&](int p) { plan(p, plans[p]); });
     for (size_t p = 0; p < np; p++) {
         if (what == 3) { length[p] = parts[p]->current_it->length; continue; }
@@ -95,10 +102,13 @@ void PhyloSuperTreePlen::groupEvaluate(int what, PlanFn plan, double *logl, doub
         dad_id[p] = plans[p].dad_id; length[p] = plans[p].length;
     }
     int rc;
+    const double t1 = now();
     if (what == 1) rc = b200lk_group_enqueue_branch_logl(group_, ops.data(), nops.data(), node_slot.data(), dad_kind.data(), dad_id.data(), length.data(), 1);
     else if (what == 2) rc = b200lk_group_enqueue_branch_derv(group_, ops.data(), nops.data(), node_slot.data(), dad_kind.data(), dad_id.data(), length.data());
     else rc = b200lk_group_enqueue_logl_from_buffer(group_, length.data());
+    const double t2 = now();
     if (rc >= 0) rc = b200lk_group_finish(group_, logl, df, ddf, nullptr);
+    if (++timing_calls_ > 4) { timing_[0] += t1 - t0; timing_[1] += t2 - t1; timing_[2] += now() - t2; timing_[3] += 1.0; }   // (skip the calls that allocate)
     if (rc < 0) {
         const std::string msg = std::string("grouped evaluation: ") + b200lk_group_last_error(group_);
         if (what != 3) for (auto *p : parts) p->planFailed();

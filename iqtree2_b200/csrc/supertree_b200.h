@@ -67,6 +67,8 @@ public:
 private:
     b200lk_group *group_ = nullptr;
     std::vector<b200lk_engine *> group_engines_;   // the members the group was built over
+    int timing_calls_ = 0;
+    double timing_[4] = {0, 0, 0, 0};              // B200ST_TIMING=1: seconds in planning / enqueue / wait, calls
     bool ensureGroup();
     void dropGroup();
     template <class PlanFn> void groupEvaluate(int what, PlanFn plan, double *logl, double *df, double *ddf);

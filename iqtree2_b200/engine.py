@@ -30,6 +30,7 @@ ABI_SYMBOLS = [
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
     "b200lk_group_create", "b200lk_group_destroy", "b200lk_group_last_error", "b200lk_group_enqueue_branch_logl",
     "b200lk_group_enqueue_branch_derv", "b200lk_group_enqueue_logl_from_buffer", "b200lk_group_finish", "b200lk_group_launch_count",
+    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -199,6 +200,26 @@ class LikelihoodEngine:
                                                 C.c_int32(int(save_log_value)), C.byref(out)))
         return out.value
 
+    # ---- asynchronous forms: queue several calls, wait once (include/b200lk.h) ------------------------------
+    def enqueue_branch_logl(self, ops, end_a, end_b, length, save_log_value=True):
+        ops = self._ops(ops)
+        self._check(self.lib.b200lk_enqueue_branch_logl(self._h, _dp(ops), C.c_int32(len(ops)), C.c_int32(end_a[1]), C.c_int32(end_b[0]),
+                                                        C.c_int32(end_b[1]), C.c_double(length), C.c_int32(int(save_log_value))))
+
+    def enqueue_branch_derv(self, ops, end_a, end_b, length):
+        ops = self._ops(ops)
+        self._check(self.lib.b200lk_enqueue_branch_derv(self._h, _dp(ops), C.c_int32(len(ops)), C.c_int32(end_a[1]), C.c_int32(end_b[0]),
+                                                        C.c_int32(end_b[1]), C.c_double(length)))
+
+    def enqueue_results_dev(self, dev_ptr):
+        """queue a copy of (logL, df, ddf) into three doubles of device memory (e.g. a torch CUDA tensor's data_ptr())"""
+        self._check(self.lib.b200lk_enqueue_results_dev(self._h, C.c_void_p(int(dev_ptr))))
+
+    def finish(self):
+        ll, df, ddf = C.c_double(), C.c_double(), C.c_double()
+        self._check(self.lib.b200lk_finish(self._h, C.byref(ll), C.byref(df), C.byref(ddf)))
+        return ll.value, df.value, ddf.value
+
     def theta_reset(self):
         self._check(self.lib.b200lk_theta_reset(self._h))
 
@@ -276,6 +297,22 @@ class LikelihoodEngine:
         out = np.zeros(self._nboot, dtype=np.float32)
         self._check(self.lib.b200lk_rell(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
+
+    def boot_reset(self):
+        self._check(self.lib.b200lk_boot_reset(self._h))
+
+    def rell_update(self, cur_logl, epsilon=0.5, uniform=None):
+        """UFBoot bookkeeping for the last evaluation's _pattern_lh: (updated flags [nboot] uint8, number of updated replicates)"""
+        u = None if uniform is None else np.ascontiguousarray(uniform, dtype=np.float64)
+        upd = np.zeros(self._nboot, dtype=np.uint8)
+        n = C.c_int32()
+        self._check(self.lib.b200lk_rell_update(self._h, C.c_double(cur_logl), C.c_double(epsilon), _dp(u) if u is not None else None, _dp(upd), C.byref(n)))
+        return upd, n.value
+
+    def get_boot_state(self):
+        bl, bc, bo = np.zeros(self._nboot), np.zeros(self._nboot, dtype=np.int32), np.zeros(self._nboot)
+        self._check(self.lib.b200lk_get_boot_state(self._h, _dp(bl), _dp(bc), _dp(bo)))
+        return bl, bc, bo
 
     def get_pattern_scaling(self):
         return self._get("b200lk_get_pattern_scaling", self.nptn)

@@ -284,6 +284,16 @@ class RefTree:
         return [dict(score=float(score[m]), new_len=new_len[m].tolist() if nni5 else new_len[m, :1].tolist(),
                      swap=(fs(sw[m, 0]), fs(sw[m, 1])), outer=[fs(outer[m, k]) for k in range(4)]) for m in range(2)]
 
+    def rell(self, pattern_lh, boot):
+        """IQTree::saveCurrentTree's RELL scores through the tree's own dotProduct member (dotProductSIMD<float, Vec8f>)"""
+        plh = np.ascontiguousarray(pattern_lh, dtype=np.float64)
+        bs = np.ascontiguousarray(boot, dtype=np.float32)
+        out = np.zeros(bs.shape[0], dtype=np.float32)
+        rc = self._L().iqref_rell(self._h, _p(plh), _p(bs), C.c_int(plh.size), C.c_int(bs.shape[0]), _p(out))
+        if rc != 0:
+            raise RuntimeError("the reference tree has no dotProduct kernel bound")
+        return out
+
     def time_eval(self, leaf=0, reps=3):
         ll, df, ddf, mean = C.c_double(), C.c_double(), C.c_double(), C.c_double()
         best = self._L().iqref_time_eval(self._h, int(leaf), int(reps), C.byref(ll), C.byref(df), C.byref(ddf), C.byref(mean))

@@ -569,6 +569,25 @@ void iqref_set_mem_save(int on, double max_mem_size) {
 }
 int iqref_max_lh_slots(void *hv) { return (int)((Handle *)hv)->tree->max_lh_slots; }
 
+// UFBoot RELL as IQTree::saveCurrentTree computes it (tree/iqtree.cpp:3564-3611): the tree's own `dotProduct` member
+// (PhyloTree::dotProductSIMD<float, Vec8f>, tree/phylokernel.h:64-70, bound by setDotProductFMA) over aligned float arrays padded
+// with zeros to the SIMD width.  boot: [nboot][nptn] floats.
+int iqref_rell(void *hv, const double *pattern_lh, const float *boot, int nptn, int nboot, float *out) {
+    PhyloTree *t = ((Handle *)hv)->tree;
+    if (!t->dotProduct) return -1;
+    const int maxnptn = (nptn + 15) / 16 * 16;
+    BootValType *lh = aligned_alloc<BootValType>(maxnptn), *bs = aligned_alloc<BootValType>(maxnptn);
+    memset(lh, 0, maxnptn * sizeof(BootValType));
+    for (int i = 0; i < nptn; i++) lh[i] = (float)pattern_lh[i];
+    for (int b = 0; b < nboot; b++) {
+        memset(bs, 0, maxnptn * sizeof(BootValType));
+        memcpy(bs, boot + (size_t)b * nptn, sizeof(float) * nptn);
+        out[b] = (t->*(t->dotProduct))(lh, bs, nptn);
+    }
+    aligned_free(lh); aligned_free(bs);
+    return 0;
+}
+
 int iqref_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -40,6 +40,14 @@ def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, t
         model = models.make_random_reversible(61, ncat=1, seed=seed)
     elif kind == "n7":
         model = models.make_random_reversible(7, ncat=2, seed=seed)
+    elif kind == "codon_g4":   # 61 states x 4 rate categories: the FP64-MMA walker for general state counts, 8 state tiles
+        model = models.make_random_reversible(61, ncat=4, seed=seed)
+    elif kind == "n12mix":     # 12 states, 2 classes x 3 rates: 2 state tiles, mixture
+        model = models.make_random_reversible(12, ncat=3, nmix=2, seed=seed)
+    elif kind == "n23":        # 23 states: 3 state tiles (odd tile count), one category
+        model = models.make_random_reversible(23, ncat=1, seed=seed)
+    elif kind == "n36g2":      # 36 states x 2 categories: 5 state tiles
+        model = models.make_random_reversible(36, ncat=2, seed=seed)
     else:
         raise ValueError(kind)
     if tree_kind == "yule":

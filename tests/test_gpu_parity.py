@@ -58,7 +58,7 @@ def compare_everything(tree, model, pat, freq, inv, safe, schedule, branches, va
     g.close()
 
 
-@pytest.mark.parametrize("kind", ["dna", "dna_inv", "dna_g1", "dna_g8", "aa", "aa_c4", "bin", "n5mix", "n7", "codon"])
+@pytest.mark.parametrize("kind", ["dna", "dna_inv", "dna_g1", "dna_g8", "aa", "aa_c4", "bin", "n5mix", "n7", "codon", "codon_g4", "n12mix", "n23", "n36g2"])
 @pytest.mark.parametrize("safe", [False, True])
 def test_parity_small(kind, safe):
     nsites = 80 if kind == "codon" else 400
@@ -98,15 +98,18 @@ def test_parity_20_state_walker_with_multi_block_tiles(variant, safe):
                        clv_tol=1e-10)
 
 
-@pytest.mark.parametrize("kind", ["dna", "aa"])
+@pytest.mark.parametrize("kind", ["dna", "aa", "n23", "codon_g4"])
 @pytest.mark.parametrize("safe", [False, True])
 def test_parity_levelled_schedule(kind, safe):
     tree, model, pat, freq, inv = make_case(kind, ntaxa=21, nsites=700, seed=5)
-    compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_LEVELLED, [2, plan.pendant_branch_of(tree, 0)])
+    # codon_g4: one pattern in 561 sits at 1.3e-11 of its largest entry (61-term dot products over the eigenvectors of a random
+    # 61-state model in another summation order than the scalar oracle; the others are at 1e-15..1e-13); logL bars unchanged
+    compare_everything(tree, model, pat, freq, inv, safe, SCHEDULE_LEVELLED, [2, plan.pendant_branch_of(tree, 0)],
+                       clv_tol=1e-10 if kind == "codon_g4" else 1e-11)
 
 
 @pytest.mark.parametrize("safe", [False, True])
-@pytest.mark.parametrize("kind", ["dna", "aa"])
+@pytest.mark.parametrize("kind", ["dna", "aa", "n23", "n12mix"])
 def test_parity_scaling_deep_tree(kind, safe):
     """Underflow path: deep caterpillar with long branches makes scale_num climb; counts must be bit-exact."""
     tree, model, pat, freq, inv = make_case(kind, ntaxa=240 if kind == "dna" else 90, nsites=150, tree_kind="caterpillar",

@@ -79,3 +79,40 @@ def test_supertree_incremental_after_one_branch():
     g.clear_all_partial_lh()
     ll_full = g.compute_likelihood_branch(9)
     assert abs(ll_inc - ll_full) < 1e-7
+
+
+def test_grouped_launches_equal_per_partition_streams(monkeypatch):
+    """The grouped launches (b200lk_group_*: one launch per kernel type for all partitions) run the single-engine kernels' own
+    device functions with per-member reduction slots: the partition scores, the linked derivatives and the optimised lengths are
+    those of one engine + stream per partition, bit for bit — in a handful of launches per evaluation instead of ~5 per partition."""
+    tree, parts = make_supercase(ntaxa=16, nparts=13, seed=12, missing=0.1)
+    g = make_gpu_super(tree, parts)
+    monkeypatch.setenv("B200ST_NO_GROUP", "1")
+    s = make_gpu_super(tree, parts)
+    ll_s = s.compute_likelihood_branch(5)
+    monkeypatch.delenv("B200ST_NO_GROUP")
+    ll_g = g.compute_likelihood_branch(5)
+    assert ll_g == ll_s
+    g.clear_all_partial_lh()               # (the first evaluation also created the engines and uploaded the models)
+    l0 = g.launch_count
+    assert g.compute_likelihood_branch(5) == ll_s
+    n_first = g.launch_count - l0
+    np.testing.assert_array_equal(g.part_scores(), s.part_scores())
+    _, _, ln = g.branches()
+    monkeypatch.setenv("B200ST_NO_GROUP", "1")
+    d_s = s.compute_likelihood_derv(5, float(ln[5]) * 0.8)
+    monkeypatch.delenv("B200ST_NO_GROUP")
+    l1 = g.launch_count
+    d_g = g.compute_likelihood_derv(5, float(ln[5]) * 0.8)
+    assert d_g == d_s
+    # two kernel families (4 and 20 states): staging + walker + conversion + root per family at most
+    assert n_first <= 10 and g.launch_count - l1 <= 8, (n_first, g.launch_count - l1)
+    monkeypatch.setenv("B200ST_NO_GROUP", "1")
+    s.set_branch_length(5, ln[5], clear_partials=True)
+    ll_os = s.optimize_all_branches(iterations=3, tolerance=0.001)
+    monkeypatch.delenv("B200ST_NO_GROUP")
+    g.set_branch_length(5, ln[5], clear_partials=True)
+    ll_og = g.optimize_all_branches(iterations=3, tolerance=0.001)
+    assert ll_og == ll_os
+    np.testing.assert_array_equal(g.branches()[2], s.branches()[2])
+    g.close(); s.close()
