@@ -35,7 +35,11 @@ WORKLOADS = {
     "dna_1000x1M_gtr_g4": (1000, 1_000_000, lambda: models.make_gtr_gamma(), "synthetic DNA 1000 taxa x 1M patterns, GTR+G4"),
     "aa_200x100k_lg_g4": (200, 100_000, lambda: models.make_lg_gamma(), "synthetic protein 200 taxa x 100k patterns, LG+G4"),
     "aa_100x50k_lg_c60_g4": (100, 50_000, lambda: models.make_lg_c60_gamma(), "synthetic protein 100 taxa x 50k patterns, LG+C60+G4"),
+    # not a BASELINE config: the general-n FP64-MMA walker.  61 sense codons, random reversible exchangeabilities,
+    # Gamma(4); SAFE_LH as the reference forces for every n outside {4, 20} (tree/phylotreesse.cpp:95-96)
+    "codon_100x20k_rev61_g4": (100, 20_000, lambda: models.make_random_reversible(61, ncat=4, seed=7), "synthetic codon 100 taxa x 20k patterns, 61-state reversible + G4"),
 }
+SAFE_WORKLOADS = {"codon_100x20k_rev61_g4"}
 
 
 SUPER_WORKLOAD = "super_500part_100taxa"   # BASELINE.json configs[4]
@@ -348,7 +352,7 @@ def make_inputs(ntaxa, nptn, model, seed_tree=1, seed_seq=2, block=262_144):
     return tree, tips, freq, data
 
 
-def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, warmup):
+def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, warmup, safe=False):
     """The reference's CPU implementation of one eval on a bounded pattern sample, all host threads.
 
     Preferred: oracle/_ref/libiqref.so = IQ-TREE 2.4.0's own AVX+FMA Vec4d OpenMP kernel (its TUs compiled in place by
@@ -358,7 +362,7 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
     sample_ptn = int(min(sample_ptn, tips.shape[1]))
     if ref_engine.available():
         threads = host_threads()   # set explicitly: the harness calls omp_set_num_threads(), which overrides OMP_NUM_THREADS
-        r = ref_engine.RefTree(tree, model, np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], nthreads=threads)
+        r = ref_engine.RefTree(tree, model, np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], safe_numeric=safe, nthreads=threads)
         if warmup:
             r.time_eval(0, warmup)
         t = r.time_eval(0, steps)
@@ -368,7 +372,7 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
                 "logl": t["logl"], "df": t["df"], "ddf": t["ddf"], "kind": "reference",
                 "what": "IQ-TREE 2.4.0 phylokernelnew.h, Vec4d AVX+FMA, OpenMP (compiled from the reference's own TUs)"}
     from oracle.oracle_engine import OracleEngine
-    o = OracleEngine(model, tree.ntaxa, sample_ptn, safe_numeric=False)
+    o = OracleEngine(model, tree.ntaxa, sample_ptn, safe_numeric=safe)
     o.set_tip_states(np.ascontiguousarray(tips[:, :sample_ptn]))
     o.set_pattern_freq(freq[:sample_ptn])
     o.set_pattern_invar(np.zeros(sample_ptn))
@@ -385,9 +389,9 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
             "what": "scalar C restatement of phylokernelnew.h (oracle/lk_oracle.c), OpenMP"}
 
 
-def shared_config(workload_name, ntaxa, nptn, model, desc, nops):
+def shared_config(workload_name, ntaxa, nptn, model, desc, nops, safe=False):
     """the `config` object: identical for this framework's arm and for the reference arm of the same workload"""
-    return {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "NORM_LH", "nstates": model.nstates,
+    return {"workload": workload_name, "ntaxa": ntaxa, "npatterns": nptn, "model": desc, "kernel": "SAFE_LH" if safe else "NORM_LH", "nstates": model.nstates,
             "ncat_mix": model.ncat_mix, "partial_updates_per_eval": nops,
             "l2": "inputs (CLVs) far larger than L2; no flush needed"}
 
@@ -411,18 +415,18 @@ def run_reference_arm(args, workload, ntaxa, nptn, model, desc, workload_name, s
     ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
     if not args.cpu_sample:
         cal_n = min(sample, 8192)
-        cal = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, cal_n, 1, 1)
+        cal = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, cal_n, 1, 1, safe=workload in SAFE_WORKLOADS)
         per_ptn = cal["best_sec"] / cal_n
         by_time = int(150.0 / ((steps + warmup) * per_ptn))
         sample = min(sample, max(by_time, min(nptn // 4, mem_cap)))
         sample = max(256, sample // 8 * 8)
-    r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, steps, warmup)
+    r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, steps, warmup, safe=workload in SAFE_WORKLOADS)
     frac = sample / nptn
     evals = frac / r["sec_per_sample_eval"]
     return {"impl": "reference", "metric": "full_tree_logl_deriv_evals_per_sec", "value": evals, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["sec_per_sample_eval"] * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": data,
-            "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops)),
+            "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops), safe=workload in SAFE_WORKLOADS),
             "sample_fraction": frac,
             "cpu_baseline": {"value": evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
                              "sample": f"{sample} of {nptn} patterns per step (fraction {frac:.4f}), all {len(ops)} partial updates + root + derivative; "
@@ -472,7 +476,8 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     import torch
     import torch.distributed as dist
     from iqtree2_b200.engine import LikelihoodEngine
-    B, S = model.nstates * model.ncat_mix, 1
+    safe = workload in SAFE_WORKLOADS
+    B, S = model.nstates * model.ncat_mix, (model.ncat_mix if safe else 1)
     overridden = bool(args.taxa or args.patterns or args.ncat)
     # pattern shard of this rank: contiguous, multiple of the 128-pattern tile except for the last rank
     per = (nptn + world - 1) // world
@@ -497,7 +502,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         ops, a, b, L, nslots = plan_mem_save(tree, model, ntaxa, mem_frac)
         mem_mode = f"LM_MEM_SAVE ({nslots - 2} of {ntaxa - 2} CLV slots recycled by the host planner)"
 
-    eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, device=local_rank, schedule=args.schedule)
+    eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, safe_numeric=safe, device=local_rank, schedule=args.schedule)
     stream = torch.cuda.current_stream()
     if args.variant:
         eng.set_schedule(10 + args.variant)
@@ -586,6 +591,8 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     elif walk4:
         kernel_name = ("k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)" if model.ncat_mix == 4 else
                        f"k_walk_n4<{model.ncat_mix}> (pattern-tile walker, 4 states x {model.ncat_mix} categories)")
+    elif args.schedule != 1 and 8 < model.nstates <= 64:
+        kernel_name = f"k_walk_gen<{(model.nstates + 7) // 8}> (pattern-tile walker, FP64 MMA m8n8k4, {model.nstates} states padded to {(model.nstates + 7) // 8 * 8})"
     else:
         kernel_name = "k_partials_generic"
     model_bytes = dram_model_bytes(ops, my_nptn, B, S, chained=walk4)
@@ -607,7 +614,9 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         fpeak, fsrc = load_fp64_peak()
         flops_alg = algorithmic_flops(ops, my_nptn, model.nstates, model.ncat_mix)
         steps8 = (my_nptn + 7) // 8 * model.ncat_mix
-        flops_exec = 512.0 * steps8 * (30 * n_ii + 15 * n_ti)
+        nt8 = (model.nstates + 7) // 8
+        per_child = 15 if model.nstates == 20 else nt8 * 2 * nt8     # general n: NT8 state tiles x n8/4 K-steps per mat-vec
+        flops_exec = 512.0 * steps8 * per_child * (2 * n_ii + n_ti)
         roofline["tensor"] = {"executed_TFLOPs": flops_exec / ker_s / 1e12, "peak": fpeak, "unit": "TFLOP/s", "frac": flops_exec / ker_s / 1e12 / fpeak,
                               "peak_source": fsrc, "executed_flops_per_launch": flops_exec,
                               "algorithmic_flops_per_launch": flops_alg, "algorithmic_equivalent_TFLOPs": flops_alg / ker_s / 1e12,
@@ -654,7 +663,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         "warmup": warmup, "ms_per_step": res_run["event_ms"] / K, "kernel_ms_per_step": res_run["device_ms"] / K,
         "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": data,
-        "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops)),
+        "config": shared_config(workload_name, ntaxa, nptn, model, desc, len(ops), safe=safe),
         "detail": {"patterns_per_gpu": my_nptn, "node_cases": {"inner_inner": n_ii, "tip_inner": n_ti, "tip_tip": n_tt},
                    "schedule": {0: "auto(walker)", 1: "levelled", 2: "walker"}.get(args.schedule, f"variant{args.schedule}"),
                    "clv_bytes_resident": eng.device_bytes, "clv_slots": mem_mode,
@@ -675,7 +684,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and cpu_baseline:
         sample = args.cpu_sample or cpu_sample_size(len(ops), B, model.nstates, ntaxa, 2.0e10, my_nptn)
-        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 5, 1)
+        r = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample, 5, 1, safe=safe)
         cpu_evals = (sample / nptn) / r["sec_per_sample_eval"]
         line["cpu_baseline"] = {"value": cpu_evals, "unit": "evals/s", "cores": r["cores"], "kind": r["kind"], "what": r["what"],
                                 "sample": f"first {sample} of {nptn} patterns, all {len(ops)} partial updates + root + derivative, "

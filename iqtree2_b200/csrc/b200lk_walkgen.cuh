@@ -23,7 +23,9 @@
 namespace b200lk {
 
 constexpr int kGenNW = 4;       // warps per CTA
-constexpr int kGenK = 3;        // ring depth (steps); a virtual op has 4 steps
+// ring depth (steps; a virtual op has 4 steps): 3, except for 8 state tiles (57..64 states: codon models) where two staged 64 x 64
+// matrices per staging block leave room for 2
+__host__ __device__ constexpr int gen_ring_depth(int n8) { return n8 >= 64 ? 2 : 3; }
 
 // element (tile nt, pattern g, value j) inside a step block of NT8*64 doubles
 __host__ __device__ __forceinline__ int f8_off(int i, int g) { return (i >> 3) * 64 + g * 8 + (i & 7); }
@@ -41,7 +43,7 @@ __host__ __device__ inline size_t gen_stage_doubles(int n8, int su) {
 __host__ __device__ inline size_t gen_stage_used(int n8, int su, int ncase) {
     return 4 + gen_part_doubles(n8, su, ncase <= 1) + gen_part_doubles(n8, su, ncase == 0);
 }
-__host__ __device__ inline size_t gen_smem_doubles(int n8, int su) { return 2 * gen_stage_doubles(n8, su) + (size_t)kGenNW * kGenK * 2 * n8 * 8; }
+__host__ __device__ inline size_t gen_smem_doubles(int n8, int su) { return 2 * gen_stage_doubles(n8, su) + (size_t)kGenNW * gen_ring_depth(n8) * 2 * n8 * 8; }
 
 // One CTA per (op, category): exp(eval r_c len), the tip table (partial_lh_leaves, tree/phylokernelnew.h:1036-1056) or P_c(len)
 __device__ __forceinline__ void walk_info_gen_body(const Dev &D, const WalkJob20 &job, double *st, const int c, double *s_exp) {
@@ -153,7 +155,7 @@ struct GenShared {
 template <bool SAFE, int NT8>
 __device__ __forceinline__ void walkgen_tile(const Dev &D, const double *stage, const int nops, const long long b0, const long long b1, double *s_dyn,
                                              GenShared &sh, unsigned &seq) {
-    constexpr int N8 = NT8 * 8, STEP = N8 * 8, KT = NT8 * 2, NTP = (NT8 + 1) / 2;
+    constexpr int N8 = NT8 * 8, STEP = N8 * 8, KT = NT8 * 2, NTP = (NT8 + 1) / 2, kGenK = gen_ring_depth(N8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, q = lane & 3;
     const int C = D.C;
     const size_t stage_sz = gen_stage_doubles(N8, D.su);
