@@ -135,7 +135,10 @@ def run_super(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    st = PhyloSuperTree(tree.names, num_threads=args.host_threads)
+    # host threads that plan the partitions' traversals: set explicitly (torchrun exports OMP_NUM_THREADS=1, which would plan
+    # 250 partitions on one thread per rank and hide the GPUs' scaling behind the host)
+    nthreads = args.host_threads or max(1, min(16, host_threads() // max(world, 1)))
+    st = PhyloSuperTree(tree.names, num_threads=nthreads)
     for i in mine:
         p = parts[i]
         st.add_partition(p["pat"], p["freq"], p["model"], part_rate=p["rate"], device=local_rank)
@@ -188,16 +191,16 @@ def run_super(args, rank, world, local_rank):
         "config": {"workload": SUPER_WORKLOAD, "ntaxa": ntaxa, "npartitions": nparts, "partitions_per_gpu": len(mine),
                    "npatterns_total": int(sum(p["pat"].shape[1] for p in parts)), "protein_partitions": int(sum(p["aa"] for p in parts)),
                    "model": "edge-linked proportional partition model (PhyloSuperTreePlen), GTR+G4 / LG+G4 per partition",
-                   "host_threads": args.host_threads, "clv_bytes_resident": st.device_bytes, "algorithmic_GB_per_eval": by / 1e9,
+                   "host_threads": nthreads, "clv_bytes_resident": st.device_bytes, "algorithmic_GB_per_eval": by / 1e9,
                    "l2": "each evaluation rewrites every CLV of every partition (working set > L2)",
-                   "parallelism": f"partition-sharded x{world}" if world > 1 else "single GPU", "timing": "wall clock around K steps, device idle on both sides (the step is host-driven: one stream per partition)"},
+                   "parallelism": f"partition-sharded x{world}" if world > 1 else "single GPU", "timing": "wall clock around K steps, device idle on both sides (the step is host-driven: traversals planned per partition, two grouped calls, one wait each)"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": int(nbytes_h2d), "d2h_bytes_per_step": 24 * len(mine),
                 "ms_per_step": wall * 1e3 / K, "what": "the b200st_* calls a PhyloSuperTree host makes: per partition the op list with branch lengths goes up and (logL, df, ddf) come back every step; identical to `value` (there is no resident-input variant of a host-driven partition sweep)"},
         "gpu_launches": int(launches), "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_walk_n4c4 / k_walk_n20_mma, one launch per partition on its own stream (concurrent)",
+        "roofline": {"bound": "hbm", "kernel": "k_group_walk_n4<4> + k_group_walk_n20v2 (grouped launches: one walker launch per kernel family for all partitions)",
                      "achieved": by / (wall / K) / 1e9, "peak": peak, "unit": "GB/s", "frac": by / (wall / K) / 1e9 / peak, "traffic": None,
                      "peak_source": peak_src, "algorithmic_bytes_per_step": by,
-                     "note": "launch- and latency-bound regime: the figure is the whole step (all partitions, all kernels), not one launch"},
+                     "note": "the figure is the whole step (host planning + all kernels of all partitions), not one launch"},
         "result": {"logl": res[0], "df": res[1], "ddf": res[2]},
     }
     if rank == 0:
