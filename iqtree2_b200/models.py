@@ -43,6 +43,10 @@ class ModelInputs:
     seq_type: str = "DNA"
     fused_mix_rate: bool = False
     Q: list = field(default_factory=list)  # normalised rate matrices per mixture class (for the brute-force checker)
+    # non-reversible models (tree/phylokernelnonrev.h): None, or a dict with the complex eigensystem the reference's default
+    # technique uses (ModelMarkov::computeTransMatrixNonrev, model/modelmarkov.cpp:477-486) — "ceval" [nmix][n][2] (re, im),
+    # "cevec" / "cinv_evec" [nmix][n][n][2] row-major, "rate_matrix" [nmix][n][n] (for the derivatives Q.P, Q.Q.P) and "rooted"
+    nonrev: dict = None
 
     @property
     def ncat(self) -> int:
@@ -177,6 +181,44 @@ def make_random_reversible(nstates, ncat=4, nmix=1, alpha=0.7, seed=0, pinvar=0.
     su = nstates if state_unknown is None else state_unknown
     seq_type = "DNA" if (nstates == 4 and su == DNA_STATE_UNKNOWN) else ("AA" if (nstates == 20 and su == PROTEIN_STATE_UNKNOWN) else "GENERIC")
     return _pack(nstates, systems, weights, rates, props, pinvar, su, seq_type)
+
+
+def make_nonreversible(nstates=4, ncat=4, nmix=1, alpha=0.7, seed=0, pinvar=0.0, state_unknown=None, rooted=True) -> ModelInputs:
+    """Random NON-reversible model (an UNREST-like general Markov rate matrix per class): Q with arbitrary positive off-diagonals,
+    normalised to one expected substitution per unit time at its stationary distribution; complex eigensystem from numpy.  The
+    reversible-kernel fields (eval / evec / inv_evec) are filled with the real parts and are not used by the non-reversible path."""
+    rng = np.random.default_rng(seed)
+    n = nstates
+    ceval, cevec, cinv, qs, freqs, weights = [], [], [], [], [], []
+    for _ in range(nmix):
+        Q = rng.gamma(1.0, 1.0, size=(n, n)) + 0.05
+        np.fill_diagonal(Q, 0.0)
+        np.fill_diagonal(Q, -Q.sum(axis=1))
+        # stationary distribution: left null vector
+        w, vl = np.linalg.eig(Q.T)
+        pi = np.real(vl[:, np.argmin(np.abs(w))])
+        pi = pi / pi.sum()
+        Q = Q / (-(pi * np.diag(Q)).sum())
+        lam, V = np.linalg.eig(Q)
+        Vi = np.linalg.inv(V)
+        ceval.append(np.stack([lam.real, lam.imag], axis=-1))
+        cevec.append(np.stack([V.real, V.imag], axis=-1))
+        cinv.append(np.stack([Vi.real, Vi.imag], axis=-1))
+        qs.append(Q)
+        freqs.append(pi)
+        weights.append(rng.uniform(0.5, 1.5))
+    weights = np.array(weights) / np.sum(weights)
+    rates = discrete_gamma_rates(alpha, ncat) if ncat > 1 else np.ones(1)
+    props = np.full(ncat, (1.0 - pinvar) / ncat)
+    su = nstates if state_unknown is None else state_unknown
+    seq_type = "DNA" if (nstates == 4 and su == DNA_STATE_UNKNOWN) else ("AA" if (nstates == 20 and su == PROTEIN_STATE_UNKNOWN) else "GENERIC")
+    f64 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    return ModelInputs(
+        nstates=n, nmix=nmix, eval=f64(np.concatenate([c[:, 0] for c in ceval])), evec=f64(np.concatenate([c[..., 0].ravel() for c in cevec])),
+        inv_evec=f64(np.concatenate([c[..., 0].ravel() for c in cinv])), state_freq=f64(np.concatenate(freqs)), mix_weight=f64(weights),
+        cat_rate=f64(rates), cat_prop=f64(props), pinvar=float(pinvar), state_unknown=su, seq_type=seq_type, Q=qs,
+        nonrev=dict(ceval=f64(np.stack(ceval)), cevec=f64(np.stack(cevec)), cinv_evec=f64(np.stack(cinv)), rate_matrix=f64(np.stack(qs)),
+                    rooted=bool(rooted)))
 
 
 def state_indicator(state: int, nstates: int, state_unknown: int, seq_type: str) -> np.ndarray:

@@ -16,6 +16,8 @@ OP_DTYPE = np.dtype([("dst_slot", "<i4"), ("pad", "<i4"), ("left", CHILD_DTYPE),
 assert OP_DTYPE.itemsize == 40
 
 KIND_TIP, KIND_SLOT = 0, 1
+KIND_ROOT = 2          # non-reversible kernel: the virtual root leaf of a rooted tree (MTree::isRootLeaf, tree/mtree.h:135)
+CHILD_TRANSPOSED = 4   # flag or-ed into a child's kind: the child's branch points TOWARD_ROOT (tree/phylokernelnew.h:939-951)
 
 
 def subtree_sizes(tree):
@@ -93,6 +95,50 @@ def plan_branch(tree, branch: int, lengths=None, sort_by_size: bool = True):
         a, b = b, a
     assert a[0] == KIND_SLOT, "a tree with a single branch between two leaves is not supported"
     return ops, a, b, float(lengths[branch])
+
+
+def plan_branch_nonrev(tree, branch: int, lengths=None, rooted: bool = True):
+    """plan_branch for the NON-REVERSIBLE kernel (tree/phylokernelnonrev.h).  `tree` has ntaxa leaves of which the LAST one is the
+    virtual root leaf the reference attaches to the root of a rooted tree (MTree::readTree, tree/mtree.cpp:742-754: id = leafNum-1);
+    the alignment has ntaxa - 1 rows.  Children whose branch points towards the root carry CHILD_TRANSPOSED, the root leaf is
+    KIND_ROOT.  Returns (ops, endA, endB, length) with endA = dad_branch->partial_lh after the reference's swap
+    (phylokernelnonrev.h:1071-1078: the root-ward end, or the inner end of a pendant branch) and endB = the other end (tip, root
+    leaf or slot).  rooted=False: an unrooted tree evaluated with the non-reversible kernel (no root leaf, no direction)."""
+    ops, a, b, L = plan_branch(tree, branch, lengths)
+    if not rooted:
+        return ops, a, b, L
+    nt = tree.ntaxa
+    rootleaf = nt - 1
+    adj = tree.adjacency()
+    # parent of every node in the orientation away from the root leaf
+    parent = {rootleaf: -1}
+    stack = [rootleaf]
+    while stack:
+        u = stack.pop()
+        for v, _ in adj[u]:
+            if v not in parent:
+                parent[v] = u
+                stack.append(v)
+    for op in ops:
+        nd = int(op["dst_slot"]) + nt
+        for name in ("left", "right"):
+            kind, cid = int(op[name]["kind"]), int(op[name]["id"])
+            v = cid if kind == KIND_TIP else cid + nt
+            if kind == KIND_TIP and cid == rootleaf:
+                kind, cid = KIND_ROOT, 0
+            if parent[nd] == v:
+                kind |= CHILD_TRANSPOSED
+            op[name]["kind"], op[name]["id"] = kind, cid
+    u, v = int(tree.edges[branch][0]), int(tree.edges[branch][1])
+    # (node, dad) after the swap: dad is a leaf if there is one, else the leaf-ward end
+    if u == rootleaf or v == rootleaf:
+        inner = v if u == rootleaf else u
+        return ops, (KIND_SLOT, inner - nt), (KIND_ROOT, 0), L
+    if u < nt or v < nt:
+        leaf, inner = (u, v) if u < nt else (v, u)
+        return ops, (KIND_SLOT, inner - nt), (KIND_TIP, leaf), L
+    rootward, leafward = (u, v) if parent[v] == u else (v, u)
+    return ops, (KIND_SLOT, rootward - nt), (KIND_SLOT, leafward - nt), L
 
 
 def op_levels(ops):

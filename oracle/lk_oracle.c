@@ -69,6 +69,9 @@ typedef struct {
     int asc_type; int64_t asc_nunobs, asc_nsite;
     orc_child *extra; /* pending extra children of multifurcating ops (consumed by the next call that takes ops) */
     int nextra;
+    /* non-reversible kernel (lk_oracle_nonrev.h): complex eigensystem [nmix][n](re,im) / [nmix][n][n](re,im), rate matrices, frequencies */
+    int nonrev, rooted;
+    double *ceval, *cevec, *cinv, *qmat, *sfreq;
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
     char err[256];
 } orc_engine;
@@ -319,7 +322,9 @@ void orc_destroy(orc_engine *e) {
     free(e->tips); free(e->ptn_freq); free(e->ptn_invar); free(e->eval); free(e->evec); free(e->inv_evec);
     free(e->mix_weight); free(e->cat_rate); free(e->cat_prop); free(e->tip_partial_lh); free(e->partial);
     free(e->scale); free(e->theta); free(e->buffer_scale_all); free(e->pattern_lh); free(e->pattern_scaling);
-    free(e->pattern_lh_cat); free(e->extra); free(e);
+    free(e->pattern_lh_cat); free(e->extra);
+    free(e->ceval); free(e->cevec); free(e->cinv); free(e->qmat); free(e->sfreq);
+    free(e);
 }
 
 const char *orc_last_error(orc_engine *e) { return e->err; }
@@ -644,7 +649,11 @@ static void compute_partial_range(orc_engine *e, const orc_opinfo *oi, size_t lo
  * 2821-2824): packets are independent pattern ranges, so children written by a packet are still cache-hot
  * when the same packet computes their parent.  Same structure here (packet = ORC_PACKET patterns). */
 #define ORC_PACKET 512
+static int nonrev_update_partials(orc_engine *e, const orc_op *ops, int nops);
+static int nonrev_branch_logl(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, double *logl_out);
+static int nonrev_branch_derv(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, double *df_out, double *ddf_out);
 int orc_update_partials(orc_engine *e, const orc_op *ops, int nops) {
+    if (e->nonrev) return nonrev_update_partials(e, ops, nops);
     if (nops <= 0) return 0;
     if (e->cfg.nstates > ORC_MAX_STATES) { snprintf(e->err, sizeof e->err, "nstates > %d", ORC_MAX_STATES); return -1; }
     orc_opinfo *info = (orc_opinfo *)malloc(sizeof(orc_opinfo) * nops);
@@ -731,6 +740,10 @@ static double holder_logl_correction(orc_engine *e, size_t Pobs) {
  * ------------------------------------------------------------------------------------------- */
 int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
                     double length, int save_log_value, double *logl_out) {
+    if (e->nonrev) {
+        if (orc_update_partials(e, ops, nops) < 0) return -1;
+        return nonrev_branch_logl(e, node_slot, dad_kind, dad_id, length, logl_out);
+    }
     orc_update_partials(e, ops, nops);
     int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric, nmix = e->cfg.nmix;
     size_t P = (size_t)e->cfg.nptn, S = S_of(e);
@@ -960,6 +973,10 @@ int orc_set_extra_children(orc_engine *e, const orc_child *children, int n) {
 /* computeLikelihoodDerv(Generic)SIMD — phylokernelnew.h:2233-2633 (joint branch length, no +ASC) */
 int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, int dad_kind, int dad_id,
                     double length, double *df_out, double *ddf_out) {
+    if (e->nonrev) {
+        if (orc_update_partials(e, ops, nops) < 0) return -1;
+        return nonrev_branch_derv(e, node_slot, dad_kind, dad_id, length, df_out, ddf_out);
+    }
     orc_update_partials(e, ops, nops);
     if (!e->theta_computed) build_theta(e, node_slot, dad_kind, dad_id);
     int B = e->B;
@@ -1133,6 +1150,8 @@ int orc_get_tip_partial_lh(orc_engine *e, double *out) {
     memcpy(out, e->tip_partial_lh, sizeof(double) * (e->cfg.state_unknown + 1) * e->cfg.nmix * e->cfg.nstates);
     return 0;
 }
+#include "lk_oracle_nonrev.h"
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

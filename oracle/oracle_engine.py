@@ -79,6 +79,12 @@ class OracleEngine:
         lib().orc_set_model(self._h, _dp(ev), _dp(U), _dp(Ui), _dp(w))
         r, p = f(model.cat_rate), f(model.cat_prop)
         lib().orc_set_rates(self._h, _dp(r), _dp(p))
+        nr = getattr(model, "nonrev", None)
+        if nr:   # non-reversible kernel (lk_oracle_nonrev.h)
+            a = [f(nr["ceval"]), f(nr["cevec"]), f(nr["cinv_evec"]), f(nr["rate_matrix"]), f(model.state_freq)]
+            rc = lib().orc_set_model_nonrev(self._h, _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(w), C.c_int(int(nr["rooted"])))
+            if rc < 0:
+                raise RuntimeError(lib().orc_last_error(self._h).decode())
 
     def set_tip_states(self, states):
         s = np.ascontiguousarray(states, dtype=np.uint8)

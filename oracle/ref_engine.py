@@ -103,6 +103,23 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def rooted_newick(tree, fmt="%.17g"):
+    """Newick of a treesim.Tree whose LAST leaf is the virtual root leaf: written from the node the root leaf hangs on (two
+    children = a rooted tree for MTree::readTree), leaves named by their alignment rows"""
+    import sys
+    sys.setrecursionlimit(max(10000, 4 * tree.nnodes))
+    adj = tree.adjacency()
+    root = tree.ntaxa - 1
+    top = adj[root][0][0]
+
+    def rec(node, dad):
+        if node < tree.ntaxa:
+            return "%d" % node
+        return "(" + ",".join(rec(v, node) + ":" + (fmt % tree.lengths[b]) for v, b in adj[node] if v != dad) + ")"
+
+    return "(" + ",".join(rec(v, top) + ":" + (fmt % tree.lengths[b]) for v, b in adj[top] if v != root) + ");"
+
+
 class RefTree:
     """One reference PhyloTree (alignment patterns + tree + harness-supplied eigensystem)."""
 
@@ -125,6 +142,11 @@ class RefTree:
             import re
             row = {nm: str(i) for i, nm in enumerate(names)}
             nwk = re.sub(r"(?<=[(,])\s*([^():,;\s]+)(?=\s*[:,)])", lambda m: row[m.group(1)], newick)
+        elif getattr(model, "nonrev", None) and model.nonrev["rooted"]:
+            # rooted tree: `tree` has ntaxa + 1 leaves, the last one the virtual root leaf; the Newick is written from the node it
+            # hangs on, with a bifurcating root, and MTree::readTree attaches the root leaf itself (tree/mtree.cpp:742-754)
+            assert tree.ntaxa == self.ntaxa + 1
+            nwk = rooted_newick(tree)
         else:
             old = tree.names
             tree.names = ["%d" % i for i in range(self.ntaxa)]   # readTreeString takes alignment row ids as leaf names
@@ -132,6 +154,10 @@ class RefTree:
                 nwk = tree.to_newick(fmt="%.17g")
             finally:
                 tree.names = old
+        nr = getattr(model, "nonrev", None)
+        if nr:
+            a = [f64(nr["ceval"]), f64(nr["cevec"]), f64(nr["cinv_evec"]), f64(nr["rate_matrix"])]
+            self._L().iqref_set_nonrev_next(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), C.c_int(self.n), C.c_int(model.nmix))
         k = self._keep
         d = _Desc(self.n, model.ncat, model.nmix, int(model.fused_mix_rate), int(self.safe), SEQ_TYPES[model.seq_type],
                   model.state_unknown, self.ntaxa, self.nptn, int(nthreads), 0, _p(k[0]), _p(k[1]), nwk.encode(),

@@ -64,11 +64,53 @@ struct HModel : public ModelSubst {
     int state_unknown;
     AVec eval, evec, inv_evec;
     std::vector<double> weight, freq;
+    // non-reversible mode (the kernels of tree/phylokernelnonrev.h): the complex eigensystem ModelMarkov would hold (ceval, cevec,
+    // cinv_evec; [nmix][n](re,im) / [nmix][n][n](re,im) row-major) and the rate matrices, supplied by the caller
+    bool nonrev = false;
+    std::vector<double> ceval, cevec, cinv, qmat;
     HModel(int n, int nmix_, int seqtype_, int su) : ModelSubst(n), nmix(nmix_), seqtype(seqtype_), state_unknown(su) {
         name = "HARNESS";
         full_name = "harness-supplied eigensystem";
     }
-    bool isReversible() override { return true; }
+    bool isReversible() override { return !nonrev; }
+    // ModelMarkov::computeTransMatrixNonrev, MET_EIGEN3LIB_DECOMPOSITION (model/modelmarkov.cpp:477-486; ModelMarkov itself needs
+    // Eigen3 and is not compiled): P = Re(cevec . diag(exp(ceval t)) . cinv_evec)
+    void computeTransMatrix(double time, double *trans_matrix, int mixture = 0, int selected_row = -1) override {
+        const int n = num_states;
+        const double *ev = &ceval[(size_t)mixture * n * 2], *V = &cevec[(size_t)mixture * n * n * 2], *W = &cinv[(size_t)mixture * n * n * 2];
+        std::vector<double> er(n), ei(n);
+        for (int k = 0; k < n; k++) {
+            const double a = exp(ev[2 * k] * time);
+            er[k] = a * cos(ev[2 * k + 1] * time);
+            ei[k] = a * sin(ev[2 * k + 1] * time);
+        }
+        for (int i = 0; i < n; i++)
+            for (int j = 0; j < n; j++) {
+                double sum = 0.0;
+                for (int k = 0; k < n; k++) {
+                    const double vr = V[(size_t)(i * n + k) * 2], vi = V[(size_t)(i * n + k) * 2 + 1];
+                    const double ar = vr * er[k] - vi * ei[k], ai = vr * ei[k] + vi * er[k];
+                    sum += ar * W[(size_t)(k * n + j) * 2] - ai * W[(size_t)(k * n + j) * 2 + 1];
+                }
+                trans_matrix[i * n + j] = sum;
+            }
+    }
+    // ModelMarkov::computeTransDerv, non-reversible (model/modelmarkov.cpp:735-747): Q.P and Q.Q.P
+    void computeTransDerv(double time, double *trans_matrix, double *trans_derv1, double *trans_derv2, int mixture = 0) override {
+        const int n = num_states;
+        const double *Q = &qmat[(size_t)mixture * n * n];
+        computeTransMatrix(time, trans_matrix, mixture);
+        for (int pass = 0; pass < 2; pass++) {
+            const double *src = pass ? trans_derv1 : trans_matrix;
+            double *dst = pass ? trans_derv2 : trans_derv1;
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) {
+                    double sum = 0.0;
+                    for (int k = 0; k < n; k++) sum += Q[i * n + k] * src[k * n + j];
+                    dst[i * n + j] = sum;
+                }
+        }
+    }
     bool isMixture() override { return nmix > 1; }
     int getNMixtures() override { return nmix; }
     double getMixtureWeight(int cat) override { return weight[cat]; }
@@ -156,7 +198,7 @@ void init_params(int nthreads) {
 PhyloNeighbor *nei_towards(PhyloNode *from, PhyloNode *to) { return (PhyloNeighbor *)from->findNeighbor(to); }
 
 void collect_leaves(Node *node, Node *dad, std::vector<uint8_t> &mask) {
-    if (node->isLeaf()) { mask[node->id] = 1; return; }
+    if (node->isLeaf()) { if (node->id >= 0 && node->id < (int)mask.size()) mask[node->id] = 1; return; }   // (the root leaf of a rooted tree has id ntaxa)
     FOR_NEIGHBOR_IT(node, dad, it) collect_leaves((*it)->node, node, mask);
 }
 
@@ -219,6 +261,19 @@ void iqref_set_asc_next(int asc_type, const uint8_t *unobs, int nunobs, int ntax
     for (int u = 0; u < nunobs; u++) g_unobs.emplace_back(unobs + (size_t)u * ntaxa, unobs + (size_t)(u + 1) * ntaxa);
 }
 
+// non-reversible model for the NEXT iqref_create: HModel::nonrev and its arrays; the Newick handed to that create has a bifurcating
+// root, so MTree::readTree makes the tree rooted and attaches the root leaf (tree/mtree.cpp:742-754) — or, with rooted = 0, a
+// trifurcating one (the non-reversible kernel on an unrooted tree, as --kernel-nonrev runs it)
+static bool g_nonrev = false;
+static std::vector<double> g_ceval, g_cevec, g_cinv, g_qmat;
+void iqref_set_nonrev_next(const double *ceval, const double *cevec, const double *cinv, const double *qmat, int n, int nmix) {
+    g_nonrev = true;
+    g_ceval.assign(ceval, ceval + (size_t)2 * nmix * n);
+    g_cevec.assign(cevec, cevec + (size_t)2 * nmix * n * n);
+    g_cinv.assign(cinv, cinv + (size_t)2 * nmix * n * n);
+    g_qmat.assign(qmat, qmat + (size_t)nmix * n * n);
+}
+
 void *iqref_create(const iqref_desc *d) {
     init_params(d->nthreads > 0 ? d->nthreads : 1);
     Params &params = Params::getInstance();
@@ -261,6 +316,7 @@ void *iqref_create(const iqref_desc *d) {
     m->inv_evec.assign(d->inv_evec, d->inv_evec + (size_t)d->nmix * n * n);
     m->weight.assign(d->mix_weight, d->mix_weight + d->nmix);
     m->freq.assign(d->state_freq, d->state_freq + (size_t)d->nmix * n);
+    if (g_nonrev) { m->nonrev = true; m->ceval = g_ceval; m->cevec = g_cevec; m->cinv = g_cinv; m->qmat = g_qmat; g_nonrev = false; }
     HRate *r = h->rate = new HRate();
     r->rate.assign(d->cat_rate, d->cat_rate + d->ncat);
     r->prop.assign(d->cat_prop, d->cat_prop + d->ncat);
@@ -289,10 +345,11 @@ void *iqref_create(const iqref_desc *d) {
     tree->setModelFactory(fac);            // -> setLikelihoodKernel(sse) + setNumThreads
     r->setTree(tree);
     tree->initializeAllPartialLh();
-    h->leaf.assign(d->ntaxa, nullptr);
+    h->leaf.assign(d->ntaxa + (tree->rooted ? 1 : 0), nullptr);   // rooted: the root leaf has id ntaxa (PhyloTree::setAlignment)
     NodeVector taxa;
     tree->getTaxa(taxa);
-    for (Node *x : taxa) if (x->id >= 0 && x->id < d->ntaxa) h->leaf[x->id] = (PhyloNode *)x;
+    for (Node *x : taxa) if (x->id >= 0 && x->id < (int)h->leaf.size()) h->leaf[x->id] = (PhyloNode *)x;
+    if (tree->rooted) h->leaf[d->ntaxa] = (PhyloNode *)tree->root;
     for (auto *x : h->leaf) if (!x) { h->err = "leaf missing"; }
     return h;
 }
