@@ -113,6 +113,31 @@ int b200lk_set_pattern_invar(b200lk_engine *e, const double *ptn_invar);
  * recomputes tip_partial_lh on device = computeTipPartialLikelihood (tree/phylotreesse.cpp:243-375) */
 int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec,
                      const double *mix_weight);
+/* ---- non-reversible models: the kernels of tree/phylokernelnonrev.h (computeNonrevPartialLikelihood :32, computeNonrevLikelihoodDerv
+ * :583, computeNonrevLikelihoodBranch :1059), which setLikelihoodKernel assigns when !model->useRevKernel() — a non-reversible
+ * model, or any model under --kernel-nonrev (model/modelsubst.h:73-75).  After this call the engine's CLV slots hold STATE-space
+ * vectors and b200lk_update_partials / (enqueue_)branch_logl / (enqueue_)branch_derv / newton_branch run that kernel:
+ *   - transition matrices are built on the device as the reference's default technique does (ModelMarkov::computeTransMatrixNonrev,
+ *     model/modelmarkov.cpp:477-486): P_m(t) = Re(cevec_m . diag(exp(ceval_m t)) . cinv_evec_m); the derivatives of the evaluation
+ *     branch are rate_matrix_m . P and rate_matrix_m^2 . P (:735-747).  ceval: [nmix][n] complex as (re, im) pairs; cevec, cinv_evec:
+ *     [nmix][n][n] complex, row-major; rate_matrix [nmix][n][n]; state_freq [nmix][n] (model->getStateFrequency(., m)).  (The
+ *     scaling-and-squaring fall-back the reference takes for non-diagonalisable matrices, :465-476, stays with the caller.)
+ *   - a child's `kind` is B200LK_CHILD_TIP / _SLOT / _ROOT (the virtual root leaf of a rooted tree, MTree::isRootLeaf,
+ *     tree/mtree.h:135: it contributes the state frequencies, tree/phylokernelnew.h:959-964), or-ed with B200LK_CHILD_TRANSPOSED when
+ *     the child's branch points towards the root (child->direction == TOWARD_ROOT: transposed matrix, :939-951);
+ *   - branch calls: node_slot = dad_branch->partial_lh AFTER the reference's swap (phylokernelnonrev.h:596-603, 1071-1078: the
+ *     root-ward end, or the inner end of a pendant branch); dad_kind = B200LK_CHILD_TIP / _SLOT / _ROOT for the other end;
+ *   - rooted = PhyloTree::rooted; 0 = an unrooted tree (the rows of the evaluation branch's matrix are weighted by state_freq,
+ *     phylokernelnonrev.h:1112-1120);
+ *   - not available in this mode (B200LK_ERR_STATE / _INVALID): b200lk_logl_from_buffer (the reference leaves
+ *     computeLikelihoodFromBufferPointer NULL), save_log_value = 0, +ASC, multifurcating ops, grouped launches, the device-resident
+ *     sweep (b200lk_enqueue_newton_branch; b200lk_newton_branch iterates from the host). */
+#define B200LK_CHILD_TIP 0
+#define B200LK_CHILD_SLOT 1
+#define B200LK_CHILD_ROOT 2
+#define B200LK_CHILD_TRANSPOSED 4
+int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double *cevec, const double *cinv_evec,
+                            const double *rate_matrix, const double *state_freq, const double *mix_weight, int32_t rooted);
 /* site_rate->getRate(c) / getProp(c) */
 int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop);
 

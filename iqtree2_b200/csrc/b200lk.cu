@@ -11,6 +11,7 @@
 #include "b200lk_walk4.cuh"
 #include "b200lk_walkgen.cuh"
 #include "b200lk_group.cuh"
+#include "b200lk_nonrev.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -116,6 +117,12 @@ struct b200lk_engine {
     // multi-device engine (b200lk_multi.inc): one shard engine per device over pattern slices [shard_lo[k], shard_lo[k+1])
     std::vector<b200lk_engine *> shards;
     std::vector<long long> shard_lo;
+    // non-reversible models (b200lk_nonrev.inc): ceval | cevec | cinv_evec | rate matrices | state frequencies | state indicators;
+    // the evaluation branch's matrices and leaf tables; the per-child jobs of the info kernel
+    bool nonrev = false, nr_rooted = false;
+    double *d_nr_model = nullptr, *d_nr_branch = nullptr;
+    NrChildJob *d_nr_jobs = nullptr;
+    size_t nr_jobs_cap = 0;
     std::string err;
 };
 
@@ -187,6 +194,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
+    cudaFree(e->d_nr_model); cudaFree(e->d_nr_branch); cudaFree(e->d_nr_jobs);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_boot_state); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -940,9 +948,12 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
     return 0;
 }
 
+#include "b200lk_nonrev.inc"
+
 // Enqueue (no sync) everything computePartialLikelihood needs for the op list.
 static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     if (nops <= 0) return 0;
+    if (e->nonrev) return nonrev_enqueue_partials(e, ops, nops);
     // multifurcating ops (reserved = number of children beyond left/right, taken in op order from b200lk_set_extra_children)
     int nextra = 0;
     for (int k = 0; k < nops; k++) {
@@ -1113,7 +1124,7 @@ static int check_branch(b200lk_engine *e, int node_slot, int dad_kind, int dad_i
     if (node_slot < 0 || node_slot >= e->cfg.nslots) return fail(e, B200LK_ERR_INVALID, "node_slot out of range");
     if (dad_kind == 0) { if (dad_id < 0 || dad_id >= e->cfg.ntaxa) return fail(e, B200LK_ERR_INVALID, "dad taxon out of range"); }
     else if (dad_kind == 1) { if (dad_id < 0 || dad_id >= e->cfg.nslots || dad_id == node_slot) return fail(e, B200LK_ERR_INVALID, "dad slot invalid"); }
-    else return fail(e, B200LK_ERR_INVALID, "dad_kind must be 0 or 1");
+    else if (!(e->nonrev && dad_kind == kNrKindRoot)) return fail(e, B200LK_ERR_INVALID, "dad_kind must be 0 or 1 (2 = the root leaf with the non-reversible kernel)");
     return 0;
 }
 
@@ -1162,6 +1173,17 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     prof_mark(e, 1);
+    if (e->nonrev) {   // computeNonrevLikelihoodBranch (tree/phylokernelnonrev.h:1062-1528); save_log_value = false has no form there
+        if (!save_log_value) return fail(e, B200LK_ERR_STATE, "non-reversible kernel: save_log_value = false is not available");
+        rc = nonrev_enqueue_root(e, node_slot, dad_kind, dad_id, length);
+        if (rc) return rc;
+        prof_mark(e, 2);
+        CK(cudaGetLastError());
+        e->have_lh_cat = true;
+        e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | PEND_SAVE_LOG;
+        e->pending_marks = 2;
+        return 0;
+    }
     const int nblocks = (int)(e->Ppad / kTile);
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
@@ -1303,8 +1325,13 @@ extern "C" int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
     if (!chained) { prof_mark(e, 1); prof_mark(e, 2); }
+    if (e->nonrev) {   // computeNonrevLikelihoodDerv (tree/phylokernelnonrev.h:586-1056): both ends' CLVs, no theta buffer
+        rc = nonrev_enqueue_derv(e, node_slot, dad_kind, dad_id, length);
+        if (rc) return rc;
+    } else {
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
     enqueue_derv(e, length);
+    }
     prof_mark(e, 3);
     CK(cudaGetLastError());
     e->pending |= PEND_DERV;
@@ -1322,6 +1349,7 @@ extern "C" int b200lk_branch_derv(b200lk_engine *e, const b200lk_op *ops, int32_
 extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) {
     if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_enqueue_logl_from_buffer(e->shards[k], length); });
     cudaSetDevice(e->cfg.device);
+    if (e->nonrev) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: the non-reversible kernel has no theta buffer (the reference leaves computeLikelihoodFromBufferPointer NULL)");
     if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
     prof_begin(e);
     prof_mark(e, 1);
@@ -1382,7 +1410,7 @@ extern "C" int b200lk_enqueue_newton_branch(b200lk_engine *e, const b200lk_op *o
                                             int32_t len_slot) {
     if (!e->shards.empty()) MG_UNSUPPORTED(e, "enqueue_newton_branch");
     cudaSetDevice(e->cfg.device);
-    if (!newton_coop_ok(e)) return fail(e, B200LK_ERR_STATE, "enqueue_newton_branch: no device-resident Newton iteration for this configuration");
+    if (e->nonrev || !newton_coop_ok(e)) return fail(e, B200LK_ERR_STATE, "enqueue_newton_branch: no device-resident Newton iteration for this configuration");
     if (len_slot < 0 || len_slot >= e->nlen_slots) return fail(e, B200LK_ERR_INVALID, "len_slot out of range");
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
@@ -1472,6 +1500,22 @@ extern "C" int b200lk_newton_branch(b200lk_engine *e, const b200lk_op *ops, int3
     if (nops > 0) e->theta_computed = false;
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
+    if (e->nonrev) {   // host-driven iteration over computeNonrevLikelihoodDerv: one matrices kernel + one pattern pass per step
+        int nsteps = 0;
+        auto fd = [&](double x, double &f, double &df) -> int {
+            int r = nonrev_enqueue_derv(e, node_slot, dad_kind, dad_id, x);
+            if (r) return r;
+            cudaError_t ce = sync_stream(e);
+            if (ce != cudaSuccess) { e->err = cudaGetErrorString(ce); return B200LK_ERR_CUDA; }
+            f = -e->h_result[1];
+            df = -e->h_result[2];
+            nsteps++;
+            return 0;
+        };
+        rc = host_newton(fd, x1, xguess, x2, xacc, maxNRStep, length_out);
+        if (steps_out) *steps_out = nsteps;
+        return rc;
+    }
     if (!e->theta_computed) enqueue_theta(e, node_slot, dad_kind, dad_id);
     if (newton_coop_ok(e)) {
         // the whole iteration in one cooperative launch (k_newton_coop); variant 9 keeps the host-driven loop below for A/B

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
     "b200lk_group_create", "b200lk_group_destroy", "b200lk_group_last_error", "b200lk_group_enqueue_branch_logl",
     "b200lk_group_enqueue_branch_derv", "b200lk_group_enqueue_logl_from_buffer", "b200lk_group_finish", "b200lk_group_launch_count",
-    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state",
+    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state", "b200lk_set_model_nonrev",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -164,6 +164,10 @@ class LikelihoodEngine:
         self._check(self.lib.b200lk_set_model(self._h, _dp(ev), _dp(U), _dp(Ui), _dp(w)))
         r, p = f(model.cat_rate), f(model.cat_prop)
         self._check(self.lib.b200lk_set_rates(self._h, _dp(r), _dp(p)))
+        nr = getattr(model, "nonrev", None)
+        if nr:   # non-reversible kernel (tree/phylokernelnonrev.h): complex eigensystem, rate matrices, state frequencies
+            a = [f(nr["ceval"]), f(nr["cevec"]), f(nr["cinv_evec"]), f(nr["rate_matrix"]), f(model.state_freq)]
+            self._check(self.lib.b200lk_set_model_nonrev(self._h, _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(a[3]), _dp(a[4]), _dp(w), C.c_int32(int(nr["rooted"]))))
 
     def set_tip_states(self, states):
         s = np.ascontiguousarray(states, dtype=np.uint8)
