@@ -37,6 +37,10 @@ WORKLOADS = {
     "aa_100x50k_lg_c60_g4": (100, 50_000, lambda: models.make_lg_c60_gamma(), "synthetic protein 100 taxa x 50k patterns, LG+C60+G4"),
     # not a BASELINE config: the general-n FP64-MMA walker.  61 sense codons, random reversible exchangeabilities,
     # Gamma(4); SAFE_LH as the reference forces for every n outside {4, 20} (tree/phylotreesse.cpp:95-96)
+    # not a BASELINE config: the non-reversible kernels (tree/phylokernelnonrev.h) on a ROOTED tree — a general 12-parameter DNA
+    # rate matrix (UNREST-like) + Gamma(4); ntaxa real taxa + the virtual root leaf
+    "dna_500x200k_unrest_g4": (500, 200_000, lambda: models.make_nonreversible(4, ncat=4, seed=11, state_unknown=models.DNA_STATE_UNKNOWN),
+                               "synthetic DNA 500 taxa x 200k patterns, rooted, non-reversible 12-parameter model + G4"),
     "codon_100x20k_rev61_g4": (100, 20_000, lambda: models.make_random_reversible(61, ncat=4, seed=7), "synthetic codon 100 taxa x 20k patterns, 61-state reversible + G4"),
 }
 SAFE_WORKLOADS = {"codon_100x20k_rev61_g4"}
@@ -414,8 +418,11 @@ def run_reference_arm(args, workload, ntaxa, nptn, model, desc, workload_name, s
     sample = max(256, min(sample, mem_cap))
     # time cap: a short calibration run, then at most ~150 s for warm-up + timed steps (never below a quarter of the patterns
     # when memory allows that)
-    tree, tips, freq, data = make_inputs(ntaxa, sample, model)
-    ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+    nonrev = getattr(model, "nonrev", None) is not None
+    tree, tips, freq, data = make_inputs(ntaxa + (1 if nonrev else 0), sample, model)
+    if nonrev:
+        tips = np.ascontiguousarray(tips[:ntaxa])
+    ops, a, b, L = (plan.plan_branch_nonrev if nonrev else plan.plan_branch)(tree, plan.pendant_branch_of(tree, 0))
     if not args.cpu_sample:
         cal_n = min(sample, 8192)
         cal = run_cpu_reference(tree, model, tips, freq, ops, a, b, L, cal_n, 1, 1, safe=workload in SAFE_WORKLOADS)
@@ -487,15 +494,23 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     per = (per + 127) // 128 * 128
     lo, hi = min(rank * per, nptn), min((rank + 1) * per, nptn)
     my_nptn = hi - lo
-    tree, tips_all, freq_all, data = make_inputs(ntaxa, nptn, model)
+    nonrev = getattr(model, "nonrev", None) is not None
+    tree, tips_all, freq_all, data = make_inputs(ntaxa + (1 if nonrev else 0), nptn, model)   # rooted: the last leaf is the root leaf
+    if nonrev:
+        tips_all = np.ascontiguousarray(tips_all[:ntaxa])
+        data += "; rooted at an extra (virtual) leaf"
     tips = np.ascontiguousarray(tips_all[:, lo:hi])
     freq = freq_all[lo:hi]
     br = plan.pendant_branch_of(tree, 0)
-    ops, a, b, L = plan.plan_branch(tree, br)
+    ops, a, b, L = plan.plan_branch_nonrev(tree, br) if nonrev else plan.plan_branch(tree, br)
+    ops_acc = ops.copy()   # byte / flop accounting: child kinds without the non-reversible flags (the root leaf counts as a tip)
+    for side in ("left", "right"):
+        k = ops_acc[side]["kind"] & 3
+        ops_acc[side]["kind"] = np.where(k == plan.KIND_ROOT, plan.KIND_TIP, k)
 
     # CLV slots: one per internal node (LM_PER_NODE) when that fits the device; otherwise the reference's -mem mode
     # (LM_MEM_SAVE, tree/phylotree.cpp:999-1021): the host mirror's planner recycles a bounded number of slots
-    nslots, mem_mode = None, "LM_PER_NODE"
+    nslots, mem_mode = (ntaxa - 1 + 2 if nonrev else None), "LM_PER_NODE"
     slot_bytes = ((my_nptn + 127) // 128 * 128) * (8 * B + 2 * S)
     dev_total = torch.cuda.get_device_properties(local_rank).total_memory
     mem_frac = args.mem
@@ -581,15 +596,17 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     K = steps
     value = K / (res_run["event_ms"] * 1e-3)     # CUDA events around the K timed steps (inputs resident), max over ranks
     e2e_value = K / (e2e_run["event_ms"] * 1e-3)
-    bytes_eval, bytes_partials = algorithmic_bytes(ops, nptn, B, S, ntaxa, n_root_slots=1 + (b[0] == plan.KIND_SLOT))
+    bytes_eval, bytes_partials = algorithmic_bytes(ops_acc, nptn, B, S, ntaxa, n_root_slots=1 + (b[0] == plan.KIND_SLOT))
     my_bytes_partials = bytes_partials * (my_nptn / nptn)
     peak, peak_src = load_peaks()
     ker_s = res_run["partials_kernel_ms"] * 1e-3 / K
     alg_gbps = my_bytes_partials / ker_s / 1e9
-    n_ii, n_ti, n_tt = plan.count_node_cases(ops)
-    walk4 = args.schedule != 1 and model.nstates == 4 and model.nmix == 1
+    n_ii, n_ti, n_tt = plan.count_node_cases(ops_acc)
+    walk4 = args.schedule != 1 and model.nstates == 4 and model.nmix == 1 and not nonrev
     walk20 = args.schedule != 1 and model.nstates == 20
-    if walk20:
+    if nonrev:
+        kernel_name = f"k_nonrev_partials<{model.nstates}> (thread per pattern, state-space CLVs, device-built transition matrices)"
+    elif walk20:
         kernel_name = "k_walk_n20v2 (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs, cp.async rings)"
     elif walk4:
         kernel_name = ("k_walk_n4c4 (pattern-tile walker, 4 states x 4 categories)" if model.ncat_mix == 4 else
@@ -598,7 +615,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         kernel_name = f"k_walk_gen<{(model.nstates + 7) // 8}> (pattern-tile walker, FP64 MMA m8n8k4, {model.nstates} states padded to {(model.nstates + 7) // 8 * 8})"
     else:
         kernel_name = "k_partials_generic"
-    model_bytes = dram_model_bytes(ops, my_nptn, B, S, chained=walk4)
+    model_bytes = dram_model_bytes(ops_acc, my_nptn, B, S, chained=walk4)
     traffic, traffic_src = load_traffic(workload, overridden or bool(args.variant or args.schedule), my_nptn)
     # roofline.frac is PHYSICAL: bytes at the DRAM pins (the committed ncu capture of this workload, else the DRAM-side model)
     # per launch / launch time / measured copy peak.  The SURVEY 8(d) algorithmic figure (every CLV written once AND read once)

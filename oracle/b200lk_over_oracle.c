@@ -22,6 +22,8 @@ int orc_set_pattern_freq(orc_engine *e, const double *f);
 int orc_set_pattern_invar(orc_engine *e, const double *f);
 int orc_set_rates(orc_engine *e, const double *rate, const double *prop);
 int orc_set_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec, const double *mix_weight);
+int orc_set_model_nonrev(orc_engine *e, const double *ceval, const double *cevec, const double *cinv_evec, const double *rate_matrix,
+                         const double *state_freq, const double *mix_weight, int rooted);
 int orc_update_partials(orc_engine *e, const void *ops, int nops);
 int orc_branch_logl(orc_engine *e, const void *ops, int nops, int node_slot, int dad_kind, int dad_id, double length, int save_log_value, double *logl_out);
 int orc_branch_derv(orc_engine *e, const void *ops, int nops, int node_slot, int dad_kind, int dad_id, double length, double *df_out, double *ddf_out);
@@ -72,6 +74,10 @@ int b200lk_set_pattern_freq(b200lk_engine *e, const double *f) { return wrap(e, 
 int b200lk_set_pattern_invar(b200lk_engine *e, const double *f) { return wrap(e, orc_set_pattern_invar(e->o, f)); }
 int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec, const double *w) {
     return wrap(e, orc_set_model(e->o, eval, evec, inv_evec, w));
+}
+int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double *cevec, const double *cinv_evec, const double *rate_matrix,
+                            const double *state_freq, const double *mix_weight, int32_t rooted) {
+    return wrap(e, orc_set_model_nonrev(e->o, ceval, cevec, cinv_evec, rate_matrix, state_freq, mix_weight, rooted));
 }
 int b200lk_set_rates(b200lk_engine *e, const double *r, const double *p) { return wrap(e, orc_set_rates(e->o, r, p)); }
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t t, int64_t n, int64_t s) { return wrap(e, orc_set_ascertainment(e->o, t, n, s)); }

@@ -24,6 +24,9 @@
 #include "b200lk.h"
 
 extern PhyloTree *(*iqref_tree_factory)();   // ref_harness.cpp: how iqref_create makes its tree
+// ref_harness.cpp: the complex eigensystem and rate matrices of the harness's non-reversible model (in a full IQ-TREE build these
+// are ModelMarkov's members ceval / cevec / cinv_evec / rate_matrix, model/modelmarkov.h); false for a reversible model
+extern bool iqref_nonrev_arrays(ModelSubst *model, const double **ceval, const double **cevec, const double **cinv, const double **qmat);
 
 namespace {
 
@@ -56,8 +59,14 @@ public:
         c.kind = nei->node->isLeaf() ? 0 : 1;
         c.id = nei->node->isLeaf() ? nei->node->id : slotOf(nei);
         c.length = nei->length;
+        if (!model->useRevKernel()) {   // computePartialInfo's non-reversible branch (tree/phylokernelnew.h:932-1008)
+            if (isRootLeaf(nei->node)) { c.kind = B200LK_CHILD_ROOT; c.id = 0; }
+            if (nei->direction == TOWARD_ROOT) c.kind |= B200LK_CHILD_TRANSPOSED;
+        }
         return c;
     }
+    int dadKind(PhyloNode *dad) { return isRootLeaf(dad) && !model->useRevKernel() ? B200LK_CHILD_ROOT : (dad->isLeaf() ? 0 : 1); }
+    int dadId(PhyloNode *dad, PhyloNeighbor *node_branch) { return isRootLeaf(dad) && !model->useRevKernel() ? 0 : (dad->isLeaf() ? dad->id : slotOf(node_branch)); }
 
     void uploadModel() {
         const int n = aln->num_states, nmix = model->getNMixtures();
@@ -68,6 +77,13 @@ public:
         std::vector<double> rate(ncat), prop(ncat);
         for (int c = 0; c < ncat; c++) { rate[c] = site_rate->getRate(c); prop[c] = site_rate->getProp(c); }
         check(b200lk_set_rates(b200, rate.data(), prop.data()), "set_rates");
+        if (!model->useRevKernel()) {   // the kernels of tree/phylokernelnonrev.h
+            const double *ceval, *cevec, *cinv, *qmat;
+            if (!iqref_nonrev_arrays(model, &ceval, &cevec, &cinv, &qmat)) outError("non-reversible kernel: the model has no complex eigensystem");
+            std::vector<double> freq((size_t)nmix * n);
+            for (int m = 0; m < nmix; m++) model->getStateFrequency(&freq[(size_t)m * n], m);
+            check(b200lk_set_model_nonrev(b200, ceval, cevec, cinv, qmat, freq.data(), w.data(), rooted ? 1 : 0), "set_model_nonrev");
+        }
         // ptn_invar: observed patterns, then the unobserved constant patterns of +ASC, which the reference keeps behind the
         // padded observed block (tree/phylotreesse.cpp:585-611)
         const size_t nobs = aln->size(), U = model_factory->unobserved_ptns.size(), max_orig = get_safe_upper_limit(nobs);
@@ -80,22 +96,23 @@ public:
 
     // after initializeAllPartialLh: create the engine, hand over the inputs, take over the kernel pointers
     void attach() {
-        ASSERT(params->lh_mem_save == LM_PER_NODE && model->useRevKernel());
+        ASSERT(params->lh_mem_save == LM_PER_NODE);
+        const int nseq = (int)aln->getNSeq();   // (a rooted tree has one leaf more: the root leaf, without a sequence)
         computeTipPartialLikelihood();   // also ptn_freq / ptn_invar (tree/phylotreesse.cpp:243-375, 537-612)
         b200lk_config cfg{};
         cfg.nstates = aln->num_states; cfg.ncat = site_rate->getNRate(); cfg.nmix = model->getNMixtures();
         cfg.fused_mix_rate = model_factory->fused_mix_rate; cfg.safe_numeric = safe_numeric;
         cfg.seq_type = aln->seq_type == SEQ_DNA ? 1 : aln->seq_type == SEQ_PROTEIN ? 2 : 0;
         const size_t U = model_factory->unobserved_ptns.size();   // +ASC: appended as the engine's last patterns
-        cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = leafNum; cfg.nptn = (int64_t)(aln->size() + U);
+        cfg.state_unknown = aln->STATE_UNKNOWN; cfg.ntaxa = nseq; cfg.nptn = (int64_t)(aln->size() + U);
         cfg.nslots = (leafNum - 2) + 2; cfg.device = 0;
         // Params::num_threads' counterpart for devices: B200LK_NDEV=N puts the tree on the first N GPUs (cfg.device = -N: one
         // engine per device over pattern slices behind the same handle, include/b200lk.h)
         if (const char *nd = getenv("B200LK_NDEV")) if (atoi(nd) > 1 && U == 0) cfg.device = -atoi(nd);
         if (b200lk_create(&cfg, &b200) != 0) outError(std::string("b200lk_create: ") + b200lk_last_error(nullptr));
         const size_t nobs = aln->size(), nptn = nobs + U;
-        std::vector<uint8_t> states((size_t)leafNum * nptn);
-        for (int t = 0; t < (int)leafNum; t++) {
+        std::vector<uint8_t> states((size_t)nseq * nptn);
+        for (int t = 0; t < nseq; t++) {
             for (size_t p = 0; p < nobs; p++) states[(size_t)t * nptn + p] = (uint8_t)aln->at(p)[t];
             for (size_t u = 0; u < U; u++) states[(size_t)t * nptn + nobs + u] = (uint8_t)model_factory->unobserved_ptns[u][t];
         }
@@ -113,6 +130,7 @@ public:
         computeLikelihoodBranchPointer = static_cast<ComputeLikelihoodBranchType>(&PhyloTreeB200::computeLikelihoodBranchB200);
         computeLikelihoodDervPointer = static_cast<ComputeLikelihoodDervType>(&PhyloTreeB200::computeLikelihoodDervB200);
         computeLikelihoodFromBufferPointer = static_cast<ComputeLikelihoodFromBufferType>(&PhyloTreeB200::computeLikelihoodFromBufferB200);
+        if (!model->useRevKernel()) computeLikelihoodFromBufferPointer = NULL;   // as setLikelihoodKernel leaves it for the non-reversible kernel
         computePartialLikelihoodPointer = static_cast<ComputePartialLikelihoodType>(&PhyloTreeB200::computePartialLikelihoodB200);
         computeLikelihoodDervMixlenPointer = NULL;
     }
@@ -143,7 +161,9 @@ public:
     void planBranch(PhyloNeighbor *&dad_branch, PhyloNode *&dad, PhyloNeighbor *&node_branch) {
         PhyloNode *node = (PhyloNode *)dad_branch->node;
         node_branch = (PhyloNeighbor *)node->findNeighbor(dad);
-        if (node->isLeaf()) {   // :2654-2661
+        const bool swap = model->useRevKernel() ? node->isLeaf()   // :2654-2661
+                                                : (node->isLeaf() || (dad_branch->direction == AWAYFROM_ROOT && !isRootLeaf(dad)));   // phylokernelnonrev.h:596-603
+        if (swap) {
             std::swap(dad, node);
             std::swap(dad_branch, node_branch);
         }
@@ -170,8 +190,8 @@ public:
         const double length = dad_branch->length;
         planBranch(dad_branch, dad, node_branch);
         double logl = 0.0;
-        int rc = b200lk_branch_logl(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
-                                    dad->isLeaf() ? dad->id : slotOf(node_branch), length, save_log_value, &logl);
+        int rc = b200lk_branch_logl(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
+                                    dadId(dad, node_branch), length, save_log_value, &logl);
         if (rc == B200LK_WARN_UNDERFLOW) outWarning("Numerical underflow for lh-branch");
         check(rc, "branch_logl");
         // callers read _pattern_lh / _pattern_lh_cat on the host (computePatternLikelihood, computePatternLhCat): tests are small,
@@ -194,8 +214,8 @@ public:
         planBranch(dad_branch, dad, node_branch);
         if (!b200_ops.empty()) theta_computed = false;
         if (!theta_computed) check(b200lk_theta_reset(b200), "theta_reset");   // :2361-2389: the buffer is rebuilt
-        int rc = b200lk_branch_derv(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
-                                    dad->isLeaf() ? dad->id : slotOf(node_branch), length, df, ddf);
+        int rc = b200lk_branch_derv(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
+                                    dadId(dad, node_branch), length, df, ddf);
         check(rc, "branch_derv");
         theta_computed = true;
     }
@@ -222,8 +242,8 @@ public:
         planBranch(dad_branch, dad, node_branch);
         double optx = current_len;
         int steps = 0;
-        check(b200lk_newton_branch(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dad->isLeaf() ? 0 : 1,
-                                   dad->isLeaf() ? dad->id : slotOf(node_branch), params->min_branch_length, current_len,
+        check(b200lk_newton_branch(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
+                                   dadId(dad, node_branch), params->min_branch_length, current_len,
                                    params->max_branch_length, params->min_branch_length, maxNRStep, &optx, &steps), "newton_branch");
         theta_computed = true;
         if (optx > params->max_branch_length * 0.95) {   // Newton-Raphson diverged: keep the better of the two (:2616-2625)

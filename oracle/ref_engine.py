@@ -271,7 +271,7 @@ class RefTree:
 
     def branches(self):
         """{frozenset(side not containing taxon 0): length}"""
-        nb = 2 * self.ntaxa - 3
+        nb = 2 * self.ntaxa   # (2T - 3 branches; a rooted tree has the root leaf's branch on top: 2T - 1)
         masks, lens = np.zeros((nb, self.ntaxa), dtype=np.uint8), np.zeros(nb)
         k = self._L().iqref_get_branches(self._h, _p(masks), _p(lens))
         return {frozenset(np.nonzero(masks[b])[0].tolist()): float(lens[b]) for b in range(k)}

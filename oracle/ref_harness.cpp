@@ -216,6 +216,14 @@ void collect_directed(PhyloNode *node, PhyloNode *dad, std::vector<Directed> &ou
 
 }  // namespace
 
+// the shim's view of the non-reversible arrays (oracle/ref_b200_shim.cpp)
+bool iqref_nonrev_arrays(ModelSubst *model, const double **ceval, const double **cevec, const double **cinv, const double **qmat) {
+    HModel *m = dynamic_cast<HModel *>(model);
+    if (!m || !m->nonrev) return false;
+    *ceval = m->ceval.data(); *cevec = m->cevec.data(); *cinv = m->cinv.data(); *qmat = m->qmat.data();
+    return true;
+}
+
 // ---- link-time stubs for members whose TUs (phylokernelsse.cpp, phylotreeavx.cpp) are not compiled -------------
 void PhyloTree::setParsimonyKernelSSE() {}   // parsimony is not on the likelihood path
 void PhyloTree::setParsimonyKernelAVX() {}

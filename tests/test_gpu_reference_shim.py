@@ -104,3 +104,35 @@ def test_reference_with_asc_over_the_cuda_kernels(asc_type):
     for k in bc:
         assert abs(bc[k] - bg[k]) < 1e-6
     cpu.close(); gpu.close()
+
+
+@pytest.mark.parametrize("nstates,ncat,safe", [(4, 4, False), (20, 2, True)])
+def test_reference_rooted_tree_with_a_nonreversible_model_over_the_cuda_kernels(nstates, ncat, safe):
+    """the reference's own PhyloTree, ROOTED (root leaf, branch directions from computeBranchDirection), with a non-reversible model:
+    its computeTraversalInfo / optimizeOneBranch / optimizeAllBranches over the product's non-reversible kernels
+    (b200lk_set_model_nonrev; child kinds and the transposition flag marshalled from isRootLeaf / PhyloNeighbor::direction) against
+    the same tree over the reference's computeNonrev* kernels (tree/phylokernelnonrev.h)"""
+    from nonrev_cases import make_nonrev_case
+    tree, model, pat, freq, invar = make_nonrev_case(nstates, ncat, 1, ntaxa=12, nptn=300, seed=37)
+    cpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, nthreads=2)
+    gpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, b200=True)
+    ll_c, plh_c = cpu.compute_likelihood()
+    ll_g, plh_g = gpu.compute_likelihood()
+    assert abs(ll_c - ll_g) < 1e-6, (ll_c, ll_g)
+    np.testing.assert_allclose(plh_g, plh_c, rtol=1e-11)
+    for leaf in (0, 5, pat.shape[0]):          # pendant branches and the branch of the root leaf
+        (lc, pc), (lg, pg) = cpu.branch_logl(leaf), gpu.branch_logl(leaf)
+        assert abs(lc - lg) < 1e-6
+        np.testing.assert_allclose(pg, pc, rtol=1e-11)
+        if leaf != pat.shape[0]:
+            np.testing.assert_allclose(gpu.branch_derv(leaf), cpu.branch_derv(leaf), rtol=1e-9)
+    oc, og = cpu.optimize_all_branches(5, 0.001, 100), gpu.optimize_all_branches(5, 0.001, 100)
+    assert abs(oc - og) < 1e-6, (oc, og)
+    assert og > ll_g
+    bc, bg = cpu.branches(), gpu.branches()
+    assert set(bc) == set(bg)
+    for k in bc:
+        assert abs(bc[k] - bg[k]) < 1e-6, (sorted(k), bc[k], bg[k])
+    calls, launches = gpu.b200_kernel_calls()
+    assert calls > 20 and launches > 20
+    cpu.close(); gpu.close()

@@ -33,3 +33,9 @@ def test_binding_with_the_fused_newton_hook_and_asc(over_oracle):
     m.test_reference_with_the_fused_newton_hook("config1")
     m.test_reference_with_asc_over_the_cuda_kernels(1)
     m.test_reference_with_asc_over_the_cuda_kernels(2)
+
+
+def test_binding_on_a_rooted_tree_with_a_nonreversible_model(over_oracle):
+    import test_gpu_reference_shim as m
+    m.test_reference_rooted_tree_with_a_nonreversible_model_over_the_cuda_kernels(4, 4, False)
+    m.test_reference_rooted_tree_with_a_nonreversible_model_over_the_cuda_kernels(20, 2, True)
