@@ -47,6 +47,9 @@ class ModelInputs:
     # technique uses (ModelMarkov::computeTransMatrixNonrev, model/modelmarkov.cpp:477-486) — "ceval" [nmix][n][2] (re, im),
     # "cevec" / "cinv_evec" [nmix][n][n][2] row-major, "rate_matrix" [nmix][n][n] (for the derivatives Q.P, Q.Q.P) and "rooted"
     nonrev: dict = None
+    # site-specific models (ModelSet: `-fs` site-frequency files / PMSF; the SITE_MODEL branch of tree/phylokernelnew.h): None, or a
+    # dict with one eigensystem per PATTERN — "eval" [nptn][n], "evec" [nptn][n][n], "inv_evec" [nptn][n][n], "Q" (list, for checkers)
+    site: dict = None
 
     @property
     def ncat(self) -> int:
@@ -181,6 +184,31 @@ def make_random_reversible(nstates, ncat=4, nmix=1, alpha=0.7, seed=0, pinvar=0.
     su = nstates if state_unknown is None else state_unknown
     seq_type = "DNA" if (nstates == 4 and su == DNA_STATE_UNKNOWN) else ("AA" if (nstates == 20 and su == PROTEIN_STATE_UNKNOWN) else "GENERIC")
     return _pack(nstates, systems, weights, rates, props, pinvar, su, seq_type)
+
+
+def make_site_specific(nstates, nptn, ncat=4, alpha=0.7, seed=0, pinvar=0.0, state_unknown=None, exch=None) -> ModelInputs:
+    """PMSF-like site-specific model: ONE set of exchangeabilities, a frequency vector per pattern (Dirichlet), hence one
+    eigensystem per pattern with the reference's normalisation.  The class-level arrays (eval / evec / inv_evec / state_freq) hold
+    the mean-frequency model and are not used by the site-specific kernels."""
+    rng = np.random.default_rng(seed)
+    n = nstates
+    S = (rng.gamma(1.0, 1.0, size=(n, n)) + 0.05) if exch is None else exch
+    S = (S + S.T) / 2
+    pis = rng.dirichlet(np.full(n, 3.0), size=nptn) * 0.9 + 0.1 / n
+    ev, U, Ui, Qs = [], [], [], []
+    for p in range(nptn):
+        w, u, ui, Q = reversible_eigensystem(S, pis[p])
+        ev.append(w); U.append(u); Ui.append(ui); Qs.append(Q)
+    mean_pi = pis.mean(axis=0)
+    w, u, ui, Q = reversible_eigensystem(S, mean_pi)
+    rates = discrete_gamma_rates(alpha, ncat) if ncat > 1 else np.ones(1)
+    props = np.full(ncat, (1.0 - pinvar) / ncat)
+    su = nstates if state_unknown is None else state_unknown
+    seq_type = "DNA" if (nstates == 4 and su == DNA_STATE_UNKNOWN) else ("AA" if (nstates == 20 and su == PROTEIN_STATE_UNKNOWN) else "GENERIC")
+    m = _pack(n, [(w, u, ui, Q, mean_pi)], [1.0], rates, props, pinvar, su, seq_type)
+    m.site = dict(eval=np.ascontiguousarray(np.stack(ev)), evec=np.ascontiguousarray(np.stack(U)), inv_evec=np.ascontiguousarray(np.stack(Ui)),
+                  Q=Qs, pi=pis)
+    return m
 
 
 def make_nonreversible(nstates=4, ncat=4, nmix=1, alpha=0.7, seed=0, pinvar=0.0, state_unknown=None, rooted=True) -> ModelInputs:

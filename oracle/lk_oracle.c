@@ -72,6 +72,9 @@ typedef struct {
     /* non-reversible kernel (lk_oracle_nonrev.h): complex eigensystem [nmix][n](re,im) / [nmix][n][n](re,im), rate matrices, frequencies */
     int nonrev, rooted;
     double *ceval, *cevec, *cinv, *qmat, *sfreq;
+    /* site-specific models (lk_oracle_site.h): one eigensystem per pattern, [p][n] / [p][n][n] */
+    int site;
+    double *s_eval, *s_evec, *s_inv;
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
     char err[256];
 } orc_engine;
@@ -324,6 +327,7 @@ void orc_destroy(orc_engine *e) {
     free(e->scale); free(e->theta); free(e->buffer_scale_all); free(e->pattern_lh); free(e->pattern_scaling);
     free(e->pattern_lh_cat); free(e->extra);
     free(e->ceval); free(e->cevec); free(e->cinv); free(e->qmat); free(e->sfreq);
+    free(e->s_eval); free(e->s_evec); free(e->s_inv);
     free(e);
 }
 
@@ -652,8 +656,13 @@ static void compute_partial_range(orc_engine *e, const orc_opinfo *oi, size_t lo
 static int nonrev_update_partials(orc_engine *e, const orc_op *ops, int nops);
 static int nonrev_branch_logl(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, double *logl_out);
 static int nonrev_branch_derv(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, double *df_out, double *ddf_out);
+static int site_update_partials(orc_engine *e, const orc_op *ops, int nops);
+static int site_branch_logl(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, int save_log_value, double *logl_out);
+static int site_branch_derv(orc_engine *e, int node_slot, int dad_kind, int dad_id, double length, double *df_out, double *ddf_out);
+static int site_logl_from_buffer(orc_engine *e, double length, double *logl_out);
 int orc_update_partials(orc_engine *e, const orc_op *ops, int nops) {
     if (e->nonrev) return nonrev_update_partials(e, ops, nops);
+    if (e->site) return site_update_partials(e, ops, nops);
     if (nops <= 0) return 0;
     if (e->cfg.nstates > ORC_MAX_STATES) { snprintf(e->err, sizeof e->err, "nstates > %d", ORC_MAX_STATES); return -1; }
     orc_opinfo *info = (orc_opinfo *)malloc(sizeof(orc_opinfo) * nops);
@@ -743,6 +752,10 @@ int orc_branch_logl(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
     if (e->nonrev) {
         if (orc_update_partials(e, ops, nops) < 0) return -1;
         return nonrev_branch_logl(e, node_slot, dad_kind, dad_id, length, logl_out);
+    }
+    if (e->site) {
+        if (orc_update_partials(e, ops, nops) < 0) return -1;
+        return site_branch_logl(e, node_slot, dad_kind, dad_id, length, save_log_value, logl_out);
     }
     orc_update_partials(e, ops, nops);
     int n = e->cfg.nstates, C = e->C, B = e->B, safe = e->cfg.safe_numeric, nmix = e->cfg.nmix;
@@ -977,6 +990,10 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         if (orc_update_partials(e, ops, nops) < 0) return -1;
         return nonrev_branch_derv(e, node_slot, dad_kind, dad_id, length, df_out, ddf_out);
     }
+    if (e->site) {
+        if (orc_update_partials(e, ops, nops) < 0) return -1;
+        return site_branch_derv(e, node_slot, dad_kind, dad_id, length, df_out, ddf_out);
+    }
     orc_update_partials(e, ops, nops);
     if (!e->theta_computed) build_theta(e, node_slot, dad_kind, dad_id);
     int B = e->B;
@@ -1037,6 +1054,7 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
 /* computeLikelihoodFromBuffer(Generic)SIMD — phylokernelnew.h:3232-3428 */
 int orc_logl_from_buffer(orc_engine *e, double length, double *logl_out) {
     if (!e->theta_computed) { snprintf(e->err, sizeof e->err, "theta not computed"); return -1; }
+    if (e->site) return site_logl_from_buffer(e, length, logl_out);
     int B = e->B;
     size_t P = (size_t)e->cfg.nptn;
     double *val0 = (double *)malloc(sizeof(double) * B);
@@ -1151,6 +1169,7 @@ int orc_get_tip_partial_lh(orc_engine *e, double *out) {
     return 0;
 }
 #include "lk_oracle_nonrev.h"
+#include "lk_oracle_site.h"
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

@@ -79,6 +79,12 @@ class OracleEngine:
         lib().orc_set_model(self._h, _dp(ev), _dp(U), _dp(Ui), _dp(w))
         r, p = f(model.cat_rate), f(model.cat_prop)
         lib().orc_set_rates(self._h, _dp(r), _dp(p))
+        st = getattr(model, "site", None)
+        if st:   # site-specific model (lk_oracle_site.h)
+            b = [f(st["eval"]), f(st["evec"]), f(st["inv_evec"])]
+            assert b[0].shape == (self.nptn, self.n)
+            if lib().orc_set_site_model(self._h, _dp(b[0]), _dp(b[1]), _dp(b[2])) < 0:
+                raise RuntimeError(lib().orc_last_error(self._h).decode())
         nr = getattr(model, "nonrev", None)
         if nr:   # non-reversible kernel (lk_oracle_nonrev.h)
             a = [f(nr["ceval"]), f(nr["cevec"]), f(nr["cinv_evec"]), f(nr["rate_matrix"]), f(model.state_freq)]

@@ -154,6 +154,10 @@ class RefTree:
                 nwk = tree.to_newick(fmt="%.17g")
             finally:
                 tree.names = old
+        st = getattr(model, "site", None)
+        if st:   # site-specific model: one eigensystem per pattern
+            b = [f64(st["eval"]), f64(st["evec"]), f64(st["inv_evec"])]
+            self._L().iqref_set_site_next(_p(b[0]), _p(b[1]), _p(b[2]), C.c_int64(self.nptn), C.c_int(self.n))
         nr = getattr(model, "nonrev", None)
         if nr:
             a = [f64(nr["ceval"]), f64(nr["cevec"]), f64(nr["cinv_evec"]), f64(nr["rate_matrix"])]

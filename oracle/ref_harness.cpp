@@ -68,6 +68,23 @@ struct HModel : public ModelSubst {
     // cinv_evec; [nmix][n](re,im) / [nmix][n][n](re,im) row-major) and the rate matrices, supplied by the caller
     bool nonrev = false;
     std::vector<double> ceval, cevec, cinv, qmat;
+    // site-specific mode (ModelSet: `-fs` site-frequency files / PMSF; the SITE_MODEL template branch of tree/phylokernelnew.h): one
+    // eigensystem per pattern, interleaved by the kernel's SIMD width V as ModelSet lays them out — eval[(p/V) n V + i V + p%V],
+    // evec / inv_evec[(p/V) n^2 V + k V + p%V] (read that way at tree/phylotreesse.cpp:271-281, phylokernelnew.h:1660-1662)
+    bool site = false;
+    AVec s_eval, s_evec, s_inv;
+    bool isSiteSpecificModel() override { return site; }
+    void make_site(const std::vector<double> &ev, const std::vector<double> &U, const std::vector<double> &Ui, size_t nptn, size_t V) {
+        const size_t n = num_states, nn = n * n, maxp = (nptn + V - 1) / V * V;
+        std::vector<double> a(maxp * n), b(maxp * nn), c(maxp * nn);
+        for (size_t p = 0; p < maxp; p++) {
+            const size_t q = p < nptn ? p : nptn - 1, base = p / V, v = p % V;   // padding patterns: the last pattern's system
+            for (size_t i = 0; i < n; i++) a[base * n * V + i * V + v] = ev[q * n + i];
+            for (size_t k = 0; k < nn; k++) { b[base * nn * V + k * V + v] = U[q * nn + k]; c[base * nn * V + k * V + v] = Ui[q * nn + k]; }
+        }
+        s_eval.assign(a.data(), a.data() + a.size()); s_evec.assign(b.data(), b.data() + b.size()); s_inv.assign(c.data(), c.data() + c.size());
+        site = true;
+    }
     HModel(int n, int nmix_, int seqtype_, int su) : ModelSubst(n), nmix(nmix_), seqtype(seqtype_), state_unknown(su) {
         name = "HARNESS";
         full_name = "harness-supplied eigensystem";
@@ -114,9 +131,9 @@ struct HModel : public ModelSubst {
     bool isMixture() override { return nmix > 1; }
     int getNMixtures() override { return nmix; }
     double getMixtureWeight(int cat) override { return weight[cat]; }
-    double *getEigenvalues() const override { return eval.data(); }
-    double *getEigenvectors() const override { return evec.data(); }
-    double *getInverseEigenvectors() const override { return inv_evec.data(); }
+    double *getEigenvalues() const override { return site ? s_eval.data() : eval.data(); }
+    double *getEigenvectors() const override { return site ? s_evec.data() : evec.data(); }
+    double *getInverseEigenvectors() const override { return site ? s_inv.data() : inv_evec.data(); }
     void getStateFrequency(double *f, int mixture = 0) override {
         // mixture -1: weighted average over classes (ModelMixture::getStateFrequency, model/modelmixture.cpp)
         if (mixture >= 0) { memcpy(f, &freq[(size_t)mixture * num_states], sizeof(double) * num_states); return; }
@@ -282,6 +299,16 @@ void iqref_set_nonrev_next(const double *ceval, const double *cevec, const doubl
     g_qmat.assign(qmat, qmat + (size_t)nmix * n * n);
 }
 
+// site-specific model for the NEXT iqref_create: per-pattern eigensystems, plain [p][n] / [p][n][n] (HModel::make_site interleaves them)
+static bool g_site = false;
+static std::vector<double> g_s_eval, g_s_evec, g_s_inv;
+void iqref_set_site_next(const double *eval, const double *evec, const double *inv_evec, int64_t nptn, int n) {
+    g_site = true;
+    g_s_eval.assign(eval, eval + (size_t)nptn * n);
+    g_s_evec.assign(evec, evec + (size_t)nptn * n * n);
+    g_s_inv.assign(inv_evec, inv_evec + (size_t)nptn * n * n);
+}
+
 void *iqref_create(const iqref_desc *d) {
     init_params(d->nthreads > 0 ? d->nthreads : 1);
     Params &params = Params::getInstance();
@@ -350,7 +377,9 @@ void *iqref_create(const iqref_desc *d) {
     tree->setRootNode(params.root);
     tree->sse = LK_AVX_FMA;
     tree->num_threads = d->nthreads > 0 ? d->nthreads : 1;
+    if (g_site) m->site = true;            // setLikelihoodKernel picks the SITE_MODEL instantiations from isSiteSpecificModel()
     tree->setModelFactory(fac);            // -> setLikelihoodKernel(sse) + setNumThreads
+    if (g_site) { m->make_site(g_s_eval, g_s_evec, g_s_inv, (size_t)d->nptn, tree->vector_size); g_site = false; }
     r->setTree(tree);
     tree->initializeAllPartialLh();
     h->leaf.assign(d->ntaxa + (tree->rooted ? 1 : 0), nullptr);   // rooted: the root leaf has id ntaxa (PhyloTree::setAlignment)
