@@ -138,6 +138,19 @@ int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, c
 #define B200LK_CHILD_TRANSPOSED 4
 int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double *cevec, const double *cinv_evec,
                             const double *rate_matrix, const double *state_freq, const double *mix_weight, int32_t rooted);
+
+/* Site-specific models (model->isSiteSpecificModel(): ModelSet — `-fs` site-frequency files and the PMSF approximation of the
+ * C10-C60 profile mixtures), the SITE_MODEL template branch of tree/phylokernelnew.h (partial :1362-1374, 1653-1683, 1772-1801,
+ * 1937-1968; buffer :2129-2140; derivative :2306-2311, 2469-2487; branch :2708-2713, 2833-2848, 2993-3008; from-buffer
+ * :3271-3276, 3316-3327; instantiations tree/phylokernelfma.cpp:43-100): pattern p has its OWN eigensystem,
+ *   eval [nptn][nstates], evec / inv_evec [nptn][nstates][nstates] row-major — ModelSet::at(p)'s getEigenvalues() /
+ *   getEigenvectors() / getInverseEigenvectors() (what ModelSet::computeTipLikelihood and the kernels index by ptn).
+ * The engine must have nmix = 1 (ncat_mix = ncat: the reference asserts it, :1362).  Afterwards every likelihood entry point runs
+ * the SITE_MODEL arithmetic; the CLV slots hold eigen coordinates of the pattern's own system, as the reference's.  Not available
+ * in this mode (B200LK_ERR_STATE / _INVALID): +ASC, robust phylo, multifurcating ops, grouped launches, the non-reversible kernel,
+ * the device-resident sweep (b200lk_enqueue_newton_branch; b200lk_newton_branch iterates from the host).  On a multi-device engine
+ * every shard takes its pattern slice of the three arrays. */
+int b200lk_set_site_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec);
 /* site_rate->getRate(c) / getProp(c) */
 int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop);
 

@@ -12,6 +12,7 @@
 #include "b200lk_walkgen.cuh"
 #include "b200lk_group.cuh"
 #include "b200lk_nonrev.cuh"
+#include "b200lk_site.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -123,6 +124,9 @@ struct b200lk_engine {
     double *d_nr_model = nullptr, *d_nr_branch = nullptr;
     NrChildJob *d_nr_jobs = nullptr;
     size_t nr_jobs_cap = 0;
+    // site-specific models (b200lk_site.inc): eval | evec | inv_evec of every pattern, warp-interleaved
+    bool site = false;
+    double *d_site = nullptr;
     std::string err;
 };
 
@@ -194,7 +198,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_nr_model); cudaFree(e->d_nr_branch); cudaFree(e->d_nr_jobs);
+    cudaFree(e->d_nr_model); cudaFree(e->d_nr_branch); cudaFree(e->d_nr_jobs); cudaFree(e->d_site);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_boot_state); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -344,6 +348,7 @@ extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
 
 extern "C" int b200lk_set_ascertainment(b200lk_engine *e, int32_t asc_type, int64_t num_unobserved, int64_t nsite) {
     if (!e->shards.empty()) { if (asc_type != 0) MG_UNSUPPORTED(e, "+ASC"); return mg_each(e, [&](int k) { return b200lk_set_ascertainment(e->shards[k], 0, 0, nsite); }); }
+    if (asc_type != 0 && e->site) return fail(e, B200LK_ERR_STATE, "+ASC is not available with site-specific models");
     if (asc_type < 0 || asc_type > 2) return fail(e, B200LK_ERR_INVALID, "asc_type: 0 = none, 1 = Lewis (ASC_VARIANT / ASC_INFORMATIVE), 2 = Holder (ASC_VARIANT_MISSING)");
     if (num_unobserved < 0 || num_unobserved >= e->P) return fail(e, B200LK_ERR_INVALID, "num_unobserved out of range");
     if (asc_type && (e->robust_keep < 1.0 || e->robust_median)) return fail(e, B200LK_ERR_INVALID, "+ASC not supported with robust phylo");
@@ -949,11 +954,13 @@ static int enqueue_walk20(b200lk_engine *e, const b200lk_op *ops, int32_t nops) 
 }
 
 #include "b200lk_nonrev.inc"
+#include "b200lk_site.inc"
 
 // Enqueue (no sync) everything computePartialLikelihood needs for the op list.
 static int enqueue_partials(b200lk_engine *e, const b200lk_op *ops, int32_t nops) {
     if (nops <= 0) return 0;
     if (e->nonrev) return nonrev_enqueue_partials(e, ops, nops);
+    if (e->site) return site_enqueue_partials(e, ops, nops);
     // multifurcating ops (reserved = number of children beyond left/right, taken in op order from b200lk_set_extra_children)
     int nextra = 0;
     for (int k = 0; k < nops; k++) {
@@ -1184,6 +1191,16 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
         e->pending_marks = 2;
         return 0;
     }
+    if (e->site) {   // SITE_MODEL: the pattern's own eigenvalues (tree/phylokernelnew.h:2833-2848, 2993-3008)
+        if (e->robust_keep < 1.0 || e->robust_median) return fail(e, B200LK_ERR_STATE, "site-specific models: robust phylo is not available");
+        site_enqueue_root(e, node_slot, dad_kind, dad_id, length, save_log_value);
+        prof_mark(e, 2);
+        CK(cudaGetLastError());
+        e->have_lh_cat = true;
+        e->pending = (e->pending & ~PEND_SAVE_LOG) | PEND_LOGL | (save_log_value ? PEND_SAVE_LOG : 0);
+        e->pending_marks = 2;
+        return 0;
+    }
     const int nblocks = (int)(e->Ppad / kTile);
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
@@ -1279,6 +1296,7 @@ extern "C" int b200lk_branch_logl(b200lk_engine *e, const b200lk_op *ops, int32_
 }
 
 static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_id) {
+    if (e->site) { site_enqueue_theta(e, node_slot, dad_kind, dad_id); return 0; }
     const int nblocks = (int)(e->Ppad / kTile);
     if (e->d.clv_state) {
         node_slot = eigen_slot(e, node_slot);
@@ -1293,6 +1311,7 @@ static int enqueue_theta(b200lk_engine *e, int node_slot, int dad_kind, int dad_
 }
 
 static void enqueue_derv(b200lk_engine *e, double length) {
+    if (e->site) { site_enqueue_derv(e, length); return; }
     const int nblocks = (int)(e->Ppad / kTile);
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * 3 * e->B : 0;
@@ -1353,6 +1372,14 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
     prof_begin(e);
     prof_mark(e, 1);
+    if (e->site) {
+        site_enqueue_from_buffer(e, length);
+        prof_mark(e, 2);
+        CK(cudaGetLastError());
+        e->pending = (e->pending & PEND_DERV) | PEND_LOGL | PEND_SAVE_LOG;
+        e->pending_marks = 2;
+        return 0;
+    }
     const int nblocks = (int)(e->Ppad / kTile);
     const int fuse = e->B <= kFuseValsMaxB;
     const size_t vsm = fuse ? sizeof(double) * e->B : 0;
@@ -1380,7 +1407,7 @@ extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *
     return b200lk_finish(e, logl, nullptr, nullptr);
 }
 
-static bool newton_coop_ok(const b200lk_engine *e) { return e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc; }
+static bool newton_coop_ok(const b200lk_engine *e) { return e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc && !e->site; }
 
 static int launch_newton_coop(b200lk_engine *e, double x1, double xguess, double x2, double xacc, int maxNRStep, double *io,
                               double *len_out, int check_divergence) {

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
     "b200lk_group_create", "b200lk_group_destroy", "b200lk_group_last_error", "b200lk_group_enqueue_branch_logl",
     "b200lk_group_enqueue_branch_derv", "b200lk_group_enqueue_logl_from_buffer", "b200lk_group_finish", "b200lk_group_launch_count",
-    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state", "b200lk_set_model_nonrev",
+    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state", "b200lk_set_model_nonrev", "b200lk_set_site_model",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -164,6 +164,11 @@ class LikelihoodEngine:
         self._check(self.lib.b200lk_set_model(self._h, _dp(ev), _dp(U), _dp(Ui), _dp(w)))
         r, p = f(model.cat_rate), f(model.cat_prop)
         self._check(self.lib.b200lk_set_rates(self._h, _dp(r), _dp(p)))
+        st = getattr(model, "site", None)
+        if st:   # site-specific model (ModelSet / PMSF): one eigensystem per pattern
+            b = [f(st["eval"]), f(st["evec"]), f(st["inv_evec"])]
+            assert b[0].shape == (self.nptn, self.n) and b[1].shape == (self.nptn, self.n, self.n) and b[2].shape == b[1].shape
+            self._check(self.lib.b200lk_set_site_model(self._h, _dp(b[0]), _dp(b[1]), _dp(b[2])))
         nr = getattr(model, "nonrev", None)
         if nr:   # non-reversible kernel (tree/phylokernelnonrev.h): complex eigensystem, rate matrices, state frequencies
             a = [f(nr["ceval"]), f(nr["cevec"]), f(nr["cinv_evec"]), f(nr["rate_matrix"]), f(model.state_freq)]

@@ -22,6 +22,7 @@ int orc_set_pattern_freq(orc_engine *e, const double *f);
 int orc_set_pattern_invar(orc_engine *e, const double *f);
 int orc_set_rates(orc_engine *e, const double *rate, const double *prop);
 int orc_set_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec, const double *mix_weight);
+int orc_set_site_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec);
 int orc_set_model_nonrev(orc_engine *e, const double *ceval, const double *cevec, const double *cinv_evec, const double *rate_matrix,
                          const double *state_freq, const double *mix_weight, int rooted);
 int orc_update_partials(orc_engine *e, const void *ops, int nops);
@@ -78,6 +79,9 @@ int b200lk_set_model(b200lk_engine *e, const double *eval, const double *evec, c
 int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double *cevec, const double *cinv_evec, const double *rate_matrix,
                             const double *state_freq, const double *mix_weight, int32_t rooted) {
     return wrap(e, orc_set_model_nonrev(e->o, ceval, cevec, cinv_evec, rate_matrix, state_freq, mix_weight, rooted));
+}
+int b200lk_set_site_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec) {
+    return wrap(e, orc_set_site_model(e->o, eval, evec, inv_evec));
 }
 int b200lk_set_rates(b200lk_engine *e, const double *r, const double *p) { return wrap(e, orc_set_rates(e->o, r, p)); }
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t t, int64_t n, int64_t s) { return wrap(e, orc_set_ascertainment(e->o, t, n, s)); }
