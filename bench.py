@@ -41,6 +41,10 @@ WORKLOADS = {
     # rate matrix (UNREST-like) + Gamma(4); ntaxa real taxa + the virtual root leaf
     "dna_500x200k_unrest_g4": (500, 200_000, lambda: models.make_nonreversible(4, ncat=4, seed=11, state_unknown=models.DNA_STATE_UNKNOWN),
                                "synthetic DNA 500 taxa x 200k patterns, rooted, non-reversible 12-parameter model + G4"),
+    # not a BASELINE config: site-specific models (ModelSet / PMSF, the SITE_MODEL branch of tree/phylokernelnew.h): one frequency
+    # profile, hence one eigensystem, per pattern + Gamma(4)
+    "aa_100x20k_pmsf_g4": (100, 20_000, lambda: models.make_site_specific_fast(20, 20_000, ncat=4, seed=9),
+                           "synthetic protein 100 taxa x 20k patterns, site-specific frequency profiles (PMSF-like) + G4"),
     "codon_100x20k_rev61_g4": (100, 20_000, lambda: models.make_random_reversible(61, ncat=4, seed=7), "synthetic codon 100 taxa x 20k patterns, 61-state reversible + G4"),
 }
 SAFE_WORKLOADS = {"codon_100x20k_rev61_g4"}
@@ -369,7 +373,7 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
     sample_ptn = int(min(sample_ptn, tips.shape[1]))
     if ref_engine.available():
         threads = host_threads()   # set explicitly: the harness calls omp_set_num_threads(), which overrides OMP_NUM_THREADS
-        r = ref_engine.RefTree(tree, model, np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], safe_numeric=safe, nthreads=threads)
+        r = ref_engine.RefTree(tree, models.site_slice(model, 0, sample_ptn), np.ascontiguousarray(tips[:, :sample_ptn]), freq[:sample_ptn], safe_numeric=safe, nthreads=threads)
         if warmup:
             r.time_eval(0, warmup)
         t = r.time_eval(0, steps)
@@ -379,7 +383,7 @@ def run_cpu_reference(tree, model, tips, freq, ops, a, b, L, sample_ptn, steps, 
                 "logl": t["logl"], "df": t["df"], "ddf": t["ddf"], "kind": "reference",
                 "what": "IQ-TREE 2.4.0 phylokernelnew.h, Vec4d AVX+FMA, OpenMP (compiled from the reference's own TUs)"}
     from oracle.oracle_engine import OracleEngine
-    o = OracleEngine(model, tree.ntaxa, sample_ptn, safe_numeric=safe)
+    o = OracleEngine(models.site_slice(model, 0, sample_ptn), tree.ntaxa, sample_ptn, safe_numeric=safe)
     o.set_tip_states(np.ascontiguousarray(tips[:, :sample_ptn]))
     o.set_pattern_freq(freq[:sample_ptn])
     o.set_pattern_invar(np.zeros(sample_ptn))
@@ -501,6 +505,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         data += "; rooted at an extra (virtual) leaf"
     tips = np.ascontiguousarray(tips_all[:, lo:hi])
     freq = freq_all[lo:hi]
+    model = models.site_slice(model, lo, hi)   # site-specific models: this rank's per-pattern eigensystems
     br = plan.pendant_branch_of(tree, 0)
     ops, a, b, L = plan.plan_branch_nonrev(tree, br) if nonrev else plan.plan_branch(tree, br)
     ops_acc = ops.copy()   # byte / flop accounting: child kinds without the non-reversible flags (the root leaf counts as a tip)
@@ -536,10 +541,16 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     h2d = int(ops.nbytes) + int(sum(t.numel() * 8 for t in pinned_model))
     d2h = 3 * 8
 
+    # what an optimisation step re-sends: the class-level eigensystem and the rates; the per-pattern eigensystems of a site-specific
+    # model are fixed for the whole analysis (the PMSF profiles come from a guide tree) and stay resident like the alignment
+    site = getattr(model, "site", None) is not None
+    import dataclasses
+    model_step = dataclasses.replace(model, site=None) if site else model
+
     def one_eval(upload_model):
         """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
         if upload_model:
-            eng.set_model(model)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
+            eng.set_model(model_step)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
         # both calls are queued on the stream and waited for ONCE (the asynchronous forms of the C ABI); with several ranks the
         # scalars go from the engine's result slot to a device buffer, through ncclAllReduce and back in the same stream order:
         # no host round trip between the kernels and the collective
@@ -604,7 +615,10 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     n_ii, n_ti, n_tt = plan.count_node_cases(ops_acc)
     walk4 = args.schedule != 1 and model.nstates == 4 and model.nmix == 1 and not nonrev
     walk20 = args.schedule != 1 and model.nstates == 20
-    if nonrev:
+    if site:
+        walk4 = walk20 = False
+        kernel_name = f"k_site_partials<{model.nstates}> (thread per pattern, per-pattern eigensystems streamed from HBM / L2)"
+    elif nonrev:
         kernel_name = f"k_nonrev_partials<{model.nstates}> (thread per pattern, state-space CLVs, device-built transition matrices)"
     elif walk20:
         kernel_name = "k_walk_n20v2 (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs, cp.async rings)"
@@ -616,6 +630,8 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     else:
         kernel_name = "k_partials_generic"
     model_bytes = dram_model_bytes(ops_acc, my_nptn, B, S, chained=walk4)
+    if site:   # + every op reads the pattern's (n + 2 n^2) doubles once (re-reads across categories are L1 / L2 hits at best)
+        model_bytes += len(ops) * my_nptn * 8 * (model.nstates + 2 * model.nstates ** 2)
     traffic, traffic_src = load_traffic(workload, overridden or bool(args.variant or args.schedule), my_nptn)
     # roofline.frac is PHYSICAL: bytes at the DRAM pins (the committed ncu capture of this workload, else the DRAM-side model)
     # per launch / launch time / measured copy peak.  The SURVEY 8(d) algorithmic figure (every CLV written once AND read once)
@@ -626,7 +642,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "launch_ms": ker_s * 1e3,
                 "dram_model_bytes_per_launch": model_bytes, "dram_model_GBps": model_bytes / ker_s / 1e9,
                 "algorithmic_bytes_per_launch": my_bytes_partials, "algorithmic_equivalent_GBps": alg_gbps, "partial_lh_GBps": alg_gbps}
-    if model.nstates >= 20:
+    if model.nstates >= 20 and not site:
         # 20-state updates: the FP64-MMA pipe and HBM are both within reach of binding (~5 flop/B at a ridge of ~5.7).
         # `tensor` = DMMA flops the kernel EXECUTES (state-space form: 30 / 15 / 0 DMMAs of 512 flops per 8 patterns x category
         # for inner-inner / tip-inner / tip-tip nodes) over the measured DMMA peak; the reference-form flops (SURVEY 8d:

@@ -211,6 +211,29 @@ def make_site_specific(nstates, nptn, ncat=4, alpha=0.7, seed=0, pinvar=0.0, sta
     return m
 
 
+def site_slice(model: ModelInputs, lo: int, hi: int) -> ModelInputs:
+    """the model of the pattern range [lo, hi) of a site-specific model (a pattern shard, a CPU sample); any other model as it is"""
+    if getattr(model, "site", None) is None:
+        return model
+    import dataclasses
+    st = model.site
+    cut = {k: (v[lo:hi] if k in ("eval", "evec", "inv_evec", "pi") else v) for k, v in st.items() if k != "Q"}
+    cut["Q"] = st["Q"][lo:hi] if "Q" in st else []
+    return dataclasses.replace(model, site={k: (np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v) for k, v in cut.items()})
+
+
+def make_site_specific_fast(nstates, nptn, ncat=4, alpha=0.7, seed=0, nprofiles=256) -> ModelInputs:
+    """make_site_specific for large pattern counts: `nprofiles` distinct frequency profiles, assigned to the patterns at random
+    (the arrays are still one eigensystem per pattern, as ModelSet holds them)"""
+    base = make_site_specific(nstates, nprofiles, ncat=ncat, alpha=alpha, seed=seed,
+                              state_unknown=DNA_STATE_UNKNOWN if nstates == 4 else (PROTEIN_STATE_UNKNOWN if nstates == 20 else None))
+    idx = np.random.default_rng(seed + 1).integers(0, nprofiles, size=nptn)
+    st = base.site
+    base.site = dict(eval=np.ascontiguousarray(st["eval"][idx]), evec=np.ascontiguousarray(st["evec"][idx]),
+                     inv_evec=np.ascontiguousarray(st["inv_evec"][idx]), pi=st["pi"][idx], Q=[])
+    return base
+
+
 def make_nonreversible(nstates=4, ncat=4, nmix=1, alpha=0.7, seed=0, pinvar=0.0, state_unknown=None, rooted=True) -> ModelInputs:
     """Random NON-reversible model (an UNREST-like general Markov rate matrix per class): Q with arbitrary positive off-diagonals,
     normalised to one expected substitution per unit time at its stationary distribution; complex eigensystem from numpy.  The
