@@ -50,6 +50,9 @@ class ModelInputs:
     # site-specific models (ModelSet: `-fs` site-frequency files / PMSF; the SITE_MODEL branch of tree/phylokernelnew.h): None, or a
     # dict with one eigensystem per PATTERN — "eval" [nptn][n], "evec" [nptn][n][n], "inv_evec" [nptn][n][n], "Q" (list, for checkers)
     site: dict = None
+    # mixed branch lengths (heterotachy; PhyloTreeMixlen): None, or [ncat] factors — the test and bench trees give every branch the
+    # per-class lengths  length * factor[c]  (the engines themselves take an arbitrary [nbranches][ncat] table)
+    mixlen_factor: np.ndarray = None
 
     @property
     def ncat(self) -> int:

@@ -29,7 +29,7 @@ cat > "$OUT/inc/iqtree_config.h" <<'EOF'
 EOF
 
 TUS=(
-  tree/phylokernelfma.cpp tree/phylotreesse.cpp tree/phylotree.cpp tree/mtree.cpp tree/node.cpp tree/phylonode.cpp
+  tree/phylokernelfma.cpp tree/phylotreesse.cpp tree/phylotree.cpp tree/mtree.cpp tree/node.cpp tree/phylonode.cpp tree/phylonodemixlen.cpp
   tree/memslot.cpp tree/constrainttree.cpp pda/split.cpp pda/hashsplitset.cpp
   alignment/alignment.cpp alignment/pattern.cpp alignment/alignmentsummary.cpp phylo-yaml/statespace.cpp
   model/modelsubst.cpp model/rateheterogeneity.cpp model/modelfactory.cpp

@@ -75,9 +75,18 @@ typedef struct {
     /* site-specific models (lk_oracle_site.h): one eigensystem per pattern, [p][n] / [p][n][n] */
     int site;
     double *s_eval, *s_evec, *s_inv;
+    /* mixed branch lengths / heterotachy (lk_oracle_mixlen.h): nmixlen = ncat lengths per branch, [rows][ncat]; a `length` argument
+     * is then the ROW of the branch in this table */
+    int mixlen, mixlen_rows;
+    double *mixlen_tab;
     /* end points of the branch the theta buffer was built for are irrelevant after the build */
     char err[256];
 } orc_engine;
+
+/* child->getLength(cat_id[c]) / dad_branch->getLength(mycat) (phylokernelnew.h:1017, 1069, 2325, 2348, 2724, 2738, 3286, 3301) */
+static inline double len_of(const orc_engine *e, double length, int r) {
+    return e->mixlen ? e->mixlen_tab[(size_t)(int)length * e->cfg.ncat + r] : length;
+}
 
 static size_t S_of(const orc_engine *e) { return e->cfg.safe_numeric ? (size_t)e->C : 1; }
 
@@ -327,7 +336,7 @@ void orc_destroy(orc_engine *e) {
     free(e->scale); free(e->theta); free(e->buffer_scale_all); free(e->pattern_lh); free(e->pattern_scaling);
     free(e->pattern_lh_cat); free(e->extra);
     free(e->ceval); free(e->cevec); free(e->cinv); free(e->qmat); free(e->sfreq);
-    free(e->s_eval); free(e->s_evec); free(e->s_inv);
+    free(e->s_eval); free(e->s_evec); free(e->s_inv); free(e->mixlen_tab);
     free(e);
 }
 
@@ -401,7 +410,7 @@ static void partial_info_child(const orc_engine *e, const orc_child *ch, double 
     double *expchild = (double *)malloc(sizeof(double) * n);
     for (int c = 0; c < C; c++) {
         int m = c / e->denom, r = c % ncat;
-        double len_child = e->cat_rate[r] * ch->length; /* :1017 */
+        double len_child = e->cat_rate[r] * len_of(e, ch->length, r); /* :1017 */
         const double *eval_ptr = e->eval + (size_t)m * n;
         const double *evec_ptr = e->evec + (size_t)m * n * n;
         for (int i = 0; i < n; i++) expchild[i] = exp(eval_ptr[i] * len_child); /* :1022 / :1073 */
@@ -707,12 +716,12 @@ static void compute_vals(const orc_engine *e, double len_branch, double *val0, d
             double myrate = e->cat_rate[r];
             for (int i = 0; i < n; i++) {
                 double cof = eval_ptr[i] * myrate;
-                double val = exp(cof * len_branch) * prop;
+                double val = exp(cof * len_of(e, len_branch, r)) * prop;
                 double v1 = cof * val;
                 val0[c * n + i] = val; val1[c * n + i] = v1; val2[c * n + i] = cof * v1;
             }
         } else {
-            double len = e->cat_rate[r] * len_branch;
+            double len = e->cat_rate[r] * len_of(e, len_branch, r);
             for (int i = 0; i < n; i++) val0[c * n + i] = exp(eval_ptr[i] * len) * prop;
         }
     }
@@ -994,6 +1003,7 @@ int orc_branch_derv(orc_engine *e, const orc_op *ops, int nops, int node_slot, i
         if (orc_update_partials(e, ops, nops) < 0) return -1;
         return site_branch_derv(e, node_slot, dad_kind, dad_id, length, df_out, ddf_out);
     }
+    if (e->mixlen) { snprintf(e->err, sizeof e->err, "mixlen: computeLikelihoodDerv returns a gradient and a Hessian (orc_branch_derv_mixlen)"); return -1; }
     orc_update_partials(e, ops, nops);
     if (!e->theta_computed) build_theta(e, node_slot, dad_kind, dad_id);
     int B = e->B;
@@ -1170,6 +1180,7 @@ int orc_get_tip_partial_lh(orc_engine *e, double *out) {
 }
 #include "lk_oracle_nonrev.h"
 #include "lk_oracle_site.h"
+#include "lk_oracle_mixlen.h"
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

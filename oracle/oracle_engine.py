@@ -159,6 +159,36 @@ class OracleEngine:
         self.last_status = rc
         return df.value, ddf.value
 
+    # ---- mixed branch lengths (lk_oracle_mixlen.h) --------------------------------------------------
+    def set_mixlen(self, table):
+        """table [nbranches][ncat] of per-class branch lengths (None / empty: off); afterwards every `length` is a ROW of it"""
+        t = np.ascontiguousarray(table if table is not None else np.zeros((0, 1)), dtype=np.float64)
+        if lib().orc_set_mixlen(self._h, _dp(t), C.c_int(t.shape[0])) < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        self._nmixlen = t.shape[1] if t.shape[0] else 0
+
+    def branch_derv_mixlen(self, ops, end_a, end_b, row):
+        """computeLikelihoodDerv of a mixlen tree -> (gradient [K], hessian [K][K], logL)"""
+        ops = np.ascontiguousarray(ops)
+        K = self._nmixlen
+        df, ddf = np.zeros(K + 1), np.zeros((K, K))
+        rc = lib().orc_branch_derv_mixlen(self._h, _dp(ops), C.c_int(len(ops)), C.c_int(end_a[1]), C.c_int(end_b[0]),
+                                          C.c_int(end_b[1]), C.c_double(row), _dp(df), _dp(ddf))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        return df[:K].copy(), ddf, float(df[K])
+
+    def branch_derv_mixlen_cur(self, ops, end_a, end_b, row, cur):
+        """computeLikelihoodDervMixlen for class `cur` -> (df, ddf)"""
+        ops = np.ascontiguousarray(ops)
+        df, ddf = C.c_double(), C.c_double()
+        rc = lib().orc_branch_derv_mixlen_cur(self._h, _dp(ops), C.c_int(len(ops)), C.c_int(end_a[1]), C.c_int(end_b[0]),
+                                              C.c_int(end_b[1]), C.c_double(row), C.c_int(cur), C.byref(df), C.byref(ddf))
+        if rc < 0:
+            raise RuntimeError(lib().orc_last_error(self._h).decode())
+        self.last_status = rc
+        return df.value, ddf.value
+
     def logl_from_buffer(self, length):
         out = C.c_double()
         rc = lib().orc_logl_from_buffer(self._h, C.c_double(length), C.byref(out))

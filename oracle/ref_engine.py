@@ -158,6 +158,12 @@ class RefTree:
         if st:   # site-specific model: one eigensystem per pattern
             b = [f64(st["eval"]), f64(st["evec"]), f64(st["inv_evec"])]
             self._L().iqref_set_site_next(_p(b[0]), _p(b[1]), _p(b[2]), C.c_int64(self.nptn), C.c_int(self.n))
+        ml = getattr(model, "mixlen_factor", None)
+        if ml is not None:   # mixed branch lengths: a MixlenTree whose branches get lengths[c] = length * factor[c]
+            fct = f64(ml)
+            assert fct.size == model.ncat
+            self._nmixlen = int(fct.size)
+            self._L().iqref_set_mixlen_next(_p(fct), C.c_int(fct.size))
         nr = getattr(model, "nonrev", None)
         if nr:
             a = [f64(nr["ceval"]), f64(nr["cevec"]), f64(nr["cinv_evec"]), f64(nr["rate_matrix"])]
@@ -228,6 +234,18 @@ class RefTree:
     def branch_derv(self, leaf=0):
         df, ddf = C.c_double(), C.c_double()
         self._L().iqref_branch_derv(self._h, int(leaf), C.byref(df), C.byref(ddf))
+        return df.value, ddf.value
+
+    def branch_derv_mixlen(self, leaf=0):
+        """computeLikelihoodDerv of a mixlen tree -> (gradient [K], hessian [K][K], logL)"""
+        K = self._nmixlen
+        df, ddf = np.zeros(K + 1), np.zeros((K, K))
+        self._L().iqref_branch_derv_mixlen(self._h, int(leaf), _p(df), _p(ddf))
+        return df[:K].copy(), ddf, float(df[K])
+
+    def branch_derv_mixlen_cur(self, leaf, cur):
+        df, ddf = C.c_double(), C.c_double()
+        self._L().iqref_branch_derv_mixlen_cur(self._h, int(leaf), int(cur), C.byref(df), C.byref(ddf))
         return df.value, ddf.value
 
     def logl_from_buffer(self):

@@ -31,6 +31,7 @@
 #include "model/modelsubst.h"
 #include "model/rateheterogeneity.h"
 #include "tree/phylotree.h"
+#include "tree/phylonodemixlen.h"
 #include "utils/starttree.h"
 #include "utils/timeutil.h"
 #include "utils/tools.h"
@@ -231,6 +232,31 @@ void collect_directed(PhyloNode *node, PhyloNode *dad, std::vector<Directed> &ou
     }
 }
 
+// a PhyloTree with mixed branch lengths (heterotachy): what PhyloTreeMixlen (tree/phylotreemixlen.h:89-98, 218; newNode
+// tree/phylotreemixlen.cpp:95-101) answers to the likelihood kernels — isMixlen(), getMixlen(), getCurMixture() — over
+// PhyloNodeMixlen / PhyloNeighborMixlen nodes; none of its optimisers (they need ModelFactoryMixlen, RateHeterotachy, BFGS ...)
+struct MixlenTree : public PhyloTree {
+    int K = 1, cur = 0;
+    explicit MixlenTree(int k) : PhyloTree(), K(k) {}
+    bool isMixlen() override { return true; }
+    int getMixlen() override { return K; }
+    int getCurMixture() override { return cur; }
+    Node *newNode(int node_id = -1, const char *node_name = NULL) override { return new PhyloNodeMixlen(node_id, node_name); }
+    Node *newNode(int node_id, int node_name) override { return new PhyloNodeMixlen(node_id, node_name); }
+    // PhyloTreeMixlen::computeFuncDerv's call (tree/phylotreemixlen.cpp:736)
+    void dervCur(PhyloNeighbor *nb, PhyloNode *dad, double &df, double &ddf) { (this->*computeLikelihoodDervMixlenPointer)(nb, dad, df, ddf); }
+};
+
+void set_mixlen_lengths(Node *node, Node *dad, const std::vector<double> &factor) {
+    FOR_NEIGHBOR_IT(node, dad, it) {
+        DoubleVector v;
+        for (double f : factor) v.push_back((*it)->length * f);
+        (*it)->setLength(v);
+        (*it)->node->findNeighbor(node)->setLength(v);
+        set_mixlen_lengths((*it)->node, node, factor);
+    }
+}
+
 }  // namespace
 
 // the shim's view of the non-reversible arrays (oracle/ref_b200_shim.cpp)
@@ -309,6 +335,11 @@ void iqref_set_site_next(const double *eval, const double *evec, const double *i
     g_s_inv.assign(inv_evec, inv_evec + (size_t)nptn * n * n);
 }
 
+// mixed branch lengths for the NEXT iqref_create: the tree is a MixlenTree with k = ncat classes, every branch gets
+// lengths[c] = length * factor[c] (the callers build the same table from the same tree)
+static std::vector<double> g_mixlen_factor;
+void iqref_set_mixlen_next(const double *factor, int k) { g_mixlen_factor.assign(factor, factor + k); }
+
 void *iqref_create(const iqref_desc *d) {
     init_params(d->nthreads > 0 ? d->nthreads : 1);
     Params &params = Params::getInstance();
@@ -369,10 +400,13 @@ void *iqref_create(const iqref_desc *d) {
     g_asc_type = 0;
     g_unobs.clear();
 
-    PhyloTree *tree = h->tree = iqref_tree_factory ? iqref_tree_factory() : new PhyloTree();
+    const std::vector<double> mixlen_factor = g_mixlen_factor;
+    g_mixlen_factor.clear();
+    PhyloTree *tree = h->tree = !mixlen_factor.empty() ? new MixlenTree((int)mixlen_factor.size()) : iqref_tree_factory ? iqref_tree_factory() : new PhyloTree();
     tree->params = &params;
     tree->aln = aln;                       // readTreeString -> assignLeafNames needs it only for named leaves
     tree->readTreeString(std::string(d->newick));
+    if (!mixlen_factor.empty()) set_mixlen_lengths(tree->root, nullptr, mixlen_factor);
     tree->setAlignment(aln);
     tree->setRootNode(params.root);
     tree->sse = LK_AVX_FMA;
@@ -452,6 +486,32 @@ void iqref_branch_derv(void *hv, int leaf, double *df, double *ddf) {
     h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
     h->tree->theta_computed = false;
     h->tree->computeLikelihoodDerv(nb, L, df, ddf);
+}
+
+// computeLikelihoodDerv of a mixlen tree (tree/phylokernelnew.h:2391-2460, 2556-2568): df [K + 1] (gradient, then the
+// log-likelihood), ddf [K][K]
+void iqref_branch_derv_mixlen(void *hv, int leaf, double *df, double *ddf) {
+    Handle *h = (Handle *)hv;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
+    h->tree->current_it = nb;
+    h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    h->tree->theta_computed = false;
+    h->tree->computeLikelihoodDerv(nb, L, df, ddf);
+}
+
+// computeLikelihoodDervMixlen (:3431-3616) for class `cur`
+void iqref_branch_derv_mixlen_cur(void *hv, int leaf, int cur, double *df, double *ddf) {
+    Handle *h = (Handle *)hv;
+    MixlenTree *t = dynamic_cast<MixlenTree *>(h->tree);
+    if (!t) { *df = *ddf = 0.0 / 0.0; return; }
+    t->cur = cur;
+    PhyloNode *L = h->leaf[leaf];
+    PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
+    t->current_it = nb;
+    t->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    t->theta_computed = false;
+    t->dervCur(nb, L, *df, *ddf);
 }
 
 double iqref_logl_from_buffer(void *hv) { return ((Handle *)hv)->tree->computeLikelihoodFromBuffer(); }

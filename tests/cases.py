@@ -14,8 +14,10 @@ def ptn_invar_for(model, pat):
     return alignment.ptn_invar(pat, freq, model.pinvar, model.nstates, model.state_unknown, model.seq_type)
 
 
-def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, tree_kind="yule", mean_len=0.1):
-    if kind == "dna":
+def make_case(kind="dna", ntaxa=12, nsites=300, seed=1, gaps=0.05, ambig=0.03, tree_kind="yule", mean_len=0.1, model=None):
+    if model is not None:
+        pass   # the caller's model
+    elif kind == "dna":
         model = models.make_gtr_gamma()
     elif kind == "dna_inv":
         model = models.make_gtr_gamma(pinvar=0.2)
