@@ -151,6 +151,30 @@ int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double 
  * the device-resident sweep (b200lk_enqueue_newton_branch; b200lk_newton_branch iterates from the host).  On a multi-device engine
  * every shard takes its pattern slice of the three arrays. */
 int b200lk_set_site_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec);
+
+/* Mixed branch lengths (heterotachy, the GHOST models `+H` / `*H`; PhyloTree::isMixlen(), tree/phylotreemixlen.h:89): every branch
+ * carries nmixlen = ncat lengths (PhyloNeighborMixlen::lengths, tree/phylonodemixlen.h:60-69).
+ *   b200lk_set_mixlen(e, table, nrows): table [nrows][ncat], row k = the lengths of the branch with Neighbor::id k (what
+ *     PhyloTree::saveBranchLengths writes at id * getMixlen(), tree/phylotree.cpp:728-731).  From then on EVERY length this API takes
+ *     — b200lk_child::length in ops, the `length` of the branch calls — is the ROW of the branch in this table (an integer value),
+ *     and rate category c reads table[row][c % ncat] wherever the reference reads child->getLength(cat_id[c]) /
+ *     dad_branch->getLength(mycat) (tree/phylokernelnew.h:1017, 1069, 2325, 2348, 2724, 2738, 3286, 3301).  Partial likelihoods,
+ *     b200lk_branch_logl and b200lk_logl_from_buffer run on the same kernels as before.  Setting the table again (new lengths
+ *     during optimisation) is a small asynchronous copy; CLVs and the theta buffer are the caller's to invalidate, as after any
+ *     length change.  nrows = 0 switches the mode off.
+ *   b200lk_branch_derv_mixlen: computeLikelihoodDerv of a mixlen tree (:2391-2460, 2556-2568): df [ncat + 1] = the gradient over
+ *     the branch's ncat lengths followed by the log-likelihood ("last entry of df now store log-likelihood"), ddf [ncat][ncat] =
+ *     the Hessian.  (b200lk_branch_derv returns B200LK_ERR_STATE in this mode, as do the Newton entry points: the reference
+ *     optimises mixlen branches with BFGS / EM over these two calls, tree/phylotreemixlen.cpp.)
+ *   b200lk_branch_derv_mixlen_cur: computeLikelihoodDervMixlen (:3431-3616) for class cur_mixlen = getCurMixture(): (df, ddf) of
+ *     that class's length alone, from its slice of the theta buffer — the M-step of PhyloTreeMixlen::optimizeOneBranch's EM
+ *     (the caller has put the class's posterior weights into ptn_freq).
+ * Not available with +ASC (the reference asserts, :2449), site-specific or non-reversible models, grouped launches. */
+int b200lk_set_mixlen(b200lk_engine *e, const double *table, int32_t nrows);
+int b200lk_branch_derv_mixlen(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                              int32_t dad_id, double length, double *df, double *ddf);
+int b200lk_branch_derv_mixlen_cur(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind,
+                                  int32_t dad_id, double length, int32_t cur_mixlen, double *df, double *ddf);
 /* site_rate->getRate(c) / getProp(c) */
 int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const double *cat_prop);
 

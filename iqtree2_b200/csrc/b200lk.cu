@@ -13,6 +13,7 @@
 #include "b200lk_group.cuh"
 #include "b200lk_nonrev.cuh"
 #include "b200lk_site.cuh"
+#include "b200lk_mixlen.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -127,6 +128,10 @@ struct b200lk_engine {
     // site-specific models (b200lk_site.inc): eval | evec | inv_evec of every pattern, warp-interleaved
     bool site = false;
     double *d_site = nullptr;
+    // mixed branch lengths (b200lk_mixlen.inc): the [rows][ncat] table, the gradient / Hessian pass's per-block sums
+    double *d_mixlen = nullptr, *d_mixlen_red = nullptr;
+    size_t mixlen_cap = 0;
+    int mixlen_rows = 0;
     std::string err;
 };
 
@@ -198,7 +203,7 @@ extern "C" void b200lk_destroy(b200lk_engine *e) {
     cudaFree(e->d.asc_tmp); cudaFree(e->d_robust); cudaFree(e->d_robust_tmp);
     cudaFree(e->d_post); cudaFree(e->d_em_red); cudaFree(e->d_em_out);
     cudaFree(e->d_jobs); cudaFree(e->d_red); cudaFree(e->d_ticket); cudaFree(e->d_counter); cudaFree(e->d_scratch);
-    cudaFree(e->d_nr_model); cudaFree(e->d_nr_branch); cudaFree(e->d_nr_jobs); cudaFree(e->d_site);
+    cudaFree(e->d_nr_model); cudaFree(e->d_nr_branch); cudaFree(e->d_nr_jobs); cudaFree(e->d_site); cudaFree(e->d_mixlen); cudaFree(e->d_mixlen_red);
     cudaFree(e->d_boot); cudaFree(e->d_rell); cudaFree(e->d_boot_state); cudaFree(e->d_mchild); cudaFree(e->d_lens); cudaFree(e->d_inv_frag20);
     if (e->h_sweep) cudaFreeHost(e->h_sweep);
     if (e->h_stage) cudaFreeHost(e->h_stage);
@@ -562,6 +567,7 @@ static void launch_partials(b200lk_engine *e, int op_begin, int op_end, int walk
 
 // a child length is a number >= 0, or -(k)-1 = slot k of the device length table (b200lk_enqueue_newton_branch)
 static bool length_ok(const b200lk_engine *e, double len) {
+    if (e->mixlen_rows) return len >= 0.0 && len < (double)e->mixlen_rows && len == std::floor(len);   // a row of the mixlen table
     if (len >= 0.0) return true;
     const double k = -len - 1.0;
     return k >= 0.0 && k < (double)e->nlen_slots && k == std::floor(k);
@@ -1176,6 +1182,7 @@ extern "C" int b200lk_enqueue_branch_logl(b200lk_engine *e, const b200lk_op *ops
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
+    if (e->mixlen_rows && !length_ok(e, length)) return fail(e, B200LK_ERR_INVALID, "length must be a row of the mixlen table");
     prof_begin(e);
     rc = enqueue_partials(e, ops, nops);
     if (rc) return rc;
@@ -1338,6 +1345,7 @@ extern "C" int b200lk_enqueue_branch_derv(b200lk_engine *e, const b200lk_op *ops
     cudaSetDevice(e->cfg.device);
     int rc = check_branch(e, node_slot, dad_kind, dad_id);
     if (rc) return rc;
+    if (e->mixlen_rows) return fail(e, B200LK_ERR_STATE, "branch_derv: with mixed branch lengths computeLikelihoodDerv returns a gradient and a Hessian (b200lk_branch_derv_mixlen)");
     const bool chained = (e->pending & PEND_LOGL) != 0;   // queued behind a logL call: keep its profiling marks
     if (!chained) prof_begin(e);
     if (nops > 0) e->theta_computed = false;
@@ -1370,6 +1378,7 @@ extern "C" int b200lk_enqueue_logl_from_buffer(b200lk_engine *e, double length) 
     cudaSetDevice(e->cfg.device);
     if (e->nonrev) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: the non-reversible kernel has no theta buffer (the reference leaves computeLikelihoodFromBufferPointer NULL)");
     if (!e->theta_computed) return fail(e, B200LK_ERR_STATE, "logl_from_buffer: theta buffer not computed");
+    if (e->mixlen_rows && !length_ok(e, length)) return fail(e, B200LK_ERR_INVALID, "length must be a row of the mixlen table");
     prof_begin(e);
     prof_mark(e, 1);
     if (e->site) {
@@ -1407,7 +1416,7 @@ extern "C" int b200lk_logl_from_buffer(b200lk_engine *e, double length, double *
     return b200lk_finish(e, logl, nullptr, nullptr);
 }
 
-static bool newton_coop_ok(const b200lk_engine *e) { return e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc && !e->site; }
+static bool newton_coop_ok(const b200lk_engine *e) { return e->B <= kFuseValsMaxB && e->kernel_variant != 9 && !e->d.asc && !e->site && !e->mixlen_rows; }
 
 static int launch_newton_coop(b200lk_engine *e, double x1, double xguess, double x2, double xacc, int maxNRStep, double *io,
                               double *len_out, int check_divergence) {
@@ -1817,4 +1826,5 @@ extern "C" int b200lk_rell(b200lk_engine *e, float *rell) {
     return 0;
 }
 
+#include "b200lk_mixlen.inc"
 #include "b200lk_group.inc"

@@ -70,9 +70,15 @@ struct Dev {
     const MultiChild *mchild;   // children of the multifurcating ops of the current call
     const double *dev_len;      // device-resident branch lengths (asynchronous branch sweep): a child length < 0 in an op means
                                 // "slot -(length) - 1 of this table", written by an earlier k_newton_coop of the same sweep
+    const double *mixlen_tab;   // mixed branch lengths (PhyloTree::isMixlen(), b200lk_set_mixlen): [rows][ncat]; a length is then the
+    int mixlen;                 // ROW of the branch, and rate category r reads mixlen_tab[row * ncat + r] (child->getLength(cat_id[c]))
 };
 
 __device__ __forceinline__ double resolve_len(const Dev &D, double len) { return len >= 0.0 ? len : D.dev_len[(int)(-len) - 1]; }
+// child->getLength(cat_id[c]) / dad_branch->getLength(mycat) (tree/phylokernelnew.h:1017, 1069, 2325, 2348, 2724, 2738, 3286, 3301)
+__device__ __forceinline__ double resolve_len_cat(const Dev &D, double len, int r) {
+    return D.mixlen ? D.mixlen_tab[(long long)(int)len * D.ncat + r] : resolve_len(D, len);
+}
 
 __device__ __forceinline__ long long pbase(long long p, int width) {
     return (p >> 5) * (long long)width * kWarp + (p & 31);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(256) k_partial_info(Dev D, const ChildJob *job
     for (int k = threadIdx.x; k < B; k += blockDim.x) {
         int c = k / n, i = k - c * n;
         int m = c / D.denom, r = c % D.ncat;
-        double len_child = D.cat_rate[r] * resolve_len(D, job.length);           // :1017
+        double len_child = D.cat_rate[r] * resolve_len_cat(D, job.length, r);           // :1017
         s_exp[k] = exp(D.eval[m * n + i] * len_child);           // :1022
     }
     __syncthreads();
@@ -212,13 +218,13 @@ __global__ void k_vals(Dev D, double length, int with_derv) {
         double prop = D.cat_prop[r] * D.mix_weight[m];
         if (with_derv) {
             double cof = D.eval[m * n + i] * D.cat_rate[r];
-            double val = exp(cof * length) * prop;
+            double val = exp(cof * resolve_len_cat(D, length, r)) * prop;
             double v1 = cof * val;
             D.val[k] = val;
             D.val[D.B + k] = v1;
             D.val[2 * D.B + k] = cof * v1;
         } else {
-            double len = D.cat_rate[r] * length;
+            double len = D.cat_rate[r] * resolve_len_cat(D, length, r);
             D.val[k] = exp(D.eval[m * n + i] * len) * prop;
         }
     }
@@ -234,13 +240,13 @@ __device__ __forceinline__ const double *stage_vals(const Dev &D, double length,
         double prop = D.cat_prop[r] * D.mix_weight[m];
         if (with_derv) {
             double cof = D.eval[m * n + i] * D.cat_rate[r];
-            double val = exp(cof * length) * prop;
+            double val = exp(cof * resolve_len_cat(D, length, r)) * prop;
             double v1 = cof * val;
             s_val[k] = val;
             s_val[D.B + k] = v1;
             s_val[2 * D.B + k] = cof * v1;
         } else {
-            double len = D.cat_rate[r] * length;
+            double len = D.cat_rate[r] * resolve_len_cat(D, length, r);
             s_val[k] = exp(D.eval[m * n + i] * len) * prop;
         }
     }
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
     const int t = threadIdx.x;
     if (t < 32) {
         const int ch = t >> 4, k = t & 15, c = k >> 2, i = k & 3;
-        const double len_child = D.cat_rate[c] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c] * resolve_len_cat(D, ch ? job.lenB : job.lenA, c);   // :1017
         const double v = exp(D.eval[i] * len_child);                           // :1022
         s_exp[ch][k] = v;
         st[4 + ch * 16 + k] = v;

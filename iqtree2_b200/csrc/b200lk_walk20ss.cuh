@@ -48,7 +48,7 @@ __device__ __forceinline__ void walk_info20ss_body(const Dev &D, const WalkJob20
     for (int k = threadIdx.x; k < 2 * B; k += blockDim.x) {
         const int ch = k / B, kk = k - ch * B, r = kk / 20, i = kk - r * 20;
         const int c = m * cpb + r;
-        const double len_child = D.cat_rate[c % D.ncat] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c % D.ncat] * resolve_len_cat(D, ch ? job.lenB : job.lenA, c % D.ncat);   // :1017
         s_exp20[k] = exp(D.eval[m * 20 + i] * len_child);                                              // :1022
     }
     if (threadIdx.x == 0) {

@@ -23,7 +23,7 @@ __device__ __forceinline__ void walk_info4_body(const Dev &D, const WalkJob4 &jo
     const int C = D.C;
     for (int t = threadIdx.x; t < 8 * C; t += blockDim.x) {
         const int ch = t / (4 * C), k = t - ch * 4 * C, c = k >> 2, i = k & 3;
-        const double len_child = D.cat_rate[c % D.ncat] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c % D.ncat] * resolve_len_cat(D, ch ? job.lenB : job.lenA, c % D.ncat);   // :1017
         const double v = exp(D.eval[i] * len_child);                                                    // :1022
         s_exp4[t] = v;
         st[4 + t] = v;

@@ -50,7 +50,7 @@ __device__ __forceinline__ void walk_info_gen_body(const Dev &D, const WalkJob20
     const int n = D.n, n8 = D.n8, m = c / D.denom;
     for (int k = threadIdx.x; k < 2 * n; k += blockDim.x) {
         const int ch = k / n, i = k - ch * n;
-        const double len_child = D.cat_rate[c % D.ncat] * resolve_len(D, ch ? job.lenB : job.lenA);   // :1017
+        const double len_child = D.cat_rate[c % D.ncat] * resolve_len_cat(D, ch ? job.lenB : job.lenA, c % D.ncat);   // :1017
         s_exp[k] = exp(D.eval[m * n + i] * len_child);                                                 // :1022
     }
     if (threadIdx.x == 0) {

@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200lk_enqueue_newton_branch", "b200lk_sweep_finish", "b200lk_compress_patterns",
     "b200lk_group_create", "b200lk_group_destroy", "b200lk_group_last_error", "b200lk_group_enqueue_branch_logl",
     "b200lk_group_enqueue_branch_derv", "b200lk_group_enqueue_logl_from_buffer", "b200lk_group_finish", "b200lk_group_launch_count",
-    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state", "b200lk_set_model_nonrev", "b200lk_set_site_model",
+    "b200lk_enqueue_results_dev", "b200lk_boot_reset", "b200lk_rell_update", "b200lk_get_boot_state", "b200lk_set_model_nonrev", "b200lk_set_site_model", "b200lk_set_mixlen", "b200lk_branch_derv_mixlen", "b200lk_branch_derv_mixlen_cur",
 ]
 
 SCHEDULE_AUTO, SCHEDULE_LEVELLED, SCHEDULE_WALKER = 0, 1, 2
@@ -238,6 +238,30 @@ class LikelihoodEngine:
         self._check(self.lib.b200lk_branch_derv(self._h, _dp(ops), C.c_int32(len(ops)), C.c_int32(end_a[1]),
                                                 C.c_int32(end_b[0]), C.c_int32(end_b[1]), C.c_double(length),
                                                 C.byref(df), C.byref(ddf)))
+        return df.value, ddf.value
+
+    # ---- mixed branch lengths (heterotachy) ---------------------------------------------------------
+    def set_mixlen(self, table):
+        """table [nbranches][ncat] of per-class branch lengths (None / empty: off); afterwards every `length` is a ROW of it"""
+        t = np.ascontiguousarray(table if table is not None else np.zeros((0, 1)), dtype=np.float64)
+        self._check(self.lib.b200lk_set_mixlen(self._h, _dp(t), C.c_int32(t.shape[0])))
+        self._nmixlen = t.shape[1] if t.shape[0] else 0
+
+    def branch_derv_mixlen(self, ops, end_a, end_b, row):
+        """computeLikelihoodDerv of a mixlen tree -> (gradient [K], hessian [K][K], logL)"""
+        ops = self._ops(ops)
+        K = self._nmixlen
+        df, ddf = np.zeros(K + 1), np.zeros((K, K))
+        self._check(self.lib.b200lk_branch_derv_mixlen(self._h, _dp(ops), C.c_int32(len(ops)), C.c_int32(end_a[1]), C.c_int32(end_b[0]),
+                                                       C.c_int32(end_b[1]), C.c_double(row), _dp(df), _dp(ddf)))
+        return df[:K].copy(), ddf, float(df[K])
+
+    def branch_derv_mixlen_cur(self, ops, end_a, end_b, row, cur):
+        """computeLikelihoodDervMixlen for class `cur` -> (df, ddf)"""
+        ops = self._ops(ops)
+        df, ddf = C.c_double(), C.c_double()
+        self._check(self.lib.b200lk_branch_derv_mixlen_cur(self._h, _dp(ops), C.c_int32(len(ops)), C.c_int32(end_a[1]), C.c_int32(end_b[0]),
+                                                           C.c_int32(end_b[1]), C.c_double(row), C.c_int32(cur), C.byref(df), C.byref(ddf)))
         return df.value, ddf.value
 
     def logl_from_buffer(self, length):

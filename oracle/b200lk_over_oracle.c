@@ -22,6 +22,9 @@ int orc_set_pattern_freq(orc_engine *e, const double *f);
 int orc_set_pattern_invar(orc_engine *e, const double *f);
 int orc_set_rates(orc_engine *e, const double *rate, const double *prop);
 int orc_set_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec, const double *mix_weight);
+int orc_set_mixlen(orc_engine *e, const double *table, int rows);
+int orc_branch_derv_mixlen(orc_engine *e, const void *ops, int nops, int node_slot, int dad_kind, int dad_id, double length, double *df, double *ddf);
+int orc_branch_derv_mixlen_cur(orc_engine *e, const void *ops, int nops, int node_slot, int dad_kind, int dad_id, double length, int cur, double *df, double *ddf);
 int orc_set_site_model(orc_engine *e, const double *eval, const double *evec, const double *inv_evec);
 int orc_set_model_nonrev(orc_engine *e, const double *ceval, const double *cevec, const double *cinv_evec, const double *rate_matrix,
                          const double *state_freq, const double *mix_weight, int rooted);
@@ -82,6 +85,17 @@ int b200lk_set_model_nonrev(b200lk_engine *e, const double *ceval, const double 
 }
 int b200lk_set_site_model(b200lk_engine *e, const double *eval, const double *evec, const double *inv_evec) {
     return wrap(e, orc_set_site_model(e->o, eval, evec, inv_evec));
+}
+int b200lk_set_mixlen(b200lk_engine *e, const double *table, int32_t nrows) { return wrap(e, orc_set_mixlen(e->o, table, nrows)); }
+int b200lk_branch_derv_mixlen(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind, int32_t dad_id,
+                              double length, double *df, double *ddf) {
+    if (refused(ops, nops)) return B200LK_ERR_INVALID;
+    return wrap(e, orc_branch_derv_mixlen(e->o, ops, nops, node_slot, dad_kind, dad_id, length, df, ddf));
+}
+int b200lk_branch_derv_mixlen_cur(b200lk_engine *e, const b200lk_op *ops, int32_t nops, int32_t node_slot, int32_t dad_kind, int32_t dad_id,
+                                  double length, int32_t cur, double *df, double *ddf) {
+    if (refused(ops, nops)) return B200LK_ERR_INVALID;
+    return wrap(e, orc_branch_derv_mixlen_cur(e->o, ops, nops, node_slot, dad_kind, dad_id, length, cur, df, ddf));
 }
 int b200lk_set_rates(b200lk_engine *e, const double *r, const double *p) { return wrap(e, orc_set_rates(e->o, r, p)); }
 int b200lk_set_ascertainment(b200lk_engine *e, int32_t t, int64_t n, int64_t s) { return wrap(e, orc_set_ascertainment(e->o, t, n, s)); }
