@@ -19,11 +19,14 @@
 #include "model/modelsubst.h"
 #include "model/rateheterogeneity.h"
 #include "tree/phylotree.h"
+#include "tree/phylonodemixlen.h"
 #include "utils/tools.h"
 
 #include "b200lk.h"
 
 extern PhyloTree *(*iqref_tree_factory)();   // ref_harness.cpp: how iqref_create makes its tree
+extern int iqref_next_mixlen_classes;         // ref_harness.cpp: > 0 = the tree being created has mixed branch lengths
+extern void (*iqref_derv_mixlen_cur_hook)(PhyloTree *, PhyloNeighbor *, PhyloNode *, int, double *, double *);
 // ref_harness.cpp: the complex eigensystem and rate matrices of the harness's non-reversible model (in a full IQ-TREE build these
 // are ModelMarkov's members ceval / cevec / cinv_evec / rate_matrix, model/modelmarkov.h); false for a reversible model
 extern bool iqref_nonrev_arrays(ModelSubst *model, const double **ceval, const double **cevec, const double **cinv, const double **qmat);
@@ -37,6 +40,18 @@ public:
     std::vector<b200lk_child> b200_extra;
     long long kernel_calls = 0;
     bool fused_newton = false;   // optimizeOneBranch through b200lk_newton_branch (the optional hook of INTEGRATION.md)
+    // mixed branch lengths: in a full build this class derives from PhyloTreeMixlen; here it answers the three questions the kernels
+    // ask (tree/phylotreemixlen.h:89-98, 218) and makes PhyloNodeMixlen nodes (tree/phylotreemixlen.cpp:95-101)
+    int mixlen_classes = 0, cur_mixture = 0;
+    bool isMixlen() override { return mixlen_classes > 0; }
+    int getMixlen() override { return mixlen_classes > 0 ? mixlen_classes : 1; }
+    int getCurMixture() override { return cur_mixture; }
+    Node *newNode(int node_id = -1, const char *node_name = NULL) override {
+        return mixlen_classes ? (Node *)new PhyloNodeMixlen(node_id, node_name) : PhyloTree::newNode(node_id, node_name);
+    }
+    Node *newNode(int node_id, int node_name) override {
+        return mixlen_classes ? (Node *)new PhyloNodeMixlen(node_id, node_name) : PhyloTree::newNode(node_id, node_name);
+    }
 
     ~PhyloTreeB200() override { if (b200) b200lk_destroy(b200); }
 
@@ -58,7 +73,7 @@ public:
         b200lk_child c;
         c.kind = nei->node->isLeaf() ? 0 : 1;
         c.id = nei->node->isLeaf() ? nei->node->id : slotOf(nei);
-        c.length = nei->length;
+        c.length = isMixlen() ? (double)nei->id : nei->length;   // mixlen: the row of the branch in the table of uploadMixlen()
         if (!model->useRevKernel()) {   // computePartialInfo's non-reversible branch (tree/phylokernelnew.h:932-1008)
             if (isRootLeaf(nei->node)) { c.kind = B200LK_CHILD_ROOT; c.id = 0; }
             if (nei->direction == TOWARD_ROOT) c.kind |= B200LK_CHILD_TRANSPOSED;
@@ -84,6 +99,17 @@ public:
             for (int m = 0; m < nmix; m++) model->getStateFrequency(&freq[(size_t)m * n], m);
             check(b200lk_set_model_nonrev(b200, ceval, cevec, cinv, qmat, freq.data(), w.data(), rooted ? 1 : 0), "set_model_nonrev");
         }
+        if (model->isSiteSpecificModel()) {   // ModelSet: one eigensystem per pattern, V-interleaved where the kernels read them
+            const size_t nobs = aln->size(), V = vector_size, ns = (size_t)n, nn = ns * ns;   // (tree/phylotreesse.cpp:271-281)
+            const double *se = model->getEigenvalues(), *su = model->getEigenvectors(), *si = model->getInverseEigenvectors();
+            std::vector<double> ev(nobs * ns), U(nobs * nn), Ui(nobs * nn);
+            for (size_t p = 0; p < nobs; p++) {
+                const size_t base = p / V, v = p % V;
+                for (size_t i = 0; i < ns; i++) ev[p * ns + i] = se[base * ns * V + i * V + v];
+                for (size_t k = 0; k < nn; k++) { U[p * nn + k] = su[base * nn * V + k * V + v]; Ui[p * nn + k] = si[base * nn * V + k * V + v]; }
+            }
+            check(b200lk_set_site_model(b200, ev.data(), U.data(), Ui.data()), "set_site_model");
+        }
         // ptn_invar: observed patterns, then the unobserved constant patterns of +ASC, which the reference keeps behind the
         // padded observed block (tree/phylotreesse.cpp:585-611)
         const size_t nobs = aln->size(), U = model_factory->unobserved_ptns.size(), max_orig = get_safe_upper_limit(nobs);
@@ -92,6 +118,22 @@ public:
         for (size_t u = 0; u < U; u++) inv[nobs + u] = ptn_invar[max_orig + u];
         check(b200lk_set_pattern_invar(b200, inv.data()), "set_pattern_invar");
         (void)n;
+    }
+
+    // mixed branch lengths: row Neighbor::id of the table = that branch's lengths (what saveBranchLengths writes, tree/phylotree.cpp:728-731)
+    void collectMixlen(Node *node, Node *dad, std::vector<double> &tab) {
+        FOR_NEIGHBOR_IT(node, dad, it) {
+            const int id = (*it)->id;
+            ASSERT(id >= 0 && id < (int)branchNum);
+            for (int c = 0; c < mixlen_classes; c++) tab[(size_t)id * mixlen_classes + c] = (*it)->getLength(c);
+            collectMixlen((*it)->node, node, tab);
+        }
+    }
+    void uploadMixlen() {
+        if (!isMixlen()) return;
+        std::vector<double> tab((size_t)branchNum * mixlen_classes, 0.0);
+        collectMixlen(root, nullptr, tab);
+        check(b200lk_set_mixlen(b200, tab.data(), (int)branchNum), "set_mixlen");
     }
 
     // after initializeAllPartialLh: create the engine, hand over the inputs, take over the kernel pointers
@@ -132,7 +174,7 @@ public:
         computeLikelihoodFromBufferPointer = static_cast<ComputeLikelihoodFromBufferType>(&PhyloTreeB200::computeLikelihoodFromBufferB200);
         if (!model->useRevKernel()) computeLikelihoodFromBufferPointer = NULL;   // as setLikelihoodKernel leaves it for the non-reversible kernel
         computePartialLikelihoodPointer = static_cast<ComputePartialLikelihoodType>(&PhyloTreeB200::computePartialLikelihoodB200);
-        computeLikelihoodDervMixlenPointer = NULL;
+        computeLikelihoodDervMixlenPointer = isMixlen() ? static_cast<ComputeLikelihoodDervMixlenType>(&PhyloTreeB200::computeLikelihoodDervMixlenB200) : NULL;
     }
 
     // traversal_info (filled by the reference's own computeTraversalInfo, tree/phylotree.cpp:5918-6028) -> b200lk_op[]
@@ -171,6 +213,7 @@ public:
             computeTipPartialLikelihood();
             uploadModel();
         }
+        uploadMixlen();   // (a production binding re-sends the table only after a length changed)
         traversal_info.clear();
         double *buffer = buffer_partial_lh;   // echildren / partial_lh_leaves are carved from it but never touched here
         computeTraversalInfo(dad_branch, dad, buffer);
@@ -187,7 +230,7 @@ public:
 
     double computeLikelihoodBranchB200(PhyloNeighbor *dad_branch, PhyloNode *dad, bool save_log_value) {
         PhyloNeighbor *node_branch;
-        const double length = dad_branch->length;
+        const double length = isMixlen() ? (double)dad_branch->id : dad_branch->length;
         planBranch(dad_branch, dad, node_branch);
         double logl = 0.0;
         int rc = b200lk_branch_logl(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
@@ -210,19 +253,38 @@ public:
 
     void computeLikelihoodDervB200(PhyloNeighbor *dad_branch, PhyloNode *dad, double *df, double *ddf) {
         PhyloNeighbor *node_branch;
-        const double length = dad_branch->length;
+        const double length = isMixlen() ? (double)dad_branch->id : dad_branch->length;
         planBranch(dad_branch, dad, node_branch);
         if (!b200_ops.empty()) theta_computed = false;
         if (!theta_computed) check(b200lk_theta_reset(b200), "theta_reset");   // :2361-2389: the buffer is rebuilt
+        if (isMixlen()) {   // df [K + 1] = gradient, logL; ddf [K][K] = Hessian (:2391-2460, 2556-2568)
+            check(b200lk_branch_derv_mixlen(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
+                                            dadId(dad, node_branch), length, df, ddf), "branch_derv_mixlen");
+            theta_computed = true;
+            return;
+        }
         int rc = b200lk_branch_derv(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
                                     dadId(dad, node_branch), length, df, ddf);
         check(rc, "branch_derv");
         theta_computed = true;
     }
 
+    // computeLikelihoodDervMixlen (:3431-3616): the current class's length alone
+    void computeLikelihoodDervMixlenB200(PhyloNeighbor *dad_branch, PhyloNode *dad, double &df, double &ddf) {
+        PhyloNeighbor *node_branch;
+        const double length = (double)dad_branch->id;
+        planBranch(dad_branch, dad, node_branch);
+        if (!b200_ops.empty()) theta_computed = false;
+        if (!theta_computed) check(b200lk_theta_reset(b200), "theta_reset");
+        check(b200lk_branch_derv_mixlen_cur(b200, b200_ops.data(), (int)b200_ops.size(), slotOf(dad_branch), dadKind(dad),
+                                            dadId(dad, node_branch), length, getCurMixture(), &df, &ddf), "branch_derv_mixlen_cur");
+        theta_computed = true;
+    }
+
     double computeLikelihoodFromBufferB200() {
         double logl = 0.0;
-        check(b200lk_logl_from_buffer(b200, current_it->length, &logl), "logl_from_buffer");
+        if (isMixlen()) uploadMixlen();
+        check(b200lk_logl_from_buffer(b200, isMixlen() ? (double)current_it->id : current_it->length, &logl), "logl_from_buffer");
         copyPatternLh();
         return logl;
     }
@@ -278,14 +340,28 @@ public:
     }
 };
 
-PhyloTree *make_b200_tree() { return new PhyloTreeB200(); }
+PhyloTree *make_b200_tree() {
+    PhyloTreeB200 *t = new PhyloTreeB200();
+    t->mixlen_classes = iqref_next_mixlen_classes;
+    return t;
+}
+
+void derv_mixlen_cur(PhyloTree *tree, PhyloNeighbor *nb, PhyloNode *dad, int cur, double *df, double *ddf) {
+    PhyloTreeB200 *t = dynamic_cast<PhyloTreeB200 *>(tree);
+    if (!t || !t->computeLikelihoodDervMixlenPointer) { *df = *ddf = 0.0 / 0.0; return; }
+    t->cur_mixture = cur;
+    (t->*(t->computeLikelihoodDervMixlenPointer))(nb, dad, *df, *ddf);   // PhyloTreeMixlen::computeFuncDerv's call
+}
 
 }  // namespace
 
 extern "C" {
 
 // trees created by iqref_create from now on are PhyloTreeB200 objects (still running the CPU kernel until attached)
-void iqref_b200_enable(int on) { iqref_tree_factory = on ? make_b200_tree : nullptr; }
+void iqref_b200_enable(int on) {
+    iqref_tree_factory = on ? make_b200_tree : nullptr;
+    iqref_derv_mixlen_cur_hook = on ? derv_mixlen_cur : iqref_derv_mixlen_cur_hook;
+}
 
 // switch the tree of this handle to the B200 kernel; returns 0, or -1 if it was not created as a PhyloTreeB200
 int iqref_b200_attach(PhyloTree *tree) {

@@ -284,6 +284,9 @@ const std::string &StartTree::Factory::getNameOfDefaultTreeBuilder() {
 
 // how iqref_create makes its tree: nullptr = `new PhyloTree()`; oracle/ref_b200_shim.cpp installs a factory for its derived class
 PhyloTree *(*iqref_tree_factory)() = nullptr;
+int iqref_next_mixlen_classes = 0;   // > 0 while iqref_create builds a tree with mixed branch lengths (read by the shim's factory)
+
+void (*iqref_derv_mixlen_cur_hook)(PhyloTree *, PhyloNeighbor *, PhyloNode *, int, double *, double *) = nullptr;
 
 int NNI_MAX_NR_STEP = 10;   // utils/pllnni.cpp:42 (PLL glue, not compiled); read by getBestNNIForBran
 
@@ -402,7 +405,9 @@ void *iqref_create(const iqref_desc *d) {
 
     const std::vector<double> mixlen_factor = g_mixlen_factor;
     g_mixlen_factor.clear();
-    PhyloTree *tree = h->tree = !mixlen_factor.empty() ? new MixlenTree((int)mixlen_factor.size()) : iqref_tree_factory ? iqref_tree_factory() : new PhyloTree();
+    iqref_next_mixlen_classes = (int)mixlen_factor.size();
+    PhyloTree *tree = h->tree = iqref_tree_factory ? iqref_tree_factory() : !mixlen_factor.empty() ? new MixlenTree((int)mixlen_factor.size()) : new PhyloTree();
+    iqref_next_mixlen_classes = 0;
     tree->params = &params;
     tree->aln = aln;                       // readTreeString -> assignLeafNames needs it only for named leaves
     tree->readTreeString(std::string(d->newick));
@@ -503,15 +508,14 @@ void iqref_branch_derv_mixlen(void *hv, int leaf, double *df, double *ddf) {
 // computeLikelihoodDervMixlen (:3431-3616) for class `cur`
 void iqref_branch_derv_mixlen_cur(void *hv, int leaf, int cur, double *df, double *ddf) {
     Handle *h = (Handle *)hv;
-    MixlenTree *t = dynamic_cast<MixlenTree *>(h->tree);
-    if (!t) { *df = *ddf = 0.0 / 0.0; return; }
-    t->cur = cur;
     PhyloNode *L = h->leaf[leaf];
     PhyloNeighbor *nb = (PhyloNeighbor *)L->neighbors[0];
-    t->current_it = nb;
-    t->current_it_back = nei_towards((PhyloNode *)nb->node, L);
-    t->theta_computed = false;
-    t->dervCur(nb, L, *df, *ddf);
+    h->tree->current_it = nb;
+    h->tree->current_it_back = nei_towards((PhyloNode *)nb->node, L);
+    h->tree->theta_computed = false;
+    if (MixlenTree *t = dynamic_cast<MixlenTree *>(h->tree)) { t->cur = cur; t->dervCur(nb, L, *df, *ddf); }
+    else if (iqref_derv_mixlen_cur_hook) iqref_derv_mixlen_cur_hook(h->tree, nb, L, cur, df, ddf);   // the shim's tree class
+    else *df = *ddf = 0.0 / 0.0;
 }
 
 double iqref_logl_from_buffer(void *hv) { return ((Handle *)hv)->tree->computeLikelihoodFromBuffer(); }

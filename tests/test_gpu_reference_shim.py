@@ -136,3 +136,51 @@ def test_reference_rooted_tree_with_a_nonreversible_model_over_the_cuda_kernels(
     calls, launches = gpu.b200_kernel_calls()
     assert calls > 20 and launches > 20
     cpu.close(); gpu.close()
+
+
+@pytest.mark.parametrize("nstates,ncat,safe", [(4, 4, False), (20, 4, True)])
+def test_reference_tree_with_a_site_specific_model_over_the_cuda_kernels(nstates, ncat, safe):
+    """ModelSet / PMSF: the binding de-interleaves the per-pattern eigensystems the reference's kernels read (V-interleaved,
+    tree/phylotreesse.cpp:271-281) into b200lk_set_site_model; the reference's own optimizeAllBranches then runs over the site kernels"""
+    from test_site_model_cpu import make_site_case
+    tree, model, pat, freq, invar = make_site_case(nstates, ncat, ntaxa=12, nptn=300, seed=43)
+    cpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, nthreads=2)
+    gpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, b200=True)
+    for leaf in (0, 5, 9):
+        (lc, pc), (lg, pg) = cpu.branch_logl(leaf), gpu.branch_logl(leaf)
+        assert abs(lc - lg) < 1e-9 * abs(lc)
+        np.testing.assert_allclose(pg, pc, rtol=1e-11)
+        np.testing.assert_allclose(gpu.branch_derv(leaf), cpu.branch_derv(leaf), rtol=1e-9)
+        assert abs(gpu.logl_from_buffer() - cpu.logl_from_buffer()) < 1e-9 * abs(lc)
+    oc, og = cpu.optimize_all_branches(5, 0.001, 100), gpu.optimize_all_branches(5, 0.001, 100)
+    assert abs(oc - og) < 1e-6, (oc, og)
+    bc, bg = cpu.branches(), gpu.branches()
+    for k in bc:
+        assert abs(bc[k] - bg[k]) < 1e-6
+    cpu.close(); gpu.close()
+
+
+@pytest.mark.parametrize("kind,ncat,safe", [("dna", 4, False), ("aa", 3, True)])
+def test_reference_mixlen_tree_over_the_cuda_kernels(kind, ncat, safe):
+    """a tree with mixed branch lengths (PhyloNodeMixlen nodes, isMixlen()): the binding sends the [branch id][class] table
+    (b200lk_set_mixlen), passes Neighbor::id where the kernels take a length, and serves computeLikelihoodDerv's gradient / Hessian form
+    and computeLikelihoodDervMixlen from the CUDA kernels"""
+    from test_mixlen_cpu import make_mixlen_case
+    tree, model, pat, freq, invar = make_mixlen_case(kind, ncat, ntaxa=12, nsites=400, seed=47)
+    cpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, nthreads=2)
+    gpu = ref_engine.RefTree(tree, model, pat, freq, safe_numeric=safe, b200=True)
+    for leaf in (0, 5, 9):
+        (lc, pc), (lg, pg) = cpu.branch_logl(leaf), gpu.branch_logl(leaf)
+        assert abs(lc - lg) < 1e-9 * abs(lc)
+        np.testing.assert_allclose(pg, pc, rtol=1e-11)
+        g_c, H_c, l_c = cpu.branch_derv_mixlen(leaf)
+        g_g, H_g, l_g = gpu.branch_derv_mixlen(leaf)
+        np.testing.assert_allclose(g_g, g_c, rtol=1e-9, atol=1e-7)
+        np.testing.assert_allclose(H_g, H_c, rtol=1e-9, atol=1e-6)
+        assert abs(l_g - l_c) < 1e-9 * abs(l_c)
+        assert abs(gpu.logl_from_buffer() - cpu.logl_from_buffer()) < 1e-9 * abs(lc)
+        for cur in range(ncat):
+            np.testing.assert_allclose(gpu.branch_derv_mixlen_cur(leaf, cur), cpu.branch_derv_mixlen_cur(leaf, cur), rtol=1e-9, atol=1e-7)
+    calls, launches = gpu.b200_kernel_calls()
+    assert calls > 10 and launches > 10
+    cpu.close(); gpu.close()
