@@ -617,7 +617,9 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     walk20 = args.schedule != 1 and model.nstates == 20
     if site:
         walk4 = walk20 = False
-        kernel_name = f"k_site_partials<{model.nstates}> (thread per pattern, per-pattern eigensystems streamed from HBM / L2)"
+        kernel_name = ("k_site_walk20 (32-pattern group per CTA, per-pattern eigensystems resident in shared memory, FP64 MMA m8n8k4 over categories x children)"
+                       if model.nstates == 20 and args.variant != 5 else
+                       f"k_site_partials<{model.nstates}> (thread per pattern, per-pattern eigensystems streamed from HBM / L2)")
     elif nonrev:
         kernel_name = f"k_nonrev_partials<{model.nstates}> (thread per pattern, state-space CLVs, device-built transition matrices)"
     elif walk20:
@@ -630,8 +632,11 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     else:
         kernel_name = "k_partials_generic"
     model_bytes = dram_model_bytes(ops_acc, my_nptn, B, S, chained=walk4)
-    if site:   # + every op reads the pattern's (n + 2 n^2) doubles once (re-reads across categories are L1 / L2 hits at best)
+    if site and not (model.nstates == 20 and args.variant != 5):
+        # thread-per-pattern kernel: every op reads the pattern's (n + 2 n^2) doubles once (re-reads across categories are L1 / L2 hits at best)
         model_bytes += len(ops) * my_nptn * 8 * (model.nstates + 2 * model.nstates ** 2)
+    elif site:   # k_site_walk20: the eigensystems are read once per evaluation
+        model_bytes += my_nptn * 8 * (model.nstates + 2 * model.nstates ** 2)
     traffic, traffic_src = load_traffic(workload, overridden or bool(args.variant or args.schedule), my_nptn)
     # roofline.frac is PHYSICAL: bytes at the DRAM pins (the committed ncu capture of this workload, else the DRAM-side model)
     # per launch / launch time / measured copy peak.  The SURVEY 8(d) algorithmic figure (every CLV written once AND read once)
@@ -657,6 +662,17 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
                               "peak_source": fsrc, "executed_flops_per_launch": flops_exec,
                               "algorithmic_flops_per_launch": flops_alg, "algorithmic_equivalent_TFLOPs": flops_alg / ker_s / 1e12,
                               "algorithmic_equivalent_frac": flops_alg / ker_s / 1e12 / fpeak}
+        if roofline["tensor"]["frac"] > roofline["frac"]:
+            roofline["bound"] = "tensor"
+    if site and model.nstates == 20 and args.variant != 5:
+        # k_site_walk20 shares the FP64 pipe between its DMMAs (30 per pattern, node and 4-category chunk) and the exponentials
+        # (160 per pattern, node and chunk, ~45 FP64 instructions each): the DMMA flops alone over the measured DMMA peak
+        fpeak, fsrc = load_fp64_peak()
+        chunks = (model.ncat_mix + 3) // 4
+        flops_exec = 512.0 * 30 * chunks * my_nptn * len(ops)
+        roofline["tensor"] = {"executed_TFLOPs": flops_exec / ker_s / 1e12, "peak": fpeak, "unit": "TFLOP/s", "frac": flops_exec / ker_s / 1e12 / fpeak,
+                              "peak_source": fsrc, "executed_flops_per_launch": flops_exec,
+                              "note": "DMMA flops only; the exp() calls of the same launch cost about as many FP64-pipe cycles again"}
         if roofline["tensor"]["frac"] > roofline["frac"]:
             roofline["bound"] = "tensor"
     # ---- N > 1: the sharded result checks itself -------------------------------------------------------------------

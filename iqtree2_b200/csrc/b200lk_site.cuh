@@ -141,6 +141,201 @@ __global__ void __launch_bounds__(kTile) k_site_partials(Dev D, SiteModel M, int
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_site_walk20: the 20-state site-specific partial-likelihood kernel on the FP64-MMA pipe (PMSF on protein alignments — what
+// site-specific models are used for).  A pattern's mat-vecs cannot share a matrix with other patterns, but they share it across the
+// CATEGORIES and the TWO CHILDREN of a node: for one pattern and node, the child pass is evec_p [20 x 20] . E [20 x 8] with
+// E[i][2c + child] = exp(eval_p[i] rate_c len_child) child[c][i] — 3 M-tiles x 5 K-steps = 15 DMMAs m8n8k4 — the product of the two
+// children's columns is lane-local in the accumulators, and the back pass inv_p [20 x 20] . tmp [20 x 4] is 15 more (half of the N
+// dimension idle).  A CTA owns one 32-pattern group for the whole post-order walk and keeps its patterns' matrices (evec, inv_evec,
+// eval, row sums of inv_evec for gap tips: 841 doubles per pattern, 215 KB) in SHARED MEMORY: they are read from HBM once per
+// evaluation instead of once per node and category (13 x the CLV traffic in k_site_partials).  A warp keeps its patterns through all
+// ops, so a CLV written at one op is read back by the same warp at the parent (L2); per pattern and op a lane takes 5 exponentials
+// per 4-category chunk.  Rows 20..23 of the padded M-tiles are zeros made in registers, never stored.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kSitePS = 841;   // evec [400] | inv_evec [400] | eval [20] | inv row sums [20] | 1 pad (odd stride: conflict-free staging)
+
+__device__ __forceinline__ double site_tip20(const double *sm, int su, int seq_type, int state, int i) {
+    if (state < 20) return sm[400 + i * 20 + state];
+    if (state == su || seq_type != 2) return sm[820 + i];
+    const int ambi = state - 20 == 0 ? 4 + 8 : (state - 20 == 1 ? 32 + 64 : 512 + 1024);
+    double s = 0.0;
+    for (int x = 0; x < 11; x++) if (ambi & (1 << x)) s += sm[400 + i * 20 + x];
+    return s;
+}
+
+template <bool SAFE, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) k_site_walk20(Dev D, SiteModel M, int seq_type, const DevOp *ops, int nops, unsigned long long *counter) {
+    extern __shared__ double s_m[];   // [32 patterns][kSitePS]
+    __shared__ long long s_item;
+    constexpr int PPW = 32 / NW;   // patterns per warp
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, q = lane & 3;
+    const int C = D.C;
+    const long long ngroups = D.Ppad / 32;
+    for (;;) {   // (the host zeroes the counter before the launch)
+        __syncthreads();
+        if (threadIdx.x == 0) s_item = (long long)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const long long grp = s_item;
+        if (grp >= ngroups) break;
+        const long long p0 = grp * 32;
+        {   // element k of the group's 32 patterns is one 256-byte line
+            const double *ge = M.evec + pbase(p0, 400), *gi = M.inv + pbase(p0, 400), *gv = M.eval + pbase(p0, 20);
+            for (int k = warp; k < 400; k += NW) {
+                s_m[lane * kSitePS + k] = ge[(long long)k * kWarp + lane];
+                s_m[lane * kSitePS + 400 + k] = gi[(long long)k * kWarp + lane];
+            }
+            for (int k = warp; k < 20; k += NW) s_m[lane * kSitePS + 800 + k] = gv[(long long)k * kWarp + lane];
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < 32 * 20; t += NW * 32) {   // tip vector of the gap state: inv_evec_p . 1 (tree/phylotreesse.cpp:283-289)
+            const int pp = t / 20, i = t - pp * 20;
+            const double *row = s_m + pp * kSitePS + 400 + i * 20;
+            double s = 0.0;
+            for (int x = 0; x < 20; x++) s += row[x];
+            s_m[pp * kSitePS + 820 + i] = s;
+        }
+        __syncthreads();
+        // CLV element offsets of this lane for each of its patterns, fixed for the whole walk: the 5 values it loads per category
+        // (i = 4 ks + q), the 3 it stores (i = 8 mt + g), the category stride
+        int offL[PPW][5], offS[PPW][3], cstride;
+        {
+            const ClvIdx at0(D, p0);
+            cstride = (int)(at0(1, 0) - at0(0, 0));
+        }
+#pragma unroll
+        for (int pw = 0; pw < PPW; pw++) {
+            const ClvIdx at(D, p0 + warp * PPW + pw);
+            const long long b0 = at(0, 0);
+#pragma unroll
+            for (int ks = 0; ks < 5; ks++) offL[pw][ks] = (int)(at(0, 4 * ks + q) - b0);
+#pragma unroll
+            for (int mt = 0; mt < 3; mt++) offS[pw][mt] = 8 * mt + g < 20 ? (int)(at(0, 8 * mt + g) - b0) : 0;
+        }
+        for (int o = 0; o < nops; o++) {
+            const DevOp op = ops[o];
+            // the lane's column of E: child = g & 1 (0 = left), category cb + (g >> 1)
+            const int ch = g & 1, cc = g >> 1;
+            const bool tip = op.ncase == 0 || (op.ncase == 1 && ch == 0);
+            const int cid = ch ? op.rid : op.lid;
+            const double len = resolve_len(D, __longlong_as_double(ch ? op.eR : op.eL));
+            const double *src = tip ? nullptr : D.partial + (long long)cid * D.slot_stride;
+            double *out = D.partial + (long long)op.dst * D.slot_stride;
+#pragma unroll
+            for (int pw = 0; pw < PPW; pw++) {
+                const int pl = warp * PPW + pw;
+                const long long p = p0 + pl;
+                const double *sm = s_m + pl * kSitePS;
+                const long long pb = ClvIdx(D, p)(0, 0);
+                const double *srcp = src ? src + pb : nullptr;
+                double *outp = out + pb;
+                const long long sb = SAFE ? pbase(p, C) : p;
+                double tv[5];
+                if (tip) {
+                    const int state = D.tips[(long long)cid * D.Ppad + p];
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++) tv[ks] = site_tip20(sm, D.su, seq_type, state, 4 * ks + q);
+                }
+                const bool check = (op.ncase != 0) && (D.invar[p] == 0.0);
+                const uint16_t *lsc = op.ncase == 2 ? D.scale + (long long)op.lid * D.scale_stride + sb : nullptr;
+                const uint16_t *rsc = op.ncase >= 1 ? D.scale + (long long)op.rid * D.scale_stride + sb : nullptr;
+                uint16_t *osc = D.scale + (long long)op.dst * D.scale_stride + sb;
+                double lh_max = 0.0;
+                for (int cb = 0; cb < C; cb += 4) {
+                    const int c = cb + cc;
+                    const bool cv = c < C;
+                    const double rl = cv ? D.cat_rate[c] * len : 0.0;   // :1365-1366
+                    double e[5];
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++) {
+                        const int i = 4 * ks + q;
+                        e[ks] = cv ? exp(sm[800 + i] * rl) * (srcp ? srcp[c * cstride + offL[pw][ks]] : tv[ks]) : 0.0;
+                    }
+                    double a[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++)
+#pragma unroll
+                        for (int mt = 0; mt < 3; mt++) {
+                            const int x = 8 * mt + g;
+                            const double A = x < 20 ? sm[x * 20 + 4 * ks + q] : 0.0;
+                            dmma_m8n8k4(a[mt][0], a[mt][1], A, e[ks]);
+                        }
+                    // a[mt] = (left, right) sums of state x = 8 mt + g, category cb + q: the product is lane-local
+                    double t[3];
+#pragma unroll
+                    for (int mt = 0; mt < 3; mt++) t[mt] = a[mt][0] * a[mt][1];
+                    double b[5];
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++) {   // B[k = q][col = g] = tmp[x = 4 ks + q][category cb + g], held by lane 4 (x % 8) + g in t[x / 8]
+                        const double v = __shfl_sync(0xffffffffu, t[ks >> 1], 4 * ((4 * ks + q) & 7) + (g & 3));
+                        b[ks] = g < 4 ? v : 0.0;
+                    }
+                    double r[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+#pragma unroll
+                    for (int ks = 0; ks < 5; ks++)
+#pragma unroll
+                        for (int mt = 0; mt < 3; mt++) {
+                            const int i = 8 * mt + g;
+                            const double A = i < 20 ? sm[400 + i * 20 + 4 * ks + q] : 0.0;
+                            dmma_m8n8k4(r[mt][0], r[mt][1], A, b[ks]);
+                        }
+                    // r[mt][j] = out[i = 8 mt + g][category cb + 2 q + j]  (q < 2)
+                    double m0 = fmax(fmax(fabs(r[0][0]), fabs(r[1][0])), fabs(r[2][0]));
+                    double m1 = fmax(fmax(fabs(r[0][1]), fabs(r[1][1])), fabs(r[2][1]));
+                    const int c0 = cb + 2 * q, c1 = c0 + 1;
+                    const bool v0 = q < 2 && c0 < C, v1 = q < 2 && c1 < C;
+                    if (!v0) m0 = 0.0;
+                    if (!v1) m1 = 0.0;
+                    if (SAFE) {
+#pragma unroll
+                        for (int off = 4; off < 32; off <<= 1) {   // over the rows g of the same column
+                            m0 = fmax(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+                            m1 = fmax(m1, __shfl_xor_sync(0xffffffffu, m1, off));
+                        }
+                        unsigned s0 = 0, s1 = 0;
+                        if (v0) s0 = (lsc ? lsc[c0 * kWarp] : 0u) + (rsc ? rsc[c0 * kWarp] : 0u);
+                        if (v1) s1 = (lsc ? lsc[c1 * kWarp] : 0u) + (rsc ? rsc[c1 * kWarp] : 0u);
+                        if (check && v0 && m0 < kScalingThreshold) { r[0][0] *= kTwo256; r[1][0] *= kTwo256; r[2][0] *= kTwo256; s0 += 1; }
+                        if (check && v1 && m1 < kScalingThreshold) { r[0][1] *= kTwo256; r[1][1] *= kTwo256; r[2][1] *= kTwo256; s1 += 1; }
+                        if (g == 0 && v0) osc[c0 * kWarp] = (uint16_t)s0;
+                        if (g == 0 && v1) osc[c1 * kWarp] = (uint16_t)s1;
+                    } else lh_max = fmax(lh_max, fmax(m0, m1));
+#pragma unroll
+                    for (int mt = 0; mt < 3; mt++) {
+                        const int i = 8 * mt + g;
+                        if (i < 20) {
+                            if (v0) outp[c0 * cstride + offS[pw][mt]] = r[mt][0];
+                            if (v1) outp[c1 * cstride + offS[pw][mt]] = r[mt][1];
+                        }
+                    }
+                }
+                if (!SAFE) {
+#pragma unroll
+                    for (int off = 1; off < 32; off <<= 1) lh_max = fmax(lh_max, __shfl_xor_sync(0xffffffffu, lh_max, off));
+                    unsigned sc = (lsc ? lsc[0] : 0u) + (rsc ? rsc[0] : 0u);
+                    if (check && lh_max < kScalingThreshold) {   // every lane re-scales what it stored itself
+                        for (int cb = 0; cb < C; cb += 4) {
+                            const int c0 = cb + 2 * q, c1 = c0 + 1;
+#pragma unroll
+                            for (int mt = 0; mt < 3; mt++) {
+                                const int i = 8 * mt + g;
+                                if (i < 20 && q < 2) {
+                                    if (c0 < C) outp[c0 * cstride + offS[pw][mt]] *= kTwo256;
+                                    if (c1 < C) outp[c1 * cstride + offS[pw][mt]] *= kTwo256;
+                                }
+                            }
+                        }
+                        sc += 1;
+                    }
+                    if (lane == 0) osc[0] = (uint16_t)sc;
+                }
+                __syncwarp();   // the parent op reads these values through other lanes of this warp
+            }
+        }
+    }
+}
+
 // computeLikelihoodBranch, SITE_MODEL (:2833-2848 leaf at the far end, :2993-3008 two CLVs): lh_cat[c] = prop_c * sum_i
 // exp(eval_p[i] rate_c len) node[c][i] dad[c][i] (dotProductExp), then the normal model's scaling alignment and logarithm
 template <bool SAFE>

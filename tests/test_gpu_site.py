@@ -67,6 +67,44 @@ def test_site_parity_scaling_deep_tree(safe):
     g.close()
 
 
+@pytest.mark.parametrize("safe", [False, True])
+@pytest.mark.parametrize("ncat", [1, 3, 4, 6])
+def test_site_20_states_both_kernels(safe, ncat):
+    """the FP64-MMA walker with the matrices resident in shared memory (k_site_walk20: 4-category chunks, so 1 / 3 / 6 categories
+    exercise partial and multiple chunks) and the thread-per-pattern kernel (kernel variant 5) against the restatement and each other"""
+    tree, model, pat, freq, invar = make_site_case(20, ncat, ntaxa=14, nptn=210, seed=53, pinvar=0.1 if ncat == 3 else 0.0)
+    o = engine(OracleEngine, tree, model, pat, freq, invar, safe)
+    ops, a, b, L = plan.plan_branch(tree, 5)
+    ll_o = o.branch_logl(ops, a, b, L)
+    for variant in (0, 5):
+        g = engine(LikelihoodEngine, tree, model, pat, freq, invar, safe)
+        if variant:
+            g.set_schedule(10 + variant)
+        ll_g = g.branch_logl(ops, a, b, L)
+        assert abs(ll_g - ll_o) < 1e-9 * abs(ll_o), (variant, ll_g, ll_o)
+        for op in ops:
+            s = int(op["dst_slot"])
+            assert np.array_equal(g.get_scale_num(s), o.get_scale_num(s))
+            assert_partials_close(g.get_partial(s), o.get_partial(s), 1e-11)
+        g.close()
+
+
+def test_site_20_states_deep_tree_rescales_on_the_mma_kernel():
+    tree, model, pat, freq, invar = make_site_case(20, 4, ntaxa=120, nptn=96, seed=7, tree_kind="caterpillar", mean_len=0.8, p_unknown=0.0)
+    for safe in (False, True):
+        g = engine(LikelihoodEngine, tree, model, pat, freq, invar, safe)
+        o = engine(OracleEngine, tree, model, pat, freq, invar, safe)
+        ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+        ll_g, ll_o = g.branch_logl(ops, a, b, L), o.branch_logl(ops, a, b, L)
+        assert max(o.get_scale_num(int(op["dst_slot"])).max() for op in ops) >= 1, "case does not rescale"
+        assert abs(ll_g - ll_o) < 1e-9 * abs(ll_o)
+        for op in ops:
+            s = int(op["dst_slot"])
+            assert np.array_equal(g.get_scale_num(s), o.get_scale_num(s))
+        np.testing.assert_allclose(g.get_pattern_lh(), o.get_pattern_lh(), rtol=1e-11, atol=0)
+        g.close()
+
+
 def test_site_with_invariant_sites():
     tree, model, pat, freq, invar = make_site_case(4, 4, ntaxa=10, nptn=400, seed=23, pinvar=0.15)
     assert (invar > 0).any()
