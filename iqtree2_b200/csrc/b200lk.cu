@@ -341,7 +341,7 @@ extern "C" int b200lk_set_stream(b200lk_engine *e, void *cuda_stream) {
 
 extern "C" int b200lk_set_schedule(b200lk_engine *e, int schedule) {
     if (!e->shards.empty()) return mg_each(e, [&](int k) { return b200lk_set_schedule(e->shards[k], schedule); });
-    if (schedule >= 10 && schedule < 20) {   // development switch: kernel variant of the walker schedule (A/B measurements)
+    if (schedule >= 10 && schedule < 40) {   // development switch: kernel variant of the walker schedule (A/B measurements)
         e->kernel_variant = schedule - 10;
         e->walk20_attr_set = false;
         return 0;
@@ -511,7 +511,8 @@ extern "C" int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const 
 static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
-    const size_t need_info = nops * 2 * (e_sz + leaf_sz);
+    size_t need_info = nops * 2 * (e_sz + leaf_sz);
+    if (e->cfg.nstates == 4) need_info = std::max(need_info, nops * (size_t)kStage4);   // k_walk_n4c4's staging blocks (full tip tables)
     if (need_info > e->opinfo_cap) {
         CK(sync_stream(e));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
@@ -659,10 +660,18 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
         const bool safe = e->cfg.safe_numeric != 0;
-        static const void *const kernels[6] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
-                                               (const void *)k_walk_n4c4<false, 2>, (const void *)k_walk_n4c4<true, 2>,
-                                               (const void *)k_walk_n4c4<false, 0>, (const void *)k_walk_n4c4<true, 0>};
-        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : 0;
+        static const void *const kernels[18] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
+                                                (const void *)k_walk_n4c4<false, 2>, (const void *)k_walk_n4c4<true, 2>,
+                                                (const void *)k_walk_n4c4<false, 0>, (const void *)k_walk_n4c4<true, 0>,
+                                                // variants 20..23 (A/B): L2 prefetches none / tip rows / sibling CLVs / both
+                                                (const void *)k_walk_n4c4<false, 1, 0, 0>, (const void *)k_walk_n4c4<true, 1, 0, 0>,
+                                                (const void *)k_walk_n4c4<false, 1, 0, 1>, (const void *)k_walk_n4c4<true, 1, 0, 1>,
+                                                (const void *)k_walk_n4c4<false, 1, 0, 2>, (const void *)k_walk_n4c4<true, 1, 0, 2>,
+                                                (const void *)k_walk_n4c4<false, 1, 0, 3>, (const void *)k_walk_n4c4<true, 1, 0, 3>,
+                                                // 24, 25: tip states through shared memory (cp.async), with / without the L2 prefetch of tip rows
+                                                (const void *)k_walk_n4c4<false, 1, 0, 5>, (const void *)k_walk_n4c4<true, 1, 0, 5>,
+                                                (const void *)k_walk_n4c4<false, 1, 0, 4>, (const void *)k_walk_n4c4<true, 1, 0, 4>};
+        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : (e->kernel_variant >= 20 && e->kernel_variant <= 25) ? e->kernel_variant - 17 : 0;
 #ifdef B200LK_DIAG
         static const void *const dbg_kernels[3] = {(const void *)k_walk_n4c4<false, 2, 1>, (const void *)k_walk_n4c4<false, 2, 2>,
                                                    (const void *)k_walk_n4c4<false, 2, 3>};   // variants 6..8: no stores / no loads / neither

@@ -606,9 +606,14 @@ struct WalkJob4 {      // host -> k_walk_info_n4c4
     int32_t dst, ncase, aid, bid, loadA, pad;
 };
 
-// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[64] | tabB[64]
-constexpr int kStage4 = 4 + 16 + 16 + 64 + 64;   // 164 doubles = 1312 bytes (16-byte multiple)
+// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[16][kTab4] | tabB[16][kTab4]
+// tab[c*4 + x][state]: partial_lh_leaves for EVERY state code 0..STATE_UNKNOWN (the four nucleotides, the IUPAC ambiguity codes with
+// the direct sum of their indicator, the gap state = the constant 1), so that a tip child costs one shared-memory load per value and
+// no branch on its state — a warp's 32 patterns almost never hold only unambiguous states
+constexpr int kTab4 = 20;                          // states per row (kMaxLeafRows4 = 19, padded to an even count)
+constexpr int kStage4 = 4 + 16 + 16 + 2 * 16 * kTab4;   // 676 doubles = 5408 bytes (16-byte multiple)
 struct StageHdr4 { int32_t dst, ncase, aid, bid, loadA, pad0, pad1, pad2; };
+constexpr int kPfAhead4 = 4;   // ops between an L2 prefetch and the use of the data (an op of one tile takes ~2 us at full load)
 
 // child A is the CLV that lives in registers (`cur`: chained from the previous op, or loaded when loadA), child B the
 // other one: an internal CLV loaded from memory (ncase 2) or a tip (ncase <= 1); ncase 0: both are tips.
@@ -626,24 +631,37 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
         st[4 + ch * 16 + k] = v;
     }
     if (t == 0) {
-        StageHdr4 h{job.dst, job.ncase, job.aid, job.bid, job.loadA, 0, 0, 0};
+        // pad0..2: what the op kPfAhead4 ops further on will read from memory that may have left L2 — its tip rows (B, A) and its
+        // sibling CLV slot; k_walk_n4c4 turns them into L2 bulk prefetches of its own tile (-1: nothing)
+        int pfB = -1, pfA = -1, pfS = -1;
+        const int on = (int)blockIdx.x + kPfAhead4;
+        if (on < (int)gridDim.x) {
+            const WalkJob4 jn = jobs[on];
+            if (jn.ncase <= 1) pfB = jn.bid;
+            if (jn.ncase == 0) pfA = jn.aid;
+            if (jn.ncase == 2) pfS = jn.bid;
+        }
+        StageHdr4 h{job.dst, job.ncase, job.aid, job.bid, job.loadA, pfB, pfA, pfS};
         *reinterpret_cast<StageHdr4 *>(st) = h;
     }
     __syncthreads();
-    // partial_lh_leaves for the 4 unambiguous states, stored [c][x][state] (:1036-1051, Vec4d lanes + horizontal_add)
-    const int c = t >> 4, x = (t >> 2) & 3, s = t & 3;
+    // partial_lh_leaves, stored [c][x][state] (:1036-1051, Vec4d lanes + horizontal_add); the gap state is the constant 1
+    const int cx = t & 15, c = cx >> 2, x = cx & 3;
     for (int ch = 0; ch < 2; ch++) {
         const bool is_tip = ch == 0 ? (job.ncase == 0) : (job.ncase <= 1);
-        double v = 0.0;
-        if (is_tip) {
-            const double *tip = D.tip_lh + s * 4;
-            double p0 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 0], s_exp[ch][c * 4 + 0]), tip[0]);
-            double p1 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 1], s_exp[ch][c * 4 + 1]), tip[1]);
-            double p2 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 2], s_exp[ch][c * 4 + 2]), tip[2]);
-            double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
-            v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
+        if (!is_tip) continue;
+        for (int s = t >> 4; s <= D.su; s += 4) {
+            double v = 1.0;
+            if (s != D.su) {
+                const double *tip = D.tip_lh + s * 4;
+                double p0 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 0], s_exp[ch][c * 4 + 0]), tip[0]);
+                double p1 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 1], s_exp[ch][c * 4 + 1]), tip[1]);
+                double p2 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 2], s_exp[ch][c * 4 + 2]), tip[2]);
+                double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
+                v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
+            }
+            st[36 + ch * 16 * kTab4 + cx * kTab4 + s] = v;
         }
-        st[36 + ch * 64 + t] = v;
     }
 }
 
@@ -651,9 +669,17 @@ __device__ __forceinline__ unsigned abs_hi(double v) { return (unsigned)__double
 constexpr unsigned kThresholdHi = (1023u - 256u) << 20;   // high word of 2^-256: |v| < 2^-256  <=>  abs_hi(v) < this
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+// one instruction, one thread: `bytes` (multiple of 16, 16-byte aligned) towards L2
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
@@ -673,21 +699,24 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 //            the kernel's time ~ compute + store time instead of their maximum).  CLV loads then bypass L1 (ld.global.cg): the
 //            bulk store writes through the async proxy, and the slot's lines may sit in this SM's L1 from an earlier read.
 // DBG (diagnosis builds, wrong results): bit 0 no CLV stores, bit 1 no sibling loads
-template <bool SAFE, int STORE = 2, int DBG = 0>
+template <bool SAFE, int STORE = 2, int DBG = 0, int PF = 4>   // PF: bit 0 = L2 prefetch of tip rows, bit 1 = of sibling CLVs (slower: A/B only), bit 2 = tip states through shared memory
 __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_constant__ Model4 M, const double *stage, int nops,
                                                        unsigned long long *counter) {
     // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
     // L1 prefetch of op o+1's operands) and block o+2 is in flight in registers.
     __shared__ __align__(16) double s_stage[3][kStage4];
-    __shared__ double s_tip[kMaxLeafRows4 * 4];
     __shared__ long long s_item;
+    // PF bit 2: the next op's tip states travel global -> shared with cp.async (no register, hence no scoreboard, is held across the
+    // op: with the register form ncu put 27 % of all stall samples on the op's first FP64 instruction, a shared-memory consumer
+    // whose scoreboard the just-issued tip-state load of the NEXT op shares)
+    constexpr bool TSM = (PF & 4) != 0;
+    __shared__ __align__(16) unsigned char s_ts[TSM ? 2 : 1][2][TSM ? kTile : 4];
     constexpr bool TST = STORE == 2, ESTORE = STORE >= 1;
     __shared__ __align__(128) double s_out[TST ? 2 : 1][TST ? 16 * kTile : 2];   // [buffer][warp][k][lane] = the tile's 16 KB of a slot
     const int tid = threadIdx.x;
     const int so = (tid >> 5) * 16 * kWarp + (tid & 31);
     int prev_dst = -1;
     long long prev_tile_off = 0;
-    for (int k = tid; k < (D.su + 1) * 4; k += kTile) s_tip[k] = D.tip_lh[k];
     const long long ntiles = D.Ppad / kTile;
     constexpr int kStageVec = kStage4 / 2;   // double2 elements per staging block
     for (;;) {
@@ -700,9 +729,9 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
         const long long pb = pbase(p, 16);
         const long long sb = SAFE ? pbase(p, 4) : p;
         const bool may_scale = D.invar[p] == 0.0;
-        if (tid < kStageVec) {
-            reinterpret_cast<double2 *>(s_stage[0])[tid] = reinterpret_cast<const double2 *>(stage)[tid];
-            if (nops > 1) reinterpret_cast<double2 *>(s_stage[1])[tid] = reinterpret_cast<const double2 *>(stage + kStage4)[tid];
+        for (int k = tid; k < kStageVec; k += kTile) {
+            reinterpret_cast<double2 *>(s_stage[0])[k] = reinterpret_cast<const double2 *>(stage)[k];
+            if (nops > 1) reinterpret_cast<double2 *>(s_stage[1])[k] = reinterpret_cast<const double2 *>(stage + kStage4)[k];
         }
         double cur[16];
         unsigned cursc[SAFE ? 4 : 1];
@@ -711,10 +740,18 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
         for (int c = 0; c < (SAFE ? 4 : 1); c++) cursc[c] = 0;
         int sA_next = 0, sB_next = 0;
+        const int ts_off = (tid >> 5) * 32 + (tid & 7) * 4;   // TSM: lanes 0..7 of a warp copy the warp's 32 states, 4 bytes each
         {   // tip states of op 0
             const int4 h = *reinterpret_cast<const int4 *>(stage);   // global: the shared copy is not visible yet
-            if (h.y <= 1) sB_next = D.tips[(long long)h.w * D.Ppad + p];
-            if (h.y == 0) sA_next = D.tips[(long long)h.z * D.Ppad + p];
+            if (TSM) {
+                if ((tid & 31) < 8) {
+                    if (h.y <= 1) cp_async4(&s_ts[0][1][ts_off], D.tips + (long long)h.w * D.Ppad + tile * kTile + ts_off);
+                    if (h.y == 0) cp_async4(&s_ts[0][0][ts_off], D.tips + (long long)h.z * D.Ppad + tile * kTile + ts_off);
+                }
+            } else {
+                if (h.y <= 1) sB_next = D.tips[(long long)h.w * D.Ppad + p];
+                if (h.y == 0) sA_next = D.tips[(long long)h.z * D.Ppad + p];
+            }
         }
 
         int buf = 0;
@@ -731,13 +768,23 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             const double *st = s_stage[buf];
             const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
             const int4 h0 = *reinterpret_cast<const int4 *>(st);
-            const int h_loadA = *reinterpret_cast<const int *>(st + 2);
+            const int4 h1 = *reinterpret_cast<const int4 *>(st + 2);
+            const int h_loadA = h1.x;
             const int dst = h0.x, ncase = h0.y, aid = h0.z, bid = h0.w;
+            if (PF && tid == 0) {
+                // tip rows are streamed from DRAM once per evaluation, and a sibling CLV written many ops ago may have left L2: under
+                // the store stream of this kernel such a read takes longer than an op (ncu: 37 % of all stall samples sat on the
+                // first uses of a tip state loaded ONE op ahead) — ask for this tile's part of them kPfAhead4 ops early
+                if ((PF & 1) && h1.y >= 0) prefetch_l2_bulk(D.tips + (long long)h1.y * D.Ppad + tile * kTile, kTile);
+                if ((PF & 1) && h1.z >= 0) prefetch_l2_bulk(D.tips + (long long)h1.z * D.Ppad + tile * kTile, kTile);
+                if ((PF & 2) && h1.w >= 0) prefetch_l2_bulk(D.partial + (long long)h1.w * D.slot_stride + tile * (16LL * kTile), 16 * kTile * sizeof(double));
+            }
             // staging block o+2 travels global -> shared with cp.async (no registers held across the op); its ring slot was
             // op o-1's, which every thread has left (barrier above)
-            if ((tid < kStageVec) && (o + 2 < nops))
-                cp_async16(&s_stage[buf2][2 * tid], stage + (size_t)(o + 2) * kStage4 + 2 * tid);
-            const int sA = sA_next, sB = sB_next;
+            if (o + 2 < nops)
+                for (int k = tid; k < kStageVec; k += kTile) cp_async16(&s_stage[buf2][2 * k], stage + (size_t)(o + 2) * kStage4 + 2 * k);
+            const int sA = TSM ? (ncase == 0 ? (int)s_ts[o & 1][0][tid] : 0) : sA_next;
+            const int sB = TSM ? (ncase <= 1 ? (int)s_ts[o & 1][1][tid] : 0) : sB_next;
 
             double X[16];
             unsigned scB[SAFE ? 4 : 1];
@@ -766,8 +813,15 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 const double *sn = s_stage[buf1];
                 const int4 hn = *reinterpret_cast<const int4 *>(sn);
                 const int n_loadA = *reinterpret_cast<const int *>(sn + 2);
-                if (hn.y <= 1) sB_next = D.tips[(long long)hn.w * D.Ppad + p];
-                if (hn.y == 0) sA_next = D.tips[(long long)hn.z * D.Ppad + p];
+                if (TSM) {
+                    if ((tid & 31) < 8) {
+                        if (hn.y <= 1) cp_async4(&s_ts[(o + 1) & 1][1][ts_off], D.tips + (long long)hn.w * D.Ppad + tile * kTile + ts_off);
+                        if (hn.y == 0) cp_async4(&s_ts[(o + 1) & 1][0][ts_off], D.tips + (long long)hn.z * D.Ppad + tile * kTile + ts_off);
+                    }
+                } else {
+                    if (hn.y <= 1) sB_next = D.tips[(long long)hn.w * D.Ppad + p];
+                    if (hn.y == 0) sA_next = D.tips[(long long)hn.z * D.Ppad + p];
+                }
                 if (hn.y == 2) {
                     const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
 #pragma unroll
@@ -779,7 +833,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                     for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(An + k * kWarp);
                 }
             }
-            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
+            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 36 + 16 * kTab4;
             double *Op = D.partial + (long long)dst * D.slot_stride + pb;
             unsigned mhi = 0;
 #pragma unroll
@@ -791,21 +845,9 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 4; x++)
                         fa[x] = fma(M.evec[x * 4 + 3], a3, fma(M.evec[x * 4 + 2], a2, fma(M.evec[x * 4 + 1], a1, M.evec[x * 4] * a0)));
-                } else if (sA < 4) {
-#pragma unroll
-                    for (int x = 0; x < 4; x++) fa[x] = tabA[c * 16 + x * 4 + sA];
-                } else if (sA == D.su) {
-#pragma unroll
-                    for (int x = 0; x < 4; x++) fa[x] = 1.0;
                 } else {
 #pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expA[c * 4 + 0]), s_tip[sA * 4 + 0]);
-                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expA[c * 4 + 1]), s_tip[sA * 4 + 1]);
-                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expA[c * 4 + 2]), s_tip[sA * 4 + 2]);
-                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expA[c * 4 + 3]), s_tip[sA * 4 + 3]);
-                        fa[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
-                    }
+                    for (int x = 0; x < 4; x++) fa[x] = tabA[(c * 4 + x) * kTab4 + sA];
                 }
                 if (ncase == 2) {
                     const double2 e01 = *reinterpret_cast<const double2 *>(expB + c * 4), e23 = *reinterpret_cast<const double2 *>(expB + c * 4 + 2);
@@ -813,21 +855,9 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 4; x++)
                         fb[x] = fma(M.evec[x * 4 + 3], b3, fma(M.evec[x * 4 + 2], b2, fma(M.evec[x * 4 + 1], b1, M.evec[x * 4] * b0)));
-                } else if (sB < 4) {
-#pragma unroll
-                    for (int x = 0; x < 4; x++) fb[x] = tabB[c * 16 + x * 4 + sB];
-                } else if (sB == D.su) {
-#pragma unroll
-                    for (int x = 0; x < 4; x++) fb[x] = 1.0;
                 } else {
 #pragma unroll
-                    for (int x = 0; x < 4; x++) {
-                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expB[c * 4 + 0]), s_tip[sB * 4 + 0]);
-                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expB[c * 4 + 1]), s_tip[sB * 4 + 1]);
-                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expB[c * 4 + 2]), s_tip[sB * 4 + 2]);
-                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expB[c * 4 + 3]), s_tip[sB * 4 + 3]);
-                        fb[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
-                    }
+                    for (int x = 0; x < 4; x++) fb[x] = tabB[(c * 4 + x) * kTab4 + sB];
                 }
                 const double t0 = fa[0] * fb[0], t1 = fa[1] * fb[1], t2 = fa[2] * fb[2], t3 = fa[3] * fb[3];
                 unsigned chi = 0;
