@@ -511,8 +511,7 @@ extern "C" int b200lk_set_rates(b200lk_engine *e, const double *cat_rate, const 
 static int ensure_op_capacity(b200lk_engine *e, size_t nops) {
     const size_t e_sz = (size_t)e->B * e->cfg.nstates;
     const size_t leaf_sz = (size_t)(e->cfg.state_unknown + 1) * e->B;
-    size_t need_info = nops * 2 * (e_sz + leaf_sz);
-    if (e->cfg.nstates == 4) need_info = std::max(need_info, nops * (size_t)kStage4);   // k_walk_n4c4's staging blocks (full tip tables)
+    const size_t need_info = nops * 2 * (e_sz + leaf_sz);
     if (need_info > e->opinfo_cap) {
         CK(sync_stream(e));
         if (e->d_opinfo) { cudaFree(e->d_opinfo); e->device_bytes -= (int64_t)(e->opinfo_cap * sizeof(double)); }
@@ -660,7 +659,7 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
         const bool safe = e->cfg.safe_numeric != 0;
-        static const void *const kernels[18] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
+        static const void *const kernels[20] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
                                                 (const void *)k_walk_n4c4<false, 2>, (const void *)k_walk_n4c4<true, 2>,
                                                 (const void *)k_walk_n4c4<false, 0>, (const void *)k_walk_n4c4<true, 0>,
                                                 // variants 20..23 (A/B): L2 prefetches none / tip rows / sibling CLVs / both
@@ -670,8 +669,10 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
                                                 (const void *)k_walk_n4c4<false, 1, 0, 3>, (const void *)k_walk_n4c4<true, 1, 0, 3>,
                                                 // 24, 25: tip states through shared memory (cp.async), with / without the L2 prefetch of tip rows
                                                 (const void *)k_walk_n4c4<false, 1, 0, 5>, (const void *)k_walk_n4c4<true, 1, 0, 5>,
-                                                (const void *)k_walk_n4c4<false, 1, 0, 4>, (const void *)k_walk_n4c4<true, 1, 0, 4>};
-        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : (e->kernel_variant >= 20 && e->kernel_variant <= 25) ? e->kernel_variant - 17 : 0;
+                                                (const void *)k_walk_n4c4<false, 1, 0, 4>, (const void *)k_walk_n4c4<true, 1, 0, 4>,
+                                                // 26: + the next op's sibling CLV through shared memory (cp.async one op ahead)
+                                                (const void *)k_walk_n4c4<false, 1, 0, 12>, (const void *)k_walk_n4c4<true, 1, 0, 12>};
+        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : (e->kernel_variant >= 20 && e->kernel_variant <= 26) ? e->kernel_variant - 17 : 0;
 #ifdef B200LK_DIAG
         static const void *const dbg_kernels[3] = {(const void *)k_walk_n4c4<false, 2, 1>, (const void *)k_walk_n4c4<false, 2, 2>,
                                                    (const void *)k_walk_n4c4<false, 2, 3>};   // variants 6..8: no stores / no loads / neither
@@ -682,7 +683,12 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
         }
 #endif
         void *args[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
-        if (v >= 0) CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, 0, e->stream));
+        const size_t xsm = v == 9 ? sizeof(double) * 2 * 16 * kTile : 0;   // variant 26: two sibling-CLV buffers in dynamic shared memory
+        if (xsm) {
+            static bool xsm_attr[2] = {false, false};
+            if (!xsm_attr[safe ? 1 : 0]) { CK(cudaFuncSetAttribute(kernels[v * 2 + (safe ? 1 : 0)], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm)); xsm_attr[safe ? 1 : 0] = true; }
+        }
+        if (v >= 0) CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, xsm, e->stream));
     }
     if (e->profiling) cudaEventRecord(e->ev[5], e->stream);
     e->partials_timed = e->profiling;

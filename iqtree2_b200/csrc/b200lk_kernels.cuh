@@ -606,12 +606,10 @@ struct WalkJob4 {      // host -> k_walk_info_n4c4
     int32_t dst, ncase, aid, bid, loadA, pad;
 };
 
-// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[16][kTab4] | tabB[16][kTab4]
-// tab[c*4 + x][state]: partial_lh_leaves for EVERY state code 0..STATE_UNKNOWN (the four nucleotides, the IUPAC ambiguity codes with
-// the direct sum of their indicator, the gap state = the constant 1), so that a tip child costs one shared-memory load per value and
-// no branch on its state — a warp's 32 patterns almost never hold only unambiguous states
-constexpr int kTab4 = 20;                          // states per row (kMaxLeafRows4 = 19, padded to an even count)
-constexpr int kStage4 = 4 + 16 + 16 + 2 * 16 * kTab4;   // 676 doubles = 5408 bytes (16-byte multiple)
+// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[64] | tabB[64]
+// (tables for EVERY state code instead of the four nucleotides — 676 doubles per block, no branch on the tip state — were measured:
+// 9 % slower on config 2, the block is re-staged per tile and op and 5.4 KB per 128 patterns is a third of the CLV it produces)
+constexpr int kStage4 = 4 + 16 + 16 + 64 + 64;   // 164 doubles = 1312 bytes (16-byte multiple)
 struct StageHdr4 { int32_t dst, ncase, aid, bid, loadA, pad0, pad1, pad2; };
 constexpr int kPfAhead4 = 4;   // ops between an L2 prefetch and the use of the data (an op of one tile takes ~2 us at full load)
 
@@ -645,23 +643,20 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
         *reinterpret_cast<StageHdr4 *>(st) = h;
     }
     __syncthreads();
-    // partial_lh_leaves, stored [c][x][state] (:1036-1051, Vec4d lanes + horizontal_add); the gap state is the constant 1
-    const int cx = t & 15, c = cx >> 2, x = cx & 3;
+    // partial_lh_leaves for the 4 unambiguous states, stored [c][x][state] (:1036-1051, Vec4d lanes + horizontal_add)
+    const int c = t >> 4, x = (t >> 2) & 3, s = t & 3;
     for (int ch = 0; ch < 2; ch++) {
         const bool is_tip = ch == 0 ? (job.ncase == 0) : (job.ncase <= 1);
-        if (!is_tip) continue;
-        for (int s = t >> 4; s <= D.su; s += 4) {
-            double v = 1.0;
-            if (s != D.su) {
-                const double *tip = D.tip_lh + s * 4;
-                double p0 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 0], s_exp[ch][c * 4 + 0]), tip[0]);
-                double p1 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 1], s_exp[ch][c * 4 + 1]), tip[1]);
-                double p2 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 2], s_exp[ch][c * 4 + 2]), tip[2]);
-                double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
-                v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
-            }
-            st[36 + ch * 16 * kTab4 + cx * kTab4 + s] = v;
+        double v = 0.0;
+        if (is_tip) {
+            const double *tip = D.tip_lh + s * 4;
+            double p0 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 0], s_exp[ch][c * 4 + 0]), tip[0]);
+            double p1 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 1], s_exp[ch][c * 4 + 1]), tip[1]);
+            double p2 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 2], s_exp[ch][c * 4 + 2]), tip[2]);
+            double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
+            v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
         }
+        st[36 + ch * 64 + t] = v;
     }
 }
 
@@ -705,18 +700,25 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
     // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
     // L1 prefetch of op o+1's operands) and block o+2 is in flight in registers.
     __shared__ __align__(16) double s_stage[3][kStage4];
+    __shared__ double s_tip[kMaxLeafRows4 * 4];
     __shared__ long long s_item;
     // PF bit 2: the next op's tip states travel global -> shared with cp.async (no register, hence no scoreboard, is held across the
     // op: with the register form ncu put 27 % of all stall samples on the op's first FP64 instruction, a shared-memory consumer
     // whose scoreboard the just-issued tip-state load of the NEXT op shares)
-    constexpr bool TSM = (PF & 4) != 0;
-    __shared__ __align__(16) unsigned char s_ts[TSM ? 2 : 1][2][TSM ? kTile : 4];
     constexpr bool TST = STORE == 2, ESTORE = STORE >= 1;
+    constexpr bool TSM = (PF & 4) != 0 && !TST;   // (the TMA-store variant's two 16 KB buffers leave no static shared memory for it)
+    __shared__ __align__(16) unsigned char s_ts[TSM ? 2 : 1][2][TSM ? kTile : 4];
+    // PF bit 3: the sibling CLV of the NEXT op (always written before this op began: the planner chains the previous op's result as
+    // child A) travels global -> shared with cp.async while this op computes, 16 KB per tile in the slot's own layout
+    constexpr bool XSM = (PF & 8) != 0 && !TST;
+    extern __shared__ __align__(16) double s_x_dyn[];   // XSM: [2][16 * kTile] (dynamic: the static arrays are near the 48 KB limit)
+    double (*s_x)[16 * kTile] = reinterpret_cast<double (*)[16 * kTile]>(s_x_dyn);
     __shared__ __align__(128) double s_out[TST ? 2 : 1][TST ? 16 * kTile : 2];   // [buffer][warp][k][lane] = the tile's 16 KB of a slot
     const int tid = threadIdx.x;
     const int so = (tid >> 5) * 16 * kWarp + (tid & 31);
     int prev_dst = -1;
     long long prev_tile_off = 0;
+    for (int k = tid; k < (D.su + 1) * 4; k += kTile) s_tip[k] = D.tip_lh[k];
     const long long ntiles = D.Ppad / kTile;
     constexpr int kStageVec = kStage4 / 2;   // double2 elements per staging block
     for (;;) {
@@ -743,6 +745,11 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
         const int ts_off = (tid >> 5) * 32 + (tid & 7) * 4;   // TSM: lanes 0..7 of a warp copy the warp's 32 states, 4 bytes each
         {   // tip states of op 0
             const int4 h = *reinterpret_cast<const int4 *>(stage);   // global: the shared copy is not visible yet
+            if (XSM && h.y == 2) {
+                const double *src = D.partial + (long long)h.w * D.slot_stride + tile * (16LL * kTile);
+#pragma unroll
+                for (int m = 0; m < 8; m++) cp_async16(&s_x[0][2 * (tid + kTile * m)], src + 2 * (tid + kTile * m));
+            }
             if (TSM) {
                 if ((tid & 31) < 8) {
                     if (h.y <= 1) cp_async4(&s_ts[0][1][ts_off], D.tips + (long long)h.w * D.Ppad + tile * kTile + ts_off);
@@ -791,7 +798,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             if (ncase == 2) {
                 const double *Bp = D.partial + (long long)bid * D.slot_stride + pb;
 #pragma unroll
-                for (int k = 0; k < 16; k++) X[k] = (DBG & 2) ? cur[15 - k] + 1e-3 : TST ? __ldcg(Bp + k * kWarp) : Bp[k * kWarp];
+                for (int k = 0; k < 16; k++) X[k] = (DBG & 2) ? cur[15 - k] + 1e-3 : XSM ? s_x[o & 1][so + k * kWarp] : TST ? __ldcg(Bp + k * kWarp) : Bp[k * kWarp];
 #pragma unroll
                 for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = D.scale[(long long)bid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
             } else {
@@ -823,9 +830,15 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                     if (hn.y == 0) sA_next = D.tips[(long long)hn.z * D.Ppad + p];
                 }
                 if (hn.y == 2) {
-                    const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
+                    if (XSM) {
+                        const double *src = D.partial + (long long)hn.w * D.slot_stride + tile * (16LL * kTile);
 #pragma unroll
-                    for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(Bn + k * kWarp);
+                        for (int m = 0; m < 8; m++) cp_async16(&s_x[(o + 1) & 1][2 * (tid + kTile * m)], src + 2 * (tid + kTile * m));
+                    } else {
+                        const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
+#pragma unroll
+                        for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(Bn + k * kWarp);
+                    }
                 }
                 if (hn.y >= 1 && n_loadA) {
                     const double *An = D.partial + (long long)hn.z * D.slot_stride + pb;
@@ -833,7 +846,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                     for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(An + k * kWarp);
                 }
             }
-            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 36 + 16 * kTab4;
+            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
             double *Op = D.partial + (long long)dst * D.slot_stride + pb;
             unsigned mhi = 0;
 #pragma unroll
@@ -845,9 +858,21 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 4; x++)
                         fa[x] = fma(M.evec[x * 4 + 3], a3, fma(M.evec[x * 4 + 2], a2, fma(M.evec[x * 4 + 1], a1, M.evec[x * 4] * a0)));
+                } else if (sA < 4) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fa[x] = tabA[c * 16 + x * 4 + sA];
+                } else if (sA == D.su) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fa[x] = 1.0;
                 } else {
 #pragma unroll
-                    for (int x = 0; x < 4; x++) fa[x] = tabA[(c * 4 + x) * kTab4 + sA];
+                    for (int x = 0; x < 4; x++) {
+                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expA[c * 4 + 0]), s_tip[sA * 4 + 0]);
+                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expA[c * 4 + 1]), s_tip[sA * 4 + 1]);
+                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expA[c * 4 + 2]), s_tip[sA * 4 + 2]);
+                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expA[c * 4 + 3]), s_tip[sA * 4 + 3]);
+                        fa[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
+                    }
                 }
                 if (ncase == 2) {
                     const double2 e01 = *reinterpret_cast<const double2 *>(expB + c * 4), e23 = *reinterpret_cast<const double2 *>(expB + c * 4 + 2);
@@ -855,9 +880,21 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
 #pragma unroll
                     for (int x = 0; x < 4; x++)
                         fb[x] = fma(M.evec[x * 4 + 3], b3, fma(M.evec[x * 4 + 2], b2, fma(M.evec[x * 4 + 1], b1, M.evec[x * 4] * b0)));
+                } else if (sB < 4) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fb[x] = tabB[c * 16 + x * 4 + sB];
+                } else if (sB == D.su) {
+#pragma unroll
+                    for (int x = 0; x < 4; x++) fb[x] = 1.0;
                 } else {
 #pragma unroll
-                    for (int x = 0; x < 4; x++) fb[x] = tabB[(c * 4 + x) * kTab4 + sB];
+                    for (int x = 0; x < 4; x++) {
+                        double q0 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 0], expB[c * 4 + 0]), s_tip[sB * 4 + 0]);
+                        double q1 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 1], expB[c * 4 + 1]), s_tip[sB * 4 + 1]);
+                        double q2 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 2], expB[c * 4 + 2]), s_tip[sB * 4 + 2]);
+                        double q3 = __dmul_rn(__dmul_rn(M.evec[x * 4 + 3], expB[c * 4 + 3]), s_tip[sB * 4 + 3]);
+                        fb[x] = __dadd_rn(__dadd_rn(q0, q1), __dadd_rn(q2, q3));
+                    }
                 }
                 const double t0 = fa[0] * fb[0], t1 = fa[1] * fb[1], t2 = fa[2] * fb[2], t3 = fa[3] * fb[3];
                 unsigned chi = 0;
