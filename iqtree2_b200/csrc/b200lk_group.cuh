@@ -87,6 +87,7 @@ template <int C, bool SAFE>
 __global__ void __launch_bounds__(kTile, (C <= 4 ? 3 : 2)) k_group_walk_n4(const GroupEntry *E, int n, int total_items, unsigned long long *counter) {
     __shared__ __align__(16) double s_stage[3][stage4_doubles(C)];
     __shared__ double s_tip[kMaxLeafRows4 * 4];
+    __shared__ __align__(16) unsigned char s_ts[2][2][kTile];
     __shared__ Dev sD;
     __shared__ int s_item, s_ent;
     const int tid = threadIdx.x;
@@ -105,7 +106,7 @@ __global__ void __launch_bounds__(kTile, (C <= 4 ? 3 : 2)) k_group_walk_n4(const
         __syncthreads();
         for (int k = tid; k < (sD.su + 1) * 4; k += kTile) s_tip[k] = sD.tip_lh[k];
         __syncthreads();
-        if (ge.nops > 0) walk4_tile<C, SAFE>(sD, M, sD.opinfo, ge.nops, (long long)(s_item - ge.item0), s_stage, s_tip);
+        if (ge.nops > 0) walk4_tile<C, SAFE>(sD, M, sD.opinfo, ge.nops, (long long)(s_item - ge.item0), s_stage, s_tip, s_ts);
     }
 }
 

@@ -62,7 +62,7 @@ __host__ __device__ constexpr int walk4_min_blocks() { return C <= 4 ? 4 : C <= 
 // kernel's parameters) or in shared memory / registers (a member of a grouped launch).
 template <int C, bool SAFE>
 __device__ __forceinline__ void walk4_tile(const Dev &D, const Model4 &M, const double *stage, const int nops, const long long tile,
-                                           double (*s_stage)[stage4_doubles(C)], const double *s_tip) {
+                                           double (*s_stage)[stage4_doubles(C)], const double *s_tip, unsigned char (*s_ts)[2][kTile]) {
     constexpr int KS = stage4_doubles(C), KSV = KS / 2;   // doubles / 16-byte chunks per staging block
     constexpr int NS = SAFE ? C : 1;
     const int tid = threadIdx.x;
@@ -91,11 +91,15 @@ __device__ __forceinline__ void walk4_tile(const Dev &D, const Model4 &M, const 
     for (int k = 0; k < 4 * C; k++) cur[k] = 0.0;
 #pragma unroll
     for (int c = 0; c < NS; c++) cursc[c] = 0;
-    int sA_next = 0, sB_next = 0;
+    // the next op's tip states travel global -> shared with cp.async, lanes 0..7 of a warp 4 bytes each: loaded into registers one op
+    // ahead, the load shared a scoreboard with the op's first shared-memory consumer and stalled it (see k_walk_n4c4)
+    const int ts_off = (tid >> 5) * 32 + (tid & 7) * 4;
     {
         const int4 h = *reinterpret_cast<const int4 *>(stage);   // global: the shared copy has not landed yet
-        if (h.y <= 1) sB_next = D.tips[(long long)h.w * D.Ppad + p];
-        if (h.y == 0) sA_next = D.tips[(long long)h.z * D.Ppad + p];
+        if ((tid & 31) < 8) {
+            if (h.y <= 1) cp_async4(&s_ts[0][1][ts_off], D.tips + (long long)h.w * D.Ppad + tile * kTile + ts_off);
+            if (h.y == 0) cp_async4(&s_ts[0][0][ts_off], D.tips + (long long)h.z * D.Ppad + tile * kTile + ts_off);
+        }
     }
     int buf = 0;
     for (int o = 0; o < nops; o++) {
@@ -107,7 +111,7 @@ __device__ __forceinline__ void walk4_tile(const Dev &D, const Model4 &M, const 
         const int h_loadA = *reinterpret_cast<const int *>(st + 2);
         const int dst = h0.x, ncase = h0.y, aid = h0.z, bid = h0.w;
         if (o + 2 < nops) stage_copy(s_stage[buf2], stage + (size_t)(o + 2) * KS);
-        const int sA = sA_next, sB = sB_next;
+        const int sA = ncase == 0 ? (int)s_ts[o & 1][0][tid] : 0, sB = ncase <= 1 ? (int)s_ts[o & 1][1][tid] : 0;
         const double *Bp = D.partial + (long long)bid * D.slot_stride + pb;
         const uint16_t *Bs = D.scale + (long long)bid * D.scale_stride + sb;
         unsigned scB[NS];
@@ -133,8 +137,10 @@ __device__ __forceinline__ void walk4_tile(const Dev &D, const Model4 &M, const 
             const double *sn = s_stage[buf1];
             const int4 hn = *reinterpret_cast<const int4 *>(sn);
             const int n_loadA = *reinterpret_cast<const int *>(sn + 2);
-            if (hn.y <= 1) sB_next = D.tips[(long long)hn.w * D.Ppad + p];
-            if (hn.y == 0) sA_next = D.tips[(long long)hn.z * D.Ppad + p];
+            if ((tid & 31) < 8) {
+                if (hn.y <= 1) cp_async4(&s_ts[(o + 1) & 1][1][ts_off], D.tips + (long long)hn.w * D.Ppad + tile * kTile + ts_off);
+                if (hn.y == 0) cp_async4(&s_ts[(o + 1) & 1][0][ts_off], D.tips + (long long)hn.z * D.Ppad + tile * kTile + ts_off);
+            }
             if (hn.y == 2) {
                 const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
 #pragma unroll
@@ -218,6 +224,7 @@ __global__ void __launch_bounds__(kTile, walk4_min_blocks<C>()) k_walk_n4(Dev D,
                                                                          unsigned long long *counter) {
     __shared__ __align__(16) double s_stage[3][stage4_doubles(C)];
     __shared__ double s_tip[kMaxLeafRows4 * 4];
+    __shared__ __align__(16) unsigned char s_ts[2][2][kTile];
     __shared__ long long s_item;
     const int tid = threadIdx.x;
     for (int k = tid; k < (D.su + 1) * 4; k += kTile) s_tip[k] = D.tip_lh[k];
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(kTile, walk4_min_blocks<C>()) k_walk_n4(Dev D,
         __syncthreads();
         const long long tile = s_item;
         if (tile >= ntiles) break;
-        walk4_tile<C, SAFE>(D, M, stage, nops, tile, s_stage, s_tip);
+        walk4_tile<C, SAFE>(D, M, stage, nops, tile, s_stage, s_tip, s_ts);
     }
 }
 
