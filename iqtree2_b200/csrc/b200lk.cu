@@ -128,6 +128,7 @@ struct b200lk_engine {
     // site-specific models (b200lk_site.inc): eval | evec | inv_evec of every pattern, warp-interleaved
     bool site = false;
     double *d_site = nullptr;
+    unsigned site_attr = 0, xsm_attr = 0;   // cudaFuncSetAttribute done on this engine's device (k_site_walk20, k_walk_n4c4 variant 26)
     // mixed branch lengths (b200lk_mixlen.inc): the [rows][ncat] table, the gradient / Hessian pass's per-block sums
     double *d_mixlen = nullptr, *d_mixlen_red = nullptr;
     size_t mixlen_cap = 0;
@@ -685,8 +686,7 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
         void *args[] = {(void *)&e->d, (void *)&M, (void *)&e->d_opinfo, (void *)&nops, (void *)&e->d_counter};
         const size_t xsm = v == 9 ? sizeof(double) * 2 * 16 * kTile : 0;   // variant 26: two sibling-CLV buffers in dynamic shared memory
         if (xsm) {
-            static bool xsm_attr[2] = {false, false};
-            if (!xsm_attr[safe ? 1 : 0]) { CK(cudaFuncSetAttribute(kernels[v * 2 + (safe ? 1 : 0)], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm)); xsm_attr[safe ? 1 : 0] = true; }
+            if (!(e->xsm_attr & (1u << (safe ? 1 : 0)))) { CK(cudaFuncSetAttribute(kernels[v * 2 + (safe ? 1 : 0)], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm)); e->xsm_attr |= 1u << (safe ? 1 : 0); }
         }
         if (v >= 0) CK(cudaLaunchKernel(kernels[v * 2 + (safe ? 1 : 0)], dim3(grid), dim3(kTile), args, xsm, e->stream));
     }

@@ -69,3 +69,37 @@ def test_reference_phylotree_on_two_gpus():
     for k in bc:
         assert abs(bc[k] - bg[k]) < 1e-6
     cpu.close(); gpu.close()
+
+
+def test_multi_device_mixlen_and_site_models():
+    """mixed branch lengths (every shard takes the table; gradient / Hessian summed in device order) and site-specific models (every
+    shard takes its pattern slice of the eigensystems) on a two-device engine"""
+    if _ndev() < 2:
+        pytest.skip("needs at least two GPUs")
+    from test_mixlen_cpu import make_mixlen_case, mixlen_engine, plan_rows
+    tree, model, pat, freq, invar = make_mixlen_case("dna", 4, ntaxa=12, nsites=1500, seed=61)
+    one = mixlen_engine(LikelihoodEngine, tree, model, pat, freq, invar, False, device=0)
+    two = mixlen_engine(LikelihoodEngine, tree, model, pat, freq, invar, False, device=-2)
+    ops, a, b, row = plan_rows(tree, 3)
+    l1, l2 = one.branch_logl(ops, a, b, row), two.branch_logl(ops, a, b, row)
+    assert abs(l1 - l2) < 1e-9 * abs(l1)
+    np.testing.assert_array_equal(one.get_pattern_lh(), two.get_pattern_lh())
+    g1, H1, ll1 = one.branch_derv_mixlen(ops[:0], a, b, row)
+    g2, H2, ll2 = two.branch_derv_mixlen(ops[:0], a, b, row)
+    np.testing.assert_allclose(g2, g1, rtol=1e-10, atol=1e-9)
+    np.testing.assert_allclose(H2, H1, rtol=1e-10, atol=1e-8)
+    assert abs(ll1 - ll2) < 1e-9 * abs(ll1)
+    for cur in range(model.ncat):
+        np.testing.assert_allclose(two.branch_derv_mixlen_cur(ops[:0], a, b, row, cur), one.branch_derv_mixlen_cur(ops[:0], a, b, row, cur), rtol=1e-10, atol=1e-9)
+    one.close(); two.close()
+
+    from test_site_model_cpu import engine, make_site_case
+    tree, model, pat, freq, invar = make_site_case(20, 4, ntaxa=11, nptn=777, seed=3)
+    one = engine(LikelihoodEngine, tree, model, pat, freq, invar, False, device=0)
+    two = engine(LikelihoodEngine, tree, model, pat, freq, invar, False, device=-2)
+    ops, a, b, L = plan.plan_branch(tree, 3)
+    l1, l2 = one.branch_logl(ops, a, b, L), two.branch_logl(ops, a, b, L)
+    assert abs(l1 - l2) < 1e-10 * abs(l1)
+    np.testing.assert_array_equal(one.get_pattern_lh(), two.get_pattern_lh())
+    np.testing.assert_allclose(two.branch_derv(ops[:0], a, b, L), one.branch_derv(ops[:0], a, b, L), rtol=1e-10)
+    one.close(); two.close()
