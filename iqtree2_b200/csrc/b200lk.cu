@@ -660,7 +660,7 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
     if (e->profiling) cudaEventRecord(e->ev[4], e->stream);
     {   // kernel_variant (A/B): 0 = per-category direct stores, 1 = TMA bulk stores from shared memory, 2 = one burst per op
         const bool safe = e->cfg.safe_numeric != 0;
-        static const void *const kernels[20] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
+        static const void *const kernels[22] = {(const void *)k_walk_n4c4<false, 1>, (const void *)k_walk_n4c4<true, 1>,
                                                 (const void *)k_walk_n4c4<false, 2>, (const void *)k_walk_n4c4<true, 2>,
                                                 (const void *)k_walk_n4c4<false, 0>, (const void *)k_walk_n4c4<true, 0>,
                                                 // variants 20..23 (A/B): L2 prefetches none / tip rows / sibling CLVs / both
@@ -672,8 +672,10 @@ static int enqueue_walk4(b200lk_engine *e, const b200lk_op *ops, int32_t nops, c
                                                 (const void *)k_walk_n4c4<false, 1, 0, 5>, (const void *)k_walk_n4c4<true, 1, 0, 5>,
                                                 (const void *)k_walk_n4c4<false, 1, 0, 4>, (const void *)k_walk_n4c4<true, 1, 0, 4>,
                                                 // 26: + the next op's sibling CLV through shared memory (cp.async one op ahead)
-                                                (const void *)k_walk_n4c4<false, 1, 0, 12>, (const void *)k_walk_n4c4<true, 1, 0, 12>};
-        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : (e->kernel_variant >= 20 && e->kernel_variant <= 26) ? e->kernel_variant - 17 : 0;
+                                                (const void *)k_walk_n4c4<false, 1, 0, 12>, (const void *)k_walk_n4c4<true, 1, 0, 12>,
+                                                // 27: the default without the L1 prefetches of the next op's CLV operands
+                                                (const void *)k_walk_n4c4<false, 1, 0, 20>, (const void *)k_walk_n4c4<true, 1, 0, 20>};
+        int v = (e->kernel_variant >= 0 && e->kernel_variant <= 2) ? e->kernel_variant : (e->kernel_variant >= 20 && e->kernel_variant <= 27) ? e->kernel_variant - 17 : 0;
 #ifdef B200LK_DIAG
         static const void *const dbg_kernels[3] = {(const void *)k_walk_n4c4<false, 2, 1>, (const void *)k_walk_n4c4<false, 2, 2>,
                                                    (const void *)k_walk_n4c4<false, 2, 3>};   // variants 6..8: no stores / no loads / neither

@@ -694,7 +694,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 //            the kernel's time ~ compute + store time instead of their maximum).  CLV loads then bypass L1 (ld.global.cg): the
 //            bulk store writes through the async proxy, and the slot's lines may sit in this SM's L1 from an earlier read.
 // DBG (diagnosis builds, wrong results): bit 0 no CLV stores, bit 1 no sibling loads
-template <bool SAFE, int STORE = 2, int DBG = 0, int PF = 4>   // PF: bit 0 = L2 prefetch of tip rows, bit 1 = of sibling CLVs (slower: A/B only), bit 2 = tip states through shared memory
+template <bool SAFE, int STORE = 2, int DBG = 0, int PF = 20>   // PF: bit 0 = L2 prefetch of tip rows, bit 1 = of sibling CLVs (slower: A/B only), bit 2 = tip states through shared memory
 __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_constant__ Model4 M, const double *stage, int nops,
                                                        unsigned long long *counter) {
     // 3-deep ring of staging blocks: while op o computes, block o+1 is already resident (its header steers the
@@ -834,13 +834,13 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                         const double *src = D.partial + (long long)hn.w * D.slot_stride + tile * (16LL * kTile);
 #pragma unroll
                         for (int m = 0; m < 8; m++) cp_async16(&s_x[(o + 1) & 1][2 * (tid + kTile * m)], src + 2 * (tid + kTile * m));
-                    } else {
+                    } else if (!(PF & 16)) {   // PF bit 4: no L1 prefetches (A/B: ncu shows the sibling loads missing L1 regardless)
                         const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
 #pragma unroll
                         for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(Bn + k * kWarp);
                     }
                 }
-                if (hn.y >= 1 && n_loadA) {
+                if (hn.y >= 1 && n_loadA && !(PF & 16)) {
                     const double *An = D.partial + (long long)hn.z * D.slot_stride + pb;
 #pragma unroll
                     for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(An + k * kWarp);

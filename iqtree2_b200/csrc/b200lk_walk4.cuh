@@ -141,16 +141,9 @@ __device__ __forceinline__ void walk4_tile(const Dev &D, const Model4 &M, const 
                 if (hn.y <= 1) cp_async4(&s_ts[(o + 1) & 1][1][ts_off], D.tips + (long long)hn.w * D.Ppad + tile * kTile + ts_off);
                 if (hn.y == 0) cp_async4(&s_ts[(o + 1) & 1][0][ts_off], D.tips + (long long)hn.z * D.Ppad + tile * kTile + ts_off);
             }
-            if (hn.y == 2) {
-                const double *Bn = D.partial + (long long)hn.w * D.slot_stride + pb;
-#pragma unroll
-                for (int k = 0; k < 4 * C; k++) prefetch_l1(Bn + k * kWarp);
-            }
-            if (hn.y >= 1 && n_loadA) {
-                const double *An = D.partial + (long long)hn.z * D.slot_stride + pb;
-#pragma unroll
-                for (int k = 0; k < 4 * C; k++) prefetch_l1(An + k * kWarp);
-            }
+            // (no L1 prefetch of the next op's CLV operands: the loads missed L1 regardless and the prefetch instructions alone cost
+            // 4.6 % of k_walk_n4c4's time, gpurun_out/r2_25 variants 0 / 27)
+            (void)n_loadA;
         }
         const double *expA = st + 4, *expB = st + 4 + 4 * C, *tabA = st + 4 + 8 * C, *tabB = st + 4 + 24 * C;
         double *Op = D.partial + (long long)dst * D.slot_stride + pb;

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out/r2_25
 O=gpurun_out/r2_25
 timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "parity_small or deep" 2>&1 | tail -3
-for v in 20 0 26 20 0 26; do
+for v in 0 27 0 27; do
 timeout 600 python bench.py --steps 10 --warmup 3 --variant $v --no-cpu-baseline --no-secondary > $O/cfg2_v$v.json 2> $O/cfg2_v$v.err; echo "v$v rc=$?"; tail -c 300 $O/cfg2_v$v.err
 python - <<PY
 import json

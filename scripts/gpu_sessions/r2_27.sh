@@ -13,3 +13,9 @@ for f in ("dna_c1","dna_c8","cfg5"):
     d=json.loads([l for l in open("$O/%s.json"%f) if l.startswith("{")][-1])
     print(f, "value %.2f ms %.3f launch_ms %.3f" % (d["value"], d["ms_per_step"], d.get("roofline",{}).get("launch_ms",0) or 0))
 PY
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-secondary > $O/cfg2.json 2> $O/cfg2.err; echo "cfg2 rc=$?"
+python - <<PY
+import json
+d=json.loads([l for l in open("$O/cfg2.json") if l.startswith("{")][-1])
+print("cfg2 value %.2f ms %.3f launch_ms %.3f" % (d["value"], d["ms_per_step"], d["roofline"]["launch_ms"]))
+PY
