@@ -606,10 +606,13 @@ struct WalkJob4 {      // host -> k_walk_info_n4c4
     int32_t dst, ncase, aid, bid, loadA, pad;
 };
 
-// staging block per op: header (4 doubles) | expA[16] | expB[16] | tabA[64] | tabB[64]
+// staging block per op: header (kHdr4 doubles: 8 ints, then 6 byte offsets — the 64-bit products slot * stride / row * Ppad that every
+// thread of every tile would otherwise recompute per op, ~11 integer instructions each) | expA[16] | expB[16] | tabA[64] | tabB[64]
 // (tables for EVERY state code instead of the four nucleotides — 676 doubles per block, no branch on the tip state — were measured:
 // 9 % slower on config 2, the block is re-staged per tile and op and 5.4 KB per 128 patterns is a third of the CLV it produces)
-constexpr int kStage4 = 4 + 16 + 16 + 64 + 64;   // 164 doubles = 1312 bytes (16-byte multiple)
+constexpr int kHdr4 = 10;
+constexpr int kStage4 = kHdr4 + 16 + 16 + 64 + 64;   // 170 doubles = 1360 bytes (16-byte multiple)
+struct StageOff4 { long long dst_clv, b_clv, dst_sc, b_sc, tip_a, tip_b; };   // bytes: CLV slot of dst / sibling, their scale vectors, tip rows
 struct StageHdr4 { int32_t dst, ncase, aid, bid, loadA, pad0, pad1, pad2; };
 constexpr int kPfAhead4 = 4;   // ops between an L2 prefetch and the use of the data (an op of one tile takes ~2 us at full load)
 
@@ -626,7 +629,17 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
         const double len_child = D.cat_rate[c] * resolve_len_cat(D, ch ? job.lenB : job.lenA, c);   // :1017
         const double v = exp(D.eval[i] * len_child);                           // :1022
         s_exp[ch][k] = v;
-        st[4 + ch * 16 + k] = v;
+        st[kHdr4 + ch * 16 + k] = v;
+    }
+    if (t == 1) {
+        StageOff4 o;
+        o.dst_clv = (long long)job.dst * D.slot_stride * (long long)sizeof(double);
+        o.b_clv = job.ncase == 2 ? (long long)job.bid * D.slot_stride * (long long)sizeof(double) : 0;
+        o.dst_sc = (long long)job.dst * D.scale_stride * (long long)sizeof(uint16_t);
+        o.b_sc = job.ncase == 2 ? (long long)job.bid * D.scale_stride * (long long)sizeof(uint16_t) : 0;
+        o.tip_a = job.ncase == 0 ? (long long)job.aid * D.Ppad : 0;
+        o.tip_b = job.ncase <= 1 ? (long long)job.bid * D.Ppad : 0;
+        *reinterpret_cast<StageOff4 *>(st + 4) = o;
     }
     if (t == 0) {
         // pad0..2: what the op kPfAhead4 ops further on will read from memory that may have left L2 — its tip rows (B, A) and its
@@ -656,7 +669,7 @@ __global__ void __launch_bounds__(64) k_walk_info_n4c4(Dev D, const WalkJob4 *jo
             double p3 = __dmul_rn(__dmul_rn(D.evec[x * 4 + 3], s_exp[ch][c * 4 + 3]), tip[3]);
             v = __dadd_rn(__dadd_rn(p0, p1), __dadd_rn(p2, p3));
         }
-        st[36 + ch * 64 + t] = v;
+        st[kHdr4 + 32 + ch * 64 + t] = v;
     }
 }
 
@@ -776,6 +789,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             const int buf1 = buf == 2 ? 0 : buf + 1, buf2 = buf1 == 2 ? 0 : buf1 + 1;
             const int4 h0 = *reinterpret_cast<const int4 *>(st);
             const int4 h1 = *reinterpret_cast<const int4 *>(st + 2);
+            const StageOff4 &off = *reinterpret_cast<const StageOff4 *>(st + 4);
             const int h_loadA = h1.x;
             const int dst = h0.x, ncase = h0.y, aid = h0.z, bid = h0.w;
             if (PF && tid == 0) {
@@ -796,11 +810,12 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             double X[16];
             unsigned scB[SAFE ? 4 : 1];
             if (ncase == 2) {
-                const double *Bp = D.partial + (long long)bid * D.slot_stride + pb;
+                const double *Bp = reinterpret_cast<const double *>(reinterpret_cast<const char *>(D.partial) + off.b_clv) + pb;
 #pragma unroll
                 for (int k = 0; k < 16; k++) X[k] = (DBG & 2) ? cur[15 - k] + 1e-3 : XSM ? s_x[o & 1][so + k * kWarp] : TST ? __ldcg(Bp + k * kWarp) : Bp[k * kWarp];
 #pragma unroll
-                for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = D.scale[(long long)bid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+                for (int c = 0; c < (SAFE ? 4 : 1); c++)
+                    scB[c] = reinterpret_cast<const uint16_t *>(reinterpret_cast<const char *>(D.scale) + off.b_sc)[sb + (SAFE ? c * kWarp : 0)];
             } else {
 #pragma unroll
                 for (int c = 0; c < (SAFE ? 4 : 1); c++) scB[c] = 0;
@@ -822,8 +837,9 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                 const int n_loadA = *reinterpret_cast<const int *>(sn + 2);
                 if (TSM) {
                     if ((tid & 31) < 8) {
-                        if (hn.y <= 1) cp_async4(&s_ts[(o + 1) & 1][1][ts_off], D.tips + (long long)hn.w * D.Ppad + tile * kTile + ts_off);
-                        if (hn.y == 0) cp_async4(&s_ts[(o + 1) & 1][0][ts_off], D.tips + (long long)hn.z * D.Ppad + tile * kTile + ts_off);
+                        const StageOff4 &offn = *reinterpret_cast<const StageOff4 *>(sn + 4);
+                        if (hn.y <= 1) cp_async4(&s_ts[(o + 1) & 1][1][ts_off], D.tips + offn.tip_b + tile * kTile + ts_off);
+                        if (hn.y == 0) cp_async4(&s_ts[(o + 1) & 1][0][ts_off], D.tips + offn.tip_a + tile * kTile + ts_off);
                     }
                 } else {
                     if (hn.y <= 1) sB_next = D.tips[(long long)hn.w * D.Ppad + p];
@@ -846,8 +862,8 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
                     for (int k = 0; k < 16; k++) if (!TST) prefetch_l1(An + k * kWarp);
                 }
             }
-            const double *expA = st + 4, *expB = st + 20, *tabA = st + 36, *tabB = st + 100;
-            double *Op = D.partial + (long long)dst * D.slot_stride + pb;
+            const double *expA = st + kHdr4, *expB = st + kHdr4 + 16, *tabA = st + kHdr4 + 32, *tabB = st + kHdr4 + 96;
+            double *Op = reinterpret_cast<double *>(reinterpret_cast<char *>(D.partial) + off.dst_clv) + pb;
             unsigned mhi = 0;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
@@ -944,7 +960,7 @@ __global__ void __launch_bounds__(kTile, 4) k_walk_n4c4(Dev D, const __grid_cons
             }
 #pragma unroll
             for (int c = 0; c < (SAFE ? 4 : 1); c++)
-                D.scale[(long long)dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
+                reinterpret_cast<uint16_t *>(reinterpret_cast<char *>(D.scale) + off.dst_sc)[sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
             buf = buf1;
             prev_dst = dst;
             prev_tile_off = tile * (16LL * kTile);
