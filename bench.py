@@ -526,7 +526,12 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         mem_mode = f"LM_MEM_SAVE ({nslots - 2} of {ntaxa - 2} CLV slots recycled by the host planner)"
 
     eng = LikelihoodEngine(model, ntaxa, my_nptn, nslots=nslots, safe_numeric=safe, device=local_rank, schedule=args.schedule)
-    stream = torch.cuda.current_stream()
+    # An explicit stream, made torch's current one: the engine queues on it (a null handle — torch's legacy default stream — would
+    # mean "the engine's own stream" to b200lk_set_stream) and torch's NCCL collectives order themselves behind the CURRENT stream, so
+    # the all-reduce of the scalars waits for the evaluation that produces them
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     if args.variant:
         eng.set_schedule(10 + args.variant)
     eng.set_stream(stream.cuda_stream)
@@ -547,7 +552,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
     import dataclasses
     model_step = dataclasses.replace(model, site=None) if site else model
 
-    def one_eval(upload_model):
+    def one_eval(upload_model, L=L):
         """clearAllPartialLH -> computeLikelihoodBranch -> computeLikelihoodDerv, host buffers in, scalars out."""
         if upload_model:
             eng.set_model(model_step)  # eigensystem + rates re-sent as a ModelFinder / BFGS step would
@@ -684,6 +689,16 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         per_rank = parts.view(world, 3).cpu().numpy()
         tot = per_rank.sum(axis=0)
         ok_sum = bool(abs(tot[0] - res_run["result"][0]) <= 1e-9 * abs(tot[0]))
+        # every timed step evaluates the same thing, so a collective that read the scalars of the PREVIOUS step would pass the test
+        # above: one more evaluation at another length of the evaluation branch, reduced and summed the same two ways
+        (ll2, df2, ddf2), _, _, local2 = one_eval(False, L * 1.37)
+        parts2 = torch.zeros(world * 3, dtype=torch.float64, device="cuda")
+        parts2[rank * 3:(rank + 1) * 3] = torch.tensor(local2, dtype=torch.float64)
+        dist.all_reduce(parts2)
+        tot2 = parts2.view(world, 3).cpu().numpy().sum(axis=0)
+        ok_fresh = bool(abs(tot2[0] - ll2) <= 1e-9 * abs(tot2[0]) and abs(tot2[1] - df2) <= 1e-7 * max(1.0, abs(tot2[1])) and abs(ll2 - res_run["result"][0]) > 1e-6)
+        ok_sum = ok_sum and ok_fresh
+        one_eval(False)   # back to the workload's evaluation (the per-pattern values below are its)
         # an independent engine on rank 0 recomputes the first patterns of the LAST rank's shard
         sl = int(min(2048, nptn - min((world - 1) * per, nptn)))
         lh_last = torch.zeros(max(sl, 1), dtype=torch.float64, device="cuda")
@@ -700,6 +715,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
             slice_diff = float(np.max(np.abs(ref - lh_last.cpu().numpy()) / np.abs(ref)))
             e2.close()
         check = {"per_rank_logl": [float(x) for x in per_rank[:, 0]], "sum_of_ranks_equals_allreduce": ok_sum,
+                 "fresh_evaluation_at_another_length": {"allreduced_logl": float(ll2), "sum_of_ranks": float(tot2[0]), "ok": ok_fresh},
                  "slice_recomputed_on_rank0": {"rank": world - 1, "patterns": sl, "max_rel_diff": slice_diff}}
         if rank == 0:
             assert ok_sum, ("all-reduced logL differs from the sum of the per-rank values", tot[0], res_run["result"][0])
