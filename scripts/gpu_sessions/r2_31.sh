@@ -5,13 +5,13 @@ O=gpurun_out/r2_31
 run() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus $1 "${@:3}"; }
 run 8 29511 --steps 20 --warmup 3 > $O/bench_n8.json 2> $O/bench_n8.err; echo "n8 rc=$?"; tail -c 200 $O/bench_n8.err
 run 4 29512 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_n4.json 2> $O/bench_n4.err; echo "n4 rc=$?"
-run 2 29513 --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_n2.json 2> $O/bench_n2.err; echo "n2 rc=$?"
-python bench.py --steps 20 --warmup 3 --no-cpu-baseline > $O/bench_n1.json 2> $O/bench_n1.err; echo "n1 rc=$?"
+
+
 python - <<PY
 import json
 def last(f):
     return json.loads([l for l in open(f) if l.startswith("{")][-1])
-for f in ("bench_n1","bench_n2","bench_n4","bench_n8"):
+for f in ("bench_n4","bench_n8"):
     try:
         d=last("$O/%s.json"%f)
         c=d.get("check") or {}
