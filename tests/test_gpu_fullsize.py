@@ -166,3 +166,54 @@ def test_config5_500_partitions_against_the_reference_per_partition():
     assert abs(ll - ll_ref) < 1e-10 * abs(ll_ref), (ll, ll_ref)
     assert abs(df - df_ref) < 1e-9 * max(mag, 1.0), (df, df_ref)
     assert abs(ddf - ddf_ref) < 1e-8 * abs(ddf_ref), (ddf, ddf_ref)
+
+
+def test_site_specific_workload_against_the_live_reference():
+    """the bench workload aa_100x20k_pmsf_g4 (one frequency profile per pattern + G4) at its full size: k_site_walk20 against the
+    reference's own SITE_MODEL kernel on every pattern — per-pattern log-likelihood 1e-11, logL / derivatives 1e-9, the pulley principle"""
+    from oracle import ref_engine
+    if not ref_engine.available():
+        pytest.skip("oracle/_ref/libiqref.so not built")
+    ntaxa, nptn, mk, _ = bench.WORKLOADS["aa_100x20k_pmsf_g4"]
+    model = mk()
+    tree, tips, freq, _ = bench.make_inputs(ntaxa, nptn, model)
+    g = LikelihoodEngine(model, ntaxa, nptn)
+    g.set_tip_states(tips); g.set_pattern_freq(freq); g.set_pattern_invar(np.zeros(nptn))
+    r = ref_engine.RefTree(tree, model, tips, freq, nthreads=8)
+    ops, a, b, L = plan.plan_branch(tree, plan.pendant_branch_of(tree, 0))
+    ll_r, plh_r = r.branch_logl(0)
+    ll_g = g.branch_logl(ops, a, b, L)
+    assert abs(ll_g - ll_r) < 1e-9 * abs(ll_r), (ll_g, ll_r)
+    np.testing.assert_allclose(g.get_pattern_lh(), plh_r, rtol=1e-11, atol=0)
+    np.testing.assert_allclose(g.branch_derv(ops[:0], a, b, L), r.branch_derv(0), rtol=1e-9)
+    ops2, a2, b2, L2 = plan.plan_branch(tree, len(tree.lengths) // 2)
+    g.theta_reset()
+    assert abs(g.branch_logl(ops2, a2, b2, L2) - ll_r) < 1e-9 * abs(ll_r)
+    g.close(); r.close()
+
+
+def test_mixed_branch_lengths_with_equal_classes_equal_plain_lengths_at_config3_size():
+    """config 3 (protein 200 x 100 000, LG+G4) evaluated with a mixlen table whose four classes all hold the branch's own length: the
+    tuned 20-state walker reads its lengths through the table and must return the plain engine's numbers bit for bit; the gradient
+    over the classes sums to the scalar derivative"""
+    ntaxa, nptn, mk, _ = bench.WORKLOADS["aa_200x100k_lg_g4"]
+    model = mk()
+    tree, tips, freq, _ = bench.make_inputs(ntaxa, nptn, model)
+    plain = LikelihoodEngine(model, ntaxa, nptn)
+    mixl = LikelihoodEngine(model, ntaxa, nptn)
+    for e in (plain, mixl):
+        e.set_tip_states(tips); e.set_pattern_freq(freq); e.set_pattern_invar(np.zeros(nptn))
+    lengths = np.asarray(tree.lengths, dtype=np.float64)
+    mixl.set_mixlen(np.repeat(lengths[:, None], model.ncat, axis=1))
+    br = plan.pendant_branch_of(tree, 0)
+    ops, a, b, L = plan.plan_branch(tree, br)
+    ops_r, a_r, b_r, row = plan.plan_branch(tree, br, lengths=np.arange(len(lengths), dtype=np.float64))
+    l1, l2 = plain.branch_logl(ops, a, b, L), mixl.branch_logl(ops_r, a_r, b_r, row)
+    assert l1 == l2
+    np.testing.assert_array_equal(plain.get_pattern_lh(), mixl.get_pattern_lh())
+    df, ddf = plain.branch_derv(ops[:0], a, b, L)
+    grad, hess, ll = mixl.branch_derv_mixlen(ops_r[:0], a_r, b_r, row)
+    assert abs(ll - l1) < 1e-9 * abs(l1)
+    assert abs(grad.sum() - df) < 1e-9 * max(1.0, abs(df)) + 1e-12 * abs(l1)
+    assert abs(hess.sum() - ddf) < 1e-8 * max(1.0, abs(ddf))
+    plain.close(); mixl.close()
