@@ -213,10 +213,26 @@ __global__ void __launch_bounds__(NW * 32, 1) k_site_walk20(Dev D, SiteModel M, 
 #pragma unroll
             for (int mt = 0; mt < 3; mt++) offS[pw][mt] = 8 * mt + g < 20 ? (int)(at(0, 8 * mt + g) - b0) : 0;
         }
+        // per pattern of this warp: may it rescale at all (ptn_invar == 0), and the tip states of the lane's child — loaded one op ahead
+        bool may_scale[PPW];
+#pragma unroll
+        for (int pw = 0; pw < PPW; pw++) may_scale[pw] = D.invar[p0 + warp * PPW + pw] == 0.0;
+        const int ch = g & 1, cc = g >> 1;   // the lane's column of E: child = g & 1 (0 = left), category cb + (g >> 1)
+        auto tip_states = [&](const DevOp &op, int (&st)[PPW]) {
+            const bool tip = op.ncase == 0 || (op.ncase == 1 && ch == 0);
+            const int cid = ch ? op.rid : op.lid;
+#pragma unroll
+            for (int pw = 0; pw < PPW; pw++) st[pw] = tip ? (int)D.tips[(long long)cid * D.Ppad + p0 + warp * PPW + pw] : 0;
+        };
+        DevOp op_next = ops[0];
+        int st_next[PPW];
+        tip_states(op_next, st_next);
         for (int o = 0; o < nops; o++) {
-            const DevOp op = ops[o];
-            // the lane's column of E: child = g & 1 (0 = left), category cb + (g >> 1)
-            const int ch = g & 1, cc = g >> 1;
+            const DevOp op = op_next;
+            int st_now[PPW];
+#pragma unroll
+            for (int pw = 0; pw < PPW; pw++) st_now[pw] = st_next[pw];
+            if (o + 1 < nops) { op_next = ops[o + 1]; tip_states(op_next, st_next); }
             const bool tip = op.ncase == 0 || (op.ncase == 1 && ch == 0);
             const int cid = ch ? op.rid : op.lid;
             const double len = resolve_len(D, __longlong_as_double(ch ? op.eR : op.eL));
@@ -233,11 +249,11 @@ __global__ void __launch_bounds__(NW * 32, 1) k_site_walk20(Dev D, SiteModel M, 
                 const long long sb = SAFE ? pbase(p, C) : p;
                 double tv[5];
                 if (tip) {
-                    const int state = D.tips[(long long)cid * D.Ppad + p];
+                    const int state = st_now[pw];
 #pragma unroll
                     for (int ks = 0; ks < 5; ks++) tv[ks] = site_tip20(sm, D.su, seq_type, state, 4 * ks + q);
                 }
-                const bool check = (op.ncase != 0) && (D.invar[p] == 0.0);
+                const bool check = (op.ncase != 0) && may_scale[pw];
                 const uint16_t *lsc = op.ncase == 2 ? D.scale + (long long)op.lid * D.scale_stride + sb : nullptr;
                 const uint16_t *rsc = op.ncase >= 1 ? D.scale + (long long)op.rid * D.scale_stride + sb : nullptr;
                 uint16_t *osc = D.scale + (long long)op.dst * D.scale_stride + sb;
