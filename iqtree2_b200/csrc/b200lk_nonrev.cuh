@@ -181,6 +181,144 @@ __global__ void __launch_bounds__(kTile) k_nonrev_partials(Dev D, const DevOp *o
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_nonrev_walk4<C, SAFE>: the 4-state non-reversible partial-likelihood kernel with the walker's structure (cf. k_walk_n4c4): a thread
+// keeps its pattern through the whole post-order op list and the CLV it has just produced stays in registers for its parent (the
+// planner's order makes an internal child the previous op's result nearly always), so an op reads at most ONE child CLV from memory
+// and tip-inner nodes none; the op's two 4 x 4 x C transition matrices (built, transposed where the branch points root-ward, by
+// k_nonrev_info) are staged in shared memory one op ahead, one double per thread; tip states are loaded one op ahead.
+// Arithmetic and summation order are process_op_nonrev's (dot4acc: two pair sums), the 2^-256 test is the signed maximum.
+// ------------------------------------------------------------------------------------------------------------
+template <int C, bool SAFE>
+__global__ void __launch_bounds__(kTile, 4) k_nonrev_walk4(Dev D, const DevOp *ops, int nops, unsigned long long *counter) {
+    constexpr int W = 16 * C, NS = SAFE ? C : 1;
+    __shared__ double s_P[2][2][W];   // [buffer][left / right][c][x][y]
+    __shared__ long long s_item;
+    const int tid = threadIdx.x;
+    const long long ntiles = D.Ppad / kTile;
+    auto stage_mats = [&](const DevOp &op, int buf) {   // internal children only: a leaf child has its table instead
+        for (int t = tid; t < 2 * W; t += kTile) {
+            const int ch = t / W, k = t - ch * W;
+            const bool internal = ch == 0 ? op.ncase == 2 : op.ncase >= 1;
+            if (internal) s_P[buf][ch][k] = D.opinfo[(ch ? op.eR : op.eL) + k];
+        }
+    };
+    for (;;) {   // (the host zeroes the counter before the launch)
+        __syncthreads();
+        if (tid == 0) s_item = (long long)atomicAdd(counter, 1ULL);
+        __syncthreads();
+        const long long tile = s_item;
+        if (tile >= ntiles) break;
+        const long long p = tile * kTile + tid;
+        const long long pb = pbase(p, 4 * C);
+        const long long sb = SAFE ? pbase(p, C) : p;
+        const bool may_scale = D.invar[p] == 0.0;
+        double cur[4 * C];
+        unsigned cursc[NS];
+#pragma unroll
+        for (int k = 0; k < 4 * C; k++) cur[k] = 0.0;
+#pragma unroll
+        for (int c = 0; c < NS; c++) cursc[c] = 0;
+        int cur_slot = -1;   // the slot whose CLV is in `cur`
+        DevOp op_next = ops[0];
+        stage_mats(op_next, 0);
+        auto tip_state = [&](const DevOp &op, int which) -> int {   // state of a leaf child (0 for the root leaf / an internal child)
+            const int id = which ? op.rid : op.lid;
+            const bool leaf = which ? op.ncase == 0 : op.ncase != 2;
+            return leaf && id >= 0 ? (int)D.tips[(long long)id * D.Ppad + p] : 0;
+        };
+        int sL_next = tip_state(op_next, 0), sR_next = tip_state(op_next, 1);
+        for (int o = 0; o < nops; o++) {
+            __syncthreads();   // the matrices of op o are staged; everyone has left op o - 1 (its buffer is rewritten below)
+            const DevOp op = op_next;
+            const int sL = sL_next, sR = sR_next;
+            if (o + 1 < nops) {
+                op_next = ops[o + 1];
+                stage_mats(op_next, (o + 1) & 1);
+                sL_next = tip_state(op_next, 0); sR_next = tip_state(op_next, 1);
+            }
+            const bool l_int = op.ncase == 2, r_int = op.ncase >= 1;
+            const bool l_reg = l_int && op.lid == cur_slot;          // left child chained
+            const bool r_reg = r_int && !l_reg;                       // otherwise the right child lives in `cur` (chained, or loaded now)
+            double X[4 * C];
+            unsigned scX[NS];
+#pragma unroll
+            for (int c = 0; c < NS; c++) scX[c] = 0;
+            if (r_reg && op.rid != cur_slot) {
+                const double *Rp = D.partial + (long long)op.rid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 4 * C; k++) cur[k] = Rp[k * kWarp];
+#pragma unroll
+                for (int c = 0; c < NS; c++) cursc[c] = D.scale[(long long)op.rid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+            }
+            if (!r_int) {
+#pragma unroll
+                for (int c = 0; c < NS; c++) cursc[c] = 0;
+            }
+            if (l_int) {   // both internal: the one that is not in registers comes from memory
+                const int xid = l_reg ? op.rid : op.lid;
+                const double *Xp = D.partial + (long long)xid * D.slot_stride + pb;
+#pragma unroll
+                for (int k = 0; k < 4 * C; k++) X[k] = Xp[k * kWarp];
+#pragma unroll
+                for (int c = 0; c < NS; c++) scX[c] = D.scale[(long long)xid * D.scale_stride + sb + (SAFE ? c * kWarp : 0)];
+            }
+            const double *leafL = l_int ? nullptr : D.opinfo + op.leafL + (op.lid < 0 ? 0 : (long long)sL * (4 * C));
+            const double *leafR = r_int ? nullptr : D.opinfo + op.leafR + (op.rid < 0 ? 0 : (long long)sR * (4 * C));
+            const double *PL = s_P[o & 1][0], *PR = s_P[o & 1][1];
+            const bool check = (op.ncase == 1 || op.ncase == 2) && may_scale;
+            double *Op = D.partial + (long long)op.dst * D.slot_stride + pb;
+            double lh_max = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                double lv[4], rv[4];
+#pragma unroll
+                for (int y = 0; y < 4; y++) {
+                    lv[y] = l_reg ? cur[c * 4 + y] : X[c * 4 + y];      // (read only when l_int)
+                    rv[y] = r_reg ? cur[c * 4 + y] : X[c * 4 + y];      // (read only when r_int)
+                }
+                double v[4], cmax = 0.0;
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    double a, b;
+                    if (l_int) {
+                        const double *m = PL + (c * 4 + x) * 4;
+                        a = (m[0] * lv[0] + m[1] * lv[1]) + (m[2] * lv[2] + m[3] * lv[3]);
+                    } else a = leafL[c * 4 + x];
+                    if (r_int) {
+                        const double *m = PR + (c * 4 + x) * 4;
+                        b = (m[0] * rv[0] + m[1] * rv[1]) + (m[2] * rv[2] + m[3] * rv[3]);
+                    } else b = leafR[c * 4 + x];
+                    v[x] = a * b;
+                    cmax = fmax(cmax, v[x]);   // signed maximum, from 0 (:446-447, 520)
+                }
+                if (SAFE) {
+                    unsigned sc = cursc[SAFE ? c : 0] + scX[SAFE ? c : 0];
+                    if (check && cmax < kScalingThreshold) {
+#pragma unroll
+                        for (int x = 0; x < 4; x++) v[x] *= kTwo256;
+                        sc += 1;
+                    }
+                    cursc[SAFE ? c : 0] = sc;
+                } else lh_max = fmax(lh_max, cmax);
+#pragma unroll
+                for (int x = 0; x < 4; x++) { cur[c * 4 + x] = v[x]; Op[(c * 4 + x) * kWarp] = v[x]; }
+            }
+            if (!SAFE) {
+                cursc[0] += scX[0];
+                if (check && lh_max < kScalingThreshold) {   // rare: rescale and store again
+#pragma unroll
+                    for (int k = 0; k < 4 * C; k++) { cur[k] *= kTwo256; Op[k * kWarp] = cur[k]; }
+                    cursc[0] += 1;
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NS; c++) D.scale[(long long)op.dst * D.scale_stride + sb + (SAFE ? c * kWarp : 0)] = (uint16_t)cursc[c];
+            cur_slot = op.dst;
+        }
+    }
+}
+
 // The evaluation branch's matrices, weighted as phylokernelnonrev.h:628-659 / 1103-1124: tm (and d1 = Q.P, d2 = Q.Q.P) [c][i][x],
 // times prop (prop*rate, prop*rate^2), rows times the state frequencies on an unrooted tree; and, for a leaf at the far end, the
 // tables T[state][c][i] = sum_x tm[c][i][x] tip[state][x] (:1160-1176, 693-724) — for the root leaf one row freq*prop (:1150-1158).

@@ -126,3 +126,30 @@ def test_nonrev_against_the_live_reference():
             if leaf != pat.shape[0]:
                 np.testing.assert_allclose(g.branch_derv(ops[:0], a, b, L), r.branch_derv(leaf), rtol=1e-9)
         g.close(); r.close()
+
+
+@pytest.mark.parametrize("safe", [False, True])
+@pytest.mark.parametrize("ncat", [4, 1, 3])
+def test_nonrev_4_state_walker_and_thread_per_op_kernel_agree(ncat, safe):
+    """k_nonrev_walk4 (register-chained walker; 4 states x 1 or 4 categories) and k_nonrev_partials (kernel variant 5, also what
+    3 categories run on) against the restatement: CLVs, scale counts, logL — on a deep tree that rescales and on a bushy one"""
+    for tree_kind, ntaxa, mean_len in (("yule", 40, 0.1), ("caterpillar", 150, 0.8)):
+        tree, model, pat, freq, invar = make_nonrev_case(4, ncat, 1, ntaxa=ntaxa, nptn=200, seed=43, tree_kind=tree_kind, mean_len=mean_len,
+                                                         p_unknown=0.0 if tree_kind == "caterpillar" else 0.05)
+        o = nonrev_engine(OracleEngine, tree, model, pat, freq, invar, safe)
+        br = plan.pendant_branch_of(tree, 0)
+        ops, a, b, L = plan.plan_branch_nonrev(tree, br)
+        ll_o = o.branch_logl(ops, a, b, L)
+        for variant in (0, 5):
+            g = nonrev_engine(LikelihoodEngine, tree, model, pat, freq, invar, safe)
+            if variant:
+                g.set_schedule(10 + variant)
+            ll_g = g.branch_logl(ops, a, b, L)
+            assert abs(ll_g - ll_o) < 1e-9 * abs(ll_o), (tree_kind, variant, ll_g, ll_o)
+            for op in ops:
+                s = int(op["dst_slot"])
+                assert np.array_equal(g.get_scale_num(s), o.get_scale_num(s)), (tree_kind, variant, s)
+                assert_partials_close(g.get_partial(s), o.get_partial(s), 1e-11)
+            # a partial traversal on resident CLVs: only the last op again (its children come from memory, nothing is chained)
+            assert g.branch_logl(ops[-1:], a, b, L) == ll_g
+            g.close()
