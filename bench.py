@@ -627,7 +627,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
                        f"k_site_partials<{model.nstates}> (thread per pattern, per-pattern eigensystems streamed from HBM / L2)")
     elif nonrev:
         kernel_name = (f"k_nonrev_walk4<{model.ncat_mix}> (pattern-tile walker with register chaining, state-space CLVs, device-built transition matrices)"
-                       if model.nstates == 4 and model.ncat_mix in (1, 4) and args.variant != 5 else
+                       if model.nstates == 4 and 1 <= model.ncat_mix <= 4 and args.variant != 5 else
                        f"k_nonrev_partials<{model.nstates}> (thread per pattern, state-space CLVs, device-built transition matrices)")
     elif walk20:
         kernel_name = "k_walk_n20v2 (pattern-tile walker, FP64 MMA m8n8k4 on state-space CLVs, cp.async rings)"
@@ -638,7 +638,7 @@ def run_tree_workload(args, rank, world, local_rank, workload, ntaxa, nptn, mode
         kernel_name = f"k_walk_gen<{(model.nstates + 7) // 8}> (pattern-tile walker, FP64 MMA m8n8k4, {model.nstates} states padded to {(model.nstates + 7) // 8 * 8})"
     else:
         kernel_name = "k_partials_generic"
-    nonrev_walk = nonrev and model.nstates == 4 and model.ncat_mix in (1, 4) and args.variant != 5
+    nonrev_walk = nonrev and model.nstates == 4 and 1 <= model.ncat_mix <= 4 and args.variant != 5
     model_bytes = dram_model_bytes(ops_acc, my_nptn, B, S, chained=walk4 or nonrev_walk)
     if site and not (model.nstates == 20 and args.variant != 5):
         # thread-per-pattern kernel: every op reads the pattern's (n + 2 n^2) doubles once (re-reads across categories are L1 / L2 hits at best)
