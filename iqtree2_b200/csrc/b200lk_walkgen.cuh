@@ -402,7 +402,18 @@ __global__ void __launch_bounds__(128) k_clv_gen_to_eigen(Dev D, int src, int ds
         const double *iv = D.inv_evec + (size_t)(c / D.denom) * n * n;
         double t[64];
         for (int x = 0; x < n; x++) t[x] = S[at(c, x)];
-        for (int i = 0; i < n; i++) {
+        int i = 0;
+        for (; i + 3 < n; i += 4) {   // four rows at a time: one pass over t, four independent chains (each row's sum keeps its order)
+            double w0 = 0.0, w1 = 0.0, w2 = 0.0, w3 = 0.0;
+            const double *r0 = iv + (size_t)i * n, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;
+            for (int x = 0; x < n; x++) {
+                const double tx = t[x];
+                w0 = fma(__ldg(r0 + x), tx, w0); w1 = fma(__ldg(r1 + x), tx, w1);
+                w2 = fma(__ldg(r2 + x), tx, w2); w3 = fma(__ldg(r3 + x), tx, w3);
+            }
+            O[at(c, i)] = w0; O[at(c, i + 1)] = w1; O[at(c, i + 2)] = w2; O[at(c, i + 3)] = w3;
+        }
+        for (; i < n; i++) {
             double w = 0.0;
             for (int x = 0; x < n; x++) w = fma(__ldg(iv + (size_t)i * n + x), t[x], w);
             O[at(c, i)] = w;
