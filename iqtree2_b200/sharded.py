@@ -50,7 +50,9 @@ class ShardedLikelihood:
         self.device = device if device is not None else torch.device("cpu")
         self.engine = None
         if self.local_nptn > 0:
-            self.engine = engine_cls(model, ntaxa, self.local_nptn, **engine_kw)
+            from . import models as _models
+            # a site-specific model (ModelSet / PMSF) carries one eigensystem per pattern: the rank takes its slice of them
+            self.engine = engine_cls(_models.site_slice(model, self.lo, self.hi), ntaxa, self.local_nptn, **engine_kw)
             self.engine.set_tip_states(np.ascontiguousarray(tips[:, self.lo:self.hi]))
             self.engine.set_pattern_freq(np.ascontiguousarray(ptn_freq[self.lo:self.hi]))
             inv = np.zeros(self.local_nptn) if ptn_invar is None else np.ascontiguousarray(ptn_invar[self.lo:self.hi])
@@ -90,7 +92,32 @@ class ShardedLikelihood:
 
     def set_model(self, model):
         if self.engine:
-            self.engine.set_model(model)
+            from . import models as _models
+            self.engine.set_model(_models.site_slice(model, self.lo, self.hi))
+
+    # ---- mixed branch lengths (heterotachy): the table is replicated, the gradient / Hessian are sums over the ranks ----------
+    def set_mixlen(self, table):
+        self._nmixlen = 0 if table is None else int(np.asarray(table).shape[1])
+        if self.engine:
+            self.engine.set_mixlen(table)
+
+    def branch_derv_mixlen(self, ops, end_a, end_b, row):
+        """computeLikelihoodDerv of a mixlen tree over all shards -> (gradient [K], hessian [K][K], logL)"""
+        K = self._nmixlen
+        if self.engine:
+            g, H, ll = self.engine.branch_derv_mixlen(ops, end_a, end_b, row)
+            v = np.concatenate([g, H.ravel(), [ll]])
+        else:
+            v = np.zeros(K + K * K + 1)
+        if self.world > 1:
+            t = self.torch.from_numpy(v).to(self.device)
+            self.dist.all_reduce(t, group=self.group)
+            v = t.cpu().numpy()
+        return v[:K].copy(), v[K:K + K * K].reshape(K, K).copy(), float(v[-1])
+
+    def branch_derv_mixlen_cur(self, ops, end_a, end_b, row, cur):
+        v = self.engine.branch_derv_mixlen_cur(ops, end_a, end_b, row, cur) if self.engine else (0.0, 0.0)
+        return tuple(self._allreduce(v))
 
     def theta_reset(self):
         if self.engine:
