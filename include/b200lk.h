@@ -91,7 +91,9 @@ void b200lk_destroy(b200lk_engine *e);
 const char *b200lk_last_error(const b200lk_engine *e); /* e may be NULL: error of the last failed create */
 /* bytes of device memory the engine holds (PhyloTree::getMemoryRequired, tree/phylotree.cpp:967) */
 int64_t b200lk_device_bytes(const b200lk_engine *e);
-/* run on a caller-owned stream (cudaStream_t as void*); NULL restores the engine's own stream */
+/* run on a caller-owned stream (cudaStream_t as void*); NULL restores the engine's own (non-blocking) stream.  NOTE: the legacy
+ * default stream's handle IS NULL — a caller that wants the engine ordered with its other work (a collective, a copy) must pass a
+ * stream it created; work on the engine's own stream is ordered with nothing but itself */
 int b200lk_set_stream(b200lk_engine *e, void *cuda_stream);
 /* Reference defects that change results; OFF by default (the engine computes the intended mathematics), ON to
  * reproduce the reference bit for bit in parity tests.
@@ -99,7 +101,8 @@ int b200lk_set_stream(b200lk_engine *e, void *cuda_stream);
  *   nstates is odd and nstates*ncat_mix is even (tree/phylokernelnew.h:700-714; e.g. codon 61 x G4, 5 states x 6). */
 #define B200LK_QUIRK_DOTTRIPLE_ODD 1
 int b200lk_set_reference_quirks(b200lk_engine *e, int32_t mask);
-/* schedule for multi-op traversals: 0 = auto, 1 = one levelled launch per tree depth, 2 = pattern-tile walker */
+/* schedule for multi-op traversals: 0 = auto, 1 = one levelled launch per tree depth, 2 = pattern-tile walker;
+ * 10 + v (v < 30): development switch between kernel variants of the walker schedule (A/B measurements) */
 int b200lk_set_schedule(b200lk_engine *e, int schedule);
 
 /* ---- inputs ------------------------------------------------------------------------------------------------- */
