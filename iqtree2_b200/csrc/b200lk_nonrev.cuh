@@ -196,11 +196,19 @@ __global__ void __launch_bounds__(kTile, 4) k_nonrev_walk4(Dev D, const DevOp *o
     __shared__ long long s_item;
     const int tid = threadIdx.x;
     const long long ntiles = D.Ppad / kTile;
-    auto stage_mats = [&](const DevOp &op, int buf) {   // internal children only: a leaf child has its table instead
+    // an internal child's matrices [c][x][y]; for a leaf child the rows of its table for the first four state codes (the
+    // nucleotides; row 0 of the root leaf's one-row table), transposed to [c][x][state] so that lanes with different states hit
+    // different banks — the other codes (ambiguity, gap) are gathered from the table in global memory
+    auto stage_mats = [&](const DevOp &op, int buf) {
         for (int t = tid; t < 2 * W; t += kTile) {
             const int ch = t / W, k = t - ch * W;
             const bool internal = ch == 0 ? op.ncase == 2 : op.ncase >= 1;
             if (internal) s_P[buf][ch][k] = D.opinfo[(ch ? op.eR : op.eL) + k];
+            else {
+                const int s = k / (4 * C), j = k - s * (4 * C);   // k = state * 4C + (c * 4 + x)
+                const bool root = (ch ? op.rid : op.lid) < 0;      // one row only
+                s_P[buf][ch][j * 4 + s] = (!root || s == 0) ? D.opinfo[(ch ? op.leafR : op.leafL) + k] : 0.0;
+            }
         }
     };
     for (;;) {   // (the host zeroes the counter before the launch)
@@ -284,11 +292,11 @@ __global__ void __launch_bounds__(kTile, 4) k_nonrev_walk4(Dev D, const DevOp *o
                     if (l_int) {
                         const double *m = PL + (c * 4 + x) * 4;
                         a = (m[0] * lv[0] + m[1] * lv[1]) + (m[2] * lv[2] + m[3] * lv[3]);
-                    } else a = leafL[c * 4 + x];
+                    } else a = sL < 4 ? PL[(c * 4 + x) * 4 + sL] : leafL[c * 4 + x];
                     if (r_int) {
                         const double *m = PR + (c * 4 + x) * 4;
                         b = (m[0] * rv[0] + m[1] * rv[1]) + (m[2] * rv[2] + m[3] * rv[3]);
-                    } else b = leafR[c * 4 + x];
+                    } else b = sR < 4 ? PR[(c * 4 + x) * 4 + sR] : leafR[c * 4 + x];
                     v[x] = a * b;
                     cmax = fmax(cmax, v[x]);   // signed maximum, from 0 (:446-447, 520)
                 }
